@@ -1,0 +1,271 @@
+"""blacklight_b200 -- Python face of the B200-native ray-tracing hot path.
+
+Thin ctypes layer over the C ABI in include/blacklight_b200.h / blacklight_b200_host.h.  The product
+is the shared library built from blacklight_b200/csrc (CUDA sm_100a kernels + C++ host layer); this
+module exists so tests and bench.py can drive it with numpy/torch host buffers.  There is no Python or
+CPU implementation of the path: importing works anywhere, but any compute call raises unless the
+library is built and a CUDA device is present.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libblacklight_b200.so')
+EXE_PATH = os.path.join(_HERE, 'bin', 'blacklight_b200')
+
+
+class BlacklightError(RuntimeError):
+    pass
+
+
+class GridView(ctypes.Structure):
+    """bl_grid_view"""
+    _fields_ = [('n_b', ctypes.c_int32), ('n_k', ctypes.c_int32), ('n_j', ctypes.c_int32), ('n_i', ctypes.c_int32),
+                ('n_var', ctypes.c_int32), ('levels', ctypes.c_void_p), ('locations', ctypes.c_void_p),
+                ('x1f', ctypes.c_void_p), ('x2f', ctypes.c_void_p), ('x3f', ctypes.c_void_p),
+                ('x1v', ctypes.c_void_p), ('x2v', ctypes.c_void_p), ('x3v', ctypes.c_void_p),
+                ('prim', ctypes.c_void_p)] + [(n, ctypes.c_int32) for n in (
+                    'ind_rho', 'ind_pgas', 'ind_kappa', 'ind_uu1', 'ind_uu2', 'ind_uu3', 'ind_bb1', 'ind_bb2', 'ind_bb3',
+                    'n_3_root')]
+
+
+class LevelStats(ctypes.Structure):
+    """bl_level_stats"""
+    _fields_ = [('num_rays', ctypes.c_int64), ('geodesic_num_steps', ctypes.c_int32),
+                ('num_bad_geodesics', ctypes.c_int64), ('num_samples', ctypes.c_int64),
+                ('num_attempts', ctypes.c_int64), ('num_accepted', ctypes.c_int64),
+                ('ms_geodesic', ctypes.c_double), ('ms_radiation', ctypes.c_double), ('ms_refine', ctypes.c_double)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+_lib = None
+
+
+def load_library():
+    """Load libblacklight_b200.so; raises BlacklightError (never falls back) if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise BlacklightError('%s is missing: run `python -c "import __graft_entry__ as g; g.build()"` '
+                              '(or make -C blacklight_b200/csrc); there is no CPU fallback' % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_double
+    sig = {
+        'bl_create': (i32, [vp, ctypes.POINTER(vp)]), 'bl_destroy': (None, [vp]),
+        'bl_last_error': (ctypes.c_char_p, [vp]), 'bl_image_num_quantities': (i32, [vp]),
+        'bl_upload_grid': (i32, [vp, ctypes.POINTER(GridView)]),
+        'bl_trace_level': (i32, [vp, i32, vp, vp, vp, i64, ctypes.POINTER(LevelStats)]),
+        'bl_radiate_level': (i32, [vp, i32, i32, vp, vp, ctypes.POINTER(LevelStats)]),
+        'bl_refine_level': (i32, [vp, i32, vp, i64, vp, ctypes.POINTER(i64)]),
+        'bl_set_taps': (i32, [vp, i32]),
+        'bl_download_samples': (i32, [vp, i32, vp, vp, vp, vp, vp]),
+        'bl_download_sample_inds': (i32, [vp, i32, vp, vp, vp, vp, vp]),
+        'bl_device_info': (i32, [vp, ctypes.c_char_p, i32, ctypes.POINTER(i32), ctypes.POINTER(dbl)]),
+        'bl_measure_fp64_peak': (i32, [vp, ctypes.POINTER(dbl)]),
+        'blh_last_error': (ctypes.c_char_p, []), 'blh_config_from_input': (i32, [ctypes.c_char_p, ctypes.POINTER(vp)]),
+        'blh_config_free': (None, [vp]), 'blh_config_params': (vp, [vp]), 'blh_config_num_runs': (i32, [vp]),
+        'blh_config_set_device': (None, [vp, i32, i64]), 'blh_camera_frame': (i32, [vp, vp]),
+        'blh_camera_root': (i64, [vp, vp, vp, vp]),
+        'blh_camera_refined': (i64, [vp, i32, vp, vp, i64, vp, vp, vp, vp]),
+        'blh_run_input_file': (i32, [ctypes.c_char_p, i32, i32, vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def parse_input_text(text):
+    """key -> value of a parameter file (same rules as the reference: whitespace removed, # comments)."""
+    out = {}
+    for line in text.splitlines():
+        line = ''.join(line.split()).split('#')[0]
+        if line:
+            k, v = line.split('=', 1)
+            out[k] = v
+    return out
+
+
+class Config:
+    """Parsed parameter file + camera frame (host side; blh_config)."""
+
+    def __init__(self, input_path, device=0, tile_rays=0):
+        lib = load_library()
+        self._h = ctypes.c_void_p()
+        if lib.blh_config_from_input(os.fsencode(input_path), ctypes.byref(self._h)) != 0:
+            raise BlacklightError(lib.blh_last_error().decode())
+        lib.blh_config_set_device(self._h, device, tile_rays)
+        with open(input_path) as f:
+            self.keys = parse_input_text(f.read())
+
+    def __del__(self):
+        if getattr(self, '_h', None) and _lib is not None:
+            _lib.blh_config_free(self._h)
+            self._h = None
+
+    @property
+    def params_ptr(self):
+        return _lib.blh_config_params(self._h)
+
+    @property
+    def resolution(self):
+        return int(self.keys['camera_resolution'])
+
+    @property
+    def block_size(self):
+        return int(self.keys.get('adaptive_block_size', 0))
+
+    def camera_frame(self):
+        out = np.empty((7, 4))
+        _lib.blh_camera_frame(self._h, _ptr(out))
+        return dict(zip(('cam_x', 'u_con', 'u_cov', 'norm_con', 'norm_con_c', 'hor_con_c', 'vert_con_c'), out))
+
+    def camera_root(self, pinned=False):
+        n = self.resolution ** 2
+        pos, dirs, fac = _host_array((n, 4), pinned), _host_array((n, 4), pinned), _host_array((n,), pinned)
+        if _lib.blh_camera_root(self._h, _ptr(pos), _ptr(dirs), _ptr(fac)) != n:
+            raise BlacklightError(_lib.blh_last_error().decode())
+        return pos, dirs, fac
+
+    def camera_refined(self, level, parent_locs, flags):
+        parent_locs = np.ascontiguousarray(parent_locs, np.int32)
+        flags = np.ascontiguousarray(flags, np.uint8)
+        nb = 4 * int(np.count_nonzero(flags))
+        npix = nb * self.block_size ** 2
+        locs, pos, dirs, fac = np.empty((nb, 2), np.int32), np.empty((npix, 4)), np.empty((npix, 4)), np.empty(npix)
+        got = _lib.blh_camera_refined(self._h, level, _ptr(parent_locs), _ptr(flags), len(flags), _ptr(locs),
+                                      _ptr(pos), _ptr(dirs), _ptr(fac))
+        if got != nb:
+            raise BlacklightError(_lib.blh_last_error().decode())
+        return locs, pos, dirs, fac
+
+
+def _host_array(shape, pinned=False, dtype=np.float64):
+    if pinned:
+        import torch
+        t = torch.empty(shape, dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
+        a = t.numpy()
+        a_base = a  # keep tensor alive through the array's base chain
+        a_base.flags.writeable = True
+        _PINNED_KEEPALIVE.append(t)
+        return a
+    return np.empty(shape, dtype)
+
+
+_PINNED_KEEPALIVE = []
+
+
+class Context:
+    """One GPU context (bl_ctx): grid residency, geodesic step buffers, radiation kernels."""
+
+    def __init__(self, config):
+        lib = load_library()
+        self.config = config
+        self._h = ctypes.c_void_p()
+        if lib.bl_create(config.params_ptr, ctypes.byref(self._h)) != 0:
+            raise BlacklightError(lib.bl_last_error(None).decode())
+        self.num_quantities = lib.bl_image_num_quantities(self._h)
+        self._rays = {}
+        self._steps = {}
+
+    def close(self):
+        if getattr(self, '_h', None) and _lib is not None:
+            _lib.bl_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc != 0:
+            raise BlacklightError(_lib.bl_last_error(self._h).decode())
+
+    def device_info(self):
+        name = ctypes.create_string_buffer(256)
+        sm, free = ctypes.c_int(), ctypes.c_double()
+        self._check(_lib.bl_device_info(self._h, name, 256, ctypes.byref(sm), ctypes.byref(free)))
+        return {'name': name.value.decode(), 'sm_count': sm.value, 'hbm_free_gb': free.value}
+
+    def measure_fp64_peak(self):
+        out = ctypes.c_double()
+        self._check(_lib.bl_measure_fp64_peak(self._h, ctypes.byref(out)))
+        return out.value
+
+    def upload_grid(self, g):
+        """g: dict from oracle.mock_snapshot.grid_view_arrays (or any reader) -- host numpy arrays."""
+        keep = {k: np.ascontiguousarray(g[k]) for k in ('levels', 'locations', 'x1f', 'x2f', 'x3f', 'x1v', 'x2v', 'x3v', 'prim')}
+        assert keep['prim'].dtype == np.float32 and keep['x1f'].dtype == np.float64
+        v = GridView()
+        for k in ('n_b', 'n_k', 'n_j', 'n_i', 'n_var', 'ind_rho', 'ind_pgas', 'ind_kappa', 'ind_uu1', 'ind_uu2', 'ind_uu3',
+                  'ind_bb1', 'ind_bb2', 'ind_bb3', 'n_3_root'):
+            setattr(v, k, int(g[k]))
+        for k, a in keep.items():
+            setattr(v, k, a.ctypes.data)
+        self._check(_lib.bl_upload_grid(self._h, ctypes.byref(v)))
+
+    def trace_level(self, level, pos, dirs, fac):
+        pos, dirs, fac = (np.ascontiguousarray(a, np.float64) for a in (pos, dirs, fac))
+        st = LevelStats()
+        self._check(_lib.bl_trace_level(self._h, level, _ptr(pos), _ptr(dirs), _ptr(fac), len(fac), ctypes.byref(st)))
+        self._rays[level] = len(fac)
+        self._steps[level] = st.geodesic_num_steps
+        return st.as_dict()
+
+    def radiate_level(self, level, snapshot=0, image=None, render=None, num_render=0):
+        n = self._rays[level]
+        if image is None:
+            image = np.empty((self.num_quantities, n))
+        if render is None and num_render > 0:
+            render = np.empty((num_render, 3, n))
+        st = LevelStats()
+        self._check(_lib.bl_radiate_level(self._h, level, snapshot, _ptr(image), _ptr(render), ctypes.byref(st)))
+        self._steps[level] = st.geodesic_num_steps
+        return image, render, st.as_dict()
+
+    def refine_level(self, level, block_locs):
+        block_locs = np.ascontiguousarray(block_locs, np.int32)
+        flags = np.zeros(len(block_locs), np.uint8)
+        cnt = ctypes.c_int64()
+        self._check(_lib.bl_refine_level(self._h, level, _ptr(block_locs), len(block_locs), _ptr(flags), ctypes.byref(cnt)))
+        return flags, cnt.value
+
+    def set_taps(self, enabled=True):
+        self._check(_lib.bl_set_taps(self._h, 1 if enabled else 0))
+
+    def download_samples(self, level, arrays=True):
+        n, s = self._rays[level], max(self._steps[level], 1)
+        flags, num = np.empty(n, np.uint8), np.empty(n, np.int32)
+        pos = np.empty((n, s, 4)) if arrays else None
+        dirs = np.empty((n, s, 4)) if arrays else None
+        length = np.empty((n, s)) if arrays else None
+        self._check(_lib.bl_download_samples(self._h, level, _ptr(flags), _ptr(num), _ptr(pos), _ptr(dirs), _ptr(length)))
+        return dict(flags=flags, num=num, pos=pos, dir=dirs, len=length)
+
+    def download_sample_inds(self, level, interp=True):
+        n, s = self._rays[level], max(self._steps[level], 1)
+        inds = np.empty((n, s, 4), np.int32)
+        fracs = np.empty((n, s, 3)) if interp else None
+        nan_, cut, fb = (np.empty((n, s), np.uint8) for _ in range(3))
+        self._check(_lib.bl_download_sample_inds(self._h, level, _ptr(inds), _ptr(fracs), _ptr(nan_), _ptr(cut), _ptr(fb)))
+        return dict(inds=inds, fracs=fracs, nan=nan_, cut=cut, fallback=fb)
+
+
+def run_input_file(path, device=-1, quiet=True):
+    """Full drop-in run (read input, trace, radiate, write output): blh_run_input_file."""
+    lib = load_library()
+    t = np.zeros(12)
+    if lib.blh_run_input_file(os.fsencode(path), device, 1 if quiet else 0, _ptr(t)) != 0:
+        raise BlacklightError(lib.blh_last_error().decode())
+    names = ('total_s', 'geodesic_s', 'read_s', 'sample_s', 'image_s', 'render_s', 'gpu_geodesic_ms',
+             'gpu_radiation_ms', 'gpu_refine_ms', 'rays', 'samples')
+    return dict(zip(names, t))

@@ -1,0 +1,787 @@
+// C-ABI glue: context, HBM residency, wave scheduling and the parity taps.
+// See include/blacklight_b200.h for the contract of each entry point.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/blacklight_b200.h"
+#include "rad_types.cuh"
+
+extern "C" cudaError_t bl_launch_geodesic_dp(const GeoArgs *args, int flat, int sm_count, cudaStream_t stream);
+extern "C" cudaError_t bl_launch_geodesic_rk(const GeoArgs *args, int flat, int order, int sm_count, cudaStream_t stream);
+extern "C" cudaError_t bl_launch_radiate_unpolarized(const RadArgs *args, int num_freq, int simulation, cudaStream_t stream);
+extern "C" cudaError_t bl_launch_radiate_polarized(const RadArgs *args, int num_freq, cudaStream_t stream);
+extern "C" cudaError_t bl_launch_relayout_grid(const float *prim, int n_var, const int *var_index, size_t cells,
+                                               float4 *out, float *kappa_out, cudaStream_t stream);
+extern "C" cudaError_t bl_launch_unpack_samples(const StepBuffer *sb, const int32_t *num, int64_t rays, int S,
+                                                double *pos, double *dir, double *len, cudaStream_t stream);
+extern "C" cudaError_t bl_launch_refine(const double *image, int64_t stride, int level, const int32_t *block_locs,
+                                        int64_t num_blocks, const bl_params *params_dev, uint8_t *flags,
+                                        cudaStream_t stream);
+extern "C" cudaError_t bl_launch_fp64_peak(double *out, int blocks, int iters, cudaStream_t stream);
+
+namespace {
+
+struct Level {
+  int64_t rays = 0;
+  double *cam_pos = nullptr, *cam_dir = nullptr, *mom = nullptr;  // device (rays,4),(rays,4),(rays)
+  int32_t *num = nullptr;     // device (rays)
+  uint8_t *flags = nullptr;   // device (rays)
+  double *step = nullptr;     // device step buffer of one wave
+  int64_t wave_rays = 0;      // rays per wave
+  bool resident = false;      // whole level traced and kept in `step`
+  bool traced = false;
+  double *image = nullptr;    // device (Q, rays)
+  double *render = nullptr;   // device (R,3,rays)
+  bl_level_stats stats{};
+  // taps (allocated on demand)
+  int32_t *tap_inds = nullptr; double *tap_fracs = nullptr; uint8_t *tap_nan = nullptr, *tap_cut = nullptr, *tap_fb = nullptr;
+  int32_t tap_S = 0;
+};
+
+}  // namespace
+
+struct bl_ctx {
+  bl_params params;
+  RadParams rad;            // host copy
+  RadParams *rad_dev = nullptr;
+  bl_params *params_dev = nullptr;
+  GridDev grid{};
+  std::vector<void *> grid_allocs;
+  bool have_grid = false;
+  int device = 0, sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  GeoCounters *counters = nullptr;          // device
+  unsigned long long *rad_counter = nullptr;  // device
+  std::vector<Level> levels;
+  std::string error;
+  bool taps_enabled = false;
+};
+
+namespace {
+
+std::string g_create_error;
+
+int bl_fail(bl_ctx *ctx, int code, const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->error = buf; else g_create_error = buf;
+  return code;
+}
+
+int bl_fail_cuda(bl_ctx *ctx, cudaError_t err, const char *what, const char *file, int line) {
+  return bl_fail(ctx, BL_ERR_CUDA, "CUDA error %s (%s) at %s:%d: %s", cudaGetErrorName(err), cudaGetErrorString(err),
+                 file, line, what);
+}
+
+template <typename T>
+cudaError_t dev_alloc(T **p, size_t count) {
+  return cudaMalloc((void **)p, count * sizeof(T) > 0 ? count * sizeof(T) : 1);
+}
+
+void free_level(Level &L) {
+  cudaFree(L.cam_pos); cudaFree(L.cam_dir); cudaFree(L.mom); cudaFree(L.num); cudaFree(L.flags);
+  cudaFree(L.step); cudaFree(L.image); cudaFree(L.render);
+  cudaFree(L.tap_inds); cudaFree(L.tap_fracs); cudaFree(L.tap_nan); cudaFree(L.tap_cut); cudaFree(L.tap_fb);
+  L = Level();
+}
+
+// 2F1 via the Pfaff transformation and a 10-term series (reference simulation_coefficients.cpp:740-773)
+double hypergeometric(double alpha, double beta, double gamma, double z) {
+  double a = alpha, b = gamma - beta, c = gamma, x = z / (z - 1.0);
+  double result = 1.0, a_k = 1.0, b_k = 1.0, c_k = 1.0, xk = 1.0, kf = 1.0;
+  for (int k = 1; k <= 10; k++) {
+    a_k *= a + k - 1.0; b_k *= b + k - 1.0; c_k *= c + k - 1.0; xk *= x; kf *= k;
+    result += a_k * b_k * xk / (c_k * kf);
+  }
+  return result * std::pow(1.0 - z, -alpha);
+}
+
+// Slot layout of image[level] (reference radiation_integrator.cpp:436-520)
+void image_layout(const bl_params &p, RadParams &r) {
+  int q = 0;
+  bool pol = p.model_type == BL_MODEL_SIMULATION && p.image_polarization;
+  int F = p.image_num_frequencies;
+  if (p.image_light) q += F * (pol ? 4 : 1);
+  r.off_time = q; if (p.image_time) q += 1;
+  r.off_length = q; if (p.image_length) q += 1;
+  r.off_lambda = q; if (p.image_lambda) q += F;
+  r.off_emission = q; if (p.image_emission) q += F;
+  r.off_tau = q; if (p.image_tau) q += F;
+  r.off_lambda_ave = q; if (p.image_lambda_ave) q += F * BL_NUM_CELL_VALUES;
+  r.off_emission_ave = q; if (p.image_emission_ave) q += F * BL_NUM_CELL_VALUES;
+  r.off_tau_int = q; if (p.image_tau_int) q += F * BL_NUM_CELL_VALUES;
+  r.off_crossings = q; if (p.image_crossings) q += 1;
+  r.num_quantities = q;
+}
+
+// Distribution-function constants (reference simulation_coefficients.cpp:53-193)
+void plasma_constants(const bl_params &p, RadParams &r) {
+  const double pi = phys::pi;
+  bool pol = p.image_light && p.image_polarization;
+  if (p.plasma_power_frac != 0.0) {
+    double pp = p.plasma_p;
+    double var_a = std::pow(3.0, pp / 2.0) * (pp - 1.0);
+    double var_b = 2.0 * (pp + 1.0);
+    double var_c = std::pow(p.plasma_gamma_min, 1.0 - pp) - std::pow(p.plasma_gamma_max, 1.0 - pp);
+    double var_d = std::tgamma((3.0 * pp - 1.0) / 12.0);
+    double var_e = std::tgamma((3.0 * pp + 19.0) / 12.0);
+    double var_f = std::pow(3.0, (pp + 1.0) / 2.0) * (pp - 1.0) / 4.0;
+    double var_g = std::tgamma((3.0 * pp + 2.0) / 12.0);
+    double var_h = std::tgamma((3.0 * pp + 22.0) / 12.0);
+    r.power_jj = var_a / var_b / var_c * var_d * var_e;
+    r.power_aa = var_f / var_c * var_g * var_h;
+    if (pol) {
+      double var_i = 2.0 * (pp + 2.0) / (pp + 1.0);
+      double var_j = std::pow(p.plasma_gamma_min, -(pp + 1.0));
+      double var_k = std::log(p.plasma_gamma_min);
+      r.power_jj_q = -(pp + 1.0) / (pp + 7.0 / 3.0);
+      r.power_jj_v = 0.684 * std::pow(pp, 0.49);
+      r.power_aa_q = -std::pow(0.034 * pp - 0.0344, 0.086);
+      r.power_aa_v = std::pow(0.71 * pp + 0.0352, 0.394);
+      r.power_rho = (pp - 1.0) / var_c;
+      r.power_rho_q = -std::pow(p.plasma_gamma_min, 2.0 - pp) / (pp / 2.0 - 1.0);
+      r.power_rho_v = var_i * var_j * var_k;
+    }
+  }
+  if (p.plasma_kappa_frac != 0.0) {
+    double kk = p.plasma_kappa, w = p.plasma_w;
+    double var_a = 4.0 * pi * std::tgamma(kk - 4.0 / 3.0);
+    double var_b = std::pow(3.0, 7.0 / 3.0) * std::tgamma(kk - 2.0);
+    double var_c = std::pow(3.0, (kk - 1.0) / 2.0);
+    double var_d = (kk - 2.0) * (kk - 1.0) / 4.0;
+    double var_e = std::tgamma(kk / 4.0 - 1.0 / 3.0);
+    double var_f = std::tgamma(kk / 4.0 + 4.0 / 3.0);
+    double var_g = std::pow(3.0, 1.0 / 6.0) * 10.0 / 41.0;
+    double var_h = w * kk;
+    double var_i = 2.0 * pi * std::pow(var_h, kk - 10.0 / 3.0);
+    double var_j = (kk - 2.0) * (kk - 1.0) * kk;
+    double var_k = 3.0 * kk - 1.0;
+    double var_l = std::tgamma(5.0 / 3.0);
+    double var_m = hypergeometric(kk - 1.0 / 3.0, kk + 1.0, kk + 2.0 / 3.0, -var_h);
+    double var_n = std::pow(pi, 1.5) / 3.0;
+    double var_o = var_j / (var_h * var_h * var_h);
+    double var_p = 2.0 * std::tgamma(2.0 + kk / 2.0) / (2.0 + kk) - 1.0;
+    r.kappa_jj_low = var_a / var_b;
+    r.kappa_jj_high = var_c * var_d * var_e * var_f;
+    r.kappa_jj_x_i = 3.0 * std::pow(kk, -1.5);
+    r.kappa_aa_low = var_g * var_i * var_j / var_k * var_l * var_m;
+    r.kappa_aa_high = var_n * var_o * var_p;
+    r.kappa_aa_x_i = std::pow(-1.75 + 1.6 * kk, -0.86);
+    // Stokes-I absorptivity blends with this factor in every mode (simulation_coefficients.cpp:660)
+    r.kappa_aa_high_i = std::pow(3.0 / kk, 4.75) + 0.6;
+    if (pol) {
+      double var_q = 14.3 * std::pow(w, -0.928);
+      double var_r = 169.0 * std::pow(kk, -8.0) + 0.0052 * kk - 0.0526 + 47.0 / (200.0 * kk);
+      r.kappa_jj_low_q = 0.5;
+      r.kappa_jj_low_v = 0.5625 * std::pow(kk, -0.528) / w;
+      r.kappa_jj_high_q = 0.64 + 0.02 * kk;
+      r.kappa_jj_high_v = 0.765625 * std::pow(kk, -0.44) / w;
+      r.kappa_jj_x_q = 3.7 * std::pow(kk, -1.6);
+      r.kappa_jj_x_v = r.kappa_jj_x_i;
+      r.kappa_aa_low_q = 25.0 / 48.0;
+      r.kappa_aa_low_v = 77.0 / (100.0 * w) * std::pow(kk, -0.7);
+      r.kappa_aa_high_q = 441.0 * std::pow(kk, -5.76) + 0.55;
+      r.kappa_aa_high_v = var_q * var_r;
+      r.kappa_aa_x_q = 1.4 * std::pow(kk, -1.15);
+      r.kappa_aa_x_v = 1.22 * std::pow(kk, -1.136) + 0.007;
+      r.kappa_rho_v = std::cyl_bessel_k(0.0, 1.0 / w) / std::cyl_bessel_k(2.0, 1.0 / w);
+      // Faraday-rotation fits are tabulated at kappa = 3.5, 4, 4.5, 5 and blended linearly in between
+      struct Fit { double qa, qb, qc, qd, qe, va, vb; };
+      double sw = std::sqrt(w), e5 = std::exp(-5.0 * w);
+      Fit f35 = {17.0 * w + sw * (-3.0 + 7.0 * e5), -1.0 / 30.0, 0.1, -1.5, 0.471,
+                 (w * w + 2.0 * w + 1.0) / (3.125 * w * w + 4.0 * w + 1.0), 0.447};
+      Fit f40 = {46.0 / 3.0 * w + sw * (-5.0 / 3.0 + 17.0 / 3.0 * e5), -1.0 / 18.0, 1.0 / 6.0, -1.75, 0.5,
+                 (w * w + 54.0 * w + 50.0) / (30.0 / 11.0 * w * w + 134.0 * w + 50.0), 0.391};
+      Fit f45 = {14.0 * w + sw * (-1.625 + 4.5 * e5), -1.0 / 12.0, 0.25, -2.0, 0.525,
+                 (w * w + 43.0 * w + 38.0) / (7.0 / 3.0 * w * w + 92.5 * w + 38.0), 0.348};
+      Fit f50 = {12.5 * w + sw * (-1.0 + 5.0 * e5), -0.125, 0.375, -2.25, 0.541,
+                 (w + 13.0 / 14.0) / (2.0 * w + 13.0 / 14.0), 0.313};
+      Fit lo, hi;
+      if (kk < 4.0) { r.kappa_rho_frac = (kk - 3.5) / (4.0 - 3.5); lo = f35; hi = f40; }
+      else if (kk < 4.5) { r.kappa_rho_frac = (kk - 4.0) / (4.5 - 4.0); lo = f40; hi = f45; }
+      else { r.kappa_rho_frac = (kk - 4.5) / (5.0 - 4.5); lo = f45; hi = f50; }
+      r.kappa_rho_q_low_a = lo.qa; r.kappa_rho_q_low_b = lo.qb; r.kappa_rho_q_low_c = lo.qc;
+      r.kappa_rho_q_low_d = lo.qd; r.kappa_rho_q_low_e = lo.qe;
+      r.kappa_rho_q_high_a = hi.qa; r.kappa_rho_q_high_b = hi.qb; r.kappa_rho_q_high_c = hi.qc;
+      r.kappa_rho_q_high_d = hi.qd; r.kappa_rho_q_high_e = hi.qe;
+      r.kappa_rho_v_low_a = lo.va; r.kappa_rho_v_low_b = lo.vb;
+      r.kappa_rho_v_high_a = hi.va; r.kappa_rho_v_high_b = hi.vb;
+    }
+  }
+}
+
+void fill_rad_params(const bl_params &p, RadParams &r) {
+  std::memset(&r, 0, sizeof r);
+  r.model_type = p.model_type; r.ray_flat = p.ray_flat; r.coord = p.simulation_coord; r.interp = p.simulation_interp;
+  r.a = p.bh_a; r.camera_r = p.camera_r;
+  for (int i = 0; i < 4; i++) {
+    r.camera_x[i] = p.camera_x[i]; r.camera_u_con[i] = p.camera_u_con[i];
+    r.camera_u_cov[i] = p.camera_u_cov[i]; r.camera_vert_con_c[i] = p.camera_vert_con_c[i];
+  }
+  r.num_freq = p.image_num_frequencies;
+  for (int l = 0; l < p.image_num_frequencies; l++) r.freqs[l] = p.image_frequencies[l];
+  r.x_unit = phys::gg_msun * p.mass_msun / (phys::c * phys::c);
+  r.t_unit = r.x_unit / phys::c;
+  r.image_light = p.image_light; r.image_time = p.image_time; r.image_length = p.image_length;
+  r.image_lambda = p.image_lambda; r.image_emission = p.image_emission; r.image_tau = p.image_tau;
+  bool sim = p.model_type == BL_MODEL_SIMULATION;
+  r.image_lambda_ave = sim && p.image_lambda_ave; r.image_emission_ave = sim && p.image_emission_ave;
+  r.image_tau_int = sim && p.image_tau_int; r.image_crossings = p.image_crossings;
+  r.polarization = sim && p.image_light && p.image_polarization;
+  r.rotation_split = p.image_rotation_split;
+  bl_params q = p;
+  q.image_lambda_ave = r.image_lambda_ave; q.image_emission_ave = r.image_emission_ave; q.image_tau_int = r.image_tau_int;
+  image_layout(q, r);
+  r.render_num_images = sim ? p.render_num_images : 0;
+  r.need_cell_values = r.image_lambda_ave || r.image_emission_ave || r.image_tau_int || r.render_num_images > 0;
+  r.d_unit = p.simulation_rho_cgs;
+  r.e_unit = r.d_unit * phys::c * phys::c;
+  r.b_unit = std::sqrt(4.0 * phys::pi * r.e_unit);
+  r.plasma_mu = p.plasma_mu; r.plasma_ne_ni = p.plasma_ne_ni; r.plasma_model = p.plasma_model; r.plasma_use_p = p.plasma_use_p;
+  r.plasma_gamma = p.plasma_gamma; r.plasma_gamma_i = p.plasma_gamma_i; r.plasma_gamma_e = p.plasma_gamma_e;
+  r.plasma_rat_low = p.plasma_rat_low; r.plasma_rat_high = p.plasma_rat_high;
+  r.power_frac = p.plasma_power_frac; r.kappa_frac = p.plasma_kappa_frac;
+  r.thermal_frac = 1.0 - (p.plasma_power_frac + p.plasma_kappa_frac);
+  r.plasma_p = p.plasma_p; r.plasma_gamma_min = p.plasma_gamma_min; r.plasma_gamma_max = p.plasma_gamma_max;
+  r.plasma_kappa = p.plasma_kappa; r.plasma_w = p.plasma_w;
+  if (sim) plasma_constants(p, r);
+  r.formula_r0 = p.formula_r0; r.formula_h = p.formula_h; r.formula_l0 = p.formula_l0; r.formula_q = p.formula_q;
+  r.formula_nup = p.formula_nup; r.formula_cn0 = p.formula_cn0; r.formula_alpha = p.formula_alpha;
+  r.formula_a = p.formula_a; r.formula_beta = p.formula_beta;
+  r.cut_rho_min = p.cut_rho_min; r.cut_rho_max = p.cut_rho_max; r.cut_n_e_min = p.cut_n_e_min; r.cut_n_e_max = p.cut_n_e_max;
+  r.cut_p_gas_min = p.cut_p_gas_min; r.cut_p_gas_max = p.cut_p_gas_max; r.cut_theta_e_min = p.cut_theta_e_min;
+  r.cut_theta_e_max = p.cut_theta_e_max; r.cut_b_min = p.cut_b_min; r.cut_b_max = p.cut_b_max;
+  r.cut_sigma_min = p.cut_sigma_min; r.cut_sigma_max = p.cut_sigma_max;
+  r.cut_beta_inverse_min = p.cut_beta_inverse_min; r.cut_beta_inverse_max = p.cut_beta_inverse_max;
+  r.cut_omit_near = p.cut_omit_near; r.cut_omit_far = p.cut_omit_far; r.cut_plane = p.cut_plane;
+  r.cut_omit_in = p.cut_omit_in; r.cut_omit_out = p.cut_omit_out;
+  r.cut_midplane_theta = p.cut_midplane_theta; r.cut_midplane_z = p.cut_midplane_z;
+  for (int i = 0; i < 3; i++) { r.cut_plane_origin[i] = p.cut_plane_origin[i]; r.cut_plane_normal[i] = p.cut_plane_normal[i]; }
+  r.fallback_nan = p.fallback_nan; r.fallback_rho = p.fallback_rho; r.fallback_pgas = p.fallback_pgas;
+  r.fallback_kappa = p.fallback_kappa;
+  for (int i = 0; i <= BL_MAX_RENDER_FEATURES; i++) r.render_feature_start[i] = p.render_feature_start[i];
+  for (int i = 0; i < BL_MAX_RENDER_FEATURES; i++) {
+    r.render_quantities[i] = p.render_quantities[i]; r.render_types[i] = p.render_types[i];
+    r.render_min_vals[i] = p.render_min_vals[i]; r.render_max_vals[i] = p.render_max_vals[i];
+    r.render_thresh_vals[i] = p.render_thresh_vals[i]; r.render_tau_scales[i] = p.render_tau_scales[i];
+    r.render_opacities[i] = p.render_opacities[i];
+    r.render_x_vals[i] = p.render_x_vals[i]; r.render_y_vals[i] = p.render_y_vals[i]; r.render_z_vals[i] = p.render_z_vals[i];
+  }
+}
+
+int validate_params(const bl_params &p) {
+  if (p.abi_version != BL_ABI_VERSION) return bl_fail(nullptr, BL_ERR_ARG, "bl_params.abi_version %d != %d", p.abi_version, BL_ABI_VERSION);
+  if (p.model_type != BL_MODEL_SIMULATION && p.model_type != BL_MODEL_FORMULA) return bl_fail(nullptr, BL_ERR_ARG, "unknown model_type");
+  // messages below are the reference's own (geodesic_integrator.cpp:39-104, radiation_integrator.cpp:201)
+  if (p.ray_max_steps <= 0) return bl_fail(nullptr, BL_ERR_ARG, "Must have positive ray_max_steps.");
+  if (p.ray_integrator == BL_INTEGRATOR_DP && p.ray_max_retries <= 0) return bl_fail(nullptr, BL_ERR_ARG, "Must have nonnegative ray_max_retries.");
+  if (p.image_num_frequencies < 1) return bl_fail(nullptr, BL_ERR_ARG, "Must have positive image_num_frequencies.");
+  if (p.image_num_frequencies > BL_MAX_FREQ) return bl_fail(nullptr, BL_ERR_UNSUPPORTED, "image_num_frequencies > %d not supported", BL_MAX_FREQ);
+  for (int l = 0; l < p.image_num_frequencies; l++)
+    if (!(p.image_frequencies[l] > 0.0)) return bl_fail(nullptr, BL_ERR_ARG, "Must choose positive image_frequency.");
+  if (p.model_type == BL_MODEL_SIMULATION && p.simulation_coord == BL_COORD_FMKS)
+    return bl_fail(nullptr, BL_ERR_UNSUPPORTED, "simulation_coord = fmks is outside the B200 hot-path scope (SURVEY.md section 2)");
+  if (p.model_type == BL_MODEL_SIMULATION && p.simulation_interp && p.simulation_block_interp)
+    return bl_fail(nullptr, BL_ERR_UNSUPPORTED, "simulation_block_interp = true not implemented yet (SURVEY.md section 8f item 1)");
+  bool sim = p.model_type == BL_MODEL_SIMULATION;
+  if (!(p.image_light || p.image_time || p.image_length || p.image_lambda || p.image_emission || p.image_tau ||
+        (sim && (p.image_lambda_ave || p.image_emission_ave || p.image_tau_int)) || p.image_crossings ||
+        (sim && p.render_num_images > 0)))
+    return bl_fail(nullptr, BL_ERR_ARG, "No image or rendering selected.");
+  if (sim && p.render_num_images > 0 && p.render_feature_start[p.render_num_images] > BL_MAX_RENDER_FEATURES)
+    return bl_fail(nullptr, BL_ERR_UNSUPPORTED, "more than %d render features", BL_MAX_RENDER_FEATURES);
+  if (sim && p.image_light && p.image_polarization && p.plasma_kappa_frac != 0.0 &&
+      (p.plasma_kappa < 3.5 || p.plasma_kappa > 5.0))
+    return bl_fail(nullptr, BL_ERR_ARG, "Polarized transport only supports kappa in [3.5, 5].");
+  if (p.adaptive_max_level > 0) {
+    if (!p.image_light) return bl_fail(nullptr, BL_ERR_ARG, "Adaptive ray tracing requires image_light.");
+    if (p.adaptive_block_size <= 0) return bl_fail(nullptr, BL_ERR_ARG, "Must have positive adaptive_block_size.");
+    if (p.camera_resolution % p.adaptive_block_size != 0) return bl_fail(nullptr, BL_ERR_ARG, "Must have adaptive_block_size divide camera_resolution.");
+    if (p.adaptive_num_regions > BL_MAX_REGIONS) return bl_fail(nullptr, BL_ERR_UNSUPPORTED, "more than %d adaptive regions", BL_MAX_REGIONS);
+  }
+  return BL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *bl_last_error(const bl_ctx *ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+int bl_create(const bl_params *params, bl_ctx **out) {
+  if (!params || !out) return bl_fail(nullptr, BL_ERR_ARG, "bl_create: null argument");
+  *out = nullptr;
+  int rc = validate_params(*params);
+  if (rc) return rc;
+  int count = 0;
+  cudaError_t err = cudaGetDeviceCount(&count);
+  if (err != cudaSuccess || count <= 0)
+    return bl_fail(nullptr, BL_ERR_CUDA, "no usable CUDA device (%s); blacklight_b200 has no CPU fallback",
+                   err != cudaSuccess ? cudaGetErrorString(err) : "device count is 0");
+  if (params->device < 0 || params->device >= count) return bl_fail(nullptr, BL_ERR_ARG, "device %d out of range (%d devices)", params->device, count);
+  bl_ctx *ctx = new (std::nothrow) bl_ctx();
+  if (!ctx) return bl_fail(nullptr, BL_ERR_NOMEM, "out of host memory");
+  ctx->params = *params;
+  ctx->device = params->device;
+  fill_rad_params(*params, ctx->rad);
+  ctx->levels.resize((size_t)params->adaptive_max_level + 1);
+#define CREATE_CHECK(call)                                                                   \
+  do {                                                                                       \
+    cudaError_t e__ = (call);                                                                \
+    if (e__ != cudaSuccess) {                                                                \
+      bl_fail(nullptr, BL_ERR_CUDA, "CUDA error %s at %s:%d: %s", cudaGetErrorString(e__), __FILE__, __LINE__, #call); \
+      bl_destroy(ctx);                                                                       \
+      return BL_ERR_CUDA;                                                                    \
+    }                                                                                        \
+  } while (0)
+  CREATE_CHECK(cudaSetDevice(ctx->device));
+  cudaDeviceProp prop;
+  CREATE_CHECK(cudaGetDeviceProperties(&prop, ctx->device));
+  ctx->sm_count = prop.multiProcessorCount;
+  CREATE_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CREATE_CHECK(cudaEventCreate(&ctx->ev0));
+  CREATE_CHECK(cudaEventCreate(&ctx->ev1));
+  CREATE_CHECK(dev_alloc(&ctx->rad_dev, 1));
+  CREATE_CHECK(dev_alloc(&ctx->params_dev, 1));
+  CREATE_CHECK(dev_alloc(&ctx->counters, 1));
+  CREATE_CHECK(dev_alloc(&ctx->rad_counter, 1));
+  CREATE_CHECK(cudaMemcpy(ctx->rad_dev, &ctx->rad, sizeof(RadParams), cudaMemcpyHostToDevice));
+  CREATE_CHECK(cudaMemcpy(ctx->params_dev, &ctx->params, sizeof(bl_params), cudaMemcpyHostToDevice));
+#undef CREATE_CHECK
+  *out = ctx;
+  return BL_OK;
+}
+
+void bl_destroy(bl_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  for (auto &L : ctx->levels) free_level(L);
+  for (void *p : ctx->grid_allocs) cudaFree(p);
+  cudaFree(ctx->rad_dev); cudaFree(ctx->params_dev); cudaFree(ctx->counters); cudaFree(ctx->rad_counter);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int bl_image_num_quantities(const bl_ctx *ctx) { return ctx ? ctx->rad.num_quantities : -1; }
+
+int bl_set_taps(bl_ctx *ctx, int enabled) {
+  if (!ctx) return BL_ERR_ARG;
+  ctx->taps_enabled = enabled != 0;
+  return BL_OK;
+}
+
+int bl_device_info(bl_ctx *ctx, char *name, int name_len, int *sm_count, double *hbm_free_gb) {
+  if (!ctx) return BL_ERR_ARG;
+  BL_CUDA_CHECK(cudaSetDevice(ctx->device));
+  cudaDeviceProp prop;
+  BL_CUDA_CHECK(cudaGetDeviceProperties(&prop, ctx->device));
+  if (name && name_len > 0) snprintf(name, (size_t)name_len, "%s", prop.name);
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  size_t fr = 0, tot = 0;
+  BL_CUDA_CHECK(cudaMemGetInfo(&fr, &tot));
+  if (hbm_free_gb) *hbm_free_gb = (double)fr / 1e9;
+  return BL_OK;
+}
+
+int bl_measure_fp64_peak(bl_ctx *ctx, double *tflops) {
+  if (!ctx || !tflops) return BL_ERR_ARG;
+  BL_CUDA_CHECK(cudaSetDevice(ctx->device));
+  double *sink = nullptr;
+  const int blocks = ctx->sm_count * 8, threads = 256, iters = 4096;
+  BL_CUDA_CHECK(dev_alloc(&sink, (size_t)blocks * threads));
+  BL_CUDA_CHECK(bl_launch_fp64_peak(sink, blocks, iters, ctx->stream));  // warm-up
+  double best = 0.0;
+  for (int rep = 0; rep < 5; rep++) {
+    BL_CUDA_CHECK(cudaEventRecord(ctx->ev0, ctx->stream));
+    BL_CUDA_CHECK(bl_launch_fp64_peak(sink, blocks, iters, ctx->stream));
+    BL_CUDA_CHECK(cudaEventRecord(ctx->ev1, ctx->stream));
+    BL_CUDA_CHECK(cudaEventSynchronize(ctx->ev1));
+    float ms = 0.f;
+    BL_CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    // 16 independent FMA chains per thread, 2 flop per FMA
+    double flop = (double)blocks * threads * (double)iters * 16.0 * 2.0;
+    double tf = flop / (ms * 1e-3) / 1e12;
+    if (tf > best) best = tf;
+  }
+  cudaFree(sink);
+  *tflops = best;
+  return BL_OK;
+}
+
+int bl_upload_grid(bl_ctx *ctx, const bl_grid_view *gv) {
+  if (!ctx || !gv) return BL_ERR_ARG;
+  if (gv->n_b <= 0 || gv->n_i <= 0 || gv->n_j <= 0 || gv->n_k <= 0 || !gv->prim || !gv->x1f || !gv->x2f ||
+      !gv->x3f || !gv->x1v || !gv->x2v || !gv->x3v)
+    return bl_fail(ctx, BL_ERR_ARG, "bl_upload_grid: incomplete grid view");
+  BL_CUDA_CHECK(cudaSetDevice(ctx->device));
+  bool same_shape = ctx->have_grid && ctx->grid.n_b == gv->n_b && ctx->grid.n_k == gv->n_k &&
+                    ctx->grid.n_j == gv->n_j && ctx->grid.n_i == gv->n_i;
+  bool want_kappa = ctx->params.plasma_model == BL_PLASMA_CODE_KAPPA;
+  if (want_kappa && (gv->ind_kappa < 0 || gv->ind_kappa >= gv->n_var))
+    return bl_fail(ctx, BL_ERR_ARG, "plasma_model = code_kappa needs an electron entropy variable");
+  size_t cells = (size_t)gv->n_b * gv->n_k * gv->n_j * gv->n_i;
+  GridDev &g = ctx->grid;
+  if (!same_shape) {
+    for (void *p : ctx->grid_allocs) cudaFree(p);
+    ctx->grid_allocs.clear();
+    g = GridDev();
+    g.n_b = gv->n_b; g.n_k = gv->n_k; g.n_j = gv->n_j; g.n_i = gv->n_i;
+    double *d = nullptr;
+    auto alloc_d = [&](const double **dst, size_t n) -> cudaError_t {
+      cudaError_t e = dev_alloc(&d, n);
+      if (e == cudaSuccess) { *dst = d; ctx->grid_allocs.push_back(d); }
+      return e;
+    };
+    BL_CUDA_CHECK(alloc_d(&g.x1f, (size_t)g.n_b * (g.n_i + 1)));
+    BL_CUDA_CHECK(alloc_d(&g.x2f, (size_t)g.n_b * (g.n_j + 1)));
+    BL_CUDA_CHECK(alloc_d(&g.x3f, (size_t)g.n_b * (g.n_k + 1)));
+    BL_CUDA_CHECK(alloc_d(&g.x1v, (size_t)g.n_b * g.n_i));
+    BL_CUDA_CHECK(alloc_d(&g.x2v, (size_t)g.n_b * g.n_j));
+    BL_CUDA_CHECK(alloc_d(&g.x3v, (size_t)g.n_b * g.n_k));
+    BL_CUDA_CHECK(alloc_d(&g.bounds, (size_t)g.n_b * 6));
+    float4 *c4 = nullptr;
+    BL_CUDA_CHECK(dev_alloc(&c4, cells * 2));
+    g.cells = c4; ctx->grid_allocs.push_back(c4);
+    if (want_kappa) {
+      float *kp = nullptr;
+      BL_CUDA_CHECK(dev_alloc(&kp, cells));
+      g.kappa = kp; ctx->grid_allocs.push_back(kp);
+    }
+  }
+  auto h2d = [&](const double *dst, const double *src, size_t n) {
+    return cudaMemcpyAsync((void *)dst, src, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+  };
+  BL_CUDA_CHECK(h2d(g.x1f, gv->x1f, (size_t)g.n_b * (g.n_i + 1)));
+  BL_CUDA_CHECK(h2d(g.x2f, gv->x2f, (size_t)g.n_b * (g.n_j + 1)));
+  BL_CUDA_CHECK(h2d(g.x3f, gv->x3f, (size_t)g.n_b * (g.n_k + 1)));
+  BL_CUDA_CHECK(h2d(g.x1v, gv->x1v, (size_t)g.n_b * g.n_i));
+  BL_CUDA_CHECK(h2d(g.x2v, gv->x2v, (size_t)g.n_b * g.n_j));
+  BL_CUDA_CHECK(h2d(g.x3v, gv->x3v, (size_t)g.n_b * g.n_k));
+  std::vector<double> bounds((size_t)g.n_b * 6);
+  for (int b = 0; b < g.n_b; b++) {
+    bounds[6 * b + 0] = gv->x1f[(size_t)b * (g.n_i + 1)];
+    bounds[6 * b + 1] = gv->x1f[(size_t)b * (g.n_i + 1) + g.n_i];
+    bounds[6 * b + 2] = gv->x2f[(size_t)b * (g.n_j + 1)];
+    bounds[6 * b + 3] = gv->x2f[(size_t)b * (g.n_j + 1) + g.n_j];
+    bounds[6 * b + 4] = gv->x3f[(size_t)b * (g.n_k + 1)];
+    bounds[6 * b + 5] = gv->x3f[(size_t)b * (g.n_k + 1) + g.n_k];
+  }
+  BL_CUDA_CHECK(cudaMemcpyAsync((void *)g.bounds, bounds.data(), bounds.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  // primitives: stage the reader's (var, b, k, j, i) planes, then re-lay out to one record per cell
+  float *stage = nullptr;
+  BL_CUDA_CHECK(dev_alloc(&stage, (size_t)gv->n_var * cells));
+  cudaError_t e = cudaMemcpyAsync(stage, gv->prim, (size_t)gv->n_var * cells * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+  int idx[9] = {gv->ind_rho, gv->ind_pgas, gv->ind_uu1, gv->ind_uu2, gv->ind_uu3, gv->ind_bb1, gv->ind_bb2, gv->ind_bb3,
+                want_kappa ? gv->ind_kappa : -1};
+  for (int q = 0; q < 8 && e == cudaSuccess; q++)
+    if (idx[q] < 0 || idx[q] >= gv->n_var) { cudaFree(stage); return bl_fail(ctx, BL_ERR_ARG, "bl_upload_grid: variable index %d out of range", q); }
+  int *idx_dev = nullptr;
+  if (e == cudaSuccess) e = dev_alloc(&idx_dev, 9);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(idx_dev, idx, sizeof idx, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = bl_launch_relayout_grid(stage, gv->n_var, idx_dev, cells, const_cast<float4 *>(g.cells), const_cast<float *>(g.kappa), ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(stage);
+  cudaFree(idx_dev);
+  if (e != cudaSuccess) return bl_fail_cuda(ctx, e, "grid upload", __FILE__, __LINE__);
+  ctx->have_grid = true;
+  return BL_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+// Trace rays [first, first+count) of a level into L.step (one wave).
+int trace_wave(bl_ctx *ctx, Level &L, int64_t first, int64_t count) {
+  const bl_params &p = ctx->params;
+  GeoArgs g{};
+  g.cam_pos = L.cam_pos + 4 * first;
+  g.cam_dir = L.cam_dir + 4 * first;
+  g.rays = count;
+  g.a = p.bh_a; g.camera_r = p.camera_r; g.r_terminate = p.r_terminate; g.r_horizon = p.r_horizon;
+  g.ray_step = p.ray_step; g.tol_abs = p.ray_tol_abs; g.tol_rel = p.ray_tol_rel;
+  g.max_steps = p.ray_max_steps; g.max_retries = p.ray_max_retries;
+  g.sb.buf = L.step; g.sb.rays = count; g.sb.cap = p.ray_max_steps;
+  g.sample_num = L.num + first;
+  g.sample_flags = L.flags + first;
+  g.counters = ctx->counters;
+  BL_CUDA_CHECK(cudaMemsetAsync(&ctx->counters->next_ray, 0, sizeof(unsigned long long), ctx->stream));
+  if (p.ray_integrator == BL_INTEGRATOR_DP)
+    BL_CUDA_CHECK(bl_launch_geodesic_dp(&g, p.ray_flat, ctx->sm_count, ctx->stream));
+  else
+    BL_CUDA_CHECK(bl_launch_geodesic_rk(&g, p.ray_flat, p.ray_integrator == BL_INTEGRATOR_RK4 ? 4 : 2, ctx->sm_count, ctx->stream));
+  return BL_OK;
+}
+
+int read_geo_counters(bl_ctx *ctx, Level &L) {
+  GeoCounters c;
+  BL_CUDA_CHECK(cudaMemcpyAsync(&c, ctx->counters, sizeof c, cudaMemcpyDeviceToHost, ctx->stream));
+  BL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  L.stats.num_rays = L.rays;
+  L.stats.geodesic_num_steps = c.max_samples;
+  L.stats.num_bad_geodesics = (int64_t)c.bad;
+  L.stats.num_samples = (int64_t)c.samples;
+  L.stats.num_attempts = (int64_t)c.attempts;
+  L.stats.num_accepted = (int64_t)c.accepted;
+  return BL_OK;
+}
+
+int radiate_wave(bl_ctx *ctx, Level &L, int64_t first, int64_t count) {
+  RadArgs A{};
+  A.P = ctx->rad_dev;
+  A.grid = ctx->grid;
+  A.sb.buf = L.step; A.sb.rays = count; A.sb.cap = ctx->params.ray_max_steps;
+  A.sample_num = L.num + first;
+  A.sample_flags = L.flags + first;
+  A.mom_factor = L.mom + first;
+  A.rays = count;
+  A.image = L.image + first;
+  A.image_stride = L.rays;
+  A.render = L.render ? L.render + first : nullptr;
+  A.sample_counter = ctx->rad_counter;
+  if (L.tap_nan) {
+    size_t o = (size_t)first * L.tap_S;
+    A.taps.S = L.tap_S;
+    A.taps.nan_ = L.tap_nan + o; A.taps.cut = L.tap_cut + o; A.taps.fallback = L.tap_fb + o;
+    A.taps.inds = L.tap_inds ? L.tap_inds + 4 * o : nullptr;
+    A.taps.fracs = L.tap_fracs ? L.tap_fracs + 3 * o : nullptr;
+  }
+  bool sim = ctx->params.model_type == BL_MODEL_SIMULATION;
+  if (ctx->rad.polarization)
+    BL_CUDA_CHECK(bl_launch_radiate_polarized(&A, ctx->rad.num_freq, ctx->stream));
+  else
+    BL_CUDA_CHECK(bl_launch_radiate_unpolarized(&A, ctx->rad.num_freq, sim ? 1 : 0, ctx->stream));
+  return BL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bl_trace_level(bl_ctx *ctx, int level, const double *cam_pos, const double *cam_dir, const double *mom_factor,
+                   int64_t num_rays, bl_level_stats *stats) {
+  if (!ctx) return BL_ERR_ARG;
+  if (level < 0 || level >= (int)ctx->levels.size()) return bl_fail(ctx, BL_ERR_ARG, "bl_trace_level: level %d out of range", level);
+  if (!cam_pos || !cam_dir || !mom_factor || num_rays < 0) return bl_fail(ctx, BL_ERR_ARG, "bl_trace_level: null camera arrays");
+  BL_CUDA_CHECK(cudaSetDevice(ctx->device));
+  Level &L = ctx->levels[level];
+  free_level(L);
+  L.rays = num_rays;
+  if (num_rays == 0) { L.traced = true; L.resident = true; if (stats) *stats = L.stats; return BL_OK; }
+  const int Q = ctx->rad.num_quantities, R = ctx->rad.render_num_images;
+  BL_CUDA_CHECK(dev_alloc(&L.cam_pos, (size_t)num_rays * 4));
+  BL_CUDA_CHECK(dev_alloc(&L.cam_dir, (size_t)num_rays * 4));
+  BL_CUDA_CHECK(dev_alloc(&L.mom, (size_t)num_rays));
+  BL_CUDA_CHECK(dev_alloc(&L.num, (size_t)num_rays));
+  BL_CUDA_CHECK(dev_alloc(&L.flags, (size_t)num_rays));
+  BL_CUDA_CHECK(dev_alloc(&L.image, (size_t)num_rays * (size_t)(Q > 0 ? Q : 1)));
+  if (R > 0) BL_CUDA_CHECK(dev_alloc(&L.render, (size_t)num_rays * 3 * R));
+  BL_CUDA_CHECK(cudaMemcpyAsync(L.cam_pos, cam_pos, (size_t)num_rays * 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  BL_CUDA_CHECK(cudaMemcpyAsync(L.cam_dir, cam_dir, (size_t)num_rays * 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  BL_CUDA_CHECK(cudaMemcpyAsync(L.mom, mom_factor, (size_t)num_rays * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+
+  // wave size from the HBM budget: 72 bytes per sample slot, ray_max_steps slots per ray
+  size_t fr = 0, tot = 0;
+  BL_CUDA_CHECK(cudaMemGetInfo(&fr, &tot));
+  size_t per_ray = (size_t)ctx->params.ray_max_steps * 9 * sizeof(double);
+  size_t budget = (size_t)((double)fr * 0.80);
+  int64_t fit = (int64_t)(budget / per_ray);
+  if (ctx->params.tile_rays > 0 && ctx->params.tile_rays < fit) fit = ctx->params.tile_rays;
+  if (fit < 128) return bl_fail(ctx, BL_ERR_NOMEM, "not enough free HBM for a 128-ray wave (%zu bytes per ray)", per_ray);
+  if (fit >= num_rays) {
+    L.wave_rays = num_rays;
+    L.resident = true;
+  } else {
+    // split into equal waves (multiples of 128 rays) and keep headroom for other levels
+    int64_t waves = (num_rays + fit - 1) / fit;
+    int64_t w = (num_rays + waves - 1) / waves;
+    L.wave_rays = (w + 127) / 128 * 128;
+    L.resident = false;
+  }
+  BL_CUDA_CHECK(dev_alloc(&L.step, (size_t)L.wave_rays * per_ray / sizeof(double)));
+  BL_CUDA_CHECK(cudaMemsetAsync(ctx->counters, 0, sizeof(GeoCounters), ctx->stream));
+  L.stats = bl_level_stats();
+  if (L.resident) {
+    BL_CUDA_CHECK(cudaEventRecord(ctx->ev0, ctx->stream));
+    int rc = trace_wave(ctx, L, 0, num_rays);
+    if (rc) return rc;
+    BL_CUDA_CHECK(cudaEventRecord(ctx->ev1, ctx->stream));
+    rc = read_geo_counters(ctx, L);
+    if (rc) return rc;
+    float ms = 0.f;
+    BL_CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    L.stats.ms_geodesic = ms;
+    L.traced = true;
+  } else {
+    // count-only information is produced by the first radiate pass; report what is known
+    L.stats.num_rays = num_rays;
+    L.traced = false;
+    BL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  }
+  if (stats) *stats = L.stats;
+  return BL_OK;
+}
+
+int bl_radiate_level(bl_ctx *ctx, int level, int snapshot, double *image, double *render, bl_level_stats *stats) {
+  (void)snapshot;
+  if (!ctx) return BL_ERR_ARG;
+  if (level < 0 || level >= (int)ctx->levels.size()) return bl_fail(ctx, BL_ERR_ARG, "bl_radiate_level: level %d out of range", level);
+  Level &L = ctx->levels[level];
+  if (!L.cam_pos && L.rays > 0) return bl_fail(ctx, BL_ERR_STATE, "bl_radiate_level: level %d has not been traced", level);
+  bool sim = ctx->params.model_type == BL_MODEL_SIMULATION;
+  if (sim && !ctx->have_grid) return bl_fail(ctx, BL_ERR_STATE, "bl_radiate_level: no grid uploaded");
+  BL_CUDA_CHECK(cudaSetDevice(ctx->device));
+  const int Q = ctx->rad.num_quantities, R = ctx->rad.render_num_images;
+  if (L.rays == 0) { if (stats) *stats = L.stats; return BL_OK; }
+  if (ctx->taps_enabled && sim && !L.tap_nan) {
+    if (!L.resident) return bl_fail(ctx, BL_ERR_STATE, "parity taps need a resident level (reduce rays or raise tile_rays)");
+    L.tap_S = L.stats.geodesic_num_steps > 0 ? L.stats.geodesic_num_steps : 1;
+    size_t ns = (size_t)L.rays * L.tap_S;
+    BL_CUDA_CHECK(dev_alloc(&L.tap_inds, ns * 4));
+    BL_CUDA_CHECK(cudaMemsetAsync(L.tap_inds, 0xff, ns * 4 * sizeof(int32_t), ctx->stream));
+    if (ctx->params.simulation_interp) {
+      BL_CUDA_CHECK(dev_alloc(&L.tap_fracs, ns * 3));
+      BL_CUDA_CHECK(cudaMemsetAsync(L.tap_fracs, 0, ns * 3 * sizeof(double), ctx->stream));
+    }
+    BL_CUDA_CHECK(dev_alloc(&L.tap_nan, ns)); BL_CUDA_CHECK(dev_alloc(&L.tap_cut, ns)); BL_CUDA_CHECK(dev_alloc(&L.tap_fb, ns));
+    BL_CUDA_CHECK(cudaMemsetAsync(L.tap_nan, 0, ns, ctx->stream));
+    BL_CUDA_CHECK(cudaMemsetAsync(L.tap_cut, 0, ns, ctx->stream));
+    BL_CUDA_CHECK(cudaMemsetAsync(L.tap_fb, 0, ns, ctx->stream));
+  }
+  BL_CUDA_CHECK(cudaMemsetAsync(ctx->rad_counter, 0, sizeof(unsigned long long), ctx->stream));
+  double ms_geo = 0.0, ms_rad = 0.0;
+  float ms = 0.f;
+  if (L.resident) {
+    BL_CUDA_CHECK(cudaEventRecord(ctx->ev0, ctx->stream));
+    int rc = radiate_wave(ctx, L, 0, L.rays);
+    if (rc) return rc;
+    BL_CUDA_CHECK(cudaEventRecord(ctx->ev1, ctx->stream));
+    BL_CUDA_CHECK(cudaEventSynchronize(ctx->ev1));
+    BL_CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ms_rad = ms;
+  } else {
+    // waves: trace then radiate, reusing one step buffer; geodesic statistics accumulate over waves
+    BL_CUDA_CHECK(cudaMemsetAsync(ctx->counters, 0, sizeof(GeoCounters), ctx->stream));
+    for (int64_t first = 0; first < L.rays; first += L.wave_rays) {
+      int64_t count = L.rays - first < L.wave_rays ? L.rays - first : L.wave_rays;
+      BL_CUDA_CHECK(cudaEventRecord(ctx->ev0, ctx->stream));
+      int rc = trace_wave(ctx, L, first, count);
+      if (rc) return rc;
+      BL_CUDA_CHECK(cudaEventRecord(ctx->ev1, ctx->stream));
+      BL_CUDA_CHECK(cudaEventSynchronize(ctx->ev1));
+      BL_CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+      ms_geo += ms;
+      BL_CUDA_CHECK(cudaEventRecord(ctx->ev0, ctx->stream));
+      rc = radiate_wave(ctx, L, first, count);
+      if (rc) return rc;
+      BL_CUDA_CHECK(cudaEventRecord(ctx->ev1, ctx->stream));
+      BL_CUDA_CHECK(cudaEventSynchronize(ctx->ev1));
+      BL_CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+      ms_rad += ms;
+    }
+    int rc = read_geo_counters(ctx, L);
+    if (rc) return rc;
+    L.stats.ms_geodesic = ms_geo;
+    L.traced = true;
+  }
+  L.stats.ms_radiation = ms_rad;
+  if (image && Q > 0)
+    BL_CUDA_CHECK(cudaMemcpyAsync(image, L.image, (size_t)L.rays * Q * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (render && R > 0 && L.render)
+    BL_CUDA_CHECK(cudaMemcpyAsync(render, L.render, (size_t)L.rays * 3 * R * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  BL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  if (stats) *stats = L.stats;
+  return BL_OK;
+}
+
+int bl_refine_level(bl_ctx *ctx, int level, const int32_t *block_locs, int64_t num_blocks, uint8_t *flags, int64_t *n_refined) {
+  if (!ctx) return BL_ERR_ARG;
+  if (level < 0 || level >= (int)ctx->levels.size()) return bl_fail(ctx, BL_ERR_ARG, "bl_refine_level: level %d out of range", level);
+  if (!block_locs || !flags || num_blocks < 0) return bl_fail(ctx, BL_ERR_ARG, "bl_refine_level: null argument");
+  Level &L = ctx->levels[level];
+  const bl_params &p = ctx->params;
+  if (p.adaptive_max_level <= 0) return bl_fail(ctx, BL_ERR_STATE, "bl_refine_level: adaptive_max_level is 0");
+  int64_t bs2 = (int64_t)p.adaptive_block_size * p.adaptive_block_size;
+  if (num_blocks * bs2 != L.rays || !L.image) return bl_fail(ctx, BL_ERR_STATE, "bl_refine_level: level %d image has %lld rays, expected %lld blocks x %lld", level, (long long)L.rays, (long long)num_blocks, (long long)bs2);
+  BL_CUDA_CHECK(cudaSetDevice(ctx->device));
+  if (n_refined) *n_refined = 0;
+  if (num_blocks == 0) return BL_OK;
+  int32_t *locs_dev = nullptr;
+  uint8_t *flags_dev = nullptr;
+  BL_CUDA_CHECK(dev_alloc(&locs_dev, (size_t)num_blocks * 2));
+  BL_CUDA_CHECK(dev_alloc(&flags_dev, (size_t)num_blocks));
+  cudaError_t e = cudaMemcpyAsync(locs_dev, block_locs, (size_t)num_blocks * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaEventRecord(ctx->ev0, ctx->stream);
+  if (e == cudaSuccess) e = bl_launch_refine(L.image, L.rays, level, locs_dev, num_blocks, ctx->params_dev, flags_dev, ctx->stream);
+  if (e == cudaSuccess) e = cudaEventRecord(ctx->ev1, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(flags, flags_dev, (size_t)num_blocks, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  float ms = 0.f;
+  if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  cudaFree(locs_dev); cudaFree(flags_dev);
+  if (e != cudaSuccess) return bl_fail_cuda(ctx, e, "refine", __FILE__, __LINE__);
+  L.stats.ms_refine = ms;
+  int64_t cnt = 0;
+  for (int64_t b = 0; b < num_blocks; b++) cnt += flags[b] ? 1 : 0;
+  if (n_refined) *n_refined = cnt;
+  return BL_OK;
+}
+
+int bl_download_samples(bl_ctx *ctx, int level, uint8_t *flags, int32_t *num, double *pos, double *dir, double *len) {
+  if (!ctx) return BL_ERR_ARG;
+  if (level < 0 || level >= (int)ctx->levels.size()) return bl_fail(ctx, BL_ERR_ARG, "bl_download_samples: level %d out of range", level);
+  Level &L = ctx->levels[level];
+  if (!L.traced) return bl_fail(ctx, BL_ERR_STATE, "bl_download_samples: level %d not traced", level);
+  BL_CUDA_CHECK(cudaSetDevice(ctx->device));
+  if (L.rays == 0) return BL_OK;
+  if (flags) BL_CUDA_CHECK(cudaMemcpyAsync(flags, L.flags, (size_t)L.rays, cudaMemcpyDeviceToHost, ctx->stream));
+  if (num) BL_CUDA_CHECK(cudaMemcpyAsync(num, L.num, (size_t)L.rays * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if (pos || dir || len) {
+    if (!L.resident) return bl_fail(ctx, BL_ERR_STATE, "bl_download_samples: level %d is traced in waves; samples are not resident", level);
+    int S = L.stats.geodesic_num_steps;
+    size_t ns = (size_t)L.rays * (size_t)(S > 0 ? S : 1);
+    double *dpos = nullptr, *ddir = nullptr, *dlen = nullptr;
+    if (pos) BL_CUDA_CHECK(dev_alloc(&dpos, ns * 4));
+    if (dir) BL_CUDA_CHECK(dev_alloc(&ddir, ns * 4));
+    if (len) BL_CUDA_CHECK(dev_alloc(&dlen, ns));
+    StepBuffer sb; sb.buf = L.step; sb.rays = L.rays; sb.cap = ctx->params.ray_max_steps;
+    cudaError_t e = bl_launch_unpack_samples(&sb, L.num, L.rays, S, dpos, ddir, dlen, ctx->stream);
+    if (e == cudaSuccess && pos) e = cudaMemcpyAsync(pos, dpos, ns * 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && dir) e = cudaMemcpyAsync(dir, ddir, ns * 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && len) e = cudaMemcpyAsync(len, dlen, ns * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(dpos); cudaFree(ddir); cudaFree(dlen);
+    if (e != cudaSuccess) return bl_fail_cuda(ctx, e, "sample download", __FILE__, __LINE__);
+  }
+  BL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  return BL_OK;
+}
+
+int bl_download_sample_inds(bl_ctx *ctx, int level, int32_t *inds, double *fracs, uint8_t *nan_, uint8_t *cut, uint8_t *fallback) {
+  if (!ctx) return BL_ERR_ARG;
+  if (level < 0 || level >= (int)ctx->levels.size()) return bl_fail(ctx, BL_ERR_ARG, "bl_download_sample_inds: level %d out of range", level);
+  Level &L = ctx->levels[level];
+  if (!L.tap_nan) return bl_fail(ctx, BL_ERR_STATE, "bl_download_sample_inds: call bl_set_taps(ctx, 1) before bl_radiate_level");
+  BL_CUDA_CHECK(cudaSetDevice(ctx->device));
+  size_t ns = (size_t)L.rays * L.tap_S;
+  if (inds) BL_CUDA_CHECK(cudaMemcpyAsync(inds, L.tap_inds, ns * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if (fracs && L.tap_fracs) BL_CUDA_CHECK(cudaMemcpyAsync(fracs, L.tap_fracs, ns * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (nan_) BL_CUDA_CHECK(cudaMemcpyAsync(nan_, L.tap_nan, ns, cudaMemcpyDeviceToHost, ctx->stream));
+  if (cut) BL_CUDA_CHECK(cudaMemcpyAsync(cut, L.tap_cut, ns, cudaMemcpyDeviceToHost, ctx->stream));
+  if (fallback) BL_CUDA_CHECK(cudaMemcpyAsync(fallback, L.tap_fb, ns, cudaMemcpyDeviceToHost, ctx->stream));
+  BL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  return BL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,33 @@
+// Minimal reader for Athena++ .athdf snapshots (HDF5 superblock v0/v1, symbol-table groups, v1 object
+// headers, contiguous datasets) -- the subset the reference's hand-written parser accepts
+// (reference src/simulation_reader/hdf5_format_*.cpp, simulation_reader.cpp:304-351,591-621,762-781,
+// 1141-1216).  Produces the host arrays the C ABI's bl_grid_view points at.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../../include/blacklight_b200.h"
+
+namespace blh {
+
+struct AthenaGrid {
+  int n_b = 0, n_k = 0, n_j = 0, n_i = 0, n_var = 0;
+  std::vector<int32_t> levels, locations;
+  std::vector<double> x1f, x2f, x3f, x1v, x2v, x3v;  // float32 file values widened to double
+  std::vector<float> prim;                           // (n_var, n_b, n_k, n_j, n_i): "prim" then "B"
+  int ind_rho = -1, ind_pgas = -1, ind_kappa = -1, ind_uu1 = -1, ind_uu2 = -1, ind_uu3 = -1;
+  int ind_bb1 = -1, ind_bb2 = -1, ind_bb3 = -1;
+  int n_3_root = 0;
+  double time = 0.0;
+  bl_grid_view view() const;
+};
+
+// kappa_name: electron-entropy variable to locate when plasma_model = code_kappa ("" = none).
+// reuse_layout: keep coordinates of `grid` (already read from the first snapshot) and only refresh cell data.
+void read_athdf(const std::string &path, const std::string &kappa_name, bool reuse_layout, AthenaGrid &grid);
+
+// File name of snapshot `number` from a pattern holding one `{Nd}` field (simulation_reader.cpp:870-904)
+std::string format_numbered(const std::string &pattern, int number, const char *what);
+
+}  // namespace blh

@@ -1,0 +1,35 @@
+// InputFile -> (CameraSetup, bl_params): the parameter copying and validation the reference does in
+// its GeodesicIntegrator and RadiationIntegrator constructors (geodesic_integrator.cpp:23-157,
+// radiation_integrator.cpp:26-541), producing the POD the C ABI takes.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "../../../include/blacklight_b200.h"
+#include "camera.hpp"
+#include "input_file.hpp"
+
+namespace blh {
+
+struct RunConfig {
+  bl_params params;        // camera frame fields filled in
+  CameraSetup camera;
+  CameraFrame frame;
+  std::vector<double> frequencies;
+  // output / reader side
+  int output_format = 0;   // 0 npz, 1 npy, 2 raw
+  std::string output_file;
+  bool output_camera = false;
+  int simulation_format = 0;  // 0 athena, 1 athenak, 2 iharm3d, 3 harm3d
+  std::string simulation_file, simulation_kappa_name;
+  bool simulation_multiple = false;
+  int simulation_start = 0, simulation_end = 0;
+  bool gamma_set = false;
+  bool checkpoint_geodesic_save = false, checkpoint_sample_save = false;
+  std::string checkpoint_geodesic_file, checkpoint_sample_file;
+  int num_runs = 1;
+};
+
+RunConfig make_config(const InputFile &in);
+
+}  // namespace blh

@@ -1,0 +1,100 @@
+// C entry points of the host layer (declared in include/blacklight_b200_host.h): what the Python
+// tests, bench.py and the command-line driver use to reach the input surface, the camera and the
+// re-hosted main without linking C++ types.
+#include "../../../include/blacklight_b200_host.h"
+
+#include <cstring>
+#include <string>
+
+#include "config.hpp"
+#include "driver.hpp"
+
+struct blh_config {
+  blh::RunConfig cfg;
+};
+
+namespace {
+thread_local std::string g_error;
+int fail(const std::exception &e) {
+  g_error = e.what();
+  return 1;
+}
+}  // namespace
+
+extern "C" {
+
+const char *blh_last_error(void) { return g_error.c_str(); }
+
+int blh_config_from_input(const char *path, blh_config **out) {
+  if (!path || !out) { g_error = "null argument"; return 1; }
+  *out = nullptr;
+  try {
+    blh::InputFile in(path);
+    blh_config *c = new blh_config{blh::make_config(in)};
+    *out = c;
+    return 0;
+  } catch (const std::exception &e) {
+    return fail(e);
+  }
+}
+
+void blh_config_free(blh_config *c) { delete c; }
+
+const bl_params *blh_config_params(const blh_config *c) { return c ? &c->cfg.params : nullptr; }
+
+int blh_config_num_runs(const blh_config *c) { return c ? c->cfg.num_runs : 0; }
+
+void blh_config_set_device(blh_config *c, int device, int64_t tile_rays) {
+  if (!c) return;
+  c->cfg.params.device = device;
+  c->cfg.params.tile_rays = tile_rays;
+}
+
+int blh_camera_frame(const blh_config *c, double out[28]) {
+  if (!c || !out) { g_error = "null argument"; return 1; }
+  const blh::CameraFrame &f = c->cfg.frame;
+  const double *v[7] = {f.x, f.u_con, f.u_cov, f.norm_con, f.norm_con_c, f.hor_con_c, f.vert_con_c};
+  for (int i = 0; i < 7; i++) std::memcpy(out + 4 * i, v[i], 4 * sizeof(double));
+  return 0;
+}
+
+int64_t blh_camera_root(const blh_config *c, double *pos, double *dir, double *factor) {
+  if (!c || !pos || !dir || !factor) { g_error = "null argument"; return -1; }
+  std::vector<double> p, d, f;
+  blh::camera_root(c->cfg.camera, c->cfg.frame, p, d, f);
+  std::memcpy(pos, p.data(), p.size() * sizeof(double));
+  std::memcpy(dir, d.data(), d.size() * sizeof(double));
+  std::memcpy(factor, f.data(), f.size() * sizeof(double));
+  return (int64_t)f.size();
+}
+
+int64_t blh_camera_refined(const blh_config *c, int level, const int32_t *parent_locs, const uint8_t *flags,
+                           int64_t num_parents, int32_t *child_locs, double *pos, double *dir, double *factor) {
+  if (!c || !parent_locs || !flags) { g_error = "null argument"; return -1; }
+  std::vector<int32_t> pl(parent_locs, parent_locs + 2 * num_parents), cl;
+  std::vector<uint8_t> fl(flags, flags + num_parents);
+  std::vector<double> p, d, f;
+  blh::camera_refined(c->cfg.camera, c->cfg.frame, level, c->cfg.params.adaptive_block_size, pl, fl, cl, p, d, f);
+  if (child_locs) std::memcpy(child_locs, cl.data(), cl.size() * sizeof(int32_t));
+  if (pos) std::memcpy(pos, p.data(), p.size() * sizeof(double));
+  if (dir) std::memcpy(dir, d.data(), d.size() * sizeof(double));
+  if (factor) std::memcpy(factor, f.data(), f.size() * sizeof(double));
+  return (int64_t)cl.size() / 2;
+}
+
+int blh_run_input_file(const char *path, int device, int quiet, double timings[12]) {
+  if (!path) { g_error = "null argument"; return 1; }
+  try {
+    blh::RunTimings t = blh::run_input_file(path, device, quiet != 0);
+    if (timings) {
+      double v[12] = {t.total, t.geodesic, t.read, t.sample, t.image, t.render, t.gpu_geodesic_ms,
+                      t.gpu_radiation_ms, t.gpu_refine_ms, (double)t.rays, (double)t.samples, 0.0};
+      std::memcpy(timings, v, sizeof v);
+    }
+    return 0;
+  } catch (const std::exception &e) {
+    return fail(e);
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,348 @@
+// Per-sample stages shared by the unpolarized and polarized transfer kernels:
+//   geometric cuts -> CKS->SKS -> block search -> cell search -> nearest / trilinear gather
+//   (reference src/radiation_integrator/simulation_sampling.cpp:205-575, :667-1033)
+//   -> plasma state in CGS, value cuts, cell values (simulation_coefficients.cpp:286-387)
+//   -> fluid four-velocity and magnetic field in Cartesian Kerr-Schild (:397-408)
+// Nothing here is written to HBM: the fused kernels consume the results in registers, so the
+// reference's N x S x (inds, fracs, 9 primitives, 8 coefficients) arrays never exist.
+#pragma once
+#include "rad_types.cuh"
+
+namespace rad {
+
+enum SampleStatus : int { kSampleOk = 0, kSampleCut = 1, kSampleNan = 2, kSampleFallback = 3 };
+
+struct Prims {
+  float rho, pgas, kappa, uu1, uu2, uu3, bb1, bb2, bb3;
+};
+
+struct SampleIndex {  // what the reference stores in sample_inds / sample_fracs
+  int b, k, j, i;
+  double fk, fj, fi;
+};
+
+// Kerr-Schild radius with ordinary (fused) arithmetic; agrees with the reference to rounding
+__device__ __forceinline__ double ks_radius(double a, double x, double y, double z) {
+  double a2 = a * a;
+  double rr2 = x * x + y * y + z * z;
+  double r2 = 0.5 * (rr2 - a2 + hypot(rr2 - a2, 2.0 * a * z));
+  return sqrt(r2);
+}
+
+// first index i in [0, n) with faces[i+1] >= x, else n (reference linear scan :458-466)
+__device__ __forceinline__ int find_cell(const double *__restrict__ faces, int n, double x) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(faces + mid + 1) >= x)
+      hi = mid;
+    else
+      lo = mid + 1;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ bool in_block(const double *__restrict__ bd, double x1, double x2, double x3) {
+  return x1 >= bd[0] && x1 <= bd[1] && x2 >= bd[2] && x2 <= bd[3] && x3 >= bd[4] && x3 <= bd[5];
+}
+
+__device__ __forceinline__ void load_cell(const GridDev &g, size_t c, float v[8]) {
+  float4 lo = __ldg(g.cells + 2 * c), hi = __ldg(g.cells + 2 * c + 1);
+  v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
+  v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+}
+
+// Geometric cuts of one sample (simulation_sampling.cpp:237-292, formula_coefficients.cpp:75-119).
+// Returns true if the sample is cut.  r is the Kerr-Schild radius of (x,y,z).
+__device__ __forceinline__ bool geometric_cut(const RadParams &P, double x, double y, double z, double r) {
+  if (r > P.camera_r) return true;
+  if (P.cut_omit_near || P.cut_omit_far) {
+    double dot = x * P.camera_x[1] + y * P.camera_x[2] + z * P.camera_x[3];
+    if ((P.cut_omit_near && dot > 0.0) || (P.cut_omit_far && dot < 0.0)) return true;
+  }
+  if ((P.cut_omit_in >= 0.0 && r < P.cut_omit_in) || (P.cut_omit_out >= 0.0 && r > P.cut_omit_out)) return true;
+  if (P.cut_midplane_theta > 0.0 || P.cut_midplane_theta < 0.0) {
+    double th = acos(z / r);
+    double off = fabs(th - phys::pi / 2.0);
+    if ((P.cut_midplane_theta > 0.0 && off > P.cut_midplane_theta) ||
+        (P.cut_midplane_theta < 0.0 && off < -P.cut_midplane_theta))
+      return true;
+  }
+  if ((P.cut_midplane_z > 0.0 && fabs(z) > P.cut_midplane_z) ||
+      (P.cut_midplane_z < 0.0 && fabs(z) < -P.cut_midplane_z))
+    return true;
+  if (P.cut_plane) {
+    double dot = (x - P.cut_plane_origin[0]) * P.cut_plane_normal[0] +
+                 (y - P.cut_plane_origin[1]) * P.cut_plane_normal[1] +
+                 (z - P.cut_plane_origin[2]) * P.cut_plane_normal[2];
+    if (dot < 0.0) return true;
+  }
+  return false;
+}
+
+// Locate and gather.  `b_cache` is the block the previous sample of this ray lay in (the reference
+// keeps the same cache per OpenMP thread, simulation_sampling.cpp:180-189,352-394).
+// smem_bounds: block bounds staged in shared memory (n_b*6 doubles) or nullptr to read from HBM.
+__device__ __forceinline__ SampleStatus sample_grid(const RadParams &P, const GridDev &g,
+                                                    const double *smem_bounds, double x, double y,
+                                                    double z, double r, int &b_cache, Prims &out,
+                                                    SampleIndex &si) {
+  // simulation coordinates of the point (radiation_geometry.cpp:37-57)
+  double x1 = x, x2 = y, x3 = z;
+  if (P.coord != 0) {
+    double th = acos(z / r);
+    double ph = atan2(y, x) - atan(P.a / r);
+    ph += ph < 0.0 ? 2.0 * phys::pi : 0.0;
+    ph -= ph >= 2.0 * phys::pi ? 2.0 * phys::pi : 0.0;
+    x1 = r; x2 = th; x3 = ph;
+  }
+  // block: keep the cached one while it still contains the point, else first match in index order
+  const double *bounds = smem_bounds ? smem_bounds : g.bounds;
+  int b = b_cache;
+  const double *bd = bounds + 6 * b;
+  if (x1 < bd[0] || x1 > bd[1] || x2 < bd[2] || x2 > bd[3] || x3 < bd[4] || x3 > bd[5]) {
+    int bn = 0;
+    for (; bn < g.n_b; bn++)
+      if (in_block(bounds + 6 * bn, x1, x2, x3)) break;
+    if (bn == g.n_b) return P.fallback_nan ? kSampleNan : kSampleFallback;
+    b = bn;
+    b_cache = bn;
+  }
+  const int n_i = g.n_i, n_j = g.n_j, n_k = g.n_k;
+  int i = find_cell(g.x1f + (size_t)b * (n_i + 1), n_i, x1);
+  int j = find_cell(g.x2f + (size_t)b * (n_j + 1), n_j, x2);
+  int k = find_cell(g.x3f + (size_t)b * (n_k + 1), n_k, x3);
+  si.b = b;
+  if (!P.interp) {
+    si.k = k; si.j = j; si.i = i;
+    si.fk = si.fj = si.fi = 0.0;
+    size_t c = (((size_t)b * n_k + k) * n_j + j) * n_i + i;
+    float v[8];
+    load_cell(g, c, v);
+    out.rho = v[0]; out.pgas = v[1]; out.uu1 = v[2]; out.uu2 = v[3]; out.uu3 = v[4];
+    out.bb1 = v[5]; out.bb2 = v[6]; out.bb3 = v[7];
+    out.kappa = g.kappa ? __ldg(g.kappa + c) : 0.0f;
+    return kSampleOk;
+  }
+  // intra-block trilinear with extrapolation at block edges (simulation_sampling.cpp:485-502)
+  const double *x1v = g.x1v + (size_t)b * n_i, *x2v = g.x2v + (size_t)b * n_j, *x3v = g.x3v + (size_t)b * n_k;
+  int i_m = (i == 0 || (i != n_i - 1 && x1 >= __ldg(x1v + i))) ? i : i - 1;
+  int j_m = (j == 0 || (j != n_j - 1 && x2 >= __ldg(x2v + j))) ? j : j - 1;
+  int k_m = (k == 0 || (k != n_k - 1 && x3 >= __ldg(x3v + k))) ? k : k - 1;
+  double xa = __ldg(x1v + i_m), xb = __ldg(x1v + i_m + 1);
+  double ya = __ldg(x2v + j_m), yb = __ldg(x2v + j_m + 1);
+  double za = __ldg(x3v + k_m), zb = __ldg(x3v + k_m + 1);
+  double f_i = (x1 - xa) / (xb - xa);
+  double f_j = (x2 - ya) / (yb - ya);
+  double f_k = (x3 - za) / (zb - za);
+  si.k = k_m; si.j = j_m; si.i = i_m;
+  si.fk = f_k; si.fj = f_j; si.fi = f_i;
+  // weights in the reference's term order (InterpolateSimple, simulation_sampling.cpp:1334-1351)
+  double gk = 1.0 - f_k, gj = 1.0 - f_j, gi = 1.0 - f_i;
+  double w[8] = {gk * gj * gi, gk * gj * f_i, gk * f_j * gi, gk * f_j * f_i,
+                 f_k * gj * gi, f_k * gj * f_i, f_k * f_j * gi, f_k * f_j * f_i};
+  size_t c0 = (((size_t)b * n_k + k_m) * n_j + j_m) * n_i + i_m;
+  size_t sj = (size_t)n_i, sk = (size_t)n_j * n_i;
+  size_t off[8] = {0, 1, sj, sj + 1, sk, sk + 1, sk + sj, sk + sj + 1};
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double acc_kappa = 0.0;
+  float corner[8];
+  float corner_kappa = 0.0f;
+#pragma unroll
+  for (int p = 0; p < 8; p++) {
+    float v[8];
+    load_cell(g, c0 + off[p], v);
+    if (p == 0) {
+#pragma unroll
+      for (int q = 0; q < 8; q++) corner[q] = v[q];
+    }
+#pragma unroll
+    for (int q = 0; q < 8; q++) acc[q] += w[p] * (double)v[q];
+    if (g.kappa) {
+      float kv = __ldg(g.kappa + c0 + off[p]);
+      if (p == 0) corner_kappa = kv;
+      acc_kappa += w[p] * (double)kv;
+    }
+  }
+  // non-positive interpolated rho / pgas / kappa fall back to the anchor cell (:822-827)
+  if (acc[0] <= 0.0) acc[0] = (double)corner[0];
+  if (acc[1] <= 0.0) acc[1] = (double)corner[1];
+  if (g.kappa && acc_kappa <= 0.0) acc_kappa = (double)corner_kappa;
+  out.rho = (float)acc[0]; out.pgas = (float)acc[1]; out.uu1 = (float)acc[2]; out.uu2 = (float)acc[3];
+  out.uu3 = (float)acc[4]; out.bb1 = (float)acc[5]; out.bb2 = (float)acc[6]; out.bb3 = (float)acc[7];
+  out.kappa = (float)acc_kappa;
+  return kSampleOk;
+}
+
+struct Plasma {
+  double rho_cgs, n_e_cgs, pgas_cgs, theta_e, kb_tt_e_cgs, bb_cgs, sigma, beta_inv, b_sq;
+  double ucon[4], bcon[4];  // Cartesian Kerr-Schild components
+  bool value_cut;           // true: skip coupling (simulation_coefficients.cpp:361-375)
+  bool b_zero;              // all three simulation field components vanish (:394)
+};
+
+// Plasma state of one sample (simulation_coefficients.cpp:286-408).  (x,y,z) CKS position, r its radius.
+// want_vectors = false stops after the value cuts (cell values only).
+__device__ __forceinline__ void plasma_state(const RadParams &P, double x, double y, double z, double r,
+                                             const Prims &pr, bool want_vectors, Plasma &s) {
+  const double a = P.a;
+  double rho = pr.rho, pgas = pr.pgas, kappa = pr.kappa;
+  double uu1 = pr.uu1, uu2 = pr.uu2, uu3 = pr.uu3, bb1 = pr.bb1, bb2 = pr.bb2, bb3 = pr.bb3;
+  s.rho_cgs = rho * P.d_unit;
+  s.pgas_cgs = pgas * P.e_unit;
+  double n_cgs = s.rho_cgs / (P.plasma_mu * phys::m_p);
+  s.n_e_cgs = n_cgs / (1.0 + 1.0 / P.plasma_ne_ni);
+
+  // simulation-coordinate metric (radiation_geometry.cpp:421-573); only the entries that are used
+  double ucon_sim[4], bcon_sim[4];
+  double r2 = r * r, a2 = a * a;
+  double cth = z / r;
+  double cth2 = cth * cth;
+  double sth2 = 1.0 - cth2;
+  if (P.coord != 0) {
+    // spherical Kerr-Schild: nonzero g_{tt} g_{tr} g_{tph} g_{rr} g_{rph} g_{thth} g_{phph}
+    double sigma = r2 + a2 * cth2;
+    double delta = r2 - 2.0 * r + a2;
+    double tr = 2.0 * r / sigma;
+    double g00 = -(1.0 - tr), g01 = tr, g03 = -tr * a * sth2;
+    double g11 = 1.0 + tr, g13 = -(1.0 + tr) * a * sth2, g22 = sigma;
+    double g33 = (r2 + a2 + tr * a2 * sth2) * sth2;
+    double gc00 = -(1.0 + tr), gc01 = tr;
+    (void)delta;
+    double uu0 = sqrt(1.0 + g11 * uu1 * uu1 + 2.0 * g13 * uu1 * uu3 + g22 * uu2 * uu2 + g33 * uu3 * uu3);
+    double lapse = 1.0 / sqrt(-gc00);
+    double shift1 = -gc01 / gc00;
+    ucon_sim[0] = uu0 / lapse;
+    ucon_sim[1] = uu1 - shift1 * uu0 / lapse;
+    ucon_sim[2] = uu2;
+    ucon_sim[3] = uu3;
+    double ucov1 = g01 * ucon_sim[0] + g11 * ucon_sim[1] + g13 * ucon_sim[3];
+    double ucov2 = g22 * ucon_sim[2];
+    double ucov3 = g03 * ucon_sim[0] + g13 * ucon_sim[1] + g33 * ucon_sim[3];
+    bcon_sim[0] = ucov1 * bb1 + ucov2 * bb2 + ucov3 * bb3;
+    bcon_sim[1] = (bb1 + bcon_sim[0] * ucon_sim[1]) / ucon_sim[0];
+    bcon_sim[2] = (bb2 + bcon_sim[0] * ucon_sim[2]) / ucon_sim[0];
+    bcon_sim[3] = (bb3 + bcon_sim[0] * ucon_sim[3]) / ucon_sim[0];
+    double bcov0 = g00 * bcon_sim[0] + g01 * bcon_sim[1] + g03 * bcon_sim[3];
+    double bcov1 = g01 * bcon_sim[0] + g11 * bcon_sim[1] + g13 * bcon_sim[3];
+    double bcov2 = g22 * bcon_sim[2];
+    double bcov3 = g03 * bcon_sim[0] + g13 * bcon_sim[1] + g33 * bcon_sim[3];
+    s.b_sq = bcov0 * bcon_sim[0] + bcov1 * bcon_sim[1] + bcov2 * bcon_sim[2] + bcov3 * bcon_sim[3];
+  } else {
+    // Cartesian Kerr-Schild simulation: g = eta + f l l
+    double f = 2.0 * r2 * r / (r2 * r2 + a2 * z * z);
+    double l[4] = {1.0, (r * x + a * y) / (r2 + a2), (r * y - a * x) / (r2 + a2), z / r};
+    double uv[4] = {0.0, uu1, uu2, uu3};
+    double lu = l[1] * uu1 + l[2] * uu2 + l[3] * uu3;
+    double uu0 = sqrt(1.0 + uu1 * uu1 + uu2 * uu2 + uu3 * uu3 + f * lu * lu);
+    double gc00 = -f - 1.0;
+    double lapse = 1.0 / sqrt(-gc00);
+    ucon_sim[0] = uu0 / lapse;
+    for (int q = 1; q < 4; q++) ucon_sim[q] = uv[q] - (-(f * l[q]) / gc00) * uu0 / lapse;
+    double lucon = l[0] * ucon_sim[0] + l[1] * ucon_sim[1] + l[2] * ucon_sim[2] + l[3] * ucon_sim[3];
+    double ucov[4];
+    ucov[0] = -ucon_sim[0] + f * l[0] * lucon;
+    for (int q = 1; q < 4; q++) ucov[q] = ucon_sim[q] + f * l[q] * lucon;
+    bcon_sim[0] = ucov[1] * bb1 + ucov[2] * bb2 + ucov[3] * bb3;
+    bcon_sim[1] = (bb1 + bcon_sim[0] * ucon_sim[1]) / ucon_sim[0];
+    bcon_sim[2] = (bb2 + bcon_sim[0] * ucon_sim[2]) / ucon_sim[0];
+    bcon_sim[3] = (bb3 + bcon_sim[0] * ucon_sim[3]) / ucon_sim[0];
+    double lb = l[0] * bcon_sim[0] + l[1] * bcon_sim[1] + l[2] * bcon_sim[2] + l[3] * bcon_sim[3];
+    s.b_sq = -bcon_sim[0] * bcon_sim[0] + bcon_sim[1] * bcon_sim[1] + bcon_sim[2] * bcon_sim[2] +
+             bcon_sim[3] * bcon_sim[3] + f * lb * lb;
+  }
+  s.bb_cgs = sqrt(s.b_sq) * P.b_unit;
+  s.sigma = s.b_sq / rho;
+  s.beta_inv = s.b_sq / (2.0 * pgas);
+
+  // electron temperature
+  s.kb_tt_e_cgs = nan("");
+  s.theta_e = nan("");
+  if (P.thermal_frac != 0.0 && P.plasma_model == 0) {
+    double bi2 = s.beta_inv * s.beta_inv;
+    double tti_tte = (P.plasma_rat_high + P.plasma_rat_low * bi2) / (1.0 + bi2);
+    double kb_tt_tot = P.plasma_mu * phys::m_p * s.pgas_cgs / s.rho_cgs;
+    if (P.plasma_use_p) {
+      s.kb_tt_e_cgs = (1.0 + P.plasma_ne_ni) / (tti_tte + P.plasma_ne_ni) * kb_tt_tot;
+    } else {
+      s.kb_tt_e_cgs = (1.0 + P.plasma_ne_ni) * kb_tt_tot / (P.plasma_gamma - 1.0);
+      s.kb_tt_e_cgs /= tti_tte / (P.plasma_gamma_i - 1.0) + P.plasma_ne_ni / (P.plasma_gamma_e - 1.0);
+    }
+    s.theta_e = s.kb_tt_e_cgs / (phys::m_e * phys::c * phys::c);
+  }
+  if (P.thermal_frac != 0.0 && P.plasma_model == 1) {
+    double mu_e = P.plasma_mu * (1.0 + 1.0 / P.plasma_ne_ni);
+    double rho_e = rho * phys::m_e / (mu_e * phys::m_p);
+    double cb = cbrt(rho_e * kappa);
+    s.theta_e = 1.0 / 5.0 * (sqrt(1.0 + 25.0 * cb * cb) - 1.0);
+    s.kb_tt_e_cgs = s.theta_e * phys::m_e * phys::c * phys::c;
+  }
+
+  s.value_cut =
+      (P.cut_rho_min >= 0.0 && s.rho_cgs < P.cut_rho_min) || (P.cut_rho_max >= 0.0 && s.rho_cgs > P.cut_rho_max) ||
+      (P.cut_n_e_min >= 0.0 && s.n_e_cgs < P.cut_n_e_min) || (P.cut_n_e_max >= 0.0 && s.n_e_cgs > P.cut_n_e_max) ||
+      (P.cut_p_gas_min >= 0.0 && s.pgas_cgs < P.cut_p_gas_min) || (P.cut_p_gas_max >= 0.0 && s.pgas_cgs > P.cut_p_gas_max) ||
+      (P.cut_theta_e_min >= 0.0 && s.theta_e < P.cut_theta_e_min) || (P.cut_theta_e_max >= 0.0 && s.theta_e > P.cut_theta_e_max) ||
+      (P.cut_b_min >= 0.0 && s.bb_cgs < P.cut_b_min) || (P.cut_b_max >= 0.0 && s.bb_cgs > P.cut_b_max) ||
+      (P.cut_sigma_min >= 0.0 && s.sigma < P.cut_sigma_min) || (P.cut_sigma_max >= 0.0 && s.sigma > P.cut_sigma_max) ||
+      (P.cut_beta_inverse_min >= 0.0 && s.beta_inv < P.cut_beta_inverse_min) ||
+      (P.cut_beta_inverse_max >= 0.0 && s.beta_inv > P.cut_beta_inverse_max);
+  s.b_zero = bb1 == 0.0 && bb2 == 0.0 && bb3 == 0.0;
+  if (s.value_cut || s.b_zero || !want_vectors) return;
+
+  // to Cartesian Kerr-Schild (CoordinateJacobian, radiation_geometry.cpp:69-126)
+  if (P.coord != 0) {
+    double sth = sqrt(sth2);
+    double rho_cyl = hypot(x, y);
+    double ra = sqrt(r2 + a2);
+    double cx = rho_cyl > 0.0 ? x / rho_cyl : 1.0, cy = rho_cyl > 0.0 ? y / rho_cyl : 0.0;
+    double cph = (cx * r + cy * a) / ra;  // cos(atan2(y,x) - atan(a/r))
+    double sph = (cy * r - cx * a) / ra;
+    double j11 = sth * cph, j12 = cth * (r * cph - a * sph), j13 = sth * (-r * sph - a * cph);
+    double j21 = sth * sph, j22 = cth * (r * sph + a * cph), j23 = sth * (r * cph - a * sph);
+    double j31 = cth, j32 = -r * sth;
+    s.ucon[0] = ucon_sim[0];
+    s.ucon[1] = j11 * ucon_sim[1] + j12 * ucon_sim[2] + j13 * ucon_sim[3];
+    s.ucon[2] = j21 * ucon_sim[1] + j22 * ucon_sim[2] + j23 * ucon_sim[3];
+    s.ucon[3] = j31 * ucon_sim[1] + j32 * ucon_sim[2];
+    s.bcon[0] = bcon_sim[0];
+    s.bcon[1] = j11 * bcon_sim[1] + j12 * bcon_sim[2] + j13 * bcon_sim[3];
+    s.bcon[2] = j21 * bcon_sim[1] + j22 * bcon_sim[2] + j23 * bcon_sim[3];
+    s.bcon[3] = j31 * bcon_sim[1] + j32 * bcon_sim[2];
+  } else {
+    for (int q = 0; q < 4; q++) {
+      s.ucon[q] = ucon_sim[q];
+      s.bcon[q] = bcon_sim[q];
+    }
+  }
+}
+
+__device__ __forceinline__ void cell_values_of(const Plasma &s, double cv[RAD_NUM_CELL_VALUES]) {
+  cv[0] = s.rho_cgs; cv[1] = s.n_e_cgs; cv[2] = s.pgas_cgs; cv[3] = s.theta_e;
+  cv[4] = s.bb_cgs; cv[5] = s.sigma; cv[6] = s.beta_inv;
+}
+
+// Proper length per unit affine parameter, sqrt(g_ij t^i t^j) with t^i the spatial projection of the
+// momentum (unpolarized.cpp:118-130, rendering.cpp:86-99).  kc = covariant momentum.
+__device__ __forceinline__ double proper_length_rate(const RadParams &P, double x, double y, double z,
+                                                     const double kc[4]) {
+  if (P.ray_flat) return sqrt(kc[1] * kc[1] + kc[2] * kc[2] + kc[3] * kc[3]);
+  double a = P.a, a2 = a * a;
+  double r = ks_radius(a, x, y, z), r2 = r * r;
+  double f = 2.0 * r2 * r / (r2 * r2 + a2 * z * z);
+  double l[3] = {(r * x + a * y) / (r2 + a2), (r * y - a * x) / (r2 + a2), z / r};
+  // t_a = (g^{a mu} - g^{0a} g^{0 mu}/g^{00}) k_mu with g^{00} = -(1+f), g^{0a} = f l_a, g^{ab} = delta - f l_a l_b
+  double g00 = -(1.0 + f);
+  double lk = l[0] * kc[1] + l[1] * kc[2] + l[2] * kc[3];
+  double t[3];
+  for (int q = 0; q < 3; q++) {
+    double g0a = f * l[q];
+    double spatial = kc[1 + q] - g0a * lk;                     // g^{ab} k_b
+    double corr = g0a * (f * lk) / g00;                        // g^{0a} g^{0b} k_b / g^{00}
+    t[q] = spatial - corr;                                     // the mu = 0 terms cancel identically
+  }
+  double lt = l[0] * t[0] + l[1] * t[1] + l[2] * t[2];
+  return sqrt(t[0] * t[0] + t[1] * t[1] + t[2] * t[2] + f * lt * lt);
+}
+
+}  // namespace rad

@@ -1,0 +1,114 @@
+// Device-side parameter blocks of the radiation kernels.
+#pragma once
+#include <stdint.h>
+#include "device_types.cuh"
+
+#define RAD_MAX_FREQ 32
+#define RAD_MAX_FEATURES 64
+#define RAD_NUM_CELL_VALUES 7
+
+// CGS constants (reference src/blacklight.hpp:18-27)
+namespace phys {
+constexpr double pi = 3.141592653589793;
+constexpr double sqrt2 = 1.4142135623730951;
+constexpr double c = 2.99792458e10;
+constexpr double h = 6.62607015e-27;
+constexpr double k_b = 1.380649e-16;
+constexpr double m_p = 1.67262192369e-24;
+constexpr double m_e = 9.1093837015e-28;
+constexpr double e = 4.80320425e-10;
+constexpr double gg_msun = 1.32712440018e26;
+}  // namespace phys
+
+// Grid resident in HBM.  Cell primitives are re-laid out at upload from the reader's
+// (var, b, k, j, i) planes into one 32-byte record per cell, so a trilinear gather touches
+// 8 fully used 32-byte sectors instead of 32 quarter-used ones:
+//   cells[2*c + 0] = (rho, pgas, uu1, uu2), cells[2*c + 1] = (uu3, bb1, bb2, bb3),
+//   c = ((b*n_k + k)*n_j + j)*n_i + i
+struct GridDev {
+  int32_t n_b, n_k, n_j, n_i;
+  const double *x1f, *x2f, *x3f;  // (n_b, n+1)
+  const double *x1v, *x2v, *x3v;  // (n_b, n)
+  const double *bounds;           // (n_b, 6): x1min, x1max, x2min, x2max, x3min, x3max
+  const float4 *cells;
+  const float *kappa;             // (n_b, n_k, n_j, n_i) electron entropy, or nullptr
+};
+
+struct RadParams {
+  int32_t model_type, ray_flat, coord, interp;
+  double a, camera_r;
+  double camera_x[4];
+  int32_t num_freq;
+  double freqs[RAD_MAX_FREQ];
+  double x_unit, t_unit;
+  // image selection and slot offsets (reference radiation_integrator.cpp:436-520)
+  int32_t image_light, image_time, image_length, image_lambda, image_emission, image_tau;
+  int32_t image_lambda_ave, image_emission_ave, image_tau_int, image_crossings, polarization;
+  int32_t off_time, off_length, off_lambda, off_emission, off_tau, off_lambda_ave;
+  int32_t off_emission_ave, off_tau_int, off_crossings, num_quantities;
+  int32_t need_cell_values;
+  // units and plasma model
+  double d_unit, e_unit, b_unit;
+  double plasma_mu, plasma_ne_ni;
+  int32_t plasma_model, plasma_use_p;
+  double plasma_gamma, plasma_gamma_i, plasma_gamma_e, plasma_rat_low, plasma_rat_high;
+  double thermal_frac, power_frac, kappa_frac;
+  double plasma_p, plasma_gamma_min, plasma_gamma_max, plasma_kappa, plasma_w;
+  // precomputed distribution constants (reference simulation_coefficients.cpp:53-193)
+  double power_jj, power_aa, power_jj_q, power_jj_v, power_aa_q, power_aa_v;
+  double power_rho, power_rho_q, power_rho_v;
+  double kappa_jj_low, kappa_jj_high, kappa_jj_x_i, kappa_aa_low, kappa_aa_high, kappa_aa_x_i;
+  double kappa_jj_low_q, kappa_jj_low_v, kappa_jj_high_q, kappa_jj_high_v, kappa_jj_x_q, kappa_jj_x_v;
+  double kappa_aa_low_q, kappa_aa_low_v, kappa_aa_high_i, kappa_aa_high_q, kappa_aa_high_v;
+  double kappa_aa_x_q, kappa_aa_x_v, kappa_rho_v, kappa_rho_frac;
+  double kappa_rho_q_low_a, kappa_rho_q_low_b, kappa_rho_q_low_c, kappa_rho_q_low_d, kappa_rho_q_low_e;
+  double kappa_rho_q_high_a, kappa_rho_q_high_b, kappa_rho_q_high_c, kappa_rho_q_high_d, kappa_rho_q_high_e;
+  double kappa_rho_v_low_a, kappa_rho_v_low_b, kappa_rho_v_high_a, kappa_rho_v_high_b;
+  // formula model
+  double formula_r0, formula_h, formula_l0, formula_q, formula_nup, formula_cn0;
+  double formula_alpha, formula_a, formula_beta;
+  // cuts
+  double cut_rho_min, cut_rho_max, cut_n_e_min, cut_n_e_max, cut_p_gas_min, cut_p_gas_max;
+  double cut_theta_e_min, cut_theta_e_max, cut_b_min, cut_b_max, cut_sigma_min, cut_sigma_max;
+  double cut_beta_inverse_min, cut_beta_inverse_max;
+  int32_t cut_omit_near, cut_omit_far, cut_plane;
+  double cut_omit_in, cut_omit_out, cut_midplane_theta, cut_midplane_z;
+  double cut_plane_origin[3], cut_plane_normal[3];
+  // fallback
+  int32_t fallback_nan;
+  float fallback_rho, fallback_pgas, fallback_kappa;
+  // polarized extras
+  int32_t rotation_split;
+  double camera_u_con[4], camera_u_cov[4], camera_vert_con_c[4];
+  // rendering
+  int32_t render_num_images;
+  int32_t render_feature_start[RAD_MAX_FEATURES + 1];
+  int32_t render_quantities[RAD_MAX_FEATURES], render_types[RAD_MAX_FEATURES];
+  double render_min_vals[RAD_MAX_FEATURES], render_max_vals[RAD_MAX_FEATURES];
+  double render_thresh_vals[RAD_MAX_FEATURES], render_tau_scales[RAD_MAX_FEATURES];
+  double render_opacities[RAD_MAX_FEATURES];
+  double render_x_vals[RAD_MAX_FEATURES], render_y_vals[RAD_MAX_FEATURES], render_z_vals[RAD_MAX_FEATURES];
+};
+
+// Optional parity taps, filled in the reference's host layout (source->camera order)
+struct SampleTaps {
+  int32_t *inds;     // (rays_level, S, 4) or nullptr
+  double *fracs;     // (rays_level, S, 3) or nullptr
+  uint8_t *nan_, *cut, *fallback;  // (rays_level, S)
+  int32_t S;
+};
+
+struct RadArgs {
+  const RadParams *P;  // device pointer
+  GridDev grid;
+  StepBuffer sb;
+  const int32_t *sample_num;    // (wave rays)
+  const uint8_t *sample_flags;  // (wave rays)
+  const double *mom_factor;     // (wave rays)
+  int64_t rays;                 // rays in this wave
+  double *image;                // (Q, level_rays) device, already offset to this wave's first ray
+  int64_t image_stride;         // level_rays
+  double *render;               // (R, 3, level_rays) or nullptr, offset likewise
+  SampleTaps taps;              // pointers already offset to this wave's first ray
+  unsigned long long *sample_counter;  // processed (ray, sample) pairs, for roofline accounting
+};

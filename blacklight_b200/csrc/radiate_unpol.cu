@@ -1,0 +1,432 @@
+// Fused sampling -> coefficients -> unpolarized transfer (-> optional rendering) kernel.
+//
+// One ray per thread.  A warp walks its 32 rays' step buffers in lock step from the far end towards
+// the camera (index n descending == the reference's source->camera order after ReverseGeodesics,
+// geodesics.cpp:808-849), so every step-buffer load is a coalesced 256-byte row.  For each sample the
+// thread locates the cell, gathers and interpolates the primitives, evaluates the synchrotron (or
+// formula) coefficients for every frequency and advances the transfer solution -- the reference's
+// sample_*, j_i, alpha_i and cell_values arrays (N x S x ...) are never materialised.
+//
+// Reference: simulation_sampling.cpp:122-1044, simulation_coefficients.cpp:254-701,
+//            formula_coefficients.cpp:25-183, unpolarized.cpp:31-221, rendering.cpp:25-179.
+#include "rad_sample.cuh"
+
+namespace {
+
+constexpr int kBlock = 128;
+
+// Synchrotron emissivity / absorptivity for Stokes I at one frequency
+// (simulation_coefficients.cpp:458-524, :559-585, :608-664; invariant forms j/nu^2, alpha*nu).
+__device__ __forceinline__ void synchrotron_unpolarized(const RadParams &P, const rad::Plasma &s, double nu_cgs,
+                                                        double sin_theta_b, bool need_j, bool need_a,
+                                                        double &j_out, double &a_out) {
+  double nu_2 = nu_cgs * nu_cgs;
+  double nu_c = phys::e * s.bb_cgs / (2.0 * phys::pi * phys::m_e * phys::c);
+  double j_val = 0.0, a_val = 0.0;
+  if (P.thermal_frac != 0.0) {
+    double nu_s = 2.0 / 9.0 * nu_c * s.theta_e * s.theta_e * sin_theta_b;
+    double xx = nu_cgs / nu_s;
+    double xx_1_2 = sqrt(xx);
+    double xx_1_3 = cbrt(xx);
+    double xx_1_6 = sqrt(xx_1_3);
+    double coefficient = P.thermal_frac * s.n_e_cgs * phys::e * phys::e * nu_c / (phys::c * nu_2) * exp(-xx_1_3);
+    double var_a = phys::sqrt2 * phys::pi / 27.0 * sin_theta_b;
+    const double var_b = 1.8877486253633870;  // 2^(11/12)
+    double var_c = xx_1_2 + var_b * xx_1_6;
+    double j_th = coefficient * var_a * var_c * var_c;
+    if (need_j) j_val = j_th;
+    double b_nu_nu_3 = 2.0 * phys::h / (phys::c * phys::c) / expm1(phys::h * nu_cgs / s.kb_tt_e_cgs);
+    if (need_a) {
+      a_val = j_th / b_nu_nu_3;
+      // absorptivities too small to square are flushed (simulation_coefficients.cpp:513-523)
+      if (1.0 / (a_val * a_val) == INFINITY) a_val = 0.0;
+    }
+  }
+  if (P.power_frac != 0.0) {
+    if (need_j) {
+      double var_a = pow(nu_cgs / (nu_c * sin_theta_b), -(P.plasma_p - 1.0) / 2.0);
+      j_val += P.power_frac * s.n_e_cgs * phys::e * phys::e * nu_c / (phys::c * nu_2) * P.power_jj * sin_theta_b * var_a;
+    }
+    if (need_a) {
+      double var_a = pow(nu_cgs / (nu_c * sin_theta_b), -(P.plasma_p + 2.0) / 2.0);
+      a_val += P.power_frac * s.n_e_cgs * phys::e * phys::e / (phys::m_e * phys::c) * P.power_aa * var_a;
+    }
+  }
+  if (P.kappa_frac != 0.0) {
+    double nu_kappa = nu_c * P.plasma_w * P.plasma_w * P.plasma_kappa * P.plasma_kappa * sin_theta_b;
+    double xx = nu_cgs / nu_kappa;
+    if (need_j) {
+      double var_a = P.kappa_frac * s.n_e_cgs * phys::e * phys::e * nu_c / (phys::c * nu_2);
+      double var_b = cbrt(xx) * sin_theta_b;
+      double var_c = pow(xx, -(P.plasma_kappa - 2.0) / 2.0) * sin_theta_b;
+      double lo = P.kappa_jj_low * var_a * var_b;
+      double hi = P.kappa_jj_high * var_a * var_c;
+      j_val += pow(pow(lo, -P.kappa_jj_x_i) + pow(hi, -P.kappa_jj_x_i), -1.0 / P.kappa_jj_x_i);
+    }
+    if (need_a) {
+      double var_a = P.kappa_frac * s.n_e_cgs * phys::e * phys::e / (phys::m_e * phys::c);
+      double var_b = pow(xx, -2.0 / 3.0);
+      double var_c = pow(xx, -(1.0 + P.plasma_kappa) / 2.0);
+      double lo = P.kappa_aa_low * var_a * var_b;
+      double hi = P.kappa_aa_high * var_a * var_c * P.kappa_aa_high_i;
+      a_val += pow(pow(lo, -P.kappa_aa_x_i) + pow(hi, -P.kappa_aa_x_i), -1.0 / P.kappa_aa_x_i);
+    }
+  }
+  j_out = j_val;
+  a_out = a_val;
+}
+
+// Analytic "formula" plasma of the 2020 ApJ 897 148 code comparison (formula_coefficients.cpp:121-179):
+// fluid velocity from a Keplerian-like angular momentum profile in Boyer-Lindquist coordinates,
+// Gaussian density, power-law emissivity / absorptivity.  Returns u^mu in CKS and n/n0.
+__device__ __forceinline__ void formula_fluid(const RadParams &P, double x, double y, double z, double r,
+                                              double ucon[4], double &n_n0) {
+  const double a = P.a;
+  double rr = sqrt(r * r - z * z);
+  double cth = z / r;
+  double sth = sqrt(1.0 - cth * cth);
+  double ph = atan2(y, x) - atan(a / r);
+  double sph, cph;
+  sincos(ph, &sph, &cph);
+  double delta = r * r - 2.0 * r + a * a;
+  double sigma = r * r + a * a * cth * cth;
+  double gtt = -(1.0 + 2.0 * r * (r * r + a * a) / (delta * sigma));
+  double gtph = -2.0 * a * r / (delta * sigma);
+  double gphph = (sigma - 2.0 * r) / (delta * sigma * sth * sth);
+  double ll = P.formula_l0 / (1.0 + rr) * pow(rr, 1.0 + P.formula_q);
+  double u_norm = 1.0 / sqrt(-gtt + 2.0 * gtph * ll - gphph * ll * ll);
+  double u_t = -u_norm, u_ph = u_norm * ll;
+  double ut = gtt * u_t + gtph * u_ph;
+  double uph = gtph * u_t + gphph * u_ph;
+  // u^r = u^theta = 0 in Boyer-Lindquist, so the KS and CKS transformations reduce to the phi column
+  ucon[0] = ut;
+  ucon[1] = sth * (-r * sph - a * cph) * uph;
+  ucon[2] = sth * (r * cph - a * sph) * uph;
+  ucon[3] = 0.0;
+  n_n0 = exp(-0.5 * (r * r / (P.formula_r0 * P.formula_r0) + P.formula_h * P.formula_h * cth * cth));
+}
+
+__device__ __forceinline__ void render_update(const RadParams &P, double *render, int64_t stride,
+                                              const double prev[RAD_NUM_CELL_VALUES],
+                                              const double cur[RAD_NUM_CELL_VALUES], double delta_length) {
+  for (int im = 0; im < P.render_num_images; im++) {
+    double *px = render + (size_t)(3 * im) * stride;
+    double cx = px[0], cy = px[stride], cz = px[2 * stride];
+    bool touched = false;
+    for (int f = P.render_feature_start[im]; f < P.render_feature_start[im + 1]; f++) {
+      int q = P.render_quantities[f];
+      int type = P.render_types[f];
+      double pv = prev[q], cv = cur[q];
+      if (type == 0 && cv >= P.render_min_vals[f] && cv <= P.render_max_vals[f]) {
+        double delta_tau = delta_length / P.render_tau_scales[f];
+        if (delta_tau <= 100.0) {
+          double en = exp(-delta_tau), em = expm1(delta_tau);
+          cx = en * (cx + P.render_x_vals[f] * em);
+          cy = en * (cy + P.render_y_vals[f] * em);
+          cz = en * (cz + P.render_z_vals[f] * em);
+        } else {
+          cx = P.render_x_vals[f];
+          cy = P.render_y_vals[f];
+          cz = P.render_z_vals[f];
+        }
+        touched = true;
+      }
+      bool crossed = false;
+      double th = P.render_thresh_vals[f];
+      if ((type == 1 || type == 2) && pv < th && cv >= th) crossed = true;
+      if ((type == 1 || type == 3) && pv > th && cv <= th) crossed = true;
+      if (crossed) {
+        double op = P.render_opacities[f];
+        cx = (1.0 - op) * cx + op * P.render_x_vals[f];
+        cy = (1.0 - op) * cy + op * P.render_y_vals[f];
+        cz = (1.0 - op) * cz + op * P.render_z_vals[f];
+        touched = true;
+      }
+    }
+    if (touched) {
+      px[0] = cx;
+      px[stride] = cy;
+      px[2 * stride] = cz;
+    }
+  }
+}
+
+template <int FMAX, bool SIM>
+__global__ void __launch_bounds__(kBlock) radiate_unpolarized_kernel(RadArgs A) {
+  extern __shared__ double smem_bounds[];
+  const RadParams &P = *A.P;
+  const GridDev &G = A.grid;
+  const double *bounds_s = nullptr;
+  if (SIM) {
+    // stage block bounds in shared memory when they fit (6 doubles per mesh block)
+    int nb6 = G.n_b * 6;
+    if ((size_t)nb6 * sizeof(double) <= 48 * 1024) {
+      for (int t = threadIdx.x; t < nb6; t += blockDim.x) smem_bounds[t] = G.bounds[t];
+      __syncthreads();
+      bounds_s = smem_bounds;
+    }
+  }
+  const unsigned full = 0xffffffffu;
+  int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool valid = m < A.rays;
+  int num = valid ? A.sample_num[m] : 0;
+  bool flagged = valid ? A.sample_flags[m] != 0 : false;
+  double mom = valid ? A.mom_factor[m] : 1.0;
+  int warp_max = num;
+  for (int off = 16; off > 0; off >>= 1) {
+    int o = __shfl_xor_sync(full, warp_max, off);
+    warp_max = o > warp_max ? o : warp_max;
+  }
+
+  const int F = P.num_freq;
+  double I[FMAX];
+#pragma unroll
+  for (int l = 0; l < FMAX; l++) I[l] = 0.0;
+  double *img = A.image + m;  // quantity q of this ray at img[q * stride]
+  const int64_t stride = A.image_stride;
+  const bool aux = P.image_time || P.image_length || P.image_lambda || P.image_emission || P.image_tau ||
+                   P.image_lambda_ave || P.image_emission_ave || P.image_tau_int || P.image_crossings;
+  const bool need_j = P.image_light || P.image_emission || P.image_emission_ave;
+  const bool need_a = P.image_light || P.image_tau || P.image_tau_int;
+  const bool want_coeff = P.image_light || P.image_emission || P.image_tau || P.image_emission_ave || P.image_tau_int;
+  const bool do_render = SIM && A.render != nullptr && P.render_num_images > 0;
+  bool fill_present = false;
+  if (do_render)
+    for (int f = 0; f < P.render_feature_start[P.render_num_images]; f++)
+      if (P.render_types[f] == 0) fill_present = true;
+
+  // zero the auxiliary slots this thread owns (image[] is accumulated in place for them)
+  if (valid && aux)
+    for (int q = P.image_light ? F : 0; q < P.num_quantities; q++) img[(size_t)q * stride] = 0.0;
+  if (valid && do_render)
+    for (int q = 0; q < 3 * P.render_num_images; q++) A.render[m + (size_t)q * stride] = 0.0;
+
+  double int_lambda[FMAX], int_emission[FMAX];
+#pragma unroll
+  for (int l = 0; l < FMAX; l++) int_lambda[l] = int_emission[l] = 0.0;
+  bool plane_sign = false;
+  int crossings = 0;
+  if (valid && num > 0 && P.image_crossings) {
+    // reference looks at sample 0 of the reversed array == our last stored sample
+    const double *p0 = A.sb.buf + A.sb.at(1, num - 1, m);
+    size_t cs = (size_t)A.sb.cap * (size_t)A.sb.rays;
+    plane_sign = P.camera_x[1] * p0[0] + P.camera_x[2] * p0[cs] + P.camera_x[3] * p0[2 * cs] > 0.0;
+  }
+  double prev_cv[RAD_NUM_CELL_VALUES];
+  for (int q = 0; q < RAD_NUM_CELL_VALUES; q++) prev_cv[q] = nan("");
+  int b_cache = 0;
+  unsigned long long processed = 0;
+  const size_t cs = (size_t)A.sb.cap * (size_t)A.sb.rays;
+
+  for (int n = warp_max - 1; n >= 0; n--) {
+    if (n >= num) continue;
+    processed++;
+    const double *src = A.sb.buf + A.sb.at(0, n, m);
+    double t = src[0], x = src[cs], y = src[2 * cs], z = src[3 * cs];
+    double kc[4] = {src[4 * cs], src[5 * cs], src[6 * cs], src[7 * cs]};
+    double dlam = -src[8 * cs];
+    int n_ref = num - 1 - n;  // index in the reference's reversed arrays (taps only)
+
+    double r = rad::ks_radius(P.a, x, y, z);
+    double omega = 0.0;      // -k_mu u^mu
+    double sin_theta_b = 0.0;
+    bool coupled = false;    // coefficients are nonzero candidates
+    bool nan_sample = false;
+    rad::Plasma ps;
+    double cv[RAD_NUM_CELL_VALUES];
+    for (int q = 0; q < RAD_NUM_CELL_VALUES; q++) cv[q] = nan("");
+    double n_n0 = 0.0;
+
+    if (SIM) {
+      rad::SampleStatus st;
+      rad::Prims pr;
+      rad::SampleIndex si;
+      si.b = si.k = si.j = si.i = -1;
+      si.fk = si.fj = si.fi = 0.0;
+      if (P.fallback_nan && flagged)
+        st = rad::kSampleNan;
+      else if (rad::geometric_cut(P, x, y, z, r))
+        st = rad::kSampleCut;
+      else
+        st = rad::sample_grid(P, G, bounds_s, x, y, z, r, b_cache, pr, si);
+      if (A.taps.nan_) {
+        size_t ti = (size_t)m * A.taps.S + n_ref;
+        A.taps.nan_[ti] = st == rad::kSampleNan;
+        A.taps.cut[ti] = st == rad::kSampleCut;
+        A.taps.fallback[ti] = st == rad::kSampleFallback;
+        if (A.taps.inds) {
+          A.taps.inds[4 * ti + 0] = si.b; A.taps.inds[4 * ti + 1] = si.k;
+          A.taps.inds[4 * ti + 2] = si.j; A.taps.inds[4 * ti + 3] = si.i;
+        }
+        if (A.taps.fracs) {
+          A.taps.fracs[3 * ti + 0] = si.fk; A.taps.fracs[3 * ti + 1] = si.fj; A.taps.fracs[3 * ti + 2] = si.fi;
+        }
+      }
+      if (st == rad::kSampleNan) {
+        float qn = nanf("");
+        pr.rho = pr.pgas = pr.kappa = pr.uu1 = pr.uu2 = pr.uu3 = pr.bb1 = pr.bb2 = pr.bb3 = qn;
+      } else if (st == rad::kSampleFallback) {
+        pr.rho = P.fallback_rho; pr.pgas = P.fallback_pgas; pr.kappa = P.fallback_kappa;
+        pr.uu1 = pr.uu2 = pr.uu3 = pr.bb1 = pr.bb2 = pr.bb3 = 0.0f;
+      }
+      if (st != rad::kSampleCut) {
+        rad::plasma_state(P, x, y, z, r, pr, want_coeff, ps);
+        if (!ps.value_cut) {
+          if (P.need_cell_values) rad::cell_values_of(ps, cv);
+          if (want_coeff && !ps.b_zero) {
+            omega = -(kc[0] * ps.ucon[0] + kc[1] * ps.ucon[1] + kc[2] * ps.ucon[2] + kc[3] * ps.ucon[3]);
+            double kb = kc[0] * ps.bcon[0] + kc[1] * ps.bcon[1] + kc[2] * ps.bcon[2] + kc[3] * ps.bcon[3];
+            // fluid-frame pitch angle: |k_spatial| = omega and |b| = sqrt(b^2) in the frame of u
+            double c2 = kb * kb / (omega * omega * ps.b_sq);
+            c2 = 1.0 < c2 ? 1.0 : c2;
+            sin_theta_b = sqrt(1.0 - c2);
+            coupled = true;
+            nan_sample = st == rad::kSampleNan;
+          }
+        }
+      }
+    } else {
+      // formula model: flagged rays are NaN in frequency slot 0 only (formula_coefficients.cpp:51-59)
+      if (P.fallback_nan && flagged) {
+        nan_sample = true;
+        coupled = true;
+      } else if (!rad::geometric_cut(P, x, y, z, r)) {
+        double ucon[4];
+        formula_fluid(P, x, y, z, r, ucon, n_n0);
+        omega = -(ucon[0] * kc[0] + ucon[1] * kc[1] + ucon[2] * kc[2] + ucon[3] * kc[3]);
+        coupled = true;
+      }
+    }
+    (void)nan_sample;
+
+    // per-sample auxiliary quantities that do not depend on frequency
+    if (aux) {
+      if (P.image_time) {
+        double t_cgs = t * P.t_unit;
+        double cur = img[(size_t)P.off_time * stride];
+        img[(size_t)P.off_time * stride] = t_cgs < cur ? t_cgs : cur;
+      }
+      if (P.image_length)
+        img[(size_t)P.off_length * stride] += rad::proper_length_rate(P, x, y, z, kc) * dlam * P.x_unit;
+      if (P.image_crossings) {
+        bool sign_new = P.camera_x[1] * x + P.camera_x[2] * y + P.camera_x[3] * z > 0.0;
+        if (sign_new != plane_sign) crossings++;
+        plane_sign = sign_new;
+      }
+    }
+    if (do_render) {
+      double dlen = fill_present ? rad::proper_length_rate(P, x, y, z, kc) * dlam * P.x_unit : 0.0;
+      render_update(P, A.render + m, stride, prev_cv, cv, dlen);
+      for (int q = 0; q < RAD_NUM_CELL_VALUES; q++) prev_cv[q] = cv[q];
+    }
+
+    // frequencies
+#pragma unroll
+    for (int l = 0; l < FMAX; l++) {
+      if (l >= F) break;
+      double freq = P.freqs[l];
+      double dlam_cgs = dlam * P.x_unit / (freq * mom);
+      double j = 0.0, alpha = 0.0;
+      if (coupled) {
+        if (SIM) {
+          synchrotron_unpolarized(P, ps, omega * freq * mom, sin_theta_b, need_j, need_a, j, alpha);
+        } else if (P.fallback_nan && flagged) {
+          if (l == 0) j = alpha = nan("");
+        } else {
+          double nu = omega * freq * mom;
+          double jn = P.formula_cn0 * n_n0 * pow(nu / P.formula_nup, -P.formula_alpha);
+          j = jn / (nu * nu);
+          double an = P.formula_a * P.formula_cn0 * n_n0 * pow(nu / P.formula_nup, -P.formula_beta - P.formula_alpha);
+          alpha = an * nu;
+        }
+      }
+      if (!need_j) j = nan("");
+      if (!need_a) alpha = nan("");
+      double delta_tau = alpha * dlam_cgs;
+      bool thin = delta_tau <= 100.0;
+      double exp_neg = 0.0, em1 = 0.0;
+      if (alpha > 0.0 || P.image_tau_int) {
+        exp_neg = exp(-delta_tau);
+        em1 = expm1(delta_tau);
+      }
+      if (P.image_light) {
+        if (alpha > 0.0) {
+          double ss = j / alpha;
+          I[l] = thin ? exp_neg * (I[l] + ss * em1) : ss;
+        } else {
+          I[l] += j * dlam_cgs;
+        }
+      }
+      if (aux) {
+        if (P.image_lambda || P.image_lambda_ave) int_lambda[l] += dlam_cgs;
+        if (P.image_emission || P.image_emission_ave) int_emission[l] += j * dlam_cgs;
+        if (P.image_tau) img[(size_t)(P.off_tau + l) * stride] += delta_tau;
+        bool have_cv = SIM && !isnan(cv[0]);
+        if (P.image_lambda_ave && have_cv)
+          for (int q = 0; q < RAD_NUM_CELL_VALUES; q++)
+            img[(size_t)(P.off_lambda_ave + l * RAD_NUM_CELL_VALUES + q) * stride] += cv[q] * dlam_cgs;
+        if (P.image_emission_ave && have_cv)
+          for (int q = 0; q < RAD_NUM_CELL_VALUES; q++)
+            img[(size_t)(P.off_emission_ave + l * RAD_NUM_CELL_VALUES + q) * stride] += cv[q] * j * dlam_cgs;
+        if (P.image_tau_int && have_cv)
+          for (int q = 0; q < RAD_NUM_CELL_VALUES; q++) {
+            double *dst = img + (size_t)(P.off_tau_int + l * RAD_NUM_CELL_VALUES + q) * stride;
+            *dst = thin ? exp_neg * (*dst + cv[q] * em1) : cv[q];
+          }
+      }
+    }
+  }
+
+  if (valid) {
+    if (P.image_light)
+#pragma unroll
+      for (int l = 0; l < FMAX; l++) {
+        if (l >= F) break;
+        double f = P.freqs[l];
+        img[(size_t)l * stride] = I[l] * (f * f * f);
+      }
+    if (aux) {
+#pragma unroll
+      for (int l = 0; l < FMAX; l++) {
+        if (l >= F) break;
+        if (P.image_lambda) img[(size_t)(P.off_lambda + l) * stride] = int_lambda[l];
+        if (P.image_emission) img[(size_t)(P.off_emission + l) * stride] = int_emission[l];
+        if (P.image_lambda_ave)
+          for (int q = 0; q < RAD_NUM_CELL_VALUES; q++)
+            img[(size_t)(P.off_lambda_ave + l * RAD_NUM_CELL_VALUES + q) * stride] /= int_lambda[l];
+        if (P.image_emission_ave)
+          for (int q = 0; q < RAD_NUM_CELL_VALUES; q++)
+            img[(size_t)(P.off_emission_ave + l * RAD_NUM_CELL_VALUES + q) * stride] /= int_emission[l];
+      }
+      if (P.image_crossings) img[(size_t)P.off_crossings * stride] = (double)crossings;
+    }
+  }
+  if (A.sample_counter) {
+    for (int off = 16; off > 0; off >>= 1) processed += __shfl_down_sync(full, processed, off);
+    if ((threadIdx.x & 31) == 0 && processed) atomicAdd(A.sample_counter, processed);
+  }
+}
+
+template <int FMAX>
+cudaError_t launch_fmax(const RadArgs &A, bool sim, int n_b, cudaStream_t stream) {
+  unsigned grid = (unsigned)((A.rays + kBlock - 1) / kBlock);
+  size_t smem = 0;
+  if (sim && (size_t)n_b * 6 * sizeof(double) <= 48 * 1024) smem = (size_t)n_b * 6 * sizeof(double);
+  if (sim)
+    radiate_unpolarized_kernel<FMAX, true><<<grid, kBlock, smem, stream>>>(A);
+  else
+    radiate_unpolarized_kernel<FMAX, false><<<grid, kBlock, 0, stream>>>(A);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+extern "C" cudaError_t bl_launch_radiate_unpolarized(const RadArgs *args, int num_freq, int simulation,
+                                                     cudaStream_t stream) {
+  if (args->rays <= 0) return cudaSuccess;
+  int n_b = args->grid.n_b;
+  if (num_freq <= 1) return launch_fmax<1>(*args, simulation != 0, n_b, stream);
+  if (num_freq <= 4) return launch_fmax<4>(*args, simulation != 0, n_b, stream);
+  if (num_freq <= 12) return launch_fmax<12>(*args, simulation != 0, n_b, stream);
+  return launch_fmax<RAD_MAX_FREQ>(*args, simulation != 0, n_b, stream);
+}

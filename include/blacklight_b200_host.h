@@ -1,0 +1,42 @@
+/* blacklight_b200 host layer -- C entry points above the kernel ABI (blacklight_b200.h):
+ * the reference's .input parameter surface, its camera construction and its main loop, re-hosted.
+ *   blh_config_from_input   <- InputReader::Read + the two integrator constructors
+ *                              (input_reader.cpp:72, geodesic_integrator.cpp:23, radiation_integrator.cpp:26)
+ *   blh_camera_root/refined <- GeodesicIntegrator::InitializeCamera / AugmentCamera (camera.cpp:27,426)
+ *   blh_run_input_file      <- main (blacklight.cpp:31-273)
+ * All functions return 0 on success (or a count where stated); blh_last_error() gives the message,
+ * which for user errors is the reference's own text. */
+#ifndef BLACKLIGHT_B200_HOST_H_
+#define BLACKLIGHT_B200_HOST_H_
+
+#include "blacklight_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct blh_config blh_config;
+
+const char *blh_last_error(void);
+int blh_config_from_input(const char *path, blh_config **out);
+void blh_config_free(blh_config *cfg);
+const bl_params *blh_config_params(const blh_config *cfg);   /* owned by cfg; camera frame filled in */
+int blh_config_num_runs(const blh_config *cfg);
+/* B200 knobs of bl_params: CUDA device ordinal and rays per wave (0 = sized from free HBM) */
+void blh_config_set_device(blh_config *cfg, int device, int64_t tile_rays);
+/* cam_x, u_con, u_cov, norm_con, norm_con_c, hor_con_c, vert_con_c: 7 x 4 doubles */
+int blh_camera_frame(const blh_config *cfg, double out[28]);
+/* pos, dir: (res*res,4); factor: (res*res).  Returns the number of rays. */
+int64_t blh_camera_root(const blh_config *cfg, double *pos, double *dir, double *factor);
+/* Children of the flagged parents.  Output buffers sized for 4 * (#flags set) blocks of
+ * adaptive_block_size^2 pixels (any may be NULL to query the count).  Returns the number of child blocks. */
+int64_t blh_camera_refined(const blh_config *cfg, int level, const int32_t *parent_locs, const uint8_t *flags,
+                           int64_t num_parents, int32_t *child_locs, double *pos, double *dir, double *factor);
+/* timings: total, geodesic, read, sample, image, render [s]; gpu geodesic, radiation, refine [ms];
+ * rays, samples, reserved */
+int blh_run_input_file(const char *path, int device, int quiet, double timings[12]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

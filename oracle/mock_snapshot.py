@@ -1,0 +1,257 @@
+"""Synthetic GRMHD snapshots for the parity tests and bench (TEST INFRASTRUCTURE, not shipped).
+
+Restates the closed-form disk model of the reference's benchmark-input generator
+(reference scripts/generate_mock_simulation.py:24-77, defaults :346-425) -- a power-law torus in
+spherical Kerr-Schild coordinates with an m=4 perturbation, Keplerian-like u^phi, vertical + toroidal
+field -- and writes it as an Athena++ `.athdf` file with a numpy-only HDF5 writer (no h5py in this
+image).  The file layout is the subset the reference's own parser accepts (SURVEY.md Appendix C:
+superblock v0, symbol-table root group, v1 object headers, contiguous float32/int datasets).
+
+The same arrays are returned in the host layout the C ABI's bl_grid_view expects, so the CUDA path and
+the reference binary see identical inputs.  `blocks=(nb_r, nb_th, nb_ph)` re-partitions the same cells
+into several MeshBlocks (all level 0) to exercise the block search.
+"""
+import struct
+
+import numpy as np
+
+
+def mock_fields(n_r=77, n_th=64, n_ph=128, pert_amp=0.1, pert_n_r=3.0, pert_n_th=2.0, pert_n_ph=4,
+                r_min=None, r_max=None):
+    """Face/centre coordinates and primitives of the mock torus (float64, (ph, th, r) order)."""
+    if r_min is None:
+        r_min = 2.0 * 25.0 ** (-1.0 / 75.0)
+    if r_max is None:
+        r_max = 2.0 * 25.0 ** (76.0 / 75.0)
+    rho_amp, rho_r_power, rho_th_scale, rho_floor = 1.0, 0.5, np.pi / 8.0, 1.0e-8
+    pgas_amp, pgas_r_power, pgas_th_scale, pgas_floor = 0.1, 1.25, np.pi / 8.0, 1.0e-9
+    r_isco = 6.0
+    omega_isco = r_isco ** -1.5
+    gamma_isco = (1.0 - 2.0 / r_isco - r_isco ** 2 * omega_isco ** 2) ** -0.5
+    uph_r_power = 1.5
+    uph_amp = gamma_isco * omega_isco * r_isco ** uph_r_power
+    uph_th_scale = np.pi / 8.0
+    bph_amp, bph_r_power, bph_th_scale = 0.2, 1.75, np.pi / 8.0
+    bz_amp, bz_rr_power = 0.02, 0.625
+    cut_r_min, cut_r_max, cut_th_min = 2.0, 50.0, np.pi / 16.0
+
+    rf = np.exp(np.linspace(np.log(r_min), np.log(r_max), n_r + 1))
+    thf = np.linspace(0.0, np.pi, n_th + 1)
+    phf = np.linspace(0.0, 2.0 * np.pi, n_ph + 1)
+    r = 0.5 * (rf[:-1] + rf[1:])
+    th = 0.5 * (thf[:-1] + thf[1:])
+    ph = 0.5 * (phf[:-1] + phf[1:])
+    R, TH, PH = r[None, None, :], th[None, :, None], ph[:, None, None]
+
+    inside = (np.where((r < cut_r_min) | (r > cut_r_max), 0.0, 1.0)[None, None, :]
+              * np.where((th < cut_th_min) | (th > np.pi - cut_th_min), 0.0, 1.0)[None, :, None]
+              * np.ones_like(ph)[:, None, None])
+    wave_r = np.cos(2.0 * np.pi * pert_n_r * np.log(r / cut_r_min) / np.log(cut_r_max / cut_r_min))
+    wave_th = -np.cos(2.0 * np.pi * pert_n_th * (th - cut_th_min) / (np.pi - 2.0 * cut_th_min))
+    wave_ph = np.cos(pert_n_ph * ph)
+    pert = 1.0 + pert_amp * wave_r[None, None, :] * wave_th[None, :, None] * wave_ph[:, None, None]
+    off = np.abs(TH - np.pi / 2.0)
+
+    rho = np.maximum(rho_amp * R ** -rho_r_power * np.exp(-off / rho_th_scale) * pert * inside, rho_floor)
+    pgas = np.maximum(pgas_amp * R ** -pgas_r_power * np.exp(-off / pgas_th_scale) * pert ** 2 * inside, pgas_floor)
+    uur = np.zeros_like(rho)
+    uuth = np.zeros_like(rho)
+    uuph = uph_amp * R ** -uph_r_power * np.exp(-off / uph_th_scale) * inside
+    cyl = np.maximum(R * np.sin(TH), cut_r_min)
+    bbz = bz_amp * cyl ** -bz_rr_power
+    bbr = np.cos(TH) * bbz * np.ones_like(PH)
+    bbth = -np.sin(TH) / R * bbz * np.ones_like(PH)
+    bbph = bph_amp * R ** -bph_r_power * np.exp(-off / bph_th_scale) * np.ones_like(PH)
+    bbph = bbph * np.where(th > np.pi / 2.0, -1.0, 1.0)[None, :, None]
+    prim = np.stack([rho, pgas, uur, uuth, uuph, bbr, bbth, bbph]).astype(np.float32)  # (8, ph, th, r)
+    return dict(rf=rf, thf=thf, phf=phf, r=r, th=th, ph=ph, prim=prim)
+
+
+def to_blocks(fields, blocks=(1, 1, 1)):
+    """Partition the single-block mock into nb_r x nb_th x nb_ph MeshBlocks (level 0).
+
+    Returns the arrays the Athena++ reader produces: float32 coordinates, prim (8, n_b, n_k, n_j, n_i).
+    Block order: x3 slowest, then x2, then x1 (Athena++ Z-order is not needed by either code)."""
+    nb_r, nb_th, nb_ph = blocks
+    prim = fields['prim']
+    n_ph, n_th, n_r = prim.shape[1:]
+    assert n_r % nb_r == 0 and n_th % nb_th == 0 and n_ph % nb_ph == 0
+    n_i, n_j, n_k = n_r // nb_r, n_th // nb_th, n_ph // nb_ph
+    n_b = nb_r * nb_th * nb_ph
+    out = dict(n_b=n_b, n_i=n_i, n_j=n_j, n_k=n_k)
+    out['x1f'] = np.empty((n_b, n_i + 1), np.float32)
+    out['x2f'] = np.empty((n_b, n_j + 1), np.float32)
+    out['x3f'] = np.empty((n_b, n_k + 1), np.float32)
+    out['x1v'] = np.empty((n_b, n_i), np.float32)
+    out['x2v'] = np.empty((n_b, n_j), np.float32)
+    out['x3v'] = np.empty((n_b, n_k), np.float32)
+    out['prim'] = np.empty((8, n_b, n_k, n_j, n_i), np.float32)
+    out['levels'] = np.zeros(n_b, np.int32)
+    out['locations'] = np.zeros((n_b, 3), np.int64)
+    b = 0
+    for bk in range(nb_ph):
+        for bj in range(nb_th):
+            for bi in range(nb_r):
+                si, sj, sk = slice(bi * n_i, (bi + 1) * n_i), slice(bj * n_j, (bj + 1) * n_j), slice(bk * n_k, (bk + 1) * n_k)
+                out['x1f'][b] = fields['rf'][bi * n_i:(bi + 1) * n_i + 1]
+                out['x2f'][b] = fields['thf'][bj * n_j:(bj + 1) * n_j + 1]
+                out['x3f'][b] = fields['phf'][bk * n_k:(bk + 1) * n_k + 1]
+                out['x1v'][b] = fields['r'][si]
+                out['x2v'][b] = fields['th'][sj]
+                out['x3v'][b] = fields['ph'][sk]
+                out['prim'][:, b] = prim[:, sk, sj, si]
+                out['locations'][b] = (bi, bj, bk)
+                b += 1
+    out['root_size'] = (n_r, n_th, n_ph)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# numpy-only HDF5 writer (superblock v0, one root group with a symbol table, contiguous datasets)
+
+_UNDEF = 0xFFFFFFFFFFFFFFFF
+
+
+def _pad8(b):
+    return b + b'\0' * (-len(b) % 8)
+
+
+def _datatype(dtype):
+    dtype = np.dtype(dtype)
+    if dtype.kind == 'i':
+        return struct.pack('<BBBBI', 0x10, 0x08, 0, 0, dtype.itemsize) + struct.pack('<HH', 0, 8 * dtype.itemsize)
+    if dtype.kind == 'f' and dtype.itemsize == 4:
+        return struct.pack('<BBBBI', 0x11, 0x20, 31, 0, 4) + struct.pack('<HHBBBBI', 0, 32, 23, 8, 0, 23, 127)
+    if dtype.kind == 'S':
+        return struct.pack('<BBBBI', 0x13, 0, 0, 0, dtype.itemsize)
+    raise ValueError(dtype)
+
+
+def _dataspace(shape):
+    return struct.pack('<BBB5x', 1, len(shape), 0) + b''.join(struct.pack('<Q', n) for n in shape)
+
+
+def _message(mtype, body):
+    body = _pad8(body)
+    return struct.pack('<HHB3x', mtype, len(body), 0) + body
+
+
+def _object_header(messages):
+    body = b''.join(messages)
+    return struct.pack('<BBHII4x', 1, 0, len(messages), 1, len(body)) + body
+
+
+def _attribute(name, value):
+    value = np.asarray(value)
+    nm = name.encode() + b'\0'
+    dt, ds = _datatype(value.dtype), _dataspace(value.shape)
+    body = struct.pack('<BBHHH', 1, 0, len(nm), len(dt), len(ds)) + _pad8(nm) + _pad8(dt) + _pad8(ds) + value.tobytes()
+    return _message(12, body)
+
+
+def write_athdf(path, grid, time=0.0):
+    """Write `grid` (output of to_blocks) as an Athena++ .athdf file."""
+    n_b = grid['n_b']
+    datasets = [
+        ('B', grid['prim'][5:8]), ('Levels', grid['levels']), ('LogicalLocations', grid['locations']),
+        ('prim', grid['prim'][0:5]), ('x1f', grid['x1f']), ('x1v', grid['x1v']), ('x2f', grid['x2f']),
+        ('x2v', grid['x2v']), ('x3f', grid['x3f']), ('x3v', grid['x3v'])]
+    n_r, n_th, n_ph = grid['root_size']
+    attrs = [
+        _attribute('NumCycles', np.int32(0)), _attribute('Time', np.float32(time)),
+        _attribute('Coordinates', np.array(b'kerr-schild', dtype='S11')),
+        _attribute('RootGridSize', np.array([n_r, n_th, n_ph], np.int32)),
+        _attribute('NumMeshBlocks', np.int32(n_b)),
+        _attribute('MeshBlockSize', np.array([grid['n_i'], grid['n_j'], grid['n_k']], np.int32)),
+        _attribute('MaxLevel', np.int32(0)), _attribute('NumVariables', np.array([5, 3], np.int32)),
+        _attribute('DatasetNames', np.array([b'prim', b'B'], dtype='S21')),
+        _attribute('VariableNames', np.array([b'rho', b'press', b'vel1', b'vel2', b'vel3', b'Bcc1', b'Bcc2', b'Bcc3'], dtype='S21'))]
+
+    # layout: [superblock 96][root header][heap header 32][heap data][TREE][SNOD][dataset headers][data]
+    heap_data = b'\0' * 8
+    name_offsets = []
+    for name, _ in datasets:
+        name_offsets.append(len(heap_data))
+        heap_data += _pad8(name.encode() + b'\0')
+    root_header_size = len(_object_header(attrs + [_message(17, struct.pack('<QQ', 0, 0))]))
+    root_addr = 96
+    heap_addr = root_addr + root_header_size
+    heap_data_addr = heap_addr + 32
+    tree_addr = heap_data_addr + len(heap_data)
+    tree = b'TREE' + struct.pack('<BBHQQ', 0, 0, 1, _UNDEF, _UNDEF)
+    snod_addr = tree_addr + len(tree) + 24
+    tree += struct.pack('<QQQ', 0, snod_addr, name_offsets[-1])
+    snod_size = 8 + 40 * len(datasets)
+    header_addr = snod_addr + snod_size
+    headers, header_addrs = [], []
+    # dataset headers have a fixed size given rank, so compute them twice (addresses, then final)
+    sizes = []
+    for name, arr in datasets:
+        arr = np.ascontiguousarray(arr)
+        h = _object_header([_message(1, _dataspace(arr.shape)), _message(3, _datatype(arr.dtype)),
+                            _message(8, struct.pack('<BBQQ', 3, 1, 0, arr.nbytes))])
+        sizes.append(len(h))
+    pos = header_addr
+    for s in sizes:
+        header_addrs.append(pos)
+        pos += s
+    data_addrs = []
+    for name, arr in datasets:
+        pos += -pos % 8
+        data_addrs.append(pos)
+        pos += np.ascontiguousarray(arr).nbytes
+    eof = pos
+    for (name, arr), daddr in zip(datasets, data_addrs):
+        arr = np.ascontiguousarray(arr)
+        headers.append(_object_header([_message(1, _dataspace(arr.shape)), _message(3, _datatype(arr.dtype)),
+                                       _message(8, struct.pack('<BBQQ', 3, 1, daddr, arr.nbytes))]))
+    snod = b'SNOD' + struct.pack('<BBH', 1, 0, len(datasets))
+    for off, haddr in zip(name_offsets, header_addrs):
+        snod += struct.pack('<QQII16x', off, haddr, 0, 0)
+    root_header = _object_header(attrs + [_message(17, struct.pack('<QQ', tree_addr, heap_addr))])
+    assert len(root_header) == root_header_size
+    heap = b'HEAP' + struct.pack('<B3xQQQ', 0, len(heap_data), _UNDEF, heap_data_addr)
+    superblock = (b'\x89HDF\r\n\x1a\n' + struct.pack('<BBBBBBBB', 0, 0, 0, 0, 0, 8, 8, 0)
+                  + struct.pack('<HHI', 4, 16, 0) + struct.pack('<QQQQ', 0, _UNDEF, eof, _UNDEF)
+                  + struct.pack('<QQII', 0, root_addr, 1, 0) + struct.pack('<QQ', tree_addr, heap_addr))
+    assert len(superblock) == 96
+    with open(path, 'wb') as f:
+        f.write(superblock + root_header + heap + heap_data + tree + snod + b''.join(headers))
+        for (name, arr), daddr in zip(datasets, data_addrs):
+            f.seek(daddr)
+            f.write(np.ascontiguousarray(arr).tobytes())
+        f.truncate(eof)
+
+
+def grid_view_arrays(grid):
+    """Arrays in the layout SimulationReader hands to the integrator (float32 coords widened to f64)."""
+    return dict(
+        n_b=grid['n_b'], n_k=grid['n_k'], n_j=grid['n_j'], n_i=grid['n_i'], n_var=8,
+        levels=np.ascontiguousarray(grid['levels'], np.int32),
+        locations=np.ascontiguousarray(grid['locations'], np.int64).astype(np.int32),
+        x1f=grid['x1f'].astype(np.float64), x2f=grid['x2f'].astype(np.float64), x3f=grid['x3f'].astype(np.float64),
+        x1v=grid['x1v'].astype(np.float64), x2v=grid['x2v'].astype(np.float64), x3v=grid['x3v'].astype(np.float64),
+        prim=np.ascontiguousarray(grid['prim'], np.float32),
+        ind_rho=0, ind_pgas=1, ind_kappa=-1, ind_uu1=2, ind_uu2=3, ind_uu3=4, ind_bb1=5, ind_bb2=6, ind_bb3=7,
+        n_3_root=grid['root_size'][2])
+
+
+def make_mock(path=None, blocks=(1, 1, 1), **kwargs):
+    grid = to_blocks(mock_fields(**kwargs), blocks)
+    if path is not None:
+        write_athdf(path, grid)
+    return grid
+
+
+if __name__ == '__main__':
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument('filename')
+    ap.add_argument('--n_r', type=int, default=77)
+    ap.add_argument('--n_th', type=int, default=64)
+    ap.add_argument('--n_ph', type=int, default=128)
+    ap.add_argument('--blocks', type=int, nargs=3, default=(1, 1, 1))
+    ap.add_argument('--pert_amp', type=float, default=0.1)
+    ap.add_argument('--pert_n_ph', type=int, default=4)
+    a = ap.parse_args()
+    make_mock(a.filename, tuple(a.blocks), n_r=a.n_r, n_th=a.n_th, n_ph=a.n_ph, pert_amp=a.pert_amp, pert_n_ph=a.pert_n_ph)
