@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""Headline benchmark: camera rays/sec of the per-pixel hot path (geodesics + sampling + coefficients +
+transfer) on the mock Athena++ snapshot, example_simulation parameters at 1024^2 per GPU.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+  python bench.py --impl reference ...                     times the unmodified reference's CPU path
+
+A step is one pass of the hot path over one full image of synthetic input.  `value` is rays/s with camera
+arrays and grid already resident in HBM; `e2e` is the same metric through the C ABI from pinned HOST
+buffers (H2D of the camera arrays and D2H of the image inside the timed region).  One JSON line on rank 0.
+"""
+import argparse
+import json
+import math
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+# As-written arithmetic of the reference per unit of geodesic work
+FLOP_PER_ATTEMPT = 6900.0
+FLOP_PER_ACCEPT = 540.0
+FLOP_PER_SAMPLE = 220.0
+# Algorithmic bytes gathered per sample, trilinear, 8 variables
+GATHER_BYTES_PER_SAMPLE = 256.0
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--resolution', type=int, default=1024, help='image side per GPU (weak scaling)')
+    ap.add_argument('--workload', default='simulation', choices=['simulation', 'formula', 'polarized'])
+    ap.add_argument('--tile-rays', type=int, default=0)
+    ap.add_argument('--cpu-resolution', type=int, default=0, help='side of the bounded CPU sample (0 = auto)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+def workload_case(args, workdir, resolution, write_mock):
+    from harness import Case
+    base = {'simulation': 'simulation.input', 'formula': 'formula.input', 'polarized': 'simulation.input'}[args.workload]
+    over = {'camera_resolution': resolution}
+    if args.workload == 'polarized':
+        over.update({'image_polarization': 'true', 'image_num_frequencies': 4, 'image_frequency_start': '8.6e10',
+                     'image_frequency_end': '3.45e11', 'image_frequency_spacing': 'log', 'plasma_kappa_frac': '1.0',
+                     'plasma_kappa': '4.0', 'plasma_w': '1.0'})
+    case = Case(workdir, base, over)
+    if not write_mock and case.sim:
+        pass
+    return case
+
+
+def workload_name(args, res_total, n_gpus):
+    d = {'simulation': 'mock Athena++ snapshot (77x64x128 SKS, generate_mock_simulation defaults), example_simulation '
+                       'parameters: unpolarized thermal synchrotron, trilinear sampling, DP geodesics',
+         'formula': 'example_formula parameters: formula plasma, DP geodesics',
+         'polarized': 'mock Athena++ snapshot, polarized kappa=4 synchrotron, 4 frequencies'}[args.workload]
+    return '%s; image %dx%d over %d GPU(s)' % (d, res_total, res_total, n_gpus)
+
+
+class ClockSampler:
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.path = tempfile.mktemp(suffix='.csv')
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.QUERY,
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(',')]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(names, f[5:9]):
+                    if val.lower().startswith('active'):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if sm:
+            out['sm_mhz'] = float(np.median(sm))
+            out['sm_max_mhz'] = float(max(mx))
+        out['reasons'] = sorted(reasons)
+        return out
+
+
+def reference_rays_per_s(case, threads):
+    """Run the unmodified reference once on `case`; rays/s from its own timers (geodesic + sample + image)."""
+    case.kv['num_threads'] = str(threads)
+    t0 = time.time()
+    ref = case.run_reference(checkpoints=False)
+    wall = time.time() - t0
+    t = ref['timers']
+    compute = t.get('Integrating geodesics', 0.0) + t.get('Sampling simulation', 0.0) + t.get('Integrating image', 0.0) \
+        + t.get('Rendering', 0.0)
+    rays = int(case.kv['camera_resolution']) ** 2
+    return rays / compute, compute, wall
+
+
+def auto_cpu_resolution(args, threads):
+    # ~3k rays/s on 8 threads measured in the survey container; aim for ~15 s of CPU work
+    est = 360.0 * threads * (0.5 if args.workload == 'formula' else 1.0) * (0.1 if args.workload == 'polarized' else 1.0)
+    side = int(math.sqrt(est * 15.0))
+    return max(32, min(256, side // 8 * 8))
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    from harness import REF_BIN
+    threads = os.cpu_count() or 1
+    line = {'impl': 'reference', 'metric': 'camera rays/sec (geodesic+RT)', 'unit': 'rays/s', 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic'}
+    if not os.path.exists(REF_BIN):
+        print(json.dumps({'impl': 'reference', 'unavailable': 'oracle/_ref/blacklight was not built (no /root/reference at build time)'}))
+        return
+    side = args.cpu_resolution or auto_cpu_resolution(args, threads)
+    workdir = tempfile.mkdtemp(prefix='bl_ref_')
+    try:
+        case = workload_case(args, workdir, side, True)
+        rates, computes = [], []
+        for i in range(args.warmup + args.steps):
+            r, c, _ = reference_rays_per_s(case, threads)
+            if i >= args.warmup:
+                rates.append(r)
+                computes.append(c)
+            if i == 0 and c > 60.0:   # keep the whole run within a few minutes
+                args.warmup = 0
+                args.steps = max(1, min(args.steps, int(120.0 / c)))
+                rates, computes = [r], [c]
+                if args.steps == 1:
+                    break
+        rays = side * side
+        value = rays * len(computes) / sum(computes)
+        res_total = int(round(args.resolution * math.sqrt(args.gpus)))
+        line.update({'value': value, 'ms_per_step': 1e3 * sum(computes) / len(computes), 'steps': len(computes),
+                     'warmup': args.warmup,
+                     'config': {'workload': workload_name(args, res_total, args.gpus),
+                                'note': 'reference CPU path timed on a bounded sample of the same camera and physics'},
+                     'cpu_baseline': {'value': value, 'unit': 'rays/s', 'cores': threads, 'kind': 'reference',
+                                      'sample': '%dx%d rays of the same camera (rays/s is resolution independent); '
+                                                'reference timers geodesic+sample+image' % (side, side)},
+                     'e2e': {'value': value, 'unit': 'rays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}})
+        print(json.dumps(line))
+    finally:
+        shutil.rmtree(workdir, ignore_errors=True)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import blacklight_b200 as bl
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; the B200 path has no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    n_gpus = world
+
+    # weak scaling: the image grows so that every GPU keeps resolution^2 rays; rows are dealt round-robin
+    res_total = args.resolution if n_gpus == 1 else int(math.ceil(args.resolution * math.sqrt(n_gpus) / (8 * n_gpus))) * 8 * n_gpus
+    workdir = tempfile.mkdtemp(prefix='bl_bench_%d_' % rank)
+    try:
+        case = workload_case(args, workdir, res_total, False)
+        cfg = case.config(device=local_rank, tile_rays=args.tile_rays)
+        ctx = bl.Context(cfg)
+        info = ctx.device_info()
+        if case.sim:
+            ctx.upload_grid(case.grid_arrays())
+        # this rank's rays: image rows rank, rank+world, ... (cost varies strongly across the image)
+        pos_all, dir_all, fac_all = cfg.camera_root()
+        rows = np.arange(rank, res_total, n_gpus)
+        idx = (rows[:, None] * res_total + np.arange(res_total)[None, :]).ravel()
+        n_rays = len(idx)
+        pos = torch.from_numpy(pos_all[idx]).pin_memory()
+        dirs = torch.from_numpy(dir_all[idx]).pin_memory()
+        fac = torch.from_numpy(fac_all[idx]).pin_memory()
+        del pos_all, dir_all, fac_all
+        Q = ctx.num_quantities
+        image_host = torch.empty((Q, n_rays), dtype=torch.float64).pin_memory()
+        image_np = image_host.numpy()
+        pos_np, dir_np, fac_np = pos.numpy(), dirs.numpy(), fac.numpy()
+        gathered = None
+        if world > 1:
+            image_dev = torch.empty((Q, n_rays), dtype=torch.float64, device='cuda')
+            gathered = [torch.empty_like(image_dev) for _ in range(world)] if rank == 0 else None
+
+        def barrier():
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        def step_e2e():
+            st0 = ctx.trace_level(0, pos_np, dir_np, fac_np)            # H2D of camera arrays (+ trace if resident)
+            _, _, st = ctx.radiate_level(0, image=image_np)               # kernels + D2H of the image
+            if world > 1:                                                 # final image gather over NVLink
+                image_dev.copy_(image_host, non_blocking=True)
+                dist.gather(image_dev, gathered, dst=0)
+            return st
+
+        def step_resident():
+            ctx.retrace_level(0)
+            _, _, st = ctx.radiate_level(0, download=False)
+            return st
+
+        for _ in range(args.warmup):
+            step_e2e()
+        fp64_peak = ctx.measure_fp64_peak()
+
+        sampler = ClockSampler(local_rank)
+        # ---- end-to-end from host buffers ----
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_e2e()
+        barrier()
+        t_e2e = time.perf_counter() - t0
+        # ---- resident: camera arrays and grid already in HBM, no image download ----
+        launches0 = ctx.launch_count()
+        barrier()
+        t0 = time.perf_counter()
+        ms_geo = ms_rad = 0.0
+        for _ in range(args.steps):
+            st = step_resident()
+            ms_geo += st['ms_geodesic']
+            ms_rad += st['ms_radiation']
+        barrier()
+        t_res = time.perf_counter() - t0
+        launches = ctx.launch_count() - launches0
+        clocks = sampler.stop()
+
+        times = torch.tensor([t_e2e, t_res], dtype=torch.float64, device='cuda')
+        counts = torch.tensor([float(n_rays), float(launches)], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(times, op=dist.ReduceOp.MAX)
+            dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+        t_e2e, t_res = times.tolist()
+        total_rays, total_launches = counts.tolist()
+
+        if rank == 0:
+            K = args.steps
+            F = int(cfg.keys.get('image_num_frequencies', '1'))
+            value = total_rays * K / t_res
+            e2e = total_rays * K / t_e2e
+            # roofline of the dominant kernel on this rank
+            geo_ms, rad_ms = ms_geo / K, ms_rad / K
+            flop = st['num_attempts'] * FLOP_PER_ATTEMPT + st['num_accepted'] * FLOP_PER_ACCEPT + st['num_samples'] * FLOP_PER_SAMPLE
+            geo_tflops = flop / (geo_ms * 1e-3) / 1e12 if geo_ms > 0 else 0.0
+            gather_gbs = st['num_samples'] * GATHER_BYTES_PER_SAMPLE / (rad_ms * 1e-3) / 1e9 if rad_ms > 0 else 0.0
+            peaks = {}
+            try:
+                peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+            except (OSError, ValueError):
+                pass
+            hbm_peak = peaks.get('hbm_gbs', 6650.0)
+            if geo_ms >= rad_ms:
+                roofline = {'kernel': 'geodesic_dp_kernel', 'bound': 'fp64', 'achieved': geo_tflops, 'peak': fp64_peak,
+                            'unit': 'TFLOP/s', 'frac': geo_tflops / fp64_peak if fp64_peak else None, 'traffic': None,
+                            'peak_source': 'DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)'}
+            else:
+                roofline = {'kernel': 'radiate_unpolarized_kernel', 'bound': 'hbm', 'achieved': gather_gbs, 'peak': hbm_peak,
+                            'unit': 'GB/s', 'frac': gather_gbs / hbm_peak, 'traffic': None,
+                            'peak_source': 'MEASURED_PEAKS.json hbm_gbs (of measured)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s',
+                            'note': 'gather is L2 resident for the 20 MB mock grid; kernel is FP64/transcendental bound, see fp64 fields'}
+            line = {
+                'metric': 'camera rays/sec (geodesic+RT)', 'value': value, 'unit': 'rays/s', 'n_gpus': n_gpus, 'steps': K,
+                'warmup': args.warmup, 'ms_per_step': 1e3 * t_res / K, 'higher_is_better': True, 'scaling': 'weak',
+                'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+                'config': {'workload': workload_name(args, res_total, n_gpus), 'rays_per_gpu': n_rays, 'frequencies': F,
+                           'l2': 'inputs larger than L2: %.1f GB step buffer written and re-read per step' %
+                                 (st['num_samples'] * 72 / 1e9),
+                           'sharding': 'image rows round-robin over ranks; grid replicated; final image gather'},
+                'e2e': {'value': e2e, 'unit': 'rays/s', 'ms_per_step': 1e3 * t_e2e / K,
+                        'h2d_bytes_per_step': int(total_rays * 72), 'd2h_bytes_per_step': int(total_rays * 8 * Q)},
+                'gpu_launches': int(total_launches),
+                'kernels': {'geodesic_ms_per_step': geo_ms, 'radiation_ms_per_step': rad_ms,
+                            'samples_per_step': st['num_samples'], 'dp_attempts_per_step': st['num_attempts'],
+                            'geodesic_tflops_as_written': geo_tflops, 'fp64_peak_tflops_measured': fp64_peak,
+                            'radiation_gather_gbs': gather_gbs, 'ray_freq_per_s': value * F},
+                'roofline': roofline, 'clocks': clocks, 'device': info['name'],
+            }
+            if n_gpus == 1 and not args.no_cpu_baseline:
+                from harness import REF_BIN
+                threads = os.cpu_count() or 1
+                side = args.cpu_resolution or auto_cpu_resolution(args, threads)
+                if os.path.exists(REF_BIN):
+                    cdir = tempfile.mkdtemp(prefix='bl_cpu_')
+                    try:
+                        ccase = workload_case(args, cdir, side, True)
+                        r, c, wall = reference_rays_per_s(ccase, threads)
+                        line['cpu_baseline'] = {'value': r, 'unit': 'rays/s', 'cores': threads, 'kind': 'reference',
+                                                'sample': '%dx%d rays of the same camera, %.1f s of reference compute '
+                                                          '(timers geodesic+sample+image)' % (side, side, c)}
+                    finally:
+                        shutil.rmtree(cdir, ignore_errors=True)
+                else:
+                    line['cpu_baseline'] = {'value': None, 'unit': 'rays/s', 'cores': threads, 'kind': 'reference',
+                                            'sample': 'unavailable: oracle/_ref/blacklight not built'}
+            print(json.dumps(line))
+        ctx.close()
+    finally:
+        shutil.rmtree(workdir, ignore_errors=True)
+        if world > 1:
+            dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

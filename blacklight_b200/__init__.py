@@ -63,6 +63,8 @@ def load_library():
         'bl_radiate_level': (i32, [vp, i32, i32, vp, vp, ctypes.POINTER(LevelStats)]),
         'bl_refine_level': (i32, [vp, i32, vp, i64, vp, ctypes.POINTER(i64)]),
         'bl_set_taps': (i32, [vp, i32]),
+        'bl_retrace_level': (i32, [vp, i32, ctypes.POINTER(LevelStats)]),
+        'bl_launch_count': (ctypes.c_longlong, [vp]),
         'bl_download_samples': (i32, [vp, i32, vp, vp, vp, vp, vp]),
         'bl_download_sample_inds': (i32, [vp, i32, vp, vp, vp, vp, vp]),
         'bl_device_info': (i32, [vp, ctypes.c_char_p, i32, ctypes.POINTER(i32), ctypes.POINTER(dbl)]),
@@ -221,9 +223,17 @@ class Context:
         self._steps[level] = st.geodesic_num_steps
         return st.as_dict()
 
-    def radiate_level(self, level, snapshot=0, image=None, render=None, num_render=0):
+    def retrace_level(self, level):
+        st = LevelStats()
+        self._check(_lib.bl_retrace_level(self._h, level, ctypes.byref(st)))
+        return st.as_dict()
+
+    def launch_count(self):
+        return int(_lib.bl_launch_count(self._h))
+
+    def radiate_level(self, level, snapshot=0, image=None, render=None, num_render=0, download=True):
         n = self._rays[level]
-        if image is None:
+        if image is None and download:
             image = np.empty((self.num_quantities, n))
         if render is None and num_render > 0:
             render = np.empty((num_render, 3, n))

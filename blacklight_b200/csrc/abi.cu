@@ -61,6 +61,7 @@ struct bl_ctx {
   std::vector<Level> levels;
   std::string error;
   bool taps_enabled = false;
+  long long launches = 0;   // kernels of ours launched so far
 };
 
 namespace {
@@ -521,6 +522,7 @@ int trace_wave(bl_ctx *ctx, Level &L, int64_t first, int64_t count) {
     BL_CUDA_CHECK(bl_launch_geodesic_dp(&g, p.ray_flat, ctx->sm_count, ctx->stream));
   else
     BL_CUDA_CHECK(bl_launch_geodesic_rk(&g, p.ray_flat, p.ray_integrator == BL_INTEGRATOR_RK4 ? 4 : 2, ctx->sm_count, ctx->stream));
+  ctx->launches++;
   return BL_OK;
 }
 
@@ -562,6 +564,7 @@ int radiate_wave(bl_ctx *ctx, Level &L, int64_t first, int64_t count) {
     BL_CUDA_CHECK(bl_launch_radiate_polarized(&A, ctx->rad.num_freq, ctx->stream));
   else
     BL_CUDA_CHECK(bl_launch_radiate_unpolarized(&A, ctx->rad.num_freq, sim ? 1 : 0, ctx->stream));
+  ctx->launches++;
   return BL_OK;
 }
 
@@ -628,6 +631,31 @@ int bl_trace_level(bl_ctx *ctx, int level, const double *cam_pos, const double *
     L.stats.num_rays = num_rays;
     L.traced = false;
     BL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  }
+  if (stats) *stats = L.stats;
+  return BL_OK;
+}
+
+long long bl_launch_count(const bl_ctx *ctx) { return ctx ? ctx->launches : -1; }
+
+int bl_retrace_level(bl_ctx *ctx, int level, bl_level_stats *stats) {
+  if (!ctx) return BL_ERR_ARG;
+  if (level < 0 || level >= (int)ctx->levels.size()) return bl_fail(ctx, BL_ERR_ARG, "bl_retrace_level: level %d out of range", level);
+  Level &L = ctx->levels[level];
+  if (!L.cam_pos) return bl_fail(ctx, BL_ERR_STATE, "bl_retrace_level: level %d has no camera arrays", level);
+  BL_CUDA_CHECK(cudaSetDevice(ctx->device));
+  if (L.resident) {
+    BL_CUDA_CHECK(cudaMemsetAsync(ctx->counters, 0, sizeof(GeoCounters), ctx->stream));
+    BL_CUDA_CHECK(cudaEventRecord(ctx->ev0, ctx->stream));
+    int rc = trace_wave(ctx, L, 0, L.rays);
+    if (rc) return rc;
+    BL_CUDA_CHECK(cudaEventRecord(ctx->ev1, ctx->stream));
+    rc = read_geo_counters(ctx, L);
+    if (rc) return rc;
+    float ms = 0.f;
+    BL_CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    L.stats.ms_geodesic = ms;
+    L.traced = true;
   }
   if (stats) *stats = L.stats;
   return BL_OK;

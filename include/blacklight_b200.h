@@ -172,6 +172,13 @@ int bl_upload_grid(bl_ctx *ctx, const bl_grid_view *grid);
 int bl_trace_level(bl_ctx *ctx, int level, const double *cam_pos, const double *cam_dir,
                    const double *mom_factor, int64_t num_rays, bl_level_stats *stats);
 
+/* Re-integrate the geodesics of a level from the camera arrays already resident in HBM (no host
+ * transfer).  A no-op for levels traced wave by wave inside bl_radiate_level. */
+int bl_retrace_level(bl_ctx *ctx, int level, bl_level_stats *stats);
+
+/* Number of CUDA kernels of this library launched by the context so far (bench accounting). */
+long long bl_launch_count(const bl_ctx *ctx);
+
 /* Replaces RadiationIntegrator::Integrate's sampling + coefficient + transfer (+ render) stages
  * for one level.  image: (image_num_quantities, N) f64; render: (R,3,N) f64 or NULL. */
 int bl_radiate_level(bl_ctx *ctx, int level, int snapshot, double *image, double *render,

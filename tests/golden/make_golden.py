@@ -1,0 +1,96 @@
+#!/usr/bin/env python
+"""Regenerate the golden fixtures in this directory by running the UNMODIFIED reference
+(oracle/_ref/blacklight, built from /root/reference by oracle/Makefile) on small cases.
+
+Run where the reference is built:  python tests/golden/make_golden.py
+Each fixture holds what the parity tests compare: sample_flags, sample_num, the image arrays, a CRC-32 of
+the masked sample_inds (simulation cases) and full samples of a few rays.
+"""
+import os
+import sys
+import tempfile
+import zlib
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from harness import Case  # noqa: E402
+
+POL = {'image_polarization': 'true', 'image_rotation_split': 'false'}
+KAPPA = {'plasma_kappa_frac': '1.0', 'plasma_kappa': '4.0', 'plasma_w': '1.0'}
+MULTI = {'image_num_frequencies': 3, 'image_frequency_start': '8.6e10', 'image_frequency_end': '3.45e11',
+         'image_frequency_spacing': 'log'}
+AUX = {'image_time': 'true', 'image_length': 'true', 'image_lambda': 'true', 'image_emission': 'true',
+       'image_tau': 'true', 'image_crossings': 'true'}
+AUX_SIM = dict(AUX, image_lambda_ave='true', image_emission_ave='true', image_tau_int='true')
+
+CASES = {
+    'formula_16': ('formula.input', {'camera_resolution': 16}, None),
+    'formula_aux_12': ('formula.input', dict(AUX, camera_resolution=12), None),
+    'simulation_32': ('simulation.input', {'camera_resolution': 32}, None),
+    'simulation_nearest_24': ('simulation.input', {'camera_resolution': 24, 'simulation_interp': 'false'}, None),
+    'simulation_blocks_24': ('simulation.input', {'camera_resolution': 24}, {'blocks': (7, 2, 4)}),
+    'simulation_aux_16': ('simulation.input', dict(AUX_SIM, camera_resolution=16), None),
+    'simulation_kerr_24': ('simulation.input', {'camera_resolution': 24, 'simulation_a': '0.9', 'camera_th': '80.0'}, None),
+    'polarized_thermal_16': ('simulation.input', dict(POL, camera_resolution=16), None),
+    'polarized_kappa_multi_12': ('simulation.input', dict(POL, **KAPPA, **MULTI, camera_resolution=12), None),
+    'adaptive_32': ('adaptive.input', {}, None),
+    'render_32': ('render.input', {'camera_resolution': 32}, None),
+    'true_color_16': ('true_color.input', {'camera_resolution': 16}, None),
+}
+
+
+def masked_inds_crc(geo, samp, sim_interp):
+    num = geo['sample_num']
+    S = samp['sample_inds'].shape[1]
+    valid = (np.arange(S)[None, :] < num[:, None]) & (samp['sample_nan'] == 0) & (samp['sample_fallback'] == 0)
+    # geometric cuts are not in the checkpoint: recompute r > camera_r from positions is done by the test,
+    # here we only keep samples whose stored index is inside the grid (unset entries are arbitrary)
+    return valid
+
+
+def main():
+    only = sys.argv[1:]
+    for name, (base, over, mock) in CASES.items():
+        if only and name not in only:
+            continue
+        with tempfile.TemporaryDirectory() as d:
+            case = Case(d, base, over, mock=mock, threads=8)
+            ref = case.run_reference(checkpoints=True)
+            out = {k: v for k, v in ref['npz'].items()}
+            geo = ref['geo']
+            out['sample_flags'] = geo['sample_flags']
+            out['sample_num'] = geo['sample_num']
+            out['geodesic_num_steps'] = np.int32(geo['geodesic_num_steps'])
+            rays = np.unique(np.linspace(0, len(geo['sample_num']) - 1, 5).astype(int))
+            out['probe_rays'] = rays
+            for r in rays:
+                n = geo['sample_num'][r]
+                out['probe_pos_%d' % r] = geo['sample_pos'][r, :n]
+                out['probe_dir_%d' % r] = geo['sample_dir'][r, :n]
+                out['probe_len_%d' % r] = geo['sample_len'][r, :n]
+            # checksum over every sample of every ray (positions, momenta, lengths) within sample_num
+            S = geo['sample_pos'].shape[1]
+            mask = np.arange(S)[None, :] < geo['sample_num'][:, None]
+            out['samples_crc'] = np.uint32(zlib.crc32(geo['sample_pos'][mask].tobytes()
+                                                       + geo['sample_dir'][mask].tobytes()
+                                                       + geo['sample_len'][mask].tobytes()))
+            if 'samp' in ref:
+                samp = ref['samp']
+                out['sample_nan_count'] = np.int64(samp['sample_nan'][mask].sum())
+                # cut samples (r > camera_r for these configs) leave sample_inds unset: mask them by radius
+                x = geo['sample_pos']
+                a = float(case.kv['simulation_a'])
+                rr2 = (x[..., 1:] ** 2).sum(-1)
+                r2 = 0.5 * (rr2 - a * a + np.hypot(rr2 - a * a, 2.0 * a * x[..., 3]))
+                cut = np.sqrt(r2) > float(case.kv['camera_r'])
+                valid = mask & ~cut & (samp['sample_nan'] == 0) & (samp['sample_fallback'] == 0)
+                out['valid_count'] = np.int64(valid.sum())
+                out['inds_crc'] = np.uint32(zlib.crc32(np.ascontiguousarray(samp['sample_inds'][valid]).tobytes()))
+            np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
+            print(name, 'rays', len(geo['sample_num']), 'S', S, 'keys', len(out), ref['timers'])
+
+
+if __name__ == '__main__':
+    main()

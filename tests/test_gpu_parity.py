@@ -1,0 +1,190 @@
+"""Parity of the CUDA path (through the C ABI) against the unmodified reference.
+
+Two sources of truth: the committed golden fixtures (tests/golden/*.npz, produced by make_golden.py from
+the reference built by oracle/Makefile) and, when oracle/_ref/blacklight travelled with the repo, a live run
+of the reference on the same inputs.  Thresholds are north_star's: exact sample_flags / sample_num / sample
+cell indices, <= 1e-6 relative per-pixel intensity, <= 1e-9 relative total flux.
+"""
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+import blacklight_b200 as bl
+from harness import REF_BIN, Case, flux_rel, rel_err
+from golden.make_golden import CASES
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+PIXEL_TOL = 1e-6
+FLUX_TOL = 1e-9
+
+UNPOLARIZED = ['formula_16', 'formula_aux_12', 'simulation_32', 'simulation_nearest_24', 'simulation_blocks_24',
+               'simulation_aux_16', 'simulation_kerr_24']
+
+
+def run_gpu_level0(case, taps=False):
+    cfg = case.config()
+    ctx = bl.Context(cfg)
+    if case.sim:
+        ctx.upload_grid(case.grid_arrays())
+    pos, dirs, fac = cfg.camera_root()
+    ctx.trace_level(0, pos, dirs, fac)
+    if taps and case.sim:
+        ctx.set_taps(True)
+    R = int(case.kv.get('render_num_images', 0)) if case.sim else 0
+    image, render, stats = ctx.radiate_level(0, num_render=R)
+    return cfg, ctx, image, render, stats
+
+
+def image_arrays(case, image, res):
+    """Split the (Q, N) image into the reference's named npz arrays (numpy_format.cpp:129-283)."""
+    kv = case.kv
+    F = int(kv['image_num_frequencies'])
+    on = lambda k: kv.get(k, 'false') == 'true'
+    pol = case.sim and on('image_light') and on('image_polarization')
+    out, q = {}, 0
+    shape = (res, res) if F == 1 else (F, res, res)
+    if on('image_light'):
+        if pol:
+            block = image[q:q + 4 * F].reshape(F, 4, -1)
+            for s, name in enumerate(('I_nu', 'Q_nu', 'U_nu', 'V_nu')):
+                out[name] = block[:, s].reshape(shape)
+            q += 4 * F
+        else:
+            out['I_nu'] = image[q:q + F].reshape(shape)
+            q += F
+    for key, name, per_freq in (('image_time', 'time', False), ('image_length', 'length', False),
+                                ('image_lambda', 'lambda', True), ('image_emission', 'emission', True),
+                                ('image_tau', 'tau', True)):
+        if on(key):
+            n = F if per_freq else 1
+            out[name] = image[q:q + n].reshape(shape if per_freq else (res, res))
+            q += n
+    cells = ('rho', 'n_e', 'p_gas', 'Theta_e', 'B', 'sigma', 'beta_inverse')
+    for key, prefix in (('image_lambda_ave', 'lambda_ave_'), ('image_emission_ave', 'emission_ave_'),
+                        ('image_tau_int', 'tau_int_')):
+        if case.sim and on(key):
+            block = image[q:q + 7 * F].reshape(F, 7, -1)
+            for c, cname in enumerate(cells):
+                out[prefix + cname] = block[:, c].reshape(shape)
+            q += 7 * F
+    if on('image_crossings'):
+        out['crossings'] = image[q].reshape(res, res)
+        q += 1
+    assert q == image.shape[0]
+    return out
+
+
+def check_images(mine, ref, what):
+    for name, arr in mine.items():
+        assert name in ref, name
+        err = rel_err(arr, ref[name])
+        assert err <= PIXEL_TOL, '%s %s: per-pixel relative error %.3e' % (what, name, err)
+        if name.endswith('_nu'):
+            assert flux_rel(arr, ref[name]) <= FLUX_TOL or np.nanmax(np.abs(ref[name])) == 0, '%s %s flux' % (what, name)
+
+
+@pytest.mark.parametrize('name', UNPOLARIZED)
+def test_golden_unpolarized(name, gpu, tmp_path):
+    base, over, mock = CASES[name]
+    gold = dict(np.load(os.path.join(GOLDEN, name + '.npz')))
+    case = Case(tmp_path, base, over, mock=mock)
+    cfg, ctx, image, _, stats = run_gpu_level0(case, taps=True)
+    res = cfg.resolution
+    s = ctx.download_samples(0)
+    # termination flags, sample counts: exact
+    assert np.array_equal(s['flags'], gold['sample_flags'])
+    assert np.array_equal(s['num'], gold['sample_num'])
+    assert stats['geodesic_num_steps'] == int(gold['geodesic_num_steps'])
+    # every stored sample of every ray: bit-identical (checksum) + explicit probes
+    S = s['pos'].shape[1]
+    mask = np.arange(S)[None, :] < s['num'][:, None]
+    crc = zlib.crc32(s['pos'][mask].tobytes() + s['dir'][mask].tobytes() + s['len'][mask].tobytes())
+    assert crc == int(gold['samples_crc']), 'geodesic samples are not bit-identical to the reference'
+    for r in gold['probe_rays']:
+        n = s['num'][r]
+        assert np.array_equal(s['pos'][r, :n], gold['probe_pos_%d' % r])
+        assert np.array_equal(s['dir'][r, :n], gold['probe_dir_%d' % r])
+        assert np.array_equal(s['len'][r, :n], gold['probe_len_%d' % r])
+    # sampled cell indices: exact on every sample the reference defines
+    if case.sim:
+        t = ctx.download_sample_inds(0, interp=case.kv['simulation_interp'] == 'true')
+        valid = mask & (t['cut'] == 0) & (t['nan'] == 0) & (t['fallback'] == 0)
+        assert int(valid.sum()) == int(gold['valid_count'])
+        assert int(t['nan'][mask].sum()) == int(gold['sample_nan_count'])
+        assert zlib.crc32(np.ascontiguousarray(t['inds'][valid]).tobytes()) == int(gold['inds_crc'])
+    check_images(image_arrays(case, image, res), gold, name)
+    ctx.close()
+
+
+@pytest.mark.parametrize('base,over,mock', [
+    ('simulation.input', {'camera_resolution': 64}, None),
+    ('simulation.input', {'camera_resolution': 48, 'simulation_a': '0.5', 'camera_th': '60.0', 'camera_type': 'pinhole'}, {'blocks': (1, 4, 8)}),
+    ('simulation.input', {'camera_resolution': 40, 'ray_integrator': 'rk4', 'ray_step': '0.02'}, None),
+    ('simulation.input', {'camera_resolution': 40, 'ray_integrator': 'rk2', 'ray_step': '0.02'}, None),
+    ('simulation.input', {'camera_resolution': 40, 'plasma_power_frac': '0.3', 'plasma_p': '3.0', 'plasma_gamma_min': '4.0', 'plasma_gamma_max': '1000.0'}, None),
+    ('simulation.input', {'camera_resolution': 32, 'fallback_nan': 'false', 'fallback_rho': '1.0e-6', 'fallback_pgas': '1.0e-8', 'camera_r': '80.0', 'camera_width': '60.0'}, None),
+    ('simulation.input', {'camera_resolution': 32, 'cut_omit_near': 'true', 'cut_omit_in': '3.0', 'cut_midplane_theta': '30.0', 'cut_rho_min': '1.0e-18'}, None),
+    ('formula.input', {'camera_resolution': 24, 'image_num_frequencies': 3, 'image_frequency_start': '1.0e11', 'image_frequency_end': '4.0e11', 'image_frequency_spacing': 'lin_wave', 'camera_th': '0.0'}, None),
+    ('formula.input', {'camera_resolution': 20, 'ray_flat': 'true', 'formula_l0': '1.0'}, None),
+])
+def test_live_reference_unpolarized(base, over, mock, gpu, tmp_path):
+    if not os.path.exists(REF_BIN):
+        pytest.skip('oracle/_ref/blacklight not present')
+    case = Case(tmp_path, base, over, mock=mock)
+    ref = case.run_reference()
+    cfg, ctx, image, _, stats = run_gpu_level0(case, taps=True)
+    s = ctx.download_samples(0)
+    g = ref['geo']
+    assert np.array_equal(s['flags'], g['sample_flags'])
+    assert np.array_equal(s['num'], g['sample_num'])
+    S = s['pos'].shape[1]
+    mask = np.arange(S)[None, :] < s['num'][:, None]
+    assert np.array_equal(s['pos'][mask], g['sample_pos'][mask])
+    assert np.array_equal(s['dir'][mask], g['sample_dir'][mask])
+    assert np.array_equal(s['len'][mask], g['sample_len'][mask])
+    if case.sim:
+        interp = case.kv['simulation_interp'] == 'true'
+        t = ctx.download_sample_inds(0, interp=interp)
+        rs = ref['samp']
+        assert np.array_equal(t['nan'][mask], rs['sample_nan'][mask])
+        assert np.array_equal(t['fallback'][mask], rs['sample_fallback'][mask])
+        valid = mask & (t['cut'] == 0) & (t['nan'] == 0) & (t['fallback'] == 0)
+        assert np.array_equal(t['inds'][valid], rs['sample_inds'][valid])
+        if interp:
+            assert np.max(np.abs(t['fracs'][valid] - rs['sample_fracs'][valid])) < 1e-9
+    check_images(image_arrays(case, image, cfg.resolution), ref['npz'], str(over))
+    ctx.close()
+
+
+def test_waves_match_resident(gpu, tmp_path):
+    """Tracing in waves (step buffer reused) must give the same image as a resident level, bit for bit."""
+    case = Case(tmp_path, 'simulation.input', {'camera_resolution': 48})
+    _, ctx, image, _, _ = run_gpu_level0(case)
+    cfg = case.config(tile_rays=512)
+    ctx2 = bl.Context(cfg)
+    ctx2.upload_grid(case.grid_arrays())
+    pos, dirs, fac = cfg.camera_root()
+    ctx2.trace_level(0, pos, dirs, fac)
+    image2, _, stats = ctx2.radiate_level(0)
+    assert np.array_equal(image, image2, equal_nan=True)
+    s1, s2 = ctx.download_samples(0, arrays=False), ctx2.download_samples(0, arrays=False)
+    assert np.array_equal(s1['num'], s2['num']) and np.array_equal(s1['flags'], s2['flags'])
+    ctx.close()
+    ctx2.close()
+
+
+def test_drop_in_executable_path(gpu, tmp_path):
+    """blh_run_input_file (the re-hosted main: parser, athdf reader, npz writer) against the golden image."""
+    base, over, mock = CASES['simulation_32']
+    case = Case(tmp_path, base, over, mock=mock)
+    npz, timings = case.run_gpu_file()
+    gold = dict(np.load(os.path.join(GOLDEN, 'simulation_32.npz')))
+    for k in ('mass_msun', 'width', 'frequency', 'adaptive_num_levels'):
+        assert np.array_equal(npz[k], gold[k]), k
+    assert npz['I_nu'].shape == gold['I_nu'].shape
+    assert rel_err(npz['I_nu'], gold['I_nu']) <= PIXEL_TOL
+    assert flux_rel(npz['I_nu'], gold['I_nu']) <= FLUX_TOL
+    assert timings['rays'] == 32 * 32
