@@ -547,6 +547,8 @@ int radiate_wave(bl_ctx *ctx, Level &L, int64_t first, int64_t count) {
   A.sample_num = L.num + first;
   A.sample_flags = L.flags + first;
   A.mom_factor = L.mom + first;
+  A.cam_pos = L.cam_pos + 4 * first;
+  A.cam_dir = L.cam_dir + 4 * first;
   A.rays = count;
   A.image = L.image + first;
   A.image_stride = L.rays;

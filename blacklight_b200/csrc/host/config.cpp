@@ -233,9 +233,16 @@ RunConfig make_config(const InputFile &in) {
         p.render_thresh_vals[feature] = in.real(fb + "thresh");
         p.render_opacities[feature] = in.real(fb + "opacity");
       }
-      double rgb[3];
-      in.triple(fb + "rgb", rgb);
-      rgb_to_xyz(rgb[0], rgb[1], rgb[2], &p.render_x_vals[feature], &p.render_y_vals[feature], &p.render_z_vals[feature]);
+      // colour: sRGB triple converted to XYZ, or XYZ given directly (render_reader.cpp:183-210)
+      if (in.has(fb + "xyz")) {
+        double xyz[3];
+        in.triple(fb + "xyz", xyz);
+        p.render_x_vals[feature] = xyz[0]; p.render_y_vals[feature] = xyz[1]; p.render_z_vals[feature] = xyz[2];
+      } else {
+        double rgb[3];
+        in.triple(fb + "rgb", rgb);
+        rgb_to_xyz(rgb[0], rgb[1], rgb[2], &p.render_x_vals[feature], &p.render_y_vals[feature], &p.render_z_vals[feature]);
+      }
     }
     p.render_feature_start[im + 1] = feature;
   }

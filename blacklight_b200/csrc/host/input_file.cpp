@@ -53,11 +53,11 @@ bool ends_with(const std::string &s, const char *suffix) {
   return s.size() >= t.size() && s.compare(s.size() - t.size(), t.size(), t) == 0;
 }
 
-// render_<i>_num_features, render_<i>_<f>_{quantity,type,min,max,thresh,tau_scale,opacity,rgb}, render_num_images
+// render_<i>_num_features, render_<i>_<f>_{quantity,type,min,max,thresh,tau_scale,opacity,rgb,xyz}, render_num_images
 bool render_key_ok(const std::string &rest) {
   if (rest == "num_images") return true;
   static const char *suffixes[] = {"_num_features", "_quantity", "_type", "_min", "_max", "_thresh",
-                                   "_tau_scale", "_opacity", "_rgb"};
+                                   "_tau_scale", "_opacity", "_rgb", "_xyz"};
   for (const char *s : suffixes)
     if (ends_with(rest, s) && rest.size() > std::string(s).size()) return true;
   return false;

@@ -182,9 +182,10 @@ struct Plasma {
 };
 
 // Plasma state of one sample (simulation_coefficients.cpp:286-408).  (x,y,z) CKS position, r its radius.
-// want_vectors = false stops after the value cuts (cell values only).
+// vectors: 0 = stop after the value cuts (cell values only); 1 = CKS u^mu, b^mu only for samples that
+// couple to the radiation; 2 = always (the polarized transport needs the fluid frame at every sample).
 __device__ __forceinline__ void plasma_state(const RadParams &P, double x, double y, double z, double r,
-                                             const Prims &pr, bool want_vectors, Plasma &s) {
+                                             const Prims &pr, int vectors, Plasma &s) {
   const double a = P.a;
   double rho = pr.rho, pgas = pr.pgas, kappa = pr.kappa;
   double uu1 = pr.uu1, uu2 = pr.uu2, uu3 = pr.uu3, bb1 = pr.bb1, bb2 = pr.bb2, bb3 = pr.bb3;
@@ -202,13 +203,11 @@ __device__ __forceinline__ void plasma_state(const RadParams &P, double x, doubl
   if (P.coord != 0) {
     // spherical Kerr-Schild: nonzero g_{tt} g_{tr} g_{tph} g_{rr} g_{rph} g_{thth} g_{phph}
     double sigma = r2 + a2 * cth2;
-    double delta = r2 - 2.0 * r + a2;
     double tr = 2.0 * r / sigma;
     double g00 = -(1.0 - tr), g01 = tr, g03 = -tr * a * sth2;
     double g11 = 1.0 + tr, g13 = -(1.0 + tr) * a * sth2, g22 = sigma;
     double g33 = (r2 + a2 + tr * a2 * sth2) * sth2;
     double gc00 = -(1.0 + tr), gc01 = tr;
-    (void)delta;
     double uu0 = sqrt(1.0 + g11 * uu1 * uu1 + 2.0 * g13 * uu1 * uu3 + g22 * uu2 * uu2 + g33 * uu3 * uu3);
     double lapse = 1.0 / sqrt(-gc00);
     double shift1 = -gc01 / gc00;
@@ -288,7 +287,7 @@ __device__ __forceinline__ void plasma_state(const RadParams &P, double x, doubl
       (P.cut_beta_inverse_min >= 0.0 && s.beta_inv < P.cut_beta_inverse_min) ||
       (P.cut_beta_inverse_max >= 0.0 && s.beta_inv > P.cut_beta_inverse_max);
   s.b_zero = bb1 == 0.0 && bb2 == 0.0 && bb3 == 0.0;
-  if (s.value_cut || s.b_zero || !want_vectors) return;
+  if (vectors == 0 || (vectors == 1 && (s.value_cut || s.b_zero))) return;
 
   // to Cartesian Kerr-Schild (CoordinateJacobian, radiation_geometry.cpp:69-126)
   if (P.coord != 0) {
@@ -343,6 +342,52 @@ __device__ __forceinline__ double proper_length_rate(const RadParams &P, double 
   }
   double lt = l[0] * t[0] + l[1] * t[1] + l[2] * t[2];
   return sqrt(t[0] * t[0] + t[1] * t[1] + t[2] * t[2] + f * lt * lt);
+}
+
+// False-colour compositing of one sample into the (R,3) XYZ accumulators of a ray (rendering.cpp:101-166)
+__device__ __forceinline__ void render_update(const RadParams &P, double *render, int64_t stride,
+                                              const double prev[RAD_NUM_CELL_VALUES],
+                                              const double cur[RAD_NUM_CELL_VALUES], double delta_length) {
+  for (int im = 0; im < P.render_num_images; im++) {
+    double *px = render + (size_t)(3 * im) * stride;
+    double cx = px[0], cy = px[stride], cz = px[2 * stride];
+    bool touched = false;
+    for (int f = P.render_feature_start[im]; f < P.render_feature_start[im + 1]; f++) {
+      int q = P.render_quantities[f];
+      int type = P.render_types[f];
+      double pv = prev[q], cv = cur[q];
+      if (type == 0 && cv >= P.render_min_vals[f] && cv <= P.render_max_vals[f]) {
+        double delta_tau = delta_length / P.render_tau_scales[f];
+        if (delta_tau <= 100.0) {
+          double en = exp(-delta_tau), em = expm1(delta_tau);
+          cx = en * (cx + P.render_x_vals[f] * em);
+          cy = en * (cy + P.render_y_vals[f] * em);
+          cz = en * (cz + P.render_z_vals[f] * em);
+        } else {
+          cx = P.render_x_vals[f];
+          cy = P.render_y_vals[f];
+          cz = P.render_z_vals[f];
+        }
+        touched = true;
+      }
+      bool crossed = false;
+      double th = P.render_thresh_vals[f];
+      if ((type == 1 || type == 2) && pv < th && cv >= th) crossed = true;
+      if ((type == 1 || type == 3) && pv > th && cv <= th) crossed = true;
+      if (crossed) {
+        double op = P.render_opacities[f];
+        cx = (1.0 - op) * cx + op * P.render_x_vals[f];
+        cy = (1.0 - op) * cy + op * P.render_y_vals[f];
+        cz = (1.0 - op) * cz + op * P.render_z_vals[f];
+        touched = true;
+      }
+    }
+    if (touched) {
+      px[0] = cx;
+      px[stride] = cy;
+      px[2 * stride] = cz;
+    }
+  }
 }
 
 }  // namespace rad

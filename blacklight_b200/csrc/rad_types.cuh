@@ -105,6 +105,8 @@ struct RadArgs {
   const int32_t *sample_num;    // (wave rays)
   const uint8_t *sample_flags;  // (wave rays)
   const double *mom_factor;     // (wave rays)
+  const double *cam_pos;        // (wave rays,4) camera position / covariant momentum of each ray:
+  const double *cam_dir;        //   the polarized kernel projects onto the camera tetrad at the end
   int64_t rays;                 // rays in this wave
   double *image;                // (Q, level_rays) device, already offset to this wave's first ray
   int64_t image_stride;         // level_rays

@@ -106,51 +106,6 @@ __device__ __forceinline__ void formula_fluid(const RadParams &P, double x, doub
   n_n0 = exp(-0.5 * (r * r / (P.formula_r0 * P.formula_r0) + P.formula_h * P.formula_h * cth * cth));
 }
 
-__device__ __forceinline__ void render_update(const RadParams &P, double *render, int64_t stride,
-                                              const double prev[RAD_NUM_CELL_VALUES],
-                                              const double cur[RAD_NUM_CELL_VALUES], double delta_length) {
-  for (int im = 0; im < P.render_num_images; im++) {
-    double *px = render + (size_t)(3 * im) * stride;
-    double cx = px[0], cy = px[stride], cz = px[2 * stride];
-    bool touched = false;
-    for (int f = P.render_feature_start[im]; f < P.render_feature_start[im + 1]; f++) {
-      int q = P.render_quantities[f];
-      int type = P.render_types[f];
-      double pv = prev[q], cv = cur[q];
-      if (type == 0 && cv >= P.render_min_vals[f] && cv <= P.render_max_vals[f]) {
-        double delta_tau = delta_length / P.render_tau_scales[f];
-        if (delta_tau <= 100.0) {
-          double en = exp(-delta_tau), em = expm1(delta_tau);
-          cx = en * (cx + P.render_x_vals[f] * em);
-          cy = en * (cy + P.render_y_vals[f] * em);
-          cz = en * (cz + P.render_z_vals[f] * em);
-        } else {
-          cx = P.render_x_vals[f];
-          cy = P.render_y_vals[f];
-          cz = P.render_z_vals[f];
-        }
-        touched = true;
-      }
-      bool crossed = false;
-      double th = P.render_thresh_vals[f];
-      if ((type == 1 || type == 2) && pv < th && cv >= th) crossed = true;
-      if ((type == 1 || type == 3) && pv > th && cv <= th) crossed = true;
-      if (crossed) {
-        double op = P.render_opacities[f];
-        cx = (1.0 - op) * cx + op * P.render_x_vals[f];
-        cy = (1.0 - op) * cy + op * P.render_y_vals[f];
-        cz = (1.0 - op) * cz + op * P.render_z_vals[f];
-        touched = true;
-      }
-    }
-    if (touched) {
-      px[0] = cx;
-      px[stride] = cy;
-      px[2 * stride] = cz;
-    }
-  }
-}
-
 template <int FMAX, bool SIM>
 __global__ void __launch_bounds__(kBlock) radiate_unpolarized_kernel(RadArgs A) {
   extern __shared__ double smem_bounds[];
@@ -270,7 +225,7 @@ __global__ void __launch_bounds__(kBlock) radiate_unpolarized_kernel(RadArgs A) 
         pr.uu1 = pr.uu2 = pr.uu3 = pr.bb1 = pr.bb2 = pr.bb3 = 0.0f;
       }
       if (st != rad::kSampleCut) {
-        rad::plasma_state(P, x, y, z, r, pr, want_coeff, ps);
+        rad::plasma_state(P, x, y, z, r, pr, want_coeff ? 1 : 0, ps);
         if (!ps.value_cut) {
           if (P.need_cell_values) rad::cell_values_of(ps, cv);
           if (want_coeff && !ps.b_zero) {
@@ -316,7 +271,7 @@ __global__ void __launch_bounds__(kBlock) radiate_unpolarized_kernel(RadArgs A) 
     }
     if (do_render) {
       double dlen = fill_present ? rad::proper_length_rate(P, x, y, z, kc) * dlam * P.x_unit : 0.0;
-      render_update(P, A.render + m, stride, prev_cv, cv, dlen);
+      rad::render_update(P, A.render + m, stride, prev_cv, cv, dlen);
       for (int q = 0; q < RAD_NUM_CELL_VALUES; q++) prev_cv[q] = cv[q];
     }
 

@@ -188,3 +188,104 @@ def test_drop_in_executable_path(gpu, tmp_path):
     assert rel_err(npz['I_nu'], gold['I_nu']) <= PIXEL_TOL
     assert flux_rel(npz['I_nu'], gold['I_nu']) <= FLUX_TOL
     assert timings['rays'] == 32 * 32
+
+
+def stokes_err(mine, ref):
+    """Q, U, V can vanish where I does not: measure their error against max(|ref|, 1e-3 * I) per pixel."""
+    out = {}
+    I = ref['I_nu']
+    for name in ('Q_nu', 'U_nu', 'V_nu'):
+        a, b = mine[name], ref[name]
+        ok = ~np.isnan(b)
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        scale = np.maximum(np.abs(b[ok]), 1e-3 * np.abs(I[ok]))
+        scale = np.where(scale > 0, scale, 1.0)
+        out[name] = float(np.max(np.abs(a[ok] - b[ok]) / scale)) if ok.any() else 0.0
+    return out
+
+
+@pytest.mark.parametrize('name', ['polarized_thermal_16', 'polarized_kappa_multi_12'])
+def test_golden_polarized(name, gpu, tmp_path):
+    base, over, mock = CASES[name]
+    gold = dict(np.load(os.path.join(GOLDEN, name + '.npz')))
+    case = Case(tmp_path, base, over, mock=mock)
+    cfg, ctx, image, _, stats = run_gpu_level0(case)
+    s = ctx.download_samples(0, arrays=False)
+    assert np.array_equal(s['flags'], gold['sample_flags'])
+    assert np.array_equal(s['num'], gold['sample_num'])
+    mine = image_arrays(case, image, cfg.resolution)
+    err_i = rel_err(mine['I_nu'], gold['I_nu'])
+    assert err_i <= PIXEL_TOL, 'I_nu %.3e' % err_i
+    assert flux_rel(mine['I_nu'], gold['I_nu']) <= FLUX_TOL
+    errs = stokes_err(mine, gold)
+    for k, v in errs.items():
+        assert v <= PIXEL_TOL, '%s %.3e' % (k, v)
+    ctx.close()
+
+
+@pytest.mark.parametrize('over', [
+    {'camera_resolution': 24, 'image_polarization': 'true', 'image_rotation_split': 'true'},
+    {'camera_resolution': 20, 'image_polarization': 'true', 'plasma_power_frac': '0.5', 'plasma_p': '3.0',
+     'plasma_gamma_min': '4.0', 'plasma_gamma_max': '1000.0', 'plasma_kappa_frac': '0.25', 'plasma_kappa': '3.7', 'plasma_w': '1.5',
+     'image_tau': 'true', 'image_emission': 'true'},
+    {'camera_resolution': 20, 'image_polarization': 'true', 'simulation_a': '0.9', 'camera_th': '20.0', 'camera_rotation': '30.0',
+     'image_normalization': 'camera', 'camera_urn': '0.1'},
+])
+def test_live_reference_polarized(over, gpu, tmp_path):
+    if not os.path.exists(REF_BIN):
+        pytest.skip('oracle/_ref/blacklight not present')
+    case = Case(tmp_path, 'simulation.input', over)
+    ref = case.run_reference(checkpoints=False)
+    cfg, ctx, image, _, _ = run_gpu_level0(case)
+    mine = image_arrays(case, image, cfg.resolution)
+    assert rel_err(mine['I_nu'], ref['npz']['I_nu']) <= PIXEL_TOL
+    assert flux_rel(mine['I_nu'], ref['npz']['I_nu']) <= FLUX_TOL
+    for k, v in stokes_err(mine, ref['npz']).items():
+        assert v <= PIXEL_TOL, '%s %.3e' % (k, v)
+    for k in mine:
+        if not k.endswith('_nu'):
+            assert rel_err(mine[k], ref['npz'][k]) <= PIXEL_TOL, k
+    ctx.close()
+
+
+def test_golden_render(gpu, tmp_path):
+    base, over, mock = CASES['render_32']
+    gold = dict(np.load(os.path.join(GOLDEN, 'render_32.npz')))
+    case = Case(tmp_path, base, over, mock=mock)
+    cfg, ctx, image, render, _ = run_gpu_level0(case)
+    s = ctx.download_samples(0, arrays=False)
+    assert np.array_equal(s['num'], gold['sample_num'])
+    got = render.reshape(gold['rendering'].shape)
+    assert rel_err(got, gold['rendering']) <= PIXEL_TOL
+    ctx.close()
+
+
+def test_golden_true_color(gpu, tmp_path):
+    base, over, mock = CASES['true_color_16']
+    gold = dict(np.load(os.path.join(GOLDEN, 'true_color_16.npz')))
+    case = Case(tmp_path, base, over, mock=mock)
+    cfg, ctx, image, _, _ = run_gpu_level0(case)
+    mine = image_arrays(case, image, cfg.resolution)
+    assert mine['I_nu'].shape == gold['I_nu'].shape
+    assert rel_err(mine['I_nu'], gold['I_nu']) <= PIXEL_TOL
+    assert np.array_equal(np.load(os.path.join(GOLDEN, 'true_color_16.npz'))['frequency'], gold['frequency'])
+    ctx.close()
+
+
+def test_adaptive_drop_in(gpu, tmp_path):
+    """example_adaptive through the re-hosted main: refinement decisions, child block order, per-level images."""
+    base, over, mock = CASES['adaptive_32']
+    gold = dict(np.load(os.path.join(GOLDEN, 'adaptive_32.npz')))
+    case = Case(tmp_path, base, over, mock=mock)
+    npz, _ = case.run_gpu_file()
+    assert int(npz['adaptive_num_levels'][0]) == int(gold['adaptive_num_levels'][0])
+    assert np.array_equal(npz['adaptive_num_blocks'], gold['adaptive_num_blocks'])
+    for k in gold:
+        if k.startswith('adaptive_block_locs'):
+            assert np.array_equal(npz[k], gold[k]), k
+    for k in ('I_nu', 'tau', 'adaptive_I_nu_1', 'adaptive_tau_1'):
+        assert npz[k].shape == gold[k].shape, k
+        assert rel_err(npz[k], gold[k]) <= PIXEL_TOL, k
+    I = {'I_nu': gold['I_nu'], 'Q_nu': gold['Q_nu'], 'U_nu': gold['U_nu'], 'V_nu': gold['V_nu']}
+    for k, v in stokes_err({n: npz[n] for n in I}, I).items():
+        assert v <= PIXEL_TOL, k
