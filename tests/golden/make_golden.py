@@ -38,6 +38,8 @@ CASES = {
     'adaptive_32': ('adaptive.input', {}, None),
     'render_32': ('render.input', {'camera_resolution': 32}, None),
     'true_color_16': ('true_color.input', {'camera_resolution': 16}, None),
+    'formula_pinhole_pole_12': ('formula.input', {'camera_resolution': 12, 'camera_type': 'pinhole', 'camera_th': '180.0',
+                                                  'camera_r': '100.0', 'camera_urn': '-0.05', 'camera_rotation': '25.0'}, None),
 }
 
 
@@ -63,6 +65,9 @@ def main():
             out['sample_flags'] = geo['sample_flags']
             out['sample_num'] = geo['sample_num']
             out['geodesic_num_steps'] = np.int32(geo['geodesic_num_steps'])
+            for k in ('cam_x', 'u_con', 'u_cov', 'norm_con', 'norm_con_c', 'hor_con_c', 'vert_con_c', 'camera_pos',
+                      'camera_dir', 'momentum_factors', 'image_frequencies'):
+                out['geo_' + k] = geo[k]
             rays = np.unique(np.linspace(0, len(geo['sample_num']) - 1, 5).astype(int))
             out['probe_rays'] = rays
             for r in rays:
