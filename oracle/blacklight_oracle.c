@@ -1,0 +1,557 @@
+/* blacklight_oracle.c -- plain-C CPU restatement of the reference's per-pixel hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under blacklight_b200/ links, loads or calls this file; it exists so
+ * the parity tests have an independent, dependency-free statement of the algorithm (dense 4x4 tensor form,
+ * as the reference writes it) next to the unmodified reference binary (oracle/_ref/blacklight).  It is
+ * pinned against the golden fixtures produced by that binary (tests/test_cpu_oracle.py): sample counts,
+ * flags and every stored sample bit for bit, images to rounding.
+ *
+ * Covered (reference file:line):
+ *   Kerr-Schild metric, inverse, inverse derivative        geodesic_geometry.cpp:19-276
+ *   Hamiltonian right-hand side with proper distance       geodesics.cpp:867-893
+ *   Dormand-Prince RK5(4)7M integrator with dense output   geodesics.cpp:39-324
+ *   truncation, momentum renormalisation, reversal         geodesics.cpp:327-371, 808-849
+ *   formula-model coefficients                             formula_coefficients.cpp:25-183
+ *   grid sampling (block/cell search, nearest, trilinear)  simulation_sampling.cpp:122-575, 636-1044
+ *   thermal synchrotron I coefficients                     simulation_coefficients.cpp:254-524
+ *   fluid-frame tetrad                                     radiation_geometry.cpp:597-658
+ *   unpolarized transfer                                   unpolarized.cpp:31-221
+ * Build: gcc -O2 -ffp-contract=off (no FMA contraction, like the reference's -O3 without -march).
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define PI 3.141592653589793
+
+typedef struct {
+  double a;             /* spin, M = 1 */
+  int flat;
+  double camera_r, r_terminate, ray_step, tol_abs, tol_rel;
+  int max_steps, max_retries;
+} orc_geo;
+
+/* ---------------------------------------------------------------- geometry (geodesic_geometry.cpp) */
+
+static double ks_radius(double a, double x, double y, double z) {
+  double a2 = a * a;
+  double rr2 = x * x + y * y + z * z;
+  double r2 = 0.5 * (rr2 - a2 + hypot(rr2 - a2, 2.0 * a * z));
+  return sqrt(r2);
+}
+
+/* null vector pieces shared by the three metric routines */
+static void ks_null(double a, double x, double y, double z, double *f, double l[4], double *r_out, double *r2_out,
+                    double *rr2_out) {
+  double a2 = a * a;
+  double rr2 = x * x + y * y + z * z;
+  double r2 = 0.5 * (rr2 - a2 + hypot(rr2 - a2, 2.0 * a * z));
+  double r = sqrt(r2);
+  *f = 2.0 * 1.0 * r2 * r / (r2 * r2 + a2 * z * z);
+  l[1] = (r * x + a * y) / (r2 + a2);
+  l[2] = (r * y - a * x) / (r2 + a2);
+  l[3] = z / r;
+  *r_out = r; *r2_out = r2; *rr2_out = rr2;
+}
+
+static void metric_cov(const orc_geo *g, double x, double y, double z, double gc[4][4]) {
+  int m, n;
+  if (g->flat) {
+    for (m = 0; m < 4; m++) for (n = 0; n < 4; n++) gc[m][n] = m == n ? (m == 0 ? -1.0 : 1.0) : 0.0;
+    return;
+  }
+  double f, l[4], r, r2, rr2;
+  ks_null(g->a, x, y, z, &f, l, &r, &r2, &rr2);
+  l[0] = 1.0;
+  for (m = 0; m < 4; m++)
+    for (n = 0; n < 4; n++) {
+      double v = f * l[m] * l[n];
+      gc[m][n] = m == n ? (m == 0 ? v - 1.0 : v + 1.0) : v;
+    }
+}
+
+static void metric_con(const orc_geo *g, double x, double y, double z, double gc[4][4]) {
+  int m, n;
+  if (g->flat) {
+    for (m = 0; m < 4; m++) for (n = 0; n < 4; n++) gc[m][n] = m == n ? (m == 0 ? -1.0 : 1.0) : 0.0;
+    return;
+  }
+  double f, l[4], r, r2, rr2;
+  ks_null(g->a, x, y, z, &f, l, &r, &r2, &rr2);
+  l[0] = -1.0;
+  for (m = 0; m < 4; m++)
+    for (n = 0; n < 4; n++) {
+      double v = -f * l[m] * l[n];
+      gc[m][n] = m == n ? (m == 0 ? v - 1.0 : v + 1.0) : v;
+    }
+}
+
+static void metric_con_deriv(const orc_geo *g, double x, double y, double z, double dg[3][4][4]) {
+  int d, m, n;
+  if (g->flat) {
+    memset(dg, 0, 48 * sizeof(double));
+    return;
+  }
+  double a = g->a, a2 = a * a;
+  double f, l[4], r, r2, rr2;
+  ks_null(a, x, y, z, &f, l, &r, &r2, &rr2);
+  l[0] = -1.0;
+  double dr[3], df[3], dl[3][4];
+  dr[0] = r * x / (2.0 * r2 - rr2 + a2);
+  dr[1] = r * y / (2.0 * r2 - rr2 + a2);
+  dr[2] = (r * z + a2 * z / r) / (2.0 * r2 - rr2 + a2);
+  df[0] = -(r2 * r2 - 3.0 * a2 * z * z) * dr[0] / (r * (r2 * r2 + a2 * z * z)) * f;
+  df[1] = -(r2 * r2 - 3.0 * a2 * z * z) * dr[1] / (r * (r2 * r2 + a2 * z * z)) * f;
+  df[2] = -((r2 * r2 - 3.0 * a2 * z * z) * dr[2] + 2.0 * a2 * r * z) / (r * (r2 * r2 + a2 * z * z)) * f;
+  for (d = 0; d < 3; d++) dl[d][0] = 0.0;
+  dl[0][1] = ((x - 2.0 * r * l[1]) * dr[0] + r) / (r2 + a2);
+  dl[1][1] = ((x - 2.0 * r * l[1]) * dr[1] + a) / (r2 + a2);
+  dl[2][1] = (x - 2.0 * r * l[1]) * dr[2] / (r2 + a2);
+  dl[0][2] = ((y - 2.0 * r * l[2]) * dr[0] - a) / (r2 + a2);
+  dl[1][2] = ((y - 2.0 * r * l[2]) * dr[1] + r) / (r2 + a2);
+  dl[2][2] = (y - 2.0 * r * l[2]) * dr[2] / (r2 + a2);
+  dl[0][3] = -z / r2 * dr[0];
+  dl[1][3] = -z / r2 * dr[1];
+  dl[2][3] = -z / r2 * dr[2] + 1.0 / r;
+  for (d = 0; d < 3; d++)
+    for (m = 0; m < 4; m++)
+      for (n = 0; n < 4; n++)
+        dg[d][m][n] = -(df[d] * l[m] * l[n] + f * dl[d][m] * l[n] + f * l[m] * dl[d][n]);
+}
+
+/* dy/dlambda for y = (x^mu, p_mu, s)  (geodesics.cpp:867-893) */
+static void rhs(const orc_geo *g, const double y[9], double k[9]) {
+  double gcov[4][4], gcon[4][4], dg[3][4][4], t[4] = {0, 0, 0, 0};
+  int a, b, m, n, p;
+  metric_cov(g, y[1], y[2], y[3], gcov);
+  metric_con(g, y[1], y[2], y[3], gcon);
+  metric_con_deriv(g, y[1], y[2], y[3], dg);
+  for (p = 0; p < 9; p++) k[p] = 0.0;
+  for (m = 0; m < 4; m++)
+    for (n = 0; n < 4; n++) k[m] += gcon[m][n] * y[4 + n];
+  for (a = 1; a < 4; a++)
+    for (m = 0; m < 4; m++)
+      for (n = 0; n < 4; n++) k[4 + a] -= 0.5 * dg[a - 1][m][n] * y[4 + m] * y[4 + n];
+  for (a = 1; a < 4; a++)
+    for (m = 0; m < 4; m++) t[a] += (gcon[a][m] - gcon[0][a] * gcon[0][m] / gcon[0][0]) * y[4 + m];
+  for (a = 1; a < 4; a++)
+    for (b = 1; b < 4; b++) k[8] += gcov[a][b] * t[a] * t[b];
+  k[8] = -sqrt(k[8]);
+}
+
+/* rescale p_i so that g^{mu nu} p_mu p_nu = 0 (geodesics.cpp:296-309) */
+static void renormalize(const orc_geo *g, const double x[4], double p[4]) {
+  double gcon[4][4];
+  int a, b;
+  metric_con(g, x[1], x[2], x[3], gcon);
+  double qa = 0.0, qb = 0.0;
+  for (a = 1; a < 4; a++)
+    for (b = 1; b < 4; b++) qa += gcon[a][b] * p[a] * p[b];
+  for (a = 1; a < 4; a++) qb += 2.0 * gcon[0][a] * p[0] * p[a];
+  double qc = gcon[0][0] * p[0] * p[0];
+  double qd = sqrt(qb * qb - 4.0 * qa * qc);
+  double factor = qb < 0.0 ? (qd - qb) / (2.0 * qa) : -2.0 * qc / (qb + qd);
+  for (a = 1; a < 4; a++) p[a] *= factor;
+}
+
+static double dmax(double a, double b) { return a < b ? b : a; }
+static double dmin(double a, double b) { return b < a ? b : a; }
+
+/* ---------------------------------------------------------------- Dormand-Prince (geodesics.cpp:39-396) */
+
+/* Traces n_rays rays.  Outputs in the reference's sample_* layout (source->camera order, len > 0):
+ * pos, dir: (n_rays, cap, 4); len: (n_rays, cap); returns geodesic_num_steps (max sample_num). */
+int orc_trace_dp(const orc_geo *g, long n_rays, const double *cam_pos, const double *cam_dir, int cap, int *num,
+                 unsigned char *flags, double *pos, double *dir, double *len) {
+  static const double A[7][6] = {
+      {0}, {1.0 / 5.0}, {3.0 / 40.0, 9.0 / 40.0}, {44.0 / 45.0, -56.0 / 15.0, 32.0 / 9.0},
+      {19372.0 / 6561.0, -25360.0 / 2187.0, 64448.0 / 6561.0, -212.0 / 729.0},
+      {9017.0 / 3168.0, -355.0 / 33.0, 46732.0 / 5247.0, 49.0 / 176.0, -5103.0 / 18656.0},
+      {35.0 / 384.0, 0.0, 500.0 / 1113.0, 125.0 / 192.0, -2187.0 / 6784.0, 11.0 / 84.0}};
+  static const double B5[7] = {35.0 / 384.0, 0.0, 500.0 / 1113.0, 125.0 / 192.0, -2187.0 / 6784.0, 11.0 / 84.0, 0.0};
+  static const double B4[7] = {5179.0 / 57600.0, 0.0, 7571.0 / 16695.0, 393.0 / 640.0, -92097.0 / 339200.0,
+                               187.0 / 2100.0, 1.0 / 40.0};
+  static const double B4M[7] = {6025192743.0 / 30085553152.0, 0.0, 51252292925.0 / 65400821598.0,
+                                -2691868925.0 / 45128329728.0, 187940372067.0 / 1594534317056.0,
+                                -1776094331.0 / 19743644256.0, 11237099.0 / 235043384.0};
+  static const double D[7] = {-12715105075.0 / 11282082432.0, 0.0, 87487479700.0 / 32700410799.0,
+                              -10690763975.0 / 1880347072.0, 701980252875.0 / 199316789632.0,
+                              -1453857185.0 / 822651844.0, 69997945.0 / 29380423.0};
+  int steps_max = 0;
+  long m;
+#pragma omp parallel for schedule(dynamic, 4) reduction(max : steps_max)
+  for (m = 0; m < n_rays; m++) {
+    int ms = g->max_steps, p, q, s;
+    double *gp = (double *)malloc((size_t)ms * 9 * sizeof(double)); /* tracing-order scratch: pos4, dir4, len */
+    double y[9], yt[9], y5[9], y4[9], ym[8], k[7][9], rv[4][8];
+    for (p = 0; p < 4; p++) { y[p] = cam_pos[4 * m + p]; y[4 + p] = cam_dir[4 * m + p]; }
+    y[8] = 0.0;
+    for (p = 0; p < 9; p++) y5[p] = y[p];
+    double r_new = ks_radius(g->a, y[1], y[2], y[3]);
+    double h_new = -g->ray_step * r_new;
+    int retry = 0, fail = 0, flag = 0, count = 0, n = 0;
+    while (n < ms) {
+      if (retry > g->max_retries) { flag = 1; break; }
+      double h = h_new;
+      if (!fail && n > 0) for (p = 0; p < 9; p++) { y[p] = y5[p]; k[0][p] = k[6][p]; }
+      if (!fail && n == 0) rhs(g, y, k[0]);
+      double r = fail ? ks_radius(g->a, y[1], y[2], y[3]) : r_new;
+      for (s = 1; s < 7; s++) {
+        for (p = 0; p < 9; p++) yt[p] = y[p];
+        for (q = 0; q < s; q++) for (p = 0; p < 9; p++) yt[p] += A[s][q] * h * k[q][p];
+        rhs(g, yt, k[s]);
+      }
+      for (p = 0; p < 9; p++) y5[p] = y4[p] = y[p];
+      for (q = 0; q < 7; q++) for (p = 0; p < 9; p++) { y5[p] += B5[q] * h * k[q][p]; y4[p] += B4[q] * h * k[q][p]; }
+      r_new = ks_radius(g->a, y5[1], y5[2], y5[3]);
+      double err = 0.0;
+      for (p = 0; p < 8; p++) {
+        double scale = g->tol_abs + g->tol_rel * dmax(fabs(y[p]), fabs(y5[p]));
+        err = dmax(err, fabs(y5[p] - y4[p]) / scale);
+      }
+      if (!(err <= 1.0)) {
+        double fac = 0.2;
+        if (isfinite(err)) fac = dmax(0.9 * pow(err, -0.2), 0.2);
+        h_new = h * fac; retry++; fail = 1;
+        continue;
+      }
+      double fac = 10.0;
+      if (err > 0.0) fac = dmin(dmax(0.9 * pow(err, -0.2), 0.2), 10.0);
+      if (fail) fac = dmin(fac, 1.0);
+      h_new = h * fac; retry = 0; fail = 0;
+      for (p = 0; p < 8; p++) ym[p] = y[p];
+      for (q = 0; q < 7; q++) for (p = 0; p < 8; p++) ym[p] += B4M[q] * h * k[q][p];
+      double r_mid = ks_radius(g->a, ym[1], ym[2], ym[3]);
+      double ds_step = g->ray_step * r_mid, ds_full = y5[8] - y[8];
+      int n_ideal = (int)ceil(ds_full / ds_step), n_sub = n_ideal;
+      if (n_sub > ms - n) { n_sub = ms - n; flag = 1; }
+      if (n_ideal == 1) {
+        for (p = 0; p < 8; p++) gp[(size_t)n * 9 + p] = ym[p];
+        gp[(size_t)n * 9 + 8] = h;
+      } else if (n_ideal > 1) {
+        int nn;
+        for (p = 0; p < 8; p++) {
+          rv[0][p] = y5[p] - y[p];
+          rv[1][p] = y[p] - y5[p] + h * k[0][p];
+          rv[2][p] = 2.0 * (y5[p] - y[p]) - h * (k[0][p] + k[6][p]);
+          rv[3][p] = 0.0;
+        }
+        for (q = 0; q < 7; q++) for (p = 0; p < 8; p++) rv[3][p] += D[q] * h * k[q][p];
+        for (nn = 0; nn < n_sub; nn++) {
+          double fr = (nn + 0.5) / n_ideal;
+          for (p = 0; p < 8; p++)
+            gp[(size_t)(n + nn) * 9 + p] =
+                y[p] + fr * (rv[0][p] + (1.0 - fr) * (rv[1][p] + fr * (rv[2][p] + (1.0 - fr) * rv[3][p])));
+          gp[(size_t)(n + nn) * 9 + 8] = h / n_ideal;
+        }
+      }
+      renormalize(g, y5, y5 + 4);
+      count += n_sub;
+      if ((r_new > g->camera_r && r_new > r) || r_new < g->r_terminate) break;
+      if (n + n_sub >= ms) flag = 1;
+      n += n_sub;
+    }
+    /* truncate at the first sample beyond the boundaries (geodesics.cpp:327-349) */
+    if (count > 1) {
+      double rn = ks_radius(g->a, gp[1], gp[2], gp[3]);
+      for (n = 1; n < count; n++) {
+        double ro = rn;
+        rn = ks_radius(g->a, gp[(size_t)n * 9 + 1], gp[(size_t)n * 9 + 2], gp[(size_t)n * 9 + 3]);
+        if ((rn > g->camera_r && rn > ro) || rn < g->r_terminate) { count = n; break; }
+      }
+    }
+    /* renormalise stored momenta, reverse (geodesics.cpp:352-371, 808-849) */
+    for (n = 0; n < count; n++) {
+      renormalize(g, gp + (size_t)n * 9, gp + (size_t)n * 9 + 4);
+      size_t o = (size_t)m * cap + (size_t)(count - 1 - n);
+      for (p = 0; p < 4; p++) { pos[4 * o + p] = gp[(size_t)n * 9 + p]; dir[4 * o + p] = gp[(size_t)n * 9 + 4 + p]; }
+      len[o] = -gp[(size_t)n * 9 + 8];
+    }
+    num[m] = count;
+    flags[m] = (unsigned char)flag;
+    if (count > steps_max) steps_max = count;
+    free(gp);
+  }
+  return steps_max;
+}
+
+/* ---------------------------------------------------------------- unpolarized transfer (unpolarized.cpp:98-110) */
+
+static double transfer_step(double image, double j, double alpha, double dl_cgs) {
+  double dtau = alpha * dl_cgs;
+  if (alpha > 0.0) {
+    if (dtau <= 100.0) return exp(-dtau) * (image + j / alpha * expm1(dtau));
+    return j / alpha;
+  }
+  return image + j * dl_cgs;
+}
+
+/* ---------------------------------------------------------------- formula model (formula_coefficients.cpp) */
+
+typedef struct {
+  double a, camera_r, x_unit;
+  double r0, h, l0, q, nup, cn0, alpha, abs_a, beta;
+  int fallback_nan;
+} orc_formula;
+
+/* image: (F, n_rays).  Samples in the layout orc_trace_dp produces. */
+void orc_formula_image(const orc_formula *P, long n_rays, int cap, const int *num, const unsigned char *flags,
+                       const double *pos, const double *dir, const double *len, const double *mom_factor,
+                       int F, const double *freqs, double *image) {
+  long m;
+#pragma omp parallel for schedule(dynamic, 4)
+  for (m = 0; m < n_rays; m++) {
+    int l, n;
+    for (l = 0; l < F; l++) {
+      double I = 0.0;
+      for (n = 0; n < num[m]; n++) {
+        size_t o = (size_t)m * cap + n;
+        double x = pos[4 * o + 1], y = pos[4 * o + 2], z = pos[4 * o + 3];
+        const double *k = dir + 4 * o;
+        double j = 0.0, al = 0.0;
+        double dl_cgs = len[o] * P->x_unit / (freqs[l] * mom_factor[m]);
+        if (P->fallback_nan && flags[m]) {
+          if (l == 0) j = al = NAN;
+        } else {
+          double a = P->a, r = ks_radius(a, x, y, z);
+          if (!(r > P->camera_r)) {
+            double rr = sqrt(r * r - z * z), cth = z / r, sth = sqrt(1.0 - cth * cth);
+            double ph = atan2(y, x) - atan(a / r), sph = sin(ph), cph = cos(ph);
+            double delta = r * r - 2.0 * 1.0 * r + a * a, sigma = r * r + a * a * cth * cth;
+            double gtt = -(1.0 + 2.0 * 1.0 * r * (r * r + a * a) / (delta * sigma));
+            double gtph = -2.0 * 1.0 * a * r / (delta * sigma);
+            double grr = delta / sigma, gthth = 1.0 / sigma;
+            double gphph = (sigma - 2.0 * 1.0 * r) / (delta * sigma * sth * sth);
+            double ll = P->l0 / (1.0 + rr) * pow(rr, 1.0 + P->q);
+            double un = 1.0 / sqrt(-gtt + 2.0 * gtph * ll - gphph * ll * ll);
+            double u_t = -un, u_ph = un * ll;
+            double ut_bl = gtt * u_t + gtph * u_ph, ur_bl = grr * 0.0, uth_bl = gthth * 0.0;
+            double uph_bl = gtph * u_t + gphph * u_ph;
+            double ut = ut_bl + 2.0 * 1.0 * r / delta * ur_bl, ur = ur_bl, uth = uth_bl, uph = uph_bl + a / delta * ur_bl;
+            double u0 = ut;
+            double u1 = sth * cph * ur + cth * (r * cph - a * sph) * uth + sth * (-r * sph - a * cph) * uph;
+            double u2 = sth * sph * ur + cth * (r * sph + a * cph) * uth + sth * (r * cph - a * sph) * uph;
+            double u3 = cth * ur - r * sth * uth;
+            double nn0 = exp(-0.5 * (r * r / (P->r0 * P->r0) + P->h * P->h * cth * cth));
+            double nu = -(u0 * k[0] + u1 * k[1] + u2 * k[2] + u3 * k[3]) * freqs[l] * mom_factor[m];
+            double jn = P->cn0 * nn0 * pow(nu / P->nup, -P->alpha);
+            j = jn / (nu * nu);
+            double an = P->abs_a * P->cn0 * nn0 * pow(nu / P->nup, -P->beta - P->alpha);
+            al = an * nu;
+          }
+        }
+        I = transfer_step(I, j, al, dl_cgs);
+      }
+      image[(size_t)l * n_rays + m] = I * (freqs[l] * freqs[l] * freqs[l]);
+    }
+  }
+}
+
+/* ---------------------------------------------------------------- simulation model */
+
+typedef struct {
+  double a, camera_r, x_unit;
+  int n_b, n_k, n_j, n_i, interp, fallback_nan;
+  double d_unit, mu, ne_ni, rat_low, rat_high;
+  double cut_sigma_max;   /* < 0 disables; the other value cuts of the examples are disabled */
+} orc_sim;
+
+static double g4(const float *prim, const orc_sim *P, int v, int b, int k, int j, int i) {
+  return (double)prim[((((size_t)v * P->n_b + b) * P->n_k + k) * P->n_j + j) * P->n_i + i];
+}
+
+static double trilinear(const float *prim, const orc_sim *P, int v, int b, int k, int j, int i, double fk, double fj,
+                        double fi) {
+  return (1.0 - fk) * (1.0 - fj) * (1.0 - fi) * g4(prim, P, v, b, k, j, i) +
+         (1.0 - fk) * (1.0 - fj) * fi * g4(prim, P, v, b, k, j, i + 1) +
+         (1.0 - fk) * fj * (1.0 - fi) * g4(prim, P, v, b, k, j + 1, i) + (1.0 - fk) * fj * fi * g4(prim, P, v, b, k, j + 1, i + 1) +
+         fk * (1.0 - fj) * (1.0 - fi) * g4(prim, P, v, b, k + 1, j, i) + fk * (1.0 - fj) * fi * g4(prim, P, v, b, k + 1, j, i + 1) +
+         fk * fj * (1.0 - fi) * g4(prim, P, v, b, k + 1, j + 1, i) + fk * fj * fi * g4(prim, P, v, b, k + 1, j + 1, i + 1);
+}
+
+/* orthonormal tetrad (radiation_geometry.cpp:597-658) */
+static void tetrad(const double ucon[4], const double ucov[4], const double kcon[4], const double kcov[4],
+                   const double up[4], double gcov[4][4], double gcon[4][4], double e[4][4]) {
+  int m, n;
+  double omega = 0.0, kup = 0.0, uup = 0.0, norm = 0.0, c[4];
+  for (m = 0; m < 4; m++) omega -= kcov[m] * ucon[m];
+  for (m = 0; m < 4; m++) kup += kcov[m] * up[m];
+  kup /= omega;
+  for (m = 0; m < 4; m++) uup += ucov[m] * up[m];
+  uup /= omega;
+  for (m = 0; m < 4; m++) e[0][m] = ucon[m];
+  for (m = 0; m < 4; m++) e[3][m] = kcon[m] / omega - ucon[m];
+  for (m = 0; m < 4; m++) e[2][m] = up[m] - kup * e[3][m] + uup * kcon[m];
+  for (m = 0; m < 4; m++) for (n = 0; n < 4; n++) norm += gcov[m][n] * e[2][m] * e[2][n];
+  norm = sqrt(norm);
+  for (m = 0; m < 4; m++) e[2][m] /= norm;
+  /* e_1 = Levi-Civita contraction of e_0, e_2, e_3 (covariant), raised */
+  static const int perm[4][3] = {{1, 2, 3}, {0, 2, 3}, {0, 1, 3}, {0, 1, 2}};
+  for (m = 0; m < 4; m++) {
+    int i0 = perm[m][0], i1 = perm[m][1], i2 = perm[m][2];
+    double det = e[0][i0] * (e[2][i1] * e[3][i2] - e[2][i2] * e[3][i1]) + e[0][i1] * (e[2][i2] * e[3][i0] - e[2][i0] * e[3][i2]) +
+                 e[0][i2] * (e[2][i0] * e[3][i1] - e[2][i1] * e[3][i0]);
+    c[m] = (m % 2 == 0) ? -det : det;
+  }
+  for (m = 0; m < 4; m++) {
+    e[1][m] = 0.0;
+    for (n = 0; n < 4; n++) e[1][m] += gcon[m][n] * c[n];
+  }
+}
+
+/* Per-sample thermal coefficients + transfer on an SKS grid.  image: (n_rays); inds out: (n_rays,cap,4) or NULL
+ * (entries of cut / off-grid samples are left at -1).  One frequency, ti_te_beta model with plasma_use_p. */
+void orc_simulation_image(const orc_sim *P, long n_rays, int cap, const int *num, const unsigned char *flags,
+                          const double *pos, const double *dir, const double *len, const double *mom_factor,
+                          double freq, const double *x1f, const double *x2f, const double *x3f, const double *x1v,
+                          const double *x2v, const double *x3v, const float *prim, double *image, int *inds) {
+  const double c = 2.99792458e10, hpl = 6.62607015e-27, m_p = 1.67262192369e-24, m_e = 9.1093837015e-28, qe = 4.80320425e-10;
+  const double e_unit = P->d_unit * c * c, b_unit = sqrt(4.0 * PI * e_unit);
+  orc_geo geo;
+  memset(&geo, 0, sizeof geo);
+  geo.a = P->a;
+  long m;
+#pragma omp parallel for schedule(dynamic, 4)
+  for (m = 0; m < n_rays; m++) {
+    int n, b = 0, i, j, k, mu, nu_;
+    double I = 0.0;
+    int n_i = P->n_i, n_j = P->n_j, n_k = P->n_k;
+    for (n = 0; n < num[m]; n++) {
+      size_t o = (size_t)m * cap + n;
+      double x = pos[4 * o + 1], y = pos[4 * o + 2], z = pos[4 * o + 3];
+      const double *kcov = dir + 4 * o;
+      double dl_cgs = len[o] * P->x_unit / (freq * mom_factor[m]);
+      double jv = 0.0, av = 0.0;
+      double rho, pgas, uu[3], bb[3];
+      int have = 0;
+      if (inds) for (i = 0; i < 4; i++) inds[4 * o + i] = -1;
+      if (P->fallback_nan && flags[m]) {
+        rho = pgas = uu[0] = uu[1] = uu[2] = bb[0] = bb[1] = bb[2] = NAN;
+        have = 1;
+      } else {
+        double a = P->a, r = ks_radius(a, x, y, z);
+        if (!(r > P->camera_r)) {
+          double x1 = r, x2 = acos(z / r), x3 = atan2(y, x) - atan(a / r);
+          x3 += x3 < 0.0 ? 2.0 * PI : 0.0;
+          x3 -= x3 >= 2.0 * PI ? 2.0 * PI : 0.0;
+          /* block: keep while inside (inclusive), else first match (simulation_sampling.cpp:352-394) */
+          if (x1 < x1f[(size_t)b * (n_i + 1)] || x1 > x1f[(size_t)b * (n_i + 1) + n_i] || x2 < x2f[(size_t)b * (n_j + 1)] ||
+              x2 > x2f[(size_t)b * (n_j + 1) + n_j] || x3 < x3f[(size_t)b * (n_k + 1)] || x3 > x3f[(size_t)b * (n_k + 1) + n_k]) {
+            int bn;
+            for (bn = 0; bn < P->n_b; bn++)
+              if (x1 >= x1f[(size_t)bn * (n_i + 1)] && x1 <= x1f[(size_t)bn * (n_i + 1) + n_i] && x2 >= x2f[(size_t)bn * (n_j + 1)] &&
+                  x2 <= x2f[(size_t)bn * (n_j + 1) + n_j] && x3 >= x3f[(size_t)bn * (n_k + 1)] && x3 <= x3f[(size_t)bn * (n_k + 1) + n_k])
+                break;
+            if (bn == P->n_b) {
+              if (P->fallback_nan) { rho = pgas = uu[0] = uu[1] = uu[2] = bb[0] = bb[1] = bb[2] = NAN; have = 1; }
+              goto sampled;
+            }
+            b = bn;
+          }
+          for (i = 0; i < n_i; i++) if (x1f[(size_t)b * (n_i + 1) + i + 1] >= x1) break;
+          for (j = 0; j < n_j; j++) if (x2f[(size_t)b * (n_j + 1) + j + 1] >= x2) break;
+          for (k = 0; k < n_k; k++) if (x3f[(size_t)b * (n_k + 1) + k + 1] >= x3) break;
+          if (!P->interp) {
+            if (inds) { inds[4 * o] = b; inds[4 * o + 1] = k; inds[4 * o + 2] = j; inds[4 * o + 3] = i; }
+            rho = g4(prim, P, 0, b, k, j, i); pgas = g4(prim, P, 1, b, k, j, i);
+            for (mu = 0; mu < 3; mu++) { uu[mu] = g4(prim, P, 2 + mu, b, k, j, i); bb[mu] = g4(prim, P, 5 + mu, b, k, j, i); }
+          } else {
+            const double *v1 = x1v + (size_t)b * n_i, *v2 = x2v + (size_t)b * n_j, *v3 = x3v + (size_t)b * n_k;
+            int im = (i == 0 || (i != n_i - 1 && x1 >= v1[i])) ? i : i - 1;
+            int jm = (j == 0 || (j != n_j - 1 && x2 >= v2[j])) ? j : j - 1;
+            int km = (k == 0 || (k != n_k - 1 && x3 >= v3[k])) ? k : k - 1;
+            double fi = (x1 - v1[im]) / (v1[im + 1] - v1[im]);
+            double fj = (x2 - v2[jm]) / (v2[jm + 1] - v2[jm]);
+            double fk = (x3 - v3[km]) / (v3[km + 1] - v3[km]);
+            if (inds) { inds[4 * o] = b; inds[4 * o + 1] = km; inds[4 * o + 2] = jm; inds[4 * o + 3] = im; }
+            rho = trilinear(prim, P, 0, b, km, jm, im, fk, fj, fi);
+            pgas = trilinear(prim, P, 1, b, km, jm, im, fk, fj, fi);
+            if (rho <= 0.0) rho = g4(prim, P, 0, b, km, jm, im);
+            if (pgas <= 0.0) pgas = g4(prim, P, 1, b, km, jm, im);
+            for (mu = 0; mu < 3; mu++) {
+              uu[mu] = trilinear(prim, P, 2 + mu, b, km, jm, im, fk, fj, fi);
+              bb[mu] = trilinear(prim, P, 5 + mu, b, km, jm, im, fk, fj, fi);
+            }
+          }
+          /* sampled values are stored as float (simulation_sampling.cpp:830-839) */
+          rho = (double)(float)rho; pgas = (double)(float)pgas;
+          for (mu = 0; mu < 3; mu++) { uu[mu] = (double)(float)uu[mu]; bb[mu] = (double)(float)bb[mu]; }
+          have = 1;
+        }
+      }
+    sampled:
+      if (have) {
+        /* plasma state (simulation_coefficients.cpp:286-348) */
+        double a = P->a, a2 = a * a;
+        double rr2 = x * x + y * y + z * z;
+        double r2 = 0.5 * (rr2 - a2 + hypot(rr2 - a2, 2.0 * a * z)), r = sqrt(r2);
+        double cth = z / r, cth2 = cth * cth, sth2 = 1.0 - cth2, sigma_ks = r2 + a2 * cth2, delta = r2 - 2.0 * r + a2;
+        double gs[4][4], gc[4][4];
+        memset(gs, 0, sizeof gs); memset(gc, 0, sizeof gc);
+        gs[0][0] = -(1.0 - 2.0 * r / sigma_ks); gs[0][1] = gs[1][0] = 2.0 * r / sigma_ks;
+        gs[0][3] = gs[3][0] = -2.0 * a * r * sth2 / sigma_ks; gs[1][1] = 1.0 + 2.0 * r / sigma_ks;
+        gs[1][3] = gs[3][1] = -(1.0 + 2.0 * r / sigma_ks) * a * sth2; gs[2][2] = sigma_ks;
+        gs[3][3] = (r2 + a2 + 2.0 * a2 * r * sth2 / sigma_ks) * sth2;
+        gc[0][0] = -(1.0 + 2.0 * r / sigma_ks); gc[0][1] = gc[1][0] = 2.0 * r / sigma_ks; gc[1][1] = delta / sigma_ks;
+        gc[1][3] = gc[3][1] = a / sigma_ks; gc[2][2] = 1.0 / sigma_ks; gc[3][3] = 1.0 / (sigma_ks * sth2);
+        double rho_cgs = rho * P->d_unit, pgas_cgs = pgas * e_unit;
+        double n_e = rho_cgs / (P->mu * m_p) / (1.0 + 1.0 / P->ne_ni);
+        double uu0 = sqrt(1.0 + gs[1][1] * uu[0] * uu[0] + 2.0 * gs[1][2] * uu[0] * uu[1] + 2.0 * gs[1][3] * uu[0] * uu[2] +
+                          gs[2][2] * uu[1] * uu[1] + 2.0 * gs[2][3] * uu[1] * uu[2] + gs[3][3] * uu[2] * uu[2]);
+        double lapse = 1.0 / sqrt(-gc[0][0]);
+        double us[4], ul[4] = {0, 0, 0, 0}, bs[4], bl_[4] = {0, 0, 0, 0}, b_sq = 0.0;
+        us[0] = uu0 / lapse;
+        for (mu = 1; mu < 4; mu++) us[mu] = uu[mu - 1] - (-gc[0][mu] / gc[0][0]) * uu0 / lapse;
+        for (mu = 0; mu < 4; mu++) for (nu_ = 0; nu_ < 4; nu_++) ul[mu] += gs[mu][nu_] * us[nu_];
+        bs[0] = ul[1] * bb[0] + ul[2] * bb[1] + ul[3] * bb[2];
+        for (mu = 1; mu < 4; mu++) bs[mu] = (bb[mu - 1] + bs[0] * us[mu]) / us[0];
+        for (mu = 0; mu < 4; mu++) for (nu_ = 0; nu_ < 4; nu_++) bl_[mu] += gs[mu][nu_] * bs[nu_];
+        for (mu = 0; mu < 4; mu++) b_sq += bl_[mu] * bs[mu];
+        double bb_cgs = sqrt(b_sq) * b_unit, sig = b_sq / rho, beta_inv = b_sq / (2.0 * pgas);
+        double tti_tte = (P->rat_high + P->rat_low * beta_inv * beta_inv) / (1.0 + beta_inv * beta_inv);
+        double kb_tot = P->mu * m_p * pgas_cgs / rho_cgs;
+        double kb_te = (1.0 + P->ne_ni) / (tti_tte + P->ne_ni) * kb_tot;
+        double theta_e = kb_te / (m_e * c * c);
+        int cut = P->cut_sigma_max >= 0.0 && sig > P->cut_sigma_max;
+        if (!cut && !(bb[0] == 0.0 && bb[1] == 0.0 && bb[2] == 0.0)) {
+          /* to CKS, tetrad, pitch angle (simulation_coefficients.cpp:397-455) */
+          double sth = sqrt(1.0 - cth * cth), ph = atan2(y, x) - atan(a / r), sph = sin(ph), cph = cos(ph);
+          double jac[4][4];
+          memset(jac, 0, sizeof jac);
+          jac[0][0] = 1.0;
+          jac[1][1] = sth * cph; jac[1][2] = cth * (r * cph - a * sph); jac[1][3] = sth * (-r * sph - a * cph);
+          jac[2][1] = sth * sph; jac[2][2] = cth * (r * sph + a * cph); jac[2][3] = sth * (r * cph - a * sph);
+          jac[3][1] = cth; jac[3][2] = -r * sth;
+          double ucon[4] = {0, 0, 0, 0}, bcon[4] = {0, 0, 0, 0}, kcon[4] = {0, 0, 0, 0}, ucov[4] = {0, 0, 0, 0}, bcov[4] = {0, 0, 0, 0};
+          double gcov[4][4], gcon[4][4], e[4][4];
+          for (mu = 0; mu < 4; mu++) for (nu_ = 0; nu_ < 4; nu_++) { ucon[mu] += jac[mu][nu_] * us[nu_]; bcon[mu] += jac[mu][nu_] * bs[nu_]; }
+          metric_cov(&geo, x, y, z, gcov);
+          metric_con(&geo, x, y, z, gcon);
+          for (mu = 0; mu < 4; mu++) for (nu_ = 0; nu_ < 4; nu_++) {
+            kcon[mu] += gcon[mu][nu_] * kcov[nu_]; ucov[mu] += gcov[mu][nu_] * ucon[nu_]; bcov[mu] += gcov[mu][nu_] * bcon[nu_];
+          }
+          tetrad(ucon, ucov, kcon, kcov, bcon, gcov, gcon, e);
+          double kt[3] = {0, 0, 0}, bt[3] = {0, 0, 0};
+          for (mu = 0; mu < 4; mu++) for (i = 0; i < 3; i++) { kt[i] += e[1 + i][mu] * kcov[mu]; bt[i] += e[1 + i][mu] * bcov[mu]; }
+          double ksq = kt[0] * kt[0] + kt[1] * kt[1] + kt[2] * kt[2], bsq = bt[0] * bt[0] + bt[1] * bt[1] + bt[2] * bt[2];
+          double kb = kt[0] * bt[0] + kt[1] * bt[1] + kt[2] * bt[2];
+          double cos2 = dmin(kb * kb / (ksq * bsq), 1.0), sin_t = sqrt(1.0 - cos2);
+          /* thermal emissivity and Kirchhoff absorptivity (simulation_coefficients.cpp:458-524) */
+          double nu = 0.0;
+          for (mu = 0; mu < 4; mu++) nu -= kcov[mu] * ucon[mu];
+          nu *= freq * mom_factor[m];
+          double nu_c = qe * bb_cgs / (2.0 * PI * m_e * c), nu_s = 2.0 / 9.0 * nu_c * theta_e * theta_e * sin_t;
+          double xx = nu / nu_s, x12 = sqrt(xx), x13 = cbrt(xx), x16 = sqrt(x13);
+          double coef = 1.0 * n_e * qe * qe * nu_c / (c * (nu * nu)) * exp(-x13);
+          double va = 1.4142135623730951 * PI / 27.0 * sin_t, vb = pow(2.0, 11.0 / 12.0), vc = x12 + vb * x16;
+          jv = coef * va * vc * vc;
+          double bnu = 2.0 * hpl / (c * c) / expm1(hpl * nu / kb_te);
+          av = jv / bnu;
+          if (1.0 / (av * av) == INFINITY) av = 0.0;
+        }
+      }
+      I = transfer_step(I, jv, av, dl_cgs);
+    }
+    image[m] = I * (freq * freq * freq);
+  }
+}

@@ -1,0 +1,95 @@
+"""ctypes face of the plain-C restatement (oracle/blacklight_oracle.c).  TEST INFRASTRUCTURE ONLY."""
+import ctypes
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, '_ref', 'libblacklight_oracle.so')
+
+
+class Geo(ctypes.Structure):
+    _fields_ = [('a', ctypes.c_double), ('flat', ctypes.c_int), ('camera_r', ctypes.c_double),
+                ('r_terminate', ctypes.c_double), ('ray_step', ctypes.c_double), ('tol_abs', ctypes.c_double),
+                ('tol_rel', ctypes.c_double), ('max_steps', ctypes.c_int), ('max_retries', ctypes.c_int)]
+
+
+class Formula(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_double) for n in ('a', 'camera_r', 'x_unit', 'r0', 'h', 'l0', 'q', 'nup', 'cn0', 'alpha',
+                                               'abs_a', 'beta')] + [('fallback_nan', ctypes.c_int)]
+
+
+class Sim(ctypes.Structure):
+    _fields_ = [('a', ctypes.c_double), ('camera_r', ctypes.c_double), ('x_unit', ctypes.c_double)] + \
+               [(n, ctypes.c_int) for n in ('n_b', 'n_k', 'n_j', 'n_i', 'interp', 'fallback_nan')] + \
+               [(n, ctypes.c_double) for n in ('d_unit', 'mu', 'ne_ni', 'rat_low', 'rat_high', 'cut_sigma_max')]
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(LIB)
+        _lib.orc_trace_dp.restype = ctypes.c_int
+    return _lib
+
+
+def r_terminate(kv, a):
+    r_h = 1.0 + np.sqrt(1.0 - a * a)
+    mode = kv['ray_terminate']
+    if mode == 'photon':
+        return 2.0 * (1.0 + np.cos(2.0 / 3.0 * np.arccos(-abs(a))))
+    return r_h * float(kv['ray_factor']) if mode == 'multiplicative' else r_h + float(kv['ray_factor'])
+
+
+def trace(kv, a, cam_pos, cam_dir):
+    g = Geo(a=a, flat=int(kv['ray_flat'] == 'true'), camera_r=float(kv['camera_r']), r_terminate=r_terminate(kv, a),
+            ray_step=float(kv['ray_step']), tol_abs=float(kv['ray_tol_abs']), tol_rel=float(kv['ray_tol_rel']),
+            max_steps=int(kv['ray_max_steps']), max_retries=int(kv['ray_max_retries']))
+    n, cap = len(cam_pos), g.max_steps
+    num, flags = np.zeros(n, np.int32), np.zeros(n, np.uint8)
+    pos, dirs, length = np.zeros((n, cap, 4)), np.zeros((n, cap, 4)), np.zeros((n, cap))
+    steps = lib().orc_trace_dp(ctypes.byref(g), ctypes.c_long(n), _p(np.ascontiguousarray(cam_pos)),
+                               _p(np.ascontiguousarray(cam_dir)), cap, _p(num), _p(flags), _p(pos), _p(dirs), _p(length))
+    return dict(num=num, flags=flags, pos=pos, dir=dirs, len=length, steps=steps, cap=cap)
+
+
+C, GG_MSUN = 2.99792458e10, 1.32712440018e26
+
+
+def formula_image(kv, s, mom, freqs):
+    a = float(kv['formula_spin'])
+    mass_msun = float(kv['formula_mass']) * C * C / GG_MSUN
+    P = Formula(a=a, camera_r=float(kv['camera_r']), x_unit=GG_MSUN * mass_msun / (C * C), r0=float(kv['formula_r0']),
+                h=float(kv['formula_h']), l0=float(kv['formula_l0']), q=float(kv['formula_q']), nup=float(kv['formula_nup']),
+                cn0=float(kv['formula_cn0']), alpha=float(kv['formula_alpha']), abs_a=float(kv['formula_a']),
+                beta=float(kv['formula_beta']), fallback_nan=int(kv['fallback_nan'] == 'true'))
+    n, F = len(mom), len(freqs)
+    image = np.zeros((F, n))
+    freqs = np.ascontiguousarray(freqs, np.float64)
+    lib().orc_formula_image(ctypes.byref(P), ctypes.c_long(n), s['cap'], _p(s['num']), _p(s['flags']), _p(s['pos']),
+                            _p(s['dir']), _p(s['len']), _p(np.ascontiguousarray(mom)), F, _p(freqs), _p(image))
+    return image
+
+
+def simulation_image(kv, s, mom, grid, want_inds=True):
+    a = float(kv['simulation_a'])
+    P = Sim(a=a, camera_r=float(kv['camera_r']), x_unit=GG_MSUN * float(kv['simulation_m_msun']) / (C * C),
+            n_b=grid['n_b'], n_k=grid['n_k'], n_j=grid['n_j'], n_i=grid['n_i'], interp=int(kv['simulation_interp'] == 'true'),
+            fallback_nan=int(kv['fallback_nan'] == 'true'), d_unit=float(kv['simulation_rho_cgs']), mu=float(kv['plasma_mu']),
+            ne_ni=float(kv['plasma_ne_ni']), rat_low=float(kv['plasma_rat_low']), rat_high=float(kv['plasma_rat_high']),
+            cut_sigma_max=float(kv['cut_sigma_max']))
+    n = len(mom)
+    image = np.zeros(n)
+    inds = np.full((n, s['cap'], 4), -1, np.int32) if want_inds else None
+    keep = [np.ascontiguousarray(grid[k]) for k in ('x1f', 'x2f', 'x3f', 'x1v', 'x2v', 'x3v', 'prim')]
+    lib().orc_simulation_image(ctypes.byref(P), ctypes.c_long(n), s['cap'], _p(s['num']), _p(s['flags']), _p(s['pos']),
+                               _p(s['dir']), _p(s['len']), _p(np.ascontiguousarray(mom)), ctypes.c_double(float(kv['image_frequency'])),
+                               *[_p(k) for k in keep], _p(image), _p(inds))
+    return image, inds
