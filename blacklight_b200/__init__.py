@@ -64,7 +64,7 @@ def load_library():
         'bl_refine_level': (i32, [vp, i32, vp, i64, vp, ctypes.POINTER(i64)]),
         'bl_set_taps': (i32, [vp, i32]),
         'bl_retrace_level': (i32, [vp, i32, ctypes.POINTER(LevelStats)]),
-        'bl_launch_count': (ctypes.c_longlong, [vp]),
+        'bl_launch_count': (ctypes.c_longlong, [vp]), 'bl_cuda_stream': (vp, [vp]),
         'bl_download_samples': (i32, [vp, i32, vp, vp, vp, vp, vp]),
         'bl_download_sample_inds': (i32, [vp, i32, vp, vp, vp, vp, vp]),
         'bl_device_info': (i32, [vp, ctypes.c_char_p, i32, ctypes.POINTER(i32), ctypes.POINTER(dbl)]),
@@ -230,6 +230,10 @@ class Context:
 
     def launch_count(self):
         return int(_lib.bl_launch_count(self._h))
+
+    def cuda_stream(self):
+        """cudaStream_t (as an integer) that this context's kernels and copies are issued on."""
+        return int(_lib.bl_cuda_stream(self._h) or 0)
 
     def radiate_level(self, level, snapshot=0, image=None, render=None, num_render=0, download=True):
         n = self._rays[level]

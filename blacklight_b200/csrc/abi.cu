@@ -581,40 +581,53 @@ int bl_trace_level(bl_ctx *ctx, int level, const double *cam_pos, const double *
   if (!cam_pos || !cam_dir || !mom_factor || num_rays < 0) return bl_fail(ctx, BL_ERR_ARG, "bl_trace_level: null camera arrays");
   BL_CUDA_CHECK(cudaSetDevice(ctx->device));
   Level &L = ctx->levels[level];
-  free_level(L);
+  // Device buffers are kept when the ray count is unchanged (time series, repeated renders): a
+  // cudaFree/cudaMalloc pair of a ~100 GB step buffer costs far more than the kernels themselves.
+  const bool reuse = L.rays == num_rays && num_rays > 0 && L.cam_pos && L.step;
+  if (reuse) {
+    cudaFree(L.tap_inds); cudaFree(L.tap_fracs); cudaFree(L.tap_nan); cudaFree(L.tap_cut); cudaFree(L.tap_fb);
+    L.tap_inds = nullptr; L.tap_fracs = nullptr; L.tap_nan = L.tap_cut = L.tap_fb = nullptr; L.tap_S = 0;
+    L.traced = false;
+  } else {
+    free_level(L);
+  }
   L.rays = num_rays;
   if (num_rays == 0) { L.traced = true; L.resident = true; if (stats) *stats = L.stats; return BL_OK; }
   const int Q = ctx->rad.num_quantities, R = ctx->rad.render_num_images;
-  BL_CUDA_CHECK(dev_alloc(&L.cam_pos, (size_t)num_rays * 4));
-  BL_CUDA_CHECK(dev_alloc(&L.cam_dir, (size_t)num_rays * 4));
-  BL_CUDA_CHECK(dev_alloc(&L.mom, (size_t)num_rays));
-  BL_CUDA_CHECK(dev_alloc(&L.num, (size_t)num_rays));
-  BL_CUDA_CHECK(dev_alloc(&L.flags, (size_t)num_rays));
-  BL_CUDA_CHECK(dev_alloc(&L.image, (size_t)num_rays * (size_t)(Q > 0 ? Q : 1)));
-  if (R > 0) BL_CUDA_CHECK(dev_alloc(&L.render, (size_t)num_rays * 3 * R));
+  if (!reuse) {
+    BL_CUDA_CHECK(dev_alloc(&L.cam_pos, (size_t)num_rays * 4));
+    BL_CUDA_CHECK(dev_alloc(&L.cam_dir, (size_t)num_rays * 4));
+    BL_CUDA_CHECK(dev_alloc(&L.mom, (size_t)num_rays));
+    BL_CUDA_CHECK(dev_alloc(&L.num, (size_t)num_rays));
+    BL_CUDA_CHECK(dev_alloc(&L.flags, (size_t)num_rays));
+    BL_CUDA_CHECK(dev_alloc(&L.image, (size_t)num_rays * (size_t)(Q > 0 ? Q : 1)));
+    if (R > 0) BL_CUDA_CHECK(dev_alloc(&L.render, (size_t)num_rays * 3 * R));
+  }
   BL_CUDA_CHECK(cudaMemcpyAsync(L.cam_pos, cam_pos, (size_t)num_rays * 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   BL_CUDA_CHECK(cudaMemcpyAsync(L.cam_dir, cam_dir, (size_t)num_rays * 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   BL_CUDA_CHECK(cudaMemcpyAsync(L.mom, mom_factor, (size_t)num_rays * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
 
-  // wave size from the HBM budget: 72 bytes per sample slot, ray_max_steps slots per ray
-  size_t fr = 0, tot = 0;
-  BL_CUDA_CHECK(cudaMemGetInfo(&fr, &tot));
-  size_t per_ray = (size_t)ctx->params.ray_max_steps * 9 * sizeof(double);
-  size_t budget = (size_t)((double)fr * 0.80);
-  int64_t fit = (int64_t)(budget / per_ray);
-  if (ctx->params.tile_rays > 0 && ctx->params.tile_rays < fit) fit = ctx->params.tile_rays;
-  if (fit < 128) return bl_fail(ctx, BL_ERR_NOMEM, "not enough free HBM for a 128-ray wave (%zu bytes per ray)", per_ray);
-  if (fit >= num_rays) {
-    L.wave_rays = num_rays;
-    L.resident = true;
-  } else {
-    // split into equal waves (multiples of 128 rays) and keep headroom for other levels
-    int64_t waves = (num_rays + fit - 1) / fit;
-    int64_t w = (num_rays + waves - 1) / waves;
-    L.wave_rays = (w + 127) / 128 * 128;
-    L.resident = false;
+  if (!reuse) {
+    // wave size from the HBM budget: 72 bytes per sample slot, ray_max_steps slots per ray
+    size_t fr = 0, tot = 0;
+    BL_CUDA_CHECK(cudaMemGetInfo(&fr, &tot));
+    size_t per_ray = (size_t)ctx->params.ray_max_steps * 9 * sizeof(double);
+    size_t budget = (size_t)((double)fr * 0.80);
+    int64_t fit = (int64_t)(budget / per_ray);
+    if (ctx->params.tile_rays > 0 && ctx->params.tile_rays < fit) fit = ctx->params.tile_rays;
+    if (fit < 128) return bl_fail(ctx, BL_ERR_NOMEM, "not enough free HBM for a 128-ray wave (%zu bytes per ray)", per_ray);
+    if (fit >= num_rays) {
+      L.wave_rays = num_rays;
+      L.resident = true;
+    } else {
+      // split into equal waves (multiples of 128 rays) and keep headroom for other levels
+      int64_t waves = (num_rays + fit - 1) / fit;
+      int64_t w = (num_rays + waves - 1) / waves;
+      L.wave_rays = (w + 127) / 128 * 128;
+      L.resident = false;
+    }
+    BL_CUDA_CHECK(dev_alloc(&L.step, (size_t)L.wave_rays * per_ray / sizeof(double)));
   }
-  BL_CUDA_CHECK(dev_alloc(&L.step, (size_t)L.wave_rays * per_ray / sizeof(double)));
   BL_CUDA_CHECK(cudaMemsetAsync(ctx->counters, 0, sizeof(GeoCounters), ctx->stream));
   L.stats = bl_level_stats();
   if (L.resident) {
@@ -639,6 +652,8 @@ int bl_trace_level(bl_ctx *ctx, int level, const double *cam_pos, const double *
 }
 
 long long bl_launch_count(const bl_ctx *ctx) { return ctx ? ctx->launches : -1; }
+
+void *bl_cuda_stream(const bl_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
 int bl_retrace_level(bl_ctx *ctx, int level, bl_level_stats *stats) {
   if (!ctx) return BL_ERR_ARG;

@@ -179,6 +179,10 @@ int bl_retrace_level(bl_ctx *ctx, int level, bl_level_stats *stats);
 /* Number of CUDA kernels of this library launched by the context so far (bench accounting). */
 long long bl_launch_count(const bl_ctx *ctx);
 
+/* The CUDA stream (cudaStream_t) every kernel and copy of this context is issued on, so that a host
+ * can bracket calls with its own events or order other work against them. */
+void *bl_cuda_stream(const bl_ctx *ctx);
+
 /* Replaces RadiationIntegrator::Integrate's sampling + coefficient + transfer (+ render) stages
  * for one level.  image: (image_num_quantities, N) f64; render: (R,3,N) f64 or NULL. */
 int bl_radiate_level(bl_ctx *ctx, int level, int snapshot, double *image, double *render,
