@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -11,10 +12,13 @@
 #include "../../include/blacklight_b200.h"
 #include "rad_types.cuh"
 
-extern "C" cudaError_t bl_launch_geodesic_dp(const GeoArgs *args, int flat, int sm_count, cudaStream_t stream);
+extern "C" cudaError_t bl_launch_geodesic_dp(const GeoArgs *args, int flat, int sm_count, int min_blocks, cudaStream_t stream);
 extern "C" cudaError_t bl_launch_geodesic_rk(const GeoArgs *args, int flat, int order, int sm_count, cudaStream_t stream);
-extern "C" cudaError_t bl_launch_radiate_unpolarized(const RadArgs *args, int num_freq, int simulation, cudaStream_t stream);
-extern "C" cudaError_t bl_launch_radiate_polarized(const RadArgs *args, int num_freq, cudaStream_t stream);
+#define BL_DECL_RAD(name) extern "C" cudaError_t name(const RadArgs *args, const RadParams *params, cudaStream_t stream)
+BL_DECL_RAD(bl_launch_radiate_unpolarized_f1); BL_DECL_RAD(bl_launch_radiate_unpolarized_f4);
+BL_DECL_RAD(bl_launch_radiate_unpolarized_f12); BL_DECL_RAD(bl_launch_radiate_unpolarized_f32);
+BL_DECL_RAD(bl_launch_radiate_polarized_f1); BL_DECL_RAD(bl_launch_radiate_polarized_f4);
+BL_DECL_RAD(bl_launch_radiate_polarized_f12); BL_DECL_RAD(bl_launch_radiate_polarized_f32);
 extern "C" cudaError_t bl_launch_relayout_grid(const float *prim, int n_var, const int *var_index, size_t cells,
                                                float4 *out, float *kappa_out, cudaStream_t stream);
 extern "C" cudaError_t bl_launch_unpack_samples(const StepBuffer *sb, const int32_t *num, int64_t rays, int S,
@@ -62,6 +66,7 @@ struct bl_ctx {
   std::string error;
   bool taps_enabled = false;
   long long launches = 0;   // kernels of ours launched so far
+  int geo_min_blocks = 2;   // occupancy variant of the DP kernel (BL_GEO_BLOCKS overrides, tuning only)
 };
 
 namespace {
@@ -229,7 +234,11 @@ void fill_rad_params(const bl_params &p, RadParams &r) {
     r.camera_u_cov[i] = p.camera_u_cov[i]; r.camera_vert_con_c[i] = p.camera_vert_con_c[i];
   }
   r.num_freq = p.image_num_frequencies;
-  for (int l = 0; l < p.image_num_frequencies; l++) r.freqs[l] = p.image_frequencies[l];
+  for (int l = 0; l < p.image_num_frequencies; l++) {
+    r.freqs[l] = p.image_frequencies[l];
+    r.inv_freqs[l] = 1.0 / p.image_frequencies[l];
+    r.log_freqs[l] = std::log(p.image_frequencies[l]);
+  }
   r.x_unit = phys::gg_msun * p.mass_msun / (phys::c * phys::c);
   r.t_unit = r.x_unit / phys::c;
   r.image_light = p.image_light; r.image_time = p.image_time; r.image_length = p.image_length;
@@ -267,6 +276,19 @@ void fill_rad_params(const bl_params &p, RadParams &r) {
   r.cut_omit_in = p.cut_omit_in; r.cut_omit_out = p.cut_omit_out;
   r.cut_midplane_theta = p.cut_midplane_theta; r.cut_midplane_z = p.cut_midplane_z;
   for (int i = 0; i < 3; i++) { r.cut_plane_origin[i] = p.cut_plane_origin[i]; r.cut_plane_normal[i] = p.cut_plane_normal[i]; }
+  r.n_e_factor = 1.0 / (p.plasma_mu * phys::m_p) / (1.0 + 1.0 / p.plasma_ne_ni);
+  r.any_value_cut = p.cut_rho_min >= 0.0 || p.cut_rho_max >= 0.0 || p.cut_n_e_min >= 0.0 || p.cut_n_e_max >= 0.0 ||
+                    p.cut_p_gas_min >= 0.0 || p.cut_p_gas_max >= 0.0 || p.cut_theta_e_min >= 0.0 || p.cut_theta_e_max >= 0.0 ||
+                    p.cut_b_min >= 0.0 || p.cut_b_max >= 0.0 || p.cut_sigma_min >= 0.0 || p.cut_sigma_max >= 0.0 ||
+                    p.cut_beta_inverse_min >= 0.0 || p.cut_beta_inverse_max >= 0.0;
+  r.need_sigma_beta = r.need_cell_values;
+  if (sim && p.plasma_kappa_frac != 0.0) {
+    r.log_w2k2 = std::log(p.plasma_w * p.plasma_w * p.plasma_kappa * p.plasma_kappa);
+    r.log_kjl = std::log(r.kappa_jj_low); r.log_kjh = std::log(r.kappa_jj_high);
+    r.log_kal = std::log(r.kappa_aa_low); r.log_kah = std::log(r.kappa_aa_high * r.kappa_aa_high_i);
+    r.log_k_j_pref = std::log(p.plasma_kappa_frac * phys::e * phys::e / phys::c);
+    r.log_k_a_pref = std::log(p.plasma_kappa_frac * phys::e * phys::e / (phys::m_e * phys::c));
+  }
   r.fallback_nan = p.fallback_nan; r.fallback_rho = p.fallback_rho; r.fallback_pgas = p.fallback_pgas;
   r.fallback_kappa = p.fallback_kappa;
   for (int i = 0; i <= BL_MAX_RENDER_FEATURES; i++) r.render_feature_start[i] = p.render_feature_start[i];
@@ -335,6 +357,7 @@ int bl_create(const bl_params *params, bl_ctx **out) {
   ctx->device = params->device;
   fill_rad_params(*params, ctx->rad);
   ctx->levels.resize((size_t)params->adaptive_max_level + 1);
+  if (const char *e = getenv("BL_GEO_BLOCKS")) ctx->geo_min_blocks = atoi(e);
 #define CREATE_CHECK(call)                                                                   \
   do {                                                                                       \
     cudaError_t e__ = (call);                                                                \
@@ -451,6 +474,9 @@ int bl_upload_grid(bl_ctx *ctx, const bl_grid_view *gv) {
     BL_CUDA_CHECK(alloc_d(&g.x2v, (size_t)g.n_b * g.n_j));
     BL_CUDA_CHECK(alloc_d(&g.x3v, (size_t)g.n_b * g.n_k));
     BL_CUDA_CHECK(alloc_d(&g.bounds, (size_t)g.n_b * 6));
+    BL_CUDA_CHECK(alloc_d(&g.x1d, (size_t)g.n_b * g.n_i));
+    BL_CUDA_CHECK(alloc_d(&g.x2d, (size_t)g.n_b * g.n_j));
+    BL_CUDA_CHECK(alloc_d(&g.x3d, (size_t)g.n_b * g.n_k));
     float4 *c4 = nullptr;
     BL_CUDA_CHECK(dev_alloc(&c4, cells * 2));
     g.cells = c4; ctx->grid_allocs.push_back(c4);
@@ -479,6 +505,20 @@ int bl_upload_grid(bl_ctx *ctx, const bl_grid_view *gv) {
     bounds[6 * b + 5] = gv->x3f[(size_t)b * (g.n_k + 1) + g.n_k];
   }
   BL_CUDA_CHECK(cudaMemcpyAsync((void *)g.bounds, bounds.data(), bounds.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  // reciprocal cell-centre spacings, so that interpolation fractions need no division on the device
+  std::vector<double> inv1((size_t)g.n_b * g.n_i), inv2((size_t)g.n_b * g.n_j), inv3((size_t)g.n_b * g.n_k);
+  auto fill_inv = [&](std::vector<double> &out, const double *xv, int n) {
+    for (int b = 0; b < g.n_b; b++)
+      for (int i = 0; i < n; i++)
+        out[(size_t)b * n + i] = i + 1 < n ? 1.0 / (xv[(size_t)b * n + i + 1] - xv[(size_t)b * n + i]) : 0.0;
+  };
+  fill_inv(inv1, gv->x1v, g.n_i);
+  fill_inv(inv2, gv->x2v, g.n_j);
+  fill_inv(inv3, gv->x3v, g.n_k);
+  BL_CUDA_CHECK(h2d(g.x1d, inv1.data(), inv1.size()));
+  BL_CUDA_CHECK(h2d(g.x2d, inv2.data(), inv2.size()));
+  BL_CUDA_CHECK(h2d(g.x3d, inv3.data(), inv3.size()));
+  BL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // the staging vectors above go out of scope
   // primitives: stage the reader's (var, b, k, j, i) planes, then re-lay out to one record per cell
   float *stage = nullptr;
   BL_CUDA_CHECK(dev_alloc(&stage, (size_t)gv->n_var * cells));
@@ -519,7 +559,7 @@ int trace_wave(bl_ctx *ctx, Level &L, int64_t first, int64_t count) {
   g.counters = ctx->counters;
   BL_CUDA_CHECK(cudaMemsetAsync(&ctx->counters->next_ray, 0, sizeof(unsigned long long), ctx->stream));
   if (p.ray_integrator == BL_INTEGRATOR_DP)
-    BL_CUDA_CHECK(bl_launch_geodesic_dp(&g, p.ray_flat, ctx->sm_count, ctx->stream));
+    BL_CUDA_CHECK(bl_launch_geodesic_dp(&g, p.ray_flat, ctx->sm_count, ctx->geo_min_blocks, ctx->stream));
   else
     BL_CUDA_CHECK(bl_launch_geodesic_rk(&g, p.ray_flat, p.ray_integrator == BL_INTEGRATOR_RK4 ? 4 : 2, ctx->sm_count, ctx->stream));
   ctx->launches++;
@@ -541,7 +581,6 @@ int read_geo_counters(bl_ctx *ctx, Level &L) {
 
 int radiate_wave(bl_ctx *ctx, Level &L, int64_t first, int64_t count) {
   RadArgs A{};
-  A.P = ctx->rad_dev;
   A.grid = ctx->grid;
   A.sb.buf = L.step; A.sb.rays = count; A.sb.cap = ctx->params.ray_max_steps;
   A.sample_num = L.num + first;
@@ -561,11 +600,21 @@ int radiate_wave(bl_ctx *ctx, Level &L, int64_t first, int64_t count) {
     A.taps.inds = L.tap_inds ? L.tap_inds + 4 * o : nullptr;
     A.taps.fracs = L.tap_fracs ? L.tap_fracs + 3 * o : nullptr;
   }
-  bool sim = ctx->params.model_type == BL_MODEL_SIMULATION;
+  // parameters travel by value in the kernel's constant bank (no device copy, no per-sample loads)
+  // the kernels are instantiated for frequency-count buckets of 1, 4, 12 and 32 (one object file each)
+  const int F = ctx->rad.num_freq;
+  cudaError_t le;
   if (ctx->rad.polarization)
-    BL_CUDA_CHECK(bl_launch_radiate_polarized(&A, ctx->rad.num_freq, ctx->stream));
+    le = F <= 1 ? bl_launch_radiate_polarized_f1(&A, &ctx->rad, ctx->stream)
+       : F <= 4 ? bl_launch_radiate_polarized_f4(&A, &ctx->rad, ctx->stream)
+       : F <= 12 ? bl_launch_radiate_polarized_f12(&A, &ctx->rad, ctx->stream)
+                 : bl_launch_radiate_polarized_f32(&A, &ctx->rad, ctx->stream);
   else
-    BL_CUDA_CHECK(bl_launch_radiate_unpolarized(&A, ctx->rad.num_freq, sim ? 1 : 0, ctx->stream));
+    le = F <= 1 ? bl_launch_radiate_unpolarized_f1(&A, &ctx->rad, ctx->stream)
+       : F <= 4 ? bl_launch_radiate_unpolarized_f4(&A, &ctx->rad, ctx->stream)
+       : F <= 12 ? bl_launch_radiate_unpolarized_f12(&A, &ctx->rad, ctx->stream)
+                 : bl_launch_radiate_unpolarized_f32(&A, &ctx->rad, ctx->stream);
+  BL_CUDA_CHECK(le);
   ctx->launches++;
   return BL_OK;
 }

@@ -14,7 +14,8 @@
 namespace {
 
 constexpr int kBlock = 128;
-constexpr int kComp = 8;  // t, x, y, z, p_x, p_y, p_z, s  (dp_t/dlambda is identically zero)
+constexpr int kComp = 7;  // t, x, y, z, p_x, p_y, p_z in shared memory (dp_t/dlambda is identically zero);
+                          // the proper-distance rate ds/dlambda of a stage is consumed at once (registers)
 
 // Butcher tableau of RK5(4)7M (Dormand & Prince 1980) and the dense-output weights of Shampine (1986)
 __constant__ double c_a[7][6] = {
@@ -45,12 +46,13 @@ struct Ray {
   int n;          // samples stored so far
   int num_retry;
   int trunc;      // first truncated sample index, -1 if none
+  double ds0;     // ds/dlambda of stage 0 (first-same-as-last)
   bool prev_fail, flag, need_k0;
 };
 
 template <bool flat>
-__device__ __forceinline__ void eval_rhs(const GeoArgs &g, const double pos[3], const double p[4],
-                                         double *ks, int q) {
+__device__ __forceinline__ double eval_rhs(const GeoArgs &g, const double pos[3], const double p[4],
+                                           double *ks, int q) {
   double dx[4], dp[3], ds;
   ksx::rhs<flat>(g.a, pos[0], pos[1], pos[2], p, dx, dp, ds);
   double *kq = ks + (size_t)q * kComp * kBlock;
@@ -61,7 +63,7 @@ __device__ __forceinline__ void eval_rhs(const GeoArgs &g, const double pos[3], 
   kq[4 * kBlock] = dp[0];
   kq[5 * kBlock] = dp[1];
   kq[6 * kBlock] = dp[2];
-  kq[7 * kBlock] = ds;
+  return ds;
 }
 
 // Store one sample: truncation test on its radius, renormalise its spatial momentum, write SoA.
@@ -95,8 +97,8 @@ __device__ __forceinline__ void store_sample(const GeoArgs &g, Ray &ray, int idx
   dst[8 * cs] = len;
 }
 
-template <bool flat>
-__global__ void __launch_bounds__(kBlock) geodesic_dp_kernel(GeoArgs g) {
+template <bool flat, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) geodesic_dp_kernel(GeoArgs g) {
   extern __shared__ double smem[];
   double *ks = smem + threadIdx.x;  // k[q][p] at ks[(q*kComp + p) * kBlock]
   const unsigned full = 0xffffffffu;
@@ -105,6 +107,7 @@ __global__ void __launch_bounds__(kBlock) geodesic_dp_kernel(GeoArgs g) {
   Ray ray;
   bool active = false;
   bool exhausted = false;
+  double ds_last = 0.0;  // ds/dlambda of stage 6 of the last attempt
   unsigned long long n_attempts = 0, n_accepted = 0;
 
   for (;;) {
@@ -155,10 +158,14 @@ __global__ void __launch_bounds__(kBlock) geodesic_dp_kernel(GeoArgs g) {
       if (!ray.prev_fail && ray.n > 0) {
         for (int c = 0; c < 9; c++) ray.y[c] = ray.y5[c];
         for (int p = 0; p < kComp; p++) ks[p * kBlock] = ks[(6 * kComp + p) * kBlock];  // FSAL
+        ray.ds0 = ds_last;
       }
       double r = ray.prev_fail ? ksx::radius(g.a, ray.y[1], ray.y[2], ray.y[3]) : ray.r_new;
 
-      // stages (stage 0 only for a fresh ray)
+      // stages (stage 0 only for a fresh ray); the distance component of the 5th-order solution is
+      // accumulated stage by stage, in the same order as the other components below
+      double s5 = ray.y[8];
+      if (!ray.need_k0) s5 += c_b5[0] * h * ray.ds0;
       for (int s = ray.need_k0 ? 0 : 1; s < 7; s++) {
         double pos[3] = {ray.y[1], ray.y[2], ray.y[3]};
         double mom[4] = {ray.y[4], ray.y[5], ray.y[6], ray.y[7]};
@@ -172,7 +179,10 @@ __global__ void __launch_bounds__(kBlock) geodesic_dp_kernel(GeoArgs g) {
           mom[2] += ah * kq[5 * kBlock];
           mom[3] += ah * kq[6 * kBlock];
         }
-        eval_rhs<flat>(g, pos, mom, ks, s);
+        double ds = eval_rhs<flat>(g, pos, mom, ks, s);
+        if (s == 0) ray.ds0 = ds;
+        s5 += c_b5[s] * h * ds;
+        ds_last = ds;
       }
       ray.need_k0 = false;
 
@@ -191,8 +201,8 @@ __global__ void __launch_bounds__(kBlock) geodesic_dp_kernel(GeoArgs g) {
         kv = kq[4 * kBlock]; ray.y5[5] += b5h * kv; y4[5] += b4h * kv;
         kv = kq[5 * kBlock]; ray.y5[6] += b5h * kv; y4[6] += b4h * kv;
         kv = kq[6 * kBlock]; ray.y5[7] += b5h * kv; y4[7] += b4h * kv;
-        kv = kq[7 * kBlock]; ray.y5[8] += b5h * kv;
       }
+      ray.y5[8] = s5;
       ray.r_new = ksx::radius(g.a, ray.y5[1], ray.y5[2], ray.y5[3]);
       double error = 0.0;
       for (int c = 0; c < 8; c++) {
@@ -400,33 +410,33 @@ __global__ void __launch_bounds__(kBlock) geodesic_rk_kernel(GeoArgs g) {
 
 }  // namespace
 
-// Launch the DP integrator for one wave of rays on `stream`.  grid_blocks = 0 picks a persistent
-// grid of (SM count x resident blocks).
-extern "C" cudaError_t bl_launch_geodesic_dp(const GeoArgs *args, int flat, int sm_count,
-                                             cudaStream_t stream) {
+namespace {
+template <bool flat, int MINB>
+cudaError_t launch_dp(const GeoArgs *args, int sm_count, cudaStream_t stream) {
   size_t smem = (size_t)7 * kComp * kBlock * sizeof(double);
-  cudaError_t err;
+  cudaError_t err = cudaFuncSetAttribute(geodesic_dp_kernel<flat, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
   int per_sm = 0;
-  if (flat) {
-    err = cudaFuncSetAttribute(geodesic_dp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err != cudaSuccess) return err;
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, geodesic_dp_kernel<true>, kBlock, smem);
-  } else {
-    err = cudaFuncSetAttribute(geodesic_dp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err != cudaSuccess) return err;
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, geodesic_dp_kernel<false>, kBlock, smem);
-  }
+  err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, geodesic_dp_kernel<flat, MINB>, kBlock, smem);
   if (err != cudaSuccess) return err;
   if (per_sm < 1) per_sm = 1;
   long long want = (args->rays + kBlock - 1) / kBlock;
   long long grid = (long long)sm_count * per_sm;
   if (grid > want) grid = want;
   if (grid < 1) grid = 1;
-  if (flat)
-    geodesic_dp_kernel<true><<<(unsigned)grid, kBlock, smem, stream>>>(*args);
-  else
-    geodesic_dp_kernel<false><<<(unsigned)grid, kBlock, smem, stream>>>(*args);
+  geodesic_dp_kernel<flat, MINB><<<(unsigned)grid, kBlock, smem, stream>>>(*args);
   return cudaGetLastError();
+}
+}  // namespace
+
+// Launch the DP integrator for one wave of rays on `stream`: a persistent grid of (SM count x resident
+// blocks).  min_blocks selects the occupancy variant (registers capped for 2, 3 or 4 blocks per SM).
+extern "C" cudaError_t bl_launch_geodesic_dp(const GeoArgs *args, int flat, int sm_count, int min_blocks,
+                                             cudaStream_t stream) {
+  if (flat) return launch_dp<true, 2>(args, sm_count, stream);
+  if (min_blocks >= 4) return launch_dp<false, 4>(args, sm_count, stream);
+  if (min_blocks == 3) return launch_dp<false, 3>(args, sm_count, stream);
+  return launch_dp<false, 2>(args, sm_count, stream);
 }
 
 extern "C" cudaError_t bl_launch_geodesic_rk(const GeoArgs *args, int flat, int order, int sm_count,

@@ -21,17 +21,53 @@ struct SampleIndex {  // what the reference stores in sample_inds / sample_fracs
   double fk, fj, fi;
 };
 
-// Kerr-Schild radius with ordinary (fused) arithmetic; agrees with the reference to rounding
-__device__ __forceinline__ double ks_radius(double a, double x, double y, double z) {
+// Kerr-Schild radius and its reciprocal with ordinary (fused) arithmetic; agrees with the reference
+// (radiation_geometry.cpp:18-25) to rounding.  One rsqrt yields both r and 1/r.
+__device__ __forceinline__ double ks_radius(double a, double x, double y, double z, double &inv_r) {
   double a2 = a * a;
   double rr2 = x * x + y * y + z * z;
-  double r2 = 0.5 * (rr2 - a2 + hypot(rr2 - a2, 2.0 * a * z));
-  return sqrt(r2);
+  double d = rr2 - a2, e = 2.0 * a * z;
+  double r2 = 0.5 * (d + sqrt(d * d + e * e));
+  inv_r = rsqrt(r2);
+  return r2 * inv_r;
+}
+__device__ __forceinline__ double ks_radius(double a, double x, double y, double z) {
+  double inv_r;
+  return ks_radius(a, x, y, z, inv_r);
 }
 
 // first index i in [0, n) with faces[i+1] >= x, else n (reference linear scan :458-466)
 __device__ __forceinline__ int find_cell(const double *__restrict__ faces, int n, double x) {
   int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(faces + mid + 1) >= x)
+      hi = mid;
+    else
+      lo = mid + 1;
+  }
+  return lo;
+}
+
+// Same result as find_cell, starting from the cell the previous sample of this ray lay in: consecutive
+// samples are ray_step * r apart, so the answer is almost always the hint or a neighbour and the two
+// (independent) face loads replace a chain of log2(n) dependent ones.  Falls back to bisection of the
+// remaining range, so the returned index is the reference's for any hint.
+__device__ __forceinline__ int find_cell_hint(const double *__restrict__ faces, int n, double x, int hint) {
+  int h = hint < 0 ? 0 : (hint > n - 1 ? n - 1 : hint);
+  double fa = __ldg(faces + h), fb = __ldg(faces + h + 1);
+  int lo, hi;
+  if (fb >= x) {
+    if (h == 0 || fa < x) return h;
+    if (h == 1 || __ldg(faces + h - 1) < x) return h - 1;
+    lo = 0;
+    hi = h - 2;
+  } else {
+    if (h + 1 >= n) return n;
+    if (__ldg(faces + h + 2) >= x) return h + 1;
+    lo = h + 2;
+    hi = n;
+  }
   while (lo < hi) {
     int mid = (lo + hi) >> 1;
     if (__ldg(faces + mid + 1) >= x)
@@ -80,25 +116,31 @@ __device__ __forceinline__ bool geometric_cut(const RadParams &P, double x, doub
   return false;
 }
 
-// Locate and gather.  `b_cache` is the block the previous sample of this ray lay in (the reference
-// keeps the same cache per OpenMP thread, simulation_sampling.cpp:180-189,352-394).
-// smem_bounds: block bounds staged in shared memory (n_b*6 doubles) or nullptr to read from HBM.
+// Where the previous sample of this ray was found: the block (the reference keeps the same cache per
+// OpenMP thread, simulation_sampling.cpp:180-189,352-394) and, as search hints only, its cell.
+struct CellCache {
+  int b, i, j, k;
+};
+
+// Locate and gather.  smem_bounds: block bounds staged in shared memory (n_b*6 doubles) or nullptr to
+// read them from HBM.  inv_r = 1/r.
 __device__ __forceinline__ SampleStatus sample_grid(const RadParams &P, const GridDev &g,
                                                     const double *smem_bounds, double x, double y,
-                                                    double z, double r, int &b_cache, Prims &out,
-                                                    SampleIndex &si) {
+                                                    double z, double r, double inv_r, CellCache &cache,
+                                                    Prims &out, SampleIndex &si) {
   // simulation coordinates of the point (radiation_geometry.cpp:37-57)
   double x1 = x, x2 = y, x3 = z;
   if (P.coord != 0) {
-    double th = acos(z / r);
-    double ph = atan2(y, x) - atan(P.a / r);
+    double th = acos(z * inv_r);
+    // atan2(y, x) - atan(a / r) as one angle: arg((x + i y)(r - i a))
+    double ph = atan2(y * r - P.a * x, x * r + P.a * y);
     ph += ph < 0.0 ? 2.0 * phys::pi : 0.0;
     ph -= ph >= 2.0 * phys::pi ? 2.0 * phys::pi : 0.0;
     x1 = r; x2 = th; x3 = ph;
   }
   // block: keep the cached one while it still contains the point, else first match in index order
   const double *bounds = smem_bounds ? smem_bounds : g.bounds;
-  int b = b_cache;
+  int b = cache.b;
   const double *bd = bounds + 6 * b;
   if (x1 < bd[0] || x1 > bd[1] || x2 < bd[2] || x2 > bd[3] || x3 < bd[4] || x3 > bd[5]) {
     int bn = 0;
@@ -106,12 +148,13 @@ __device__ __forceinline__ SampleStatus sample_grid(const RadParams &P, const Gr
       if (in_block(bounds + 6 * bn, x1, x2, x3)) break;
     if (bn == g.n_b) return P.fallback_nan ? kSampleNan : kSampleFallback;
     b = bn;
-    b_cache = bn;
+    cache.b = bn;
   }
   const int n_i = g.n_i, n_j = g.n_j, n_k = g.n_k;
-  int i = find_cell(g.x1f + (size_t)b * (n_i + 1), n_i, x1);
-  int j = find_cell(g.x2f + (size_t)b * (n_j + 1), n_j, x2);
-  int k = find_cell(g.x3f + (size_t)b * (n_k + 1), n_k, x3);
+  int i = find_cell_hint(g.x1f + (size_t)b * (n_i + 1), n_i, x1, cache.i);
+  int j = find_cell_hint(g.x2f + (size_t)b * (n_j + 1), n_j, x2, cache.j);
+  int k = find_cell_hint(g.x3f + (size_t)b * (n_k + 1), n_k, x3, cache.k);
+  cache.i = i; cache.j = j; cache.k = k;
   si.b = b;
   if (!P.interp) {
     si.k = k; si.j = j; si.i = i;
@@ -129,12 +172,9 @@ __device__ __forceinline__ SampleStatus sample_grid(const RadParams &P, const Gr
   int i_m = (i == 0 || (i != n_i - 1 && x1 >= __ldg(x1v + i))) ? i : i - 1;
   int j_m = (j == 0 || (j != n_j - 1 && x2 >= __ldg(x2v + j))) ? j : j - 1;
   int k_m = (k == 0 || (k != n_k - 1 && x3 >= __ldg(x3v + k))) ? k : k - 1;
-  double xa = __ldg(x1v + i_m), xb = __ldg(x1v + i_m + 1);
-  double ya = __ldg(x2v + j_m), yb = __ldg(x2v + j_m + 1);
-  double za = __ldg(x3v + k_m), zb = __ldg(x3v + k_m + 1);
-  double f_i = (x1 - xa) / (xb - xa);
-  double f_j = (x2 - ya) / (yb - ya);
-  double f_k = (x3 - za) / (zb - za);
+  double f_i = (x1 - __ldg(x1v + i_m)) * __ldg(g.x1d + (size_t)b * n_i + i_m);
+  double f_j = (x2 - __ldg(x2v + j_m)) * __ldg(g.x2d + (size_t)b * n_j + j_m);
+  double f_k = (x3 - __ldg(x3v + k_m)) * __ldg(g.x3d + (size_t)b * n_k + k_m);
   si.k = k_m; si.j = j_m; si.i = i_m;
   si.fk = f_k; si.fj = f_j; si.fi = f_i;
   // weights in the reference's term order (InterpolateSimple, simulation_sampling.cpp:1334-1351)
@@ -175,29 +215,30 @@ __device__ __forceinline__ SampleStatus sample_grid(const RadParams &P, const Gr
 }
 
 struct Plasma {
-  double rho_cgs, n_e_cgs, pgas_cgs, theta_e, kb_tt_e_cgs, bb_cgs, sigma, beta_inv, b_sq;
+  double rho_cgs, n_e_cgs, pgas_cgs, theta_e, inv_theta_e, kb_tt_e_cgs, bb_cgs, sigma, beta_inv, b_sq;
   double ucon[4], bcon[4];  // Cartesian Kerr-Schild components
   bool value_cut;           // true: skip coupling (simulation_coefficients.cpp:361-375)
   bool b_zero;              // all three simulation field components vanish (:394)
 };
 
-// Plasma state of one sample (simulation_coefficients.cpp:286-408).  (x,y,z) CKS position, r its radius.
-// vectors: 0 = stop after the value cuts (cell values only); 1 = CKS u^mu, b^mu only for samples that
-// couple to the radiation; 2 = always (the polarized transport needs the fluid frame at every sample).
+// Plasma state of one sample (simulation_coefficients.cpp:286-408).  (x,y,z) CKS position, r its radius,
+// inv_r = 1/r.  vectors: 0 = stop after the value cuts (cell values only); 1 = CKS u^mu, b^mu only for
+// samples that couple to the radiation; 2 = always (the polarized transport needs the fluid frame at every
+// sample).  Algebraically the reference's formulas; reciprocals are shared and divisions by parameters are
+// folded into host-side constants (the results agree to a few ulp, far inside the 1e-6 image tolerance).
 __device__ __forceinline__ void plasma_state(const RadParams &P, double x, double y, double z, double r,
-                                             const Prims &pr, int vectors, Plasma &s) {
+                                             double inv_r, const Prims &pr, int vectors, Plasma &s) {
   const double a = P.a;
   double rho = pr.rho, pgas = pr.pgas, kappa = pr.kappa;
   double uu1 = pr.uu1, uu2 = pr.uu2, uu3 = pr.uu3, bb1 = pr.bb1, bb2 = pr.bb2, bb3 = pr.bb3;
   s.rho_cgs = rho * P.d_unit;
   s.pgas_cgs = pgas * P.e_unit;
-  double n_cgs = s.rho_cgs / (P.plasma_mu * phys::m_p);
-  s.n_e_cgs = n_cgs / (1.0 + 1.0 / P.plasma_ne_ni);
+  s.n_e_cgs = s.rho_cgs * P.n_e_factor;
 
   // simulation-coordinate metric (radiation_geometry.cpp:421-573); only the entries that are used
   double ucon_sim[4], bcon_sim[4];
   double r2 = r * r, a2 = a * a;
-  double cth = z / r;
+  double cth = z * inv_r;
   double cth2 = cth * cth;
   double sth2 = 1.0 - cth2;
   if (P.coord != 0) {
@@ -207,21 +248,21 @@ __device__ __forceinline__ void plasma_state(const RadParams &P, double x, doubl
     double g00 = -(1.0 - tr), g01 = tr, g03 = -tr * a * sth2;
     double g11 = 1.0 + tr, g13 = -(1.0 + tr) * a * sth2, g22 = sigma;
     double g33 = (r2 + a2 + tr * a2 * sth2) * sth2;
-    double gc00 = -(1.0 + tr), gc01 = tr;
     double uu0 = sqrt(1.0 + g11 * uu1 * uu1 + 2.0 * g13 * uu1 * uu3 + g22 * uu2 * uu2 + g33 * uu3 * uu3);
-    double lapse = 1.0 / sqrt(-gc00);
-    double shift1 = -gc01 / gc00;
-    ucon_sim[0] = uu0 / lapse;
-    ucon_sim[1] = uu1 - shift1 * uu0 / lapse;
+    // lapse = 1/sqrt(1 + tr), shift^r = tr/(1 + tr)
+    double rs = rsqrt(g11);
+    ucon_sim[0] = uu0 * (g11 * rs);
+    ucon_sim[1] = uu1 - tr * (rs * rs) * ucon_sim[0];
     ucon_sim[2] = uu2;
     ucon_sim[3] = uu3;
     double ucov1 = g01 * ucon_sim[0] + g11 * ucon_sim[1] + g13 * ucon_sim[3];
     double ucov2 = g22 * ucon_sim[2];
     double ucov3 = g03 * ucon_sim[0] + g13 * ucon_sim[1] + g33 * ucon_sim[3];
     bcon_sim[0] = ucov1 * bb1 + ucov2 * bb2 + ucov3 * bb3;
-    bcon_sim[1] = (bb1 + bcon_sim[0] * ucon_sim[1]) / ucon_sim[0];
-    bcon_sim[2] = (bb2 + bcon_sim[0] * ucon_sim[2]) / ucon_sim[0];
-    bcon_sim[3] = (bb3 + bcon_sim[0] * ucon_sim[3]) / ucon_sim[0];
+    double inv_u0 = 1.0 / ucon_sim[0];
+    bcon_sim[1] = (bb1 + bcon_sim[0] * ucon_sim[1]) * inv_u0;
+    bcon_sim[2] = (bb2 + bcon_sim[0] * ucon_sim[2]) * inv_u0;
+    bcon_sim[3] = (bb3 + bcon_sim[0] * ucon_sim[3]) * inv_u0;
     double bcov0 = g00 * bcon_sim[0] + g01 * bcon_sim[1] + g03 * bcon_sim[3];
     double bcov1 = g01 * bcon_sim[0] + g11 * bcon_sim[1] + g13 * bcon_sim[3];
     double bcov2 = g22 * bcon_sim[2];
@@ -230,73 +271,94 @@ __device__ __forceinline__ void plasma_state(const RadParams &P, double x, doubl
   } else {
     // Cartesian Kerr-Schild simulation: g = eta + f l l
     double f = 2.0 * r2 * r / (r2 * r2 + a2 * z * z);
-    double l[4] = {1.0, (r * x + a * y) / (r2 + a2), (r * y - a * x) / (r2 + a2), z / r};
+    double inv_ra2 = 1.0 / (r2 + a2);
+    double l[4] = {1.0, (r * x + a * y) * inv_ra2, (r * y - a * x) * inv_ra2, cth};
     double uv[4] = {0.0, uu1, uu2, uu3};
     double lu = l[1] * uu1 + l[2] * uu2 + l[3] * uu3;
     double uu0 = sqrt(1.0 + uu1 * uu1 + uu2 * uu2 + uu3 * uu3 + f * lu * lu);
-    double gc00 = -f - 1.0;
-    double lapse = 1.0 / sqrt(-gc00);
-    ucon_sim[0] = uu0 / lapse;
-    for (int q = 1; q < 4; q++) ucon_sim[q] = uv[q] - (-(f * l[q]) / gc00) * uu0 / lapse;
+    double g11 = 1.0 + f;  // -g^{00}
+    double rs = rsqrt(g11);
+    ucon_sim[0] = uu0 * (g11 * rs);
+    for (int q = 1; q < 4; q++) ucon_sim[q] = uv[q] - f * l[q] * (rs * rs) * ucon_sim[0];
     double lucon = l[0] * ucon_sim[0] + l[1] * ucon_sim[1] + l[2] * ucon_sim[2] + l[3] * ucon_sim[3];
     double ucov[4];
     ucov[0] = -ucon_sim[0] + f * l[0] * lucon;
     for (int q = 1; q < 4; q++) ucov[q] = ucon_sim[q] + f * l[q] * lucon;
     bcon_sim[0] = ucov[1] * bb1 + ucov[2] * bb2 + ucov[3] * bb3;
-    bcon_sim[1] = (bb1 + bcon_sim[0] * ucon_sim[1]) / ucon_sim[0];
-    bcon_sim[2] = (bb2 + bcon_sim[0] * ucon_sim[2]) / ucon_sim[0];
-    bcon_sim[3] = (bb3 + bcon_sim[0] * ucon_sim[3]) / ucon_sim[0];
+    double inv_u0 = 1.0 / ucon_sim[0];
+    bcon_sim[1] = (bb1 + bcon_sim[0] * ucon_sim[1]) * inv_u0;
+    bcon_sim[2] = (bb2 + bcon_sim[0] * ucon_sim[2]) * inv_u0;
+    bcon_sim[3] = (bb3 + bcon_sim[0] * ucon_sim[3]) * inv_u0;
     double lb = l[0] * bcon_sim[0] + l[1] * bcon_sim[1] + l[2] * bcon_sim[2] + l[3] * bcon_sim[3];
     s.b_sq = -bcon_sim[0] * bcon_sim[0] + bcon_sim[1] * bcon_sim[1] + bcon_sim[2] * bcon_sim[2] +
              bcon_sim[3] * bcon_sim[3] + f * lb * lb;
   }
   s.bb_cgs = sqrt(s.b_sq) * P.b_unit;
-  s.sigma = s.b_sq / rho;
-  s.beta_inv = s.b_sq / (2.0 * pgas);
+  s.sigma = s.beta_inv = nan("");
+  if (P.need_sigma_beta) {
+    s.sigma = s.b_sq / rho;
+    s.beta_inv = s.b_sq / (2.0 * pgas);
+  }
 
   // electron temperature
   s.kb_tt_e_cgs = nan("");
-  s.theta_e = nan("");
+  s.theta_e = s.inv_theta_e = nan("");
+  const double me_c2 = phys::m_e * phys::c * phys::c;
   if (P.thermal_frac != 0.0 && P.plasma_model == 0) {
-    double bi2 = s.beta_inv * s.beta_inv;
-    double tti_tte = (P.plasma_rat_high + P.plasma_rat_low * bi2) / (1.0 + bi2);
-    double kb_tt_tot = P.plasma_mu * phys::m_p * s.pgas_cgs / s.rho_cgs;
+    // T_i/T_e = (R_high beta^-2 ... ) with beta^-1 = b^2 / (2 p): written over the common denominator so
+    // that kT_e and its reciprocal come from one division
+    double p2 = 4.0 * pgas * pgas, b4 = s.b_sq * s.b_sq;
+    double rat_num = P.plasma_rat_high * p2 + P.plasma_rat_low * b4;  // (T_i/T_e) * (p2 + b4)
+    double one_num = p2 + b4;
+    double num, den;
     if (P.plasma_use_p) {
-      s.kb_tt_e_cgs = (1.0 + P.plasma_ne_ni) / (tti_tte + P.plasma_ne_ni) * kb_tt_tot;
+      num = (1.0 + P.plasma_ne_ni) * P.plasma_mu * phys::m_p * s.pgas_cgs * one_num;
+      den = (rat_num + P.plasma_ne_ni * one_num) * s.rho_cgs;
     } else {
-      s.kb_tt_e_cgs = (1.0 + P.plasma_ne_ni) * kb_tt_tot / (P.plasma_gamma - 1.0);
-      s.kb_tt_e_cgs /= tti_tte / (P.plasma_gamma_i - 1.0) + P.plasma_ne_ni / (P.plasma_gamma_e - 1.0);
+      num = (1.0 + P.plasma_ne_ni) * P.plasma_mu * phys::m_p * s.pgas_cgs * one_num;
+      den = (P.plasma_gamma - 1.0) * s.rho_cgs *
+            (rat_num / (P.plasma_gamma_i - 1.0) + P.plasma_ne_ni * one_num / (P.plasma_gamma_e - 1.0));
     }
-    s.theta_e = s.kb_tt_e_cgs / (phys::m_e * phys::c * phys::c);
+    double q = 1.0 / (num * den);
+    s.kb_tt_e_cgs = num * num * q;
+    s.theta_e = s.kb_tt_e_cgs * (1.0 / me_c2);
+    s.inv_theta_e = den * den * q * me_c2;
   }
   if (P.thermal_frac != 0.0 && P.plasma_model == 1) {
     double mu_e = P.plasma_mu * (1.0 + 1.0 / P.plasma_ne_ni);
     double rho_e = rho * phys::m_e / (mu_e * phys::m_p);
     double cb = cbrt(rho_e * kappa);
     s.theta_e = 1.0 / 5.0 * (sqrt(1.0 + 25.0 * cb * cb) - 1.0);
-    s.kb_tt_e_cgs = s.theta_e * phys::m_e * phys::c * phys::c;
+    s.inv_theta_e = 1.0 / s.theta_e;
+    s.kb_tt_e_cgs = s.theta_e * me_c2;
   }
 
-  s.value_cut =
-      (P.cut_rho_min >= 0.0 && s.rho_cgs < P.cut_rho_min) || (P.cut_rho_max >= 0.0 && s.rho_cgs > P.cut_rho_max) ||
-      (P.cut_n_e_min >= 0.0 && s.n_e_cgs < P.cut_n_e_min) || (P.cut_n_e_max >= 0.0 && s.n_e_cgs > P.cut_n_e_max) ||
-      (P.cut_p_gas_min >= 0.0 && s.pgas_cgs < P.cut_p_gas_min) || (P.cut_p_gas_max >= 0.0 && s.pgas_cgs > P.cut_p_gas_max) ||
-      (P.cut_theta_e_min >= 0.0 && s.theta_e < P.cut_theta_e_min) || (P.cut_theta_e_max >= 0.0 && s.theta_e > P.cut_theta_e_max) ||
-      (P.cut_b_min >= 0.0 && s.bb_cgs < P.cut_b_min) || (P.cut_b_max >= 0.0 && s.bb_cgs > P.cut_b_max) ||
-      (P.cut_sigma_min >= 0.0 && s.sigma < P.cut_sigma_min) || (P.cut_sigma_max >= 0.0 && s.sigma > P.cut_sigma_max) ||
-      (P.cut_beta_inverse_min >= 0.0 && s.beta_inv < P.cut_beta_inverse_min) ||
-      (P.cut_beta_inverse_max >= 0.0 && s.beta_inv > P.cut_beta_inverse_max);
+  s.value_cut = false;
+  if (P.any_value_cut) {
+    // sigma = b^2/rho and beta^-1 = b^2/(2 p) are compared in product form (rho, p > 0)
+    s.value_cut =
+        (P.cut_rho_min >= 0.0 && s.rho_cgs < P.cut_rho_min) || (P.cut_rho_max >= 0.0 && s.rho_cgs > P.cut_rho_max) ||
+        (P.cut_n_e_min >= 0.0 && s.n_e_cgs < P.cut_n_e_min) || (P.cut_n_e_max >= 0.0 && s.n_e_cgs > P.cut_n_e_max) ||
+        (P.cut_p_gas_min >= 0.0 && s.pgas_cgs < P.cut_p_gas_min) || (P.cut_p_gas_max >= 0.0 && s.pgas_cgs > P.cut_p_gas_max) ||
+        (P.cut_theta_e_min >= 0.0 && s.theta_e < P.cut_theta_e_min) || (P.cut_theta_e_max >= 0.0 && s.theta_e > P.cut_theta_e_max) ||
+        (P.cut_b_min >= 0.0 && s.bb_cgs < P.cut_b_min) || (P.cut_b_max >= 0.0 && s.bb_cgs > P.cut_b_max) ||
+        (P.cut_sigma_min >= 0.0 && s.b_sq < P.cut_sigma_min * rho) || (P.cut_sigma_max >= 0.0 && s.b_sq > P.cut_sigma_max * rho) ||
+        (P.cut_beta_inverse_min >= 0.0 && s.b_sq < P.cut_beta_inverse_min * (2.0 * pgas)) ||
+        (P.cut_beta_inverse_max >= 0.0 && s.b_sq > P.cut_beta_inverse_max * (2.0 * pgas));
+  }
   s.b_zero = bb1 == 0.0 && bb2 == 0.0 && bb3 == 0.0;
   if (vectors == 0 || (vectors == 1 && (s.value_cut || s.b_zero))) return;
 
   // to Cartesian Kerr-Schild (CoordinateJacobian, radiation_geometry.cpp:69-126)
   if (P.coord != 0) {
-    double sth = sqrt(sth2);
-    double rho_cyl = hypot(x, y);
-    double ra = sqrt(r2 + a2);
-    double cx = rho_cyl > 0.0 ? x / rho_cyl : 1.0, cy = rho_cyl > 0.0 ? y / rho_cyl : 0.0;
-    double cph = (cx * r + cy * a) / ra;  // cos(atan2(y,x) - atan(a/r))
-    double sph = (cy * r - cx * a) / ra;
+    // x^2 + y^2 = (r^2 + a^2) sin^2(theta):  sin(theta) and the azimuth come from two rsqrt
+    double rc2 = x * x + y * y;
+    double inv_ra = rsqrt(r2 + a2);
+    double inv_rc = rc2 > 0.0 ? rsqrt(rc2) : 0.0;
+    double sth = rc2 * inv_rc * inv_ra;
+    double cx = rc2 > 0.0 ? x * inv_rc : 1.0, cy = rc2 > 0.0 ? y * inv_rc : 0.0;
+    double cph = (cx * r + cy * a) * inv_ra;  // cos(atan2(y,x) - atan(a/r))
+    double sph = (cy * r - cx * a) * inv_ra;
     double j11 = sth * cph, j12 = cth * (r * cph - a * sph), j13 = sth * (-r * sph - a * cph);
     double j21 = sth * sph, j22 = cth * (r * sph + a * cph), j23 = sth * (r * cph - a * sph);
     double j31 = cth, j32 = -r * sth;

@@ -30,6 +30,7 @@ struct GridDev {
   const double *x1f, *x2f, *x3f;  // (n_b, n+1)
   const double *x1v, *x2v, *x3v;  // (n_b, n)
   const double *bounds;           // (n_b, 6): x1min, x1max, x2min, x2max, x3min, x3max
+  const double *x1d, *x2d, *x3d;  // (n_b, n): 1 / (xv[i+1] - xv[i]) for i < n-1 (interpolation weights)
   const float4 *cells;
   const float *kappa;             // (n_b, n_k, n_j, n_i) electron entropy, or nullptr
 };
@@ -80,6 +81,17 @@ struct RadParams {
   // polarized extras
   int32_t rotation_split;
   double camera_u_con[4], camera_u_cov[4], camera_vert_con_c[4];
+  // derived on the host (abi.cu fill_rad_params): reciprocals and logarithms hoisted out of the kernels
+  double inv_freqs[RAD_MAX_FREQ];   // 1 / image_frequencies[l]
+  double log_freqs[RAD_MAX_FREQ];   // ln image_frequencies[l]
+  double n_e_factor;                // n_e_cgs = rho_cgs * n_e_factor
+  int32_t any_value_cut;            // any of the cut_{rho,...,beta_inverse}_{min,max} enabled
+  // logarithms of distribution constants: powers of per-sample quantities are evaluated as exp(c * ln x)
+  // with the logarithms shared between all exponents and frequencies
+  double log_w2k2;                  // ln(w^2 kappa^2)
+  double log_kjl, log_kjh, log_kal, log_kah;   // ln of kappa_jj_low, _high, kappa_aa_low, kappa_aa_high*kappa_aa_high_i
+  double log_k_j_pref, log_k_a_pref;           // ln(kappa_frac e^2 / c), ln(kappa_frac e^2 / (m_e c))
+  int32_t need_sigma_beta;          // sigma / beta_inverse needed as values (cell values or cuts)
   // rendering
   int32_t render_num_images;
   int32_t render_feature_start[RAD_MAX_FEATURES + 1];
@@ -99,7 +111,6 @@ struct SampleTaps {
 };
 
 struct RadArgs {
-  const RadParams *P;  // device pointer
   GridDev grid;
   StepBuffer sb;
   const int32_t *sample_num;    // (wave rays)

@@ -545,9 +545,9 @@ __device__ __forceinline__ void couple(const RadParams &P, const Coefficients &C
 }
 
 template <int FMAX>
-__global__ void __launch_bounds__(kBlock) radiate_polarized_kernel(RadArgs A) {
+__global__ void __launch_bounds__(kBlock)
+radiate_polarized_kernel(const __grid_constant__ RadArgs A, const __grid_constant__ RadParams P) {
   extern __shared__ double smem_bounds[];
-  const RadParams &P = *A.P;
   const GridDev &G = A.grid;
   const double *bounds_s = nullptr;
   {
@@ -599,7 +599,7 @@ __global__ void __launch_bounds__(kBlock) radiate_polarized_kernel(RadArgs A) {
   }
   double prev_cv[RAD_NUM_CELL_VALUES];
   for (int q = 0; q < RAD_NUM_CELL_VALUES; q++) prev_cv[q] = nan("");
-  int b_cache = 0;
+  rad::CellCache cache = {0, 0, 0, 0};
   unsigned long long processed = 0;
 
   // frequency-independent state carried from the previous sample
@@ -615,7 +615,8 @@ __global__ void __launch_bounds__(kBlock) radiate_polarized_kernel(RadArgs A) {
     double t = src[0], x = src[cs], y = src[2 * cs], z = src[3 * cs];
     double kc[4] = {src[4 * cs], src[5 * cs], src[6 * cs], src[7 * cs]};
     double dlam = -src[8 * cs];
-    double r = rad::ks_radius(P.a, x, y, z);
+    double inv_r;
+    double r = rad::ks_radius(P.a, x, y, z, inv_r);
 
     // ---- sample the plasma ----
     rad::SampleStatus st;
@@ -627,7 +628,7 @@ __global__ void __launch_bounds__(kBlock) radiate_polarized_kernel(RadArgs A) {
     else if (rad::geometric_cut(P, x, y, z, r))
       st = rad::kSampleCut;
     else
-      st = rad::sample_grid(P, G, bounds_s, x, y, z, r, b_cache, pr, si);
+      st = rad::sample_grid(P, G, bounds_s, x, y, z, r, inv_r, cache, pr, si);
     if (st == rad::kSampleNan) {
       float qn = nanf("");
       pr.rho = pr.pgas = pr.kappa = pr.uu1 = pr.uu2 = pr.uu3 = pr.bb1 = pr.bb2 = pr.bb3 = qn;
@@ -636,7 +637,7 @@ __global__ void __launch_bounds__(kBlock) radiate_polarized_kernel(RadArgs A) {
       pr.uu1 = pr.uu2 = pr.uu3 = pr.bb1 = pr.bb2 = pr.bb3 = 0.0f;
     }
     rad::Plasma ps;
-    rad::plasma_state(P, x, y, z, r, pr, 2, ps);
+    rad::plasma_state(P, x, y, z, r, inv_r, pr, 2, ps);
     bool coupled = st != rad::kSampleCut && !ps.value_cut && !ps.b_zero;
     double cv[RAD_NUM_CELL_VALUES];
     for (int q = 0; q < RAD_NUM_CELL_VALUES; q++) cv[q] = nan("");
@@ -831,20 +832,24 @@ __global__ void __launch_bounds__(kBlock) radiate_polarized_kernel(RadArgs A) {
 }
 
 template <int FMAX>
-cudaError_t launch_fmax(const RadArgs &A, cudaStream_t stream) {
+cudaError_t launch_fmax(const RadArgs &A, const RadParams &P, cudaStream_t stream) {
   unsigned grid = (unsigned)((A.rays + kBlock - 1) / kBlock);
   size_t smem = 0;
   if ((size_t)A.grid.n_b * 6 * sizeof(double) <= 48 * 1024) smem = (size_t)A.grid.n_b * 6 * sizeof(double);
-  radiate_polarized_kernel<FMAX><<<grid, kBlock, smem, stream>>>(A);
+  radiate_polarized_kernel<FMAX><<<grid, kBlock, smem, stream>>>(A, P);
   return cudaGetLastError();
 }
 
 }  // namespace
 
-extern "C" cudaError_t bl_launch_radiate_polarized(const RadArgs *args, int num_freq, cudaStream_t stream) {
+// One translation unit per frequency-count bucket (BL_FMAX = 1, 4, 12, 32; see the Makefile).
+#ifndef BL_FMAX
+#define BL_FMAX 1
+#endif
+#define BL_CAT2(a, b) a##b
+#define BL_CAT(a, b) BL_CAT2(a, b)
+extern "C" cudaError_t BL_CAT(bl_launch_radiate_polarized_f, BL_FMAX)(const RadArgs *args, const RadParams *params,
+                                                                      cudaStream_t stream) {
   if (args->rays <= 0) return cudaSuccess;
-  if (num_freq <= 1) return launch_fmax<1>(*args, stream);
-  if (num_freq <= 4) return launch_fmax<4>(*args, stream);
-  if (num_freq <= 12) return launch_fmax<12>(*args, stream);
-  return launch_fmax<RAD_MAX_FREQ>(*args, stream);
+  return launch_fmax<BL_FMAX>(*args, *params, stream);
 }

@@ -15,61 +15,95 @@ namespace {
 
 constexpr int kBlock = 128;
 
-// Synchrotron emissivity / absorptivity for Stokes I at one frequency
-// (simulation_coefficients.cpp:458-524, :559-585, :608-664; invariant forms j/nu^2, alpha*nu).
-__device__ __forceinline__ void synchrotron_unpolarized(const RadParams &P, const rad::Plasma &s, double nu_cgs,
-                                                        double sin_theta_b, bool need_j, bool need_a,
-                                                        double &j_out, double &a_out) {
-  double nu_2 = nu_cgs * nu_cgs;
-  double nu_c = phys::e * s.bb_cgs / (2.0 * phys::pi * phys::m_e * phys::c);
+// Frequency-independent part of the Stokes-I synchrotron coefficients of one sample
+// (simulation_coefficients.cpp:458-524 thermal, :559-585 power law, :608-664 kappa; invariant forms
+// j/nu^2, alpha*nu).  The reference evaluates every power with std::pow per frequency; here the logarithms
+// of the per-sample quantities are taken once and each power is exp(c * ln x).
+struct SynchSample {
+  double om;          // omega * momentum_factor: nu = om * image_frequency
+  double inv_om;      // 1 / om
+  double n_nuc;       // n_e e^2 nu_c / c
+  double inv_nu_s;    // thermal: 1 / (2/9 nu_c theta_e^2 sin(theta_B))
+  double th_shape;    // thermal: thermal_frac * sqrt(2) pi / 27 * sin(theta_B) * n_nuc
+  double h_kt;        // thermal: h / (k T_e)
+  double log_om, log_ncs, log_ne;  // ln(om), ln(nu_c sin(theta_B)), ln(n_e)  [power law / kappa only]
+  double nu_c, sin_theta_b, n_e;
+};
+
+__device__ __forceinline__ void synch_sample(const RadParams &P, const rad::Plasma &s, double om,
+                                             double sin_theta_b, SynchSample &q) {
+  q.om = om;
+  q.inv_om = 1.0 / om;
+  q.nu_c = s.bb_cgs * (phys::e / (2.0 * phys::pi * phys::m_e * phys::c));
+  q.sin_theta_b = sin_theta_b;
+  q.n_e = s.n_e_cgs;
+  q.n_nuc = s.n_e_cgs * q.nu_c * (phys::e * phys::e / phys::c);
+  q.inv_nu_s = q.th_shape = q.h_kt = 0.0;
+  if (P.thermal_frac != 0.0) {
+    // 1/nu_s = 9/2 / (nu_c theta_e^2 sin(theta_B)), with 1/theta_e already known
+    q.inv_nu_s = 4.5 * s.inv_theta_e * s.inv_theta_e / (q.nu_c * sin_theta_b);
+    q.th_shape = P.thermal_frac * (phys::sqrt2 * phys::pi / 27.0) * sin_theta_b * q.n_nuc;
+    q.h_kt = phys::h * s.inv_theta_e * (1.0 / (phys::m_e * phys::c * phys::c));
+  }
+  q.log_om = q.log_ncs = q.log_ne = 0.0;
+  if (P.power_frac != 0.0 || P.kappa_frac != 0.0) {
+    q.log_om = log(om);
+    q.log_ncs = log(q.nu_c * sin_theta_b);
+    q.log_ne = log(s.n_e_cgs);
+  }
+}
+
+// Coefficients at image frequency l.
+__device__ __forceinline__ void synchrotron_unpolarized(const RadParams &P, const SynchSample &q, int l,
+                                                        bool need_j, bool need_a, double &j_out, double &a_out) {
+  double nu_cgs = q.om * P.freqs[l];
+  double inv_nu = q.inv_om * P.inv_freqs[l];
+  double inv_nu_2 = inv_nu * inv_nu;
   double j_val = 0.0, a_val = 0.0;
   if (P.thermal_frac != 0.0) {
-    double nu_s = 2.0 / 9.0 * nu_c * s.theta_e * s.theta_e * sin_theta_b;
-    double xx = nu_cgs / nu_s;
+    double xx = nu_cgs * q.inv_nu_s;
     double xx_1_2 = sqrt(xx);
     double xx_1_3 = cbrt(xx);
     double xx_1_6 = sqrt(xx_1_3);
-    double coefficient = P.thermal_frac * s.n_e_cgs * phys::e * phys::e * nu_c / (phys::c * nu_2) * exp(-xx_1_3);
-    double var_a = phys::sqrt2 * phys::pi / 27.0 * sin_theta_b;
     const double var_b = 1.8877486253633870;  // 2^(11/12)
     double var_c = xx_1_2 + var_b * xx_1_6;
-    double j_th = coefficient * var_a * var_c * var_c;
+    double j_th = q.th_shape * inv_nu_2 * exp(-xx_1_3) * (var_c * var_c);
     if (need_j) j_val = j_th;
-    double b_nu_nu_3 = 2.0 * phys::h / (phys::c * phys::c) / expm1(phys::h * nu_cgs / s.kb_tt_e_cgs);
     if (need_a) {
-      a_val = j_th / b_nu_nu_3;
-      // absorptivities too small to square are flushed (simulation_coefficients.cpp:513-523)
-      if (1.0 / (a_val * a_val) == INFINITY) a_val = 0.0;
+      // Kirchhoff: alpha nu = j/nu^2 / (B_nu/nu^3), B_nu/nu^3 = 2h/c^2 / expm1(h nu / k T_e)
+      a_val = j_th * expm1(q.h_kt * nu_cgs) * (phys::c * phys::c / (2.0 * phys::h));
+      // absorptivities too small to square are flushed (simulation_coefficients.cpp:513-523:
+      // 1/(a*a) == inf  <=>  a*a <= 2^-1024)
+      if (a_val * a_val <= 0x1p-1024) a_val = 0.0;
     }
   }
-  if (P.power_frac != 0.0) {
-    if (need_j) {
-      double var_a = pow(nu_cgs / (nu_c * sin_theta_b), -(P.plasma_p - 1.0) / 2.0);
-      j_val += P.power_frac * s.n_e_cgs * phys::e * phys::e * nu_c / (phys::c * nu_2) * P.power_jj * sin_theta_b * var_a;
+  if (P.power_frac != 0.0 || P.kappa_frac != 0.0) {
+    double log_nu = q.log_om + P.log_freqs[l];
+    double lr = log_nu - q.log_ncs;  // ln(nu / (nu_c sin(theta_B)))
+    if (P.power_frac != 0.0) {
+      if (need_j)
+        j_val += P.power_frac * q.n_nuc * inv_nu_2 * P.power_jj * q.sin_theta_b * exp(-(P.plasma_p - 1.0) / 2.0 * lr);
+      if (need_a)
+        a_val += P.power_frac * q.n_e * (phys::e * phys::e / (phys::m_e * phys::c)) * P.power_aa *
+                 exp(-(P.plasma_p + 2.0) / 2.0 * lr);
     }
-    if (need_a) {
-      double var_a = pow(nu_cgs / (nu_c * sin_theta_b), -(P.plasma_p + 2.0) / 2.0);
-      a_val += P.power_frac * s.n_e_cgs * phys::e * phys::e / (phys::m_e * phys::c) * P.power_aa * var_a;
-    }
-  }
-  if (P.kappa_frac != 0.0) {
-    double nu_kappa = nu_c * P.plasma_w * P.plasma_w * P.plasma_kappa * P.plasma_kappa * sin_theta_b;
-    double xx = nu_cgs / nu_kappa;
-    if (need_j) {
-      double var_a = P.kappa_frac * s.n_e_cgs * phys::e * phys::e * nu_c / (phys::c * nu_2);
-      double var_b = cbrt(xx) * sin_theta_b;
-      double var_c = pow(xx, -(P.plasma_kappa - 2.0) / 2.0) * sin_theta_b;
-      double lo = P.kappa_jj_low * var_a * var_b;
-      double hi = P.kappa_jj_high * var_a * var_c;
-      j_val += pow(pow(lo, -P.kappa_jj_x_i) + pow(hi, -P.kappa_jj_x_i), -1.0 / P.kappa_jj_x_i);
-    }
-    if (need_a) {
-      double var_a = P.kappa_frac * s.n_e_cgs * phys::e * phys::e / (phys::m_e * phys::c);
-      double var_b = pow(xx, -2.0 / 3.0);
-      double var_c = pow(xx, -(1.0 + P.plasma_kappa) / 2.0);
-      double lo = P.kappa_aa_low * var_a * var_b;
-      double hi = P.kappa_aa_high * var_a * var_c * P.kappa_aa_high_i;
-      a_val += pow(pow(lo, -P.kappa_aa_x_i) + pow(hi, -P.kappa_aa_x_i), -1.0 / P.kappa_aa_x_i);
+    if (P.kappa_frac != 0.0) {
+      double lx = lr - P.log_w2k2;  // ln(nu / nu_kappa)
+      if (need_j) {
+        // ln of kappa_frac n_e e^2 nu_c / (c nu^2) * sin(theta_B)
+        double lva = P.log_k_j_pref + q.log_ne + q.log_ncs - 2.0 * log_nu;
+        double l_lo = P.log_kjl + lva + lx * (1.0 / 3.0);
+        double l_hi = P.log_kjh + lva - (P.plasma_kappa - 2.0) / 2.0 * lx;
+        double sum = exp(-P.kappa_jj_x_i * l_lo) + exp(-P.kappa_jj_x_i * l_hi);
+        j_val += exp(-log(sum) / P.kappa_jj_x_i);
+      }
+      if (need_a) {
+        double lva = P.log_k_a_pref + q.log_ne;
+        double l_lo = P.log_kal + lva - 2.0 / 3.0 * lx;
+        double l_hi = P.log_kah + lva - (1.0 + P.plasma_kappa) / 2.0 * lx;
+        double sum = exp(-P.kappa_aa_x_i * l_lo) + exp(-P.kappa_aa_x_i * l_hi);
+        a_val += exp(-log(sum) / P.kappa_aa_x_i);
+      }
     }
   }
   j_out = j_val;
@@ -106,10 +140,12 @@ __device__ __forceinline__ void formula_fluid(const RadParams &P, double x, doub
   n_n0 = exp(-0.5 * (r * r / (P.formula_r0 * P.formula_r0) + P.formula_h * P.formula_h * cth * cth));
 }
 
-template <int FMAX, bool SIM>
-__global__ void __launch_bounds__(kBlock) radiate_unpolarized_kernel(RadArgs A) {
+// LEAN: only the light image is requested (no auxiliary images, no rendering) -- the common case gets a
+// kernel without the dead register state of the rest.
+template <int FMAX, bool SIM, bool LEAN>
+__global__ void __launch_bounds__(kBlock, (FMAX <= 4 ? 4 : 2))
+radiate_unpolarized_kernel(const __grid_constant__ RadArgs A, const __grid_constant__ RadParams P) {
   extern __shared__ double smem_bounds[];
-  const RadParams &P = *A.P;
   const GridDev &G = A.grid;
   const double *bounds_s = nullptr;
   if (SIM) {
@@ -139,12 +175,12 @@ __global__ void __launch_bounds__(kBlock) radiate_unpolarized_kernel(RadArgs A) 
   for (int l = 0; l < FMAX; l++) I[l] = 0.0;
   double *img = A.image + m;  // quantity q of this ray at img[q * stride]
   const int64_t stride = A.image_stride;
-  const bool aux = P.image_time || P.image_length || P.image_lambda || P.image_emission || P.image_tau ||
-                   P.image_lambda_ave || P.image_emission_ave || P.image_tau_int || P.image_crossings;
+  const bool aux = !LEAN && (P.image_time || P.image_length || P.image_lambda || P.image_emission || P.image_tau ||
+                             P.image_lambda_ave || P.image_emission_ave || P.image_tau_int || P.image_crossings);
   const bool need_j = P.image_light || P.image_emission || P.image_emission_ave;
   const bool need_a = P.image_light || P.image_tau || P.image_tau_int;
   const bool want_coeff = P.image_light || P.image_emission || P.image_tau || P.image_emission_ave || P.image_tau_int;
-  const bool do_render = SIM && A.render != nullptr && P.render_num_images > 0;
+  const bool do_render = !LEAN && SIM && A.render != nullptr && P.render_num_images > 0;
   bool fill_present = false;
   if (do_render)
     for (int f = 0; f < P.render_feature_start[P.render_num_images]; f++)
@@ -169,7 +205,8 @@ __global__ void __launch_bounds__(kBlock) radiate_unpolarized_kernel(RadArgs A) 
   }
   double prev_cv[RAD_NUM_CELL_VALUES];
   for (int q = 0; q < RAD_NUM_CELL_VALUES; q++) prev_cv[q] = nan("");
-  int b_cache = 0;
+  rad::CellCache cache = {0, 0, 0, 0};
+  const double inv_mom_x = P.x_unit / mom;  // affine step -> cm per unit image frequency
   unsigned long long processed = 0;
   const size_t cs = (size_t)A.sb.cap * (size_t)A.sb.rays;
 
@@ -182,9 +219,10 @@ __global__ void __launch_bounds__(kBlock) radiate_unpolarized_kernel(RadArgs A) 
     double dlam = -src[8 * cs];
     int n_ref = num - 1 - n;  // index in the reference's reversed arrays (taps only)
 
-    double r = rad::ks_radius(P.a, x, y, z);
+    double inv_r;
+    double r = rad::ks_radius(P.a, x, y, z, inv_r);
     double omega = 0.0;      // -k_mu u^mu
-    double sin_theta_b = 0.0;
+    SynchSample sq;
     bool coupled = false;    // coefficients are nonzero candidates
     bool nan_sample = false;
     rad::Plasma ps;
@@ -203,7 +241,7 @@ __global__ void __launch_bounds__(kBlock) radiate_unpolarized_kernel(RadArgs A) 
       else if (rad::geometric_cut(P, x, y, z, r))
         st = rad::kSampleCut;
       else
-        st = rad::sample_grid(P, G, bounds_s, x, y, z, r, b_cache, pr, si);
+        st = rad::sample_grid(P, G, bounds_s, x, y, z, r, inv_r, cache, pr, si);
       if (A.taps.nan_) {
         size_t ti = (size_t)m * A.taps.S + n_ref;
         A.taps.nan_[ti] = st == rad::kSampleNan;
@@ -225,16 +263,16 @@ __global__ void __launch_bounds__(kBlock) radiate_unpolarized_kernel(RadArgs A) 
         pr.uu1 = pr.uu2 = pr.uu3 = pr.bb1 = pr.bb2 = pr.bb3 = 0.0f;
       }
       if (st != rad::kSampleCut) {
-        rad::plasma_state(P, x, y, z, r, pr, want_coeff ? 1 : 0, ps);
+        rad::plasma_state(P, x, y, z, r, inv_r, pr, want_coeff ? 1 : 0, ps);
         if (!ps.value_cut) {
-          if (P.need_cell_values) rad::cell_values_of(ps, cv);
+          if (!LEAN && P.need_cell_values) rad::cell_values_of(ps, cv);
           if (want_coeff && !ps.b_zero) {
             omega = -(kc[0] * ps.ucon[0] + kc[1] * ps.ucon[1] + kc[2] * ps.ucon[2] + kc[3] * ps.ucon[3]);
             double kb = kc[0] * ps.bcon[0] + kc[1] * ps.bcon[1] + kc[2] * ps.bcon[2] + kc[3] * ps.bcon[3];
             // fluid-frame pitch angle: |k_spatial| = omega and |b| = sqrt(b^2) in the frame of u
             double c2 = kb * kb / (omega * omega * ps.b_sq);
             c2 = 1.0 < c2 ? 1.0 : c2;
-            sin_theta_b = sqrt(1.0 - c2);
+            synch_sample(P, ps, omega * mom, sqrt(1.0 - c2), sq);
             coupled = true;
             nan_sample = st == rad::kSampleNan;
           }
@@ -279,16 +317,15 @@ __global__ void __launch_bounds__(kBlock) radiate_unpolarized_kernel(RadArgs A) 
 #pragma unroll
     for (int l = 0; l < FMAX; l++) {
       if (l >= F) break;
-      double freq = P.freqs[l];
-      double dlam_cgs = dlam * P.x_unit / (freq * mom);
+      double dlam_cgs = dlam * inv_mom_x * P.inv_freqs[l];
       double j = 0.0, alpha = 0.0;
       if (coupled) {
         if (SIM) {
-          synchrotron_unpolarized(P, ps, omega * freq * mom, sin_theta_b, need_j, need_a, j, alpha);
+          synchrotron_unpolarized(P, sq, l, need_j, need_a, j, alpha);
         } else if (P.fallback_nan && flagged) {
           if (l == 0) j = alpha = nan("");
         } else {
-          double nu = omega * freq * mom;
+          double nu = omega * P.freqs[l] * mom;
           double jn = P.formula_cn0 * n_n0 * pow(nu / P.formula_nup, -P.formula_alpha);
           j = jn / (nu * nu);
           double an = P.formula_a * P.formula_cn0 * n_n0 * pow(nu / P.formula_nup, -P.formula_beta - P.formula_alpha);
@@ -300,16 +337,26 @@ __global__ void __launch_bounds__(kBlock) radiate_unpolarized_kernel(RadArgs A) 
       double delta_tau = alpha * dlam_cgs;
       bool thin = delta_tau <= 100.0;
       double exp_neg = 0.0, em1 = 0.0;
-      if (alpha > 0.0 || P.image_tau_int) {
-        exp_neg = exp(-delta_tau);
-        em1 = expm1(delta_tau);
-      }
-      if (P.image_light) {
+      if (LEAN) {
+        // I <- e^-dtau (I + S expm1(dtau)) = I + (S - I)(1 - e^-dtau)   (unpolarized.cpp:99-110)
         if (alpha > 0.0) {
           double ss = j / alpha;
-          I[l] = thin ? exp_neg * (I[l] + ss * em1) : ss;
+          I[l] = thin ? I[l] - (ss - I[l]) * expm1(-delta_tau) : ss;
         } else {
           I[l] += j * dlam_cgs;
+        }
+      } else {
+        if (alpha > 0.0 || P.image_tau_int) {
+          exp_neg = exp(-delta_tau);
+          em1 = expm1(delta_tau);
+        }
+        if (P.image_light) {
+          if (alpha > 0.0) {
+            double ss = j / alpha;
+            I[l] = thin ? exp_neg * (I[l] + ss * em1) : ss;
+          } else {
+            I[l] += j * dlam_cgs;
+          }
         }
       }
       if (aux) {
@@ -363,25 +410,37 @@ __global__ void __launch_bounds__(kBlock) radiate_unpolarized_kernel(RadArgs A) 
 }
 
 template <int FMAX>
-cudaError_t launch_fmax(const RadArgs &A, bool sim, int n_b, cudaStream_t stream) {
+cudaError_t launch_fmax(const RadArgs &A, const RadParams &P, cudaStream_t stream) {
+  const bool sim = P.model_type == 0;
+  const bool lean = P.image_light && !(P.image_time || P.image_length || P.image_lambda || P.image_emission ||
+                                       P.image_tau || P.image_lambda_ave || P.image_emission_ave || P.image_tau_int ||
+                                       P.image_crossings) &&
+                    !(sim && A.render != nullptr && P.render_num_images > 0);
   unsigned grid = (unsigned)((A.rays + kBlock - 1) / kBlock);
   size_t smem = 0;
-  if (sim && (size_t)n_b * 6 * sizeof(double) <= 48 * 1024) smem = (size_t)n_b * 6 * sizeof(double);
-  if (sim)
-    radiate_unpolarized_kernel<FMAX, true><<<grid, kBlock, smem, stream>>>(A);
+  if (sim && (size_t)A.grid.n_b * 6 * sizeof(double) <= 48 * 1024) smem = (size_t)A.grid.n_b * 6 * sizeof(double);
+  if (sim && lean)
+    radiate_unpolarized_kernel<FMAX, true, true><<<grid, kBlock, smem, stream>>>(A, P);
+  else if (sim)
+    radiate_unpolarized_kernel<FMAX, true, false><<<grid, kBlock, smem, stream>>>(A, P);
+  else if (lean)
+    radiate_unpolarized_kernel<FMAX, false, true><<<grid, kBlock, 0, stream>>>(A, P);
   else
-    radiate_unpolarized_kernel<FMAX, false><<<grid, kBlock, 0, stream>>>(A);
+    radiate_unpolarized_kernel<FMAX, false, false><<<grid, kBlock, 0, stream>>>(A, P);
   return cudaGetLastError();
 }
 
 }  // namespace
 
-extern "C" cudaError_t bl_launch_radiate_unpolarized(const RadArgs *args, int num_freq, int simulation,
-                                                     cudaStream_t stream) {
+// One translation unit per frequency-count bucket (BL_FMAX = 1, 4, 12, 32; see the Makefile) so that the
+// buckets compile in parallel.
+#ifndef BL_FMAX
+#define BL_FMAX 1
+#endif
+#define BL_CAT2(a, b) a##b
+#define BL_CAT(a, b) BL_CAT2(a, b)
+extern "C" cudaError_t BL_CAT(bl_launch_radiate_unpolarized_f, BL_FMAX)(const RadArgs *args, const RadParams *params,
+                                                                        cudaStream_t stream) {
   if (args->rays <= 0) return cudaSuccess;
-  int n_b = args->grid.n_b;
-  if (num_freq <= 1) return launch_fmax<1>(*args, simulation != 0, n_b, stream);
-  if (num_freq <= 4) return launch_fmax<4>(*args, simulation != 0, n_b, stream);
-  if (num_freq <= 12) return launch_fmax<12>(*args, simulation != 0, n_b, stream);
-  return launch_fmax<RAD_MAX_FREQ>(*args, simulation != 0, n_b, stream);
+  return launch_fmax<BL_FMAX>(*args, *params, stream);
 }
