@@ -16,9 +16,9 @@ extern "C" cudaError_t bl_launch_geodesic_dp(const GeoArgs *args, int flat, int 
 extern "C" cudaError_t bl_launch_geodesic_rk(const GeoArgs *args, int flat, int order, int sm_count, cudaStream_t stream);
 #define BL_DECL_RAD(name) extern "C" cudaError_t name(const RadArgs *args, const RadParams *params, cudaStream_t stream)
 BL_DECL_RAD(bl_launch_radiate_unpolarized_f1); BL_DECL_RAD(bl_launch_radiate_unpolarized_f4);
-BL_DECL_RAD(bl_launch_radiate_unpolarized_f12); BL_DECL_RAD(bl_launch_radiate_unpolarized_f32);
+BL_DECL_RAD(bl_launch_radiate_unpolarized_f32);
 BL_DECL_RAD(bl_launch_radiate_polarized_f1); BL_DECL_RAD(bl_launch_radiate_polarized_f4);
-BL_DECL_RAD(bl_launch_radiate_polarized_f12); BL_DECL_RAD(bl_launch_radiate_polarized_f32);
+BL_DECL_RAD(bl_launch_radiate_polarized_f32);
 extern "C" cudaError_t bl_launch_relayout_grid(const float *prim, int n_var, const int *var_index, size_t cells,
                                                float4 *out, float *kappa_out, cudaStream_t stream);
 extern "C" cudaError_t bl_launch_unpack_samples(const StepBuffer *sb, const int32_t *num, int64_t rays, int S,
@@ -288,7 +288,15 @@ void fill_rad_params(const bl_params &p, RadParams &r) {
     r.log_kal = std::log(r.kappa_aa_low); r.log_kah = std::log(r.kappa_aa_high * r.kappa_aa_high_i);
     r.log_k_j_pref = std::log(p.plasma_kappa_frac * phys::e * phys::e / phys::c);
     r.log_k_a_pref = std::log(p.plasma_kappa_frac * phys::e * phys::e / (phys::m_e * phys::c));
+    r.log_kah_base = std::log(r.kappa_aa_high);
+    if (r.polarization) {
+      r.log_kj_low_q = std::log(r.kappa_jj_low_q); r.log_kj_low_v = std::log(r.kappa_jj_low_v);
+      r.log_kj_high_q = std::log(r.kappa_jj_high_q); r.log_kj_high_v = std::log(r.kappa_jj_high_v);
+      r.log_ka_low_q = std::log(r.kappa_aa_low_q); r.log_ka_low_v = std::log(r.kappa_aa_low_v);
+      r.log_ka_high_q = std::log(r.kappa_aa_high_q); r.log_ka_high_v = std::log(r.kappa_aa_high_v);
+    }
   }
+  if (sim && p.plasma_power_frac != 0.0) r.log_power_gmin = std::log(2.0 * p.plasma_gamma_min * p.plasma_gamma_min / 3.0);
   r.fallback_nan = p.fallback_nan; r.fallback_rho = p.fallback_rho; r.fallback_pgas = p.fallback_pgas;
   r.fallback_kappa = p.fallback_kappa;
   for (int i = 0; i <= BL_MAX_RENDER_FEATURES; i++) r.render_feature_start[i] = p.render_feature_start[i];
@@ -601,18 +609,16 @@ int radiate_wave(bl_ctx *ctx, Level &L, int64_t first, int64_t count) {
     A.taps.fracs = L.tap_fracs ? L.tap_fracs + 3 * o : nullptr;
   }
   // parameters travel by value in the kernel's constant bank (no device copy, no per-sample loads)
-  // the kernels are instantiated for frequency-count buckets of 1, 4, 12 and 32 (one object file each)
+  // the kernels are instantiated for frequency-count buckets of 1, 4 and 32 (one object file each)
   const int F = ctx->rad.num_freq;
   cudaError_t le;
   if (ctx->rad.polarization)
     le = F <= 1 ? bl_launch_radiate_polarized_f1(&A, &ctx->rad, ctx->stream)
        : F <= 4 ? bl_launch_radiate_polarized_f4(&A, &ctx->rad, ctx->stream)
-       : F <= 12 ? bl_launch_radiate_polarized_f12(&A, &ctx->rad, ctx->stream)
                  : bl_launch_radiate_polarized_f32(&A, &ctx->rad, ctx->stream);
   else
     le = F <= 1 ? bl_launch_radiate_unpolarized_f1(&A, &ctx->rad, ctx->stream)
        : F <= 4 ? bl_launch_radiate_unpolarized_f4(&A, &ctx->rad, ctx->stream)
-       : F <= 12 ? bl_launch_radiate_unpolarized_f12(&A, &ctx->rad, ctx->stream)
                  : bl_launch_radiate_unpolarized_f32(&A, &ctx->rad, ctx->stream);
   BL_CUDA_CHECK(le);
   ctx->launches++;

@@ -91,6 +91,10 @@ struct RadParams {
   double log_w2k2;                  // ln(w^2 kappa^2)
   double log_kjl, log_kjh, log_kal, log_kah;   // ln of kappa_jj_low, _high, kappa_aa_low, kappa_aa_high*kappa_aa_high_i
   double log_k_j_pref, log_k_a_pref;           // ln(kappa_frac e^2 / c), ln(kappa_frac e^2 / (m_e c))
+  double log_kah_base;                         // ln kappa_aa_high (without the Stokes-I factor)
+  double log_kj_low_q, log_kj_low_v, log_kj_high_q, log_kj_high_v;   // ln kappa_jj_{low,high}_{q,v}
+  double log_ka_low_q, log_ka_low_v, log_ka_high_q, log_ka_high_v;   // ln kappa_aa_{low,high}_{q,v}
+  double log_power_gmin;                       // ln(2 gamma_min^2 / 3)
   int32_t need_sigma_beta;          // sigma / beta_inverse needed as values (cell values or cuts)
   // rendering
   int32_t render_num_images;

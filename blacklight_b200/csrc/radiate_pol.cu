@@ -16,6 +16,15 @@ namespace {
 
 constexpr int kBlock = 128;
 
+// Frequency loops: fully unrolled with the per-frequency state in registers for the small buckets
+// (FMAX <= 4); a rolled loop over state in thread-local memory for the large one (the per-frequency
+// work is ~1e3 instructions, so the loop overhead is nothing and the code stays small).
+#if defined(BL_FMAX) && BL_FMAX > 4
+#define BL_FREQ_LOOP _Pragma("unroll 1")
+#else
+#define BL_FREQ_LOOP _Pragma("unroll")
+#endif
+
 // ---------------------------------------------------------------------------------------------------
 // Kerr-Schild geometry: g_{mu nu} = eta + f l_mu l_nu, l_mu = (1, l_i), l^mu = (-1, l_i), M = 1.
 struct KsJet {
@@ -253,126 +262,188 @@ struct Coefficients {
   double j[3], a[3], rho[2];  // (I,Q,V), (I,Q,V), (Q,V); Stokes U components vanish in this tetrad
 };
 
-// Polarized synchrotron coefficients at one frequency (simulation_coefficients.cpp:458-698).
-// kk = (K_0, K_1, K_2)(1/theta_e) hoisted out of the frequency loop (valid iff theta_e >= 0.01).
-__device__ __forceinline__ void synchrotron_polarized(const RadParams &P, const rad::Plasma &s, double nu_cgs,
-                                                      double sin_theta_b, double cos_theta_b, const double kk[3],
-                                                      Coefficients &C) {
-  const double e2 = phys::e * phys::e;
-  double nu_2 = nu_cgs * nu_cgs;
-  double sin2 = sin_theta_b * sin_theta_b;   // 1 - cos^2 as formed by the caller
-  double nu_c = phys::e * s.bb_cgs / (2.0 * phys::pi * phys::m_e * phys::c);
-  for (int q = 0; q < 3; q++) C.j[q] = C.a[q] = 0.0;
-  C.rho[0] = C.rho[1] = 0.0;
-  double n_e = s.n_e_cgs;
+// (lo^-x + hi^-x)^(-1/x) from the logarithms a = ln lo, b = ln hi: the bridging form every kappa fit uses
+// (simulation_coefficients.cpp:641-698).  Evaluated around the smaller of the two, so no intermediate
+// overflows; lo = 0 or hi = 0 (logarithm -inf) gives 0 and NaN propagates, as in the reference.
+__device__ __forceinline__ double bridge(double a, double b, double x, double inv_x) {
+  double d = a == b ? 0.0 : a - b;
+  double m = d < 0.0 ? a : b;
+  return exp(m - log(1.0 + exp(-x * fabs(d))) * inv_x);
+}
+
+// Frequency-independent part of the polarized synchrotron coefficients of one sample.  The reference
+// (simulation_coefficients.cpp:458-698) evaluates ~45 std::pow per frequency for the kappa distribution;
+// here logarithms of the per-sample quantities are taken once, powers of the pitch angle are hoisted, and
+// each remaining power is exp(c * ln x).
+struct PolSample {
+  double om, inv_om;        // nu = om * image_frequency
+  double nu_c, sin_b, cos_b, sin2, n_e, n_nuc;   // n_nuc = n_e e^2 nu_c / c
+  double sgn;               // sign of cos(theta_B)
+  // thermal
+  double inv_nu_s, log_inv_nu_s, h_kt, theta_e, var_d, cos_over_theta;
+  double k1_k2, k0, inv_k2; // Bessel ratios (valid iff theta_e >= 0.01)
+  // power law / kappa
+  double log_om, log_ncs, log_ne, cot;
+  double power_vb;          // (3.1 sin^-1.92 - 3.1)^0.512
+  double inv_nu_k;          // 1 / nu_kappa
+  double lvd_j, lvf_j, lvd_a, lvf_a;   // ln of the pitch-angle factors of j_V and alpha_V (kappa)
+};
+
+__device__ __forceinline__ void pol_sample(const RadParams &P, const rad::Plasma &s, double om, double sin_b,
+                                           double cos_b, const double kk[3], PolSample &q) {
+  q.om = om;
+  q.inv_om = 1.0 / om;
+  q.nu_c = s.bb_cgs * (phys::e / (2.0 * phys::pi * phys::m_e * phys::c));
+  q.sin_b = sin_b;
+  q.cos_b = cos_b;
+  q.sin2 = sin_b * sin_b;
+  q.sgn = cos_b >= 0.0 ? 1.0 : -1.0;
+  q.n_e = s.n_e_cgs;
+  q.n_nuc = s.n_e_cgs * q.nu_c * (phys::e * phys::e / phys::c);
+  q.theta_e = s.theta_e;
+  q.inv_nu_s = q.log_inv_nu_s = q.h_kt = q.var_d = q.cos_over_theta = 0.0;
+  q.k1_k2 = q.k0 = q.inv_k2 = 0.0;
   if (P.thermal_frac != 0.0) {
-    double nu_s = 2.0 / 9.0 * nu_c * s.theta_e * s.theta_e * sin_theta_b;
-    double xx = nu_cgs / nu_s;
-    double xx_1_2 = sqrt(xx), xx_1_3 = cbrt(xx);
+    q.inv_nu_s = 4.5 * s.inv_theta_e * s.inv_theta_e / (q.nu_c * sin_b);
+    q.h_kt = phys::h * s.inv_theta_e * (1.0 / (phys::m_e * phys::c * phys::c));
+    double te96 = pow(s.theta_e, 0.96);
+    q.var_d = (7.0 * te96 + 35.0) / (10.0 * te96 + 75.0) * 1.8877486253633870;
+    q.cos_over_theta = cos_b * s.inv_theta_e;
+    if (s.theta_e >= 0.01) {
+      q.log_inv_nu_s = log(q.inv_nu_s);
+      q.inv_k2 = 1.0 / kk[2];
+      q.k1_k2 = kk[1] * q.inv_k2;
+      q.k0 = kk[0];
+    }
+  }
+  q.log_om = log(om);
+  q.log_ncs = q.log_ne = q.cot = q.power_vb = q.inv_nu_k = 0.0;
+  q.lvd_j = q.lvf_j = q.lvd_a = q.lvf_a = 0.0;
+  if (P.power_frac != 0.0 || P.kappa_frac != 0.0) {
+    q.log_ncs = log(q.nu_c * sin_b);
+    q.log_ne = log(s.n_e_cgs);
+    double log_sin = log(sin_b);
+    if (P.power_frac != 0.0) {
+      q.cot = cos_b / sin_b;
+      q.power_vb = pow(3.1 * exp(-1.92 * log_sin) - 3.1, 0.512);
+    }
+    if (P.kappa_frac != 0.0) {
+      q.inv_nu_k = 1.0 / (q.nu_c * P.plasma_w * P.plasma_w * P.plasma_kappa * P.plasma_kappa * sin_b);
+      q.lvd_j = 0.48 * log(exp(-2.4 * log_sin) - 1.0);
+      q.lvf_j = 0.44 * log(exp(-2.5 * log_sin) - 1.0);
+      q.lvd_a = 0.446 * log(exp(-2.28 * log_sin) - 1.0);
+      q.lvf_a = 0.5 * log(exp(-2.05 * log_sin) - 1.0);
+    }
+  }
+}
+
+// Polarized synchrotron coefficients at image frequency l (simulation_coefficients.cpp:458-698).
+__device__ __forceinline__ void synchrotron_polarized(const RadParams &P, const PolSample &q, int l, Coefficients &C) {
+  const double e2 = phys::e * phys::e;
+  double nu_cgs = q.om * P.freqs[l];
+  double inv_nu = q.inv_om * P.inv_freqs[l];
+  double inv_nu_2 = inv_nu * inv_nu;
+  for (int i = 0; i < 3; i++) C.j[i] = C.a[i] = 0.0;
+  C.rho[0] = C.rho[1] = 0.0;
+  if (P.thermal_frac != 0.0) {
+    double xx = nu_cgs * q.inv_nu_s;
+    double xx_neg_1_2 = rsqrt(xx);
+    double xx_1_2 = xx * xx_neg_1_2, xx_1_3 = cbrt(xx);
     double xx_1_6 = sqrt(xx_1_3);
-    double coefficient = P.thermal_frac * n_e * e2 * nu_c / (phys::c * nu_2) * exp(-xx_1_3);
-    double var_a = phys::sqrt2 * phys::pi / 27.0 * sin_theta_b;
+    double coefficient = P.thermal_frac * q.n_nuc * inv_nu_2 * exp(-xx_1_3);
+    double var_a = phys::sqrt2 * phys::pi / 27.0 * q.sin_b;
     const double var_b = 1.8877486253633870;  // 2^(11/12)
     double var_c = xx_1_2 + var_b * xx_1_6;
     C.j[0] = coefficient * var_a * var_c * var_c;
-    double te96 = pow(s.theta_e, 0.96);
-    double var_d = (7.0 * te96 + 35.0) / (10.0 * te96 + 75.0) * var_b;
-    double var_e = xx_1_2 + var_d * xx_1_6;
-    double var_f = cos_theta_b / s.theta_e;
+    double var_e = xx_1_2 + q.var_d * xx_1_6;
     double var_g = phys::pi / 3.0 + phys::pi / 3.0 * xx_1_3 + 2.0 / 300.0 * xx_1_2 + 2.0 / 19.0 * phys::pi * xx_1_3 * xx_1_3;
     C.j[1] = -coefficient * var_a * var_e * var_e;
-    C.j[2] = coefficient * var_f * var_g;
-    double b_nu_nu_3 = 2.0 * phys::h / (phys::c * phys::c) / expm1(phys::h * nu_cgs / s.kb_tt_e_cgs);
-    C.a[0] = C.j[0] / b_nu_nu_3;
-    C.a[1] = C.j[1] / b_nu_nu_3;
-    C.a[2] = C.j[2] / b_nu_nu_3;
-    if (1.0 / (C.a[0] * C.a[0]) == INFINITY) C.a[0] = C.a[1] = C.a[2] = 0.0;
-    // Faraday rotation and conversion (M 33-37), with the cold-plasma trap below theta_e = 0.01
-    double coefficient_q = -P.thermal_frac * n_e * e2 * nu_c * nu_c * sin2 / (phys::m_e * phys::c * nu_2);
-    double coefficient_v = P.thermal_frac * 2.0 * n_e * e2 * nu_c * cos_theta_b / (phys::m_e * phys::c * nu_cgs);
+    C.j[2] = coefficient * q.cos_over_theta * var_g;
+    double inv_b_nu = expm1(q.h_kt * nu_cgs) * (phys::c * phys::c / (2.0 * phys::h));
+    C.a[0] = C.j[0] * inv_b_nu;
+    C.a[1] = C.j[1] * inv_b_nu;
+    C.a[2] = C.j[2] * inv_b_nu;
+    if (C.a[0] * C.a[0] <= 0x1p-1024) C.a[0] = C.a[1] = C.a[2] = 0.0;
+    // Faraday rotation and conversion, with the cold-plasma trap below theta_e = 0.01
+    double coefficient_q = -P.thermal_frac * q.n_e * e2 * q.nu_c * q.nu_c * q.sin2 * inv_nu_2 * (1.0 / (phys::m_e * phys::c));
+    double coefficient_v = P.thermal_frac * 2.0 * q.n_e * e2 * q.nu_c * q.cos_b * inv_nu * (1.0 / (phys::m_e * phys::c));
     double factor_q = 0.0, factor_v = 1.0;
-    if (s.theta_e >= 0.01) {
-      double xx_neg_1_2 = 1.0 / sqrt(xx);
-      double va = 2.011 * exp(-19.78 * pow(xx, -0.5175));
-      double vb = cos(39.89 * xx_neg_1_2) * exp(-70.16 * pow(xx, -0.6));
+    if (q.theta_e >= 0.01) {
+      double lx = q.log_om + P.log_freqs[l] + q.log_inv_nu_s;  // ln xx
+      double va = 2.011 * exp(-19.78 * exp(-0.5175 * lx));
+      double vb = cos(39.89 * xx_neg_1_2) * exp(-70.16 * exp(-0.6 * lx));
       double vc = 0.011 * exp(-1.69 * xx_neg_1_2);
-      double vd = 0.003135 * pow(xx, 4.0 / 3.0);
-      double ve = 0.5 * (1.0 + tanh(10.0 * log(0.6648 * xx_neg_1_2)));
+      double vd = 0.003135 * xx * xx_1_3;
+      double ve = 0.5 * (1.0 + tanh(10.0 * (-0.4082690354408987 - 0.5 * lx)));  // ln 0.6648
       double f_0 = va - vb - vc;
       double f_m = f_0 + (vc - vd) * ve;
-      double delta_jj_5 = 0.4379 * log(1.0 + 1.3414 * pow(xx, -0.7515));
-      factor_q = f_m * (kk[1] / kk[2] + 6.0 * s.theta_e);
-      factor_v = (kk[0] - delta_jj_5) / kk[2];
+      double delta_jj_5 = 0.4379 * log(1.0 + 1.3414 * exp(-0.7515 * lx));
+      factor_q = f_m * (q.k1_k2 + 6.0 * q.theta_e);
+      factor_v = (q.k0 - delta_jj_5) * q.inv_k2;
       factor_v = (factor_v < 0.0 || factor_v > 1.0) ? 1.0 : factor_v;
     }
     C.rho[0] = coefficient_q * factor_q;
     C.rho[1] = coefficient_v * factor_v;
   }
-  if (P.power_frac != 0.0) {
-    double ratio = nu_cgs / (nu_c * sin_theta_b);
-    double coefficient = P.power_frac * n_e * e2 * nu_c / (phys::c * nu_2) * P.power_jj * sin_theta_b *
-                         pow(ratio, -(P.plasma_p - 1.0) / 2.0);
-    double cot = cos_theta_b / sin_theta_b;
-    C.j[0] += coefficient;
-    C.j[1] += coefficient * P.power_jj_q;
-    C.j[2] += coefficient * P.power_jj_v * cot * (1.0 / sqrt(nu_cgs / (3.0 * nu_c * sin_theta_b)));
-    double coefficient_a = P.power_frac * n_e * e2 / (phys::m_e * phys::c) * P.power_aa * pow(ratio, -(P.plasma_p + 2.0) / 2.0);
-    double vb = pow(3.1 * pow(sin_theta_b, -1.92) - 3.1, 0.512);
-    double vc = 1.0 / sqrt(ratio);
-    double vd = cos_theta_b >= 0.0 ? 1.0 : -1.0;
-    C.a[0] += coefficient_a;
-    C.a[1] += coefficient_a * P.power_aa_q;
-    C.a[2] += coefficient_a * P.power_aa_v * vb * vc * vd;
-    double ra = n_e * e2 * nu_cgs / (phys::m_e * phys::c * nu_c * sin_theta_b);
-    double rb = nu_c * sin_theta_b / nu_cgs;
-    double rc = rb * rb, rd = rc * rb;
-    double re = 1.0 - pow(2.0 * nu_c * P.plasma_gamma_min * P.plasma_gamma_min * sin_theta_b / (3.0 * nu_cgs), P.plasma_p / 2.0 - 1.0);
-    double coefficient_r = P.power_frac * P.power_rho * ra;
-    C.rho[0] += coefficient_r * P.power_rho_q * rd * re;
-    C.rho[1] += coefficient_r * P.power_rho_v * rc * cot;
-  }
-  if (P.kappa_frac != 0.0) {
-    double nu_kappa = nu_c * P.plasma_w * P.plasma_w * P.plasma_kappa * P.plasma_kappa * sin_theta_b;
-    double xx = nu_cgs / nu_kappa;
-    double sgn = cos_theta_b >= 0.0 ? 1.0 : -1.0;
-    double xx_m035 = pow(xx, -0.35), xx_m12 = 1.0 / sqrt(xx);
-    {
-      double va = P.kappa_frac * n_e * e2 * nu_c / (phys::c * nu_2);
-      double lo = P.kappa_jj_low * va * (cbrt(xx) * sin_theta_b);
-      double hi = P.kappa_jj_high * va * (pow(xx, -(P.plasma_kappa - 2.0) / 2.0) * sin_theta_b);
-      C.j[0] += pow(pow(lo, -P.kappa_jj_x_i) + pow(hi, -P.kappa_jj_x_i), -1.0 / P.kappa_jj_x_i);
-      double vd = pow(pow(sin_theta_b, -2.4) - 1.0, 0.48);
-      double vf = pow(pow(sin_theta_b, -2.5) - 1.0, 0.44);
-      double q_lo = lo * P.kappa_jj_low_q, v_lo = lo * P.kappa_jj_low_v * vd * xx_m035;
-      double q_hi = hi * P.kappa_jj_high_q, v_hi = hi * P.kappa_jj_high_v * vf * xx_m12;
-      C.j[1] -= pow(pow(q_lo, -P.kappa_jj_x_q) + pow(q_hi, -P.kappa_jj_x_q), -1.0 / P.kappa_jj_x_q);
-      C.j[2] += pow(pow(v_lo, -P.kappa_jj_x_v) + pow(v_hi, -P.kappa_jj_x_v), -1.0 / P.kappa_jj_x_v) * sgn;
+  if (P.power_frac != 0.0 || P.kappa_frac != 0.0) {
+    double log_nu = q.log_om + P.log_freqs[l];
+    double lr = log_nu - q.log_ncs;  // ln(nu / (nu_c sin(theta_B)))
+    if (P.power_frac != 0.0) {
+      double e_half = exp(-0.5 * lr);  // (nu / (nu_c sin))^-1/2
+      double coefficient = P.power_frac * q.n_nuc * inv_nu_2 * P.power_jj * q.sin_b * exp(-(P.plasma_p - 1.0) / 2.0 * lr);
+      C.j[0] += coefficient;
+      C.j[1] += coefficient * P.power_jj_q;
+      C.j[2] += coefficient * P.power_jj_v * q.cot * (1.7320508075688772 * e_half);
+      double coefficient_a = P.power_frac * q.n_e * (e2 / (phys::m_e * phys::c)) * P.power_aa * exp(-(P.plasma_p + 2.0) / 2.0 * lr);
+      C.a[0] += coefficient_a;
+      C.a[1] += coefficient_a * P.power_aa_q;
+      C.a[2] += coefficient_a * P.power_aa_v * q.power_vb * e_half * q.sgn;
+      double rb = e_half * e_half;  // nu_c sin / nu
+      double ra = q.n_e * (e2 / (phys::m_e * phys::c)) / rb;
+      double rc = rb * rb, rd = rc * rb;
+      double re = 1.0 - exp((P.plasma_p / 2.0 - 1.0) * (P.log_power_gmin - lr));
+      double coefficient_r = P.power_frac * P.power_rho * ra;
+      C.rho[0] += coefficient_r * P.power_rho_q * rd * re;
+      C.rho[1] += coefficient_r * P.power_rho_v * rc * q.cot;
     }
-    {
-      double va = P.kappa_frac * n_e * e2 / (phys::m_e * phys::c);
-      double lo = P.kappa_aa_low * va * pow(xx, -2.0 / 3.0);
-      double hi = P.kappa_aa_high * va * pow(xx, -(1.0 + P.plasma_kappa) / 2.0);
-      double i_hi = hi * P.kappa_aa_high_i;
-      C.a[0] += pow(pow(lo, -P.kappa_aa_x_i) + pow(i_hi, -P.kappa_aa_x_i), -1.0 / P.kappa_aa_x_i);
-      double vd = pow(pow(sin_theta_b, -2.28) - 1.0, 0.446);
-      double vf = sqrt(pow(sin_theta_b, -2.05) - 1.0);
-      double q_lo = lo * P.kappa_aa_low_q, v_lo = lo * P.kappa_aa_low_v * vd * xx_m035;
-      double q_hi = hi * P.kappa_aa_high_q, v_hi = hi * P.kappa_aa_high_v * vf * xx_m12;
-      C.a[1] -= pow(pow(q_lo, -P.kappa_aa_x_q) + pow(q_hi, -P.kappa_aa_x_q), -1.0 / P.kappa_aa_x_q);
-      C.a[2] += pow(pow(v_lo, -P.kappa_aa_x_v) + pow(v_hi, -P.kappa_aa_x_v), -1.0 / P.kappa_aa_x_v) * sgn;
-    }
-    {
-      double va = -P.kappa_frac * n_e * e2 * nu_c * nu_c * sin2 / (phys::m_e * phys::c * nu_2);
-      double vb = P.kappa_frac * 2.0 * n_e * e2 * nu_c * cos_theta_b / (phys::m_e * phys::c * nu_cgs);
-      double x084 = pow(xx, 0.84);
-      double q_lo = va * P.kappa_rho_q_low_a * (1.0 - exp(P.kappa_rho_q_low_b * x084) -
-                    sin(P.kappa_rho_q_low_c * xx) * exp(P.kappa_rho_q_low_d * pow(xx, P.kappa_rho_q_low_e)));
-      double q_hi = va * P.kappa_rho_q_high_a * (1.0 - exp(P.kappa_rho_q_high_b * x084) -
-                    sin(P.kappa_rho_q_high_c * xx) * exp(P.kappa_rho_q_high_d * pow(xx, P.kappa_rho_q_high_e)));
-      double v_lo = P.kappa_rho_v * vb * P.kappa_rho_v_low_a * (1.0 - 0.17 * log(1.0 + P.kappa_rho_v_low_b * xx_m12));
-      double v_hi = P.kappa_rho_v * vb * P.kappa_rho_v_high_a * (1.0 - 0.17 * log(1.0 + P.kappa_rho_v_high_b * xx_m12));
-      C.rho[0] += (1.0 - P.kappa_rho_frac) * q_lo + P.kappa_rho_frac * q_hi;
-      C.rho[1] += (1.0 - P.kappa_rho_frac) * v_lo + P.kappa_rho_frac * v_hi;
+    if (P.kappa_frac != 0.0) {
+      double lx = lr - P.log_w2k2;   // ln(nu / nu_kappa)
+      double xx = nu_cgs * q.inv_nu_k;
+      double lm035 = -0.35 * lx, lm12 = -0.5 * lx;
+      {
+        const double ix_i = 1.0 / P.kappa_jj_x_i, ix_q = 1.0 / P.kappa_jj_x_q, ix_v = 1.0 / P.kappa_jj_x_v;
+        double lva = P.log_k_j_pref + q.log_ne + q.log_ncs - 2.0 * log_nu;  // includes the sin(theta_B) factor
+        double l_lo = P.log_kjl + lva + lx * (1.0 / 3.0);
+        double l_hi = P.log_kjh + lva - (P.plasma_kappa - 2.0) / 2.0 * lx;
+        C.j[0] += bridge(l_lo, l_hi, P.kappa_jj_x_i, ix_i);
+        C.j[1] -= bridge(l_lo + P.log_kj_low_q, l_hi + P.log_kj_high_q, P.kappa_jj_x_q, ix_q);
+        C.j[2] += bridge(l_lo + P.log_kj_low_v + q.lvd_j + lm035, l_hi + P.log_kj_high_v + q.lvf_j + lm12,
+                         P.kappa_jj_x_v, ix_v) * q.sgn;
+      }
+      {
+        const double ix_i = 1.0 / P.kappa_aa_x_i, ix_q = 1.0 / P.kappa_aa_x_q, ix_v = 1.0 / P.kappa_aa_x_v;
+        double lva = P.log_k_a_pref + q.log_ne;
+        double l_lo = P.log_kal + lva - 2.0 / 3.0 * lx;
+        double l_hi = P.log_kah_base + lva - (1.0 + P.plasma_kappa) / 2.0 * lx;
+        C.a[0] += bridge(l_lo, l_hi + (P.log_kah - P.log_kah_base), P.kappa_aa_x_i, ix_i);
+        C.a[1] -= bridge(l_lo + P.log_ka_low_q, l_hi + P.log_ka_high_q, P.kappa_aa_x_q, ix_q);
+        C.a[2] += bridge(l_lo + P.log_ka_low_v + q.lvd_a + lm035, l_hi + P.log_ka_high_v + q.lvf_a + lm12,
+                         P.kappa_aa_x_v, ix_v) * q.sgn;
+      }
+      {
+        double va = -P.kappa_frac * q.n_e * e2 * q.nu_c * q.nu_c * q.sin2 * inv_nu_2 * (1.0 / (phys::m_e * phys::c));
+        double vb = P.kappa_frac * 2.0 * q.n_e * e2 * q.nu_c * q.cos_b * inv_nu * (1.0 / (phys::m_e * phys::c));
+        double x084 = exp(0.84 * lx);
+        double xx_m12 = exp(lm12);
+        double q_lo = va * P.kappa_rho_q_low_a * (1.0 - exp(P.kappa_rho_q_low_b * x084) -
+                      sin(P.kappa_rho_q_low_c * xx) * exp(P.kappa_rho_q_low_d * exp(P.kappa_rho_q_low_e * lx)));
+        double q_hi = va * P.kappa_rho_q_high_a * (1.0 - exp(P.kappa_rho_q_high_b * x084) -
+                      sin(P.kappa_rho_q_high_c * xx) * exp(P.kappa_rho_q_high_d * exp(P.kappa_rho_q_high_e * lx)));
+        double v_lo = P.kappa_rho_v * vb * P.kappa_rho_v_low_a * (1.0 - 0.17 * log(1.0 + P.kappa_rho_v_low_b * xx_m12));
+        double v_hi = P.kappa_rho_v * vb * P.kappa_rho_v_high_a * (1.0 - 0.17 * log(1.0 + P.kappa_rho_v_high_b * xx_m12));
+        C.rho[0] += (1.0 - P.kappa_rho_frac) * q_lo + P.kappa_rho_frac * q_hi;
+        C.rho[1] += (1.0 - P.kappa_rho_frac) * v_lo + P.kappa_rho_frac * v_hi;
+      }
     }
   }
 }
@@ -600,6 +671,7 @@ radiate_polarized_kernel(const __grid_constant__ RadArgs A, const __grid_constan
   double prev_cv[RAD_NUM_CELL_VALUES];
   for (int q = 0; q < RAD_NUM_CELL_VALUES; q++) prev_cv[q] = nan("");
   rad::CellCache cache = {0, 0, 0, 0};
+  const double inv_mom_x = P.x_unit / mom;  // affine step -> cm per unit image frequency
   unsigned long long processed = 0;
 
   // frequency-independent state carried from the previous sample
@@ -683,17 +755,19 @@ radiate_polarized_kernel(const __grid_constant__ RadArgs A, const __grid_constan
 
     // pitch angle from invariants (see radiate_unpol.cu)
     double omega = -dot4(kc, ps.ucon);
-    double sin_theta_b = 0.0, cos_theta_b = 0.0, kk[3] = {0.0, 0.0, 0.0};
+    PolSample sq;
     if (coupled) {
+      double kk[3] = {0.0, 0.0, 0.0};
       double kb = dot4(kc, ps.bcon);
       double c2 = kb * kb / (omega * omega * ps.b_sq);
       c2 = 1.0 < c2 ? 1.0 : c2;
-      sin_theta_b = sqrt(1.0 - c2);
-      cos_theta_b = sqrt(c2) * (kb >= 0.0 ? 1.0 : -1.0);
+      double sin_theta_b = sqrt(1.0 - c2);
+      double cos_theta_b = sqrt(c2) * (kb >= 0.0 ? 1.0 : -1.0);
       if (P.thermal_frac != 0.0 && ps.theta_e >= 0.01) {
-        bessel_k01(1.0 / ps.theta_e, kk[0], kk[1]);
+        bessel_k01(ps.inv_theta_e, kk[0], kk[1]);
         kk[2] = kk[0] + 2.0 * ps.theta_e * kk[1];
       }
+      pol_sample(P, ps, omega * mom, sin_theta_b, cos_theta_b, kk, sq);
     }
 
     // ---- per-sample auxiliary quantities ----
@@ -718,11 +792,10 @@ radiate_polarized_kernel(const __grid_constant__ RadArgs A, const __grid_constan
     }
 
     // ---- frequencies: rotate Stokes into the new frame, couple to the plasma ----
-#pragma unroll
-    for (int l = 0; l < FMAX; l++) {
+BL_FREQ_LOOP
+    for (int l = 0; l < (FMAX > 4 ? F : FMAX); l++) {
       if (l >= F) break;
-      double freq = P.freqs[l];
-      double dl_cgs = dlam * P.x_unit / (freq * mom);
+      double dl_cgs = dlam * inv_mom_x * P.inv_freqs[l];
       double s[4] = {0.0, 0.0, 0.0, 0.0};
       if (have_prev) {
         s[0] = M.m[0][0] * S[l][0] + M.m[0][1] * S[l][1] + M.m[0][2] * S[l][2];
@@ -733,7 +806,7 @@ radiate_polarized_kernel(const __grid_constant__ RadArgs A, const __grid_constan
       Coefficients C;
       for (int q = 0; q < 3; q++) C.j[q] = C.a[q] = 0.0;
       C.rho[0] = C.rho[1] = 0.0;
-      if (coupled) synchrotron_polarized(P, ps, omega * freq * mom, sin_theta_b, cos_theta_b, kk, C);
+      if (coupled) synchrotron_polarized(P, sq, l, C);
       double delta_tau = C.a[0] * dl_cgs;
       if (aux) {
         bool thin = delta_tau <= 100.0;
@@ -799,8 +872,8 @@ radiate_polarized_kernel(const __grid_constant__ RadArgs A, const __grid_constan
       StokesMap M;
       stokes_map(L, 0.0, dlam_p / 2.0, false, M);
       if (P.image_light)
-#pragma unroll
-        for (int l = 0; l < FMAX; l++) {
+BL_FREQ_LOOP
+        for (int l = 0; l < (FMAX > 4 ? F : FMAX); l++) {
           if (l >= F) break;
           double f = P.freqs[l], nu_cu = f * f * f;
           img[(size_t)(4 * l + 0) * stride] = (M.m[0][0] * S[l][0] + M.m[0][1] * S[l][1] + M.m[0][2] * S[l][2]) * nu_cu;
@@ -809,8 +882,8 @@ radiate_polarized_kernel(const __grid_constant__ RadArgs A, const __grid_constan
           img[(size_t)(4 * l + 3) * stride] = M.vv * S[l][3] * nu_cu;
         }
       if (aux) {
-#pragma unroll
-        for (int l = 0; l < FMAX; l++) {
+BL_FREQ_LOOP
+        for (int l = 0; l < (FMAX > 4 ? F : FMAX); l++) {
           if (l >= F) break;
           if (P.image_lambda) img[(size_t)(P.off_lambda + l) * stride] = int_lambda[l];
           if (P.image_emission) img[(size_t)(P.off_emission + l) * stride] = int_emission[l];
@@ -842,7 +915,7 @@ cudaError_t launch_fmax(const RadArgs &A, const RadParams &P, cudaStream_t strea
 
 }  // namespace
 
-// One translation unit per frequency-count bucket (BL_FMAX = 1, 4, 12, 32; see the Makefile).
+// One translation unit per frequency-count bucket (BL_FMAX = 1, 4, 32; see the Makefile).
 #ifndef BL_FMAX
 #define BL_FMAX 1
 #endif

@@ -15,6 +15,15 @@ namespace {
 
 constexpr int kBlock = 128;
 
+// Frequency loops: fully unrolled with the per-frequency state in registers for the small buckets
+// (FMAX <= 4); a rolled loop over state in thread-local memory for the large one (the per-frequency
+// work is ~1e3 instructions, so the loop overhead is nothing and the code stays small).
+#if defined(BL_FMAX) && BL_FMAX > 4
+#define BL_FREQ_LOOP _Pragma("unroll 1")
+#else
+#define BL_FREQ_LOOP _Pragma("unroll")
+#endif
+
 // Frequency-independent part of the Stokes-I synchrotron coefficients of one sample
 // (simulation_coefficients.cpp:458-524 thermal, :559-585 power law, :608-664 kappa; invariant forms
 // j/nu^2, alpha*nu).  The reference evaluates every power with std::pow per frequency; here the logarithms
@@ -314,8 +323,8 @@ radiate_unpolarized_kernel(const __grid_constant__ RadArgs A, const __grid_const
     }
 
     // frequencies
-#pragma unroll
-    for (int l = 0; l < FMAX; l++) {
+BL_FREQ_LOOP
+    for (int l = 0; l < (FMAX > 4 ? F : FMAX); l++) {
       if (l >= F) break;
       double dlam_cgs = dlam * inv_mom_x * P.inv_freqs[l];
       double j = 0.0, alpha = 0.0;
@@ -381,15 +390,15 @@ radiate_unpolarized_kernel(const __grid_constant__ RadArgs A, const __grid_const
 
   if (valid) {
     if (P.image_light)
-#pragma unroll
-      for (int l = 0; l < FMAX; l++) {
+BL_FREQ_LOOP
+      for (int l = 0; l < (FMAX > 4 ? F : FMAX); l++) {
         if (l >= F) break;
         double f = P.freqs[l];
         img[(size_t)l * stride] = I[l] * (f * f * f);
       }
     if (aux) {
-#pragma unroll
-      for (int l = 0; l < FMAX; l++) {
+BL_FREQ_LOOP
+      for (int l = 0; l < (FMAX > 4 ? F : FMAX); l++) {
         if (l >= F) break;
         if (P.image_lambda) img[(size_t)(P.off_lambda + l) * stride] = int_lambda[l];
         if (P.image_emission) img[(size_t)(P.off_emission + l) * stride] = int_emission[l];
@@ -432,7 +441,7 @@ cudaError_t launch_fmax(const RadArgs &A, const RadParams &P, cudaStream_t strea
 
 }  // namespace
 
-// One translation unit per frequency-count bucket (BL_FMAX = 1, 4, 12, 32; see the Makefile) so that the
+// One translation unit per frequency-count bucket (BL_FMAX = 1, 4, 32; see the Makefile) so that the
 // buckets compile in parallel.
 #ifndef BL_FMAX
 #define BL_FMAX 1
