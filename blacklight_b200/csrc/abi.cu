@@ -17,8 +17,7 @@ extern "C" cudaError_t bl_launch_geodesic_rk(const GeoArgs *args, int flat, int 
 #define BL_DECL_RAD(name) extern "C" cudaError_t name(const RadArgs *args, const RadParams *params, cudaStream_t stream)
 BL_DECL_RAD(bl_launch_radiate_unpolarized_f1); BL_DECL_RAD(bl_launch_radiate_unpolarized_f4);
 BL_DECL_RAD(bl_launch_radiate_unpolarized_f32);
-BL_DECL_RAD(bl_launch_radiate_polarized_f1); BL_DECL_RAD(bl_launch_radiate_polarized_f4);
-BL_DECL_RAD(bl_launch_radiate_polarized_f32);
+BL_DECL_RAD(bl_launch_radiate_polarized);
 extern "C" cudaError_t bl_launch_relayout_grid(const float *prim, int n_var, const int *var_index, size_t cells,
                                                float4 *out, float *kappa_out, cudaStream_t stream);
 extern "C" cudaError_t bl_launch_unpack_samples(const StepBuffer *sb, const int32_t *num, int64_t rays, int S,
@@ -609,13 +608,11 @@ int radiate_wave(bl_ctx *ctx, Level &L, int64_t first, int64_t count) {
     A.taps.fracs = L.tap_fracs ? L.tap_fracs + 3 * o : nullptr;
   }
   // parameters travel by value in the kernel's constant bank (no device copy, no per-sample loads)
-  // the kernels are instantiated for frequency-count buckets of 1, 4 and 32 (one object file each)
+  // the unpolarized kernel is instantiated for frequency-count buckets of 1, 4 and 32 (one object file each)
   const int F = ctx->rad.num_freq;
   cudaError_t le;
   if (ctx->rad.polarization)
-    le = F <= 1 ? bl_launch_radiate_polarized_f1(&A, &ctx->rad, ctx->stream)
-       : F <= 4 ? bl_launch_radiate_polarized_f4(&A, &ctx->rad, ctx->stream)
-                 : bl_launch_radiate_polarized_f32(&A, &ctx->rad, ctx->stream);
+    le = bl_launch_radiate_polarized(&A, &ctx->rad, ctx->stream);
   else
     le = F <= 1 ? bl_launch_radiate_unpolarized_f1(&A, &ctx->rad, ctx->stream)
        : F <= 4 ? bl_launch_radiate_unpolarized_f4(&A, &ctx->rad, ctx->stream)

@@ -16,14 +16,10 @@ namespace {
 
 constexpr int kBlock = 128;
 
-// Frequency loops: fully unrolled with the per-frequency state in registers for the small buckets
-// (FMAX <= 4); a rolled loop over state in thread-local memory for the large one (the per-frequency
-// work is ~1e3 instructions, so the loop overhead is nothing and the code stays small).
-#if defined(BL_FMAX) && BL_FMAX > 4
+// Frequency loop: rolled, with the per-frequency Stokes state in thread-local memory.  The per-frequency
+// work is ~1.5e3 instructions (coefficients + 4x4 coupling), so loop and local-memory overhead are nothing,
+// while an unrolled body overflows the instruction cache (ncu: no_instruction was the top stall).
 #define BL_FREQ_LOOP _Pragma("unroll 1")
-#else
-#define BL_FREQ_LOOP _Pragma("unroll")
-#endif
 
 // ---------------------------------------------------------------------------------------------------
 // Kerr-Schild geometry: g_{mu nu} = eta + f l_mu l_nu, l_mu = (1, l_i), l^mu = (-1, l_i), M = 1.
@@ -793,7 +789,7 @@ radiate_polarized_kernel(const __grid_constant__ RadArgs A, const __grid_constan
 
     // ---- frequencies: rotate Stokes into the new frame, couple to the plasma ----
 BL_FREQ_LOOP
-    for (int l = 0; l < (FMAX > 4 ? F : FMAX); l++) {
+    for (int l = 0; l < F; l++) {
       if (l >= F) break;
       double dl_cgs = dlam * inv_mom_x * P.inv_freqs[l];
       double s[4] = {0.0, 0.0, 0.0, 0.0};
@@ -873,7 +869,7 @@ BL_FREQ_LOOP
       stokes_map(L, 0.0, dlam_p / 2.0, false, M);
       if (P.image_light)
 BL_FREQ_LOOP
-        for (int l = 0; l < (FMAX > 4 ? F : FMAX); l++) {
+        for (int l = 0; l < F; l++) {
           if (l >= F) break;
           double f = P.freqs[l], nu_cu = f * f * f;
           img[(size_t)(4 * l + 0) * stride] = (M.m[0][0] * S[l][0] + M.m[0][1] * S[l][1] + M.m[0][2] * S[l][2]) * nu_cu;
@@ -883,7 +879,7 @@ BL_FREQ_LOOP
         }
       if (aux) {
 BL_FREQ_LOOP
-        for (int l = 0; l < (FMAX > 4 ? F : FMAX); l++) {
+        for (int l = 0; l < F; l++) {
           if (l >= F) break;
           if (P.image_lambda) img[(size_t)(P.off_lambda + l) * stride] = int_lambda[l];
           if (P.image_emission) img[(size_t)(P.off_emission + l) * stride] = int_emission[l];
@@ -915,14 +911,7 @@ cudaError_t launch_fmax(const RadArgs &A, const RadParams &P, cudaStream_t strea
 
 }  // namespace
 
-// One translation unit per frequency-count bucket (BL_FMAX = 1, 4, 32; see the Makefile).
-#ifndef BL_FMAX
-#define BL_FMAX 1
-#endif
-#define BL_CAT2(a, b) a##b
-#define BL_CAT(a, b) BL_CAT2(a, b)
-extern "C" cudaError_t BL_CAT(bl_launch_radiate_polarized_f, BL_FMAX)(const RadArgs *args, const RadParams *params,
-                                                                      cudaStream_t stream) {
+extern "C" cudaError_t bl_launch_radiate_polarized(const RadArgs *args, const RadParams *params, cudaStream_t stream) {
   if (args->rays <= 0) return cudaSuccess;
-  return launch_fmax<BL_FMAX>(*args, *params, stream);
+  return launch_fmax<RAD_MAX_FREQ>(*args, *params, stream);
 }
