@@ -312,7 +312,7 @@ def main():
                 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
                 'config': {'workload': workload_name(args, res_total, n_gpus), 'rays_per_gpu': n_rays, 'frequencies': F,
                            'l2': 'inputs larger than L2: %.1f GB step buffer written and re-read per step' %
-                                 (st['num_samples'] * 72 / 1e9),
+                                 (st['num_samples'] * 64 / 1e9),
                            'sharding': 'image rows round-robin over ranks; grid replicated; final image gather'},
                 'e2e': {'value': e2e, 'unit': 'rays/s', 'ms_per_step': 1e3 * t_e2e / K,
                         'h2d_bytes_per_step': int(total_rays * 72), 'd2h_bytes_per_step': int(total_rays * 8 * Q)},

@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libblacklight_b200.so')
+# BLACKLIGHT_B200_LIB points at an alternative build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get('BLACKLIGHT_B200_LIB') or os.path.join(_HERE, 'libblacklight_b200.so')
 EXE_PATH = os.path.join(_HERE, 'bin', 'blacklight_b200')
 
 

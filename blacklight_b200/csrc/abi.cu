@@ -20,8 +20,9 @@ BL_DECL_RAD(bl_launch_radiate_unpolarized_f32);
 BL_DECL_RAD(bl_launch_radiate_polarized);
 extern "C" cudaError_t bl_launch_relayout_grid(const float *prim, int n_var, const int *var_index, size_t cells,
                                                float4 *out, float *kappa_out, cudaStream_t stream);
-extern "C" cudaError_t bl_launch_unpack_samples(const StepBuffer *sb, const int32_t *num, int64_t rays, int S,
-                                                double *pos, double *dir, double *len, cudaStream_t stream);
+extern "C" cudaError_t bl_launch_unpack_samples(const StepBuffer *sb, const int32_t *num, const double *cam_dir,
+                                                int64_t rays, int S, double *pos, double *dir, double *len,
+                                                cudaStream_t stream);
 extern "C" cudaError_t bl_launch_refine(const double *image, int64_t stride, int level, const int32_t *block_locs,
                                         int64_t num_blocks, const bl_params *params_dev, uint8_t *flags,
                                         cudaStream_t stream);
@@ -660,10 +661,10 @@ int bl_trace_level(bl_ctx *ctx, int level, const double *cam_pos, const double *
   BL_CUDA_CHECK(cudaMemcpyAsync(L.mom, mom_factor, (size_t)num_rays * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
 
   if (!reuse) {
-    // wave size from the HBM budget: 72 bytes per sample slot, ray_max_steps slots per ray
+    // wave size from the HBM budget: 64 bytes per sample slot, ray_max_steps slots per ray
     size_t fr = 0, tot = 0;
     BL_CUDA_CHECK(cudaMemGetInfo(&fr, &tot));
-    size_t per_ray = (size_t)ctx->params.ray_max_steps * 9 * sizeof(double);
+    size_t per_ray = (size_t)ctx->params.ray_max_steps * StepBuffer::kRecord * sizeof(double);
     size_t budget = (size_t)((double)fr * 0.80);
     int64_t fit = (int64_t)(budget / per_ray);
     if (ctx->params.tile_rays > 0 && ctx->params.tile_rays < fit) fit = ctx->params.tile_rays;
@@ -853,7 +854,7 @@ int bl_download_samples(bl_ctx *ctx, int level, uint8_t *flags, int32_t *num, do
     if (dir) BL_CUDA_CHECK(dev_alloc(&ddir, ns * 4));
     if (len) BL_CUDA_CHECK(dev_alloc(&dlen, ns));
     StepBuffer sb; sb.buf = L.step; sb.rays = L.rays; sb.cap = ctx->params.ray_max_steps;
-    cudaError_t e = bl_launch_unpack_samples(&sb, L.num, L.rays, S, dpos, ddir, dlen, ctx->stream);
+    cudaError_t e = bl_launch_unpack_samples(&sb, L.num, L.cam_dir, L.rays, S, dpos, ddir, dlen, ctx->stream);
     if (e == cudaSuccess && pos) e = cudaMemcpyAsync(pos, dpos, ns * 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess && dir) e = cudaMemcpyAsync(dir, ddir, ns * 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess && len) e = cudaMemcpyAsync(len, dlen, ns * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);

@@ -3,19 +3,21 @@
 #include <stdint.h>
 #include <cuda_runtime.h>
 
-// Step buffer of one wave ("tile") of rays, structure-of-arrays with the ray index fastest:
-//   comp c of sample n of ray m lives at buf[(c * cap + n) * rays + m],  c in [0,9):
-//   0..3 = x^mu (t,x,y,z), 4..7 = covariant momentum p_mu, 8 = affine step length (negative while
-//   tracing backwards; consumers use -len, see reference geodesics.cpp:840).
+// Step buffer of one wave ("tile") of rays: one 64-byte record per stored sample,
+//   rec[n * rays + m] = (t, x, y, z | p_x, p_y, p_z, len)      n = sample index in tracing order, m = ray
+// i.e. two full 32-byte sectors per sample.  The geodesic kernel (lanes at unrelated n) writes a record
+// with four 16-byte stores that fill both sectors completely; the radiation kernels (a warp walks 32
+// adjacent rays in lock step) read 2 KB contiguous rows.  p_t is not stored: it is conserved along the ray
+// (dp_t/dlambda = 0 exactly, geodesics.cpp:867-893) and equals the camera array's cam_dir[m][0].
+// len is the affine step (negative while tracing backwards; consumers use -len, geodesics.cpp:840).
 // Samples are stored in tracing order (n = 0 at the camera); the radiation kernels walk n downwards,
 // which is the reference's source->camera order (geodesics.cpp:808-849) without the reversal copy.
 struct StepBuffer {
   double *buf;
-  int64_t rays;  // rays in this wave (stride between consecutive samples)
+  int64_t rays;  // rays in this wave
   int32_t cap;   // sample capacity per ray (= ray_max_steps)
-  __host__ __device__ size_t at(int c, int n, int64_t m) const {
-    return ((size_t)c * cap + n) * (size_t)rays + m;
-  }
+  static constexpr int kRecord = 8;  // doubles per sample
+  __host__ __device__ size_t at(int n, int64_t m) const { return ((size_t)n * (size_t)rays + (size_t)m) * kRecord; }
 };
 
 struct GeoCounters {

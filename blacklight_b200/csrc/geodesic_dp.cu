@@ -1,7 +1,7 @@
 // Backward null-geodesic integration, Dormand-Prince RK5(4)7M with dense output -- one FP64
 // sm_100a kernel: one ray per thread, persistent warps that refill finished lanes from a global
 // ray queue (warp ballot + one aggregated atomic), stage derivatives in shared memory, step buffer
-// written structure-of-arrays.  Truncation (reference geodesics.cpp:327-349), momentum
+// written as 64-byte records (device_types.cuh).  Truncation (reference geodesics.cpp:327-349), momentum
 // renormalisation of stored samples (:352-371), the max/bad-ray reductions (:374-382) are fused
 // into the same kernel; the reversal copy (:808-849) is eliminated (consumers walk backwards).
 //
@@ -83,18 +83,12 @@ __device__ __forceinline__ void store_sample(const GeoArgs &g, Ray &ray, int idx
   ray.r_prev_sample = rs;
   double p[4] = {v[4], v[5], v[6], v[7]};
   ksx::renormalize_momentum<flat>(g.a, v[1], v[2], v[3], p);
-  const StepBuffer &sb = g.sb;
-  double *dst = sb.buf + sb.at(0, idx, ray.m);
-  size_t cs = (size_t)sb.cap * (size_t)sb.rays;
-  dst[0 * cs] = v[0];
-  dst[1 * cs] = v[1];
-  dst[2 * cs] = v[2];
-  dst[3 * cs] = v[3];
-  dst[4 * cs] = p[0];
-  dst[5 * cs] = p[1];
-  dst[6 * cs] = p[2];
-  dst[7 * cs] = p[3];
-  dst[8 * cs] = len;
+  // one 64-byte record = two full sectors, written with four 16-byte streaming stores
+  double2 *dst = reinterpret_cast<double2 *>(g.sb.buf + g.sb.at(idx, ray.m));
+  __stcs(dst + 0, make_double2(v[0], v[1]));
+  __stcs(dst + 1, make_double2(v[2], v[3]));
+  __stcs(dst + 2, make_double2(p[1], p[2]));
+  __stcs(dst + 3, make_double2(p[3], len));
 }
 
 template <bool flat, int MINB>

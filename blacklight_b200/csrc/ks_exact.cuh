@@ -45,7 +45,7 @@ BL_HD KsPoint ks_point(double a, double x, double y, double z) {
 // Solve the null condition g^{mu nu} p_mu p_nu = 0 for a rescaling of the spatial momentum
 // (geodesics.cpp:296-309 and :352-371).  p = (p_0, p_1, p_2, p_3) covariant; p[1..3] are scaled.
 template <bool flat>
-BL_HD void renormalize_momentum(double a, double x, double y, double z, double p[4]) {
+BL_HD_SAMPLE void renormalize_momentum(double a, double x, double y, double z, double p[4]) {
   double g00, g0[3], gs[3][3];
   if (flat) {
     g00 = -1.0;

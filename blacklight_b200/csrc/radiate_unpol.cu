@@ -208,24 +208,24 @@ radiate_unpolarized_kernel(const __grid_constant__ RadArgs A, const __grid_const
   int crossings = 0;
   if (valid && num > 0 && P.image_crossings) {
     // reference looks at sample 0 of the reversed array == our last stored sample
-    const double *p0 = A.sb.buf + A.sb.at(1, num - 1, m);
-    size_t cs = (size_t)A.sb.cap * (size_t)A.sb.rays;
-    plane_sign = P.camera_x[1] * p0[0] + P.camera_x[2] * p0[cs] + P.camera_x[3] * p0[2 * cs] > 0.0;
+    const double *p0 = A.sb.buf + A.sb.at(num - 1, m);
+    plane_sign = P.camera_x[1] * p0[1] + P.camera_x[2] * p0[2] + P.camera_x[3] * p0[3] > 0.0;
   }
   double prev_cv[RAD_NUM_CELL_VALUES];
   for (int q = 0; q < RAD_NUM_CELL_VALUES; q++) prev_cv[q] = nan("");
   rad::CellCache cache = {0, 0, 0, 0};
   const double inv_mom_x = P.x_unit / mom;  // affine step -> cm per unit image frequency
   unsigned long long processed = 0;
-  const size_t cs = (size_t)A.sb.cap * (size_t)A.sb.rays;
+  const double k_t = valid ? A.cam_dir[4 * m] : 0.0;  // conserved covariant time component of the momentum
 
   for (int n = warp_max - 1; n >= 0; n--) {
     if (n >= num) continue;
     processed++;
-    const double *src = A.sb.buf + A.sb.at(0, n, m);
-    double t = src[0], x = src[cs], y = src[2 * cs], z = src[3 * cs];
-    double kc[4] = {src[4 * cs], src[5 * cs], src[6 * cs], src[7 * cs]};
-    double dlam = -src[8 * cs];
+    const double2 *src = reinterpret_cast<const double2 *>(A.sb.buf + A.sb.at(n, m));
+    double2 r0 = __ldcs(src), r1 = __ldcs(src + 1), r2 = __ldcs(src + 2), r3 = __ldcs(src + 3);
+    double t = r0.x, x = r0.y, y = r1.x, z = r1.y;
+    double kc[4] = {k_t, r2.x, r2.y, r3.x};
+    double dlam = -r3.y;
     int n_ref = num - 1 - n;  // index in the reference's reversed arrays (taps only)
 
     double inv_r;

@@ -18,10 +18,11 @@ __global__ void relayout_grid_kernel(const float *__restrict__ prim, const int *
   if (kappa_out) kappa_out[c] = prim[(size_t)var_index[8] * cells + c];
 }
 
-// Step buffer (SoA, tracing order) -> the reference's sample_pos/dir/len host layout
+// Step buffer (64-byte records, tracing order) -> the reference's sample_pos/dir/len host layout
 // (N,S,4)/(N,S) in source->camera order with len > 0 (geodesics.cpp:808-849); tail zero-filled.
-__global__ void unpack_samples_kernel(StepBuffer sb, const int32_t *__restrict__ num, int64_t rays, int S,
-                                      double *__restrict__ pos, double *__restrict__ dir, double *__restrict__ len) {
+__global__ void unpack_samples_kernel(StepBuffer sb, const int32_t *__restrict__ num, const double *__restrict__ cam_dir,
+                                      int64_t rays, int S, double *__restrict__ pos, double *__restrict__ dir,
+                                      double *__restrict__ len) {
   int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int n_out = blockIdx.y;
   if (m >= rays) return;
@@ -29,11 +30,13 @@ __global__ void unpack_samples_kernel(StepBuffer sb, const int32_t *__restrict__
   size_t o = (size_t)m * S + n_out;
   if (n_out < cnt) {
     int n = cnt - 1 - n_out;
-    size_t cs = (size_t)sb.cap * (size_t)sb.rays;
-    const double *src = sb.buf + sb.at(0, n, m);
-    if (pos) for (int c = 0; c < 4; c++) pos[4 * o + c] = src[c * cs];
-    if (dir) for (int c = 0; c < 4; c++) dir[4 * o + c] = src[(4 + c) * cs];
-    if (len) len[o] = -src[8 * cs];
+    const double *src = sb.buf + sb.at(n, m);
+    if (pos) for (int c = 0; c < 4; c++) pos[4 * o + c] = src[c];
+    if (dir) {
+      dir[4 * o] = cam_dir[4 * m];  // p_t is conserved and not stored per sample
+      for (int c = 1; c < 4; c++) dir[4 * o + c] = src[3 + c];
+    }
+    if (len) len[o] = -src[7];
   } else {
     if (pos) for (int c = 0; c < 4; c++) pos[4 * o + c] = 0.0;
     if (dir) for (int c = 0; c < 4; c++) dir[4 * o + c] = 0.0;
@@ -161,11 +164,12 @@ extern "C" cudaError_t bl_launch_relayout_grid(const float *prim, int n_var, con
   return cudaGetLastError();
 }
 
-extern "C" cudaError_t bl_launch_unpack_samples(const StepBuffer *sb, const int32_t *num, int64_t rays, int S,
-                                                double *pos, double *dir, double *len, cudaStream_t stream) {
+extern "C" cudaError_t bl_launch_unpack_samples(const StepBuffer *sb, const int32_t *num, const double *cam_dir,
+                                                int64_t rays, int S, double *pos, double *dir, double *len,
+                                                cudaStream_t stream) {
   if (rays <= 0 || S <= 0) return cudaSuccess;
   dim3 grid((unsigned)((rays + 127) / 128), (unsigned)S);
-  unpack_samples_kernel<<<grid, 128, 0, stream>>>(*sb, num, rays, S, pos, dir, len);
+  unpack_samples_kernel<<<grid, 128, 0, stream>>>(*sb, num, cam_dir, rays, S, pos, dir, len);
   return cudaGetLastError();
 }
 
