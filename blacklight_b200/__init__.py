@@ -70,6 +70,7 @@ def load_library():
         'bl_download_sample_inds': (i32, [vp, i32, vp, vp, vp, vp, vp]),
         'bl_device_info': (i32, [vp, ctypes.c_char_p, i32, ctypes.POINTER(i32), ctypes.POINTER(dbl)]),
         'bl_measure_fp64_peak': (i32, [vp, ctypes.POINTER(dbl)]),
+        'bl_selftest_division': (i32, [vp, ctypes.c_uint64, i64, ctypes.POINTER(i64)]),
         'blh_last_error': (ctypes.c_char_p, []), 'blh_config_from_input': (i32, [ctypes.c_char_p, ctypes.POINTER(vp)]),
         'blh_config_free': (None, [vp]), 'blh_config_params': (vp, [vp]), 'blh_config_num_runs': (i32, [vp]),
         'blh_config_set_device': (None, [vp, i32, i64]), 'blh_camera_frame': (i32, [vp, vp]),
@@ -202,6 +203,12 @@ class Context:
     def measure_fp64_peak(self):
         out = ctypes.c_double()
         self._check(_lib.bl_measure_fp64_peak(self._h, ctypes.byref(out)))
+        return out.value
+
+    def selftest_division(self, num_pairs, seed=1):
+        """Mismatches between the shared-reciprocal division and the hardware IEEE division (must be 0)."""
+        out = ctypes.c_int64()
+        self._check(_lib.bl_selftest_division(self._h, seed, num_pairs, ctypes.byref(out)))
         return out.value
 
     def upload_grid(self, g):

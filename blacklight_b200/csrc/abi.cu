@@ -27,6 +27,8 @@ extern "C" cudaError_t bl_launch_refine(const double *image, int64_t stride, int
                                         int64_t num_blocks, const bl_params *params_dev, uint8_t *flags,
                                         cudaStream_t stream);
 extern "C" cudaError_t bl_launch_fp64_peak(double *out, int blocks, int iters, cudaStream_t stream);
+extern "C" cudaError_t bl_launch_division_selftest(unsigned long long seed, int blocks, int iters,
+                                                   unsigned long long *mismatches, cudaStream_t stream);
 
 namespace {
 
@@ -66,7 +68,7 @@ struct bl_ctx {
   std::string error;
   bool taps_enabled = false;
   long long launches = 0;   // kernels of ours launched so far
-  int geo_min_blocks = 2;   // occupancy variant of the DP kernel (BL_GEO_BLOCKS overrides, tuning only)
+  int geo_min_blocks = 3;   // occupancy variant of the DP kernel (BL_GEO_BLOCKS overrides, tuning only)
 };
 
 namespace {
@@ -448,6 +450,25 @@ int bl_measure_fp64_peak(bl_ctx *ctx, double *tflops) {
   }
   cudaFree(sink);
   *tflops = best;
+  return BL_OK;
+}
+
+int bl_selftest_division(bl_ctx *ctx, uint64_t seed, int64_t num_pairs, int64_t *mismatches) {
+  if (!ctx || !mismatches || num_pairs <= 0) return BL_ERR_ARG;
+  BL_CUDA_CHECK(cudaSetDevice(ctx->device));
+  unsigned long long *dev = nullptr;
+  BL_CUDA_CHECK(dev_alloc(&dev, 1));
+  const int blocks = ctx->sm_count * 8, threads = 256;
+  int iters = (int)((num_pairs + (int64_t)blocks * threads - 1) / ((int64_t)blocks * threads));
+  cudaError_t e = cudaMemsetAsync(dev, 0, sizeof *dev, ctx->stream);
+  if (e == cudaSuccess) e = bl_launch_division_selftest(seed, blocks, iters, dev, ctx->stream);
+  unsigned long long host = 0;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&host, dev, sizeof host, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(dev);
+  if (e != cudaSuccess) return bl_fail_cuda(ctx, e, "division self-test", __FILE__, __LINE__);
+  *mismatches = (int64_t)host;
+  ctx->launches++;
   return BL_OK;
 }
 

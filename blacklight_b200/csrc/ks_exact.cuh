@@ -36,8 +36,9 @@ BL_HD KsPoint ks_point(double a, double x, double y, double z) {
   q.r2 = 0.5 * (rr2 - a2 + blmath::hypot_glibc(rr2 - a2, 2.0 * a * z));
   q.r = sqrt(q.r2);
   q.f = 2.0 * q.r2 * q.r / (q.r2 * q.r2 + a2 * z * z);
-  q.l1 = (q.r * x + a * y) / (q.r2 + a2);
-  q.l2 = (q.r * y - a * x) / (q.r2 + a2);
+  blmath::Recip ra = blmath::recip_of(q.r2 + a2);
+  q.l1 = blmath::div_by(q.r * x + a * y, ra);
+  q.l2 = blmath::div_by(q.r * y - a * x, ra);
   q.l3 = z / q.r;
   return q;
 }
@@ -97,8 +98,10 @@ BL_HD void rhs(double a, double x, double y, double z, const double p[4], double
   double r4 = r2 * r2;
   double a2zz = a2 * z * z;
   double f = 2.0 * r2 * r / (r4 + a2zz);
-  double ra = r2 + a2;
-  double l[3] = {(r * x + a * y) / ra, (r * y - a * x) / ra, z / r};
+  // shared denominators: quotients below are the correctly rounded a / b (blmath::div_by)
+  using blmath::div_by;
+  const blmath::Recip ra = blmath::recip_of(r2 + a2), rr = blmath::recip_of(r);
+  double l[3] = {div_by(r * x + a * y, ra), div_by(r * y - a * x, ra), div_by(z, rr)};
   double fl[3] = {f * l[0], f * l[1], f * l[2]};
   double P[3][3];
   for (int i = 0; i < 3; i++)
@@ -106,6 +109,7 @@ BL_HD void rhs(double a, double x, double y, double z, const double p[4], double
 
   // dx^mu/dlambda = sum_nu g^{mu nu} p_nu (nu ascending)
   double gcon00 = -f - 1.0;
+  const blmath::Recip g00 = blmath::recip_of(gcon00);
   dx[0] = gcon00 * p[0] + fl[0] * p[1] + fl[1] * p[2] + fl[2] * p[3];
   for (int i = 0; i < 3; i++) {
     double acc = fl[i] * p[0];
@@ -117,27 +121,27 @@ BL_HD void rhs(double a, double x, double y, double z, const double p[4], double
   }
 
   // scalar and vector derivatives (geodesic_geometry.cpp:203-224)
-  double den = 2.0 * r2 - rr2 + a2;
-  double dr[3] = {r * x / den, r * y / den, (r * z + a2 * z / r) / den};
+  const blmath::Recip den = blmath::recip_of(2.0 * r2 - rr2 + a2);
+  double dr[3] = {div_by(r * x, den), div_by(r * y, den), div_by(r * z + div_by(a2 * z, rr), den)};
   double qn = r4 - 3.0 * a2 * z * z;
-  double w = r * (r4 + a2zz);
+  const blmath::Recip w = blmath::recip_of(r * (r4 + a2zz));
   double df[3];
-  df[0] = -qn * dr[0] / w * f;
-  df[1] = -qn * dr[1] / w * f;
-  df[2] = -(qn * dr[2] + 2.0 * a2 * r * z) / w * f;
+  df[0] = div_by(-qn * dr[0], w) * f;
+  df[1] = div_by(-qn * dr[1], w) * f;
+  df[2] = div_by(-(qn * dr[2] + 2.0 * a2 * r * z), w) * f;
   double c1 = x - 2.0 * r * l[0];
   double c2 = y - 2.0 * r * l[1];
   double mz = -z / r2;
   double dl[3][3];  // dl[a][m] = d l_m / d x^a
-  dl[0][0] = (c1 * dr[0] + r) / ra;
-  dl[1][0] = (c1 * dr[1] + a) / ra;
-  dl[2][0] = c1 * dr[2] / ra;
-  dl[0][1] = (c2 * dr[0] - a) / ra;
-  dl[1][1] = (c2 * dr[1] + r) / ra;
-  dl[2][1] = c2 * dr[2] / ra;
+  dl[0][0] = div_by(c1 * dr[0] + r, ra);
+  dl[1][0] = div_by(c1 * dr[1] + a, ra);
+  dl[2][0] = div_by(c1 * dr[2], ra);
+  dl[0][1] = div_by(c2 * dr[0] - a, ra);
+  dl[1][1] = div_by(c2 * dr[1] + r, ra);
+  dl[2][1] = div_by(c2 * dr[2], ra);
   dl[0][2] = mz * dr[0];
   dl[1][2] = mz * dr[1];
-  dl[2][2] = mz * dr[2] + 1.0 / r;
+  dl[2][2] = mz * dr[2] + rr.y;  // RN(1/r)
 
   // dp_a/dlambda = -sum_{mu,nu} (1/2 d_a g^{mu nu}) p_mu p_nu, (mu,nu) row-major, summed one by one
   double hp[4] = {0.5 * p[0], 0.5 * p[1], 0.5 * p[2], 0.5 * p[3]};
@@ -163,10 +167,10 @@ BL_HD void rhs(double a, double x, double y, double z, const double p[4], double
   // proper-distance rate: t_a = sum_mu (g^{a mu} - g^{0a} g^{0 mu} / g^{00}) p_mu
   double t[3];
   for (int i = 0; i < 3; i++) {
-    double acc = (fl[i] - fl[i] * gcon00 / gcon00) * p[0];
+    double acc = (fl[i] - div_by(fl[i] * gcon00, g00)) * p[0];
     for (int j = 0; j < 3; j++) {
       double g = i == j ? 1.0 - P[i][j] : -P[i][j];
-      acc += (g - fl[i] * fl[j] / gcon00) * p[1 + j];
+      acc += (g - div_by(fl[i] * fl[j], g00)) * p[1 + j];
     }
     t[i] = acc;
   }

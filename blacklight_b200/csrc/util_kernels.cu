@@ -2,6 +2,7 @@
 // decision (reference radiation_adaptive.cpp:19-312) and an FP64 FMA peak probe for rooflines.
 #include "../../include/blacklight_b200.h"
 #include "rad_types.cuh"
+#include "glibc_math.cuh"
 
 namespace {
 
@@ -161,6 +162,52 @@ extern "C" cudaError_t bl_launch_relayout_grid(const float *prim, int n_var, con
   (void)n_var;
   unsigned grid = (unsigned)((cells + 255) / 256);
   relayout_grid_kernel<<<grid, 256, 0, stream>>>(prim, var_index, cells, out, kappa_out);
+  return cudaGetLastError();
+}
+
+// Self-test of blmath::div_by (shared-reciprocal division) against the hardware IEEE division: every thread
+// draws operand pairs from a xorshift stream -- uniformly random significands over 60 binades, plus the hard
+// cases for rounding (numerators RN(q b) +- 1 ulp, whose quotients sit next to representable numbers and
+// midpoints; denominators with all-ones / all-zeros significand tails) -- and counts differing bit patterns.
+__global__ void division_selftest_kernel(unsigned long long seed, int iters, unsigned long long *mismatches) {
+  unsigned long long s = seed + 0x9E3779B97F4A7C15ull * (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x + 1);
+  auto next = [&]() {
+    s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+    return s;
+  };
+  auto rnd = [&](int kind) {
+    unsigned long long u = next();
+    unsigned long long mant = u & 0xFFFFFFFFFFFFFull;
+    if (kind == 1) mant |= 0xFFFFFFFFFF000ull;          // long run of ones
+    if (kind == 2) mant &= 0x0000000000FFFull;          // long run of zeros
+    if (kind == 3) mant = (mant & ~0xFFFull) | 0xFFFull; // ones at the bottom
+    long long e = 1023 + (long long)((u >> 52) % 61) - 30;
+    unsigned long long sign = (u >> 63) << 63;
+    return __longlong_as_double((long long)(sign | ((unsigned long long)e << 52) | mant));
+  };
+  unsigned long long bad = 0;
+  for (int it = 0; it < iters; it++) {
+    int kb = (int)(next() & 3), ka = (int)(next() & 3);
+    double b = rnd(kb);
+    double a = rnd(ka);
+    if ((it & 3) == 1) {
+      // quotient next to a representable number or a midpoint
+      double q = rnd(0);
+      a = __dmul_rn(q, b);
+      long long bits = __double_as_longlong(a) + (long long)(next() % 5) - 2;
+      a = __longlong_as_double(bits);
+    }
+    blmath::Recip d = blmath::recip_of(b);
+    double got = blmath::div_by(a, d);
+    double want = __ddiv_rn(a, b);
+    if (__double_as_longlong(got) != __double_as_longlong(want)) bad++;
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+
+extern "C" cudaError_t bl_launch_division_selftest(unsigned long long seed, int blocks, int iters,
+                                                   unsigned long long *mismatches, cudaStream_t stream) {
+  division_selftest_kernel<<<blocks, 256, 0, stream>>>(seed, iters, mismatches);
   return cudaGetLastError();
 }
 

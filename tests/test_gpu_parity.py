@@ -289,3 +289,17 @@ def test_adaptive_drop_in(gpu, tmp_path):
     I = {'I_nu': gold['I_nu'], 'Q_nu': gold['Q_nu'], 'U_nu': gold['U_nu'], 'V_nu': gold['V_nu']}
     for k, v in stokes_err({n: npz[n] for n in I}, I).items():
         assert v <= PIXEL_TOL, k
+
+
+def test_shared_division(gpu, tmp_path):
+    """The geodesic kernel divides through one correctly rounded reciprocal per shared denominator
+    (csrc/glibc_math.cuh: div_by).  Its results must be the hardware IEEE quotients bit for bit -- the
+    integrator's exact parity with the reference rests on that -- so compare 2^31 operand pairs, half of them
+    hard cases for rounding (quotients adjacent to representable numbers and to midpoints)."""
+    case = Case(str(tmp_path), 'formula.input', {'camera_resolution': 8})
+    ctx = bl.Context(case.config())
+    try:
+        for seed in (1, 2):
+            assert ctx.selftest_division(1 << 30, seed=seed) == 0
+    finally:
+        ctx.close()
