@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(kBlock, MINB) geodesic_dp_kernel(GeoArgs g) {
         double ya = fabs(ray.y[c]), yb = fabs(ray.y5[c]);
         double y_abs = ya < yb ? yb : ya;
         double scale = g.tol_abs + g.tol_rel * y_abs;
-        double ratio = fabs(ray.y5[c] - y4[c]) / scale;
+        double ratio = blmath::div_rn(fabs(ray.y5[c] - y4[c]), scale);
         error = error < ratio ? ratio : error;
       }
 
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(kBlock, MINB) geodesic_dp_kernel(GeoArgs g) {
         double r_mid = ksx::radius(g.a, ym[1], ym[2], ym[3]);
         double ds_step = g.ray_step * r_mid;
         double ds_full = ray.y5[8] - ray.y[8];
-        int n_ideal = (int)ceil(ds_full / ds_step);
+        int n_ideal = (int)ceil(blmath::div_rn(ds_full, ds_step));
         int n_room = g.max_steps - ray.n;
         int n_sub = n_ideal;
         if (n_sub > n_room) {
@@ -278,9 +278,10 @@ __global__ void __launch_bounds__(kBlock, MINB) geodesic_dp_kernel(GeoArgs g) {
 #pragma unroll
             for (int j = 0; j < 7; j++) q3[j] += dh * kq[j * kBlock];
           }
-          double len = h / n_ideal;
+          const blmath::Recip inv_n = blmath::recip_of((double)n_ideal);
+          double len = blmath::div_by(h, inv_n);
           for (int nn = 0; nn < n_sub; nn++) {
-            double frac = (nn + 0.5) / n_ideal;
+            double frac = blmath::div_by(nn + 0.5, inv_n);
             double v[8];
             v[4] = ray.y[4];
 #pragma unroll

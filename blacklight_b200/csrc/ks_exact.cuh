@@ -26,7 +26,7 @@ BL_HD double radius(double a, double x, double y, double z) {
   double a2 = a * a;
   double rr2 = x * x + y * y + z * z;
   double r2 = 0.5 * (rr2 - a2 + blmath::hypot_glibc(rr2 - a2, 2.0 * a * z));
-  return sqrt(r2);
+  return blmath::sqrt_rn(r2);
 }
 
 BL_HD KsPoint ks_point(double a, double x, double y, double z) {
@@ -34,12 +34,12 @@ BL_HD KsPoint ks_point(double a, double x, double y, double z) {
   double a2 = a * a;
   double rr2 = x * x + y * y + z * z;
   q.r2 = 0.5 * (rr2 - a2 + blmath::hypot_glibc(rr2 - a2, 2.0 * a * z));
-  q.r = sqrt(q.r2);
-  q.f = 2.0 * q.r2 * q.r / (q.r2 * q.r2 + a2 * z * z);
+  q.r = blmath::sqrt_rn(q.r2);
+  q.f = blmath::div_rn(2.0 * q.r2 * q.r, q.r2 * q.r2 + a2 * z * z);
   blmath::Recip ra = blmath::recip_of(q.r2 + a2);
   q.l1 = blmath::div_by(q.r * x + a * y, ra);
   q.l2 = blmath::div_by(q.r * y - a * x, ra);
-  q.l3 = z / q.r;
+  q.l3 = blmath::div_rn(z, q.r);
   return q;
 }
 
@@ -70,8 +70,8 @@ BL_HD_SAMPLE void renormalize_momentum(double a, double x, double y, double z, d
   double qb = 0.0;
   for (int i = 0; i < 3; i++) qb += 2.0 * g0[i] * p[0] * p[1 + i];
   double qc = g00 * p[0] * p[0];
-  double qd = sqrt(qb * qb - 4.0 * qa * qc);
-  double scale = qb < 0.0 ? (qd - qb) / (2.0 * qa) : -2.0 * qc / (qb + qd);
+  double qd = blmath::sqrt_rn(qb * qb - 4.0 * qa * qc);
+  double scale = qb < 0.0 ? blmath::div_rn(qd - qb, 2.0 * qa) : blmath::div_rn(-2.0 * qc, qb + qd);
   for (int i = 0; i < 3; i++) p[1 + i] *= scale;
 }
 
@@ -88,17 +88,17 @@ BL_HD void rhs(double a, double x, double y, double z, const double p[4], double
     dx[2] = p[2];
     dx[3] = p[3];
     dp[0] = dp[1] = dp[2] = 0.0;
-    ds = -sqrt(p[1] * p[1] + p[2] * p[2] + p[3] * p[3]);
+    ds = -blmath::sqrt_rn(p[1] * p[1] + p[2] * p[2] + p[3] * p[3]);
     return;
   }
   double a2 = a * a;
   double rr2 = x * x + y * y + z * z;
   double r2 = 0.5 * (rr2 - a2 + blmath::hypot_glibc(rr2 - a2, 2.0 * a * z));
-  double r = sqrt(r2);
+  double r = blmath::sqrt_rn(r2);
   double r4 = r2 * r2;
   double a2zz = a2 * z * z;
-  double f = 2.0 * r2 * r / (r4 + a2zz);
-  // shared denominators: quotients below are the correctly rounded a / b (blmath::div_by)
+  double f = blmath::div_rn(2.0 * r2 * r, r4 + a2zz);
+  // shared denominators: quotients below are the IEEE quotients a / b (blmath::div_by)
   using blmath::div_by;
   const blmath::Recip ra = blmath::recip_of(r2 + a2), rr = blmath::recip_of(r);
   double l[3] = {div_by(r * x + a * y, ra), div_by(r * y - a * x, ra), div_by(z, rr)};
@@ -131,7 +131,7 @@ BL_HD void rhs(double a, double x, double y, double z, const double p[4], double
   df[2] = div_by(-(qn * dr[2] + 2.0 * a2 * r * z), w) * f;
   double c1 = x - 2.0 * r * l[0];
   double c2 = y - 2.0 * r * l[1];
-  double mz = -z / r2;
+  double mz = blmath::div_rn(-z, r2);
   double dl[3][3];  // dl[a][m] = d l_m / d x^a
   dl[0][0] = div_by(c1 * dr[0] + r, ra);
   dl[1][0] = div_by(c1 * dr[1] + a, ra);
@@ -141,7 +141,7 @@ BL_HD void rhs(double a, double x, double y, double z, const double p[4], double
   dl[2][1] = div_by(c2 * dr[2], ra);
   dl[0][2] = mz * dr[0];
   dl[1][2] = mz * dr[1];
-  dl[2][2] = mz * dr[2] + rr.y;  // RN(1/r)
+  dl[2][2] = mz * dr[2] + div_by(1.0, rr);
 
   // dp_a/dlambda = -sum_{mu,nu} (1/2 d_a g^{mu nu}) p_mu p_nu, (mu,nu) row-major, summed one by one
   double hp[4] = {0.5 * p[0], 0.5 * p[1], 0.5 * p[2], 0.5 * p[3]};
@@ -180,7 +180,7 @@ BL_HD void rhs(double a, double x, double y, double z, const double p[4], double
       double g = i == j ? P[i][j] + 1.0 : P[i][j];
       s2 += g * t[i] * t[j];
     }
-  ds = -sqrt(s2);
+  ds = -blmath::sqrt_rn(s2);
 }
 
 }  // namespace ksx

@@ -165,7 +165,7 @@ extern "C" cudaError_t bl_launch_relayout_grid(const float *prim, int n_var, con
   return cudaGetLastError();
 }
 
-// Self-test of blmath::div_by (shared-reciprocal division) against the hardware IEEE division: every thread
+// Self-test of blmath::div_by / sqrt_rn (branch-free sequences) against the hardware IEEE operations: every thread
 // draws operand pairs from a xorshift stream -- uniformly random significands over 60 binades, plus the hard
 // cases for rounding (numerators RN(q b) +- 1 ulp, whose quotients sit next to representable numbers and
 // midpoints; denominators with all-ones / all-zeros significand tails) -- and counts differing bit patterns.
@@ -201,6 +201,8 @@ __global__ void division_selftest_kernel(unsigned long long seed, int iters, uns
     double got = blmath::div_by(a, d);
     double want = __ddiv_rn(a, b);
     if (__double_as_longlong(got) != __double_as_longlong(want)) bad++;
+    double x = fabs(a);
+    if (__double_as_longlong(blmath::sqrt_rn(x)) != __double_as_longlong(__dsqrt_rn(x))) bad++;
   }
   if (bad) atomicAdd(mismatches, bad);
 }

@@ -214,9 +214,9 @@ int bl_device_info(bl_ctx *ctx, char *name, int name_len, int *sm_count, double 
 int bl_measure_fp64_peak(bl_ctx *ctx, double *tflops);
 
 
-/* Self-test of the geodesic kernel's shared-reciprocal division (csrc/glibc_math.cuh: div_by) against the
- * hardware IEEE division on num_pairs pseudo-random operand pairs; *mismatches = differing results (must be 0:
- * the integrator's bit-for-bit parity with the reference rests on it). */
+/* Self-test of the geodesic kernel's branch-free division and square root (csrc/glibc_math.cuh: div_by,
+ * sqrt_rn) against the hardware IEEE operations on num_pairs pseudo-random operand pairs; *mismatches =
+ * differing results (must be 0: the integrator's bit-for-bit parity with the reference rests on it). */
 int bl_selftest_division(bl_ctx *ctx, uint64_t seed, int64_t num_pairs, int64_t *mismatches);
 
 #ifdef __cplusplus

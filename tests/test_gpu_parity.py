@@ -291,11 +291,12 @@ def test_adaptive_drop_in(gpu, tmp_path):
         assert v <= PIXEL_TOL, k
 
 
-def test_shared_division(gpu, tmp_path):
-    """The geodesic kernel divides through one correctly rounded reciprocal per shared denominator
-    (csrc/glibc_math.cuh: div_by).  Its results must be the hardware IEEE quotients bit for bit -- the
-    integrator's exact parity with the reference rests on that -- so compare 2^31 operand pairs, half of them
-    hard cases for rounding (quotients adjacent to representable numbers and to midpoints)."""
+def test_division_sqrt_sequences(gpu, tmp_path):
+    """The geodesic kernel divides and takes square roots through branch-free instruction sequences with one
+    refined reciprocal per shared denominator (csrc/glibc_math.cuh: div_by, sqrt_rn).  Their results must be
+    the hardware IEEE results bit for bit -- the integrator's exact parity with the reference rests on that --
+    so compare 2^31 operand pairs, a quarter of them hard cases for rounding (quotients adjacent to
+    representable numbers and to midpoints)."""
     case = Case(str(tmp_path), 'formula.input', {'camera_resolution': 8})
     ctx = bl.Context(case.config())
     try:
