@@ -29,8 +29,20 @@ sys.path.insert(0, os.path.join(ROOT, 'tests'))
 FLOP_PER_ATTEMPT = 6900.0
 FLOP_PER_ACCEPT = 540.0
 FLOP_PER_SAMPLE = 220.0
-# Algorithmic bytes gathered per sample, trilinear, 8 variables
+# As-written arithmetic of the reference per sample of radiation work: sampling 60 flop,
+# plasma state + frame geometry 950 flop, and 12 libm calls at the survey's 80 flop-equivalents each
+# (acos, atan2, atan, hypot; atan2, atan, sin, cos, 4 hypot); per frequency, thermal unpolarized:
+# coefficients 60 flop + transfer 10 flop + 8 libm calls (exp, expm1, cbrt, 2 sqrt, pow; exp, expm1);
+# polarized: 6.1 kflop transport/coupling + (thermal 180 flop + 15 calls | kappa 250 flop + 45 calls).
+RAD_FLOP_PER_SAMPLE = 60.0 + 950.0 + 12 * 80.0
+RAD_FLOP_PER_SAMPLE_FREQ = {'simulation': 70.0 + 8 * 80.0, 'formula': 70.0 + 5 * 80.0, 'polarized': 6100.0 + 250.0 + 45 * 80.0}
+# Algorithmic bytes per sample: trilinear gather of 8 variables and one 64-byte
+# step-buffer record written by the geodesic kernel and read once by the radiation kernel
 GATHER_BYTES_PER_SAMPLE = 256.0
+RECORD_BYTES_PER_SAMPLE = 64.0
+# dram__bytes_read.sum + dram__bytes_write.sum per stored sample from the committed ncu --set full captures
+# (profiles/r01_ncu_full_512.txt): geodesic kernel 64.1 B (all writes), radiation kernel 64.4 B (all reads)
+NCU_DRAM_BYTES_PER_SAMPLE = {'geodesic_dp_kernel': 64.1, 'radiate_unpolarized_kernel': 64.4}
 
 
 def parse_args():
@@ -228,11 +240,31 @@ def main():
             image_dev = torch.empty((Q, n_rays), dtype=torch.float64, device='cuda')
             gathered = [torch.empty_like(image_dev) for _ in range(world)] if rank == 0 else None
 
+        # every kernel and copy of the library is issued on the context's own stream: time with CUDA events
+        # recorded on THAT stream (torch's current stream sees none of it)
+        lib_stream = torch.cuda.ExternalStream(ctx.cuda_stream(), device=torch.device('cuda', local_rank))
+
         def barrier():
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
+
+        def timed(fn, steps):
+            """barrier + sync, `steps` calls of fn bracketed by events on the library stream, sync + barrier;
+            returns (device seconds, host seconds, last result)."""
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            t0 = time.perf_counter()
+            ev0.record(lib_stream)
+            out = None
+            for _ in range(steps):
+                out = fn()
+            lib_stream.wait_stream(torch.cuda.current_stream())   # the NCCL gather of the last step (N > 1)
+            ev1.record(lib_stream)
+            ev1.synchronize()
+            barrier()
+            return ev0.elapsed_time(ev1) * 1e-3, time.perf_counter() - t0, out
 
         def step_e2e():
             st0 = ctx.trace_level(0, pos_np, dir_np, fac_np)            # H2D of camera arrays (+ trace if resident)
@@ -253,23 +285,19 @@ def main():
 
         sampler = ClockSampler(local_rank)
         # ---- end-to-end from host buffers ----
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            step_e2e()
-        barrier()
-        t_e2e = time.perf_counter() - t0
+        t_e2e, wall_e2e, _ = timed(step_e2e, args.steps)
         # ---- resident: camera arrays and grid already in HBM, no image download ----
         launches0 = ctx.launch_count()
-        barrier()
-        t0 = time.perf_counter()
-        ms_geo = ms_rad = 0.0
-        for _ in range(args.steps):
-            st = step_resident()
-            ms_geo += st['ms_geodesic']
-            ms_rad += st['ms_radiation']
-        barrier()
-        t_res = time.perf_counter() - t0
+        ms_acc = {'geo': 0.0, 'rad': 0.0}
+
+        def step_resident_acc():
+            st_ = step_resident()
+            ms_acc['geo'] += st_['ms_geodesic']
+            ms_acc['rad'] += st_['ms_radiation']
+            return st_
+
+        t_res, wall_res, st = timed(step_resident_acc, args.steps)
+        ms_geo, ms_rad = ms_acc['geo'], ms_acc['rad']
         launches = ctx.launch_count() - launches0
         clocks = sampler.stop()
 
@@ -286,10 +314,12 @@ def main():
             F = int(cfg.keys.get('image_num_frequencies', '1'))
             value = total_rays * K / t_res
             e2e = total_rays * K / t_e2e
-            # roofline of the dominant kernel on this rank
+            # rooflines of both kernels on this rank; `roofline` carries the dominant (slower) one
             geo_ms, rad_ms = ms_geo / K, ms_rad / K
             flop = st['num_attempts'] * FLOP_PER_ATTEMPT + st['num_accepted'] * FLOP_PER_ACCEPT + st['num_samples'] * FLOP_PER_SAMPLE
             geo_tflops = flop / (geo_ms * 1e-3) / 1e12 if geo_ms > 0 else 0.0
+            rad_flop = st['num_samples'] * (RAD_FLOP_PER_SAMPLE + F * RAD_FLOP_PER_SAMPLE_FREQ[args.workload])
+            rad_tflops = rad_flop / (rad_ms * 1e-3) / 1e12 if rad_ms > 0 else 0.0
             gather_gbs = st['num_samples'] * GATHER_BYTES_PER_SAMPLE / (rad_ms * 1e-3) / 1e9 if rad_ms > 0 else 0.0
             peaks = {}
             try:
@@ -297,15 +327,28 @@ def main():
             except (OSError, ValueError):
                 pass
             hbm_peak = peaks.get('hbm_gbs', 6650.0)
-            if geo_ms >= rad_ms:
-                roofline = {'kernel': 'geodesic_dp_kernel', 'bound': 'fp64', 'achieved': geo_tflops, 'peak': fp64_peak,
-                            'unit': 'TFLOP/s', 'frac': geo_tflops / fp64_peak if fp64_peak else None, 'traffic': None,
-                            'peak_source': 'DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)'}
-            else:
-                roofline = {'kernel': 'radiate_unpolarized_kernel', 'bound': 'hbm', 'achieved': gather_gbs, 'peak': hbm_peak,
-                            'unit': 'GB/s', 'frac': gather_gbs / hbm_peak, 'traffic': None,
-                            'peak_source': 'MEASURED_PEAKS.json hbm_gbs (of measured)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s',
-                            'note': 'gather is L2 resident for the 20 MB mock grid; kernel is FP64/transcendental bound, see fp64 fields'}
+            hbm_src = 'MEASURED_PEAKS.json hbm_gbs (of measured)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s (of fallback)'
+            peak_src = 'DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry); no-FMA code such as the bit-exact geodesic kernel is bounded by half of it'
+            rad_name = 'radiate_polarized_kernel' if args.workload == 'polarized' else 'radiate_unpolarized_kernel'
+            roofs = {
+                'geodesic_dp_kernel': {'kernel': 'geodesic_dp_kernel', 'bound': 'fp64', 'achieved': geo_tflops, 'peak': fp64_peak,
+                                       'unit': 'TFLOP/s', 'frac': geo_tflops / fp64_peak if fp64_peak else None,
+                                       'traffic': st['num_samples'] * NCU_DRAM_BYTES_PER_SAMPLE['geodesic_dp_kernel'],
+                                       'ms': geo_ms, 'peak_source': peak_src,
+                                       'hbm': {'achieved': st['num_samples'] * RECORD_BYTES_PER_SAMPLE / (geo_ms * 1e-3) / 1e9 if geo_ms > 0 else 0.0,
+                                               'peak': hbm_peak, 'unit': 'GB/s', 'peak_source': hbm_src}},
+                rad_name: {'kernel': rad_name, 'bound': 'fp64', 'achieved': rad_tflops, 'peak': fp64_peak, 'unit': 'TFLOP/s',
+                           'frac': rad_tflops / fp64_peak if fp64_peak else None,
+                           'traffic': st['num_samples'] * NCU_DRAM_BYTES_PER_SAMPLE.get(rad_name) if rad_name in NCU_DRAM_BYTES_PER_SAMPLE else None,
+                           'ms': rad_ms, 'peak_source': peak_src,
+                           'note': 'as-written flop-equivalents of the reference per sample (libm calls at 80); the cell gather is '
+                                   'L2 resident for the 20 MB mock grid',
+                           'gather': {'achieved': gather_gbs, 'unit': 'GB/s', 'bytes_per_sample': GATHER_BYTES_PER_SAMPLE},
+                           'hbm': {'achieved': st['num_samples'] * RECORD_BYTES_PER_SAMPLE / (rad_ms * 1e-3) / 1e9 if rad_ms > 0 else 0.0,
+                                   'peak': hbm_peak, 'unit': 'GB/s', 'peak_source': hbm_src}},
+            }
+            roofline = roofs['geodesic_dp_kernel'] if geo_ms >= rad_ms else roofs[rad_name]
+            other = roofs[rad_name] if geo_ms >= rad_ms else roofs['geodesic_dp_kernel']
             line = {
                 'metric': 'camera rays/sec (geodesic+RT)', 'value': value, 'unit': 'rays/s', 'n_gpus': n_gpus, 'steps': K,
                 'warmup': args.warmup, 'ms_per_step': 1e3 * t_res / K, 'higher_is_better': True, 'scaling': 'weak',
@@ -319,9 +362,12 @@ def main():
                 'gpu_launches': int(total_launches),
                 'kernels': {'geodesic_ms_per_step': geo_ms, 'radiation_ms_per_step': rad_ms,
                             'samples_per_step': st['num_samples'], 'dp_attempts_per_step': st['num_attempts'],
-                            'geodesic_tflops_as_written': geo_tflops, 'fp64_peak_tflops_measured': fp64_peak,
-                            'radiation_gather_gbs': gather_gbs, 'ray_freq_per_s': value * F},
-                'roofline': roofline, 'clocks': clocks, 'device': info['name'],
+                            'geodesic_tflops_as_written': geo_tflops, 'radiation_tflops_as_written': rad_tflops,
+                            'fp64_peak_tflops_measured': fp64_peak,
+                            'radiation_gather_gbs': gather_gbs, 'ray_freq_per_s': value * F,
+                            'host_wall_ms_per_step': 1e3 * wall_res / K, 'host_wall_ms_per_step_e2e': 1e3 * wall_e2e / K},
+                'roofline': roofline, 'roofline_other_kernel': other, 'clocks': clocks, 'device': info['name'],
+                'timing': 'CUDA events on the library stream, barrier + synchronize on both sides, max over ranks',
             }
             if n_gpus == 1 and not args.no_cpu_baseline:
                 from harness import REF_BIN

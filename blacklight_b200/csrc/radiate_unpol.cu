@@ -14,6 +14,9 @@
 namespace {
 
 constexpr int kBlock = 128;
+#ifndef BL_RAD_MINB
+#define BL_RAD_MINB 5  // resident blocks per SM the small-bucket kernels are register-capped for
+#endif
 
 // Frequency loops: fully unrolled with the per-frequency state in registers for the small buckets
 // (FMAX <= 4); a rolled loop over state in thread-local memory for the large one (the per-frequency
@@ -152,7 +155,7 @@ __device__ __forceinline__ void formula_fluid(const RadParams &P, double x, doub
 // LEAN: only the light image is requested (no auxiliary images, no rendering) -- the common case gets a
 // kernel without the dead register state of the rest.
 template <int FMAX, bool SIM, bool LEAN>
-__global__ void __launch_bounds__(kBlock, (FMAX <= 4 ? 4 : 2))
+__global__ void __launch_bounds__(kBlock, (FMAX <= 4 ? BL_RAD_MINB : 2))
 radiate_unpolarized_kernel(const __grid_constant__ RadArgs A, const __grid_constant__ RadParams P) {
   extern __shared__ double smem_bounds[];
   const GridDev &G = A.grid;
