@@ -184,8 +184,12 @@ void plasma_constants(const bl_params &p, RadParams &r) {
     r.kappa_aa_low = var_g * var_i * var_j / var_k * var_l * var_m;
     r.kappa_aa_high = var_n * var_o * var_p;
     r.kappa_aa_x_i = std::pow(-1.75 + 1.6 * kk, -0.86);
-    // Stokes-I absorptivity blends with this factor in every mode (simulation_coefficients.cpp:660)
-    r.kappa_aa_high_i = std::pow(3.0 / kk, 4.75) + 0.6;
+    // Stokes-I absorptivity blends with this factor in every mode (simulation_coefficients.cpp:652), but the
+    // reference only assigns it for polarized runs (:121); in an unpolarized run it reads the never-written
+    // member of a freshly allocated object, which is zero in practice, and the kappa absorptivity bridges to
+    // (lo^-x + 0^-x)^(-1/x) = 0.  Reproduced, not fixed (verified against the reference
+    // binary by tests/test_gpu_parity.py::test_live_reference_unpolarized).
+    r.kappa_aa_high_i = pol ? std::pow(3.0 / kk, 4.75) + 0.6 : 0.0;
     if (pol) {
       double var_q = 14.3 * std::pow(w, -0.928);
       double var_r = 169.0 * std::pow(kk, -8.0) + 0.0052 * kk - 0.0526 + 47.0 / (200.0 * kk);

@@ -11,6 +11,7 @@
 // coefficients and the 4x4 coupling -- the reference redoes all of it per frequency with 4x4x4 loops.
 // Same one-ray-per-thread, warp-lock-step walk over the SoA step buffer as the unpolarized kernel.
 #include "rad_sample.cuh"
+#include "bf_math.cuh"
 
 namespace {
 
@@ -258,15 +259,6 @@ struct Coefficients {
   double j[3], a[3], rho[2];  // (I,Q,V), (I,Q,V), (Q,V); Stokes U components vanish in this tetrad
 };
 
-// (lo^-x + hi^-x)^(-1/x) from the logarithms a = ln lo, b = ln hi: the bridging form every kappa fit uses
-// (simulation_coefficients.cpp:641-698).  Evaluated around the smaller of the two, so no intermediate
-// overflows; lo = 0 or hi = 0 (logarithm -inf) gives 0 and NaN propagates, as in the reference.
-__device__ __forceinline__ double bridge(double a, double b, double x, double inv_x) {
-  double d = a == b ? 0.0 : a - b;
-  double m = d < 0.0 ? a : b;
-  return exp(m - log(1.0 + exp(-x * fabs(d))) * inv_x);
-}
-
 // Frequency-independent part of the polarized synchrotron coefficients of one sample.  The reference
 // (simulation_coefficients.cpp:458-698) evaluates ~45 std::pow per frequency for the kappa distribution;
 // here logarithms of the per-sample quantities are taken once, powers of the pitch angle are hoisted, and
@@ -346,7 +338,7 @@ __device__ __forceinline__ void synchrotron_polarized(const RadParams &P, const 
     double xx_neg_1_2 = rsqrt(xx);
     double xx_1_2 = xx * xx_neg_1_2, xx_1_3 = cbrt(xx);
     double xx_1_6 = sqrt(xx_1_3);
-    double coefficient = P.thermal_frac * q.n_nuc * inv_nu_2 * exp(-xx_1_3);
+    double coefficient = P.thermal_frac * q.n_nuc * inv_nu_2 * bfm::exp_bf(-xx_1_3);
     double var_a = phys::sqrt2 * phys::pi / 27.0 * q.sin_b;
     const double var_b = 1.8877486253633870;  // 2^(11/12)
     double var_c = xx_1_2 + var_b * xx_1_6;
@@ -366,14 +358,14 @@ __device__ __forceinline__ void synchrotron_polarized(const RadParams &P, const 
     double factor_q = 0.0, factor_v = 1.0;
     if (q.theta_e >= 0.01) {
       double lx = q.log_om + P.log_freqs[l] + q.log_inv_nu_s;  // ln xx
-      double va = 2.011 * exp(-19.78 * exp(-0.5175 * lx));
-      double vb = cos(39.89 * xx_neg_1_2) * exp(-70.16 * exp(-0.6 * lx));
-      double vc = 0.011 * exp(-1.69 * xx_neg_1_2);
+      double va = 2.011 * bfm::exp_bf(-19.78 * bfm::exp_bf(-0.5175 * lx));
+      double vb = cos(39.89 * xx_neg_1_2) * bfm::exp_bf(-70.16 * bfm::exp_bf(-0.6 * lx));
+      double vc = 0.011 * bfm::exp_bf(-1.69 * xx_neg_1_2);
       double vd = 0.003135 * xx * xx_1_3;
       double ve = 0.5 * (1.0 + tanh(10.0 * (-0.4082690354408987 - 0.5 * lx)));  // ln 0.6648
       double f_0 = va - vb - vc;
       double f_m = f_0 + (vc - vd) * ve;
-      double delta_jj_5 = 0.4379 * log(1.0 + 1.3414 * exp(-0.7515 * lx));
+      double delta_jj_5 = 0.4379 * bfm::log_bf(1.0 + 1.3414 * bfm::exp_bf(-0.7515 * lx));
       factor_q = f_m * (q.k1_k2 + 6.0 * q.theta_e);
       factor_v = (q.k0 - delta_jj_5) * q.inv_k2;
       factor_v = (factor_v < 0.0 || factor_v > 1.0) ? 1.0 : factor_v;
@@ -385,19 +377,19 @@ __device__ __forceinline__ void synchrotron_polarized(const RadParams &P, const 
     double log_nu = q.log_om + P.log_freqs[l];
     double lr = log_nu - q.log_ncs;  // ln(nu / (nu_c sin(theta_B)))
     if (P.power_frac != 0.0) {
-      double e_half = exp(-0.5 * lr);  // (nu / (nu_c sin))^-1/2
-      double coefficient = P.power_frac * q.n_nuc * inv_nu_2 * P.power_jj * q.sin_b * exp(-(P.plasma_p - 1.0) / 2.0 * lr);
+      double e_half = bfm::exp_bf(-0.5 * lr);  // (nu / (nu_c sin))^-1/2
+      double coefficient = P.power_frac * q.n_nuc * inv_nu_2 * P.power_jj * q.sin_b * bfm::exp_bf(-(P.plasma_p - 1.0) / 2.0 * lr);
       C.j[0] += coefficient;
       C.j[1] += coefficient * P.power_jj_q;
       C.j[2] += coefficient * P.power_jj_v * q.cot * (1.7320508075688772 * e_half);
-      double coefficient_a = P.power_frac * q.n_e * (e2 / (phys::m_e * phys::c)) * P.power_aa * exp(-(P.plasma_p + 2.0) / 2.0 * lr);
+      double coefficient_a = P.power_frac * q.n_e * (e2 / (phys::m_e * phys::c)) * P.power_aa * bfm::exp_bf(-(P.plasma_p + 2.0) / 2.0 * lr);
       C.a[0] += coefficient_a;
       C.a[1] += coefficient_a * P.power_aa_q;
       C.a[2] += coefficient_a * P.power_aa_v * q.power_vb * e_half * q.sgn;
       double rb = e_half * e_half;  // nu_c sin / nu
       double ra = q.n_e * (e2 / (phys::m_e * phys::c)) / rb;
       double rc = rb * rb, rd = rc * rb;
-      double re = 1.0 - exp((P.plasma_p / 2.0 - 1.0) * (P.log_power_gmin - lr));
+      double re = 1.0 - bfm::exp_bf((P.plasma_p / 2.0 - 1.0) * (P.log_power_gmin - lr));
       double coefficient_r = P.power_frac * P.power_rho * ra;
       C.rho[0] += coefficient_r * P.power_rho_q * rd * re;
       C.rho[1] += coefficient_r * P.power_rho_v * rc * q.cot;
@@ -411,9 +403,9 @@ __device__ __forceinline__ void synchrotron_polarized(const RadParams &P, const 
         double lva = P.log_k_j_pref + q.log_ne + q.log_ncs - 2.0 * log_nu;  // includes the sin(theta_B) factor
         double l_lo = P.log_kjl + lva + lx * (1.0 / 3.0);
         double l_hi = P.log_kjh + lva - (P.plasma_kappa - 2.0) / 2.0 * lx;
-        C.j[0] += bridge(l_lo, l_hi, P.kappa_jj_x_i, ix_i);
-        C.j[1] -= bridge(l_lo + P.log_kj_low_q, l_hi + P.log_kj_high_q, P.kappa_jj_x_q, ix_q);
-        C.j[2] += bridge(l_lo + P.log_kj_low_v + q.lvd_j + lm035, l_hi + P.log_kj_high_v + q.lvf_j + lm12,
+        C.j[0] += bfm::bridge(l_lo, l_hi, P.kappa_jj_x_i, ix_i);
+        C.j[1] -= bfm::bridge(l_lo + P.log_kj_low_q, l_hi + P.log_kj_high_q, P.kappa_jj_x_q, ix_q);
+        C.j[2] += bfm::bridge(l_lo + P.log_kj_low_v + q.lvd_j + lm035, l_hi + P.log_kj_high_v + q.lvf_j + lm12,
                          P.kappa_jj_x_v, ix_v) * q.sgn;
       }
       {
@@ -421,22 +413,22 @@ __device__ __forceinline__ void synchrotron_polarized(const RadParams &P, const 
         double lva = P.log_k_a_pref + q.log_ne;
         double l_lo = P.log_kal + lva - 2.0 / 3.0 * lx;
         double l_hi = P.log_kah_base + lva - (1.0 + P.plasma_kappa) / 2.0 * lx;
-        C.a[0] += bridge(l_lo, l_hi + (P.log_kah - P.log_kah_base), P.kappa_aa_x_i, ix_i);
-        C.a[1] -= bridge(l_lo + P.log_ka_low_q, l_hi + P.log_ka_high_q, P.kappa_aa_x_q, ix_q);
-        C.a[2] += bridge(l_lo + P.log_ka_low_v + q.lvd_a + lm035, l_hi + P.log_ka_high_v + q.lvf_a + lm12,
+        C.a[0] += bfm::bridge(l_lo, l_hi + (P.log_kah - P.log_kah_base), P.kappa_aa_x_i, ix_i);
+        C.a[1] -= bfm::bridge(l_lo + P.log_ka_low_q, l_hi + P.log_ka_high_q, P.kappa_aa_x_q, ix_q);
+        C.a[2] += bfm::bridge(l_lo + P.log_ka_low_v + q.lvd_a + lm035, l_hi + P.log_ka_high_v + q.lvf_a + lm12,
                          P.kappa_aa_x_v, ix_v) * q.sgn;
       }
       {
         double va = -P.kappa_frac * q.n_e * e2 * q.nu_c * q.nu_c * q.sin2 * inv_nu_2 * (1.0 / (phys::m_e * phys::c));
         double vb = P.kappa_frac * 2.0 * q.n_e * e2 * q.nu_c * q.cos_b * inv_nu * (1.0 / (phys::m_e * phys::c));
-        double x084 = exp(0.84 * lx);
-        double xx_m12 = exp(lm12);
-        double q_lo = va * P.kappa_rho_q_low_a * (1.0 - exp(P.kappa_rho_q_low_b * x084) -
-                      sin(P.kappa_rho_q_low_c * xx) * exp(P.kappa_rho_q_low_d * exp(P.kappa_rho_q_low_e * lx)));
-        double q_hi = va * P.kappa_rho_q_high_a * (1.0 - exp(P.kappa_rho_q_high_b * x084) -
-                      sin(P.kappa_rho_q_high_c * xx) * exp(P.kappa_rho_q_high_d * exp(P.kappa_rho_q_high_e * lx)));
-        double v_lo = P.kappa_rho_v * vb * P.kappa_rho_v_low_a * (1.0 - 0.17 * log(1.0 + P.kappa_rho_v_low_b * xx_m12));
-        double v_hi = P.kappa_rho_v * vb * P.kappa_rho_v_high_a * (1.0 - 0.17 * log(1.0 + P.kappa_rho_v_high_b * xx_m12));
+        double x084 = bfm::exp_bf(0.84 * lx);
+        double xx_m12 = bfm::exp_bf(lm12);
+        double q_lo = va * P.kappa_rho_q_low_a * (1.0 - bfm::exp_bf(P.kappa_rho_q_low_b * x084) -
+                      sin(P.kappa_rho_q_low_c * xx) * bfm::exp_bf(P.kappa_rho_q_low_d * bfm::exp_bf(P.kappa_rho_q_low_e * lx)));
+        double q_hi = va * P.kappa_rho_q_high_a * (1.0 - bfm::exp_bf(P.kappa_rho_q_high_b * x084) -
+                      sin(P.kappa_rho_q_high_c * xx) * bfm::exp_bf(P.kappa_rho_q_high_d * bfm::exp_bf(P.kappa_rho_q_high_e * lx)));
+        double v_lo = P.kappa_rho_v * vb * P.kappa_rho_v_low_a * (1.0 - 0.17 * bfm::log_bf(1.0 + P.kappa_rho_v_low_b * xx_m12));
+        double v_hi = P.kappa_rho_v * vb * P.kappa_rho_v_high_a * (1.0 - 0.17 * bfm::log_bf(1.0 + P.kappa_rho_v_high_b * xx_m12));
         C.rho[0] += (1.0 - P.kappa_rho_frac) * q_lo + P.kappa_rho_frac * q_hi;
         C.rho[1] += (1.0 - P.kappa_rho_frac) * v_lo + P.kappa_rho_frac * v_hi;
       }

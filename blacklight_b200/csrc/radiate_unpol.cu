@@ -10,6 +10,7 @@
 // Reference: simulation_sampling.cpp:122-1044, simulation_coefficients.cpp:254-701,
 //            formula_coefficients.cpp:25-183, unpolarized.cpp:31-221, rendering.cpp:25-179.
 #include "rad_sample.cuh"
+#include "bf_math.cuh"
 
 namespace {
 
@@ -79,7 +80,7 @@ __device__ __forceinline__ void synchrotron_unpolarized(const RadParams &P, cons
     double xx_1_6 = sqrt(xx_1_3);
     const double var_b = 1.8877486253633870;  // 2^(11/12)
     double var_c = xx_1_2 + var_b * xx_1_6;
-    double j_th = q.th_shape * inv_nu_2 * exp(-xx_1_3) * (var_c * var_c);
+    double j_th = q.th_shape * inv_nu_2 * bfm::exp_bf(-xx_1_3) * (var_c * var_c);
     if (need_j) j_val = j_th;
     if (need_a) {
       // Kirchhoff: alpha nu = j/nu^2 / (B_nu/nu^3), B_nu/nu^3 = 2h/c^2 / expm1(h nu / k T_e)
@@ -94,10 +95,10 @@ __device__ __forceinline__ void synchrotron_unpolarized(const RadParams &P, cons
     double lr = log_nu - q.log_ncs;  // ln(nu / (nu_c sin(theta_B)))
     if (P.power_frac != 0.0) {
       if (need_j)
-        j_val += P.power_frac * q.n_nuc * inv_nu_2 * P.power_jj * q.sin_theta_b * exp(-(P.plasma_p - 1.0) / 2.0 * lr);
+        j_val += P.power_frac * q.n_nuc * inv_nu_2 * P.power_jj * q.sin_theta_b * bfm::exp_bf(-(P.plasma_p - 1.0) / 2.0 * lr);
       if (need_a)
         a_val += P.power_frac * q.n_e * (phys::e * phys::e / (phys::m_e * phys::c)) * P.power_aa *
-                 exp(-(P.plasma_p + 2.0) / 2.0 * lr);
+                 bfm::exp_bf(-(P.plasma_p + 2.0) / 2.0 * lr);
     }
     if (P.kappa_frac != 0.0) {
       double lx = lr - P.log_w2k2;  // ln(nu / nu_kappa)
@@ -106,15 +107,13 @@ __device__ __forceinline__ void synchrotron_unpolarized(const RadParams &P, cons
         double lva = P.log_k_j_pref + q.log_ne + q.log_ncs - 2.0 * log_nu;
         double l_lo = P.log_kjl + lva + lx * (1.0 / 3.0);
         double l_hi = P.log_kjh + lva - (P.plasma_kappa - 2.0) / 2.0 * lx;
-        double sum = exp(-P.kappa_jj_x_i * l_lo) + exp(-P.kappa_jj_x_i * l_hi);
-        j_val += exp(-log(sum) / P.kappa_jj_x_i);
+        j_val += bfm::bridge(l_lo, l_hi, P.kappa_jj_x_i, 1.0 / P.kappa_jj_x_i);
       }
       if (need_a) {
         double lva = P.log_k_a_pref + q.log_ne;
         double l_lo = P.log_kal + lva - 2.0 / 3.0 * lx;
         double l_hi = P.log_kah + lva - (1.0 + P.plasma_kappa) / 2.0 * lx;
-        double sum = exp(-P.kappa_aa_x_i * l_lo) + exp(-P.kappa_aa_x_i * l_hi);
-        a_val += exp(-log(sum) / P.kappa_aa_x_i);
+        a_val += bfm::bridge(l_lo, l_hi, P.kappa_aa_x_i, 1.0 / P.kappa_aa_x_i);
       }
     }
   }

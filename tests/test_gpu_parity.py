@@ -125,6 +125,10 @@ def test_golden_unpolarized(name, gpu, tmp_path):
     ('simulation.input', {'camera_resolution': 40, 'ray_integrator': 'rk4', 'ray_step': '0.02'}, None),
     ('simulation.input', {'camera_resolution': 40, 'ray_integrator': 'rk2', 'ray_step': '0.02'}, None),
     ('simulation.input', {'camera_resolution': 40, 'plasma_power_frac': '0.3', 'plasma_p': '3.0', 'plasma_gamma_min': '4.0', 'plasma_gamma_max': '1000.0'}, None),
+    ('simulation.input', {'camera_resolution': 32, 'plasma_kappa_frac': '0.4', 'plasma_kappa': '4.2', 'plasma_w': '0.8',
+                          'plasma_power_frac': '0.2', 'plasma_p': '2.5', 'plasma_gamma_min': '2.0', 'plasma_gamma_max': '500.0',
+                          'image_num_frequencies': 3, 'image_frequency_start': '8.6e10', 'image_frequency_end': '6.9e11',
+                          'image_frequency_spacing': 'log'}, None),
     ('simulation.input', {'camera_resolution': 32, 'fallback_nan': 'false', 'fallback_rho': '1.0e-6', 'fallback_pgas': '1.0e-8', 'camera_r': '80.0', 'camera_width': '60.0'}, None),
     ('simulation.input', {'camera_resolution': 32, 'cut_omit_near': 'true', 'cut_omit_in': '3.0', 'cut_midplane_theta': '30.0', 'cut_rho_min': '1.0e-18'}, None),
     ('formula.input', {'camera_resolution': 24, 'image_num_frequencies': 3, 'image_frequency_start': '1.0e11', 'image_frequency_end': '4.0e11', 'image_frequency_spacing': 'lin_wave', 'camera_th': '0.0'}, None),
