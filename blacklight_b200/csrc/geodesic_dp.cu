@@ -13,7 +13,10 @@
 
 namespace {
 
-constexpr int kBlock = 128;
+#ifndef BL_GEO_BLOCK
+#define BL_GEO_BLOCK 128
+#endif
+constexpr int kBlock = BL_GEO_BLOCK;
 constexpr int kComp = 7;  // t, x, y, z, p_x, p_y, p_z in shared memory (dp_t/dlambda is identically zero);
                           // the proper-distance rate ds/dlambda of a stage is consumed at once (registers)
 
@@ -138,7 +141,12 @@ __global__ void __launch_bounds__(kBlock, MINB) geodesic_dp_kernel(GeoArgs g) {
       }
       if (base + __popc(idle) >= (unsigned long long)g.rays) exhausted = true;
     }
+#if !defined(BL_GEO_NOSYNC)
+    // keep the CTA's warps in the same region of the (instruction-cache-sized) loop body
+    if (!__syncthreads_or(active ? 1 : 0)) break;
+#else
     if (!__any_sync(full, active)) break;
+#endif
     if (!active) continue;
 
     // ---- one step attempt ----

@@ -16,7 +16,7 @@ namespace {
 
 constexpr int kBlock = 128;
 #ifndef BL_RAD_MINB
-#define BL_RAD_MINB 5  // resident blocks per SM the small-bucket kernels are register-capped for
+#define BL_RAD_MINB 6  // resident blocks per SM the small-bucket kernels are register-capped for
 #endif
 
 // Frequency loops: fully unrolled with the per-frequency state in registers for the small buckets
