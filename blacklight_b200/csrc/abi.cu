@@ -234,6 +234,7 @@ void plasma_constants(const bl_params &p, RadParams &r) {
 void fill_rad_params(const bl_params &p, RadParams &r) {
   std::memset(&r, 0, sizeof r);
   r.model_type = p.model_type; r.ray_flat = p.ray_flat; r.coord = p.simulation_coord; r.interp = p.simulation_interp;
+  r.block_interp = p.simulation_interp && p.simulation_block_interp;
   r.a = p.bh_a; r.camera_r = p.camera_r;
   for (int i = 0; i < 4; i++) {
     r.camera_x[i] = p.camera_x[i]; r.camera_u_con[i] = p.camera_u_con[i];
@@ -327,8 +328,6 @@ int validate_params(const bl_params &p) {
     if (!(p.image_frequencies[l] > 0.0)) return bl_fail(nullptr, BL_ERR_ARG, "Must choose positive image_frequency.");
   if (p.model_type == BL_MODEL_SIMULATION && p.simulation_coord == BL_COORD_FMKS)
     return bl_fail(nullptr, BL_ERR_UNSUPPORTED, "simulation_coord = fmks is outside the B200 hot-path scope (SURVEY.md section 2)");
-  if (p.model_type == BL_MODEL_SIMULATION && p.simulation_interp && p.simulation_block_interp)
-    return bl_fail(nullptr, BL_ERR_UNSUPPORTED, "simulation_block_interp = true not implemented yet (SURVEY.md section 8f item 1)");
   bool sim = p.model_type == BL_MODEL_SIMULATION;
   if (!(p.image_light || p.image_time || p.image_length || p.image_lambda || p.image_emission || p.image_tau ||
         (sim && (p.image_lambda_ave || p.image_emission_ave || p.image_tau_int)) || p.image_crossings ||
@@ -503,9 +502,25 @@ int bl_upload_grid(bl_ctx *ctx, const bl_grid_view *gv) {
     BL_CUDA_CHECK(alloc_d(&g.x1f, (size_t)g.n_b * (g.n_i + 1)));
     BL_CUDA_CHECK(alloc_d(&g.x2f, (size_t)g.n_b * (g.n_j + 1)));
     BL_CUDA_CHECK(alloc_d(&g.x3f, (size_t)g.n_b * (g.n_k + 1)));
-    BL_CUDA_CHECK(alloc_d(&g.x1v, (size_t)g.n_b * g.n_i));
-    BL_CUDA_CHECK(alloc_d(&g.x2v, (size_t)g.n_b * g.n_j));
-    BL_CUDA_CHECK(alloc_d(&g.x3v, (size_t)g.n_b * g.n_k));
+    // one element of padding: the reference's inter-block fractions read x?v(b, n) -- the first centre of the
+    // next block, and one element past the array for the last block (simulation_sampling.cpp:519-521)
+    BL_CUDA_CHECK(alloc_d(&g.x1v, (size_t)g.n_b * g.n_i + 1));
+    BL_CUDA_CHECK(alloc_d(&g.x2v, (size_t)g.n_b * g.n_j + 1));
+    BL_CUDA_CHECK(alloc_d(&g.x3v, (size_t)g.n_b * g.n_k + 1));
+    BL_CUDA_CHECK(cudaMemsetAsync((void *)(g.x1v + (size_t)g.n_b * g.n_i), 0, sizeof(double), ctx->stream));
+    BL_CUDA_CHECK(cudaMemsetAsync((void *)(g.x2v + (size_t)g.n_b * g.n_j), 0, sizeof(double), ctx->stream));
+    BL_CUDA_CHECK(cudaMemsetAsync((void *)(g.x3v + (size_t)g.n_b * g.n_k), 0, sizeof(double), ctx->stream));
+    if (ctx->rad.block_interp) {
+      uint32_t size = 16;
+      while (size < 2u * (uint32_t)g.n_b) size <<= 1;
+      g.hash_mask = size - 1;
+      int32_t *ip = nullptr;
+      unsigned long long *kp = nullptr;
+      BL_CUDA_CHECK(dev_alloc(&ip, (size_t)g.n_b)); g.levels = ip; ctx->grid_allocs.push_back(ip);
+      BL_CUDA_CHECK(dev_alloc(&ip, (size_t)g.n_b * 3)); g.locs = ip; ctx->grid_allocs.push_back(ip);
+      BL_CUDA_CHECK(dev_alloc(&ip, (size_t)size)); g.hash_vals = ip; ctx->grid_allocs.push_back(ip);
+      BL_CUDA_CHECK(dev_alloc(&kp, (size_t)size)); g.hash_keys = kp; ctx->grid_allocs.push_back(kp);
+    }
     BL_CUDA_CHECK(alloc_d(&g.bounds, (size_t)g.n_b * 6));
     BL_CUDA_CHECK(alloc_d(&g.x1d, (size_t)g.n_b * g.n_i));
     BL_CUDA_CHECK(alloc_d(&g.x2d, (size_t)g.n_b * g.n_j));
@@ -538,6 +553,35 @@ int bl_upload_grid(bl_ctx *ctx, const bl_grid_view *gv) {
     bounds[6 * b + 5] = gv->x3f[(size_t)b * (g.n_k + 1) + g.n_k];
   }
   BL_CUDA_CHECK(cudaMemcpyAsync((void *)g.bounds, bounds.data(), bounds.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  // mesh topology: levels, logical locations and the (level, location) -> block hash
+  std::vector<unsigned long long> hkeys;
+  std::vector<int32_t> hvals;
+  if (ctx->rad.block_interp) {
+    if (!gv->levels || !gv->locations)
+      return bl_fail(ctx, BL_ERR_ARG, "simulation_block_interp needs the blocks' levels and logical locations");
+    if (gv->n_3_root <= 0 || gv->n_3_root % g.n_k != 0)
+      return bl_fail(ctx, BL_ERR_ARG, "simulation_block_interp needs RootGridSize[2] (n_3_root) as a multiple of the block size");
+    g.n3_root = gv->n_3_root / g.n_k;
+    g.max_level = 0;
+    hkeys.assign((size_t)g.hash_mask + 1, ~0ull);
+    hvals.assign((size_t)g.hash_mask + 1, -1);
+    for (int b = 0; b < g.n_b; b++) {
+      int lev = gv->levels[b];
+      const int32_t *loc = gv->locations + 3 * (size_t)b;
+      if (lev < 0 || lev > 40 || loc[0] < 0 || loc[1] < 0 || loc[2] < 0 || loc[0] >= (1 << 19) || loc[1] >= (1 << 19) || loc[2] >= (1 << 19))
+        return bl_fail(ctx, BL_ERR_ARG, "block %d: level/location outside the supported range", b);
+      if (lev > g.max_level) g.max_level = lev;
+      unsigned long long key = block_key(lev, loc[0], loc[1], loc[2]);
+      uint32_t h = block_hash(key) & g.hash_mask;
+      while (hkeys[h] != ~0ull) h = (h + 1) & g.hash_mask;
+      hkeys[h] = key;
+      hvals[h] = b;
+    }
+    BL_CUDA_CHECK(cudaMemcpyAsync((void *)g.levels, gv->levels, (size_t)g.n_b * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    BL_CUDA_CHECK(cudaMemcpyAsync((void *)g.locs, gv->locations, (size_t)g.n_b * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    BL_CUDA_CHECK(cudaMemcpyAsync((void *)g.hash_keys, hkeys.data(), hkeys.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+    BL_CUDA_CHECK(cudaMemcpyAsync((void *)g.hash_vals, hvals.data(), hvals.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  }
   // reciprocal cell-centre spacings, so that interpolation fractions need no division on the device
   std::vector<double> inv1((size_t)g.n_b * g.n_i), inv2((size_t)g.n_b * g.n_j), inv3((size_t)g.n_b * g.n_k);
   auto fill_inv = [&](std::vector<double> &out, const double *xv, int n) {

@@ -116,6 +116,125 @@ __device__ __forceinline__ bool geometric_cut(const RadParams &P, double x, doub
   return false;
 }
 
+// ---- inter-block interpolation (simulation_block_interp; reference simulation_sampling.cpp:504-549) ----
+
+// Block with the given refinement level and logical location, or -1.
+__device__ __forceinline__ int find_block(const GridDev &g, int level, int li, int lj, int lk) {
+  if (level < 0 || level > g.max_level || li < 0 || lj < 0 || lk < 0) return -1;
+  unsigned long long key = block_key(level, li, lj, lk);
+  uint32_t h = block_hash(key) & g.hash_mask;
+  for (;;) {
+    unsigned long long kk = __ldg(g.hash_keys + h);
+    if (kk == key) return __ldg(g.hash_vals + h);
+    if (kk == ~0ull) return -1;
+    h = (h + 1) & g.hash_mask;
+  }
+}
+
+// Cell (block, k, j, i) standing in for cell (k, j, i) of block b when an index is one beyond the block
+// (reference FindNearbyInds, simulation_sampling.cpp:1068-1321): the ghost cell's owner at the same level,
+// else the coarser cell containing it, else the nearest finer cell; constant extrapolation off the grid;
+// periodic in x3 for spherical coordinates.  (k_c, j_c, i_c) is the cell containing the sample point.
+// The reference scans all blocks for each of its existence tests; here each test is one hash lookup.
+static __device__ __noinline__ void find_nearby_inds(const RadParams &P, const GridDev &g, int b, int k, int j, int i, int k_c,
+                                              int j_c, int i_c, double x3, double x2, double x1, int inds[4]) {
+  const int n_i = g.n_i, n_j = g.n_j, n_k = g.n_k;
+  const int level = __ldg(g.levels + b);
+  const int li = __ldg(g.locs + 3 * b), lj = __ldg(g.locs + 3 * b + 1), lk = __ldg(g.locs + 3 * b + 2);
+  const bool upper_i = i > n_i / 2, upper_j = j > n_j / 2, upper_k = k > n_k / 2;
+  const int i_safe = max(min(i, n_i - 1), 0), j_safe = max(min(j, n_j - 1), 0), k_safe = max(min(k, n_k - 1), 0);
+  inds[0] = b; inds[1] = k; inds[2] = j; inds[3] = i;
+  if (i == i_safe && j == j_safe && k == k_safe) return;
+  const bool sks = P.coord != 0;
+  auto n3 = [&](int lev) { return g.n3_root << lev; };   // blocks around x3 at a level
+  const int ui = upper_i ? 1 : 0, uj = upper_j ? 1 : 0, uk = upper_k ? 1 : 0;
+
+  // does the grid continue in each direction in which the cell lies outside the block?
+  bool x1_off = false, x2_off = false, x3_off = false;
+  if (i != i_safe) {
+    int s = i == -1 ? -1 : 1;
+    x1_off = find_block(g, level, li + s, lj, lk) < 0 && find_block(g, level - 1, (li + s) / 2, lj / 2, lk / 2) < 0 &&
+             find_block(g, level + 1, i == -1 ? li * 2 - 1 : li * 2 + 2, lj * 2 + uj, lk * 2 + uk) < 0;
+  }
+  if (j != j_safe) {
+    int s = j == -1 ? -1 : 1;
+    x2_off = find_block(g, level, li, lj + s, lk) < 0 && find_block(g, level - 1, li / 2, (lj + s) / 2, lk / 2) < 0 &&
+             find_block(g, level + 1, li * 2 + ui, j == -1 ? lj * 2 - 1 : lj * 2 + 2, lk * 2 + uk) < 0;
+  }
+  if (k != k_safe) {
+    int s = k == -1 ? -1 : 1;
+    x3_off = find_block(g, level, li, lj, lk + s) < 0 && find_block(g, level - 1, li / 2, lj / 2, (lk + s) / 2) < 0 &&
+             find_block(g, level + 1, li * 2 + ui, lj * 2 + uj, k == -1 ? lk * 2 - 1 : lk * 2 + 2) < 0;
+    // across the periodic boundary
+    if (x3_off && sks && ((k == -1 && lk == 0) || (k == n_k && lk == n3(level) - 1))) {
+      bool low = k == -1;
+      x3_off = find_block(g, level, li, lj, low ? n3(level) - 1 : 0) < 0 &&
+               (level < 1 || find_block(g, level - 1, li / 2, lj / 2, low ? n3(level - 1) - 1 : 0) < 0) &&
+               (level + 1 > g.max_level ||
+                find_block(g, level + 1, li * 2 + ui, lj * 2 + uj, low ? n3(level + 1) - 1 : 0) < 0);
+    }
+  }
+  if (x1_off) i = i_safe;
+  if (x2_off) j = j_safe;
+  if (x3_off) k = k_safe;
+  const bool wrap_low = sks && k == -1 && lk == 0;
+  const bool wrap_high = sks && k == n_k && lk == n3(level) - 1;
+
+  // same level
+  {
+    int si = i == i_safe ? li : (i == -1 ? li - 1 : li + 1);
+    int sj = j == j_safe ? lj : (j == -1 ? lj - 1 : lj + 1);
+    int sk = k == k_safe ? lk : (k == -1 ? lk - 1 : lk + 1);
+    if (wrap_low) sk = n3(level) - 1;
+    if (wrap_high) sk = 0;
+    int bb = find_block(g, level, si, sj, sk);
+    if (bb >= 0) {
+      inds[0] = bb;
+      inds[1] = k == k_safe ? k : (k == -1 ? n_k - 1 : 0);
+      inds[2] = j == j_safe ? j : (j == -1 ? n_j - 1 : 0);
+      inds[3] = i == i_safe ? i : (i == -1 ? n_i - 1 : 0);
+      return;
+    }
+  }
+  // coarser level
+  if (level - 1 >= 0) {
+    int si = i == i_safe ? li / 2 : (i == -1 ? (li - 1) / 2 : (li + 1) / 2);
+    int sj = j == j_safe ? lj / 2 : (j == -1 ? (lj - 1) / 2 : (lj + 1) / 2);
+    int sk = k == k_safe ? lk / 2 : (k == -1 ? (lk - 1) / 2 : (lk + 1) / 2);
+    if (wrap_low) sk = n3(level - 1) - 1;
+    if (wrap_high) sk = 0;
+    int bb = find_block(g, level - 1, si, sj, sk);
+    if (bb >= 0) {
+      inds[0] = bb;
+      inds[1] = k == k_safe ? (lk % 2 * n_k + k) / 2 : (k == -1 ? n_k - 1 : 0);
+      inds[2] = j == j_safe ? (lj % 2 * n_j + j) / 2 : (j == -1 ? n_j - 1 : 0);
+      inds[3] = i == i_safe ? (li % 2 * n_i + i) / 2 : (i == -1 ? n_i - 1 : 0);
+      return;
+    }
+  }
+  // finer level
+  {
+    int si = li * 2 + (i == i_safe ? 0 : (i == -1 ? -1 : 1)) + ui;
+    int sj = lj * 2 + (j == j_safe ? 0 : (j == -1 ? -1 : 1)) + uj;
+    int sk = lk * 2 + (k == k_safe ? 0 : (k == -1 ? -1 : 1)) + uk;
+    if (wrap_low && level + 1 <= g.max_level) sk = n3(level + 1) - 1;
+    if (wrap_high) sk = 0;
+    int bb = find_block(g, level + 1, si, sj, sk);
+    if (bb >= 0) {
+      inds[0] = bb;
+      inds[1] = k == k_safe ? (upper_k ? (k - n_k / 2) * 2 : k * 2) : (k == -1 ? n_k - 2 : 0);
+      inds[2] = j == j_safe ? (upper_j ? (j - n_j / 2) * 2 : j * 2) : (j == -1 ? n_j - 2 : 0);
+      inds[3] = i == i_safe ? (upper_i ? (i - n_i / 2) * 2 : i * 2) : (i == -1 ? n_i - 2 : 0);
+      inds[1] += (k < k_c || (k == k_c && x3 > __ldg(g.x3v + (size_t)b * n_k + k_c))) ? 1 : 0;
+      inds[2] += (j < j_c || (j == j_c && x2 > __ldg(g.x2v + (size_t)b * n_j + j_c))) ? 1 : 0;
+      inds[3] += (i < i_c || (i == i_c && x1 > __ldg(g.x1v + (size_t)b * n_i + i_c))) ? 1 : 0;
+      return;
+    }
+  }
+  // inconsistent mesh (the reference throws "Grid interpolation failed."): fall back to the nearest own cell
+  inds[0] = b; inds[1] = k_safe; inds[2] = j_safe; inds[3] = i_safe;
+}
+
 // Where the previous sample of this ray was found: the block (the reference keeps the same cache per
 // OpenMP thread, simulation_sampling.cpp:180-189,352-394) and, as search hints only, its cell.
 struct CellCache {
@@ -124,6 +243,9 @@ struct CellCache {
 
 // Locate and gather.  smem_bounds: block bounds staged in shared memory (n_b*6 doubles) or nullptr to
 // read them from HBM.  inv_r = 1/r.
+// BI: inter-block interpolation compiled in (selected at run time by P.block_interp); the light-only
+// unpolarized kernel is instantiated without it so that the common path keeps its register budget.
+template <bool BI>
 __device__ __forceinline__ SampleStatus sample_grid(const RadParams &P, const GridDev &g,
                                                     const double *smem_bounds, double x, double y,
                                                     double z, double r, double inv_r, CellCache &cache,
@@ -167,8 +289,61 @@ __device__ __forceinline__ SampleStatus sample_grid(const RadParams &P, const Gr
     out.kappa = g.kappa ? __ldg(g.kappa + c) : 0.0f;
     return kSampleOk;
   }
-  // intra-block trilinear with extrapolation at block edges (simulation_sampling.cpp:485-502)
   const double *x1v = g.x1v + (size_t)b * n_i, *x2v = g.x2v + (size_t)b * n_j, *x3v = g.x3v + (size_t)b * n_k;
+  if (BI && P.block_interp) {
+    // inter-block trilinear: anchors may be ghost cells, resolved on neighbouring blocks of any level
+    // (simulation_sampling.cpp:504-549).  Upper ghost coordinates are formed exactly as the reference
+    // does, from x?v(b, i+1) -- for i = n-1 the next block's first centre (the arrays carry one element of
+    // padding for the last block).
+    const double *x1fb = g.x1f + (size_t)b * (n_i + 1), *x2fb = g.x2f + (size_t)b * (n_j + 1), *x3fb = g.x3f + (size_t)b * (n_k + 1);
+    int i_m = x1 >= __ldg(x1v + i) ? i : i - 1, i_p = i_m + 1;
+    int j_m = x2 >= __ldg(x2v + j) ? j : j - 1, j_p = j_m + 1;
+    int k_m = x3 >= __ldg(x3v + k) ? k : k - 1, k_p = k_m + 1;
+    double x1_m = i_m == -1 ? 2.0 * __ldg(x1fb + i) - __ldg(x1v + i) : __ldg(x1v + i_m);
+    double x2_m = j_m == -1 ? 2.0 * __ldg(x2fb + j) - __ldg(x2v + j) : __ldg(x2v + j_m);
+    double x3_m = k_m == -1 ? 2.0 * __ldg(x3fb + k) - __ldg(x3v + k) : __ldg(x3v + k_m);
+    double x1_p = i_p == n_i ? 2.0 * __ldg(x1v + i + 1) - __ldg(x1v + i) : __ldg(x1v + i_p);
+    double x2_p = j_p == n_j ? 2.0 * __ldg(x2v + j + 1) - __ldg(x2v + j) : __ldg(x2v + j_p);
+    double x3_p = k_p == n_k ? 2.0 * __ldg(x3v + k + 1) - __ldg(x3v + k) : __ldg(x3v + k_p);
+    double f_i = (x1 - x1_m) / (x1_p - x1_m);
+    double f_j = (x2 - x2_m) / (x2_p - x2_m);
+    double f_k = (x3 - x3_m) / (x3_p - x3_m);
+    double gk = 1.0 - f_k, gj = 1.0 - f_j, gi = 1.0 - f_i;
+    double w[8] = {gk * gj * gi, gk * gj * f_i, gk * f_j * gi, gk * f_j * f_i,
+                   f_k * gj * gi, f_k * gj * f_i, f_k * f_j * gi, f_k * f_j * f_i};
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double acc_kappa = 0.0;
+    float corner[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float corner_kappa = 0.0f;
+#pragma unroll 1
+    for (int p = 0; p < 8; p++) {
+      int inds[4];
+      find_nearby_inds(P, g, b, (p & 4) ? k_p : k_m, (p & 2) ? j_p : j_m, (p & 1) ? i_p : i_m, k, j, i, x3, x2, x1, inds);
+      if (p == 0) {
+        si.b = inds[0]; si.k = inds[1]; si.j = inds[2]; si.i = inds[3];
+      }
+      size_t c = (((size_t)inds[0] * n_k + inds[1]) * n_j + inds[2]) * n_i + inds[3];
+      float v[8];
+      load_cell(g, c, v);
+      if (p == 0)
+        for (int q = 0; q < 8; q++) corner[q] = v[q];
+      for (int q = 0; q < 8; q++) acc[q] += w[p] * (double)v[q];
+      if (g.kappa) {
+        float kv = __ldg(g.kappa + c);
+        if (p == 0) corner_kappa = kv;
+        acc_kappa += w[p] * (double)kv;
+      }
+    }
+    si.fk = f_k; si.fj = f_j; si.fi = f_i;
+    if (acc[0] <= 0.0) acc[0] = (double)corner[0];
+    if (acc[1] <= 0.0) acc[1] = (double)corner[1];
+    if (g.kappa && acc_kappa <= 0.0) acc_kappa = (double)corner_kappa;
+    out.rho = (float)acc[0]; out.pgas = (float)acc[1]; out.uu1 = (float)acc[2]; out.uu2 = (float)acc[3];
+    out.uu3 = (float)acc[4]; out.bb1 = (float)acc[5]; out.bb2 = (float)acc[6]; out.bb3 = (float)acc[7];
+    out.kappa = (float)acc_kappa;
+    return kSampleOk;
+  }
+  // intra-block trilinear with extrapolation at block edges (simulation_sampling.cpp:485-502)
   int i_m = (i == 0 || (i != n_i - 1 && x1 >= __ldg(x1v + i))) ? i : i - 1;
   int j_m = (j == 0 || (j != n_j - 1 && x2 >= __ldg(x2v + j))) ? j : j - 1;
   int k_m = (k == 0 || (k != n_k - 1 && x3 >= __ldg(x3v + k))) ? k : k - 1;

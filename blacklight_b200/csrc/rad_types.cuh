@@ -33,10 +33,30 @@ struct GridDev {
   const double *x1d, *x2d, *x3d;  // (n_b, n): 1 / (xv[i+1] - xv[i]) for i < n-1 (interpolation weights)
   const float4 *cells;
   const float *kappa;             // (n_b, n_k, n_j, n_i) electron entropy, or nullptr
+  // mesh topology for inter-block interpolation (simulation_block_interp): refinement level and logical
+  // location of every block, and an open-addressing hash (level, location) -> block built at upload, which
+  // replaces the reference's linear scans over all blocks (simulation_sampling.cpp:1068-1321)
+  const int32_t *levels;          // (n_b)
+  const int32_t *locs;            // (n_b, 3): x1, x2, x3 logical locations
+  const unsigned long long *hash_keys;
+  const int32_t *hash_vals;
+  uint32_t hash_mask;             // table size - 1 (power of two)
+  int32_t max_level;
+  int32_t n3_root;                // blocks around x3 at level 0 (RootGridSize[2] / n_k)
 };
 
+// key of a block in the topology hash; locations are < 2^19 on every level that can occur
+__host__ __device__ inline unsigned long long block_key(int level, int li, int lj, int lk) {
+  return ((unsigned long long)level << 57) | ((unsigned long long)li << 38) | ((unsigned long long)lj << 19) |
+         (unsigned long long)lk;
+}
+__host__ __device__ inline uint32_t block_hash(unsigned long long key) {
+  key ^= key >> 33; key *= 0xff51afd7ed558ccdull; key ^= key >> 33; key *= 0xc4ceb9fe1a85ec53ull; key ^= key >> 33;
+  return (uint32_t)key;
+}
+
 struct RadParams {
-  int32_t model_type, ray_flat, coord, interp;
+  int32_t model_type, ray_flat, coord, interp, block_interp;
   double a, camera_r;
   double camera_x[4];
   int32_t num_freq;

@@ -603,7 +603,8 @@ __device__ __forceinline__ void couple(const RadParams &P, const Coefficients &C
   for (int a = 0; a < 4; a++) s[a] = out[a];
 }
 
-template <int FMAX>
+// BI: inter-block interpolation compiled in (a separate instantiation keeps it out of the common kernel)
+template <int FMAX, bool BI>
 __global__ void __launch_bounds__(kBlock)
 radiate_polarized_kernel(const __grid_constant__ RadArgs A, const __grid_constant__ RadParams P) {
   extern __shared__ double smem_bounds[];
@@ -689,7 +690,7 @@ radiate_polarized_kernel(const __grid_constant__ RadArgs A, const __grid_constan
     else if (rad::geometric_cut(P, x, y, z, r))
       st = rad::kSampleCut;
     else
-      st = rad::sample_grid(P, G, bounds_s, x, y, z, r, inv_r, cache, pr, si);
+      st = rad::sample_grid<BI>(P, G, bounds_s, x, y, z, r, inv_r, cache, pr, si);
     if (st == rad::kSampleNan) {
       float qn = nanf("");
       pr.rho = pr.pgas = pr.kappa = pr.uu1 = pr.uu2 = pr.uu3 = pr.bb1 = pr.bb2 = pr.bb3 = qn;
@@ -898,7 +899,10 @@ cudaError_t launch_fmax(const RadArgs &A, const RadParams &P, cudaStream_t strea
   unsigned grid = (unsigned)((A.rays + kBlock - 1) / kBlock);
   size_t smem = 0;
   if ((size_t)A.grid.n_b * 6 * sizeof(double) <= 48 * 1024) smem = (size_t)A.grid.n_b * 6 * sizeof(double);
-  radiate_polarized_kernel<FMAX><<<grid, kBlock, smem, stream>>>(A, P);
+  if (P.block_interp)
+    radiate_polarized_kernel<FMAX, true><<<grid, kBlock, smem, stream>>>(A, P);
+  else
+    radiate_polarized_kernel<FMAX, false><<<grid, kBlock, smem, stream>>>(A, P);
   return cudaGetLastError();
 }
 

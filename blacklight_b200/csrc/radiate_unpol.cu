@@ -151,8 +151,8 @@ __device__ __forceinline__ void formula_fluid(const RadParams &P, double x, doub
   n_n0 = exp(-0.5 * (r * r / (P.formula_r0 * P.formula_r0) + P.formula_h * P.formula_h * cth * cth));
 }
 
-// LEAN: only the light image is requested (no auxiliary images, no rendering) -- the common case gets a
-// kernel without the dead register state of the rest.
+// LEAN: only the light image is requested (no auxiliary images, no rendering, no inter-block interpolation)
+// -- the common case gets a kernel without the dead register state of the rest.
 template <int FMAX, bool SIM, bool LEAN>
 __global__ void __launch_bounds__(kBlock, (FMAX <= 4 ? BL_RAD_MINB : 2))
 radiate_unpolarized_kernel(const __grid_constant__ RadArgs A, const __grid_constant__ RadParams P) {
@@ -252,7 +252,7 @@ radiate_unpolarized_kernel(const __grid_constant__ RadArgs A, const __grid_const
       else if (rad::geometric_cut(P, x, y, z, r))
         st = rad::kSampleCut;
       else
-        st = rad::sample_grid(P, G, bounds_s, x, y, z, r, inv_r, cache, pr, si);
+        st = rad::sample_grid<!LEAN>(P, G, bounds_s, x, y, z, r, inv_r, cache, pr, si);
       if (A.taps.nan_) {
         size_t ti = (size_t)m * A.taps.S + n_ref;
         A.taps.nan_[ti] = st == rad::kSampleNan;
@@ -426,7 +426,7 @@ cudaError_t launch_fmax(const RadArgs &A, const RadParams &P, cudaStream_t strea
   const bool lean = P.image_light && !(P.image_time || P.image_length || P.image_lambda || P.image_emission ||
                                        P.image_tau || P.image_lambda_ave || P.image_emission_ave || P.image_tau_int ||
                                        P.image_crossings) &&
-                    !(sim && A.render != nullptr && P.render_num_images > 0);
+                    !(sim && A.render != nullptr && P.render_num_images > 0) && !(sim && P.block_interp);
   unsigned grid = (unsigned)((A.rays + kBlock - 1) / kBlock);
   size_t smem = 0;
   if (sim && (size_t)A.grid.n_b * 6 * sizeof(double) <= 48 * 1024) smem = (size_t)A.grid.n_b * 6 * sizeof(double);

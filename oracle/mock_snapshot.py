@@ -163,7 +163,7 @@ def write_athdf(path, grid, time=0.0):
         _attribute('RootGridSize', np.array([n_r, n_th, n_ph], np.int32)),
         _attribute('NumMeshBlocks', np.int32(n_b)),
         _attribute('MeshBlockSize', np.array([grid['n_i'], grid['n_j'], grid['n_k']], np.int32)),
-        _attribute('MaxLevel', np.int32(0)), _attribute('NumVariables', np.array([5, 3], np.int32)),
+        _attribute('MaxLevel', np.int32(int(np.max(grid['levels'])))), _attribute('NumVariables', np.array([5, 3], np.int32)),
         _attribute('DatasetNames', np.array([b'prim', b'B'], dtype='S21')),
         _attribute('VariableNames', np.array([b'rho', b'press', b'vel1', b'vel2', b'vel3', b'Bcc1', b'Bcc2', b'Bcc3'], dtype='S21'))]
 
@@ -236,8 +236,54 @@ def grid_view_arrays(grid):
         n_3_root=grid['root_size'][2])
 
 
-def make_mock(path=None, blocks=(1, 1, 1), **kwargs):
-    grid = to_blocks(mock_fields(**kwargs), blocks)
+def to_blocks_amr(n_r, n_th, n_ph, blocks, refine, **kwargs):
+    """Two-level mesh: the root grid of `blocks` MeshBlocks at level 0, with the root blocks for which
+    refine(bi, bj, bk) is true replaced by their 8 children at level 1 (same cells per block, half the spacing).
+    Both levels are independent evaluations of the same closed-form model (mock_fields) at their own cell
+    centres -- what an AMR code would produce for a smooth field.  Exercises the inter-block interpolation
+    (reference simulation_sampling.cpp:1068-1321) across same-level, coarser and finer neighbours."""
+    coarse = to_blocks(mock_fields(n_r=n_r, n_th=n_th, n_ph=n_ph, **kwargs), blocks)
+    fine = to_blocks(mock_fields(n_r=2 * n_r, n_th=2 * n_th, n_ph=2 * n_ph, **kwargs),
+                     tuple(2 * b for b in blocks))
+    fine_id = {tuple(int(v) for v in loc): b for b, loc in enumerate(fine['locations'])}
+    keys = ('x1f', 'x2f', 'x3f', 'x1v', 'x2v', 'x3v')
+    rows = {k: [] for k in keys}
+    prims, levels, locs = [], [], []
+    for b, loc in enumerate(coarse['locations']):
+        bi, bj, bk = (int(v) for v in loc)
+        if refine(bi, bj, bk):
+            for dk in (0, 1):
+                for dj in (0, 1):
+                    for di in (0, 1):
+                        child = (2 * bi + di, 2 * bj + dj, 2 * bk + dk)
+                        fb = fine_id[child]
+                        for k in keys:
+                            rows[k].append(fine[k][fb])
+                        prims.append(fine['prim'][:, fb])
+                        levels.append(1)
+                        locs.append(child)
+        else:
+            for k in keys:
+                rows[k].append(coarse[k][b])
+            prims.append(coarse['prim'][:, b])
+            levels.append(0)
+            locs.append((bi, bj, bk))
+    out = dict(n_b=len(levels), n_i=coarse['n_i'], n_j=coarse['n_j'], n_k=coarse['n_k'])
+    for k in keys:
+        out[k] = np.stack(rows[k]).astype(np.float32)
+    out['prim'] = np.stack(prims, axis=1).astype(np.float32)
+    out['levels'] = np.array(levels, np.int32)
+    out['locations'] = np.array(locs, np.int64)
+    out['root_size'] = coarse['root_size']
+    return out
+
+
+def make_mock(path=None, blocks=(1, 1, 1), refine=None, **kwargs):
+    if refine is not None:
+        n_r, n_th, n_ph = kwargs.pop('n_r', 77), kwargs.pop('n_th', 64), kwargs.pop('n_ph', 128)
+        grid = to_blocks_amr(n_r, n_th, n_ph, blocks, refine, **kwargs)
+    else:
+        grid = to_blocks(mock_fields(**kwargs), blocks)
     if path is not None:
         write_athdf(path, grid)
     return grid
