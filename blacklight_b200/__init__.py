@@ -73,7 +73,7 @@ def load_library():
         'bl_selftest_division': (i32, [vp, ctypes.c_uint64, i64, ctypes.POINTER(i64)]),
         'blh_last_error': (ctypes.c_char_p, []), 'blh_config_from_input': (i32, [ctypes.c_char_p, ctypes.POINTER(vp)]),
         'blh_config_free': (None, [vp]), 'blh_config_params': (vp, [vp]), 'blh_config_num_runs': (i32, [vp]),
-        'blh_config_set_device': (None, [vp, i32, i64]), 'blh_camera_frame': (i32, [vp, vp]),
+        'blh_config_set_device': (None, [vp, i32, i64]), 'blh_config_set_level0_block_major': (None, [vp, i32]), 'blh_camera_frame': (i32, [vp, vp]),
         'blh_camera_root': (i64, [vp, vp, vp, vp]),
         'blh_camera_refined': (i64, [vp, i32, vp, vp, i64, vp, vp, vp, vp]),
         'blh_run_input_file': (i32, [ctypes.c_char_p, i32, i32, vp]),
@@ -117,6 +117,10 @@ class Config:
         if getattr(self, '_h', None) and _lib is not None:
             _lib.blh_config_free(self._h)
             self._h = None
+
+    def set_level0_block_major(self, on=True):
+        """Level-0 rays will be handed over block by block (sharded adaptive runs); set before Context()."""
+        _lib.blh_config_set_level0_block_major(self._h, 1 if on else 0)
 
     @property
     def params_ptr(self):

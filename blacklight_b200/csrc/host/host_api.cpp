@@ -50,6 +50,10 @@ void blh_config_set_device(blh_config *c, int device, int64_t tile_rays) {
   c->cfg.params.tile_rays = tile_rays;
 }
 
+void blh_config_set_level0_block_major(blh_config *c, int block_major) {
+  if (c) c->cfg.params.level0_block_major = block_major != 0;
+}
+
 int blh_camera_frame(const blh_config *c, double out[28]) {
   if (!c || !out) { g_error = "null argument"; return 1; }
   const blh::CameraFrame &f = c->cfg.frame;

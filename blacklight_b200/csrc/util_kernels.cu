@@ -80,12 +80,13 @@ __global__ void refine_kernel(const double *__restrict__ image, int64_t stride, 
   // pixel (row i, column j) of this block
   int root_blocks = P.camera_resolution / bs;
   int64_t row0 = 0, col0 = 0;
-  if (level == 0) {
+  const bool raster = level == 0 && !P.level0_block_major;
+  if (raster) {
     row0 = block / root_blocks * bs;
     col0 = block % root_blocks * bs;
   }
   auto at = [&](int i, int j) -> double {
-    if (level == 0) return plane[(row0 + i) * (int64_t)P.camera_resolution + col0 + j];
+    if (raster) return plane[(row0 + i) * (int64_t)P.camera_resolution + col0 + j];
     return plane[block * (int64_t)bs * bs + (int64_t)i * bs + j];
   };
   for (int t = threadIdx.x; t < bs * bs; t += blockDim.x) {

@@ -125,6 +125,10 @@ typedef struct bl_params {
   /* B200 knobs (new, optional; 0 = default) */
   int32_t device;                 /* CUDA device ordinal */
   int64_t tile_rays;              /* rays traced per wave; 0 = sized from free HBM */
+  int32_t level0_block_major;     /* 1: level-0 rays are given block by block (m = block*bs^2 + row*bs + col, like the
+                                   * refined levels) instead of as the full raster -- lets the root blocks of an
+                                   * adaptive image be sharded over GPUs; affects only
+                                   * bl_refine_level's addressing of level 0 */
 } bl_params;
 
 /* Host view of one snapshot exactly as SimulationReader leaves it

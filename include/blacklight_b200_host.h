@@ -24,6 +24,8 @@ const bl_params *blh_config_params(const blh_config *cfg);   /* owned by cfg; ca
 int blh_config_num_runs(const blh_config *cfg);
 /* B200 knobs of bl_params: CUDA device ordinal and rays per wave (0 = sized from free HBM) */
 void blh_config_set_device(blh_config *cfg, int device, int64_t tile_rays);
+/* bl_params.level0_block_major (sharded adaptive runs) */
+void blh_config_set_level0_block_major(blh_config *cfg, int block_major);
 /* cam_x, u_con, u_cov, norm_con, norm_con_c, hor_con_c, vert_con_c: 7 x 4 doubles */
 int blh_camera_frame(const blh_config *cfg, double out[28]);
 /* pos, dir: (res*res,4); factor: (res*res).  Returns the number of rays. */

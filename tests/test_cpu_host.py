@@ -208,3 +208,71 @@ def test_row_sharding_and_gather_world_size_2():
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=10) is True
+
+
+class _FakeConfig:
+    """Stands in for blacklight_b200.Config in the sharded-adaptive host logic test: an 8x8 image of 2x2 blocks."""
+    resolution, block_size = 8, 2
+
+    def camera_root(self):
+        m = np.arange(64, dtype=np.float64)
+        return np.stack([m, m, m, m], 1), np.stack([-m, m, m, m], 1), m.copy()
+
+    def camera_refined(self, level, parent_locs, flags):
+        kids = []
+        for (v, u), f in zip(parent_locs, flags):
+            if f:
+                kids += [(2 * v, 2 * u), (2 * v, 2 * u + 1), (2 * v + 1, 2 * u), (2 * v + 1, 2 * u + 1)]
+        locs = np.array(kids, np.int32).reshape(-1, 2)
+        n = len(locs) * 4
+        tag = 1000.0 * level + (locs[:, 0].repeat(4) * 64 + locs[:, 1].repeat(4)) * 4.0 + np.tile(np.arange(4.0), len(locs))
+        return locs, np.stack([tag] * 4, 1), np.stack([-tag] * 4, 1), tag.copy()
+
+
+class _FakeContext:
+    """"Image" of a ray = its momentum factor (so assembly order is checkable); refine blocks whose first
+    pixel's tag is a multiple of 3."""
+
+    def trace_level(self, level, pos, dirs, fac):
+        self.fac = fac
+        return {'num_bad_geodesics': 0}
+
+    def radiate_level(self, level, num_render=0):
+        return self.fac[None, :].copy(), None, {'num_samples': len(self.fac)}
+
+    def refine_level(self, level, locs):
+        f = (np.round(self.fac.reshape(len(locs), -1)[:, 0]) % 3 == 0).astype(np.uint8)
+        return f, int(f.sum())
+
+
+def _adaptive_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from blacklight_b200 import multigpu
+    dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%d' % port, rank=rank, world_size=world)
+    out = multigpu.run_distributed(multigpu.adaptive_worker(_FakeConfig(), _FakeContext(), rank, world, 2), rank, world)
+    if rank == 0:
+        q.put([(L['locs'].tolist(), L['image'].tolist()) for L in out])
+    dist.destroy_process_group()
+
+
+def test_adaptive_block_sharding_world_size_2_matches_single_rank():
+    """Host logic of blacklight_b200/multigpu.py over a gloo group of 2: flag all-gather, identical child lists,
+    image gather and assembly -- against the same generator run as a single rank in this process."""
+    import torch.multiprocessing as mp
+    from blacklight_b200 import multigpu
+    single = multigpu.run_local([multigpu.adaptive_worker(_FakeConfig(), _FakeContext(), 0, 1, 2)])[0]
+    assert len(single) == 3 and np.array_equal(single[0]['image'][0], np.arange(64.0))
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 31000 + os.getpid() % 2000
+    procs = [ctx.Process(target=_adaptive_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert len(got) == len(single)
+    for (locs, image), L in zip(got, single):
+        assert np.array_equal(np.array(locs).reshape(-1, 2), L['locs'])
+        assert np.array_equal(np.array(image), L['image'])

@@ -348,6 +348,48 @@ def test_adaptive_drop_in(gpu, tmp_path):
         assert v <= PIXEL_TOL, k
 
 
+@pytest.mark.parametrize('world', [1, 3])
+def test_adaptive_sharded_over_ranks(world, gpu, tmp_path):
+    """example_adaptive with the blocks of every level (root level included) dealt round-robin over `world` ranks
+    (blacklight_b200/multigpu.py; the ranks are stepped in lock step inside this process, each with its own
+    context): refinement flags, child block order and per-level images must not depend on the number of ranks
+    and must match the reference."""
+    from blacklight_b200 import multigpu
+    base, over, mock = CASES['adaptive_32']
+    gold = dict(np.load(os.path.join(GOLDEN, 'adaptive_32.npz')))
+    case = Case(tmp_path, base, over, mock=mock)
+    max_level = int(case.kv['adaptive_max_level'])
+    ctxs, workers = [], []
+    for rank in range(world):
+        cfg = case.config()
+        cfg.set_level0_block_major(True)
+        ctx = bl.Context(cfg)
+        ctx.upload_grid(case.grid_arrays())
+        ctxs.append(ctx)
+        workers.append(multigpu.adaptive_worker(cfg, ctx, rank, world, max_level))
+    levels = multigpu.run_local(workers)[0]
+    for ctx in ctxs:
+        ctx.close()
+    assert len(levels) - 1 == int(gold['adaptive_num_levels'][0])
+    assert np.array_equal(levels[1]['locs'], gold['adaptive_block_locs_1'])
+    res, bs = 32, int(case.kv['adaptive_block_size'])
+    root = image_arrays(case, levels[0]['image'], res)
+    assert rel_err(root['I_nu'], gold['I_nu']) <= PIXEL_TOL
+    assert rel_err(root['tau'], gold['tau']) <= PIXEL_TOL
+    nb1 = len(levels[1]['locs'])
+    I1 = levels[1]['image'][0].reshape(nb1, bs, bs)
+    assert rel_err(I1, gold['adaptive_I_nu_1']) <= PIXEL_TOL
+    # bitwise independence of the rank count: compare against the single-rank run of the same code
+    key = os.path.join(str(tmp_path.parent), 'adaptive_sharded_world1.npz')
+    arrays = {'l%d_%s' % (i, k): L[k] for i, L in enumerate(levels) for k in ('locs', 'image') }
+    if world == 1:
+        np.savez(key, **arrays)
+    elif os.path.exists(key):
+        one = np.load(key)
+        for k, v in arrays.items():
+            assert np.array_equal(one[k], v, equal_nan=True), k
+
+
 def test_division_sqrt_sequences(gpu, tmp_path):
     """The geodesic kernel divides and takes square roots through branch-free instruction sequences with one
     refined reciprocal per shared denominator (csrc/glibc_math.cuh: div_by, sqrt_rn).  Their results must be
