@@ -604,8 +604,11 @@ __device__ __forceinline__ void couple(const RadParams &P, const Coefficients &C
 }
 
 // BI: inter-block interpolation compiled in (a separate instantiation keeps it out of the common kernel)
+#ifndef BL_POL_MINB
+#define BL_POL_MINB 2  // resident CTAs per SM the kernel is register-capped for
+#endif
 template <int FMAX, bool BI>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, BL_POL_MINB)
 radiate_polarized_kernel(const __grid_constant__ RadArgs A, const __grid_constant__ RadParams P) {
   extern __shared__ double smem_bounds[];
   const GridDev &G = A.grid;

@@ -1,3 +1,3 @@
-set -x
-timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -4
-timeout 300 python bench.py --workload polarized --resolution 512 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_pol512.json 2> gpurun_out/bench_pol512.err
+for v in p3 p4; do
+  BLACKLIGHT_B200_LIB=$PWD/gpurun_tmp/lib_$v.so timeout 300 python bench.py --workload polarized --resolution 512 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_$v.json 2> gpurun_out/bench_$v.err
+done
