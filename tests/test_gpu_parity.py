@@ -403,3 +403,34 @@ def test_division_sqrt_sequences(gpu, tmp_path):
             assert ctx.selftest_division(1 << 30, seed=seed) == 0
     finally:
         ctx.close()
+
+
+def test_full_resolution_window_against_reference(gpu, tmp_path):
+    """Parity at a resolution the reference cannot hold in memory as a full frame: a coarse
+    root image whose forced refinement region is refined twice makes the reference trace EXACTLY the pixel rays
+    that a 4x finer full frame has inside that window (same u_ind/v_ind expression, camera.cpp:393-396 vs
+    :476-479).  The CUDA path renders the fine full frame in one piece; its window must match the reference's
+    level-2 blocks pixel by pixel.  (Here 32^2 root -> 128^2 frame; the recipe is resolution independent.)"""
+    if not os.path.exists(REF_BIN):
+        pytest.skip('oracle/_ref/blacklight not present')
+    root, bs, levels = 32, 8, 2
+    fine = root * 2 ** levels
+    over = {'camera_resolution': root, 'image_polarization': 'false', 'image_tau': 'false',
+            'adaptive_max_level': levels, 'adaptive_block_size': bs, 'adaptive_num_regions': 1,
+            'adaptive_region_1_level': levels, 'adaptive_region_1_x_min': '-4.0', 'adaptive_region_1_x_max': '7.0',
+            'adaptive_region_1_y_min': '-5.0', 'adaptive_region_1_y_max': '2.0',
+            'adaptive_val_frac': '-1.0', 'adaptive_abs_grad_frac': '-1.0', 'adaptive_rel_grad_frac': '-1.0',
+            'adaptive_abs_lapl_frac': '-1.0', 'adaptive_rel_lapl_frac': '-1.0'}
+    case = Case(tmp_path / 'ref', 'adaptive.input', over)
+    ref = case.run_reference(checkpoints=False)['npz']
+    assert int(ref['adaptive_num_levels'][0]) == levels
+    locs, blocks = ref['adaptive_block_locs_%d' % levels], ref['adaptive_I_nu_%d' % levels]
+    assert len(locs) > 0 and blocks.shape[1:] == (bs, bs)
+    full_over = {k: v for k, v in over.items() if not k.startswith('adaptive_')}
+    full_over.update({'camera_resolution': fine, 'adaptive_max_level': 0})
+    full_case = Case(tmp_path / 'gpu', 'adaptive.input', full_over)
+    cfg, ctx, image, _, _ = run_gpu_level0(full_case)
+    frame = image[0].reshape(fine, fine)
+    window = np.stack([frame[v * bs:(v + 1) * bs, u * bs:(u + 1) * bs] for v, u in locs])
+    assert rel_err(window, blocks) <= PIXEL_TOL
+    ctx.close()
