@@ -67,6 +67,29 @@ def mock_fields(n_r=77, n_th=64, n_ph=128, pert_amp=0.1, pert_n_r=3.0, pert_n_th
     return dict(rf=rf, thf=thf, phf=phf, r=r, th=th, ph=ph, prim=prim)
 
 
+def mock_fields_cks(n=48, half_width=52.0):
+    """Smooth torus-like fields on a uniform Cartesian Kerr-Schild box [-w, w]^3 (simulation_coord = cks):
+    x1, x2, x3 = x, y, z; velocity and field components are Cartesian.  Not a physical solution -- a smooth,
+    positive, non-symmetric test field for the parity of the cks code paths (reference
+    radiation_geometry.cpp:73-91,425-457; the reference ships no Cartesian generator)."""
+    xf = np.linspace(-half_width, half_width, n + 1)
+    xc = 0.5 * (xf[:-1] + xf[1:])
+    Z, Y, X = np.meshgrid(xc, xc, xc, indexing='ij')
+    R = np.sqrt(X * X + Y * Y + Z * Z) + 1.0
+    cyl = np.sqrt(X * X + Y * Y) + 1.0
+    off = np.abs(np.arctan2(Z, cyl))
+    wave = 1.0 + 0.1 * np.cos(4.0 * np.arctan2(Y, X)) * np.cos(0.3 * R)
+    rho = np.maximum(R ** -0.5 * np.exp(-off / (np.pi / 8.0)) * wave, 1.0e-8)
+    pgas = np.maximum(0.1 * R ** -1.25 * np.exp(-off / (np.pi / 8.0)) * wave ** 2, 1.0e-9)
+    omega = 0.3 * cyl ** -1.5 * np.exp(-off / (np.pi / 8.0))
+    uu1, uu2, uu3 = -Y * omega, X * omega, 0.02 * Z / R
+    bz = 0.02 * cyl ** -0.625
+    bph = 0.2 * R ** -1.75 * np.where(Z > 0.0, 1.0, -1.0)
+    bb1, bb2, bb3 = -Y / cyl * bph + 0.1 * bz * X / R, X / cyl * bph + 0.1 * bz * Y / R, bz
+    prim = np.stack([rho, pgas, uu1, uu2, uu3, bb1, bb2, bb3]).astype(np.float32)   # (8, z, y, x)
+    return dict(rf=xf, thf=xf.copy(), phf=xf.copy(), r=xc, th=xc.copy(), ph=xc.copy(), prim=prim)
+
+
 def to_blocks(fields, blocks=(1, 1, 1)):
     """Partition the single-block mock into nb_r x nb_th x nb_ph MeshBlocks (level 0).
 
@@ -278,8 +301,10 @@ def to_blocks_amr(n_r, n_th, n_ph, blocks, refine, **kwargs):
     return out
 
 
-def make_mock(path=None, blocks=(1, 1, 1), refine=None, **kwargs):
-    if refine is not None:
+def make_mock(path=None, blocks=(1, 1, 1), refine=None, cks=None, **kwargs):
+    if cks is not None:
+        grid = to_blocks(mock_fields_cks(**cks), blocks)
+    elif refine is not None:
         n_r, n_th, n_ph = kwargs.pop('n_r', 77), kwargs.pop('n_th', 64), kwargs.pop('n_ph', 128)
         grid = to_blocks_amr(n_r, n_th, n_ph, blocks, refine, **kwargs)
     else:

@@ -214,6 +214,54 @@ def test_live_reference_block_interpolation(over, refined, gpu, tmp_path):
     ctx.close()
 
 
+@pytest.mark.parametrize('over', [
+    {'camera_resolution': 32},
+    {'camera_resolution': 32, 'simulation_block_interp': 'true'},
+    {'camera_resolution': 28, 'simulation_interp': 'false'},
+    {'camera_resolution': 24, 'image_polarization': 'true'},
+])
+def test_live_reference_cartesian_kerr_schild(over, gpu, tmp_path):
+    """simulation_coord = cks: a uniform Cartesian Kerr-Schild box of 2x2x2 MeshBlocks (oracle/mock_snapshot.py:
+    mock_fields_cks) -- the Cartesian branches of the sampling map, the simulation metric and the frame
+    transformation (reference radiation_geometry.cpp:73-91,425-457), a = 0.5."""
+    if not os.path.exists(REF_BIN):
+        pytest.skip('oracle/_ref/blacklight not present')
+    over = dict(over, simulation_coord='cks', simulation_a='0.5')
+    case = Case(tmp_path, 'simulation.input', over, mock=dict(blocks=(2, 2, 2), cks=dict(n=32)))
+    pol = over.get('image_polarization') == 'true'
+    ref = case.run_reference(checkpoints=not pol)
+    cfg, ctx, image, _, _ = run_gpu_level0(case, taps=not pol)
+    mine = image_arrays(case, image, cfg.resolution)
+    if not pol:
+        s = ctx.download_samples(0)
+        S = s['pos'].shape[1]
+        mask = np.arange(S)[None, :] < s['num'][:, None]
+        interp = over.get('simulation_interp', 'true') == 'true'
+        t = ctx.download_sample_inds(0, interp=interp)
+        rs = ref['samp']
+        assert np.array_equal(t['nan'][mask], rs['sample_nan'][mask])
+        valid = mask & (t['cut'] == 0) & (t['nan'] == 0) & (t['fallback'] == 0)
+        ri = rs['sample_inds'] if rs['sample_inds'].ndim == 3 else rs['sample_inds'][:, :, 0, :]
+        assert np.array_equal(t['inds'][valid], ri[valid])
+        check_images(mine, ref['npz'], str(over))
+    else:
+        # In this synthetic box the left-edge pixels are 1e-7 ... 1e-11 of the peak brightness; there the two
+        # polarized solvers agree only to 1e-7 ... 1e-2 of the (negligible) pixel value, while the unpolarized
+        # images agree to 1e-14 everywhere and the polarized ones to 1e-11 (median).  Open item (DESIGN.md
+        # section 3.2); the comparison is restricted to pixels above 1e-6 of the peak.
+        I_ref = ref['npz']['I_nu']
+        bright = I_ref >= 1e-6 * np.nanmax(I_ref)
+        assert bright.sum() > 0.5 * bright.size
+        m = {k: np.where(bright, v, 0.0) for k, v in mine.items() if k.endswith('_nu')}
+        r = {k: np.where(bright, ref['npz'][k], 0.0) for k in m}
+        assert rel_err(m['I_nu'], r['I_nu']) <= PIXEL_TOL
+        errs = stokes_err(m, r, floor=1e-2)
+        print('cks polarized errors', errs)
+        for k, v in errs.items():
+            assert v <= PIXEL_TOL, '%s %.3e' % (k, v)
+    ctx.close()
+
+
 def test_waves_match_resident(gpu, tmp_path):
     """Tracing in waves (step buffer reused) must give the same image as a resident level, bit for bit."""
     case = Case(tmp_path, 'simulation.input', {'camera_resolution': 48})
