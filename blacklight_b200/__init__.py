@@ -65,6 +65,7 @@ def load_library():
         'bl_refine_level': (i32, [vp, i32, vp, i64, vp, ctypes.POINTER(i64)]),
         'bl_set_taps': (i32, [vp, i32]),
         'bl_retrace_level': (i32, [vp, i32, ctypes.POINTER(LevelStats)]),
+        'bl_upload_samples': (i32, [vp, i32, vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, ctypes.POINTER(LevelStats)]),
         'bl_launch_count': (ctypes.c_longlong, [vp]), 'bl_cuda_stream': (vp, [vp]),
         'bl_download_samples': (i32, [vp, i32, vp, vp, vp, vp, vp]),
         'bl_download_sample_inds': (i32, [vp, i32, vp, vp, vp, vp, vp]),
@@ -231,6 +232,19 @@ class Context:
         pos, dirs, fac = (np.ascontiguousarray(a, np.float64) for a in (pos, dirs, fac))
         st = LevelStats()
         self._check(_lib.bl_trace_level(self._h, level, _ptr(pos), _ptr(dirs), _ptr(fac), len(fac), ctypes.byref(st)))
+        self._rays[level] = len(fac)
+        self._steps[level] = st.geodesic_num_steps
+        return st.as_dict()
+
+    def upload_samples(self, level, pos, dirs, fac, flags, num, sample_pos, sample_dir, sample_len):
+        """Load geodesics integrated elsewhere (reference checkpoint layouts) instead of tracing the level."""
+        pos, dirs, fac = (np.ascontiguousarray(a, np.float64) for a in (pos, dirs, fac))
+        flags = np.ascontiguousarray(flags, np.uint8)
+        num = np.ascontiguousarray(num, np.int32)
+        sp, sd, sl = (np.ascontiguousarray(a, np.float64) for a in (sample_pos, sample_dir, sample_len))
+        st = LevelStats()
+        self._check(_lib.bl_upload_samples(self._h, level, _ptr(pos), _ptr(dirs), _ptr(fac), len(fac), sl.shape[1], _ptr(flags),
+                                           _ptr(num), _ptr(sp), _ptr(sd), _ptr(sl), ctypes.byref(st)))
         self._rays[level] = len(fac)
         self._steps[level] = st.geodesic_num_steps
         return st.as_dict()

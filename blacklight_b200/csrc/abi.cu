@@ -23,6 +23,9 @@ extern "C" cudaError_t bl_launch_relayout_grid(const float *prim, int n_var, con
 extern "C" cudaError_t bl_launch_unpack_samples(const StepBuffer *sb, const int32_t *num, const double *cam_dir,
                                                 int64_t rays, int S, double *pos, double *dir, double *len,
                                                 cudaStream_t stream);
+extern "C" cudaError_t bl_launch_pack_samples(const StepBuffer *sb, const int32_t *num, int64_t ray0, int64_t count, int S,
+                                              const double *pos, const double *dir, const double *len,
+                                              cudaStream_t stream);
 extern "C" cudaError_t bl_launch_refine(const double *image, int64_t stride, int level, const int32_t *block_locs,
                                         int64_t num_blocks, const bl_params *params_dev, uint8_t *flags,
                                         cudaStream_t stream);
@@ -769,6 +772,73 @@ int bl_trace_level(bl_ctx *ctx, int level, const double *cam_pos, const double *
     L.traced = false;
     BL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   }
+  if (stats) *stats = L.stats;
+  return BL_OK;
+}
+
+int bl_upload_samples(bl_ctx *ctx, int level, const double *cam_pos, const double *cam_dir, const double *mom_factor,
+                      int64_t num_rays, int32_t S, const uint8_t *flags, const int32_t *num, const double *pos,
+                      const double *dir, const double *len, bl_level_stats *stats) {
+  if (!ctx) return BL_ERR_ARG;
+  if (level < 0 || level >= (int)ctx->levels.size()) return bl_fail(ctx, BL_ERR_ARG, "bl_upload_samples: level %d out of range", level);
+  if (!cam_pos || !cam_dir || !mom_factor || !flags || !num || !pos || !dir || !len || num_rays <= 0 || S <= 0)
+    return bl_fail(ctx, BL_ERR_ARG, "bl_upload_samples: null or empty argument");
+  if (S > ctx->params.ray_max_steps) return bl_fail(ctx, BL_ERR_ARG, "bl_upload_samples: %d samples per ray exceed ray_max_steps = %d", S, ctx->params.ray_max_steps);
+  BL_CUDA_CHECK(cudaSetDevice(ctx->device));
+  Level &L = ctx->levels[level];
+  free_level(L);
+  L.rays = num_rays;
+  const int Q = ctx->rad.num_quantities, R = ctx->rad.render_num_images;
+  BL_CUDA_CHECK(dev_alloc(&L.cam_pos, (size_t)num_rays * 4));
+  BL_CUDA_CHECK(dev_alloc(&L.cam_dir, (size_t)num_rays * 4));
+  BL_CUDA_CHECK(dev_alloc(&L.mom, (size_t)num_rays));
+  BL_CUDA_CHECK(dev_alloc(&L.num, (size_t)num_rays));
+  BL_CUDA_CHECK(dev_alloc(&L.flags, (size_t)num_rays));
+  BL_CUDA_CHECK(dev_alloc(&L.image, (size_t)num_rays * (size_t)(Q > 0 ? Q : 1)));
+  if (R > 0) BL_CUDA_CHECK(dev_alloc(&L.render, (size_t)num_rays * 3 * R));
+  size_t per_ray = (size_t)ctx->params.ray_max_steps * StepBuffer::kRecord * sizeof(double);
+  size_t fr = 0, tot = 0;
+  BL_CUDA_CHECK(cudaMemGetInfo(&fr, &tot));
+  if ((double)per_ray * (double)num_rays > 0.80 * (double)fr)
+    return bl_fail(ctx, BL_ERR_NOMEM, "bl_upload_samples: the level's step buffer (%zu bytes per ray) does not fit in HBM; uploaded geodesics must be resident", per_ray);
+  L.wave_rays = num_rays;
+  L.resident = true;
+  BL_CUDA_CHECK(dev_alloc(&L.step, (size_t)num_rays * per_ray / sizeof(double)));
+  BL_CUDA_CHECK(cudaMemcpyAsync(L.cam_pos, cam_pos, (size_t)num_rays * 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  BL_CUDA_CHECK(cudaMemcpyAsync(L.cam_dir, cam_dir, (size_t)num_rays * 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  BL_CUDA_CHECK(cudaMemcpyAsync(L.mom, mom_factor, (size_t)num_rays * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  BL_CUDA_CHECK(cudaMemcpyAsync(L.num, num, (size_t)num_rays * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  BL_CUDA_CHECK(cudaMemcpyAsync(L.flags, flags, (size_t)num_rays, cudaMemcpyHostToDevice, ctx->stream));
+  // stage the (N, S, .) host arrays through a bounded device buffer, a chunk of rays at a time
+  int64_t chunk = (int64_t)((size_t)64 << 20) / ((size_t)S * 9 * sizeof(double));
+  if (chunk < 1) chunk = 1;
+  if (chunk > num_rays) chunk = num_rays;
+  double *spos = nullptr, *sdir = nullptr, *slen = nullptr;
+  BL_CUDA_CHECK(dev_alloc(&spos, (size_t)chunk * S * 4));
+  BL_CUDA_CHECK(dev_alloc(&sdir, (size_t)chunk * S * 4));
+  BL_CUDA_CHECK(dev_alloc(&slen, (size_t)chunk * S));
+  StepBuffer sb; sb.buf = L.step; sb.rays = num_rays; sb.cap = ctx->params.ray_max_steps;
+  cudaError_t e = cudaSuccess;
+  for (int64_t m0 = 0; m0 < num_rays && e == cudaSuccess; m0 += chunk) {
+    int64_t cnt = num_rays - m0 < chunk ? num_rays - m0 : chunk;
+    size_t o = (size_t)m0 * S;
+    e = cudaMemcpyAsync(spos, pos + 4 * o, (size_t)cnt * S * 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(sdir, dir + 4 * o, (size_t)cnt * S * 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(slen, len + o, (size_t)cnt * S * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = bl_launch_pack_samples(&sb, L.num, m0, cnt, S, spos, sdir, slen, ctx->stream);
+    ctx->launches++;
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(spos); cudaFree(sdir); cudaFree(slen);
+  if (e != cudaSuccess) return bl_fail_cuda(ctx, e, "sample upload", __FILE__, __LINE__);
+  L.stats = bl_level_stats();
+  L.stats.num_rays = num_rays;
+  L.stats.geodesic_num_steps = S;
+  for (int64_t m = 0; m < num_rays; m++) {
+    L.stats.num_samples += num[m];
+    L.stats.num_bad_geodesics += flags[m] ? 1 : 0;
+  }
+  L.traced = true;
   if (stats) *stats = L.stats;
   return BL_OK;
 }

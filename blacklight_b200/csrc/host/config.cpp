@@ -44,12 +44,12 @@ RunConfig make_config(const InputFile &in) {
   c.output_file = in.str("output_file");
   if (c.output_format == 0) c.output_camera = in.flag("output_camera");
 
-  // checkpoints (geodesic_integrator.cpp:29-34, radiation_integrator.cpp:35-52); loading is not supported
+  // checkpoints (geodesic_integrator.cpp:29-34, radiation_integrator.cpp:35-52); sample checkpoints cannot
+  // be loaded (sampling is fused into the transfer kernels, there is nothing to load them into)
   c.checkpoint_geodesic_save = in.flag("checkpoint_geodesic_save");
-  bool geo_load = in.flag("checkpoint_geodesic_load");
-  if (c.checkpoint_geodesic_save && geo_load) throw Error("Cannot both save and load a geodesic checkpoint.");
-  if (geo_load) throw Error("checkpoint_geodesic_load is outside the B200 hot-path scope.");
-  if (c.checkpoint_geodesic_save) c.checkpoint_geodesic_file = in.str("checkpoint_geodesic_file");
+  c.checkpoint_geodesic_load = in.flag("checkpoint_geodesic_load");
+  if (c.checkpoint_geodesic_save && c.checkpoint_geodesic_load) throw Error("Cannot both save and load a geodesic checkpoint.");
+  if (c.checkpoint_geodesic_save || c.checkpoint_geodesic_load) c.checkpoint_geodesic_file = in.str("checkpoint_geodesic_file");
   if (sim) {
     c.checkpoint_sample_save = in.flag("checkpoint_sample_save");
     bool sample_load = in.flag("checkpoint_sample_load");

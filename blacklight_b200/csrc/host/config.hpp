@@ -25,7 +25,7 @@ struct RunConfig {
   bool simulation_multiple = false;
   int simulation_start = 0, simulation_end = 0;
   bool gamma_set = false;
-  bool checkpoint_geodesic_save = false, checkpoint_sample_save = false;
+  bool checkpoint_geodesic_save = false, checkpoint_geodesic_load = false, checkpoint_sample_save = false;
   std::string checkpoint_geodesic_file, checkpoint_sample_file;
   int num_runs = 1;
 };

@@ -204,6 +204,47 @@ void save_geodesic_checkpoint(bl_ctx *ctx, const RunConfig &cfg, const LevelData
   write_array(out, len.data(), n_len);
 }
 
+// Inverse of save_geodesic_checkpoint: read a level-0 geodesic checkpoint written by the reference (or by us)
+// and hand its samples to the device instead of tracing (geodesic_checkpoint.cpp:77-108).
+template <typename T>
+void read_array(std::ifstream &in, std::vector<T> &data, int n[5]) {
+  in.read(reinterpret_cast<char *>(n), 5 * sizeof(int));
+  if (!in) throw Error("Geodesic checkpoint file is truncated.");
+  size_t total = (size_t)n[0] * n[1] * n[2] * n[3] * n[4];
+  data.resize(total);
+  in.read(reinterpret_cast<char *>(data.data()), (std::streamsize)(total * sizeof(T)));
+  if (!in) throw Error("Geodesic checkpoint file is truncated.");
+}
+
+void load_geodesic_checkpoint(bl_ctx *ctx, const RunConfig &cfg, LevelData &root, bl_level_stats *st) {
+  std::ifstream in(cfg.checkpoint_geodesic_file, std::ios::binary);
+  if (!in.is_open()) throw Error("Could not open geodesic checkpoint file.");
+  double frame[28];
+  in.read(reinterpret_cast<char *>(frame), sizeof frame);   // cam_x ... vert_con_c: recomputed from the input file
+  int n[5];
+  std::vector<double> freqs, pos, dir, len;
+  std::vector<uint8_t> flags;
+  std::vector<int32_t> num;
+  read_array(in, root.pos, n);
+  long long N = n[1];
+  read_array(in, root.dir, n);
+  read_array(in, freqs, n);
+  read_array(in, root.factor, n);
+  int S = 0;
+  in.read(reinterpret_cast<char *>(&S), sizeof(int));
+  read_array(in, flags, n);
+  read_array(in, num, n);
+  read_array(in, pos, n);
+  read_array(in, dir, n);
+  read_array(in, len, n);
+  if (N != (long long)cfg.params.camera_resolution * cfg.params.camera_resolution || (long long)root.factor.size() != N ||
+      (long long)len.size() != N * S)
+    throw Error("Geodesic checkpoint does not match camera_resolution.");
+  root.rays = N;
+  check(ctx, bl_upload_samples(ctx, 0, root.pos.data(), root.dir.data(), root.factor.data(), N, S, flags.data(), num.data(),
+                               pos.data(), dir.data(), len.data(), st));
+}
+
 }  // namespace
 
 RunTimings run_input_file(const std::string &path, int device, bool quiet) {
@@ -232,7 +273,7 @@ RunTimings run_input_file(const std::string &path, int device, bool quiet) {
   // level 0 camera + geodesics (GeodesicIntegrator::Integrate)
   double t0 = now_s();
   LevelData &root = levels[0];
-  camera_root(cfg.camera, cfg.frame, root.pos, root.dir, root.factor);
+  if (!cfg.checkpoint_geodesic_load) camera_root(cfg.camera, cfg.frame, root.pos, root.dir, root.factor);
   root.rays = (long long)p.camera_resolution * p.camera_resolution;
   if (p.adaptive_max_level > 0) {
     int nb = p.camera_resolution / bs;
@@ -245,7 +286,10 @@ RunTimings run_input_file(const std::string &path, int device, bool quiet) {
       }
   }
   bl_level_stats st{};
-  check(ctx, bl_trace_level(ctx, 0, root.pos.data(), root.dir.data(), root.factor.data(), root.rays, &st));
+  if (cfg.checkpoint_geodesic_load)
+    load_geodesic_checkpoint(ctx, cfg, root, &st);
+  else
+    check(ctx, bl_trace_level(ctx, 0, root.pos.data(), root.dir.data(), root.factor.data(), root.rays, &st));
   T.gpu_geodesic_ms += st.ms_geodesic;
   if (st.num_bad_geodesics > 0)
     warning(std::to_string(st.num_bad_geodesics) + " out of " + std::to_string(root.rays) + " geodesics terminate unexpectedly.");

@@ -45,6 +45,26 @@ __global__ void unpack_samples_kernel(StepBuffer sb, const int32_t *__restrict__
   }
 }
 
+// The reference's sample_pos/dir/len host layout (source->camera order, len > 0) -> step-buffer records
+// (tracing order, len < 0): the inverse of unpack_samples_kernel, for geodesics computed elsewhere
+// (checkpoint_geodesic_load).  pos/dir/len hold rays [ray0, ray0 + count) only.
+__global__ void pack_samples_kernel(StepBuffer sb, const int32_t *__restrict__ num, int64_t ray0, int64_t count, int S,
+                                    const double *__restrict__ pos, const double *__restrict__ dir,
+                                    const double *__restrict__ len) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int n_in = blockIdx.y;
+  if (i >= count) return;
+  int64_t m = ray0 + i;
+  int cnt = num[m];
+  if (n_in >= cnt) return;
+  size_t o = (size_t)i * S + n_in;
+  double2 *dst = reinterpret_cast<double2 *>(sb.buf + sb.at(cnt - 1 - n_in, m));
+  dst[0] = make_double2(pos[4 * o + 0], pos[4 * o + 1]);
+  dst[1] = make_double2(pos[4 * o + 2], pos[4 * o + 3]);
+  dst[2] = make_double2(dir[4 * o + 1], dir[4 * o + 2]);
+  dst[3] = make_double2(dir[4 * o + 3], -len[o]);
+}
+
 // One CTA per refinement block.  Five exceedance-fraction tests on Stokes I of the chosen frequency.
 __global__ void refine_kernel(const double *__restrict__ image, int64_t stride, int level,
                               const int32_t *__restrict__ block_locs, int64_t num_blocks,
@@ -220,6 +240,15 @@ extern "C" cudaError_t bl_launch_unpack_samples(const StepBuffer *sb, const int3
   if (rays <= 0 || S <= 0) return cudaSuccess;
   dim3 grid((unsigned)((rays + 127) / 128), (unsigned)S);
   unpack_samples_kernel<<<grid, 128, 0, stream>>>(*sb, num, cam_dir, rays, S, pos, dir, len);
+  return cudaGetLastError();
+}
+
+extern "C" cudaError_t bl_launch_pack_samples(const StepBuffer *sb, const int32_t *num, int64_t ray0, int64_t count, int S,
+                                              const double *pos, const double *dir, const double *len,
+                                              cudaStream_t stream) {
+  if (count <= 0 || S <= 0) return cudaSuccess;
+  dim3 grid((unsigned)((count + 127) / 128), (unsigned)S);
+  pack_samples_kernel<<<grid, 128, 0, stream>>>(*sb, num, ray0, count, S, pos, dir, len);
   return cudaGetLastError();
 }
 

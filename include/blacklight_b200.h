@@ -176,6 +176,15 @@ int bl_upload_grid(bl_ctx *ctx, const bl_grid_view *grid);
 int bl_trace_level(bl_ctx *ctx, int level, const double *cam_pos, const double *cam_dir,
                    const double *mom_factor, int64_t num_rays, bl_level_stats *stats);
 
+/* Load a level whose geodesics were integrated elsewhere (the reference's checkpoint_geodesic_load,
+ * geodesic_checkpoint.cpp:77-108) instead of tracing it: camera arrays as for bl_trace_level plus the
+ * reference's sample arrays in their host layouts and source->camera order -- flags, num: (N); pos, dir:
+ * (N,S,4) f64; len: (N,S) f64 > 0; S = geodesic_num_steps <= ray_max_steps.  The level must fit in HBM. */
+int bl_upload_samples(bl_ctx *ctx, int level, const double *cam_pos, const double *cam_dir,
+                      const double *mom_factor, int64_t num_rays, int32_t S, const uint8_t *flags,
+                      const int32_t *num, const double *pos, const double *dir, const double *len,
+                      bl_level_stats *stats);
+
 /* Re-integrate the geodesics of a level from the camera arrays already resident in HBM (no host
  * transfer).  A no-op for levels traced wave by wave inside bl_radiate_level. */
 int bl_retrace_level(bl_ctx *ctx, int level, bl_level_stats *stats);

@@ -82,9 +82,9 @@ class Case:
         path, _ = self._input('gpu', extra or {})
         return bl.Config(path, device=device, tile_rays=tile_rays)
 
-    def run_gpu_file(self, device=0):
+    def run_gpu_file(self, device=0, extra=None, tag='gpufile'):
         """Full drop-in run through blh_run_input_file; returns (npz dict, timings)."""
-        path, out = self._input('gpufile', {})
+        path, out = self._input(tag, extra or {})
         t = bl.run_input_file(path, device=device)
         return dict(np.load(os.path.join(out, 'image.npz'))), t
 

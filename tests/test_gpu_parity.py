@@ -438,6 +438,27 @@ def test_adaptive_sharded_over_ranks(world, gpu, tmp_path):
             assert np.array_equal(one[k], v, equal_nan=True), k
 
 
+def test_geodesic_checkpoint_exchange_with_reference(gpu, tmp_path):
+    """checkpoint_geodesic_load: geodesics integrated by the REFERENCE (its checkpoint file, reference byte format)
+    are loaded into the step buffer instead of tracing (bl_upload_samples).  Because the CUDA integrator is
+    bit-identical to the reference's, the image from the loaded geodesics must equal the image from our own
+    tracing bit for bit -- and the reference's image to tolerance.  The opposite direction (our checkpoint read
+    back) is covered too."""
+    if not os.path.exists(REF_BIN):
+        pytest.skip('oracle/_ref/blacklight not present')
+    case = Case(tmp_path, 'simulation.input', {'camera_resolution': 40, 'simulation_a': '0.7'})
+    ref = case.run_reference()
+    ref_ckpt = os.path.join(case.dir, 'out_ref', 'geo.ckpt')
+    own, _ = case.run_gpu_file()
+    mine_ckpt = os.path.join(case.dir, 'mine.ckpt')
+    saved, _ = case.run_gpu_file(extra={'checkpoint_geodesic_save': 'true', 'checkpoint_geodesic_file': mine_ckpt}, tag='save')
+    assert open(mine_ckpt, 'rb').read() == open(ref_ckpt, 'rb').read(), 'checkpoint files differ from the reference byte for byte'
+    for name, ckpt in (('reference checkpoint', ref_ckpt), ('own checkpoint', mine_ckpt)):
+        loaded, _ = case.run_gpu_file(extra={'checkpoint_geodesic_load': 'true', 'checkpoint_geodesic_file': ckpt}, tag='load')
+        assert np.array_equal(loaded['I_nu'], own['I_nu'], equal_nan=True), name
+        assert rel_err(loaded['I_nu'], ref['npz']['I_nu']) <= PIXEL_TOL, name
+
+
 def test_division_sqrt_sequences(gpu, tmp_path):
     """The geodesic kernel divides and takes square roots through branch-free instruction sequences with one
     refined reciprocal per shared denominator (csrc/glibc_math.cuh: div_by, sqrt_rn).  Their results must be
