@@ -159,7 +159,7 @@ def run_reference_arm(args, rank, world):
             'steps': args.steps, 'warmup': args.warmup, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic'}
     if not os.path.exists(REF_BIN):
-        print(json.dumps({'impl': 'reference', 'unavailable': 'oracle/_ref/blacklight was not built (no /root/reference at build time)'}))
+        emit({'impl': 'reference', 'unavailable': 'oracle/_ref/blacklight was not built (no /root/reference at build time)'})
         return
     side = args.cpu_resolution or auto_cpu_resolution(args, threads)
     workdir = tempfile.mkdtemp(prefix='bl_ref_')
@@ -188,12 +188,31 @@ def run_reference_arm(args, rank, world):
                                       'sample': '%dx%d rays of the same camera (rays/s is resolution independent); '
                                                 'reference timers geodesic+sample+image' % (side, side)},
                      'e2e': {'value': value, 'unit': 'rays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}})
-        print(json.dumps(line))
+        emit(line)
     finally:
         shutil.rmtree(workdir, ignore_errors=True)
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """Write the one JSON result line to the process's ORIGINAL stdout (see main)."""
+    data = (json.dumps(line) + '\n').encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
+    # stdout must carry exactly one JSON line: everything else that writes to fd 1 (NCCL's version banner,
+    # library chatter) is sent to stderr for the whole run
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     args = parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -388,7 +407,7 @@ def main():
                 else:
                     line['cpu_baseline'] = {'value': None, 'unit': 'rays/s', 'cores': threads, 'kind': 'reference',
                                             'sample': 'unavailable: oracle/_ref/blacklight not built'}
-            print(json.dumps(line))
+            emit(line)
         ctx.close()
     finally:
         shutil.rmtree(workdir, ignore_errors=True)
