@@ -217,7 +217,7 @@ class Context:
         return out.value
 
     def upload_grid(self, g):
-        """g: dict from oracle.mock_snapshot.grid_view_arrays (or any reader) -- host numpy arrays."""
+        """g: dict from blacklight_b200.mock_snapshot.grid_view_arrays (or any reader) -- host numpy arrays."""
         keep = {k: np.ascontiguousarray(g[k]) for k in ('levels', 'locations', 'x1f', 'x2f', 'x3f', 'x1v', 'x2v', 'x3v', 'prim')}
         assert keep['prim'].dtype == np.float32 and keep['x1f'].dtype == np.float64
         v = GridView()

@@ -1,4 +1,4 @@
-"""Synthetic GRMHD snapshots for the parity tests and bench (TEST INFRASTRUCTURE, not shipped).
+"""Synthetic GRMHD snapshots: the input generator of bench.py and of the parity tests (not on the product path).
 
 Restates the closed-form disk model of the reference's benchmark-input generator
 (reference scripts/generate_mock_simulation.py:24-77, defaults :346-425) -- a power-law torus in

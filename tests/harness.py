@@ -11,8 +11,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'oracle'))
 
 import blacklight_b200 as bl  # noqa: E402
-import mock_snapshot  # noqa: E402
-import refio  # noqa: E402
+from blacklight_b200 import mock_snapshot  # noqa: E402
 
 INPUTS = os.path.join(ROOT, 'tests', 'inputs')
 REF_BIN = os.path.join(ROOT, 'oracle', '_ref', 'blacklight')
@@ -72,6 +71,7 @@ class Case:
         res = {'npz': dict(np.load(os.path.join(out, 'image.npz'))), 'stdout': proc.stdout, 'stderr': proc.stderr}
         res['timers'] = parse_timers(proc.stdout)
         if checkpoints:
+            import refio  # oracle/: checkpoint readers, reference runs only
             res['geo'] = refio.read_geodesic_checkpoint(extra['checkpoint_geodesic_file'])
             if self.sim:
                 res['samp'] = refio.read_sample_checkpoint(extra['checkpoint_sample_file'],

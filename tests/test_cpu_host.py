@@ -158,7 +158,7 @@ int main() {
 def test_mock_snapshot_is_stable_and_readable(tmp_path):
     """The synthetic snapshot generator is deterministic (CRC pinned; it was checked bit-for-bit against the
     reference's scripts/generate_mock_simulation.py) and its .athdf round-trips through our own reader."""
-    import mock_snapshot
+    from blacklight_b200 import mock_snapshot
     grid = mock_snapshot.make_mock(os.path.join(tmp_path, 'm.athdf'), blocks=(7, 2, 4))
     single = mock_snapshot.make_mock(None)
     assert zlib.crc32(single['prim'].tobytes()) == 0x52C06F21

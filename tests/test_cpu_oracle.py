@@ -11,7 +11,7 @@ import blacklight_b200 as bl
 from harness import ROOT, load_input, write_input
 from golden.make_golden import CASES
 
-import mock_snapshot
+from blacklight_b200 import mock_snapshot
 import oracle_lib
 
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')

@@ -221,7 +221,7 @@ def test_live_reference_block_interpolation(over, refined, gpu, tmp_path):
     {'camera_resolution': 24, 'image_polarization': 'true'},
 ])
 def test_live_reference_cartesian_kerr_schild(over, gpu, tmp_path):
-    """simulation_coord = cks: a uniform Cartesian Kerr-Schild box of 2x2x2 MeshBlocks (oracle/mock_snapshot.py:
+    """simulation_coord = cks: a uniform Cartesian Kerr-Schild box of 2x2x2 MeshBlocks (blacklight_b200/mock_snapshot.py:
     mock_fields_cks) -- the Cartesian branches of the sampling map, the simulation metric and the frame
     transformation (reference radiation_geometry.cpp:73-91,425-457), a = 0.5."""
     if not os.path.exists(REF_BIN):
