@@ -47,6 +47,7 @@ struct Level {
   double *image = nullptr;    // device (Q, rays)
   double *render = nullptr;   // device (R,3,rays)
   bl_level_stats stats{};
+  bl_slow_stats slow{};
   // taps (allocated on demand)
   int32_t *tap_inds = nullptr; double *tap_fracs = nullptr; uint8_t *tap_nan = nullptr, *tap_cut = nullptr, *tap_fb = nullptr;
   int32_t tap_S = 0;
@@ -67,6 +68,7 @@ struct bl_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   GeoCounters *counters = nullptr;          // device
   unsigned long long *rad_counter = nullptr;  // device
+  unsigned long long *slow_counters = nullptr;  // device, 8 words (see RadArgs::slow_counters)
   std::vector<Level> levels;
   std::string error;
   bool taps_enabled = false;
@@ -238,6 +240,10 @@ void fill_rad_params(const bl_params &p, RadParams &r) {
   std::memset(&r, 0, sizeof r);
   r.model_type = p.model_type; r.ray_flat = p.ray_flat; r.coord = p.simulation_coord; r.interp = p.simulation_interp;
   r.block_interp = p.simulation_interp && p.simulation_block_interp;
+  r.slow_light = p.model_type == BL_MODEL_SIMULATION && p.slow_light_on;
+  r.slow_interp = r.slow_light && p.slow_interp;
+  r.slow_count = 0;   // set by bl_set_time_window
+  r.extrap_tol = p.extrapolation_tolerance;
   r.a = p.bh_a; r.camera_r = p.camera_r;
   for (int i = 0; i < 4; i++) {
     r.camera_x[i] = p.camera_x[i]; r.camera_u_con[i] = p.camera_u_con[i];
@@ -332,6 +338,9 @@ int validate_params(const bl_params &p) {
   if (p.model_type == BL_MODEL_SIMULATION && p.simulation_coord == BL_COORD_FMKS)
     return bl_fail(nullptr, BL_ERR_UNSUPPORTED, "simulation_coord = fmks is outside the B200 hot-path scope (SURVEY.md section 2)");
   bool sim = p.model_type == BL_MODEL_SIMULATION;
+  if (sim && p.slow_light_on && (p.slow_chunk_size < 2 || p.slow_chunk_size > BL_MAX_SLICES))
+    return bl_fail(nullptr, p.slow_chunk_size < 2 ? BL_ERR_ARG : BL_ERR_UNSUPPORTED,
+                   p.slow_chunk_size < 2 ? "Must have slow_chunk_size be at least 2." : "slow_chunk_size > %d not supported", BL_MAX_SLICES);
   if (!(p.image_light || p.image_time || p.image_length || p.image_lambda || p.image_emission || p.image_tau ||
         (sim && (p.image_lambda_ave || p.image_emission_ave || p.image_tau_int)) || p.image_crossings ||
         (sim && p.render_num_images > 0)))
@@ -394,6 +403,7 @@ int bl_create(const bl_params *params, bl_ctx **out) {
   CREATE_CHECK(dev_alloc(&ctx->params_dev, 1));
   CREATE_CHECK(dev_alloc(&ctx->counters, 1));
   CREATE_CHECK(dev_alloc(&ctx->rad_counter, 1));
+  CREATE_CHECK(dev_alloc(&ctx->slow_counters, 8));
   CREATE_CHECK(cudaMemcpy(ctx->rad_dev, &ctx->rad, sizeof(RadParams), cudaMemcpyHostToDevice));
   CREATE_CHECK(cudaMemcpy(ctx->params_dev, &ctx->params, sizeof(bl_params), cudaMemcpyHostToDevice));
 #undef CREATE_CHECK
@@ -406,7 +416,7 @@ void bl_destroy(bl_ctx *ctx) {
   cudaSetDevice(ctx->device);
   for (auto &L : ctx->levels) free_level(L);
   for (void *p : ctx->grid_allocs) cudaFree(p);
-  cudaFree(ctx->rad_dev); cudaFree(ctx->params_dev); cudaFree(ctx->counters); cudaFree(ctx->rad_counter);
+  cudaFree(ctx->rad_dev); cudaFree(ctx->params_dev); cudaFree(ctx->counters); cudaFree(ctx->rad_counter); cudaFree(ctx->slow_counters);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -478,7 +488,40 @@ int bl_selftest_division(bl_ctx *ctx, uint64_t seed, int64_t num_pairs, int64_t 
   return BL_OK;
 }
 
-int bl_upload_grid(bl_ctx *ctx, const bl_grid_view *gv) {
+static int upload_grid_slot(bl_ctx *ctx, const bl_grid_view *gv, int slot);
+
+int bl_upload_grid(bl_ctx *ctx, const bl_grid_view *gv) { return upload_grid_slot(ctx, gv, 0); }
+
+int bl_upload_grid_slice(bl_ctx *ctx, const bl_grid_view *gv, int slot) {
+  if (!ctx) return BL_ERR_ARG;
+  if (!ctx->rad.slow_light) return bl_fail(ctx, BL_ERR_STATE, "bl_upload_grid_slice: slow_light_on is false");
+  if (slot < 0 || slot >= ctx->params.slow_chunk_size) return bl_fail(ctx, BL_ERR_ARG, "bl_upload_grid_slice: slot %d outside [0, slow_chunk_size)", slot);
+  return upload_grid_slot(ctx, gv, slot);
+}
+
+int bl_set_time_window(bl_ctx *ctx, int count, const int32_t *slots, const double *times, double snapshot_time) {
+  if (!ctx || !slots || !times) return BL_ERR_ARG;
+  if (!ctx->rad.slow_light) return bl_fail(ctx, BL_ERR_STATE, "bl_set_time_window: slow_light_on is false");
+  if (count != ctx->params.slow_chunk_size) return bl_fail(ctx, BL_ERR_ARG, "bl_set_time_window: %d entries, slow_chunk_size is %d", count, ctx->params.slow_chunk_size);
+  for (int t = 0; t < count; t++) {
+    if (slots[t] < 0 || slots[t] >= count) return bl_fail(ctx, BL_ERR_ARG, "bl_set_time_window: slot %d out of range", slots[t]);
+    if (t > 0 && !(times[t] < times[t - 1])) return bl_fail(ctx, BL_ERR_ARG, "bl_set_time_window: times must decrease (entry 0 is the latest snapshot)");
+    ctx->rad.slow_slot[t] = slots[t];
+    ctx->rad.slow_time[t] = times[t];
+  }
+  ctx->rad.slow_count = count;
+  ctx->rad.snapshot_time = snapshot_time;
+  return BL_OK;
+}
+
+int bl_slow_light_stats(bl_ctx *ctx, int level, bl_slow_stats *out) {
+  if (!ctx || !out) return BL_ERR_ARG;
+  if (level < 0 || level >= (int)ctx->levels.size()) return bl_fail(ctx, BL_ERR_ARG, "bl_slow_light_stats: level %d out of range", level);
+  *out = ctx->levels[level].slow;
+  return BL_OK;
+}
+
+static int upload_grid_slot(bl_ctx *ctx, const bl_grid_view *gv, int slot) {
   if (!ctx || !gv) return BL_ERR_ARG;
   if (gv->n_b <= 0 || gv->n_i <= 0 || gv->n_j <= 0 || gv->n_k <= 0 || !gv->prim || !gv->x1f || !gv->x2f ||
       !gv->x3f || !gv->x1v || !gv->x2v || !gv->x3v)
@@ -528,12 +571,15 @@ int bl_upload_grid(bl_ctx *ctx, const bl_grid_view *gv) {
     BL_CUDA_CHECK(alloc_d(&g.x1d, (size_t)g.n_b * g.n_i));
     BL_CUDA_CHECK(alloc_d(&g.x2d, (size_t)g.n_b * g.n_j));
     BL_CUDA_CHECK(alloc_d(&g.x3d, (size_t)g.n_b * g.n_k));
+    // slow light keeps slow_chunk_size snapshots resident, back to back
+    const size_t slices = ctx->rad.slow_light ? (size_t)ctx->params.slow_chunk_size : 1;
+    g.slice_cells = cells;
     float4 *c4 = nullptr;
-    BL_CUDA_CHECK(dev_alloc(&c4, cells * 2));
+    BL_CUDA_CHECK(dev_alloc(&c4, cells * 2 * slices));
     g.cells = c4; ctx->grid_allocs.push_back(c4);
     if (want_kappa) {
       float *kp = nullptr;
-      BL_CUDA_CHECK(dev_alloc(&kp, cells));
+      BL_CUDA_CHECK(dev_alloc(&kp, cells * slices));
       g.kappa = kp; ctx->grid_allocs.push_back(kp);
     }
   }
@@ -610,7 +656,9 @@ int bl_upload_grid(bl_ctx *ctx, const bl_grid_view *gv) {
   int *idx_dev = nullptr;
   if (e == cudaSuccess) e = dev_alloc(&idx_dev, 9);
   if (e == cudaSuccess) e = cudaMemcpyAsync(idx_dev, idx, sizeof idx, cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess) e = bl_launch_relayout_grid(stage, gv->n_var, idx_dev, cells, const_cast<float4 *>(g.cells), const_cast<float *>(g.kappa), ctx->stream);
+  if (e == cudaSuccess)
+    e = bl_launch_relayout_grid(stage, gv->n_var, idx_dev, cells, const_cast<float4 *>(g.cells) + 2 * cells * (size_t)slot,
+                                g.kappa ? const_cast<float *>(g.kappa) + cells * (size_t)slot : nullptr, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   cudaFree(stage);
   cudaFree(idx_dev);
@@ -673,6 +721,7 @@ int radiate_wave(bl_ctx *ctx, Level &L, int64_t first, int64_t count) {
   A.image_stride = L.rays;
   A.render = L.render ? L.render + first : nullptr;
   A.sample_counter = ctx->rad_counter;
+  A.slow_counters = ctx->rad.slow_light ? ctx->slow_counters : nullptr;
   if (L.tap_nan) {
     size_t o = (size_t)first * L.tap_S;
     A.taps.S = L.tap_S;
@@ -897,6 +946,11 @@ int bl_radiate_level(bl_ctx *ctx, int level, int snapshot, double *image, double
     BL_CUDA_CHECK(cudaMemsetAsync(L.tap_fb, 0, ns, ctx->stream));
   }
   BL_CUDA_CHECK(cudaMemsetAsync(ctx->rad_counter, 0, sizeof(unsigned long long), ctx->stream));
+  if (ctx->rad.slow_light) {
+    if (ctx->rad.slow_count != ctx->params.slow_chunk_size)
+      return bl_fail(ctx, BL_ERR_STATE, "bl_radiate_level: slow light needs bl_set_time_window before radiating");
+    BL_CUDA_CHECK(cudaMemsetAsync(ctx->slow_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+  }
   double ms_geo = 0.0, ms_rad = 0.0;
   float ms = 0.f;
   if (L.resident) {
@@ -937,7 +991,18 @@ int bl_radiate_level(bl_ctx *ctx, int level, int snapshot, double *image, double
     BL_CUDA_CHECK(cudaMemcpyAsync(image, L.image, (size_t)L.rays * Q * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   if (render && R > 0 && L.render)
     BL_CUDA_CHECK(cudaMemcpyAsync(render, L.render, (size_t)L.rays * 3 * R * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  unsigned long long slow_raw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (ctx->rad.slow_light)
+    BL_CUDA_CHECK(cudaMemcpyAsync(slow_raw, ctx->slow_counters, sizeof slow_raw, cudaMemcpyDeviceToHost, ctx->stream));
   BL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  L.slow = bl_slow_stats();
+  if (ctx->rad.slow_light)
+    for (int side = 0; side < 2; side++) {
+      L.slow.num_small[side] = (int64_t)slow_raw[2 * side];
+      L.slow.num_large[side] = (int64_t)slow_raw[2 * side + 1];
+      std::memcpy(&L.slow.val_small[side], &slow_raw[4 + 2 * side], sizeof(double));
+      std::memcpy(&L.slow.val_large[side], &slow_raw[4 + 2 * side + 1], sizeof(double));
+    }
   if (stats) *stats = L.stats;
   return BL_OK;
 }

@@ -267,6 +267,17 @@ bl_grid_view AthenaGrid::view() const {
   return v;
 }
 
+double read_athdf_time(const std::string &path) {
+  H5File f(path);
+  Datatype dt;
+  size_t count = 0;
+  const uint8_t *d = f.attribute("Time", dt, count);
+  if (dt.cls != 1 || dt.size != 4) throw Error("Unexpected HDF5 datatype for attribute Time.");
+  float t;
+  std::memcpy(&t, d, 4);
+  return t;
+}
+
 void read_athdf(const std::string &path, const std::string &kappa_name, bool reuse_layout, AthenaGrid &g) {
   H5File f(path);
   {

@@ -26,6 +26,8 @@ struct AthenaGrid {
 // kappa_name: electron-entropy variable to locate when plasma_model = code_kappa ("" = none).
 // reuse_layout: keep coordinates of `grid` (already read from the first snapshot) and only refresh cell data.
 void read_athdf(const std::string &path, const std::string &kappa_name, bool reuse_layout, AthenaGrid &grid);
+// only the file's Time attribute (slow light looks ahead for the first snapshot late enough)
+double read_athdf_time(const std::string &path);
 
 // File name of snapshot `number` from a pattern holding one `{Nd}` field (simulation_reader.cpp:870-904)
 std::string format_numbered(const std::string &pattern, int number, const char *what);

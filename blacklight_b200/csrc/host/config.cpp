@@ -158,7 +158,21 @@ RunConfig make_config(const InputFile &in) {
       p.simulation_block_interp = in.flag("simulation_block_interp");
     else if (in.has("simulation_block_interp"))
       warning("Ignoring simulation_block_interp selection.");
-    if (in.flag("slow_light_on")) throw Error("slow_light_on is outside the B200 hot-path scope (SURVEY.md section 8f).");
+    // slow light (simulation_reader.cpp:64-82, radiation_integrator.cpp:203-214)
+    p.slow_light_on = in.flag("slow_light_on");
+    p.extrapolation_tolerance = 1.0;   // simulation_reader.hpp:99
+    if (p.slow_light_on) {
+      if (!c.simulation_multiple) throw Error("Must enable simulation_multiple to use slow light.");
+      if (c.checkpoint_sample_save) throw Error("Cannot use sample checkpoints with slow light.");
+      p.slow_interp = in.flag("slow_interp");
+      p.slow_chunk_size = in.integer("slow_chunk_size");
+      if (p.slow_chunk_size < 2) throw Error("Must have slow_chunk_size be at least 2.");
+      if (p.slow_chunk_size > c.simulation_end - c.simulation_start + 1) throw Error("Not enough simulation files for given slow_chunk_size.");
+      c.slow_t_start = in.real("slow_t_start");
+      c.slow_dt = in.real("slow_dt");
+      if (c.slow_dt <= 0.0) throw Error("Must have positive time interval slow_dt.");
+      c.slow_offset = in.integer("slow_offset");
+    }
   } else {
     double formula_mass = in.real("formula_mass");
     p.mass_msun = formula_mass * kC * kC / kGgMsun;

@@ -27,6 +27,9 @@ struct RunConfig {
   bool gamma_set = false;
   bool checkpoint_geodesic_save = false, checkpoint_geodesic_load = false, checkpoint_sample_save = false;
   std::string checkpoint_geodesic_file, checkpoint_sample_file;
+  // slow light (simulation_reader.cpp:64-82, output_writer.cpp:104)
+  double slow_t_start = 0.0, slow_dt = 0.0;
+  int slow_offset = 0;
   int num_runs = 1;
 };
 

@@ -6,6 +6,7 @@
 #include <cstring>
 #include <fstream>
 #include <memory>
+#include <sstream>
 #include <vector>
 
 #include "athdf.hpp"
@@ -132,7 +133,8 @@ void write_output(const RunConfig &cfg, const std::vector<LevelData> &levels, in
   const bl_params &p = cfg.params;
   const bool sim = p.model_type == BL_MODEL_SIMULATION;
   std::string path = cfg.output_file;
-  if (sim && cfg.simulation_multiple) path = format_numbered(cfg.output_file, snapshot + cfg.simulation_start, "output_file");
+  if (sim && cfg.simulation_multiple)
+    path = format_numbered(cfg.output_file, snapshot + (p.slow_light_on ? cfg.slow_offset : cfg.simulation_start), "output_file");
   const LevelData &root = levels[0];
   const Offsets o = image_offsets(p);
   if (cfg.output_format == 0) {
@@ -297,8 +299,68 @@ RunTimings run_input_file(const std::string &path, int device, bool quiet) {
   T.geodesic += now_s() - t0;
 
   AthenaGrid grid;
+  // slow light: the reader's sliding window of snapshots (simulation_reader.cpp:211-303), kept resident in HBM.
+  // Window entry t (0 = latest) lives in device slot window_slot[t]; shifting the window permutes the slots.
+  std::vector<int32_t> window_slot;
+  std::vector<double> window_time;
+  int latest_file_number = -1;
+  bool first_read = true;
   for (int n = 0; n < cfg.num_runs; n++) {
-    if (sim) {
+    if (sim && p.slow_light_on) {
+      t0 = now_s();
+      const int chunk = p.slow_chunk_size;
+      const double tol = p.extrapolation_tolerance;
+      const double snapshot_time = cfg.slow_t_start + cfg.slow_dt * n;
+      double latest_time = first_read ? snapshot_time - 2.0 * tol : window_time[0];
+      int latest_old = -1;
+      if (first_read) {
+        latest_file_number = cfg.simulation_start + chunk - 2;
+        window_slot.resize((size_t)chunk);
+        window_time.assign((size_t)chunk, 0.0);
+        for (int t = 0; t < chunk; t++) window_slot[(size_t)t] = t;
+      } else {
+        latest_old = latest_file_number;
+      }
+      while (latest_time < snapshot_time && latest_file_number < cfg.simulation_end) {
+        latest_file_number++;
+        latest_time = read_athdf_time(format_numbered(cfg.simulation_file, latest_file_number, "simulation_file"));
+      }
+      if (latest_time < snapshot_time - tol) {
+        std::ostringstream msg;
+        msg << "Snapshot " << n << " at time " << snapshot_time << " would require significant extrapolation beyond file "
+            << cfg.simulation_end << ".";
+        throw Error(msg.str());
+      } else if (latest_time < snapshot_time) {
+        std::ostringstream msg;
+        msg << "Snapshot " << n << " at time " << snapshot_time << " requires moderate extrapolation.";
+        warning(msg.str());
+      }
+      int num_read;
+      if (latest_file_number == latest_old) {
+        num_read = 0;
+      } else if (latest_file_number - chunk + 1 <= latest_old) {
+        num_read = latest_file_number - latest_old;
+        // entries move back by num_read; the slots of the entries that fall off the end are reused for the new ones
+        std::vector<int32_t> freed(window_slot.end() - num_read, window_slot.end());
+        for (int t = chunk - 1; t >= num_read; t--) {
+          window_slot[(size_t)t] = window_slot[(size_t)(t - num_read)];
+          window_time[(size_t)t] = window_time[(size_t)(t - num_read)];
+        }
+        for (int t = 0; t < num_read; t++) window_slot[(size_t)t] = freed[(size_t)t];
+      } else {
+        num_read = chunk;
+      }
+      for (int t = 0; t < num_read; t++) {
+        std::string file = format_numbered(cfg.simulation_file, latest_file_number - t, "simulation_file");
+        read_athdf(file, p.plasma_model == BL_PLASMA_CODE_KAPPA ? cfg.simulation_kappa_name : "", !first_read, grid);
+        first_read = false;
+        window_time[(size_t)t] = grid.time;
+        bl_grid_view view = grid.view();
+        check(ctx, bl_upload_grid_slice(ctx, &view, window_slot[(size_t)t]));
+      }
+      check(ctx, bl_set_time_window(ctx, chunk, window_slot.data(), window_time.data(), snapshot_time));
+      T.read += now_s() - t0;
+    } else if (sim) {
       t0 = now_s();
       std::string file = cfg.simulation_file;
       if (cfg.simulation_multiple) file = format_numbered(cfg.simulation_file, cfg.simulation_start + n, "simulation_file");
@@ -315,6 +377,29 @@ RunTimings run_input_file(const std::string &path, int device, bool quiet) {
       if (R > 0) L.render.resize((size_t)R * 3 * L.rays);
       check(ctx, bl_radiate_level(ctx, level, n, L.image.data(), R > 0 ? L.render.data() : nullptr, &st));
       T.gpu_radiation_ms += st.ms_radiation;
+      if (sim && p.slow_light_on) {
+        // same errors / warnings as the reference's sampling stage (simulation_sampling.cpp:577-617)
+        bl_slow_stats ss{};
+        check(ctx, bl_slow_light_stats(ctx, level, &ss));
+        const double snapshot_time = cfg.slow_t_start + cfg.slow_dt * n;
+        const char *direction[2] = {"forward", "backward"};
+        for (int side = 0; side < 2; side++)
+          if (ss.num_large[side] > 0) {
+            std::ostringstream msg;
+            msg << "Snapshot " << n << " at time " << snapshot_time << " requires significant extrapolation " << direction[side]
+                << " in time (" << ss.num_large[side] << "/" << L.rays << " pixels, by up to " << ss.val_large[side]
+                << " gravitational times).";
+            throw Error(msg.str());
+          }
+        for (int side = 0; side < 2; side++)
+          if (ss.num_small[side] > 0) {
+            std::ostringstream msg;
+            msg << "Snapshot " << n << " at time " << snapshot_time << " requires moderate extrapolation " << direction[side]
+                << " in time (" << ss.num_small[side] << "/" << L.rays << " pixels, by up to " << ss.val_small[side]
+                << " gravitational times).";
+            warning(msg.str());
+          }
+      }
       if (level == 0 && n == 0 && st.ms_geodesic > 0 && T.gpu_geodesic_ms == 0) T.gpu_geodesic_ms += st.ms_geodesic;
       T.rays += L.rays;
       T.samples += st.num_samples;

@@ -243,13 +243,56 @@ struct CellCache {
 
 // Locate and gather.  smem_bounds: block bounds staged in shared memory (n_b*6 doubles) or nullptr to
 // read them from HBM.  inv_r = 1/r.
-// BI: inter-block interpolation compiled in (selected at run time by P.block_interp); the light-only
-// unpolarized kernel is instantiated without it so that the common path keeps its register budget.
-template <bool BI>
+// Which time slice(s) of the resident window a sample at coordinate time x0 reads (slow light; reference
+// simulation_sampling.cpp:298-349): entry t_ind, blended with entry t_ind + 1 by t_frac when interpolating.
+struct SlowLight {   // per-ray accumulation of the extrapolation accounting (simulation_sampling.cpp:556-575)
+  int extrap;        // bit 0: camera side small, 1: camera side large, 2: source side small, 3: source side large
+  double ext[4];     // largest extrapolation seen in each category
+};
+
+__device__ __forceinline__ void time_slice(const RadParams &P, double x0, int &t_ind, double &t_frac, SlowLight &sl) {
+  t_ind = 0;
+  t_frac = 0.0;
+  const int last = P.slow_count - 1;
+  if (x0 >= P.slow_time[0]) {
+    if (x0 > P.slow_time[0] + P.extrap_tol) { sl.extrap |= 2; sl.ext[1] = fmax(sl.ext[1], x0 - P.slow_time[0]); }
+    else if (x0 > P.slow_time[0]) { sl.extrap |= 1; sl.ext[0] = fmax(sl.ext[0], x0 - P.slow_time[0]); }
+  } else if (x0 <= P.slow_time[last]) {
+    if (x0 < P.slow_time[last] - P.extrap_tol) { sl.extrap |= 8; sl.ext[3] = fmax(sl.ext[3], P.slow_time[last] - x0); }
+    else if (x0 < P.slow_time[last]) { sl.extrap |= 4; sl.ext[2] = fmax(sl.ext[2], P.slow_time[last] - x0); }
+    if (P.slow_interp) { t_ind = last - 1; t_frac = 1.0; }
+    else t_ind = last;
+  } else {
+    while (P.slow_time[t_ind++] > x0) {}
+    t_ind--;
+    if (P.slow_interp) {
+      t_ind--;
+      t_frac = (x0 - P.slow_time[t_ind]) / (P.slow_time[t_ind + 1] - P.slow_time[t_ind]);
+    } else if (P.slow_time[t_ind - 1] - x0 <= x0 - P.slow_time[t_ind]) {
+      t_ind--;
+    }
+  }
+}
+
+// End of a ray: add its extrapolation flags to the per-launch counters (pixels per category, largest values;
+// positive doubles order like their bit patterns, so atomicMax on the bits is a max on the values).
+__device__ __forceinline__ void flush_slow_light(unsigned long long *counters, const SlowLight &sl) {
+  if (!counters || !sl.extrap) return;
+  for (int c = 0; c < 4; c++)
+    if (sl.extrap & (1 << c)) {
+      atomicAdd(counters + c, 1ull);
+      atomicMax(counters + 4 + c, (unsigned long long)__double_as_longlong(sl.ext[c]));
+    }
+}
+
+// EXT: inter-block interpolation and slow light compiled in (selected at run time by P.block_interp /
+// P.slow_light); the light-only unpolarized kernel is instantiated without them so that the common path keeps
+// its register budget.  x0 = coordinate time of the sample + camera time of the image (slow light only).
+template <bool EXT>
 __device__ __forceinline__ SampleStatus sample_grid(const RadParams &P, const GridDev &g,
                                                     const double *smem_bounds, double x, double y,
-                                                    double z, double r, double inv_r, CellCache &cache,
-                                                    Prims &out, SampleIndex &si) {
+                                                    double z, double r, double inv_r, double x0, CellCache &cache,
+                                                    Prims &out, SampleIndex &si, SlowLight &slow) {
   // simulation coordinates of the point (radiation_geometry.cpp:37-57)
   double x1 = x, x2 = y, x3 = z;
   if (P.coord != 0) {
@@ -259,6 +302,17 @@ __device__ __forceinline__ SampleStatus sample_grid(const RadParams &P, const Gr
     ph += ph < 0.0 ? 2.0 * phys::pi : 0.0;
     ph -= ph >= 2.0 * phys::pi ? 2.0 * phys::pi : 0.0;
     x1 = r; x2 = th; x3 = ph;
+  }
+  // time slices (slow light): slot_a always, slot_b blended in with weight t_frac when interpolating in time
+  size_t slot_a = 0, slot_b = 0;
+  double t_frac = 0.0;
+  bool two_slices = false;
+  if (EXT && P.slow_light) {
+    int t_ind;
+    time_slice(P, x0, t_ind, t_frac, slow);
+    slot_a = (size_t)P.slow_slot[t_ind] * g.slice_cells;
+    two_slices = P.slow_interp != 0;
+    if (two_slices) slot_b = (size_t)P.slow_slot[t_ind + 1] * g.slice_cells;
   }
   // block: keep the cached one while it still contains the point, else first match in index order
   const double *bounds = smem_bounds ? smem_bounds : g.bounds;
@@ -278,19 +332,40 @@ __device__ __forceinline__ SampleStatus sample_grid(const RadParams &P, const Gr
   int k = find_cell_hint(g.x3f + (size_t)b * (n_k + 1), n_k, x3, cache.k);
   cache.i = i; cache.j = j; cache.k = k;
   si.b = b;
+  const double *x1v = g.x1v + (size_t)b * n_i, *x2v = g.x2v + (size_t)b * n_j, *x3v = g.x3v + (size_t)b * n_k;
+
+  // The three sampling modes below only differ in which cells they read and with what weights; `finish`
+  // evaluates a mode on the time slice(s) and stores the float primitives the way the reference does
+  // (per-slice fallback of non-positive rho / pgas / kappa to the anchor cell, blend in double, cast).
+  auto finish = [&](auto gather) {
+    double v[9];
+    gather(slot_a, v);
+    if (EXT && two_slices) {
+      double w[9];
+      gather(slot_b, w);
+#pragma unroll
+      for (int q = 0; q < 9; q++) v[q] = (1.0 - t_frac) * v[q] + t_frac * w[q];
+    }
+    out.rho = (float)v[0]; out.pgas = (float)v[1]; out.uu1 = (float)v[2]; out.uu2 = (float)v[3];
+    out.uu3 = (float)v[4]; out.bb1 = (float)v[5]; out.bb2 = (float)v[6]; out.bb3 = (float)v[7];
+    out.kappa = (float)v[8];
+  };
+
   if (!P.interp) {
     si.k = k; si.j = j; si.i = i;
     si.fk = si.fj = si.fi = 0.0;
     size_t c = (((size_t)b * n_k + k) * n_j + j) * n_i + i;
-    float v[8];
-    load_cell(g, c, v);
-    out.rho = v[0]; out.pgas = v[1]; out.uu1 = v[2]; out.uu2 = v[3]; out.uu3 = v[4];
-    out.bb1 = v[5]; out.bb2 = v[6]; out.bb3 = v[7];
-    out.kappa = g.kappa ? __ldg(g.kappa + c) : 0.0f;
+    finish([&](size_t slot, double v[9]) {
+      float f[8];
+      load_cell(g, slot + c, f);
+#pragma unroll
+      for (int q = 0; q < 8; q++) v[q] = (double)f[q];
+      v[8] = g.kappa ? (double)__ldg(g.kappa + slot + c) : 0.0;
+    });
     return kSampleOk;
   }
-  const double *x1v = g.x1v + (size_t)b * n_i, *x2v = g.x2v + (size_t)b * n_j, *x3v = g.x3v + (size_t)b * n_k;
-  if (BI && P.block_interp) {
+
+  if (EXT && P.block_interp) {
     // inter-block trilinear: anchors may be ghost cells, resolved on neighbouring blocks of any level
     // (simulation_sampling.cpp:504-549).  Upper ghost coordinates are formed exactly as the reference
     // does, from x?v(b, i+1) -- for i = n-1 the next block's first centre (the arrays carry one element of
@@ -311,10 +386,7 @@ __device__ __forceinline__ SampleStatus sample_grid(const RadParams &P, const Gr
     double gk = 1.0 - f_k, gj = 1.0 - f_j, gi = 1.0 - f_i;
     double w[8] = {gk * gj * gi, gk * gj * f_i, gk * f_j * gi, gk * f_j * f_i,
                    f_k * gj * gi, f_k * gj * f_i, f_k * f_j * gi, f_k * f_j * f_i};
-    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    double acc_kappa = 0.0;
-    float corner[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    float corner_kappa = 0.0f;
+    size_t cell[8];
 #pragma unroll 1
     for (int p = 0; p < 8; p++) {
       int inds[4];
@@ -322,27 +394,33 @@ __device__ __forceinline__ SampleStatus sample_grid(const RadParams &P, const Gr
       if (p == 0) {
         si.b = inds[0]; si.k = inds[1]; si.j = inds[2]; si.i = inds[3];
       }
-      size_t c = (((size_t)inds[0] * n_k + inds[1]) * n_j + inds[2]) * n_i + inds[3];
-      float v[8];
-      load_cell(g, c, v);
-      if (p == 0)
-        for (int q = 0; q < 8; q++) corner[q] = v[q];
-      for (int q = 0; q < 8; q++) acc[q] += w[p] * (double)v[q];
-      if (g.kappa) {
-        float kv = __ldg(g.kappa + c);
-        if (p == 0) corner_kappa = kv;
-        acc_kappa += w[p] * (double)kv;
-      }
+      cell[p] = (((size_t)inds[0] * n_k + inds[1]) * n_j + inds[2]) * n_i + inds[3];
     }
     si.fk = f_k; si.fj = f_j; si.fi = f_i;
-    if (acc[0] <= 0.0) acc[0] = (double)corner[0];
-    if (acc[1] <= 0.0) acc[1] = (double)corner[1];
-    if (g.kappa && acc_kappa <= 0.0) acc_kappa = (double)corner_kappa;
-    out.rho = (float)acc[0]; out.pgas = (float)acc[1]; out.uu1 = (float)acc[2]; out.uu2 = (float)acc[3];
-    out.uu3 = (float)acc[4]; out.bb1 = (float)acc[5]; out.bb2 = (float)acc[6]; out.bb3 = (float)acc[7];
-    out.kappa = (float)acc_kappa;
+    finish([&](size_t slot, double v[9]) {
+      float corner[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      float corner_kappa = 0.0f;
+#pragma unroll
+      for (int q = 0; q < 9; q++) v[q] = 0.0;
+      for (int p = 0; p < 8; p++) {
+        float f[8];
+        load_cell(g, slot + cell[p], f);
+        if (p == 0)
+          for (int q = 0; q < 8; q++) corner[q] = f[q];
+        for (int q = 0; q < 8; q++) v[q] += w[p] * (double)f[q];
+        if (g.kappa) {
+          float kv = __ldg(g.kappa + slot + cell[p]);
+          if (p == 0) corner_kappa = kv;
+          v[8] += w[p] * (double)kv;
+        }
+      }
+      if (v[0] <= 0.0) v[0] = (double)corner[0];
+      if (v[1] <= 0.0) v[1] = (double)corner[1];
+      if (g.kappa && v[8] <= 0.0) v[8] = (double)corner_kappa;
+    });
     return kSampleOk;
   }
+
   // intra-block trilinear with extrapolation at block edges (simulation_sampling.cpp:485-502)
   int i_m = (i == 0 || (i != n_i - 1 && x1 >= __ldg(x1v + i))) ? i : i - 1;
   int j_m = (j == 0 || (j != n_j - 1 && x2 >= __ldg(x2v + j))) ? j : j - 1;
@@ -359,33 +437,32 @@ __device__ __forceinline__ SampleStatus sample_grid(const RadParams &P, const Gr
   size_t c0 = (((size_t)b * n_k + k_m) * n_j + j_m) * n_i + i_m;
   size_t sj = (size_t)n_i, sk = (size_t)n_j * n_i;
   size_t off[8] = {0, 1, sj, sj + 1, sk, sk + 1, sk + sj, sk + sj + 1};
-  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  double acc_kappa = 0.0;
-  float corner[8];
-  float corner_kappa = 0.0f;
+  finish([&](size_t slot, double v[9]) {
+    float corner[8];
+    float corner_kappa = 0.0f;
 #pragma unroll
-  for (int p = 0; p < 8; p++) {
-    float v[8];
-    load_cell(g, c0 + off[p], v);
-    if (p == 0) {
+    for (int q = 0; q < 9; q++) v[q] = 0.0;
 #pragma unroll
-      for (int q = 0; q < 8; q++) corner[q] = v[q];
+    for (int p = 0; p < 8; p++) {
+      float f[8];
+      load_cell(g, slot + c0 + off[p], f);
+      if (p == 0) {
+#pragma unroll
+        for (int q = 0; q < 8; q++) corner[q] = f[q];
+      }
+#pragma unroll
+      for (int q = 0; q < 8; q++) v[q] += w[p] * (double)f[q];
+      if (g.kappa) {
+        float kv = __ldg(g.kappa + slot + c0 + off[p]);
+        if (p == 0) corner_kappa = kv;
+        v[8] += w[p] * (double)kv;
+      }
     }
-#pragma unroll
-    for (int q = 0; q < 8; q++) acc[q] += w[p] * (double)v[q];
-    if (g.kappa) {
-      float kv = __ldg(g.kappa + c0 + off[p]);
-      if (p == 0) corner_kappa = kv;
-      acc_kappa += w[p] * (double)kv;
-    }
-  }
-  // non-positive interpolated rho / pgas / kappa fall back to the anchor cell (:822-827)
-  if (acc[0] <= 0.0) acc[0] = (double)corner[0];
-  if (acc[1] <= 0.0) acc[1] = (double)corner[1];
-  if (g.kappa && acc_kappa <= 0.0) acc_kappa = (double)corner_kappa;
-  out.rho = (float)acc[0]; out.pgas = (float)acc[1]; out.uu1 = (float)acc[2]; out.uu2 = (float)acc[3];
-  out.uu3 = (float)acc[4]; out.bb1 = (float)acc[5]; out.bb2 = (float)acc[6]; out.bb3 = (float)acc[7];
-  out.kappa = (float)acc_kappa;
+    // non-positive interpolated rho / pgas / kappa fall back to the anchor cell (:822-827)
+    if (v[0] <= 0.0) v[0] = (double)corner[0];
+    if (v[1] <= 0.0) v[1] = (double)corner[1];
+    if (g.kappa && v[8] <= 0.0) v[8] = (double)corner_kappa;
+  });
   return kSampleOk;
 }
 

@@ -4,6 +4,7 @@
 #include "device_types.cuh"
 
 #define RAD_MAX_FREQ 32
+#define RAD_MAX_SLICES 64
 #define RAD_MAX_FEATURES 64
 #define RAD_NUM_CELL_VALUES 7
 
@@ -33,6 +34,9 @@ struct GridDev {
   const double *x1d, *x2d, *x3d;  // (n_b, n): 1 / (xv[i+1] - xv[i]) for i < n-1 (interpolation weights)
   const float4 *cells;
   const float *kappa;             // (n_b, n_k, n_j, n_i) electron entropy, or nullptr
+  // slow light: `cells` / `kappa` hold several snapshots back to back, slot s at cells + s * slice_cells * 2
+  // and kappa + s * slice_cells
+  size_t slice_cells;
   // mesh topology for inter-block interpolation (simulation_block_interp): refinement level and logical
   // location of every block, and an open-addressing hash (level, location) -> block built at upload, which
   // replaces the reference's linear scans over all blocks (simulation_sampling.cpp:1068-1321)
@@ -106,6 +110,11 @@ struct RadParams {
   double log_freqs[RAD_MAX_FREQ];   // ln image_frequencies[l]
   double n_e_factor;                // n_e_cgs = rho_cgs * n_e_factor
   int32_t any_value_cut;            // any of the cut_{rho,...,beta_inverse}_{min,max} enabled
+  // slow light: the resident time window (index 0 = latest snapshot), see bl_set_time_window
+  int32_t slow_light, slow_interp, slow_count;
+  int32_t slow_slot[RAD_MAX_SLICES];
+  double slow_time[RAD_MAX_SLICES];
+  double snapshot_time, extrap_tol;
   // logarithms of distribution constants: powers of per-sample quantities are evaluated as exp(c * ln x)
   // with the logarithms shared between all exponents and frequencies
   double log_w2k2;                  // ln(w^2 kappa^2)
@@ -148,4 +157,6 @@ struct RadArgs {
   double *render;               // (R, 3, level_rays) or nullptr, offset likewise
   SampleTaps taps;              // pointers already offset to this wave's first ray
   unsigned long long *sample_counter;  // processed (ray, sample) pairs, for roofline accounting
+  unsigned long long *slow_counters;   // [0..3] pixels extrapolating (camera small, camera large, source small,
+                                       // source large), [4..7] the largest extrapolations as double bits; or nullptr
 };

@@ -603,7 +603,8 @@ __device__ __forceinline__ void couple(const RadParams &P, const Coefficients &C
   for (int a = 0; a < 4; a++) s[a] = out[a];
 }
 
-// BI: inter-block interpolation compiled in (a separate instantiation keeps it out of the common kernel)
+// BI: inter-block interpolation and slow light compiled in (a separate instantiation keeps them out of the
+// common kernel)
 #ifndef BL_POL_MINB
 #define BL_POL_MINB 2  // resident CTAs per SM the kernel is register-capped for
 #endif
@@ -663,6 +664,7 @@ radiate_polarized_kernel(const __grid_constant__ RadArgs A, const __grid_constan
   double prev_cv[RAD_NUM_CELL_VALUES];
   for (int q = 0; q < RAD_NUM_CELL_VALUES; q++) prev_cv[q] = nan("");
   rad::CellCache cache = {0, 0, 0, 0};
+  rad::SlowLight slow = {0, {0.0, 0.0, 0.0, 0.0}};
   const double inv_mom_x = P.x_unit / mom;  // affine step -> cm per unit image frequency
   unsigned long long processed = 0;
 
@@ -693,7 +695,7 @@ radiate_polarized_kernel(const __grid_constant__ RadArgs A, const __grid_constan
     else if (rad::geometric_cut(P, x, y, z, r))
       st = rad::kSampleCut;
     else
-      st = rad::sample_grid<BI>(P, G, bounds_s, x, y, z, r, inv_r, cache, pr, si);
+      st = rad::sample_grid<BI>(P, G, bounds_s, x, y, z, r, inv_r, t + P.snapshot_time, cache, pr, si, slow);
     if (st == rad::kSampleNan) {
       float qn = nanf("");
       pr.rho = pr.pgas = pr.kappa = pr.uu1 = pr.uu2 = pr.uu3 = pr.bb1 = pr.bb2 = pr.bb3 = qn;
@@ -891,6 +893,7 @@ BL_FREQ_LOOP
       }
     }
   }
+  if (BI) rad::flush_slow_light(A.slow_counters, slow);
   if (A.sample_counter) {
     for (int off = 16; off > 0; off >>= 1) processed += __shfl_down_sync(full, processed, off);
     if ((threadIdx.x & 31) == 0 && processed) atomicAdd(A.sample_counter, processed);
@@ -902,7 +905,7 @@ cudaError_t launch_fmax(const RadArgs &A, const RadParams &P, cudaStream_t strea
   unsigned grid = (unsigned)((A.rays + kBlock - 1) / kBlock);
   size_t smem = 0;
   if ((size_t)A.grid.n_b * 6 * sizeof(double) <= 48 * 1024) smem = (size_t)A.grid.n_b * 6 * sizeof(double);
-  if (P.block_interp)
+  if (P.block_interp || P.slow_light)
     radiate_polarized_kernel<FMAX, true><<<grid, kBlock, smem, stream>>>(A, P);
   else
     radiate_polarized_kernel<FMAX, false><<<grid, kBlock, smem, stream>>>(A, P);

@@ -216,6 +216,7 @@ radiate_unpolarized_kernel(const __grid_constant__ RadArgs A, const __grid_const
   double prev_cv[RAD_NUM_CELL_VALUES];
   for (int q = 0; q < RAD_NUM_CELL_VALUES; q++) prev_cv[q] = nan("");
   rad::CellCache cache = {0, 0, 0, 0};
+  rad::SlowLight slow = {0, {0.0, 0.0, 0.0, 0.0}};
   const double inv_mom_x = P.x_unit / mom;  // affine step -> cm per unit image frequency
   unsigned long long processed = 0;
   const double k_t = valid ? A.cam_dir[4 * m] : 0.0;  // conserved covariant time component of the momentum
@@ -252,7 +253,7 @@ radiate_unpolarized_kernel(const __grid_constant__ RadArgs A, const __grid_const
       else if (rad::geometric_cut(P, x, y, z, r))
         st = rad::kSampleCut;
       else
-        st = rad::sample_grid<!LEAN>(P, G, bounds_s, x, y, z, r, inv_r, cache, pr, si);
+        st = rad::sample_grid<!LEAN>(P, G, bounds_s, x, y, z, r, inv_r, t + P.snapshot_time, cache, pr, si, slow);
       if (A.taps.nan_) {
         size_t ti = (size_t)m * A.taps.S + n_ref;
         A.taps.nan_[ti] = st == rad::kSampleNan;
@@ -414,6 +415,7 @@ BL_FREQ_LOOP
       if (P.image_crossings) img[(size_t)P.off_crossings * stride] = (double)crossings;
     }
   }
+  if (!LEAN && SIM) rad::flush_slow_light(A.slow_counters, slow);
   if (A.sample_counter) {
     for (int off = 16; off > 0; off >>= 1) processed += __shfl_down_sync(full, processed, off);
     if ((threadIdx.x & 31) == 0 && processed) atomicAdd(A.sample_counter, processed);
@@ -426,7 +428,7 @@ cudaError_t launch_fmax(const RadArgs &A, const RadParams &P, cudaStream_t strea
   const bool lean = P.image_light && !(P.image_time || P.image_length || P.image_lambda || P.image_emission ||
                                        P.image_tau || P.image_lambda_ave || P.image_emission_ave || P.image_tau_int ||
                                        P.image_crossings) &&
-                    !(sim && A.render != nullptr && P.render_num_images > 0) && !(sim && P.block_interp);
+                    !(sim && A.render != nullptr && P.render_num_images > 0) && !(sim && (P.block_interp || P.slow_light));
   unsigned grid = (unsigned)((A.rays + kBlock - 1) / kBlock);
   size_t smem = 0;
   if (sim && (size_t)A.grid.n_b * 6 * sizeof(double) <= 48 * 1024) smem = (size_t)A.grid.n_b * 6 * sizeof(double);

@@ -125,6 +125,9 @@ typedef struct bl_params {
   /* B200 knobs (new, optional; 0 = default) */
   int32_t device;                 /* CUDA device ordinal */
   int64_t tile_rays;              /* rays traced per wave; 0 = sized from free HBM */
+  /* slow light (radiation_integrator.cpp:203-214, simulation_reader.hpp:99) */
+  int32_t slow_light_on, slow_interp, slow_chunk_size;
+  double extrapolation_tolerance; /* the reference's constant 1.0 */
   int32_t level0_block_major;     /* 1: level-0 rays are given block by block (m = block*bs^2 + row*bs + col, like the
                                    * refined levels) instead of as the full raster -- lets the root blocks of an
                                    * adaptive image be sharded over GPUs; affects only
@@ -175,6 +178,26 @@ int bl_upload_grid(bl_ctx *ctx, const bl_grid_view *grid);
  * step buffer fits the HBM budget, otherwise tile by tile inside bl_radiate_level. */
 int bl_trace_level(bl_ctx *ctx, int level, const double *cam_pos, const double *cam_dir,
                    const double *mom_factor, int64_t num_rays, bl_level_stats *stats);
+
+/* Slow light (reference simulation_reader.cpp:211-303, simulation_sampling.cpp:298-349): the context keeps
+ * slow_chunk_size snapshots resident in HBM.  bl_upload_grid_slice puts one snapshot into slot `slot`
+ * (0 <= slot < slow_chunk_size; slot 0 is what bl_upload_grid fills); bl_set_time_window then declares, for the
+ * next bl_radiate_level calls, which slot holds window entry t (t = 0 the latest ... count-1 the earliest, as in
+ * the reader's prim[t]/time[t]), the entries' simulation times, and the camera time of the image
+ * (slow_t_start + slow_dt * snapshot).  Shifting the window is a permutation of `slots` on the host; no device
+ * data moves. */
+#define BL_MAX_SLICES 64
+int bl_upload_grid_slice(bl_ctx *ctx, const bl_grid_view *grid, int slot);
+int bl_set_time_window(bl_ctx *ctx, int count, const int32_t *slots, const double *times, double snapshot_time);
+
+/* Extrapolation accounting of the last bl_radiate_level on a level (simulation_sampling.cpp:556-618): pixels that
+ * needed time slices beyond the window, by less / more than extrapolation_tolerance, and by how much at most.
+ * Index 0: forward in time (camera side), 1: backward (source side). */
+typedef struct bl_slow_stats {
+  int64_t num_small[2], num_large[2];
+  double val_small[2], val_large[2];
+} bl_slow_stats;
+int bl_slow_light_stats(bl_ctx *ctx, int level, bl_slow_stats *out);
 
 /* Load a level whose geodesics were integrated elsewhere (the reference's checkpoint_geodesic_load,
  * geodesic_checkpoint.cpp:77-108) instead of tracing it: camera arrays as for bl_trace_level plus the

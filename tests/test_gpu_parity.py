@@ -438,6 +438,56 @@ def test_adaptive_sharded_over_ranks(world, gpu, tmp_path):
             assert np.array_equal(one[k], v, equal_nan=True), k
 
 
+@pytest.mark.parametrize('over', [
+    {'slow_interp': 'true'},
+    {'slow_interp': 'false'},
+    {'slow_interp': 'true', 'simulation_interp': 'false'},
+    {'slow_interp': 'true', 'image_polarization': 'true', 'camera_resolution': 16},
+])
+def test_slow_light_against_reference(over, gpu, tmp_path):
+    """slow_light_on: a time series of mock snapshots (perturbation amplitude growing with time), a sliding window
+    of slow_chunk_size snapshots resident in HBM, time-slice choice / interpolation per sample
+    (simulation_sampling.cpp:298-349) -- three consecutive images through the drop-in executable path against
+    the reference binary, including the window shift between images."""
+    if not os.path.exists(REF_BIN):
+        pytest.skip('oracle/_ref/blacklight not present')
+    import subprocess
+    from blacklight_b200 import mock_snapshot as ms
+    from harness import write_input
+    d = str(tmp_path)
+    case = Case(d, 'simulation.input', dict({'camera_resolution': 24}, **over))
+    n_files = 12
+    for n in range(n_files):
+        grid = ms.to_blocks(ms.mock_fields(n_r=32, n_th=16, n_ph=32, pert_amp=0.1 + 0.05 * n), (1, 1, 2))
+        ms.write_athdf(os.path.join(d, 'data', 'mock.%05d.athdf' % n), grid, time=25.0 * n)
+    images = {}
+    for who in ('ref', 'gpu'):
+        out = os.path.join(d, 'out_' + who)
+        os.makedirs(out)
+        kv = dict(case.kv)
+        kv.update({'simulation_file': os.path.join(d, 'data', 'mock.{05d}.athdf'), 'simulation_multiple': 'true',
+                   'simulation_start': '0', 'simulation_end': str(n_files - 1), 'slow_light_on': 'true',
+                   'slow_chunk_size': '8', 'slow_t_start': '200.0', 'slow_dt': '20.0', 'slow_num_images': '3',
+                   'slow_offset': '5', 'output_file': os.path.join(out, 'img.{03d}.npz')})
+        path = os.path.join(d, who + '.input')
+        write_input(path, kv)
+        if who == 'ref':
+            proc = subprocess.run([REF_BIN, path], cwd=d, capture_output=True, text=True, timeout=3600)
+            assert proc.returncode == 0 and 'Calculation completed' in proc.stdout, proc.stdout + proc.stderr
+        else:
+            bl.run_input_file(path)
+        images[who] = [dict(np.load(os.path.join(out, 'img.%03d.npz' % k))) for k in (5, 6, 7)]
+    pol = over.get('image_polarization') == 'true'
+    for ref, mine in zip(images['ref'], images['gpu']):
+        assert rel_err(mine['I_nu'], ref['I_nu']) <= PIXEL_TOL
+        assert flux_rel(mine['I_nu'], ref['I_nu']) <= FLUX_TOL
+        if pol:
+            for k, v in stokes_err(mine, ref).items():
+                assert v <= PIXEL_TOL, '%s %.3e' % (k, v)
+    # the series must actually evolve
+    assert rel_err(images['gpu'][2]['I_nu'], images['gpu'][0]['I_nu']) > 1e-3
+
+
 def test_geodesic_checkpoint_exchange_with_reference(gpu, tmp_path):
     """checkpoint_geodesic_load: geodesics integrated by the REFERENCE (its checkpoint file, reference byte format)
     are loaded into the step buffer instead of tracing (bl_upload_samples).  Because the CUDA integrator is

@@ -1,4 +1,4 @@
-mkdir -p /tmp/p
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"radiate_unpol" -c 1 -f -o /tmp/p/u python bench.py --resolution 512 --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_u.log 2>&1
-ncu -i /tmp/p/u.ncu-rep --page raw --csv > gpurun_out/r01h_unpol_raw.csv
-ncu -i /tmp/p/u.ncu-rep --page source --csv --print-source cuda,sass 2>/dev/null | gzip -9 > gpurun_out/r01h_unpol_source.csv.gz
+set -x
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -4
+timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_1024.json 2> gpurun_out/bench_1024.err
+timeout 300 python bench.py --workload polarized --resolution 512 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_pol512.json 2> gpurun_out/bench_pol512.err
