@@ -175,9 +175,16 @@ def _attribute(name, value):
 def write_athdf(path, grid, time=0.0):
     """Write `grid` (output of to_blocks) as an Athena++ .athdf file."""
     n_b = grid['n_b']
+    # optional electron-entropy variable (plasma_model = code_kappa): a sixth hydro variable named 'r0'
+    hydro = grid['prim'][0:5]
+    names = [b'rho', b'press', b'vel1', b'vel2', b'vel3']
+    if 'kappa' in grid:
+        hydro = np.concatenate([hydro, grid['kappa'][None]], axis=0)
+        names.append(b'r0')
+    names += [b'Bcc1', b'Bcc2', b'Bcc3']
     datasets = [
         ('B', grid['prim'][5:8]), ('Levels', grid['levels']), ('LogicalLocations', grid['locations']),
-        ('prim', grid['prim'][0:5]), ('x1f', grid['x1f']), ('x1v', grid['x1v']), ('x2f', grid['x2f']),
+        ('prim', hydro), ('x1f', grid['x1f']), ('x1v', grid['x1v']), ('x2f', grid['x2f']),
         ('x2v', grid['x2v']), ('x3f', grid['x3f']), ('x3v', grid['x3v'])]
     n_r, n_th, n_ph = grid['root_size']
     attrs = [
@@ -186,9 +193,9 @@ def write_athdf(path, grid, time=0.0):
         _attribute('RootGridSize', np.array([n_r, n_th, n_ph], np.int32)),
         _attribute('NumMeshBlocks', np.int32(n_b)),
         _attribute('MeshBlockSize', np.array([grid['n_i'], grid['n_j'], grid['n_k']], np.int32)),
-        _attribute('MaxLevel', np.int32(int(np.max(grid['levels'])))), _attribute('NumVariables', np.array([5, 3], np.int32)),
+        _attribute('MaxLevel', np.int32(int(np.max(grid['levels'])))), _attribute('NumVariables', np.array([len(names) - 3, 3], np.int32)),
         _attribute('DatasetNames', np.array([b'prim', b'B'], dtype='S21')),
-        _attribute('VariableNames', np.array([b'rho', b'press', b'vel1', b'vel2', b'vel3', b'Bcc1', b'Bcc2', b'Bcc3'], dtype='S21'))]
+        _attribute('VariableNames', np.array(names, dtype='S21'))]
 
     # layout: [superblock 96][root header][heap header 32][heap data][TREE][SNOD][dataset headers][data]
     heap_data = b'\0' * 8
@@ -248,6 +255,11 @@ def write_athdf(path, grid, time=0.0):
 
 def grid_view_arrays(grid):
     """Arrays in the layout SimulationReader hands to the integrator (float32 coords widened to f64)."""
+    if 'kappa' in grid:   # the reader stacks hydro (with the entropy variable last) before the field
+        prim = np.concatenate([grid['prim'][0:5], grid['kappa'][None], grid['prim'][5:8]], axis=0)
+        out = grid_view_arrays({k: v for k, v in grid.items() if k != 'kappa'})
+        out.update(n_var=9, prim=np.ascontiguousarray(prim, np.float32), ind_kappa=5, ind_bb1=6, ind_bb2=7, ind_bb3=8)
+        return out
     return dict(
         n_b=grid['n_b'], n_k=grid['n_k'], n_j=grid['n_j'], n_i=grid['n_i'], n_var=8,
         levels=np.ascontiguousarray(grid['levels'], np.int32),
@@ -301,7 +313,17 @@ def to_blocks_amr(n_r, n_th, n_ph, blocks, refine, **kwargs):
     return out
 
 
-def make_mock(path=None, blocks=(1, 1, 1), refine=None, cks=None, **kwargs):
+def add_entropy(grid, scale=2.0e7):
+    """Electron-entropy variable kappa_e ~ p / rho^(4/3), a smooth positive field for plasma_model = code_kappa
+    (theta_e = (sqrt(1 + 25 (rho_e kappa)^(2/3)) - 1) / 5).  The default scale gives theta_e of order 1-100 in the
+    torus; much colder electrons (scale <= 1e5) make the plasma Faraday-thick by many orders of magnitude per
+    step, where the polarized solution of ANY implementation is limited by the rounding of sin/cos of 1e9."""
+    rho, pgas = grid['prim'][0].astype(np.float64), grid['prim'][1].astype(np.float64)
+    grid['kappa'] = (scale * pgas / rho ** (4.0 / 3.0)).astype(np.float32)
+    return grid
+
+
+def make_mock(path=None, blocks=(1, 1, 1), refine=None, cks=None, entropy=False, **kwargs):
     if cks is not None:
         grid = to_blocks(mock_fields_cks(**cks), blocks)
     elif refine is not None:
@@ -309,6 +331,8 @@ def make_mock(path=None, blocks=(1, 1, 1), refine=None, cks=None, **kwargs):
         grid = to_blocks_amr(n_r, n_th, n_ph, blocks, refine, **kwargs)
     else:
         grid = to_blocks(mock_fields(**kwargs), blocks)
+    if entropy:
+        add_entropy(grid)
     if path is not None:
         write_athdf(path, grid)
     return grid

@@ -262,6 +262,33 @@ def test_live_reference_cartesian_kerr_schild(over, gpu, tmp_path):
     ctx.close()
 
 
+@pytest.mark.parametrize('over', [
+    {'camera_resolution': 32},
+    {'camera_resolution': 28, 'simulation_interp': 'false'},
+    {'camera_resolution': 24, 'image_polarization': 'true'},
+])
+def test_live_reference_code_kappa(over, gpu, tmp_path):
+    """plasma_model = code_kappa: electron temperature from an electron-entropy variable of the snapshot
+    (simulation_coefficients.cpp:351-358; the variable is gathered and interpolated like the other primitives,
+    with its own non-positive fallback), through the .athdf reader of the drop-in executable."""
+    if not os.path.exists(REF_BIN):
+        pytest.skip('oracle/_ref/blacklight not present')
+    over = dict(over, plasma_model='code_kappa', simulation_kappa_name='r0')
+    case = Case(tmp_path, 'simulation.input', over, mock=dict(blocks=(1, 2, 2), entropy=True))
+    ref = case.run_reference(checkpoints=False)
+    cfg, ctx, image, _, _ = run_gpu_level0(case)
+    mine = image_arrays(case, image, cfg.resolution)
+    assert float(np.nanmax(ref['npz']['I_nu'])) > 0.0
+    assert rel_err(mine['I_nu'], ref['npz']['I_nu']) <= PIXEL_TOL
+    assert flux_rel(mine['I_nu'], ref['npz']['I_nu']) <= FLUX_TOL
+    if over.get('image_polarization') == 'true':
+        for k, v in stokes_err(mine, ref['npz']).items():
+            assert v <= PIXEL_TOL, '%s %.3e' % (k, v)
+    ctx.close()
+    npz, _ = case.run_gpu_file()   # the reader locates the variable by name
+    assert rel_err(npz['I_nu'], ref['npz']['I_nu']) <= PIXEL_TOL
+
+
 def test_waves_match_resident(gpu, tmp_path):
     """Tracing in waves (step buffer reused) must give the same image as a resident level, bit for bit."""
     case = Case(tmp_path, 'simulation.input', {'camera_resolution': 48})
