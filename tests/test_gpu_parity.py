@@ -131,6 +131,16 @@ def test_golden_unpolarized(name, gpu, tmp_path):
                           'image_frequency_spacing': 'log'}, None),
     ('simulation.input', {'camera_resolution': 32, 'fallback_nan': 'false', 'fallback_rho': '1.0e-6', 'fallback_pgas': '1.0e-8', 'camera_r': '80.0', 'camera_width': '60.0'}, None),
     ('simulation.input', {'camera_resolution': 32, 'cut_omit_near': 'true', 'cut_omit_in': '3.0', 'cut_midplane_theta': '30.0', 'cut_rho_min': '1.0e-18'}, None),
+    ('simulation.input', {'camera_resolution': 32, 'plasma_use_p': 'false', 'plasma_gamma_i': '1.6666666666666667',
+                          'plasma_gamma_e': '1.3333333333333333', 'plasma_gamma': '1.5'}, None),
+    ('simulation.input', {'camera_resolution': 28, 'cut_omit_far': 'true', 'cut_omit_out': '30.0', 'cut_midplane_z': '6.0',
+                          'cut_plane': 'true', 'cut_plane_origin': '1.0,0.0,0.5', 'cut_plane_normal': '0.2,1.0,0.1',
+                          'cut_sigma_max': '-1.0', 'cut_beta_inverse_max': '5.0', 'cut_theta_e_max': '50.0'}, None),
+    ('simulation.input', {'camera_resolution': 24, 'image_num_frequencies': 2, 'image_frequency_start': '1.0e11',
+                          'image_frequency_end': '4.0e11', 'image_frequency_spacing': 'log', 'image_time': 'true',
+                          'image_length': 'true', 'image_lambda': 'true', 'image_emission': 'true', 'image_tau': 'true',
+                          'image_lambda_ave': 'true', 'image_emission_ave': 'true', 'image_tau_int': 'true',
+                          'image_crossings': 'true'}, {'blocks': (1, 2, 2)}),
     ('formula.input', {'camera_resolution': 24, 'image_num_frequencies': 3, 'image_frequency_start': '1.0e11', 'image_frequency_end': '4.0e11', 'image_frequency_spacing': 'lin_wave', 'camera_th': '0.0'}, None),
     ('formula.input', {'camera_resolution': 20, 'ray_flat': 'true', 'formula_l0': '1.0'}, None),
 ])
@@ -360,6 +370,10 @@ def test_golden_polarized(name, gpu, tmp_path):
      'image_tau': 'true', 'image_emission': 'true'},
     {'camera_resolution': 20, 'image_polarization': 'true', 'simulation_a': '0.9', 'camera_th': '20.0', 'camera_rotation': '30.0',
      'image_normalization': 'camera', 'camera_urn': '0.1'},
+    {'camera_resolution': 16, 'image_polarization': 'true', 'image_num_frequencies': 2, 'image_frequency_start': '2.3e11',
+     'image_frequency_end': '4.6e11', 'image_frequency_spacing': 'log', 'image_time': 'true', 'image_length': 'true',
+     'image_lambda': 'true', 'image_emission': 'true', 'image_tau': 'true', 'image_lambda_ave': 'true',
+     'image_emission_ave': 'true', 'image_tau_int': 'true', 'image_crossings': 'true'},
 ])
 def test_live_reference_polarized(over, gpu, tmp_path):
     if not os.path.exists(REF_BIN):
