@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "athdf.hpp"
+#include "harm3d.hpp"
 #include "config.hpp"
 #include "npz_writer.hpp"
 
@@ -257,7 +258,26 @@ RunTimings run_input_file(const std::string &path, int device, bool quiet) {
   validate_output_options(cfg);
   bl_params &p = cfg.params;
   const bool sim = p.model_type == BL_MODEL_SIMULATION;
-  if (sim && cfg.simulation_format != 0) throw Error("Only simulation_format = athena is inside the B200 hot-path scope.");
+  if (sim && cfg.simulation_format != 0 && cfg.simulation_format != 3)
+    throw Error("Only simulation_format = athena and harm3d are inside the B200 hot-path scope.");
+  const bool harm = sim && cfg.simulation_format == 3;
+  if (harm && !cfg.gamma_set) {
+    // the adiabatic index comes from the file header and is a kernel parameter: read it before bl_create
+    std::string first = cfg.simulation_multiple ? format_numbered(cfg.simulation_file, cfg.simulation_start, "simulation_file")
+                                                : cfg.simulation_file;
+    read_harm3d_header(first, nullptr, &p.plasma_gamma);
+  }
+  auto read_snapshot = [&](const std::string &file, bool reuse, AthenaGrid &into) {
+    if (harm)
+      read_harm3d(file, p.plasma_model == BL_PLASMA_CODE_KAPPA, true, &p.plasma_gamma, p.bh_a, reuse, into);
+    else
+      read_athdf(file, p.plasma_model == BL_PLASMA_CODE_KAPPA ? cfg.simulation_kappa_name : "", reuse, into);
+  };
+  auto snapshot_time_of = [&](const std::string &file) {
+    double t = 0.0;
+    if (harm) read_harm3d_header(file, &t, nullptr); else t = read_athdf_time(file);
+    return t;
+  };
   if (device < 0) {
     const char *env = std::getenv("BLACKLIGHT_DEVICE");
     device = env ? std::atoi(env) : 0;
@@ -323,7 +343,7 @@ RunTimings run_input_file(const std::string &path, int device, bool quiet) {
       }
       while (latest_time < snapshot_time && latest_file_number < cfg.simulation_end) {
         latest_file_number++;
-        latest_time = read_athdf_time(format_numbered(cfg.simulation_file, latest_file_number, "simulation_file"));
+        latest_time = snapshot_time_of(format_numbered(cfg.simulation_file, latest_file_number, "simulation_file"));
       }
       if (latest_time < snapshot_time - tol) {
         std::ostringstream msg;
@@ -352,7 +372,7 @@ RunTimings run_input_file(const std::string &path, int device, bool quiet) {
       }
       for (int t = 0; t < num_read; t++) {
         std::string file = format_numbered(cfg.simulation_file, latest_file_number - t, "simulation_file");
-        read_athdf(file, p.plasma_model == BL_PLASMA_CODE_KAPPA ? cfg.simulation_kappa_name : "", !first_read, grid);
+        read_snapshot(file, !first_read, grid);
         first_read = false;
         window_time[(size_t)t] = grid.time;
         bl_grid_view view = grid.view();
@@ -364,7 +384,7 @@ RunTimings run_input_file(const std::string &path, int device, bool quiet) {
       t0 = now_s();
       std::string file = cfg.simulation_file;
       if (cfg.simulation_multiple) file = format_numbered(cfg.simulation_file, cfg.simulation_start + n, "simulation_file");
-      read_athdf(file, p.plasma_model == BL_PLASMA_CODE_KAPPA ? cfg.simulation_kappa_name : "", n > 0, grid);
+      read_snapshot(file, n > 0, grid);
       bl_grid_view view = grid.view();
       check(ctx, bl_upload_grid(ctx, &view));
       T.read += now_s() - t0;

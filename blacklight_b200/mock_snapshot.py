@@ -253,6 +253,55 @@ def write_athdf(path, grid, time=0.0):
         f.truncate(eof)
 
 
+def write_harm3d(path, fields, gamma_adi=4.0 / 3.0, time=0.0):
+    """Write the single-block mock (output of mock_fields) in the 'harm3d' ascii-header + binary format
+    (reference scripts/generate_mock_simulation.py:79-157,245-279): modified Kerr-Schild coordinates
+    x1 = ln r, x2 = theta / pi (h = 1), x3 = phi; per cell 6 coordinates, rho, u_gas and the coordinate-frame
+    four-velocity and magnetic four-vector, float32, with the variable index fastest."""
+    rf, thf, phf, r, th, ph = (fields[k] for k in ('rf', 'thf', 'phf', 'r', 'th', 'ph'))
+    rho, pgas, uur, uuth, uuph, bbr, bbth, bbph = (fields['prim'][q].astype(np.float64) for q in range(8))
+    R, TH = r[None, None, :], th[None, :, None]
+    sigma = R ** 2
+    f = 2.0 * R / sigma
+    g_tt, g_tr, g_rr, g_thth, g_phph = -(1.0 - f), f, 1.0 + f, sigma, R ** 2 * np.sin(TH) ** 2
+    gtt, gtr = -(1.0 + f), f
+    alpha = 1.0 / np.sqrt(-gtt)
+    ugas = pgas / (gamma_adi - 1.0)
+    uut = np.sqrt(1.0 + g_rr * uur ** 2 + g_thth * uuth ** 2 + g_phph * uuph ** 2)
+    ut = uut / alpha
+    ur = uur - alpha * uut * gtr
+    uth, uph = uuth, uuph
+    u_r = g_tr * ut + g_rr * ur
+    u_th = g_thth * uth
+    u_ph = g_phph * uph
+    u0, u1, u2, u3 = ut, ur / R, uth / np.pi, uph
+    bt = u_r * bbr + u_th * bbth + u_ph * bbph
+    br = (bbr + bt * ur) / ut
+    bth = (bbth + bt * uth) / ut
+    bph = (bbph + bt * uph) / ut
+    b0, b1, b2, b3 = bt, br / R, bth / np.pi, bph
+    lrf, lr = np.log(rf), np.log(r)
+    x2f, x2 = thf / np.pi, th / np.pi
+    dlr, dx2, dph = lrf[1] - lrf[0], x2f[1] - x2f[0], phf[1] - phf[0]
+    shape = rho.shape
+    data = [np.broadcast_to(lr[None, None, :], shape), np.broadcast_to(x2[None, :, None], shape),
+            np.broadcast_to(ph[:, None, None], shape), np.broadcast_to(r[None, None, :], shape),
+            np.broadcast_to(th[None, :, None], shape), np.broadcast_to(ph[:, None, None], shape),
+            rho, ugas, u0 * np.ones(shape), u1 * np.ones(shape), u2 * np.ones(shape), u3 * np.ones(shape),
+            b0 * np.ones(shape), b1 * np.ones(shape), b2 * np.ones(shape), b3 * np.ones(shape)]
+    with open(path, 'w') as f_out:
+        f_out.write('{0:24.16e} '.format(time))
+        f_out.write('{0} {1} {2} '.format(len(r), len(th), len(ph)))
+        f_out.write('{0:24.16e} {1:24.16e} {2:24.16e} '.format(lrf[0], x2f[0], phf[0]))
+        f_out.write('{0:24.16e} {1:24.16e} {2:24.16e} '.format(dlr, dx2, dph))
+        f_out.write('0.0 ')
+        f_out.write('{0:24.16e} '.format(gamma_adi))
+        f_out.write('{0:24.16e} '.format(rf[0]))
+        f_out.write('1.0 ')
+        f_out.write('8\n')
+        np.array(data, dtype=np.float32).transpose().tofile(f_out)
+
+
 def grid_view_arrays(grid):
     """Arrays in the layout SimulationReader hands to the integrator (float32 coords widened to f64)."""
     if 'kappa' in grid:   # the reader stacks hydro (with the entropy variable last) before the field

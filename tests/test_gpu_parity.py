@@ -529,6 +529,51 @@ def test_slow_light_against_reference(over, gpu, tmp_path):
     assert rel_err(images['gpu'][2]['I_nu'], images['gpu'][0]['I_nu']) > 1e-3
 
 
+@pytest.mark.parametrize('over', [
+    {'camera_resolution': 32},
+    {'camera_resolution': 24, 'image_polarization': 'true', 'simulation_a': '0.0'},
+    {'camera_resolution': 24, 'plasma_gamma': '1.5', 'plasma_use_p': 'false', 'plasma_gamma_i': '1.6666666666666667',
+     'plasma_gamma_e': '1.3333333333333333'},
+])
+def test_harm3d_reader_against_reference(over, gpu, tmp_path):
+    """simulation_format = harm3d: ascii header + float32 cell records in modified Kerr-Schild coordinates,
+    converted on the host to spherical Kerr-Schild coordinates / normal-frame primitives exactly as the
+    reference's reader does (simulation_reader.cpp:661-720,808-848, simulation_geometry.cpp:29-92,242-327);
+    the device path is unchanged.  Through the drop-in executable, against the reference binary."""
+    if not os.path.exists(REF_BIN):
+        pytest.skip('oracle/_ref/blacklight not present')
+    import subprocess
+    from blacklight_b200 import mock_snapshot as ms
+    from harness import write_input
+    d = str(tmp_path)
+    case = Case(d, 'simulation.input', over)
+    snap = os.path.join(d, 'data', 'mock.harm3d')
+    ms.write_harm3d(snap, ms.mock_fields(n_r=48, n_th=32, n_ph=32), time=3.0)
+    images = {}
+    for who in ('ref', 'gpu'):
+        kv = dict(case.kv)
+        kv.update({'simulation_format': 'harm3d', 'simulation_file': snap, 'simulation_coord': 'sks',
+                   'output_file': os.path.join(d, who + '.npz')})
+        if 'plasma_gamma' not in over:
+            kv.pop('plasma_gamma', None)     # taken from the file header
+        kv.pop('simulation_block_interp', None)
+        path = os.path.join(d, who + '.input')
+        write_input(path, kv)
+        if who == 'ref':
+            proc = subprocess.run([REF_BIN, path], cwd=d, capture_output=True, text=True, timeout=3600)
+            assert proc.returncode == 0 and 'Calculation completed' in proc.stdout, proc.stdout + proc.stderr
+        else:
+            bl.run_input_file(path)
+        images[who] = dict(np.load(os.path.join(d, who + '.npz')))
+    ref, mine = images['ref'], images['gpu']
+    assert float(np.nanmax(ref['I_nu'])) > 0.0
+    assert rel_err(mine['I_nu'], ref['I_nu']) <= PIXEL_TOL
+    assert flux_rel(mine['I_nu'], ref['I_nu']) <= FLUX_TOL
+    if over.get('image_polarization') == 'true':
+        for k, v in stokes_err(mine, ref).items():
+            assert v <= PIXEL_TOL, '%s %.3e' % (k, v)
+
+
 def test_geodesic_checkpoint_exchange_with_reference(gpu, tmp_path):
     """checkpoint_geodesic_load: geodesics integrated by the REFERENCE (its checkpoint file, reference byte format)
     are loaded into the step buffer instead of tracing (bl_upload_samples).  Because the CUDA integrator is
