@@ -574,6 +574,29 @@ def test_harm3d_reader_against_reference(over, gpu, tmp_path):
             assert v <= PIXEL_TOL, '%s %.3e' % (k, v)
 
 
+def test_adaptive_two_levels_with_forced_region_against_reference(gpu, tmp_path):
+    """Two refinement levels (a forced region plus the relative-Laplacian criterion), polarized, through the
+    drop-in executable: block lists, block counts and every per-level image against the reference."""
+    if not os.path.exists(REF_BIN):
+        pytest.skip('oracle/_ref/blacklight not present')
+    over = {'camera_resolution': 32, 'adaptive_max_level': 2, 'adaptive_block_size': 8, 'adaptive_num_regions': 1,
+            'adaptive_region_1_level': 2, 'adaptive_region_1_x_min': '-3.0', 'adaptive_region_1_x_max': '5.0',
+            'adaptive_region_1_y_min': '-4.0', 'adaptive_region_1_y_max': '1.0', 'adaptive_rel_lapl_cut': '0.5',
+            'adaptive_rel_lapl_frac': '0.1', 'adaptive_abs_grad_frac': '-1.0'}
+    case = Case(tmp_path, 'adaptive.input', over)
+    ref = case.run_reference(checkpoints=False)['npz']
+    mine, _ = case.run_gpu_file()
+    assert int(ref['adaptive_num_levels'][0]) == 2
+    assert int(mine['adaptive_num_levels'][0]) == 2
+    assert np.array_equal(mine['adaptive_num_blocks'], ref['adaptive_num_blocks'])
+    for level in (1, 2):
+        assert np.array_equal(mine['adaptive_block_locs_%d' % level], ref['adaptive_block_locs_%d' % level])
+    for k in ref:
+        if k.endswith('I_nu') or 'I_nu_' in k or k.endswith('tau') or 'tau_' in k:
+            assert mine[k].shape == ref[k].shape, k
+            assert rel_err(mine[k], ref[k]) <= PIXEL_TOL, k
+
+
 def test_geodesic_checkpoint_exchange_with_reference(gpu, tmp_path):
     """checkpoint_geodesic_load: geodesics integrated by the REFERENCE (its checkpoint file, reference byte format)
     are loaded into the step buffer instead of tracing (bl_upload_samples).  Because the CUDA integrator is
