@@ -54,6 +54,9 @@ def parse_args():
     ap.add_argument('--resolution', type=int, default=1024, help='image side per GPU (weak scaling)')
     ap.add_argument('--workload', default='simulation', choices=['simulation', 'formula', 'polarized'])
     ap.add_argument('--tile-rays', type=int, default=0)
+    ap.add_argument('--grid-scale', type=int, default=1,
+                    help='refine the mock snapshot by this factor per dimension (4: 308x256x512 cells, 1.3 GB of primitives -- '
+                         'the gather leaves L2 and becomes HBM traffic; SURVEY.md section 8d)')
     ap.add_argument('--cpu-resolution', type=int, default=0, help='side of the bounded CPU sample (0 = auto)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     return ap.parse_args()
@@ -67,14 +70,17 @@ def workload_case(args, workdir, resolution, write_mock):
         over.update({'image_polarization': 'true', 'image_num_frequencies': 4, 'image_frequency_start': '8.6e10',
                      'image_frequency_end': '3.45e11', 'image_frequency_spacing': 'log', 'plasma_kappa_frac': '1.0',
                      'plasma_kappa': '4.0', 'plasma_w': '1.0'})
-    case = Case(workdir, base, over)
-    if not write_mock and case.sim:
-        pass
+    mock = None
+    if args.grid_scale > 1 and base == 'simulation.input':
+        k = args.grid_scale
+        mock = {'n_r': 77 * k, 'n_th': 64 * k, 'n_ph': 128 * k}
+    case = Case(workdir, base, over, mock=mock)
     return case
 
 
 def workload_name(args, res_total, n_gpus):
-    d = {'simulation': 'mock Athena++ snapshot (77x64x128 SKS, generate_mock_simulation defaults), example_simulation '
+    g = '%dx%dx%d' % (77 * args.grid_scale, 64 * args.grid_scale, 128 * args.grid_scale)
+    d = {'simulation': 'mock Athena++ snapshot (' + g + ' SKS, generate_mock_simulation defaults), example_simulation '
                        'parameters: unpolarized thermal synchrotron, trilinear sampling, DP geodesics',
          'formula': 'example_formula parameters: formula plasma, DP geodesics',
          'polarized': 'mock Athena++ snapshot, polarized kappa=4 synchrotron, 4 frequencies'}[args.workload]
