@@ -633,20 +633,26 @@ def test_division_sqrt_sequences(gpu, tmp_path):
         ctx.close()
 
 
-def test_full_resolution_window_against_reference(gpu, tmp_path):
+@pytest.mark.parametrize('root,levels,pol,window', [
+    (32, 2, False, ('-4.0', '7.0', '-5.0', '2.0')),
+    (256, 2, False, ('-1.0', '4.5', '-3.5', '0.5')),      # the benchmark's 1024^2 frame
+    (256, 4, True, ('1.0', '3.2', '-2.5', '-1.0')),       # the 4096^2 polarized target frame (traced in waves)
+])
+def test_full_resolution_window_against_reference(root, levels, pol, window, gpu, tmp_path):
     """Parity at a resolution the reference cannot hold in memory as a full frame: a coarse
     root image whose forced refinement region is refined twice makes the reference trace EXACTLY the pixel rays
     that a 4x finer full frame has inside that window (same u_ind/v_ind expression, camera.cpp:393-396 vs
     :476-479).  The CUDA path renders the fine full frame in one piece; its window must match the reference's
-    level-2 blocks pixel by pixel.  (Here 32^2 root -> 128^2 frame; the recipe is resolution independent.)"""
+    deepest-level blocks pixel by pixel.  32^2 root -> 128^2 frame, 256^2 root -> the benchmark's 1024^2 frame and,
+    with four levels and polarization, the 4096^2 Stokes frame of the north-star target."""
     if not os.path.exists(REF_BIN):
         pytest.skip('oracle/_ref/blacklight not present')
-    root, bs, levels = 32, 8, 2
+    bs = 8
     fine = root * 2 ** levels
-    over = {'camera_resolution': root, 'image_polarization': 'false', 'image_tau': 'false',
+    over = {'camera_resolution': root, 'image_polarization': 'true' if pol else 'false', 'image_tau': 'false',
             'adaptive_max_level': levels, 'adaptive_block_size': bs, 'adaptive_num_regions': 1,
-            'adaptive_region_1_level': levels, 'adaptive_region_1_x_min': '-4.0', 'adaptive_region_1_x_max': '7.0',
-            'adaptive_region_1_y_min': '-5.0', 'adaptive_region_1_y_max': '2.0',
+            'adaptive_region_1_level': levels, 'adaptive_region_1_x_min': window[0], 'adaptive_region_1_x_max': window[1],
+            'adaptive_region_1_y_min': window[2], 'adaptive_region_1_y_max': window[3],
             'adaptive_val_frac': '-1.0', 'adaptive_abs_grad_frac': '-1.0', 'adaptive_rel_grad_frac': '-1.0',
             'adaptive_abs_lapl_frac': '-1.0', 'adaptive_rel_lapl_frac': '-1.0'}
     case = Case(tmp_path / 'ref', 'adaptive.input', over)
@@ -661,4 +667,13 @@ def test_full_resolution_window_against_reference(gpu, tmp_path):
     frame = image[0].reshape(fine, fine)
     window = np.stack([frame[v * bs:(v + 1) * bs, u * bs:(u + 1) * bs] for v, u in locs])
     assert rel_err(window, blocks) <= PIXEL_TOL
+    if pol:
+        mine = {'I_nu': window}
+        theirs = {'I_nu': blocks}
+        for s_ind, name in ((1, 'Q_nu'), (2, 'U_nu'), (3, 'V_nu')):
+            plane = image[s_ind].reshape(fine, fine)
+            mine[name] = np.stack([plane[v * bs:(v + 1) * bs, u * bs:(u + 1) * bs] for v, u in locs])
+            theirs[name] = ref['adaptive_%s_%d' % (name, levels)]
+        for k, v in stokes_err(mine, theirs).items():
+            assert v <= PIXEL_TOL, '%s %.3e' % (k, v)
     ctx.close()
