@@ -57,8 +57,7 @@ struct Level {
 
 struct bl_ctx {
   bl_params params;
-  RadParams rad;            // host copy
-  RadParams *rad_dev = nullptr;
+  RadParams rad;            // passed by value (constant bank) with every radiation launch
   bl_params *params_dev = nullptr;
   GridDev grid{};
   std::vector<void *> grid_allocs;
@@ -399,12 +398,10 @@ int bl_create(const bl_params *params, bl_ctx **out) {
   CREATE_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   CREATE_CHECK(cudaEventCreate(&ctx->ev0));
   CREATE_CHECK(cudaEventCreate(&ctx->ev1));
-  CREATE_CHECK(dev_alloc(&ctx->rad_dev, 1));
   CREATE_CHECK(dev_alloc(&ctx->params_dev, 1));
   CREATE_CHECK(dev_alloc(&ctx->counters, 1));
   CREATE_CHECK(dev_alloc(&ctx->rad_counter, 1));
   CREATE_CHECK(dev_alloc(&ctx->slow_counters, 8));
-  CREATE_CHECK(cudaMemcpy(ctx->rad_dev, &ctx->rad, sizeof(RadParams), cudaMemcpyHostToDevice));
   CREATE_CHECK(cudaMemcpy(ctx->params_dev, &ctx->params, sizeof(bl_params), cudaMemcpyHostToDevice));
 #undef CREATE_CHECK
   *out = ctx;
@@ -416,7 +413,7 @@ void bl_destroy(bl_ctx *ctx) {
   cudaSetDevice(ctx->device);
   for (auto &L : ctx->levels) free_level(L);
   for (void *p : ctx->grid_allocs) cudaFree(p);
-  cudaFree(ctx->rad_dev); cudaFree(ctx->params_dev); cudaFree(ctx->counters); cudaFree(ctx->rad_counter); cudaFree(ctx->slow_counters);
+  cudaFree(ctx->params_dev); cudaFree(ctx->counters); cudaFree(ctx->rad_counter); cudaFree(ctx->slow_counters);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
