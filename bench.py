@@ -35,7 +35,8 @@ FLOP_PER_SAMPLE = 220.0
 # coefficients 60 flop + transfer 10 flop + 8 libm calls (exp, expm1, cbrt, 2 sqrt, pow; exp, expm1);
 # polarized: 6.1 kflop transport/coupling + (thermal 180 flop + 15 calls | kappa 250 flop + 45 calls).
 RAD_FLOP_PER_SAMPLE = 60.0 + 950.0 + 12 * 80.0
-RAD_FLOP_PER_SAMPLE_FREQ = {'simulation': 70.0 + 8 * 80.0, 'formula': 70.0 + 5 * 80.0, 'polarized': 6100.0 + 250.0 + 45 * 80.0}
+RAD_FLOP_PER_SAMPLE_FREQ = {'simulation': 70.0 + 8 * 80.0, 'formula': 70.0 + 5 * 80.0, 'polarized': 6100.0 + 250.0 + 45 * 80.0,
+                            'polarized_thermal': 6100.0 + 180.0 + 15 * 80.0}
 # Algorithmic bytes per sample: trilinear gather of 8 variables and one 64-byte
 # step-buffer record written by the geodesic kernel and read once by the radiation kernel
 GATHER_BYTES_PER_SAMPLE = 256.0
@@ -52,7 +53,7 @@ def parse_args():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--resolution', type=int, default=1024, help='image side per GPU (weak scaling)')
-    ap.add_argument('--workload', default='simulation', choices=['simulation', 'formula', 'polarized'])
+    ap.add_argument('--workload', default='simulation', choices=['simulation', 'formula', 'polarized', 'polarized_thermal'])
     ap.add_argument('--tile-rays', type=int, default=0)
     ap.add_argument('--grid-scale', type=int, default=1,
                     help='refine the mock snapshot by this factor per dimension (4: 308x256x512 cells, 1.3 GB of primitives -- '
@@ -64,7 +65,8 @@ def parse_args():
 
 def workload_case(args, workdir, resolution, write_mock):
     from harness import Case
-    base = {'simulation': 'simulation.input', 'formula': 'formula.input', 'polarized': 'simulation.input'}[args.workload]
+    base = {'simulation': 'simulation.input', 'formula': 'formula.input', 'polarized': 'simulation.input',
+            'polarized_thermal': 'simulation.input'}[args.workload]
     over = {'camera_resolution': resolution}
     if args.workload == 'polarized':
         over.update({'image_polarization': 'true', 'image_num_frequencies': 4, 'image_frequency_start': '8.6e10',
@@ -74,6 +76,8 @@ def workload_case(args, workdir, resolution, write_mock):
     if args.grid_scale > 1 and base == 'simulation.input':
         k = args.grid_scale
         mock = {'n_r': 77 * k, 'n_th': 64 * k, 'n_ph': 128 * k}
+    if args.workload == 'polarized_thermal':
+        over.update({'image_polarization': 'true'})
     case = Case(workdir, base, over, mock=mock)
     return case
 
@@ -83,7 +87,8 @@ def workload_name(args, res_total, n_gpus):
     d = {'simulation': 'mock Athena++ snapshot (' + g + ' SKS, generate_mock_simulation defaults), example_simulation '
                        'parameters: unpolarized thermal synchrotron, trilinear sampling, DP geodesics',
          'formula': 'example_formula parameters: formula plasma, DP geodesics',
-         'polarized': 'mock Athena++ snapshot, polarized kappa=4 synchrotron, 4 frequencies'}[args.workload]
+         'polarized': 'mock Athena++ snapshot, polarized kappa=4 synchrotron, 4 frequencies',
+         'polarized_thermal': 'mock Athena++ snapshot, polarized thermal synchrotron, 1 frequency'}[args.workload]
     return '%s; image %dx%d over %d GPU(s)' % (d, res_total, res_total, n_gpus)
 
 
@@ -356,7 +361,7 @@ def main():
             hbm_peak = peaks.get('hbm_gbs', 6650.0)
             hbm_src = 'MEASURED_PEAKS.json hbm_gbs (of measured)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s (of fallback)'
             peak_src = 'DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry); no-FMA code such as the bit-exact geodesic kernel is bounded by half of it'
-            rad_name = 'radiate_polarized_kernel' if args.workload == 'polarized' else 'radiate_unpolarized_kernel'
+            rad_name = 'radiate_polarized_kernel' if args.workload.startswith('polarized') else 'radiate_unpolarized_kernel'
             roofs = {
                 'geodesic_dp_kernel': {'kernel': 'geodesic_dp_kernel', 'bound': 'fp64', 'achieved': geo_tflops, 'peak': fp64_peak,
                                        'unit': 'TFLOP/s', 'frac': geo_tflops / fp64_peak if fp64_peak else None,

@@ -207,54 +207,6 @@ __device__ __forceinline__ void stokes_map(const LegProj L[2], double h, double 
   M.vv = 0.5 * (Pm[1][0][1][0] - Pm[0][1][1][0] - Pm[1][0][0][1] + Pm[0][1][0][1]);
 }
 
-// ---------------------------------------------------------------------------------------------------
-// Modified Bessel functions K_0, K_1 (the reference calls std::cyl_bessel_k, simulation_coefficients.cpp:537-539).
-// x < 2: ascending series (Abramowitz & Stegun 9.6.11, 9.6.13); x >= 2: Steed's continued fraction CF2
-// (the method libstdc++'s __bessel_ik uses there).  Relative accuracy ~2e-15 (checked against scipy).
-__device__ __forceinline__ void bessel_k01(double x, double &k0, double &k1) {
-  const double euler = 0.5772156649015328606;
-  if (x < 2.0) {
-    double q = 0.25 * x * x, lg = log(0.5 * x);
-    double term = 1.0, i0 = 1.0, s0 = 0.0, hk = 0.0;
-    double t1 = 1.0, i1s = 1.0, s1 = 1.0 - 2.0 * euler;
-    for (int k = 1; k < 40; k++) {
-      double dk = (double)k;
-      term *= q / (dk * dk);
-      hk += 1.0 / dk;
-      i0 += term;
-      s0 += term * hk;
-      t1 *= q / (dk * (dk + 1.0));
-      i1s += t1;
-      s1 += t1 * (2.0 * (hk - euler) + 1.0 / (dk + 1.0));
-      if (term < 1e-17 * i0 && t1 < 1e-17 * i1s) break;
-    }
-    k0 = -(lg + euler) * i0 + s0;
-    k1 = 1.0 / x + lg * (0.5 * x * i1s) - 0.25 * x * s1;
-    return;
-  }
-  double b = 2.0 * (1.0 + x), d = 1.0 / b, h = d, delh = d;
-  double q1 = 0.0, q2 = 1.0, a1 = 0.25, q = a1, c = a1, a = -a1;
-  double s = 1.0 + q * delh;
-  for (int i = 2; i < 500; i++) {
-    a -= 2.0 * (i - 1);
-    c = -a * c / i;
-    double qnew = (q1 - b * q2) / a;
-    q1 = q2;
-    q2 = qnew;
-    q += c * qnew;
-    b += 2.0;
-    d = 1.0 / (b + a * d);
-    delh = (b * d - 1.0) * delh;
-    h += delh;
-    double dels = q * delh;
-    s += dels;
-    if (fabs(dels / s) < 1e-16) break;
-  }
-  h = a1 * h;
-  k0 = sqrt(phys::pi / (2.0 * x)) * exp(-x) / s;
-  k1 = k0 * (x + 0.5 - h) / x;
-}
-
 struct Coefficients {
   double j[3], a[3], rho[2];  // (I,Q,V), (I,Q,V), (Q,V); Stokes U components vanish in this tetrad
 };
@@ -294,7 +246,7 @@ __device__ __forceinline__ void pol_sample(const RadParams &P, const rad::Plasma
   if (P.thermal_frac != 0.0) {
     q.inv_nu_s = 4.5 * s.inv_theta_e * s.inv_theta_e / (q.nu_c * sin_b);
     q.h_kt = phys::h * s.inv_theta_e * (1.0 / (phys::m_e * phys::c * phys::c));
-    double te96 = pow(s.theta_e, 0.96);
+    double te96 = exp(0.96 * log(s.theta_e));
     q.var_d = (7.0 * te96 + 35.0) / (10.0 * te96 + 75.0) * 1.8877486253633870;
     q.cos_over_theta = cos_b * s.inv_theta_e;
     if (s.theta_e >= 0.01) {
@@ -759,7 +711,7 @@ radiate_polarized_kernel(const __grid_constant__ RadArgs A, const __grid_constan
       double sin_theta_b = sqrt(1.0 - c2);
       double cos_theta_b = sqrt(c2) * (kb >= 0.0 ? 1.0 : -1.0);
       if (P.thermal_frac != 0.0 && ps.theta_e >= 0.01) {
-        bessel_k01(ps.inv_theta_e, kk[0], kk[1]);
+        bfm::bessel_k01(ps.inv_theta_e, kk[0], kk[1]);
         kk[2] = kk[0] + 2.0 * ps.theta_e * kk[1];
       }
       pol_sample(P, ps, omega * mom, sin_theta_b, cos_theta_b, kk, sq);

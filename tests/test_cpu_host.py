@@ -276,3 +276,32 @@ def test_adaptive_block_sharding_world_size_2_matches_single_rank():
     for (locs, image), L in zip(got, single):
         assert np.array_equal(np.array(locs).reshape(-1, 2), L['locs'])
         assert np.array_equal(np.array(image), L['image'])
+
+
+def test_branch_free_math_against_libm_and_mpmath(tmp_path):
+    """blacklight_b200/csrc/bf_math.cuh compiled for the host: exp_bf / log_bf against libm, bessel_k01 against
+    40-digit values (the radiation kernels use these in their per-frequency coefficient code; the image tolerance
+    is 1e-6, the functions are good to a few ulp)."""
+    import subprocess
+    mp = pytest.importorskip('mpmath')
+    src = os.path.join(tmp_path, 'bf_check.cpp')
+    with open(src, 'w') as f:
+        f.write('#include <cstdio>\n#include <cmath>\n#include "%s"\n' % os.path.join(ROOT, 'blacklight_b200', 'csrc', 'bf_math.cuh'))
+        f.write('int main() { double x; while (scanf("%lf", &x) == 1) { double k0, k1; bfm::bessel_k01(x > 0 ? x : 1.0, k0, k1);\n'
+                '  printf("%.17e %.17e %.17e %.17e %.17e\\n", x, bfm::exp_bf(x), bfm::log_bf(x > 0 ? x : 1.0), k0, k1); } }\n')
+    exe = os.path.join(tmp_path, 'bf_check')
+    subprocess.run(['g++', '-O2', '-ffp-contract=off', '-o', exe, src, '-lm'], check=True)
+    rng = np.random.default_rng(5)
+    xs = np.concatenate([rng.uniform(-700.0, 700.0, 20000), np.exp(rng.uniform(np.log(1e-3), np.log(150.0), 3000)), [2.0, 1.0, 100.0]])
+    out = subprocess.run([exe], input='\n'.join('%.17e' % x for x in xs), capture_output=True, text=True, check=True).stdout
+    v = np.array([[float(t) for t in line.split()] for line in out.strip().splitlines()])
+    x = v[:, 0]
+    assert np.max(np.abs(v[:, 1] - np.exp(x)) / np.exp(x)) < 1e-15
+    pos = x > 0
+    ref_log = np.log(x[pos])
+    assert np.max(np.abs(v[pos, 2] - ref_log) / np.maximum(np.abs(ref_log), 1e-3)) < 2e-15
+    mp.mp.dps = 40
+    sel = np.where((x > 1e-3) & (x < 150.0))[0][-300:]
+    for i in sel:
+        k0, k1 = float(mp.besselk(0, mp.mpf(x[i]))), float(mp.besselk(1, mp.mpf(x[i])))
+        assert abs(v[i, 3] - k0) <= 4e-15 * k0 and abs(v[i, 4] - k1) <= 4e-15 * k1, x[i]

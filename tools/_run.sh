@@ -1,5 +1,4 @@
 set -x
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -4
-timeout 900 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err
-timeout 600 python bench.py --impl reference --steps 1 --warmup 1 > gpurun_out/bench_final_ref.json 2> gpurun_out/bench_final_ref.err
+timeout 900 python -m pytest tests -m gpu -q -k "polar or adaptive or slow or code_kappa or harm3d or block_interp or cartesian" 2>&1 | tail -4
+timeout 300 python bench.py --workload polarized_thermal --resolution 1024 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_polth.json 2> gpurun_out/bench_polth.err
+timeout 300 python bench.py --workload polarized --resolution 512 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_pol512.json 2> gpurun_out/bench_pol512.err
