@@ -30,7 +30,8 @@ struct KsJet {
   double dl[3][3];     // dl[i][a] = d_a l_i
 };
 
-__device__ __forceinline__ void ks_jet(const RadParams &P, double x, double y, double z, KsJet &J) {
+// r and inv_r = 1/r: the Kerr-Schild radius of the point (the caller has them from the sampling stage).
+__device__ __forceinline__ void ks_jet(const RadParams &P, double x, double y, double z, double r, double inv_r, KsJet &J) {
   if (P.ray_flat) {
     J.f = 0.0;
     for (int i = 0; i < 3; i++) {
@@ -42,23 +43,23 @@ __device__ __forceinline__ void ks_jet(const RadParams &P, double x, double y, d
   }
   const double a = P.a, a2 = a * a;
   double rr2 = x * x + y * y + z * z;
-  double r2 = 0.5 * (rr2 - a2 + hypot(rr2 - a2, 2.0 * a * z));
-  double r = sqrt(r2), r4 = r2 * r2;
+  double r2 = r * r, r4 = r2 * r2;
   double den_f = r4 + a2 * z * z;
-  J.f = 2.0 * r2 * r / den_f;
+  double inv_den = 1.0 / den_f;
+  J.f = 2.0 * r2 * r * inv_den;
   double ra = 1.0 / (r2 + a2);
   J.l[0] = (r * x + a * y) * ra;
   J.l[1] = (r * y - a * x) * ra;
-  J.l[2] = z / r;
+  J.l[2] = z * inv_r;
   // reference geodesic_geometry.cpp:203-224 (derivatives of r, f, l)
   double inv = 1.0 / (2.0 * r2 - rr2 + a2);
-  double dr[3] = {r * x * inv, r * y * inv, (r * z + a2 * z / r) * inv};
+  double dr[3] = {r * x * inv, r * y * inv, (r * z + a2 * z * inv_r) * inv};
   double qn = r4 - 3.0 * a2 * z * z;
-  double w = J.f / (r * den_f);
+  double w = J.f * inv_r * inv_den;
   J.df[0] = -qn * dr[0] * w;
   J.df[1] = -qn * dr[1] * w;
   J.df[2] = -(qn * dr[2] + 2.0 * a2 * r * z) * w;
-  double c1 = x - 2.0 * r * J.l[0], c2 = y - 2.0 * r * J.l[1], mz = -z / r2;
+  double c1 = x - 2.0 * r * J.l[0], c2 = y - 2.0 * r * J.l[1], mz = -z * inv_r * inv_r;
   J.dl[0][0] = (c1 * dr[0] + r) * ra;
   J.dl[0][1] = (c1 * dr[1] + a) * ra;
   J.dl[0][2] = c1 * dr[2] * ra;
@@ -67,7 +68,7 @@ __device__ __forceinline__ void ks_jet(const RadParams &P, double x, double y, d
   J.dl[1][2] = c2 * dr[2] * ra;
   J.dl[2][0] = mz * dr[0];
   J.dl[2][1] = mz * dr[1];
-  J.dl[2][2] = mz * dr[2] + 1.0 / r;
+  J.dl[2][2] = mz * dr[2] + inv_r;
 }
 
 // v_mu = g_{mu nu} v^nu and v^mu = g^{mu nu} v_nu
@@ -137,17 +138,17 @@ __device__ __forceinline__ double dot4(const double a[4], const double b[4]) {
 __device__ __forceinline__ void tetrad_legs(const KsJet &J, const double ucon[4], const double ucov[4],
                                             const double kcon[4], const double kcov[4], const double up[4],
                                             double e1[4], double e2[4], double f1[4], double f2[4]) {
-  double omega = -dot4(kcov, ucon);
-  double k_up = dot4(kcov, up) / omega;
-  double u_up = dot4(ucov, up) / omega;
+  double inv_omega = -1.0 / dot4(kcov, ucon);
+  double k_up = dot4(kcov, up) * inv_omega;
+  double u_up = dot4(ucov, up) * inv_omega;
   double e3[4];
-  for (int mu = 0; mu < 4; mu++) e3[mu] = kcon[mu] / omega - ucon[mu];
+  for (int mu = 0; mu < 4; mu++) e3[mu] = kcon[mu] * inv_omega - ucon[mu];
   for (int mu = 0; mu < 4; mu++) e2[mu] = up[mu] - k_up * e3[mu] + u_up * kcon[mu];
   lower(J, e2, f2);
-  double norm = sqrt(dot4(f2, e2));
+  double inv_norm = rsqrt(dot4(f2, e2));
   for (int mu = 0; mu < 4; mu++) {
-    e2[mu] /= norm;
-    f2[mu] /= norm;
+    e2[mu] *= inv_norm;
+    f2[mu] *= inv_norm;
   }
   const double *t0 = ucon, *t2 = e2, *t3 = e3;
   f1[0] = t0[1] * (t2[3] * t3[2] - t2[2] * t3[3]) + t0[2] * (t2[1] * t3[3] - t2[3] * t3[1]) +
@@ -664,7 +665,7 @@ radiate_polarized_kernel(const __grid_constant__ RadArgs A, const __grid_constan
 
     // ---- geometry: metric jet, momenta, fluid-frame tetrad ----
     KsJet jet;
-    ks_jet(P, x, y, z, jet);
+    ks_jet(P, x, y, z, r, inv_r, jet);
     double kcon[4], ucov[4];
     raise(jet, kc, kcon);
     lower(jet, ps.ucon, ucov);
@@ -795,7 +796,9 @@ BL_FREQ_LOOP
       // last half step of transport, then projection on the camera tetrad (polarized.cpp:816-833, :875-939)
       const double *cp = A.cam_pos + 4 * m, *cd = A.cam_dir + 4 * m;
       KsJet jc;
-      ks_jet(P, cp[1], cp[2], cp[3], jc);
+      double inv_rc;
+      double rc = rad::ks_radius(P.a, cp[1], cp[2], cp[3], inv_rc);
+      ks_jet(P, cp[1], cp[2], cp[3], rc, inv_rc, jc);
       double kcov[4] = {cd[0], cd[1], cd[2], cd[3]}, kcon[4];
       raise(jc, kcov, kcon);
       const double *uc = P.camera_u_con, *ul = P.camera_u_cov, *vc = P.camera_vert_con_c;
