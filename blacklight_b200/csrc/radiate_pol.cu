@@ -247,22 +247,22 @@ __device__ __forceinline__ void pol_sample(const RadParams &P, const rad::Plasma
   if (P.thermal_frac != 0.0) {
     q.inv_nu_s = 4.5 * s.inv_theta_e * s.inv_theta_e / (q.nu_c * sin_b);
     q.h_kt = phys::h * s.inv_theta_e * (1.0 / (phys::m_e * phys::c * phys::c));
-    double te96 = exp(0.96 * log(s.theta_e));
+    double te96 = bfm::exp_bf(0.96 * bfm::log_bf(s.theta_e));
     q.var_d = (7.0 * te96 + 35.0) / (10.0 * te96 + 75.0) * 1.8877486253633870;
     q.cos_over_theta = cos_b * s.inv_theta_e;
     if (s.theta_e >= 0.01) {
-      q.log_inv_nu_s = log(q.inv_nu_s);
+      q.log_inv_nu_s = bfm::log_bf(q.inv_nu_s);
       q.inv_k2 = 1.0 / kk[2];
       q.k1_k2 = kk[1] * q.inv_k2;
       q.k0 = kk[0];
     }
   }
-  q.log_om = log(om);
+  q.log_om = bfm::log_bf(om);
   q.log_ncs = q.log_ne = q.cot = q.power_vb = q.inv_nu_k = 0.0;
   q.lvd_j = q.lvf_j = q.lvd_a = q.lvf_a = 0.0;
   if (P.power_frac != 0.0 || P.kappa_frac != 0.0) {
     q.log_ncs = log(q.nu_c * sin_b);
-    q.log_ne = log(s.n_e_cgs);
+    q.log_ne = bfm::log_bf(s.n_e_cgs);
     double log_sin = log(sin_b);
     if (P.power_frac != 0.0) {
       q.cot = cos_b / sin_b;
@@ -315,7 +315,8 @@ __device__ __forceinline__ void synchrotron_polarized(const RadParams &P, const 
       double vb = cos(39.89 * xx_neg_1_2) * bfm::exp_bf(-70.16 * bfm::exp_bf(-0.6 * lx));
       double vc = 0.011 * bfm::exp_bf(-1.69 * xx_neg_1_2);
       double vd = 0.003135 * xx * xx_1_3;
-      double ve = 0.5 * (1.0 + tanh(10.0 * (-0.4082690354408987 - 0.5 * lx)));  // ln 0.6648
+      // 0.5 (1 + tanh y) = 1 - 1/(1 + e^(2y)),  y = 10 ln(0.6648 xx^-1/2),  ln 0.6648 = -0.40826...
+      double ve = 1.0 - 1.0 / (1.0 + bfm::exp_bf(20.0 * (-0.4082690354408987 - 0.5 * lx)));
       double f_0 = va - vb - vc;
       double f_m = f_0 + (vc - vd) * ve;
       double delta_jj_5 = 0.4379 * bfm::log_bf(1.0 + 1.3414 * bfm::exp_bf(-0.7515 * lx));
@@ -528,10 +529,9 @@ __device__ __forceinline__ void couple(const RadParams &P, const Coefficients &C
       }
     double ex = 0.0, sn = 0.0, cs = 0.0, snh = 0.0, csh = 0.0;
     if (thin) {
-      ex = exp(-delta_tau);
+      ex = bfm::exp_bf(-delta_tau);
       sincos(lambda_2 * dl, &sn, &cs);
-      snh = sinh(lambda_1 * dl);
-      csh = cosh(lambda_1 * dl);
+      bfm::sinhcosh_bf(lambda_1 * dl, snh, csh);
     }
     double f_1 = 1.0 / (al[0] * al[0] - lambda_1 * lambda_1);
     double f_2 = 1.0 / (al[0] * al[0] + lambda_2 * lambda_2);
