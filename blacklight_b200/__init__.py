@@ -78,6 +78,9 @@ def load_library():
         'blh_camera_root': (i64, [vp, vp, vp, vp]),
         'blh_camera_refined': (i64, [vp, i32, vp, vp, i64, vp, vp, vp, vp]),
         'blh_run_input_file': (i32, [ctypes.c_char_p, i32, i32, vp]),
+        'blh_snapshot_read': (i32, [vp, ctypes.c_char_p, ctypes.POINTER(vp)]),
+        'blh_snapshot_view': (i32, [vp, ctypes.POINTER(GridView), ctypes.POINTER(dbl), ctypes.POINTER(dbl)]),
+        'blh_snapshot_free': (None, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -298,6 +301,36 @@ class Context:
         nan_, cut, fb = (np.empty((n, s), np.uint8) for _ in range(3))
         self._check(_lib.bl_download_sample_inds(self._h, level, _ptr(inds), _ptr(fracs), _ptr(nan_), _ptr(cut), _ptr(fb)))
         return dict(inds=inds, fracs=fracs, nan=nan_, cut=cut, fallback=fb)
+
+
+def read_snapshot(config, path=None):
+    """Read one snapshot with the reader the input file selects (simulation_format = athena, athenak or harm3d):
+    blh_snapshot_read.  Returns the arrays of bl_grid_view as numpy copies (what Context.upload_grid takes) plus
+    'time' and 'plasma_gamma'."""
+    lib = load_library()
+    h = ctypes.c_void_p()
+    if lib.blh_snapshot_read(config._h, os.fsencode(path) if path else None, ctypes.byref(h)) != 0:
+        raise BlacklightError(lib.blh_last_error().decode())
+    try:
+        v, t, g = GridView(), ctypes.c_double(), ctypes.c_double()
+        lib.blh_snapshot_view(h, ctypes.byref(v), ctypes.byref(t), ctypes.byref(g))
+        out = {n: getattr(v, n) for n, c in GridView._fields_ if c is ctypes.c_int32}
+
+        def arr(ptr, shape, dtype):
+            n = int(np.prod(shape))
+            buf = (ctypes.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr)
+            return np.frombuffer(buf, dtype=dtype).reshape(shape).copy()
+        nb, nk, nj, ni = v.n_b, v.n_k, v.n_j, v.n_i
+        out['levels'] = arr(v.levels, (nb,), np.int32)
+        out['locations'] = arr(v.locations, (nb, 3), np.int32)
+        for name, n in (('x1', ni), ('x2', nj), ('x3', nk)):
+            out[name + 'f'] = arr(getattr(v, name + 'f'), (nb, n + 1), np.float64)
+            out[name + 'v'] = arr(getattr(v, name + 'v'), (nb, n), np.float64)
+        out['prim'] = arr(v.prim, (v.n_var, nb, nk, nj, ni), np.float32)
+        out['time'], out['plasma_gamma'] = t.value, g.value
+        return out
+    finally:
+        lib.blh_snapshot_free(h)
 
 
 def run_input_file(path, device=-1, quiet=True):

@@ -605,9 +605,11 @@ static int upload_grid_slot(bl_ctx *ctx, const bl_grid_view *gv, int slot) {
   if (ctx->rad.block_interp) {
     if (!gv->levels || !gv->locations)
       return bl_fail(ctx, BL_ERR_ARG, "simulation_block_interp needs the blocks' levels and logical locations");
-    if (gv->n_3_root <= 0 || gv->n_3_root % g.n_k != 0)
+    // blocks around x3 at the root level: only the azimuthal wrap of spherical grids looks at it
+    const bool periodic_x3 = ctx->params.simulation_coord == BL_COORD_SKS;
+    if (periodic_x3 && (gv->n_3_root <= 0 || gv->n_3_root % g.n_k != 0))
       return bl_fail(ctx, BL_ERR_ARG, "simulation_block_interp needs RootGridSize[2] (n_3_root) as a multiple of the block size");
-    g.n3_root = gv->n_3_root / g.n_k;
+    g.n3_root = periodic_x3 ? gv->n_3_root / g.n_k : 0;
     g.max_level = 0;
     hkeys.assign((size_t)g.hash_mask + 1, ~0ull);
     hvals.assign((size_t)g.hash_mask + 1, -1);

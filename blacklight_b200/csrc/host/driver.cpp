@@ -10,7 +10,7 @@
 #include <vector>
 
 #include "athdf.hpp"
-#include "harm3d.hpp"
+#include "snapshot.hpp"
 #include "config.hpp"
 #include "npz_writer.hpp"
 
@@ -258,26 +258,13 @@ RunTimings run_input_file(const std::string &path, int device, bool quiet) {
   validate_output_options(cfg);
   bl_params &p = cfg.params;
   const bool sim = p.model_type == BL_MODEL_SIMULATION;
-  if (sim && cfg.simulation_format != 0 && cfg.simulation_format != 3)
-    throw Error("Only simulation_format = athena and harm3d are inside the B200 hot-path scope.");
-  const bool harm = sim && cfg.simulation_format == 3;
-  if (harm && !cfg.gamma_set) {
-    // the adiabatic index comes from the file header and is a kernel parameter: read it before bl_create
-    std::string first = cfg.simulation_multiple ? format_numbered(cfg.simulation_file, cfg.simulation_start, "simulation_file")
-                                                : cfg.simulation_file;
-    read_harm3d_header(first, nullptr, &p.plasma_gamma);
+  std::unique_ptr<SnapshotReader> reader;
+  if (sim) {
+    reader.reset(new SnapshotReader(cfg));
+    p.plasma_gamma = reader->plasma_gamma();
   }
-  auto read_snapshot = [&](const std::string &file, bool reuse, AthenaGrid &into) {
-    if (harm)
-      read_harm3d(file, p.plasma_model == BL_PLASMA_CODE_KAPPA, true, &p.plasma_gamma, p.bh_a, reuse, into);
-    else
-      read_athdf(file, p.plasma_model == BL_PLASMA_CODE_KAPPA ? cfg.simulation_kappa_name : "", reuse, into);
-  };
-  auto snapshot_time_of = [&](const std::string &file) {
-    double t = 0.0;
-    if (harm) read_harm3d_header(file, &t, nullptr); else t = read_athdf_time(file);
-    return t;
-  };
+  auto read_snapshot = [&](const std::string &file, bool reuse, AthenaGrid &into) { reader->read(file, reuse, into); };
+  auto snapshot_time_of = [&](const std::string &file) { return reader->time_of(file); };
   if (device < 0) {
     const char *env = std::getenv("BLACKLIGHT_DEVICE");
     device = env ? std::atoi(env) : 0;

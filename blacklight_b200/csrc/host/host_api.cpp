@@ -8,9 +8,15 @@
 
 #include "config.hpp"
 #include "driver.hpp"
+#include "snapshot.hpp"
 
 struct blh_config {
   blh::RunConfig cfg;
+};
+
+struct blh_snapshot {
+  blh::AthenaGrid grid;
+  double plasma_gamma = 0.0;
 };
 
 namespace {
@@ -85,6 +91,37 @@ int64_t blh_camera_refined(const blh_config *c, int level, const int32_t *parent
   if (factor) std::memcpy(factor, f.data(), f.size() * sizeof(double));
   return (int64_t)cl.size() / 2;
 }
+
+int blh_snapshot_read(const blh_config *c, const char *file, blh_snapshot **out) {
+  if (!c || !out) { g_error = "null argument"; return 1; }
+  *out = nullptr;
+  try {
+    if (c->cfg.params.model_type != BL_MODEL_SIMULATION) throw blh::Error("model_type is not simulation.");
+    blh::SnapshotReader reader(c->cfg);
+    blh_snapshot *s = new blh_snapshot;
+    try {
+      reader.read(file ? std::string(file) : reader.first_file(), false, s->grid);
+    } catch (...) {
+      delete s;
+      throw;
+    }
+    s->plasma_gamma = reader.plasma_gamma();
+    *out = s;
+    return 0;
+  } catch (const std::exception &e) {
+    return fail(e);
+  }
+}
+
+int blh_snapshot_view(const blh_snapshot *s, bl_grid_view *view, double *time, double *plasma_gamma) {
+  if (!s || !view) { g_error = "null argument"; return 1; }
+  *view = s->grid.view();
+  if (time) *time = s->grid.time;
+  if (plasma_gamma) *plasma_gamma = s->plasma_gamma;
+  return 0;
+}
+
+void blh_snapshot_free(blh_snapshot *s) { delete s; }
 
 int blh_run_input_file(const char *path, int device, int quiet, double timings[12]) {
   if (!path) { g_error = "null argument"; return 1; }

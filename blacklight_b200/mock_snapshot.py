@@ -302,6 +302,43 @@ def write_harm3d(path, fields, gamma_adi=4.0 / 3.0, time=0.0):
         np.array(data, dtype=np.float32).transpose().tofile(f_out)
 
 
+def write_athenak(path, grid, gamma_adi=4.0 / 3.0, time=0.0, location_size=4, variable_size=4, spin=0.0,
+                  extra_first=('spare',)):
+    """Write a uniform-block Cartesian grid (output of to_blocks on mock_fields_cks) as an AthenaK binary dump,
+    version 1.1, the way the reference's reader takes it apart (simulation_reader.cpp:434-588,915-1131): ascii
+    pre-header (time, sizes, variable names, header offset), the run's input parameters as text (<coord> a,
+    <mhd> gamma are looked at), then per MeshBlock 6 int32 cell index bounds, 3 int32 logical location + int32
+    level, 6 face positions (x1min, x1max, x2min, ...) of location_size bytes and the cell data variable by
+    variable.  Pressure is stored as internal energy `eint`; `extra_first` puts unrelated variables in front so
+    that the by-name lookup is exercised.  The reference ships no AthenaK generator."""
+    names = list(extra_first) + ['dens', 'velx', 'vely', 'velz', 'eint', 'bcc1', 'bcc2', 'bcc3']
+    prim = grid['prim'].astype(np.float64)
+    src = {'dens': prim[0], 'eint': prim[1] / (gamma_adi - 1.0), 'velx': prim[2], 'vely': prim[3], 'velz': prim[4],
+           'bcc1': prim[5], 'bcc2': prim[6], 'bcc3': prim[7]}
+    if 'kappa' in grid:
+        names.append('r0')
+        src['r0'] = grid['kappa'].astype(np.float64)
+    params = ('# mock AthenaK parameter dump\n<coord>\ngeneral_rel = true\na = %.17g\n<mhd>\neos = ideal\n'
+              'gamma = %.17g\n<problem>\nuser_hist = false\n' % (spin, gamma_adi)).encode()
+    head = ('Athena binary output version=1.1\n  size of preheader=5\n  time=%.16e\n  cycle=0\n'
+            '  size of location=%d\n  size of variable=%d\n  number of variables=%d\n  variables:  %s  \n'
+            '  header offset=%d\n' % (time, location_size, variable_size, len(names), ' '.join(names), len(params))).encode()
+    loc_t = np.float32 if location_size == 4 else np.float64
+    var_t = np.float32 if variable_size == 4 else np.float64
+    n_i, n_j, n_k = grid['n_i'], grid['n_j'], grid['n_k']
+    with open(path, 'wb') as f:
+        f.write(head + params)
+        for b in range(grid['n_b']):
+            li, lj, lk = (int(v) for v in grid['locations'][b])
+            np.array([li * n_i, (li + 1) * n_i - 1, lj * n_j, (lj + 1) * n_j - 1, lk * n_k, (lk + 1) * n_k - 1,
+                      li, lj, lk, int(grid['levels'][b])], np.int32).tofile(f)
+            np.array([grid['x1f'][b, 0], grid['x1f'][b, -1], grid['x2f'][b, 0], grid['x2f'][b, -1],
+                      grid['x3f'][b, 0], grid['x3f'][b, -1]], loc_t).tofile(f)
+            for name in names:
+                data = src[name][b] if name in src else np.full((n_k, n_j, n_i), 1.0e30)
+                np.ascontiguousarray(data, var_t).tofile(f)
+
+
 def grid_view_arrays(grid):
     """Arrays in the layout SimulationReader hands to the integrator (float32 coords widened to f64)."""
     if 'kappa' in grid:   # the reader stacks hydro (with the entropy variable last) before the field

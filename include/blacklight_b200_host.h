@@ -36,6 +36,15 @@ int64_t blh_camera_refined(const blh_config *cfg, int level, const int32_t *pare
                            int64_t num_parents, int32_t *child_locs, double *pos, double *dir, double *factor);
 /* timings: total, geodesic, read, sample, image, render [s]; gpu geodesic, radiation, refine [ms];
  * rays, samples, reserved */
+/* Snapshot readers -- the upload side of SimulationReader::Read (simulation_reader.cpp:200-861): simulation_format
+ * athena (.athdf), athenak (binary dump) or harm3d, as the input file names it.  file = NULL reads the input file's
+ * simulation_file (first of the series).  The view's arrays are owned by the snapshot and are what bl_upload_grid takes;
+ * plasma_gamma is the adiabatic index the reader settled on (the file's where the input file gives none). */
+typedef struct blh_snapshot blh_snapshot;
+int blh_snapshot_read(const blh_config *cfg, const char *file, blh_snapshot **out);
+int blh_snapshot_view(const blh_snapshot *snap, bl_grid_view *view, double *time, double *plasma_gamma);
+void blh_snapshot_free(blh_snapshot *snap);
+
 int blh_run_input_file(const char *path, int device, int quiet, double timings[12]);
 
 #ifdef __cplusplus

@@ -169,6 +169,84 @@ def test_mock_snapshot_is_stable_and_readable(tmp_path):
     assert os.path.getsize(os.path.join(tmp_path, 'm.athdf')) > grid['prim'].nbytes
 
 
+def _reader_case(tmp_path, fmt, snap, over=None):
+    from harness import load_input, write_input
+    kv = load_input('simulation.input')
+    kv.update({'simulation_format': fmt, 'simulation_file': snap, 'camera_resolution': '8'})
+    kv.update(over or {})
+    path = os.path.join(str(tmp_path), fmt + '.input')
+    write_input(path, kv)
+    return bl.Config(path)
+
+
+@pytest.mark.parametrize('location_size,variable_size', [(4, 4), (8, 8)])
+def test_athenak_reader(tmp_path, location_size, variable_size, capfd):
+    """simulation_format = athenak: pre-header, parameter dump, per-block records; variables
+    located by name; faces rebuilt from block edges in double; eint -> pressure in float32; the adiabatic index
+    taken from <mhd> gamma (reference simulation_reader.cpp:434-588,915-1131,1225-1290)."""
+    from blacklight_b200 import mock_snapshot as ms
+    grid = ms.add_entropy(ms.to_blocks(ms.mock_fields_cks(n=12), (2, 3, 1)))
+    snap = os.path.join(str(tmp_path), 'mock.bin')
+    ms.write_athenak(snap, grid, gamma_adi=1.5, time=7.25, location_size=location_size, variable_size=variable_size,
+                     spin=0.5)
+    kv = {'simulation_coord': 'cks', 'simulation_a': '0.5', 'plasma_model': 'code_kappa', 'simulation_kappa_name': 'r0'}
+    cfg = _reader_case(tmp_path, 'athenak', snap, kv)
+    g = bl.read_snapshot(cfg)
+    assert (g['n_b'], g['n_k'], g['n_j'], g['n_i'], g['n_var']) == (6, 12, 4, 6, 9)
+    assert g['time'] == 7.25 and g['plasma_gamma'] == 1.5
+    assert np.array_equal(g['locations'], grid['locations']) and np.array_equal(g['levels'], grid['levels'])
+    loc_t = np.float32 if location_size == 4 else np.float64
+    for b in range(6):
+        lo, hi = float(loc_t(grid['x1f'][b, 0])), float(loc_t(grid['x1f'][b, -1]))
+        f = np.array([lo] + [lo + i * ((hi - lo) / 6) for i in range(1, 6)] + [hi])
+        assert np.array_equal(g['x1f'][b], f)
+        assert np.array_equal(g['x1v'][b], 0.5 * (f[:-1] + f[1:]))
+    var_t = np.float32 if variable_size == 4 else np.float64
+    prim = grid['prim'].astype(np.float64)
+    eint = (prim[1] / 0.5).astype(var_t).astype(np.float32) * np.float32(0.5)
+    order = [0, 2, 3, 4, None, 5, 6, 7]   # internal order rho, uu1, uu2, uu3, pgas, bb1, bb2, bb3, kappa
+    for v, src in enumerate(order):
+        want = eint if src is None else grid['prim'][src]
+        assert np.array_equal(g['prim'][v], want), v
+    assert np.array_equal(g['prim'][8], grid['kappa'])
+    assert [g[k] for k in ('ind_rho', 'ind_uu1', 'ind_uu2', 'ind_uu3', 'ind_pgas', 'ind_bb1', 'ind_bb2', 'ind_bb3',
+                           'ind_kappa')] == list(range(9))
+    capfd.readouterr()
+    # an input-file spin that differs from the dump's is warned about, in the reference's words
+    bl.read_snapshot(_reader_case(tmp_path, 'athenak', snap, dict(kv, simulation_a='0.25')))
+    assert 'Given spin of 0.25 does not match file value of 0.5; ignoring the latter.' in capfd.readouterr().err
+    with pytest.raises(bl.BlacklightError, match='Unable to locate electron entropy values'):
+        bl.read_snapshot(_reader_case(tmp_path, 'athenak', snap, dict(kv, simulation_kappa_name='s_e')))
+    with open(snap, 'r+b') as f:
+        f.write(b'Athena binary output version=1.0')
+    with pytest.raises(bl.BlacklightError, match='Unknown AthenaK file format.'):
+        bl.read_snapshot(cfg)
+
+
+def test_athdf_and_harm3d_readers_return_the_generator_arrays(tmp_path):
+    """blh_snapshot_read for the other two formats: the .athdf reader returns exactly the arrays the generator
+    wrote (float32 coordinates widened); the harm3d reader returns one spherical Kerr-Schild block of the same
+    shape with the header's time and adiabatic index."""
+    from blacklight_b200 import mock_snapshot as ms
+    d = str(tmp_path)
+    grid = ms.make_mock(os.path.join(d, 'm.athdf'), blocks=(1, 2, 2), n_r=16, n_th=8, n_ph=8)
+    want = ms.grid_view_arrays(grid)
+    g = bl.read_snapshot(_reader_case(tmp_path, 'athena', os.path.join(d, 'm.athdf')))
+    for k in ('levels', 'locations', 'x1f', 'x2f', 'x3f', 'x1v', 'x2v', 'x3v', 'prim'):
+        assert np.array_equal(g[k], want[k]), k
+    for k in ('n_b', 'n_var', 'ind_rho', 'ind_pgas', 'ind_uu1', 'ind_bb3', 'n_3_root'):
+        assert g[k] == want[k], k
+    fields = ms.mock_fields(n_r=16, n_th=8, n_ph=8)
+    ms.write_harm3d(os.path.join(d, 'm.harm3d'), fields, gamma_adi=1.4, time=3.0)
+    kv = {'simulation_coord': 'sks'}
+    cfg = _reader_case(tmp_path, 'harm3d', os.path.join(d, 'm.harm3d'), kv)
+    h = bl.read_snapshot(cfg)
+    assert (h['n_b'], h['n_k'], h['n_j'], h['n_i']) == (1, 8, 8, 16)
+    assert h['time'] == 3.0
+    np.testing.assert_allclose(h['x1v'][0], np.sqrt(fields['rf'][:-1] * fields['rf'][1:]), rtol=1e-12)   # centres in ln r
+    np.testing.assert_allclose(h['prim'][h['ind_rho'], 0], fields['prim'][0], rtol=1e-6)
+
+
 def test_npz_writer_and_athdf_reader_through_driver_without_gpu(tmp_path):
     """blh_run_input_file must fail loudly without a GPU, after parsing the file."""
     import torch

@@ -574,6 +574,60 @@ def test_harm3d_reader_against_reference(over, gpu, tmp_path):
             assert v <= PIXEL_TOL, '%s %.3e' % (k, v)
 
 
+@pytest.mark.parametrize('over,sizes', [
+    ({'camera_resolution': 32}, (4, 4)),
+    ({'camera_resolution': 28, 'simulation_interp': 'false'}, (8, 8)),
+    ({'camera_resolution': 24, 'simulation_block_interp': 'true'}, (8, 4)),
+    ({'camera_resolution': 24, 'image_polarization': 'true'}, (4, 8)),
+    ({'camera_resolution': 24, 'plasma_model': 'code_kappa', 'simulation_kappa_name': 'r0'}, (4, 4)),
+])
+def test_athenak_reader_against_reference(over, sizes, gpu, tmp_path):
+    """simulation_format = athenak: AthenaK binary dump of a Cartesian Kerr-Schild box of
+    2x2x2 MeshBlocks, a = 0.5, read by our host reader (faces rebuilt from block edges, eint -> pressure, adiabatic
+    index from the dump's <mhd> block; reference simulation_reader.cpp:434-588,915-1131) and rendered through the
+    drop-in executable, against the reference binary on the same file."""
+    if not os.path.exists(REF_BIN):
+        pytest.skip('oracle/_ref/blacklight not present')
+    import subprocess
+    from blacklight_b200 import mock_snapshot as ms
+    from harness import write_input
+    d = str(tmp_path)
+    case = Case(d, 'simulation.input', over)
+    grid = ms.to_blocks(ms.mock_fields_cks(n=32), (2, 2, 2))
+    if 'simulation_kappa_name' in over:
+        ms.add_entropy(grid)
+    snap = os.path.join(d, 'data', 'mock.athenak.bin')
+    ms.write_athenak(snap, grid, gamma_adi=13.0 / 9.0, time=1.0, location_size=sizes[0], variable_size=sizes[1], spin=0.5)
+    images = {}
+    for who in ('ref', 'gpu'):
+        kv = dict(case.kv)
+        kv.update({'simulation_format': 'athenak', 'simulation_file': snap, 'simulation_coord': 'cks', 'simulation_a': '0.5',
+                   'output_file': os.path.join(d, who + '.npz')})
+        kv.pop('plasma_gamma', None)     # taken from the dump
+        path = os.path.join(d, who + '.input')
+        write_input(path, kv)
+        if who == 'ref':
+            proc = subprocess.run([REF_BIN, path], cwd=d, capture_output=True, text=True, timeout=3600)
+            assert proc.returncode == 0 and 'Calculation completed' in proc.stdout, proc.stdout + proc.stderr
+        else:
+            bl.run_input_file(path)
+        images[who] = dict(np.load(os.path.join(d, who + '.npz')))
+    ref, mine = images['ref'], images['gpu']
+    assert float(np.nanmax(ref['I_nu'])) > 0.0
+    if over.get('image_polarization') == 'true':
+        # as in test_live_reference_cartesian_kerr_schild: pixels above 1e-6 of the peak (DESIGN.md section 3.2)
+        bright = ref['I_nu'] >= 1e-6 * np.nanmax(ref['I_nu'])
+        assert bright.sum() > 0.5 * bright.size
+        m = {k: np.where(bright, v, 0.0) for k, v in mine.items() if k.endswith('_nu')}
+        r = {k: np.where(bright, ref[k], 0.0) for k in m}
+        assert rel_err(m['I_nu'], r['I_nu']) <= PIXEL_TOL
+        for k, v in stokes_err(m, r, floor=1e-2).items():
+            assert v <= PIXEL_TOL, '%s %.3e' % (k, v)
+    else:
+        assert rel_err(mine['I_nu'], ref['I_nu']) <= PIXEL_TOL
+        assert flux_rel(mine['I_nu'], ref['I_nu']) <= FLUX_TOL
+
+
 def test_adaptive_two_levels_with_forced_region_against_reference(gpu, tmp_path):
     """Two refinement levels (a forced region plus the relative-Laplacian criterion), polarized, through the
     drop-in executable: block lists, block counts and every per-level image against the reference."""
