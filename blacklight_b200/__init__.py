@@ -29,7 +29,9 @@ class GridView(ctypes.Structure):
                 ('x1v', ctypes.c_void_p), ('x2v', ctypes.c_void_p), ('x3v', ctypes.c_void_p),
                 ('prim', ctypes.c_void_p)] + [(n, ctypes.c_int32) for n in (
                     'ind_rho', 'ind_pgas', 'ind_kappa', 'ind_uu1', 'ind_uu2', 'ind_uu3', 'ind_bb1', 'ind_bb2', 'ind_bb3',
-                    'n_3_root')]
+                    'n_3_root')] + [('sks_map', ctypes.c_void_p), ('sks_map_n1', ctypes.c_int32), ('sks_map_n2', ctypes.c_int32),
+                                    ('sks_map_r_in', ctypes.c_double), ('sks_map_dr', ctypes.c_double),
+                                    ('sks_map_dtheta', ctypes.c_double), ('simulation_bounds', ctypes.c_double * 6)]
 
 
 class LevelStats(ctypes.Structure):
@@ -229,6 +231,13 @@ class Context:
             setattr(v, k, int(g[k]))
         for k, a in keep.items():
             setattr(v, k, a.ctypes.data)
+        if 'sks_map' in g:   # simulation_coord = fmks (blacklight_b200.read_snapshot of an iharm3d dump)
+            keep['sks_map'] = np.ascontiguousarray(g['sks_map'], np.float64)
+            v.sks_map = keep['sks_map'].ctypes.data
+            v.sks_map_n2, v.sks_map_n1 = keep['sks_map'].shape[1:]
+            v.sks_map_r_in, v.sks_map_dr, v.sks_map_dtheta = g['sks_map_r_in'], g['sks_map_dr'], g['sks_map_dtheta']
+            for d in range(6):
+                v.simulation_bounds[d] = float(g['simulation_bounds'][d])
         self._check(_lib.bl_upload_grid(self._h, ctypes.byref(v)))
 
     def trace_level(self, level, pos, dirs, fac):
@@ -314,7 +323,7 @@ def read_snapshot(config, path=None):
     try:
         v, t, g = GridView(), ctypes.c_double(), ctypes.c_double()
         lib.blh_snapshot_view(h, ctypes.byref(v), ctypes.byref(t), ctypes.byref(g))
-        out = {n: getattr(v, n) for n, c in GridView._fields_ if c is ctypes.c_int32}
+        out = {n: getattr(v, n) for n, c in GridView._fields_ if c is ctypes.c_int32 and not n.startswith('sks_map')}
 
         def arr(ptr, shape, dtype):
             n = int(np.prod(shape))
@@ -328,6 +337,11 @@ def read_snapshot(config, path=None):
             out[name + 'v'] = arr(getattr(v, name + 'v'), (nb, n), np.float64)
         out['prim'] = arr(v.prim, (v.n_var, nb, nk, nj, ni), np.float32)
         out['time'], out['plasma_gamma'] = t.value, g.value
+        if v.sks_map:   # simulation_coord = fmks
+            out['sks_map'] = arr(v.sks_map, (2, v.sks_map_n2, v.sks_map_n1), np.float64)
+            out['simulation_bounds'] = np.array(list(v.simulation_bounds))
+            for k in ('sks_map_r_in', 'sks_map_dr', 'sks_map_dtheta'):
+                out[k] = getattr(v, k)
         return out
     finally:
         lib.blh_snapshot_free(h)

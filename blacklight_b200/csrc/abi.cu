@@ -334,8 +334,6 @@ int validate_params(const bl_params &p) {
   if (p.image_num_frequencies > BL_MAX_FREQ) return bl_fail(nullptr, BL_ERR_UNSUPPORTED, "image_num_frequencies > %d not supported", BL_MAX_FREQ);
   for (int l = 0; l < p.image_num_frequencies; l++)
     if (!(p.image_frequencies[l] > 0.0)) return bl_fail(nullptr, BL_ERR_ARG, "Must choose positive image_frequency.");
-  if (p.model_type == BL_MODEL_SIMULATION && p.simulation_coord == BL_COORD_FMKS)
-    return bl_fail(nullptr, BL_ERR_UNSUPPORTED, "simulation_coord = fmks is outside the B200 hot-path scope (SURVEY.md section 2)");
   bool sim = p.model_type == BL_MODEL_SIMULATION;
   if (sim && p.slow_light_on && (p.slow_chunk_size < 2 || p.slow_chunk_size > BL_MAX_SLICES))
     return bl_fail(nullptr, p.slow_chunk_size < 2 ? BL_ERR_ARG : BL_ERR_UNSUPPORTED,
@@ -529,6 +527,10 @@ static int upload_grid_slot(bl_ctx *ctx, const bl_grid_view *gv, int slot) {
   bool want_kappa = ctx->params.plasma_model == BL_PLASMA_CODE_KAPPA;
   if (want_kappa && (gv->ind_kappa < 0 || gv->ind_kappa >= gv->n_var))
     return bl_fail(ctx, BL_ERR_ARG, "plasma_model = code_kappa needs an electron entropy variable");
+  const bool fmks = ctx->params.simulation_coord == BL_COORD_FMKS;
+  if (fmks && (gv->n_b != 1 || !gv->sks_map || gv->sks_map_n1 < 2 || gv->sks_map_n2 < 2 || !(gv->sks_map_dr > 0.0) ||
+               !(gv->sks_map_dtheta > 0.0) || gv->n_i < 2 || gv->n_j < 2))
+    return bl_fail(ctx, BL_ERR_ARG, "simulation_coord = fmks needs a single block and the reader's sks_map in the grid view");
   size_t cells = (size_t)gv->n_b * gv->n_k * gv->n_j * gv->n_i;
   GridDev &g = ctx->grid;
   if (!same_shape) {
@@ -565,6 +567,11 @@ static int upload_grid_slot(bl_ctx *ctx, const bl_grid_view *gv, int slot) {
       BL_CUDA_CHECK(dev_alloc(&kp, (size_t)size)); g.hash_keys = kp; ctx->grid_allocs.push_back(kp);
     }
     BL_CUDA_CHECK(alloc_d(&g.bounds, (size_t)g.n_b * 6));
+    if (fmks) {
+      BL_CUDA_CHECK(alloc_d(&g.sks_map, (size_t)2 * gv->sks_map_n2 * gv->sks_map_n1));
+      g.map_n1 = gv->sks_map_n1;
+      g.map_n2 = gv->sks_map_n2;
+    }
     BL_CUDA_CHECK(alloc_d(&g.x1d, (size_t)g.n_b * g.n_i));
     BL_CUDA_CHECK(alloc_d(&g.x2d, (size_t)g.n_b * g.n_j));
     BL_CUDA_CHECK(alloc_d(&g.x3d, (size_t)g.n_b * g.n_k));
@@ -597,6 +604,16 @@ static int upload_grid_slot(bl_ctx *ctx, const bl_grid_view *gv, int slot) {
     bounds[6 * b + 3] = gv->x2f[(size_t)b * (g.n_j + 1) + g.n_j];
     bounds[6 * b + 4] = gv->x3f[(size_t)b * (g.n_k + 1)];
     bounds[6 * b + 5] = gv->x3f[(size_t)b * (g.n_k + 1) + g.n_k];
+  }
+  if (fmks) {
+    // the grid's extent in (r, theta, phi) stands in for the native face positions (simulation_sampling.cpp:190-198)
+    if (g.map_n1 != gv->sks_map_n1 || g.map_n2 != gv->sks_map_n2)
+      return bl_fail(ctx, BL_ERR_ARG, "bl_upload_grid: sks_map changed shape between snapshots");
+    for (int d = 0; d < 6; d++) bounds[(size_t)d] = gv->simulation_bounds[d];
+    g.map_r_in = gv->sks_map_r_in;
+    g.map_dr = gv->sks_map_dr;
+    g.map_dtheta = gv->sks_map_dtheta;
+    BL_CUDA_CHECK(h2d(g.sks_map, gv->sks_map, (size_t)2 * g.map_n2 * g.map_n1));
   }
   BL_CUDA_CHECK(cudaMemcpyAsync((void *)g.bounds, bounds.data(), bounds.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   // mesh topology: levels, logical locations and the (level, location) -> block hash
@@ -652,6 +669,11 @@ static int upload_grid_slot(bl_ctx *ctx, const bl_grid_view *gv, int slot) {
                 want_kappa ? gv->ind_kappa : -1};
   for (int q = 0; q < 8 && e == cudaSuccess; q++)
     if (idx[q] < 0 || idx[q] >= gv->n_var) { cudaFree(stage); return bl_fail(ctx, BL_ERR_ARG, "bl_upload_grid: variable index %d out of range", q); }
+  for (int q = 0; q < 9; q++) {
+    g.next_slot[q] = -1;
+    for (int u = 0; u < 9; u++)
+      if (idx[q] >= 0 && idx[u] == idx[q] + 1) g.next_slot[q] = (int8_t)u;
+  }
   int *idx_dev = nullptr;
   if (e == cudaSuccess) e = dev_alloc(&idx_dev, 9);
   if (e == cudaSuccess) e = cudaMemcpyAsync(idx_dev, idx, sizeof idx, cudaMemcpyHostToDevice, ctx->stream);

@@ -20,6 +20,12 @@ struct AthenaGrid {
   int ind_bb1 = -1, ind_bb2 = -1, ind_bb3 = -1;
   int n_3_root = 0;
   double time = 0.0;
+  // simulation_coord = fmks only: map from spherical Kerr-Schild (r, theta) to the native (x1, x2), its sampling
+  // and the grid's extent in (r, theta, phi) (simulation_reader.hpp:103-112)
+  std::vector<double> sks_map;                       // (2, sks_map_n2, sks_map_n1)
+  int sks_map_n1 = 0, sks_map_n2 = 0;
+  double sks_map_r_in = 0.0, sks_map_dr = 0.0, sks_map_dtheta = 0.0;
+  double simulation_bounds[6] = {0, 0, 0, 0, 0, 0};
   bl_grid_view view() const;
 };
 

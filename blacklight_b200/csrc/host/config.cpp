@@ -313,6 +313,9 @@ RunConfig make_config(const InputFile &in) {
         if (c.simulation_format != 2) {
           p.plasma_gamma_i = in.real("plasma_gamma_i");
           p.plasma_gamma_e = in.real("plasma_gamma_e");
+        } else {   // iharm3d: the dump's header/gam_p, gam_e stand in (simulation_reader.cpp:113-125)
+          if (in.has("plasma_gamma_i")) { p.plasma_gamma_i = in.real("plasma_gamma_i"); c.gamma_i_set = true; }
+          if (in.has("plasma_gamma_e")) { p.plasma_gamma_e = in.real("plasma_gamma_e"); c.gamma_e_set = true; }
         }
       }
     } else {

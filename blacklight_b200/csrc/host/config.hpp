@@ -24,7 +24,7 @@ struct RunConfig {
   std::string simulation_file, simulation_kappa_name;
   bool simulation_multiple = false;
   int simulation_start = 0, simulation_end = 0;
-  bool gamma_set = false;
+  bool gamma_set = false, gamma_i_set = false, gamma_e_set = false;
   bool checkpoint_geodesic_save = false, checkpoint_geodesic_load = false, checkpoint_sample_save = false;
   std::string checkpoint_geodesic_file, checkpoint_sample_file;
   // slow light (simulation_reader.cpp:64-82, output_writer.cpp:104)

@@ -262,6 +262,8 @@ RunTimings run_input_file(const std::string &path, int device, bool quiet) {
   if (sim) {
     reader.reset(new SnapshotReader(cfg));
     p.plasma_gamma = reader->plasma_gamma();
+    p.plasma_gamma_i = reader->plasma_gamma_i();
+    p.plasma_gamma_e = reader->plasma_gamma_e();
   }
   auto read_snapshot = [&](const std::string &file, bool reuse, AthenaGrid &into) { reader->read(file, reuse, into); };
   auto snapshot_time_of = [&](const std::string &file) { return reader->time_of(file); };

@@ -10,8 +10,23 @@ enum { kAthena = 0, kAthenaK = 1, kIharm3d = 2, kHarm3d = 3 };
 }
 
 SnapshotReader::SnapshotReader(const RunConfig &cfg) : cfg_(cfg), gamma_(cfg.params.plasma_gamma) {
-  if (cfg.simulation_format == kIharm3d)
-    throw Error("simulation_format = iharm3d is outside the B200 hot-path scope (athena, athenak and harm3d are read).");
+  const bl_params &p = cfg.params;
+  iharm_.fmks = p.simulation_coord == BL_COORD_FMKS;
+  iharm_.simulation_a = p.bh_a;
+  iharm_.gamma_set = cfg.gamma_set;
+  iharm_.gamma_i_set = cfg.gamma_i_set;
+  iharm_.gamma_e_set = cfg.gamma_e_set;
+  iharm_.need_gamma_ie = p.plasma_model == BL_PLASMA_TI_TE_BETA && !p.plasma_use_p;
+  iharm_.plasma_gamma = p.plasma_gamma;
+  iharm_.plasma_gamma_i = p.plasma_gamma_i;
+  iharm_.plasma_gamma_e = p.plasma_gamma_e;
+  if (cfg.simulation_format == kIharm3d) {
+    if (p.simulation_coord == BL_COORD_CKS) throw Error("Invalid simulation_coord for Harm format.");
+    read_iharm3d_gammas(first_file(), iharm_);
+    gamma_ = iharm_.plasma_gamma;
+  } else if (p.simulation_coord == BL_COORD_FMKS) {
+    throw Error("simulation_coord = fmks needs simulation_format = iharm3d.");
+  }
   if (!cfg.gamma_set) {
     if (cfg.simulation_format == kHarm3d) read_harm3d_header(first_file(), nullptr, &gamma_);
     if (cfg.simulation_format == kAthenaK) read_athenak_header(first_file(), nullptr, &gamma_);
@@ -38,6 +53,8 @@ void SnapshotReader::read(const std::string &file, bool reuse_layout, AthenaGrid
     read_harm3d(file, code_kappa, cfg_.gamma_set, &g, cfg_.params.bh_a, reuse_layout, grid);
   } else if (cfg_.simulation_format == kAthenaK) {
     read_athenak(file, kappa_name, reuse_layout, athenak_, grid);
+  } else if (cfg_.simulation_format == kIharm3d) {
+    read_iharm3d(file, kappa_name, reuse_layout, iharm_, grid);
   } else {
     read_athdf(file, kappa_name, reuse_layout, grid);
   }
@@ -47,6 +64,7 @@ double SnapshotReader::time_of(const std::string &file) const {
   double t = 0.0;
   if (cfg_.simulation_format == kHarm3d) read_harm3d_header(file, &t, nullptr);
   else if (cfg_.simulation_format == kAthenaK) read_athenak_header(file, &t, nullptr);
+  else if (cfg_.simulation_format == kIharm3d) t = read_iharm3d_time(file);
   else t = read_athdf_time(file);
   return t;
 }

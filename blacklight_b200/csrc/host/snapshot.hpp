@@ -6,6 +6,7 @@
 #include "athdf.hpp"
 #include "athenak.hpp"
 #include "config.hpp"
+#include "iharm3d.hpp"
 
 namespace blh {
 
@@ -15,6 +16,9 @@ class SnapshotReader {
   // does not override it: plasma_gamma() is a kernel parameter and must be known before bl_create.
   explicit SnapshotReader(const RunConfig &cfg);
   double plasma_gamma() const { return gamma_; }
+  // ion / electron indices (plasma_use_p = false): the iharm3d dump's where the input file gives none
+  double plasma_gamma_i() const { return iharm_.plasma_gamma_i; }
+  double plasma_gamma_e() const { return iharm_.plasma_gamma_e; }
   // reuse_layout: `grid` already holds the first snapshot's coordinates; only refresh the cell data.
   void read(const std::string &file, bool reuse_layout, AthenaGrid &grid);
   double time_of(const std::string &file) const;
@@ -24,6 +28,7 @@ class SnapshotReader {
   const RunConfig &cfg_;
   double gamma_;
   AthenaKExpect athenak_;
+  Iharm3dExpect iharm_;
 };
 
 }  // namespace blh

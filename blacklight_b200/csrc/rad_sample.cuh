@@ -88,6 +88,27 @@ __device__ __forceinline__ void load_cell(const GridDev &g, size_t c, float v[8]
   v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
 }
 
+// FMKS only: cell index c >= the number of cells, i.e. past the end of every variable's plane of the reader's
+// (variable, cell) array -- each variable reads the first cells of the variable stored after it (GridDev::next_slot).
+__device__ __forceinline__ void load_cell_past_end(const GridDev &g, size_t slot, size_t over, float v[8], float &kappa) {
+  float t[8];
+  load_cell(g, slot + over, t);
+  float tk = g.kappa ? __ldg(g.kappa + slot + over) : 0.0f;
+#pragma unroll
+  for (int q = 0; q < 8; q++) {
+    int ns = g.next_slot[q];
+    float val = 0.0f;
+#pragma unroll
+    for (int u = 0; u < 8; u++) val = ns == u ? t[u] : val;
+    v[q] = ns == 8 ? tk : val;
+  }
+  int nk = g.next_slot[8];
+  float val = 0.0f;
+#pragma unroll
+  for (int u = 0; u < 8; u++) val = nk == u ? t[u] : val;
+  kappa = val;
+}
+
 // Geometric cuts of one sample (simulation_sampling.cpp:237-292, formula_coefficients.cpp:75-119).
 // Returns true if the sample is cut.  r is the Kerr-Schild radius of (x,y,z).
 __device__ __forceinline__ bool geometric_cut(const RadParams &P, double x, double y, double z, double r) {
@@ -327,8 +348,12 @@ __device__ __forceinline__ SampleStatus sample_grid(const RadParams &P, const Gr
     cache.b = bn;
   }
   const int n_i = g.n_i, n_j = g.n_j, n_k = g.n_k;
-  int i = find_cell_hint(g.x1f + (size_t)b * (n_i + 1), n_i, x1, cache.i);
-  int j = find_cell_hint(g.x2f + (size_t)b * (n_j + 1), n_j, x2, cache.j);
+  const bool fmks = EXT && P.coord == 2;
+  int i = 0, j = 0;
+  if (!fmks) {
+    i = find_cell_hint(g.x1f + (size_t)b * (n_i + 1), n_i, x1, cache.i);
+    j = find_cell_hint(g.x2f + (size_t)b * (n_j + 1), n_j, x2, cache.j);
+  }
   int k = find_cell_hint(g.x3f + (size_t)b * (n_k + 1), n_k, x3, cache.k);
   cache.i = i; cache.j = j; cache.k = k;
   si.b = b;
@@ -351,16 +376,47 @@ __device__ __forceinline__ SampleStatus sample_grid(const RadParams &P, const Gr
     out.kappa = (float)v[8];
   };
 
+  // FMKS grids: zone and fractional position by scaling in the native coordinates, found through the reader's
+  // (r, theta) -> (x1, x2) table (simulation_sampling.cpp:397-452).  The arithmetic is spelled out operation by
+  // operation (no contraction) because truncations of its results are cell indices.  Indices one past a row (the
+  // reference forms them for the last zone) address the following cells of the flat array, as they do there.
+  int fm_i = 0, fm_j = 0;
+  double fm_fi = 0.0, fm_fj = 0.0;
+  const size_t last_cell = (size_t)g.n_b * n_k * n_j * n_i - 1;
+  if (fmks) {
+    const int m1 = g.map_n1, m2 = g.map_n2;
+    double i_ind, j_ind;
+    double t_i = modf(__ddiv_rn(__dsub_rn(x1, g.map_r_in), g.map_dr), &i_ind);
+    double t_j = modf(__ddiv_rn(x2, g.map_dtheta), &j_ind);
+    int mi = min(max((int)i_ind, 0), m1 - 1), mj = min(max((int)j_ind, 0), m2 - 1);
+    const double *map_x1 = g.sks_map + (size_t)mj * m1, *map_x2 = g.sks_map + ((size_t)m2 + min(mj + 1, m2 - 1)) * m1;
+    double a_lo = __ldg(map_x1 + mi), a_hi = __ldg(map_x1 + min(mi + 1, m1 - 1)), b_hi = __ldg(map_x2 + mi);
+    double nat_x1 = __dadd_rn(__dmul_rn(__dsub_rn(1.0, t_i), a_lo), __dmul_rn(t_i, a_hi));
+    double nat_x2 = __dadd_rn(__dmul_rn(__dsub_rn(1.0, t_j), b_hi), __dmul_rn(t_j, b_hi));   // both terms at j+1, as the reference
+    double x1_0 = __ldg(g.x1f), dx1 = __dsub_rn(__ldg(g.x1f + 1), x1_0), dx2 = __dsub_rn(__ldg(g.x2f + 1), __ldg(g.x2f));
+    fm_fi = modf(__ddiv_rn(__dsub_rn(nat_x1, x1_0), dx1), &i_ind);
+    fm_fj = modf(__ddiv_rn(nat_x2, dx2), &j_ind);
+    fm_i = (int)i_ind;
+    fm_j = (int)j_ind;
+    i = fm_fi >= 0.5 ? fm_i + 1 : fm_i;
+    j = fm_fj >= 0.5 ? fm_j + 1 : fm_j;
+  }
+
   if (!P.interp) {
     si.k = k; si.j = j; si.i = i;
     si.fk = si.fj = si.fi = 0.0;
     size_t c = (((size_t)b * n_k + k) * n_j + j) * n_i + i;
     finish([&](size_t slot, double v[9]) {
-      float f[8];
-      load_cell(g, slot + c, f);
+      float f[8], kv = 0.0f;
+      if (fmks && c > last_cell) {
+        load_cell_past_end(g, slot, c - last_cell - 1, f, kv);
+      } else {
+        load_cell(g, slot + c, f);
+        if (g.kappa) kv = __ldg(g.kappa + slot + c);
+      }
 #pragma unroll
       for (int q = 0; q < 8; q++) v[q] = (double)f[q];
-      v[8] = g.kappa ? (double)__ldg(g.kappa + slot + c) : 0.0;
+      v[8] = (double)kv;
     });
     return kSampleOk;
   }
@@ -422,11 +478,18 @@ __device__ __forceinline__ SampleStatus sample_grid(const RadParams &P, const Gr
   }
 
   // intra-block trilinear with extrapolation at block edges (simulation_sampling.cpp:485-502)
-  int i_m = (i == 0 || (i != n_i - 1 && x1 >= __ldg(x1v + i))) ? i : i - 1;
-  int j_m = (j == 0 || (j != n_j - 1 && x2 >= __ldg(x2v + j))) ? j : j - 1;
+  int i_m, j_m;
+  double f_i, f_j;
+  if (fmks) {
+    i_m = fm_i; j_m = fm_j;
+    f_i = fm_fi; f_j = fm_fj;
+  } else {
+    i_m = (i == 0 || (i != n_i - 1 && x1 >= __ldg(x1v + i))) ? i : i - 1;
+    j_m = (j == 0 || (j != n_j - 1 && x2 >= __ldg(x2v + j))) ? j : j - 1;
+    f_i = (x1 - __ldg(x1v + i_m)) * __ldg(g.x1d + (size_t)b * n_i + i_m);
+    f_j = (x2 - __ldg(x2v + j_m)) * __ldg(g.x2d + (size_t)b * n_j + j_m);
+  }
   int k_m = (k == 0 || (k != n_k - 1 && x3 >= __ldg(x3v + k))) ? k : k - 1;
-  double f_i = (x1 - __ldg(x1v + i_m)) * __ldg(g.x1d + (size_t)b * n_i + i_m);
-  double f_j = (x2 - __ldg(x2v + j_m)) * __ldg(g.x2d + (size_t)b * n_j + j_m);
   double f_k = (x3 - __ldg(x3v + k_m)) * __ldg(g.x3d + (size_t)b * n_k + k_m);
   si.k = k_m; si.j = j_m; si.i = i_m;
   si.fk = f_k; si.fj = f_j; si.fi = f_i;
@@ -444,8 +507,14 @@ __device__ __forceinline__ SampleStatus sample_grid(const RadParams &P, const Gr
     for (int q = 0; q < 9; q++) v[q] = 0.0;
 #pragma unroll
     for (int p = 0; p < 8; p++) {
-      float f[8];
-      load_cell(g, slot + c0 + off[p], f);
+      float f[8], kv = 0.0f;
+      size_t cell = c0 + off[p];
+      if (fmks && cell > last_cell) {
+        load_cell_past_end(g, slot, cell - last_cell - 1, f, kv);
+      } else {
+        load_cell(g, slot + cell, f);
+        if (g.kappa) kv = __ldg(g.kappa + slot + cell);
+      }
       if (p == 0) {
 #pragma unroll
         for (int q = 0; q < 8; q++) corner[q] = f[q];
@@ -453,7 +522,6 @@ __device__ __forceinline__ SampleStatus sample_grid(const RadParams &P, const Gr
 #pragma unroll
       for (int q = 0; q < 8; q++) v[q] += w[p] * (double)f[q];
       if (g.kappa) {
-        float kv = __ldg(g.kappa + slot + c0 + off[p]);
         if (p == 0) corner_kappa = kv;
         v[8] += w[p] * (double)kv;
       }

@@ -47,6 +47,15 @@ struct GridDev {
   uint32_t hash_mask;             // table size - 1 (power of two)
   int32_t max_level;
   int32_t n3_root;                // blocks around x3 at level 0 (RootGridSize[2] / n_k)
+  // simulation_coord = fmks: x1f, x2f stay native; (r, theta) -> native (x1, x2) through the reader's table
+  // sks_map(0|1, j, i) sampled at r = map_r_in + i map_dr, theta = j map_dtheta (simulation_geometry.cpp:330-413)
+  const double *sks_map;          // (2, map_n2, map_n1) or nullptr
+  int32_t map_n1, map_n2;
+  double map_r_in, map_dr, map_dtheta;
+  // The reference indexes one zone past the last row / plane there; in its (variable, cell) array that addresses the
+  // following cells and, past a variable's last cell, the first cells of the variable stored after it.  next_slot[q]:
+  // record slot (0-7; 8 = kappa) holding the variable that follows slot q in the reader's array, -1 = none (read as 0).
+  int8_t next_slot[9];
 };
 
 // key of a block in the topology hash; locations are < 2^19 on every level that can occur

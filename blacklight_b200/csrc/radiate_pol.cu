@@ -860,7 +860,7 @@ cudaError_t launch_fmax(const RadArgs &A, const RadParams &P, cudaStream_t strea
   unsigned grid = (unsigned)((A.rays + kBlock - 1) / kBlock);
   size_t smem = 0;
   if ((size_t)A.grid.n_b * 6 * sizeof(double) <= 48 * 1024) smem = (size_t)A.grid.n_b * 6 * sizeof(double);
-  if (P.block_interp || P.slow_light)
+  if (P.block_interp || P.slow_light || P.coord == 2)
     radiate_polarized_kernel<FMAX, true><<<grid, kBlock, smem, stream>>>(A, P);
   else
     radiate_polarized_kernel<FMAX, false><<<grid, kBlock, smem, stream>>>(A, P);

@@ -428,7 +428,7 @@ cudaError_t launch_fmax(const RadArgs &A, const RadParams &P, cudaStream_t strea
   const bool lean = P.image_light && !(P.image_time || P.image_length || P.image_lambda || P.image_emission ||
                                        P.image_tau || P.image_lambda_ave || P.image_emission_ave || P.image_tau_int ||
                                        P.image_crossings) &&
-                    !(sim && A.render != nullptr && P.render_num_images > 0) && !(sim && (P.block_interp || P.slow_light));
+                    !(sim && A.render != nullptr && P.render_num_images > 0) && !(sim && (P.block_interp || P.slow_light || P.coord == 2));
   unsigned grid = (unsigned)((A.rays + kBlock - 1) / kBlock);
   size_t smem = 0;
   if (sim && (size_t)A.grid.n_b * 6 * sizeof(double) <= 48 * 1024) smem = (size_t)A.grid.n_b * 6 * sizeof(double);

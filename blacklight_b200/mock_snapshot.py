@@ -67,6 +67,33 @@ def mock_fields(n_r=77, n_th=64, n_ph=128, pert_amp=0.1, pert_n_r=3.0, pert_n_th
     return dict(rf=rf, thf=thf, phf=phf, r=r, th=th, ph=ph, prim=prim)
 
 
+def mock_fields_at(R, TH, PH, pert_amp=0.1, pert_n_r=3.0, pert_n_th=2.0, pert_n_ph=4, inflow=0.05):
+    """The closed-form torus of mock_fields evaluated at arbitrary (broadcastable) spherical Kerr-Schild points,
+    plus a small poloidal velocity (`inflow`) so that every component of the vector transformations of the Harm
+    readers carries signal.  Returns 8 float64 arrays (rho, pgas, normal-frame uu^r, uu^th, uu^ph, B^r, B^th, B^ph)."""
+    r_isco = 6.0
+    omega_isco = r_isco ** -1.5
+    gamma_isco = (1.0 - 2.0 / r_isco - r_isco ** 2 * omega_isco ** 2) ** -0.5
+    uph_amp = gamma_isco * omega_isco * r_isco ** 1.5
+    cut_r_min, cut_r_max, cut_th_min, scale = 2.0, 50.0, np.pi / 16.0, np.pi / 8.0
+    R, TH, PH = np.broadcast_arrays(R, TH, PH)
+    inside = np.where((R < cut_r_min) | (R > cut_r_max) | (TH < cut_th_min) | (TH > np.pi - cut_th_min), 0.0, 1.0)
+    pert = 1.0 + pert_amp * (np.cos(2.0 * np.pi * pert_n_r * np.log(R / cut_r_min) / np.log(cut_r_max / cut_r_min))
+                             * -np.cos(2.0 * np.pi * pert_n_th * (TH - cut_th_min) / (np.pi - 2.0 * cut_th_min))
+                             * np.cos(pert_n_ph * PH))
+    off = np.abs(TH - np.pi / 2.0)
+    rho = np.maximum(R ** -0.5 * np.exp(-off / scale) * pert * inside, 1.0e-8)
+    pgas = np.maximum(0.1 * R ** -1.25 * np.exp(-off / scale) * pert ** 2 * inside, 1.0e-9)
+    uur = -inflow * R ** -0.5 * np.exp(-off / scale) * inside
+    uuth = 0.2 * inflow * np.cos(TH) / R * inside
+    uuph = uph_amp * R ** -1.5 * np.exp(-off / scale) * inside
+    bbz = 0.02 * np.maximum(R * np.sin(TH), cut_r_min) ** -0.625
+    bbr = np.cos(TH) * bbz
+    bbth = -np.sin(TH) / R * bbz
+    bbph = 0.2 * R ** -1.75 * np.exp(-off / scale) * np.where(TH > np.pi / 2.0, -1.0, 1.0)
+    return [np.array(a, np.float64) for a in (rho, pgas, uur, uuth, uuph, bbr, bbth, bbph)]
+
+
 def mock_fields_cks(n=48, half_width=52.0):
     """Smooth torus-like fields on a uniform Cartesian Kerr-Schild box [-w, w]^3 (simulation_coord = cks):
     x1, x2, x3 = x, y, z; velocity and field components are Cartesian.  Not a physical solution -- a smooth,
@@ -145,6 +172,8 @@ def _datatype(dtype):
         return struct.pack('<BBBBI', 0x10, 0x08, 0, 0, dtype.itemsize) + struct.pack('<HH', 0, 8 * dtype.itemsize)
     if dtype.kind == 'f' and dtype.itemsize == 4:
         return struct.pack('<BBBBI', 0x11, 0x20, 31, 0, 4) + struct.pack('<HHBBBBI', 0, 32, 23, 8, 0, 23, 127)
+    if dtype.kind == 'f' and dtype.itemsize == 8:
+        return struct.pack('<BBBBI', 0x11, 0x20, 63, 0, 8) + struct.pack('<HHBBBBI', 0, 64, 52, 11, 0, 52, 1023)
     if dtype.kind == 'S':
         return struct.pack('<BBBBI', 0x13, 0, 0, 0, dtype.itemsize)
     raise ValueError(dtype)
@@ -251,6 +280,133 @@ def write_athdf(path, grid, time=0.0):
             f.seek(daddr)
             f.write(np.ascontiguousarray(arr).tobytes())
         f.truncate(eof)
+
+
+def write_h5_tree(path, tree):
+    """Write nested dicts {name: ndarray | dict} as an HDF5 file of old-style groups (symbol table + local heap +
+    one B-tree leaf per group, v1 object headers whose first message is the symbol-table message, contiguous
+    datasets; 0-d arrays become scalar dataspaces) -- the subset the reference's parser walks for 'a/b/c' paths
+    (hdf5_format_metadata.cpp:29-160)."""
+    out = bytearray(96)
+
+    def put(b):
+        out.extend(b'\0' * (-len(out) % 8))
+        addr = len(out)
+        out.extend(b)
+        return addr
+
+    def dataset(arr):
+        arr = np.ascontiguousarray(arr).reshape(np.shape(arr))     # ascontiguousarray promotes 0-d to 1-d
+        daddr = put(arr.tobytes() if arr.nbytes else b'\0' * 8)
+        return put(_object_header([_message(1, _dataspace(arr.shape)), _message(3, _datatype(arr.dtype)),
+                                   _message(8, struct.pack('<BBQQ', 3, 1, daddr, arr.nbytes))]))
+
+    def group(node):
+        names = sorted(node)
+        headers = [group(node[n]) if isinstance(node[n], dict) else (dataset(np.asarray(node[n])), None, None) for n in names]
+        heap_data, offs = b'\0' * 8, []
+        for n in names:
+            offs.append(len(heap_data))
+            heap_data += _pad8(n.encode() + b'\0')
+        heap_data_addr = put(heap_data)
+        heap_addr = put(b'HEAP' + struct.pack('<B3xQQQ', 0, len(heap_data), _UNDEF, heap_data_addr))
+        snod = b'SNOD' + struct.pack('<BBH', 1, 0, len(names))
+        for off, (haddr, bt, hp) in zip(offs, headers):
+            snod += struct.pack('<QQII', off, haddr, 0 if bt is None else 1, 0)
+            snod += struct.pack('<QQ', bt, hp) if bt is not None else b'\0' * 16
+        snod_addr = put(snod)
+        tree_addr = put(b'TREE' + struct.pack('<BBHQQ', 0, 0, 1, _UNDEF, _UNDEF) + struct.pack('<QQQ', 0, snod_addr, offs[-1]))
+        header_addr = put(_object_header([_message(17, struct.pack('<QQ', tree_addr, heap_addr))]))
+        return header_addr, tree_addr, heap_addr
+
+    root_addr, tree_addr, heap_addr = group(tree)
+    eof = len(out)
+    out[0:96] = (b'\x89HDF\r\n\x1a\n' + struct.pack('<BBBBBBBB', 0, 0, 0, 0, 0, 8, 8, 0)
+                 + struct.pack('<HHI', 4, 16, 0) + struct.pack('<QQQQ', 0, _UNDEF, eof, _UNDEF)
+                 + struct.pack('<QQII', 0, root_addr, 1, 0) + struct.pack('<QQ', tree_addr, heap_addr))
+    with open(path, 'wb') as f:
+        f.write(bytes(out))
+
+
+def fmks_theta(x1, x2, hslope, r_in, poly_xt, poly_alpha, mks_smooth):
+    """theta(x1, x2) of the FMKS coordinates (reference simulation_geometry.cpp:416-434)."""
+    poly_norm = (poly_alpha + 1.0) * poly_xt ** poly_alpha
+    poly_norm = 0.5 * np.pi * poly_norm / (poly_norm + 1.0)
+    y = 2.0 * x2 - 1.0
+    theta_g = np.pi * x2 + (1.0 - hslope) / 2.0 * np.sin(2.0 * np.pi * x2)
+    theta_j = 0.5 * np.pi + poly_norm * y * (1.0 + (y / poly_xt) ** poly_alpha / (poly_alpha + 1.0))
+    return theta_g + np.exp(mks_smooth * (np.log(r_in) - x1)) * (theta_j - theta_g)
+
+
+def write_iharm3d(path, n_r=48, n_th=32, n_ph=32, gamma_adi=4.0 / 3.0, time=0.0, spin=0.0, hslope=1.0, fmks=None,
+                  r_min=None, r_max=None, **model):
+    """iharm3d-format HDF5 dump of the mock torus (reference scripts/generate_mock_simulation.py:79-157,200-243 for
+    the MKS case): header/{n1,n2,n3,gam,metric,n_prim,prim_names,geom/...}, t, and prims (n1, n2, n3, 8) float32 =
+    RHO, UU, normal-frame velocity U1-3 and lab-frame field B1-3 in the modified coordinates.
+    fmks = dict(poly_xt, poly_alpha, mks_smooth) writes FMKS coordinates instead (theta depends on x1 and x2); the
+    closed-form model is then evaluated at each cell's own (r, theta).  The reference ships no FMKS generator.
+    Spin 0 only (the generator's metric is Schwarzschild in Kerr-Schild form)."""
+    assert spin == 0.0
+    if r_min is None:
+        r_min = 2.0 * 25.0 ** (-1.0 / 75.0)
+    if r_max is None:
+        r_max = 2.0 * 25.0 ** (76.0 / 75.0)
+    lrf = np.linspace(np.log(r_min), np.log(r_max), n_r + 1)
+    x2f = np.linspace(0.0, 1.0, n_th + 1)
+    phf = np.linspace(0.0, 2.0 * np.pi, n_ph + 1)
+    lr, x2, ph = (0.5 * (f[:-1] + f[1:]) for f in (lrf, x2f, phf))
+    X1, X2 = np.meshgrid(lr, x2, indexing='xy')            # (th, r)
+    R = np.exp(X1)
+    if fmks is None:
+        TH = np.pi * X2 + (1.0 - hslope) / 2.0 * np.sin(2.0 * np.pi * X2)
+        dth_dx1 = np.zeros_like(TH)
+        dth_dx2 = np.pi + (1.0 - hslope) * np.pi * np.cos(2.0 * np.pi * X2)
+    else:
+        args = (hslope, r_min, fmks['poly_xt'], fmks['poly_alpha'], fmks['mks_smooth'])
+        TH = fmks_theta(X1, X2, *args)
+        eps = 1.0e-6
+        dth_dx1 = (fmks_theta(X1 + eps, X2, *args) - fmks_theta(X1 - eps, X2, *args)) / (2.0 * eps)
+        dth_dx2 = (fmks_theta(X1, X2 + eps, *args) - fmks_theta(X1, X2 - eps, *args)) / (2.0 * eps)
+    prim = mock_fields_at(R[None], TH[None], ph[:, None, None], **model)       # 8 x (ph, th, r), float64
+    rho, pgas, uur, uuth, uuph, bbr, bbth, bbph = prim
+    R3, TH3 = R[None], TH[None]
+    f = 2.0 / R3
+    g_tr, g_rr, g_thth, g_phph = f, 1.0 + f, R3 ** 2, R3 ** 2 * np.sin(TH3) ** 2
+    gtt, gtr = -(1.0 + f), f
+    alpha = 1.0 / np.sqrt(-gtt)
+    # standard normal frame -> standard coordinate frame
+    uut = np.sqrt(1.0 + g_rr * uur ** 2 + g_thth * uuth ** 2 + g_phph * uuph ** 2)
+    ut, ur, uth, uph = uut / alpha, uur - alpha * uut * gtr, uuth, uuph
+    u_r, u_th, u_ph = g_tr * ut + g_rr * ur, g_thth * uth, g_phph * uph
+    bt = u_r * bbr + u_th * bbth + u_ph * bbph
+    br, bth, bph = (bbr + bt * ur) / ut, (bbth + bt * uth) / ut, (bbph + bt * uph) / ut
+    # standard -> modified coordinate frame: dr = r dx1, dth = dth_dx1 dx1 + dth_dx2 dx2
+    a1, a2 = dth_dx1[None], dth_dx2[None]
+    u1, u3 = ur / R3, uph
+    u2 = (uth - a1 * u1) / a2
+    b1, b3 = br / R3, bph
+    b2 = (bth - a1 * b1) / a2
+    # modified coordinate frame -> modified normal frame primitives: g^{0i} of the modified coordinates
+    g01 = gtr / R3
+    g02 = -a1 * gtr / (R3 * a2)
+    uu1, uu2, uu3 = u1 + alpha ** 2 * g01 * ut, u2 + alpha ** 2 * g02 * ut, u3
+    bb1, bb2, bb3 = b1 * ut - bt * u1, b2 * ut - bt * u2, b3 * ut - bt * u3
+    prims = np.array([rho, pgas / (gamma_adi - 1.0), uu1, uu2, uu3, bb1, bb2, bb3], dtype=np.float32).transpose()
+    name = 'MKS' if fmks is None else 'FMKS'
+    S20 = lambda *v: np.array(v, dtype='S20')
+    f64, i32 = (lambda v: np.array(v, np.float64)), (lambda v: np.array(v, np.int32))
+    params = {'a': f64(spin), 'hslope': f64(hslope), 'r_eh': f64(2.0), 'r_in': f64(r_min), 'r_out': f64(r_max)}
+    if fmks is not None:
+        params.update({k: f64(fmks[k]) for k in ('poly_xt', 'poly_alpha', 'mks_smooth')})
+    tree = {'header': {'version': S20(b'iharm-blacklight'), 'gam': f64(gamma_adi), 'tf': f64(0.0), 'n1': i32(n_r), 'n2': i32(n_th),
+                       'n3': i32(n_ph), 'metric': S20(name.encode()), 'n_prim': i32(8),
+                       'prim_names': S20(b'RHO', b'UU', b'U1', b'U2', b'U3', b'B1', b'B2', b'B3'), 'has_electrons': i32(0),
+                       'geom': {'dx1': f64(lrf[1] - lrf[0]), 'dx2': f64(x2f[1] - x2f[0]), 'dx3': f64(phf[1] - phf[0]),
+                                'startx1': f64(lrf[0]), 'startx2': f64(x2f[0]), 'startx3': f64(phf[0]), 'n_dim': i32(4),
+                                name.lower(): params}},
+            't': f64(time), 'prims': prims}
+    write_h5_tree(path, tree)
+    return dict(lrf=lrf, x2f=x2f, phf=phf, r=R, th=TH, prims=prims)
 
 
 def write_harm3d(path, fields, gamma_adi=4.0 / 3.0, time=0.0):

@@ -146,6 +146,13 @@ typedef struct bl_grid_view {
   const float *prim;              /* (n_var, n_b, n_k, n_j, n_i) */
   int32_t ind_rho, ind_pgas, ind_kappa, ind_uu1, ind_uu2, ind_uu3, ind_bb1, ind_bb2, ind_bb3;
   int32_t n_3_root;               /* RootGridSize[2], inter-block interpolation only */
+  /* simulation_coord = fmks only (simulation_reader.hpp:103-112, simulation_geometry.cpp:330-413): x1f, x2f, x?v stay in
+   * the native coordinates; sks_map(0|1, j, i) = native x1 | x2 at r = r_in + i dr, theta = j dtheta; the block test uses
+   * simulation_bounds = (r_min, r_max, theta_min, theta_max, phi_min, phi_max) (simulation_sampling.cpp:190-198,397-413) */
+  const double *sks_map;          /* (2, sks_map_n2, sks_map_n1) or NULL */
+  int32_t sks_map_n1, sks_map_n2;
+  double sks_map_r_in, sks_map_dr, sks_map_dtheta;
+  double simulation_bounds[6];
 } bl_grid_view;
 
 typedef struct bl_level_stats {

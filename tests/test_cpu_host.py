@@ -247,6 +247,56 @@ def test_athdf_and_harm3d_readers_return_the_generator_arrays(tmp_path):
     np.testing.assert_allclose(h['prim'][h['ind_rho'], 0], fields['prim'][0], rtol=1e-6)
 
 
+@pytest.mark.parametrize('fmks', [None, dict(poly_xt=0.82, poly_alpha=14.0, mks_smooth=0.5)])
+def test_iharm3d_reader(tmp_path, fmks, capfd):
+    """simulation_format = iharm3d (SURVEY section 8f-3): nested HDF5 groups, scalar datasets, prims (n1, n2, n3, n_prim);
+    MKS coordinates converted to spherical Kerr-Schild, FMKS kept native with the (r, theta) -> (x1, x2) table; the
+    vector conversion (reference simulation_geometry.cpp:95-236) must recover the generator's standard
+    normal-frame velocity and coordinate-frame field, which the generator transformed the other way independently."""
+    from blacklight_b200 import mock_snapshot as ms
+    snap = os.path.join(str(tmp_path), 'mock.h5')
+    hslope = 0.3 if fmks else 0.7
+    w = ms.write_iharm3d(snap, n_r=24, n_th=16, n_ph=8, gamma_adi=1.5, time=4.5, hslope=hslope, fmks=fmks)
+    kv = {'simulation_coord': 'fmks' if fmks else 'sks', 'simulation_a': '0.0'}
+    from harness import load_input
+    base = load_input('simulation.input')
+    cfg = _reader_case(tmp_path, 'iharm3d', snap, kv)
+    g = bl.read_snapshot(cfg)
+    assert (g['n_b'], g['n_k'], g['n_j'], g['n_i'], g['n_var']) == (1, 8, 16, 24, 8)
+    assert g['time'] == 4.5
+    assert g['plasma_gamma'] == (float(base['plasma_gamma']) if 'plasma_gamma' in base else 1.5)
+    lr = 0.5 * (w['lrf'][:-1] + w['lrf'][1:])
+    x2 = 0.5 * (w['x2f'][:-1] + w['x2f'][1:])
+    if fmks:
+        np.testing.assert_allclose(g['x1v'][0], lr, rtol=1e-14)          # native coordinates
+        np.testing.assert_allclose(g['x2v'][0], x2, rtol=1e-14)
+        # the table inverts theta(x1, x2) on a 2048 x 2048 lattice of (r, theta).  (Not to the bisection tolerance of
+        # 1e-8: the reference's loop, restated as is, moves x2 to the midpoint of the next bracket before testing
+        # the previous midpoint's theta, simulation_geometry.cpp:381-395.)
+        m = g['sks_map']
+        assert m.shape == (2, 2048, 2048)
+        r_in = np.exp(w['lrf'][0])
+        assert g['sks_map_r_in'] == r_in and abs(g['sks_map_dtheta'] - np.pi / 2047) < 1e-15
+        jj, ii = np.meshgrid(np.arange(0, 2048, 89), np.arange(0, 2048, 97), indexing='ij')
+        np.testing.assert_allclose(m[0, jj, ii], np.log(r_in + ii * g['sks_map_dr']), rtol=1e-14)
+        th = ms.fmks_theta(m[0, jj, ii], m[1, jj, ii], hslope, r_in, fmks['poly_xt'], fmks['poly_alpha'], fmks['mks_smooth'])
+        assert np.max(np.abs(th - jj * g['sks_map_dtheta'])) < 1e-4
+        np.testing.assert_allclose(g['simulation_bounds'], [r_in, np.exp(w['lrf'][-1]), 0.0, np.pi, 0.0, 2.0 * np.pi], atol=1e-12)
+    else:
+        np.testing.assert_allclose(g['x1v'][0], np.exp(lr), rtol=1e-14)
+        np.testing.assert_allclose(g['x2v'][0], np.pi * x2 + (1.0 - hslope) / 2.0 * np.sin(2.0 * np.pi * x2), rtol=1e-14)
+    ph = 0.5 * (w['phf'][:-1] + w['phf'][1:])
+    want = ms.mock_fields_at(w['r'][None], w['th'][None], ph[:, None, None])
+    gm1 = np.float32(g['plasma_gamma'] - 1.0)
+    names = ('ind_rho', 'ind_pgas', 'ind_uu1', 'ind_uu2', 'ind_uu3', 'ind_bb1', 'ind_bb2', 'ind_bb3')
+    for q, name in enumerate(names):
+        got = g['prim'][g[name], 0].astype(np.float64)
+        ref = want[q] if q != 1 else (want[1] / 0.5).astype(np.float32).astype(np.float64) * float(gm1)
+        scale = np.max(np.abs(ref))
+        tol = 3e-7 if not fmks or q < 2 else 2e-5     # the FMKS generator differentiates theta(x1, x2) numerically
+        assert np.max(np.abs(got - ref)) <= tol * scale, (name, np.max(np.abs(got - ref)) / scale)
+
+
 def test_npz_writer_and_athdf_reader_through_driver_without_gpu(tmp_path):
     """blh_run_input_file must fail loudly without a GPU, after parsing the file."""
     import torch

@@ -628,6 +628,109 @@ def test_athenak_reader_against_reference(over, sizes, gpu, tmp_path):
         assert flux_rel(mine['I_nu'], ref['I_nu']) <= FLUX_TOL
 
 
+@pytest.mark.parametrize('over,fmks', [
+    ({'camera_resolution': 32}, False),
+    ({'camera_resolution': 28, 'simulation_interp': 'false'}, False),
+    ({'camera_resolution': 24, 'image_polarization': 'true'}, False),
+    ({'camera_resolution': 32}, True),
+    ({'camera_resolution': 28, 'simulation_interp': 'false'}, True),
+    ({'camera_resolution': 24, 'image_polarization': 'true'}, True),
+    ({'camera_resolution': 24, 'plasma_use_p': 'false', 'plasma_gamma_i': '1.6666666666666667'}, True),
+])
+def test_iharm3d_reader_against_reference(over, fmks, gpu, tmp_path):
+    """simulation_format = iharm3d, simulation_coord = sks (MKS dump, converted on the host) and
+    fmks (native coordinates + the reader's (r, theta) -> (x1, x2) table; cells found by scaling on the device,
+    reference simulation_sampling.cpp:190-198,397-452).  Through the drop-in executable against the reference
+    binary on the same dump; unpolarized cases also compare the sampled cell indices and fractions."""
+    if not os.path.exists(REF_BIN):
+        pytest.skip('oracle/_ref/blacklight not present')
+    import subprocess
+    import refio
+    from blacklight_b200 import mock_snapshot as ms
+    from harness import write_input
+    d = str(tmp_path)
+    case = Case(d, 'simulation.input', over)
+    snap = os.path.join(d, 'data', 'mock.iharm3d.h5')
+    ms.write_iharm3d(snap, n_r=48, n_th=32, n_ph=32, gamma_adi=13.0 / 9.0, time=2.0, hslope=0.3 if fmks else 0.7,
+                     fmks=dict(poly_xt=0.82, poly_alpha=14.0, mks_smooth=0.5) if fmks else None)
+    pol = over.get('image_polarization') == 'true'
+    interp = over.get('simulation_interp', 'true') == 'true'
+    images, paths = {}, {}
+    for who in ('ref', 'gpu'):
+        kv = dict(case.kv)
+        kv.update({'simulation_format': 'iharm3d', 'simulation_file': snap, 'simulation_coord': 'fmks' if fmks else 'sks',
+                   'simulation_a': '0.0', 'output_file': os.path.join(d, who + '.npz')})
+        kv.pop('simulation_block_interp', None)
+        kv.pop('plasma_gamma', None)           # header/gam of the dump
+        if 'plasma_gamma_i' in over:
+            kv['plasma_gamma_e'] = '1.3333333333333333'   # the mock dump carries neither gam_p nor gam_e
+        if who == 'ref' and not pol and 'plasma_gamma_i' not in over:
+            kv.update({'checkpoint_sample_save': 'true', 'checkpoint_sample_load': 'false',
+                       'checkpoint_sample_file': os.path.join(d, 'samp.ckpt')})
+        paths[who] = os.path.join(d, who + '.input')
+        write_input(paths[who], kv)
+        if who == 'ref':
+            proc = subprocess.run([REF_BIN, paths[who]], cwd=d, capture_output=True, text=True, timeout=3600)
+            assert proc.returncode == 0 and 'Calculation completed' in proc.stdout, proc.stdout + proc.stderr
+        else:
+            bl.run_input_file(paths[who])
+        images[who] = dict(np.load(os.path.join(d, who + '.npz')))
+    ref, mine = images['ref'], images['gpu']
+    assert float(np.nanmax(ref['I_nu'])) > 0.0
+    # sampled cells: our reader's arrays through the C ABI with the parity taps on (unpolarized kernel, same rays)
+    kv = dict(bl.parse_input_text(open(paths['gpu']).read()), image_polarization='false')
+    paths['taps'] = os.path.join(d, 'taps.input')
+    write_input(paths['taps'], kv)
+    cfg = bl.Config(paths['taps'])
+    ctx = bl.Context(cfg)
+    grid = bl.read_snapshot(cfg)
+    ctx.upload_grid(grid)
+    pos, dirs, fac = cfg.camera_root()
+    ctx.trace_level(0, pos, dirs, fac)
+    ctx.set_taps(True)
+    ctx.radiate_level(0)
+    s = ctx.download_samples(0)
+    t = ctx.download_sample_inds(0, interp=interp)
+    ctx.close()
+    mask = np.arange(s['pos'].shape[1])[None, :] < s['num'][:, None]
+    valid = mask & (t['cut'] == 0) & (t['nan'] == 0) & (t['fallback'] == 0)
+    res = int(over['camera_resolution'])
+    defined = np.ones((res, res), bool)
+    if fmks and interp:
+        # The FMKS lookup interpolates between zone (i, j) and (i + 1, j + 1) for every zone, the last ones included
+        # (simulation_sampling.cpp:412-418,437-446): past a row that is the next row, past a variable's last cell the
+        # first cells of the next variable (reproduced) -- and past the LAST variable's last cell whatever follows the
+        # reference's array in memory.  Pixels whose rays take such a sample are compared loosely.
+        nk, nj, ni = grid['n_k'], grid['n_j'], grid['n_i']
+        k_m, j_m, i_m = (t['inds'][..., c] for c in (1, 2, 3))
+        past = valid & (k_m == nk - 2) & ((j_m == nj - 1) | ((j_m == nj - 2) & (i_m == ni - 1)))
+        defined = ~past.any(axis=1).reshape(res, res)
+        assert defined.sum() > 0.9 * defined.size
+        assert rel_err(mine['I_nu'], ref['I_nu']) <= 1e-4
+    keep = lambda img: np.where(defined, img, 0.0)
+    assert rel_err(keep(mine['I_nu']), keep(ref['I_nu'])) <= PIXEL_TOL
+    assert flux_rel(keep(mine['I_nu']), keep(ref['I_nu'])) <= FLUX_TOL
+    if pol:
+        for k, v in stokes_err({q: keep(v) for q, v in mine.items() if q.endswith('_nu')},
+                               {q: keep(v) for q, v in ref.items() if q.endswith('_nu')}).items():
+            assert v <= PIXEL_TOL, '%s %.3e' % (k, v)
+        return
+    if 'plasma_gamma_i' in over:
+        return
+    rs = refio.read_sample_checkpoint(os.path.join(d, 'samp.ckpt'), interp=interp)
+    assert np.array_equal(t['nan'][mask], rs['sample_nan'][mask])
+    assert valid.sum() > 1000
+    same = np.all(t['inds'][valid] == rs['sample_inds'][valid], axis=-1)
+    print('iharm3d fmks=%s: %d of %d sampled cells differ' % (fmks, int((~same).sum()), int(valid.sum())))
+    # theta = acos(z / r) comes from two different math libraries: a sample within an ulp of a zone boundary could
+    # land on the other side (none observed)
+    assert (~same).sum() <= 1e-5 * valid.sum()
+    if interp:
+        both = valid.copy()
+        both[valid] = same
+        assert np.max(np.abs(t['fracs'][both] - rs['sample_fracs'][both])) < 1e-6
+
+
 def test_adaptive_two_levels_with_forced_region_against_reference(gpu, tmp_path):
     """Two refinement levels (a forced region plus the relative-Laplacian criterion), polarized, through the
     drop-in executable: block lists, block counts and every per-level image against the reference."""
