@@ -42,8 +42,29 @@ RAD_FLOP_PER_SAMPLE_FREQ = {'simulation': 70.0 + 8 * 80.0, 'formula': 70.0 + 5 *
 GATHER_BYTES_PER_SAMPLE = 256.0
 RECORD_BYTES_PER_SAMPLE = 64.0
 # dram__bytes_read.sum + dram__bytes_write.sum per stored sample from the committed ncu --set full captures
-# (profiles/r01_ncu_full_512.txt): geodesic kernel 64.1 B (all writes), radiation kernel 64.4 B (all reads)
-NCU_DRAM_BYTES_PER_SAMPLE = {'geodesic_dp_kernel': 64.1, 'radiate_unpolarized_kernel': 64.4}
+# (profiles/r01k_ncu_full_summary.txt): geodesic kernel 65.4 B (all writes), radiation kernel 65.3 B (all reads)
+NCU_DRAM_BYTES_PER_SAMPLE = {'geodesic_dp_kernel': 65.4, 'radiate_unpolarized_kernel': 65.3}
+# Executed FP64 work from the committed ncu captures (profiles/r01k_ncu_full_summary.txt): thread-level
+# DADD + DMUL + 2 DFMA per unit (DP attempt for the geodesic kernel, stored sample for the radiation kernels, at the
+# workload's frequency count) and the share of cycles the FP64 pipe was active.  Unlike the as-written counts above
+# (the reference's operation count, the reproducible contract of SURVEY 8d) these are what the restructured kernels
+# really issue; a kernel keyed by workload has no entry for workloads that were not captured.
+NCU_EXECUTED = {
+    'geodesic_dp_kernel': {'flop_per_unit': 1.577e11 / 19384738, 'unit': 'attempt', 'fp64_pipe_active': 0.670},
+    'simulation': {'flop_per_unit': 1.544e11 / 184675182, 'unit': 'sample', 'fp64_pipe_active': 0.301, 'dram_bytes_per_sample': 65.3},
+    'polarized_thermal': {'flop_per_unit': 4.495e11 / 103872314, 'unit': 'sample', 'fp64_pipe_active': 0.277, 'dram_bytes_per_sample': 67.5},
+    'polarized': {'flop_per_unit': 5.414e11 / 46164658, 'unit': 'sample (4 frequencies)', 'fp64_pipe_active': 0.294, 'dram_bytes_per_sample': 69.3},
+}
+
+
+def executed_roofline(key, units, ms, fp64_peak):
+    e = NCU_EXECUTED.get(key)
+    if e is None or ms <= 0:
+        return None
+    tflops = e['flop_per_unit'] * units / (ms * 1e-3) / 1e12
+    return {'achieved': tflops, 'unit': 'TFLOP/s', 'frac': tflops / fp64_peak if fp64_peak else None,
+            'flop_per_unit': e['flop_per_unit'], 'per': e['unit'], 'fp64_pipe_active': e['fp64_pipe_active'],
+            'source': 'profiles/r01k_ncu_full_summary.txt (ncu DADD + DMUL + 2 DFMA thread instructions per unit x live unit count / live kernel time)'}
 
 
 def parse_args():
@@ -367,12 +388,16 @@ def main():
                                        'unit': 'TFLOP/s', 'frac': geo_tflops / fp64_peak if fp64_peak else None,
                                        'traffic': st['num_samples'] * NCU_DRAM_BYTES_PER_SAMPLE['geodesic_dp_kernel'],
                                        'ms': geo_ms, 'peak_source': peak_src,
+                                       'executed': executed_roofline('geodesic_dp_kernel', st['num_attempts'], geo_ms, fp64_peak),
                                        'hbm': {'achieved': st['num_samples'] * RECORD_BYTES_PER_SAMPLE / (geo_ms * 1e-3) / 1e9 if geo_ms > 0 else 0.0,
                                                'peak': hbm_peak, 'unit': 'GB/s', 'peak_source': hbm_src}},
                 rad_name: {'kernel': rad_name, 'bound': 'fp64', 'achieved': rad_tflops, 'peak': fp64_peak, 'unit': 'TFLOP/s',
                            'frac': rad_tflops / fp64_peak if fp64_peak else None,
-                           'traffic': st['num_samples'] * NCU_DRAM_BYTES_PER_SAMPLE.get(rad_name) if rad_name in NCU_DRAM_BYTES_PER_SAMPLE else None,
+                           'traffic': (st['num_samples'] * NCU_EXECUTED[args.workload]['dram_bytes_per_sample']
+                                       if args.workload in NCU_EXECUTED and args.grid_scale == 1 else None),
                            'ms': rad_ms, 'peak_source': peak_src,
+                           'executed': (executed_roofline(args.workload, st['num_samples'], rad_ms, fp64_peak)
+                                        if F == (4 if args.workload == 'polarized' else 1) else None),
                            'note': 'as-written flop-equivalents of the reference per sample (libm calls at 80); the cell gather is '
                                    'L2 resident for the 20 MB mock grid',
                            'gather': {'achieved': gather_gbs, 'unit': 'GB/s', 'bytes_per_sample': GATHER_BYTES_PER_SAMPLE},

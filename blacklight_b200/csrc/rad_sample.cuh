@@ -306,6 +306,100 @@ __device__ __forceinline__ void flush_slow_light(unsigned long long *counters, c
     }
 }
 
+// FMKS grids (simulation_coord = fmks): zone and fractional position by scaling in the native coordinates, found
+// through the reader's (r, theta) -> (x1, x2) table (simulation_sampling.cpp:397-452).  The arithmetic is spelled out
+// operation by operation (no contraction) because truncations of its results are cell indices.  Indices one past a
+// row (the reference forms them for the last zone) address the following cells of the flat array, as they do there;
+// past the last cell see load_cell_past_end.  Kept apart from sample_grid so that the other coordinate systems'
+// code is not perturbed.
+static __device__ __noinline__ SampleStatus sample_grid_fmks(const RadParams &P, const GridDev &g, int b, double x1, double x2,
+                                                      double x3, size_t slot_a, size_t slot_b, bool two_slices,
+                                                      double t_frac, CellCache &cache, Prims &out, SampleIndex &si) {
+  const int n_i = g.n_i, n_j = g.n_j, n_k = g.n_k;
+  const size_t last_cell = (size_t)g.n_b * n_k * n_j * n_i - 1;
+  int k = find_cell_hint(g.x3f + (size_t)b * (n_k + 1), n_k, x3, cache.k);
+  cache.k = k;
+  si.b = b;
+  const int m1 = g.map_n1, m2 = g.map_n2;
+  double i_ind, j_ind;
+  double t_i = modf(__ddiv_rn(__dsub_rn(x1, g.map_r_in), g.map_dr), &i_ind);
+  double t_j = modf(__ddiv_rn(x2, g.map_dtheta), &j_ind);
+  int mi = min(max((int)i_ind, 0), m1 - 1), mj = min(max((int)j_ind, 0), m2 - 1);
+  const double *map_x1 = g.sks_map + (size_t)mj * m1, *map_x2 = g.sks_map + ((size_t)m2 + min(mj + 1, m2 - 1)) * m1;
+  double a_lo = __ldg(map_x1 + mi), a_hi = __ldg(map_x1 + min(mi + 1, m1 - 1)), b_hi = __ldg(map_x2 + mi);
+  double nat_x1 = __dadd_rn(__dmul_rn(__dsub_rn(1.0, t_i), a_lo), __dmul_rn(t_i, a_hi));
+  double nat_x2 = __dadd_rn(__dmul_rn(__dsub_rn(1.0, t_j), b_hi), __dmul_rn(t_j, b_hi));   // both terms at j+1, as the reference
+  double x1_0 = __ldg(g.x1f), dx1 = __dsub_rn(__ldg(g.x1f + 1), x1_0), dx2 = __dsub_rn(__ldg(g.x2f + 1), __ldg(g.x2f));
+  double f_i = modf(__ddiv_rn(__dsub_rn(nat_x1, x1_0), dx1), &i_ind);
+  double f_j = modf(__ddiv_rn(nat_x2, dx2), &j_ind);
+  int i_m = (int)i_ind, j_m = (int)j_ind;
+
+  auto load = [&](size_t slot, size_t cell, float f[8], float &kv) {
+    if (cell > last_cell) {
+      load_cell_past_end(g, slot, cell - last_cell - 1, f, kv);
+    } else {
+      load_cell(g, slot + cell, f);
+      kv = g.kappa ? __ldg(g.kappa + slot + cell) : 0.0f;
+    }
+  };
+  auto finish = [&](auto gather) {
+    double v[9];
+    gather(slot_a, v);
+    if (two_slices) {
+      double w[9];
+      gather(slot_b, w);
+      for (int q = 0; q < 9; q++) v[q] = (1.0 - t_frac) * v[q] + t_frac * w[q];
+    }
+    out.rho = (float)v[0]; out.pgas = (float)v[1]; out.uu1 = (float)v[2]; out.uu2 = (float)v[3];
+    out.uu3 = (float)v[4]; out.bb1 = (float)v[5]; out.bb2 = (float)v[6]; out.bb3 = (float)v[7];
+    out.kappa = (float)v[8];
+  };
+
+  if (!P.interp) {
+    int i = f_i >= 0.5 ? i_m + 1 : i_m, j = f_j >= 0.5 ? j_m + 1 : j_m;
+    si.k = k; si.j = j; si.i = i;
+    si.fk = si.fj = si.fi = 0.0;
+    size_t c = (((size_t)b * n_k + k) * n_j + j) * n_i + i;
+    finish([&](size_t slot, double v[9]) {
+      float f[8], kv;
+      load(slot, c, f, kv);
+      for (int q = 0; q < 8; q++) v[q] = (double)f[q];
+      v[8] = (double)kv;
+    });
+    return kSampleOk;
+  }
+  const double *x3v = g.x3v + (size_t)b * n_k;
+  int k_m = (k == 0 || (k != n_k - 1 && x3 >= __ldg(x3v + k))) ? k : k - 1;
+  double f_k = (x3 - __ldg(x3v + k_m)) * __ldg(g.x3d + (size_t)b * n_k + k_m);
+  si.k = k_m; si.j = j_m; si.i = i_m;
+  si.fk = f_k; si.fj = f_j; si.fi = f_i;
+  double gk = 1.0 - f_k, gj = 1.0 - f_j, gi = 1.0 - f_i;
+  double w[8] = {gk * gj * gi, gk * gj * f_i, gk * f_j * gi, gk * f_j * f_i,
+                 f_k * gj * gi, f_k * gj * f_i, f_k * f_j * gi, f_k * f_j * f_i};
+  size_t c0 = (((size_t)b * n_k + k_m) * n_j + j_m) * n_i + i_m;
+  size_t sj = (size_t)n_i, sk = (size_t)n_j * n_i;
+  size_t off[8] = {0, 1, sj, sj + 1, sk, sk + 1, sk + sj, sk + sj + 1};
+  finish([&](size_t slot, double v[9]) {
+    float corner[8] = {0, 0, 0, 0, 0, 0, 0, 0}, corner_kappa = 0.0f;
+    for (int q = 0; q < 9; q++) v[q] = 0.0;
+    for (int p = 0; p < 8; p++) {
+      float f[8], kv;
+      load(slot, c0 + off[p], f, kv);
+      if (p == 0) {
+        for (int q = 0; q < 8; q++) corner[q] = f[q];
+        corner_kappa = kv;
+      }
+      for (int q = 0; q < 8; q++) v[q] += w[p] * (double)f[q];
+      v[8] += w[p] * (double)kv;
+    }
+    // non-positive interpolated rho / pgas / kappa fall back to the anchor cell (:822-827)
+    if (v[0] <= 0.0) v[0] = (double)corner[0];
+    if (v[1] <= 0.0) v[1] = (double)corner[1];
+    if (g.kappa && v[8] <= 0.0) v[8] = (double)corner_kappa;
+  });
+  return kSampleOk;
+}
+
 // EXT: inter-block interpolation and slow light compiled in (selected at run time by P.block_interp /
 // P.slow_light); the light-only unpolarized kernel is instantiated without them so that the common path keeps
 // its register budget.  x0 = coordinate time of the sample + camera time of the image (slow light only).
@@ -348,12 +442,9 @@ __device__ __forceinline__ SampleStatus sample_grid(const RadParams &P, const Gr
     cache.b = bn;
   }
   const int n_i = g.n_i, n_j = g.n_j, n_k = g.n_k;
-  const bool fmks = EXT && P.coord == 2;
-  int i = 0, j = 0;
-  if (!fmks) {
-    i = find_cell_hint(g.x1f + (size_t)b * (n_i + 1), n_i, x1, cache.i);
-    j = find_cell_hint(g.x2f + (size_t)b * (n_j + 1), n_j, x2, cache.j);
-  }
+  if (EXT && P.coord == 2) return sample_grid_fmks(P, g, b, x1, x2, x3, slot_a, slot_b, two_slices, t_frac, cache, out, si);
+  int i = find_cell_hint(g.x1f + (size_t)b * (n_i + 1), n_i, x1, cache.i);
+  int j = find_cell_hint(g.x2f + (size_t)b * (n_j + 1), n_j, x2, cache.j);
   int k = find_cell_hint(g.x3f + (size_t)b * (n_k + 1), n_k, x3, cache.k);
   cache.i = i; cache.j = j; cache.k = k;
   si.b = b;
@@ -376,47 +467,16 @@ __device__ __forceinline__ SampleStatus sample_grid(const RadParams &P, const Gr
     out.kappa = (float)v[8];
   };
 
-  // FMKS grids: zone and fractional position by scaling in the native coordinates, found through the reader's
-  // (r, theta) -> (x1, x2) table (simulation_sampling.cpp:397-452).  The arithmetic is spelled out operation by
-  // operation (no contraction) because truncations of its results are cell indices.  Indices one past a row (the
-  // reference forms them for the last zone) address the following cells of the flat array, as they do there.
-  int fm_i = 0, fm_j = 0;
-  double fm_fi = 0.0, fm_fj = 0.0;
-  const size_t last_cell = (size_t)g.n_b * n_k * n_j * n_i - 1;
-  if (fmks) {
-    const int m1 = g.map_n1, m2 = g.map_n2;
-    double i_ind, j_ind;
-    double t_i = modf(__ddiv_rn(__dsub_rn(x1, g.map_r_in), g.map_dr), &i_ind);
-    double t_j = modf(__ddiv_rn(x2, g.map_dtheta), &j_ind);
-    int mi = min(max((int)i_ind, 0), m1 - 1), mj = min(max((int)j_ind, 0), m2 - 1);
-    const double *map_x1 = g.sks_map + (size_t)mj * m1, *map_x2 = g.sks_map + ((size_t)m2 + min(mj + 1, m2 - 1)) * m1;
-    double a_lo = __ldg(map_x1 + mi), a_hi = __ldg(map_x1 + min(mi + 1, m1 - 1)), b_hi = __ldg(map_x2 + mi);
-    double nat_x1 = __dadd_rn(__dmul_rn(__dsub_rn(1.0, t_i), a_lo), __dmul_rn(t_i, a_hi));
-    double nat_x2 = __dadd_rn(__dmul_rn(__dsub_rn(1.0, t_j), b_hi), __dmul_rn(t_j, b_hi));   // both terms at j+1, as the reference
-    double x1_0 = __ldg(g.x1f), dx1 = __dsub_rn(__ldg(g.x1f + 1), x1_0), dx2 = __dsub_rn(__ldg(g.x2f + 1), __ldg(g.x2f));
-    fm_fi = modf(__ddiv_rn(__dsub_rn(nat_x1, x1_0), dx1), &i_ind);
-    fm_fj = modf(__ddiv_rn(nat_x2, dx2), &j_ind);
-    fm_i = (int)i_ind;
-    fm_j = (int)j_ind;
-    i = fm_fi >= 0.5 ? fm_i + 1 : fm_i;
-    j = fm_fj >= 0.5 ? fm_j + 1 : fm_j;
-  }
-
   if (!P.interp) {
     si.k = k; si.j = j; si.i = i;
     si.fk = si.fj = si.fi = 0.0;
     size_t c = (((size_t)b * n_k + k) * n_j + j) * n_i + i;
     finish([&](size_t slot, double v[9]) {
-      float f[8], kv = 0.0f;
-      if (fmks && c > last_cell) {
-        load_cell_past_end(g, slot, c - last_cell - 1, f, kv);
-      } else {
-        load_cell(g, slot + c, f);
-        if (g.kappa) kv = __ldg(g.kappa + slot + c);
-      }
+      float f[8];
+      load_cell(g, slot + c, f);
 #pragma unroll
       for (int q = 0; q < 8; q++) v[q] = (double)f[q];
-      v[8] = (double)kv;
+      v[8] = g.kappa ? (double)__ldg(g.kappa + slot + c) : 0.0;
     });
     return kSampleOk;
   }
@@ -478,18 +538,11 @@ __device__ __forceinline__ SampleStatus sample_grid(const RadParams &P, const Gr
   }
 
   // intra-block trilinear with extrapolation at block edges (simulation_sampling.cpp:485-502)
-  int i_m, j_m;
-  double f_i, f_j;
-  if (fmks) {
-    i_m = fm_i; j_m = fm_j;
-    f_i = fm_fi; f_j = fm_fj;
-  } else {
-    i_m = (i == 0 || (i != n_i - 1 && x1 >= __ldg(x1v + i))) ? i : i - 1;
-    j_m = (j == 0 || (j != n_j - 1 && x2 >= __ldg(x2v + j))) ? j : j - 1;
-    f_i = (x1 - __ldg(x1v + i_m)) * __ldg(g.x1d + (size_t)b * n_i + i_m);
-    f_j = (x2 - __ldg(x2v + j_m)) * __ldg(g.x2d + (size_t)b * n_j + j_m);
-  }
+  int i_m = (i == 0 || (i != n_i - 1 && x1 >= __ldg(x1v + i))) ? i : i - 1;
+  int j_m = (j == 0 || (j != n_j - 1 && x2 >= __ldg(x2v + j))) ? j : j - 1;
   int k_m = (k == 0 || (k != n_k - 1 && x3 >= __ldg(x3v + k))) ? k : k - 1;
+  double f_i = (x1 - __ldg(x1v + i_m)) * __ldg(g.x1d + (size_t)b * n_i + i_m);
+  double f_j = (x2 - __ldg(x2v + j_m)) * __ldg(g.x2d + (size_t)b * n_j + j_m);
   double f_k = (x3 - __ldg(x3v + k_m)) * __ldg(g.x3d + (size_t)b * n_k + k_m);
   si.k = k_m; si.j = j_m; si.i = i_m;
   si.fk = f_k; si.fj = f_j; si.fi = f_i;
@@ -507,14 +560,8 @@ __device__ __forceinline__ SampleStatus sample_grid(const RadParams &P, const Gr
     for (int q = 0; q < 9; q++) v[q] = 0.0;
 #pragma unroll
     for (int p = 0; p < 8; p++) {
-      float f[8], kv = 0.0f;
-      size_t cell = c0 + off[p];
-      if (fmks && cell > last_cell) {
-        load_cell_past_end(g, slot, cell - last_cell - 1, f, kv);
-      } else {
-        load_cell(g, slot + cell, f);
-        if (g.kappa) kv = __ldg(g.kappa + slot + cell);
-      }
+      float f[8];
+      load_cell(g, slot + c0 + off[p], f);
       if (p == 0) {
 #pragma unroll
         for (int q = 0; q < 8; q++) corner[q] = f[q];
@@ -522,6 +569,7 @@ __device__ __forceinline__ SampleStatus sample_grid(const RadParams &P, const Gr
 #pragma unroll
       for (int q = 0; q < 8; q++) v[q] += w[p] * (double)f[q];
       if (g.kappa) {
+        float kv = __ldg(g.kappa + slot + c0 + off[p]);
         if (p == 0) corner_kappa = kv;
         v[8] += w[p] * (double)kv;
       }
