@@ -394,6 +394,51 @@ def test_live_reference_polarized(over, gpu, tmp_path):
     ctx.close()
 
 
+@pytest.mark.parametrize('base,over', [
+    ('true_color.input', {'camera_resolution': 16}),
+    ('render.input', {'camera_resolution': 24}),
+])
+def test_time_series_true_color_and_render_against_reference(base, over, gpu, tmp_path):
+    """BASELINE config 5: true-colour (10 unpolarized frequencies) and render (flat space, no light image) modes over
+    a time series of mock snapshots -- simulation_multiple with a {05d} field in simulation_file and output_file
+    (simulation_reader.cpp:870-904, output_writer.cpp:283-316), one geodesic pass reused by every frame -- through
+    the drop-in executable against the reference binary, every array of every frame."""
+    if not os.path.exists(REF_BIN):
+        pytest.skip('oracle/_ref/blacklight not present')
+    import subprocess
+    from blacklight_b200 import mock_snapshot as ms
+    from harness import write_input
+    d = str(tmp_path)
+    case = Case(d, base, over)
+    for n in range(3):
+        grid = ms.to_blocks(ms.mock_fields(n_r=32, n_th=16, n_ph=32, pert_amp=0.1 + 0.2 * n, pert_n_ph=3 + n), (1, 1, 2))
+        ms.write_athdf(os.path.join(d, 'data', 'mock.%05d.athdf' % (n + 4)), grid, time=10.0 * n)
+    frames = {}
+    for who in ('ref', 'gpu'):
+        out = os.path.join(d, 'out_' + who)
+        os.makedirs(out)
+        kv = dict(case.kv)
+        kv.update({'simulation_file': os.path.join(d, 'data', 'mock.{05d}.athdf'), 'simulation_multiple': 'true',
+                   'simulation_start': '4', 'simulation_end': '6', 'output_file': os.path.join(out, 'frame.{05d}.npz')})
+        path = os.path.join(d, who + '.input')
+        write_input(path, kv)
+        if who == 'ref':
+            proc = subprocess.run([REF_BIN, path], cwd=d, capture_output=True, text=True, timeout=3600)
+            assert proc.returncode == 0 and 'Calculation completed' in proc.stdout, proc.stdout + proc.stderr
+        else:
+            bl.run_input_file(path)
+        frames[who] = [dict(np.load(os.path.join(out, 'frame.%05d.npz' % k))) for k in (4, 5, 6)]
+    key = 'rendering' if base == 'render.input' else 'I_nu'
+    for ref, mine in zip(frames['ref'], frames['gpu']):
+        assert sorted(ref) == sorted(mine)
+        for name in ref:
+            if ref[name].dtype.kind == 'f' and ref[name].size > 16:
+                assert mine[name].shape == ref[name].shape
+                assert rel_err(mine[name], ref[name]) <= PIXEL_TOL, name
+        assert float(np.nanmax(np.abs(ref[key]))) > 0.0
+    assert rel_err(frames['gpu'][2][key], frames['gpu'][0][key]) > 1e-3      # the series evolves
+
+
 def test_golden_render(gpu, tmp_path):
     base, over, mock = CASES['render_32']
     gold = dict(np.load(os.path.join(GOLDEN, 'render_32.npz')))
