@@ -334,6 +334,7 @@ void camera_refined(const CameraSetup &s, const CameraFrame &f, int level, int b
   pos.resize(refined * 4 * bpix * 4);
   dir.resize(refined * 4 * bpix * 4);
   factor.resize(refined * 4 * bpix);
+  // child list: parents in index order x 4 children (camera.cpp:445-459); then every pixel is independent
   size_t block = 0;
   for (size_t parent = 0; parent < flags.size(); parent++) {
     if (!flags[parent]) continue;
@@ -342,15 +343,19 @@ void camera_refined(const CameraSetup &s, const CameraFrame &f, int level, int b
       for (int bu = 2 * pu; bu <= 2 * pu + 1; bu++, block++) {
         child_locs[2 * block] = bv;
         child_locs[2 * block + 1] = bu;
-        int row_off = bv * block_size, col_off = bu * block_size;
-        for (size_t m = 0; m < bpix; m++) {
-          int row = (int)(m / block_size), col = (int)(m % block_size);
-          double u_ind = (col + col_off - eff_res / 2.0 + 0.5) / eff_res;
-          double v_ind = (row + row_off - eff_res / 2.0 + 0.5) / eff_res;
-          size_t o = block * bpix + m;
-          camera_pixel(s, f, u_ind, v_ind, &pos[4 * o], &dir[4 * o], &factor[o]);
-        }
       }
+  }
+  const long long blocks = (long long)block;
+#pragma omp parallel for schedule(static)
+  for (long long b = 0; b < blocks; b++) {
+    int row_off = child_locs[2 * (size_t)b] * block_size, col_off = child_locs[2 * (size_t)b + 1] * block_size;
+    for (size_t m = 0; m < bpix; m++) {
+      int row = (int)(m / block_size), col = (int)(m % block_size);
+      double u_ind = (col + col_off - eff_res / 2.0 + 0.5) / eff_res;
+      double v_ind = (row + row_off - eff_res / 2.0 + 0.5) / eff_res;
+      size_t o = (size_t)b * bpix + m;
+      camera_pixel(s, f, u_ind, v_ind, &pos[4 * o], &dir[4 * o], &factor[o]);
+    }
   }
 }
 

@@ -1,5 +1,7 @@
 #include "config.hpp"
 
+#include <omp.h>
+
 #include <cmath>
 #include <cstring>
 
@@ -38,6 +40,10 @@ RunConfig make_config(const InputFile &in) {
   p.model_type = in.choice("model_type", {"simulation", "formula"}, "ModelType");
   const bool sim = p.model_type == BL_MODEL_SIMULATION;
   c.num_runs = in.num_runs();
+  // host-side parallel loops (camera pixels, reader conversions) use the input file's thread count, as the
+  // reference's main does (blacklight.cpp:77)
+  c.num_threads = in.integer("num_threads");
+  if (c.num_threads > 0) omp_set_num_threads(c.num_threads);
 
   // output
   c.output_format = in.choice("output_format", {"npz", "npy", "raw"}, "OutputFormat");

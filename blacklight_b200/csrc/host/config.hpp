@@ -31,6 +31,7 @@ struct RunConfig {
   double slow_t_start = 0.0, slow_dt = 0.0;
   int slow_offset = 0;
   int num_runs = 1;
+  int num_threads = 0;
 };
 
 RunConfig make_config(const InputFile &in);

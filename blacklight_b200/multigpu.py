@@ -11,9 +11,15 @@ The algorithm is written once as a generator that yields its collectives; it is 
 torch.distributed (one process per GPU) or, for tests and single-GPU checks, by an in-process scheduler that
 steps several virtual ranks in lock step.  Results are bitwise independent of the number of ranks.
 """
+import time
+
 import numpy as np
 
 from .sharding import shard_blocks
+
+# host wall-clock seconds per stage of the last adaptive_worker run on this process (diagnostics for
+# tools/bench_adaptive.py; trace / radiate / refine are synchronous calls, so they include the kernels)
+last_stage_seconds = {}
 
 
 def _root_blocks(cfg):
@@ -30,51 +36,78 @@ def _root_blocks(cfg):
 
 def adaptive_worker(cfg, ctx, rank, world, max_level, num_render=0):
     """Generator.  Yields ('allgather', uint8 array) -> list of per-rank arrays, and finally
-    ('gather', payload) -> list on rank 0 / None elsewhere; returns (via StopIteration.value) on rank 0 a list
+    ('gather_arrays', arrays, shapes of every rank's arrays) -> per-rank lists of arrays on rank 0 / None elsewhere; returns (via StopIteration.value) on rank 0 a list
     over levels of dict(locs=(B,2) int32, flags=(B,) uint8 or None, image=(Q, B*bs*bs) f64 in the reference's
     pixel order for that level [level 0: raster], stats=...), None on other ranks."""
     bs2 = cfg.block_size ** 2
+    T = {k: 0.0 for k in ('camera', 'select', 'trace', 'radiate', 'refine', 'exchange', 'assemble')}
+    last_stage_seconds.clear()
+    last_stage_seconds.update(T)
+    clock = time.perf_counter
+    t0 = clock()
     locs_all, pix = _root_blocks(cfg)
     pos_r, dir_r, fac_r = cfg.camera_root()
+    T['camera'] += clock() - t0
     mine_levels = []
     level = 0
     pos = dirs = fac = None
     while True:
+        t0 = clock()
         blocks = shard_blocks(len(locs_all), rank, world)
         if level == 0:
             sel = pix[blocks].ravel()
             pos, dirs, fac = pos_r[sel], dir_r[sel], fac_r[sel]
-        else:
-            sel = (blocks[:, None] * bs2 + np.arange(bs2)[None, :]).ravel()
-            pos, dirs, fac = pos[sel], dirs[sel], fac[sel]
+        elif world > 1:   # whole blocks: rows of the (blocks, bs2, ...) view
+            pos = pos.reshape(-1, bs2, 4)[blocks].reshape(-1, 4)
+            dirs = dirs.reshape(-1, bs2, 4)[blocks].reshape(-1, 4)
+            fac = fac.reshape(-1, bs2)[blocks].ravel()
+        t1 = clock()
         stats = ctx.trace_level(level, pos, dirs, fac)
+        t2 = clock()
         image, render, rstats = ctx.radiate_level(level, num_render=num_render)
+        t3 = clock()
+        T['select'] += t1 - t0
+        T['trace'] += t2 - t1
+        T['radiate'] += t3 - t2
         flags_all = None
         if level < max_level:
             flags_mine, _ = ctx.refine_level(level, locs_all[blocks]) if len(blocks) else (np.zeros(0, np.uint8), 0)
+            t4 = clock()
             parts = yield ('allgather', flags_mine)
+            t5 = clock()
             flags_all = np.zeros(len(locs_all), np.uint8)
             for r, part in enumerate(parts):
                 flags_all[shard_blocks(len(locs_all), r, world)] = part
+            T['refine'] += t4 - t3
+            T['exchange'] += t5 - t4
         mine_levels.append(dict(blocks=blocks, image=image, render=render, locs=locs_all, flags=flags_all,
                                 samples=rstats['num_samples'], bad=stats['num_bad_geodesics']))
         if flags_all is None or not flags_all.any():
             break
         level += 1
         # every rank derives the same child list and camera arrays; it then keeps its own share
+        t0 = clock()
         locs_all, pos, dirs, fac = cfg.camera_refined(level, locs_all, flags_all)
-    gathered = yield ('gather', [dict(blocks=L['blocks'], image=L['image'], render=L['render']) for L in mine_levels])
+        T['camera'] += clock() - t0
+    t0 = clock()
+    # final exchange: every rank's image blocks of every level to rank 0, as flat float64 arrays whose shapes all
+    # ranks can derive (levels x Q x this rank's blocks x bs2) -- no pickling, NCCL point-to-point when distributed
+    Q = mine_levels[0]['image'].shape[0]
+    shapes = [[(Q, len(shard_blocks(len(L['locs']), r, world)) * bs2) for L in mine_levels] for r in range(world)]
+    gathered = yield ('gather_arrays', [np.ascontiguousarray(L['image'], np.float64) for L in mine_levels], shapes)
+    T['exchange'] += clock() - t0
+    last_stage_seconds.update(T)
     if gathered is None:
         return None
+    t0 = clock()
     out = []
     res = cfg.resolution
     for lv, L in enumerate(mine_levels):
         n_blocks = len(L['locs'])
-        Q = L['image'].shape[0]
         full = np.empty((Q, n_blocks, bs2))
-        for part in gathered:
-            P = part[lv]
-            full[:, P['blocks']] = P['image'].reshape(Q, len(P['blocks']), bs2)
+        for r, part in enumerate(gathered):
+            blocks_r = shard_blocks(n_blocks, r, world)
+            full[:, blocks_r] = part[lv].reshape(Q, len(blocks_r), bs2)
         if lv == 0:   # back to the reference's raster order for the root level
             raster = np.empty((Q, res * res))
             raster[:, pix.ravel()] = full.reshape(Q, -1)
@@ -82,6 +115,8 @@ def adaptive_worker(cfg, ctx, rank, world, max_level, num_render=0):
         else:
             image = full.reshape(Q, -1)
         out.append(dict(locs=L['locs'], flags=L['flags'], image=image))
+    T['assemble'] += clock() - t0
+    last_stage_seconds.update(T)
     return out
 
 
@@ -109,14 +144,38 @@ def run_local(workers):
 
 def run_distributed(worker, rank, world):
     """Drive one rank's generator with torch.distributed object collectives (NCCL or gloo group)."""
+    import torch
     import torch.distributed as dist
     request = worker.send(None)
     while True:
-        kind, payload = request
+        kind, payload = request[0], request[1]
         if kind == 'allgather':
             parts = [None] * world
             dist.all_gather_object(parts, payload)
             reply = parts
+        elif kind == 'gather_arrays':
+            # one flat float64 message per rank; device tensors with the nccl backend (NVLink), host tensors with gloo
+            shapes = request[2]
+            dev = torch.device('cuda', torch.cuda.current_device()) if dist.get_backend() == 'nccl' else torch.device('cpu')
+            count = lambda r: sum(int(np.prod(sh)) for sh in shapes[r])
+            if rank == 0:
+                bufs = {r: torch.empty(count(r), dtype=torch.float64, device=dev) for r in range(1, world)}
+                reqs = [dist.irecv(bufs[r], src=r) for r in range(1, world) if count(r)]
+                for q in reqs:
+                    q.wait()
+                reply = [payload]
+                for r in range(1, world):
+                    flat, arrays, at = bufs[r].cpu().numpy(), [], 0
+                    for sh in shapes[r]:
+                        n = int(np.prod(sh))
+                        arrays.append(flat[at:at + n].reshape(sh))
+                        at += n
+                    reply.append(arrays)
+            else:
+                if count(rank):
+                    flat = np.concatenate([np.asarray(a, np.float64).ravel() for a in payload])
+                    dist.send(torch.from_numpy(flat).to(dev), dst=0)
+                reply = None
         else:
             parts = [None] * world if rank == 0 else None
             dist.gather_object(payload, parts, dst=0)

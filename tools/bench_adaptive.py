@@ -48,7 +48,7 @@ def main():
         w = '%g' % args.region
         over.update({'adaptive_num_regions': 1, 'adaptive_region_1_level': args.levels, 'adaptive_region_1_x_min': '-' + w,
                      'adaptive_region_1_x_max': w, 'adaptive_region_1_y_min': '-' + w, 'adaptive_region_1_y_max': w})
-    case = Case(workdir, 'adaptive.input', over)
+    case = Case(workdir, 'adaptive.input', over, threads=max(1, (os.cpu_count() or 1) // world))
     cfg = case.config(device=local_rank)
     cfg.set_level0_block_major(True)
     ctx = bl.Context(cfg)
@@ -81,6 +81,7 @@ def main():
         print(json.dumps({'workload': 'example_adaptive parameters, root %d^2, block %d, up to %d levels, central window |x|,|y| < %g forced to the deepest level' % (args.root, args.block, args.levels, args.region),
                           'n_gpus': world, 'steps': args.steps, 'ms_per_step': 1e3 * dt, 'rays_per_s': sum(rays) / dt,
                           'blocks_per_level': blocks, 'rays_per_level': rays, 'mean_I_root': flux,
+                          'rank0_stage_ms_last_step': {k: round(1e3 * v, 2) for k, v in multigpu.last_stage_seconds.items()},
                           'timing': 'host wall clock between barriers, includes host camera generation for refined levels, '
                                     'flag all-gather and final image gather'}))
     ctx.close()
