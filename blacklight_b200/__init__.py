@@ -80,6 +80,7 @@ def load_library():
         'blh_camera_root': (i64, [vp, vp, vp, vp]),
         'blh_camera_refined': (i64, [vp, i32, vp, vp, i64, vp, vp, vp, vp]),
         'blh_run_input_file': (i32, [ctypes.c_char_p, i32, i32, vp]),
+        'blh_camera_blocks': (i64, [vp, i32, vp, i64, vp, vp, vp]),
         'blh_snapshot_read': (i32, [vp, ctypes.c_char_p, ctypes.POINTER(vp)]),
         'blh_snapshot_view': (i32, [vp, ctypes.POINTER(GridView), ctypes.POINTER(dbl), ctypes.POINTER(dbl)]),
         'blh_snapshot_free': (None, [vp]),
@@ -163,6 +164,16 @@ class Config:
         if got != nb:
             raise BlacklightError(_lib.blh_last_error().decode())
         return locs, pos, dirs, fac
+
+
+    def camera_blocks(self, level, locs):
+        """Camera arrays of the given blocks of a level only ((n,2) block locations): blh_camera_blocks."""
+        locs = np.ascontiguousarray(locs, np.int32).reshape(-1, 2)
+        npix = len(locs) * self.block_size ** 2
+        pos, dirs, fac = np.empty((npix, 4)), np.empty((npix, 4)), np.empty(npix)
+        if _lib.blh_camera_blocks(self._h, level, _ptr(locs), len(locs), _ptr(pos), _ptr(dirs), _ptr(fac)) != len(locs):
+            raise BlacklightError(_lib.blh_last_error().decode())
+        return pos, dirs, fac
 
 
 def _host_array(shape, pinned=False, dtype=np.float64):

@@ -321,6 +321,24 @@ void camera_root(const CameraSetup &s, const CameraFrame &f, std::vector<double>
   }
 }
 
+void camera_blocks(const CameraSetup &s, const CameraFrame &f, int level, int block_size, const int32_t *locs, long long blocks,
+                   double *pos, double *dir, double *factor) {
+  int eff_res = s.resolution;
+  for (int n = 1; n <= level; n++) eff_res *= 2;
+  const size_t bpix = (size_t)block_size * block_size;
+#pragma omp parallel for schedule(static)
+  for (long long b = 0; b < blocks; b++) {
+    int row_off = locs[2 * (size_t)b] * block_size, col_off = locs[2 * (size_t)b + 1] * block_size;
+    for (size_t m = 0; m < bpix; m++) {
+      int row = (int)(m / block_size), col = (int)(m % block_size);
+      double u_ind = (col + col_off - eff_res / 2.0 + 0.5) / eff_res;
+      double v_ind = (row + row_off - eff_res / 2.0 + 0.5) / eff_res;
+      size_t o = (size_t)b * bpix + m;
+      camera_pixel(s, f, u_ind, v_ind, &pos[4 * o], &dir[4 * o], &factor[o]);
+    }
+  }
+}
+
 void camera_refined(const CameraSetup &s, const CameraFrame &f, int level, int block_size,
                     const std::vector<int32_t> &parent_locs, const std::vector<uint8_t> &flags,
                     std::vector<int32_t> &child_locs, std::vector<double> &pos, std::vector<double> &dir,
@@ -345,18 +363,7 @@ void camera_refined(const CameraSetup &s, const CameraFrame &f, int level, int b
         child_locs[2 * block + 1] = bu;
       }
   }
-  const long long blocks = (long long)block;
-#pragma omp parallel for schedule(static)
-  for (long long b = 0; b < blocks; b++) {
-    int row_off = child_locs[2 * (size_t)b] * block_size, col_off = child_locs[2 * (size_t)b + 1] * block_size;
-    for (size_t m = 0; m < bpix; m++) {
-      int row = (int)(m / block_size), col = (int)(m % block_size);
-      double u_ind = (col + col_off - eff_res / 2.0 + 0.5) / eff_res;
-      double v_ind = (row + row_off - eff_res / 2.0 + 0.5) / eff_res;
-      size_t o = (size_t)b * bpix + m;
-      camera_pixel(s, f, u_ind, v_ind, &pos[4 * o], &dir[4 * o], &factor[o]);
-    }
-  }
+  camera_blocks(s, f, level, block_size, child_locs.data(), (long long)block, pos.data(), dir.data(), factor.data());
 }
 
 }  // namespace blh

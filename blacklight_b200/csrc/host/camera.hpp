@@ -45,6 +45,12 @@ void camera_refined(const CameraSetup &s, const CameraFrame &f, int level, int b
                     std::vector<int32_t> &child_locs, std::vector<double> &pos, std::vector<double> &dir,
                     std::vector<double> &factor);
 
+// Pixels of the given blocks of a level (locs: (blocks,2) (v,u) at effective resolution res * 2^level), block-major:
+// pos, dir (blocks * bs^2, 4), factor (blocks * bs^2).  The same per-pixel expressions as camera_refined; what a rank
+// that owns only some blocks of a level calls.
+void camera_blocks(const CameraSetup &s, const CameraFrame &f, int level, int block_size, const int32_t *locs, long long blocks,
+                   double *pos, double *dir, double *factor);
+
 // Image frequencies (camera.cpp:30-50). spacing: 0 lin_freq, 1 lin_wave, 2 log
 std::vector<double> image_frequencies(int num, double single, double start, double end, int spacing);
 

@@ -92,6 +92,13 @@ int64_t blh_camera_refined(const blh_config *c, int level, const int32_t *parent
   return (int64_t)cl.size() / 2;
 }
 
+int64_t blh_camera_blocks(const blh_config *c, int level, const int32_t *locs, int64_t num_blocks, double *pos, double *dir,
+                          double *factor) {
+  if (!c || !locs || !pos || !dir || !factor || num_blocks < 0 || level < 0) { g_error = "bad argument"; return -1; }
+  blh::camera_blocks(c->cfg.camera, c->cfg.frame, level, c->cfg.params.adaptive_block_size, locs, num_blocks, pos, dir, factor);
+  return num_blocks;
+}
+
 int blh_snapshot_read(const blh_config *c, const char *file, blh_snapshot **out) {
   if (!c || !out) { g_error = "null argument"; return 1; }
   *out = nullptr;

@@ -57,16 +57,14 @@ def adaptive_worker(cfg, ctx, rank, world, max_level, num_render=0):
         if level == 0:
             sel = pix[blocks].ravel()
             pos, dirs, fac = pos_r[sel], dir_r[sel], fac_r[sel]
-        elif world > 1:   # whole blocks: rows of the (blocks, bs2, ...) view
-            pos = pos.reshape(-1, bs2, 4)[blocks].reshape(-1, 4)
-            dirs = dirs.reshape(-1, bs2, 4)[blocks].reshape(-1, 4)
-            fac = fac.reshape(-1, bs2)[blocks].ravel()
+        else:             # refined level: camera pixels of this rank's blocks only
+            pos, dirs, fac = cfg.camera_blocks(level, locs_all[blocks])
         t1 = clock()
+        T['camera' if level else 'select'] += t1 - t0
         stats = ctx.trace_level(level, pos, dirs, fac)
         t2 = clock()
         image, render, rstats = ctx.radiate_level(level, num_render=num_render)
         t3 = clock()
-        T['select'] += t1 - t0
         T['trace'] += t2 - t1
         T['radiate'] += t3 - t2
         flags_all = None
@@ -85,9 +83,13 @@ def adaptive_worker(cfg, ctx, rank, world, max_level, num_render=0):
         if flags_all is None or not flags_all.any():
             break
         level += 1
-        # every rank derives the same child list and camera arrays; it then keeps its own share
+        # every rank derives the same child list (parents in index order x 4 children (2v..2v+1) x (2u..2u+1),
+        # camera.cpp:445-459) and then builds the camera arrays of its own share
         t0 = clock()
-        locs_all, pos, dirs, fac = cfg.camera_refined(level, locs_all, flags_all)
+        parents = locs_all[flags_all != 0]
+        dv, du = np.array([0, 0, 1, 1], np.int32), np.array([0, 1, 0, 1], np.int32)
+        locs_all = np.stack([2 * parents[:, None, 0] + dv[None, :], 2 * parents[:, None, 1] + du[None, :]], axis=2)
+        locs_all = np.ascontiguousarray(locs_all.reshape(-1, 2), np.int32)
         T['camera'] += clock() - t0
     t0 = clock()
     # final exchange: every rank's image blocks of every level to rank 0, as flat float64 arrays whose shapes all
@@ -105,9 +107,8 @@ def adaptive_worker(cfg, ctx, rank, world, max_level, num_render=0):
     for lv, L in enumerate(mine_levels):
         n_blocks = len(L['locs'])
         full = np.empty((Q, n_blocks, bs2))
-        for r, part in enumerate(gathered):
-            blocks_r = shard_blocks(n_blocks, r, world)
-            full[:, blocks_r] = part[lv].reshape(Q, len(blocks_r), bs2)
+        for r, part in enumerate(gathered):   # shard_blocks deals blocks round-robin: rank r owns blocks r, r + world, ...
+            full[:, r::world] = part[lv].reshape(Q, -1, bs2)
         if lv == 0:   # back to the reference's raster order for the root level
             raster = np.empty((Q, res * res))
             raster[:, pix.ravel()] = full.reshape(Q, -1)
@@ -159,16 +160,18 @@ def run_distributed(worker, rank, world):
             dev = torch.device('cuda', torch.cuda.current_device()) if dist.get_backend() == 'nccl' else torch.device('cpu')
             count = lambda r: sum(int(np.prod(sh)) for sh in shapes[r])
             if rank == 0:
-                bufs = {r: torch.empty(count(r), dtype=torch.float64, device=dev) for r in range(1, world)}
-                reqs = [dist.irecv(bufs[r], src=r) for r in range(1, world) if count(r)]
+                starts = np.concatenate([[0], np.cumsum([count(r) for r in range(1, world)])]).astype(np.int64)
+                buf = torch.empty(int(starts[-1]), dtype=torch.float64, device=dev)
+                reqs = [dist.irecv(buf[int(starts[r - 1]):int(starts[r])], src=r) for r in range(1, world) if count(r)]
                 for q in reqs:
                     q.wait()
+                flat_all = buf.cpu().numpy()          # one device-to-host copy for all ranks
                 reply = [payload]
                 for r in range(1, world):
-                    flat, arrays, at = bufs[r].cpu().numpy(), [], 0
+                    arrays, at = [], int(starts[r - 1])
                     for sh in shapes[r]:
                         n = int(np.prod(sh))
-                        arrays.append(flat[at:at + n].reshape(sh))
+                        arrays.append(flat_all[at:at + n].reshape(sh))
                         at += n
                     reply.append(arrays)
             else:

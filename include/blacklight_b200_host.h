@@ -34,6 +34,10 @@ int64_t blh_camera_root(const blh_config *cfg, double *pos, double *dir, double 
  * adaptive_block_size^2 pixels (any may be NULL to query the count).  Returns the number of child blocks. */
 int64_t blh_camera_refined(const blh_config *cfg, int level, const int32_t *parent_locs, const uint8_t *flags,
                            int64_t num_parents, int32_t *child_locs, double *pos, double *dir, double *factor);
+/* Pixels of the listed blocks of `level` only (locs: (num_blocks,2) block (v,u) at that level), block-major -- for a rank
+ * that owns a share of a level's blocks (AugmentCamera's per-pixel expressions, camera.cpp:461-503). */
+int64_t blh_camera_blocks(const blh_config *cfg, int level, const int32_t *locs, int64_t num_blocks, double *pos, double *dir,
+                          double *factor);
 /* timings: total, geodesic, read, sample, image, render [s]; gpu geodesic, radiation, refine [ms];
  * rays, samples, reserved */
 /* Snapshot readers -- the upload side of SimulationReader::Read (simulation_reader.cpp:200-861): simulation_format

@@ -87,6 +87,14 @@ def test_camera_refined_blocks(tmp_path):
             m_blk = blk * bs * bs + row * bs + col
             assert np.array_equal(pos[m_blk], pos64[m_fine]) and np.array_equal(dirs[m_blk], dir64[m_fine])
             assert fac[m_blk] == fac64[m_fine]
+    # a rank that owns only some of the level's blocks builds exactly their pixels (blh_camera_blocks)
+    mine = [6, 1, 3]
+    bpix = bs * bs
+    p2, d2, f2 = cfg.camera_blocks(1, locs[mine])
+    for n, b in enumerate(mine):
+        assert np.array_equal(p2[n * bpix:(n + 1) * bpix], pos[b * bpix:(b + 1) * bpix])
+        assert np.array_equal(d2[n * bpix:(n + 1) * bpix], dirs[b * bpix:(b + 1) * bpix])
+        assert np.array_equal(f2[n * bpix:(n + 1) * bpix], fac[b * bpix:(b + 1) * bpix])
 
 
 def test_input_surface_errors(tmp_path):
@@ -346,15 +354,10 @@ class _FakeConfig:
         m = np.arange(64, dtype=np.float64)
         return np.stack([m, m, m, m], 1), np.stack([-m, m, m, m], 1), m.copy()
 
-    def camera_refined(self, level, parent_locs, flags):
-        kids = []
-        for (v, u), f in zip(parent_locs, flags):
-            if f:
-                kids += [(2 * v, 2 * u), (2 * v, 2 * u + 1), (2 * v + 1, 2 * u), (2 * v + 1, 2 * u + 1)]
-        locs = np.array(kids, np.int32).reshape(-1, 2)
-        n = len(locs) * 4
+    def camera_blocks(self, level, locs):
+        locs = np.asarray(locs, np.int32).reshape(-1, 2)
         tag = 1000.0 * level + (locs[:, 0].repeat(4) * 64 + locs[:, 1].repeat(4)) * 4.0 + np.tile(np.arange(4.0), len(locs))
-        return locs, np.stack([tag] * 4, 1), np.stack([-tag] * 4, 1), tag.copy()
+        return np.stack([tag] * 4, 1), np.stack([-tag] * 4, 1), tag.copy()
 
 
 class _FakeContext:
