@@ -230,6 +230,14 @@ struct PolSample {
   double lvd_j, lvf_j, lvd_a, lvf_a;   // ln of the pitch-angle factors of j_V and alpha_V (kappa)
 };
 
+// DIST: electron distributions compiled into an instantiation -- bit 0 thermal, bit 1 power law, bit 2 kappa; 7 = all,
+// chosen at run time from the fractions.  The single-distribution instantiations (thermal only, kappa only) drop
+// the other distributions' code and, above all, their live registers from the frequency loop.
+template <int DIST> __device__ __forceinline__ bool has_thermal(const RadParams &P) { return DIST == 7 ? P.thermal_frac != 0.0 : (DIST & 1) != 0; }
+template <int DIST> __device__ __forceinline__ bool has_power(const RadParams &P) { return DIST == 7 ? P.power_frac != 0.0 : (DIST & 2) != 0; }
+template <int DIST> __device__ __forceinline__ bool has_kappa(const RadParams &P) { return DIST == 7 ? P.kappa_frac != 0.0 : (DIST & 4) != 0; }
+
+template <int DIST>
 __device__ __forceinline__ void pol_sample(const RadParams &P, const rad::Plasma &s, double om, double sin_b,
                                            double cos_b, const double kk[3], PolSample &q) {
   q.om = om;
@@ -244,7 +252,7 @@ __device__ __forceinline__ void pol_sample(const RadParams &P, const rad::Plasma
   q.theta_e = s.theta_e;
   q.inv_nu_s = q.log_inv_nu_s = q.h_kt = q.var_d = q.cos_over_theta = 0.0;
   q.k1_k2 = q.k0 = q.inv_k2 = 0.0;
-  if (P.thermal_frac != 0.0) {
+  if (has_thermal<DIST>(P)) {
     q.inv_nu_s = 4.5 * s.inv_theta_e * s.inv_theta_e / (q.nu_c * sin_b);
     q.h_kt = phys::h * s.inv_theta_e * (1.0 / (phys::m_e * phys::c * phys::c));
     double te96 = bfm::exp_bf(0.96 * bfm::log_bf(s.theta_e));
@@ -260,15 +268,15 @@ __device__ __forceinline__ void pol_sample(const RadParams &P, const rad::Plasma
   q.log_om = bfm::log_bf(om);
   q.log_ncs = q.log_ne = q.cot = q.power_vb = q.inv_nu_k = 0.0;
   q.lvd_j = q.lvf_j = q.lvd_a = q.lvf_a = 0.0;
-  if (P.power_frac != 0.0 || P.kappa_frac != 0.0) {
+  if (has_power<DIST>(P) || has_kappa<DIST>(P)) {
     q.log_ncs = log(q.nu_c * sin_b);
     q.log_ne = bfm::log_bf(s.n_e_cgs);
     double log_sin = log(sin_b);
-    if (P.power_frac != 0.0) {
+    if (has_power<DIST>(P)) {
       q.cot = cos_b / sin_b;
       q.power_vb = pow(3.1 * exp(-1.92 * log_sin) - 3.1, 0.512);
     }
-    if (P.kappa_frac != 0.0) {
+    if (has_kappa<DIST>(P)) {
       q.inv_nu_k = 1.0 / (q.nu_c * P.plasma_w * P.plasma_w * P.plasma_kappa * P.plasma_kappa * sin_b);
       q.lvd_j = 0.48 * log(exp(-2.4 * log_sin) - 1.0);
       q.lvf_j = 0.44 * log(exp(-2.5 * log_sin) - 1.0);
@@ -279,6 +287,7 @@ __device__ __forceinline__ void pol_sample(const RadParams &P, const rad::Plasma
 }
 
 // Polarized synchrotron coefficients at image frequency l (simulation_coefficients.cpp:458-698).
+template <int DIST>
 __device__ __forceinline__ void synchrotron_polarized(const RadParams &P, const PolSample &q, int l, Coefficients &C) {
   const double e2 = phys::e * phys::e;
   double nu_cgs = q.om * P.freqs[l];
@@ -286,7 +295,7 @@ __device__ __forceinline__ void synchrotron_polarized(const RadParams &P, const 
   double inv_nu_2 = inv_nu * inv_nu;
   for (int i = 0; i < 3; i++) C.j[i] = C.a[i] = 0.0;
   C.rho[0] = C.rho[1] = 0.0;
-  if (P.thermal_frac != 0.0) {
+  if (has_thermal<DIST>(P)) {
     double xx = nu_cgs * q.inv_nu_s;
     double xx_neg_1_2 = rsqrt(xx);
     double xx_1_2 = xx * xx_neg_1_2, xx_1_3 = cbrt(xx);
@@ -327,10 +336,10 @@ __device__ __forceinline__ void synchrotron_polarized(const RadParams &P, const 
     C.rho[0] = coefficient_q * factor_q;
     C.rho[1] = coefficient_v * factor_v;
   }
-  if (P.power_frac != 0.0 || P.kappa_frac != 0.0) {
+  if (has_power<DIST>(P) || has_kappa<DIST>(P)) {
     double log_nu = q.log_om + P.log_freqs[l];
     double lr = log_nu - q.log_ncs;  // ln(nu / (nu_c sin(theta_B)))
-    if (P.power_frac != 0.0) {
+    if (has_power<DIST>(P)) {
       double e_half = bfm::exp_bf(-0.5 * lr);  // (nu / (nu_c sin))^-1/2
       double coefficient = P.power_frac * q.n_nuc * inv_nu_2 * P.power_jj * q.sin_b * bfm::exp_bf(-(P.plasma_p - 1.0) / 2.0 * lr);
       C.j[0] += coefficient;
@@ -348,7 +357,7 @@ __device__ __forceinline__ void synchrotron_polarized(const RadParams &P, const 
       C.rho[0] += coefficient_r * P.power_rho_q * rd * re;
       C.rho[1] += coefficient_r * P.power_rho_v * rc * q.cot;
     }
-    if (P.kappa_frac != 0.0) {
+    if (has_kappa<DIST>(P)) {
       double lx = lr - P.log_w2k2;   // ln(nu / nu_kappa)
       double xx = nu_cgs * q.inv_nu_k;
       double lm035 = -0.35 * lx, lm12 = -0.5 * lx;
@@ -561,7 +570,7 @@ __device__ __forceinline__ void couple(const RadParams &P, const Coefficients &C
 #ifndef BL_POL_MINB
 #define BL_POL_MINB 2  // resident CTAs per SM the kernel is register-capped for
 #endif
-template <int FMAX, bool BI>
+template <int FMAX, bool BI, int DIST>
 __global__ void __launch_bounds__(kBlock, BL_POL_MINB)
 radiate_polarized_kernel(const __grid_constant__ RadArgs A, const __grid_constant__ RadParams P) {
   extern __shared__ double smem_bounds[];
@@ -711,11 +720,11 @@ radiate_polarized_kernel(const __grid_constant__ RadArgs A, const __grid_constan
       c2 = 1.0 < c2 ? 1.0 : c2;
       double sin_theta_b = sqrt(1.0 - c2);
       double cos_theta_b = sqrt(c2) * (kb >= 0.0 ? 1.0 : -1.0);
-      if (P.thermal_frac != 0.0 && ps.theta_e >= 0.01) {
+      if (has_thermal<DIST>(P) && ps.theta_e >= 0.01) {
         bfm::bessel_k01(ps.inv_theta_e, kk[0], kk[1]);
         kk[2] = kk[0] + 2.0 * ps.theta_e * kk[1];
       }
-      pol_sample(P, ps, omega * mom, sin_theta_b, cos_theta_b, kk, sq);
+      pol_sample<DIST>(P, ps, omega * mom, sin_theta_b, cos_theta_b, kk, sq);
     }
 
     // ---- per-sample auxiliary quantities ----
@@ -754,7 +763,7 @@ BL_FREQ_LOOP
       Coefficients C;
       for (int q = 0; q < 3; q++) C.j[q] = C.a[q] = 0.0;
       C.rho[0] = C.rho[1] = 0.0;
-      if (coupled) synchrotron_polarized(P, sq, l, C);
+      if (coupled) synchrotron_polarized<DIST>(P, sq, l, C);
       double delta_tau = C.a[0] * dl_cgs;
       if (aux) {
         bool thin = delta_tau <= 100.0;
@@ -860,10 +869,16 @@ cudaError_t launch_fmax(const RadArgs &A, const RadParams &P, cudaStream_t strea
   unsigned grid = (unsigned)((A.rays + kBlock - 1) / kBlock);
   size_t smem = 0;
   if ((size_t)A.grid.n_b * 6 * sizeof(double) <= 48 * 1024) smem = (size_t)A.grid.n_b * 6 * sizeof(double);
+  const bool thermal_only = P.thermal_frac != 0.0 && P.power_frac == 0.0 && P.kappa_frac == 0.0;
+  const bool kappa_only = P.kappa_frac != 0.0 && P.power_frac == 0.0 && P.thermal_frac == 0.0;
   if (P.block_interp || P.slow_light || P.coord == 2)
-    radiate_polarized_kernel<FMAX, true><<<grid, kBlock, smem, stream>>>(A, P);
+    radiate_polarized_kernel<FMAX, true, 7><<<grid, kBlock, smem, stream>>>(A, P);
+  else if (thermal_only)
+    radiate_polarized_kernel<FMAX, false, 1><<<grid, kBlock, smem, stream>>>(A, P);
+  else if (kappa_only)
+    radiate_polarized_kernel<FMAX, false, 4><<<grid, kBlock, smem, stream>>>(A, P);
   else
-    radiate_polarized_kernel<FMAX, false><<<grid, kBlock, smem, stream>>>(A, P);
+    radiate_polarized_kernel<FMAX, false, 7><<<grid, kBlock, smem, stream>>>(A, P);
   return cudaGetLastError();
 }
 
