@@ -43,6 +43,14 @@ struct SynchSample {
   double nu_c, sin_theta_b, n_e;
 };
 
+// DIST: electron distributions compiled into an instantiation -- bit 0 thermal, bit 1 power law, bit 2 kappa; 7 = all,
+// chosen at run time from the fractions.  The thermal-only instantiation of the light-only kernel drops the other
+// distributions' code and live registers.
+template <int DIST> __device__ __forceinline__ bool has_thermal(const RadParams &P) { return DIST == 7 ? P.thermal_frac != 0.0 : (DIST & 1) != 0; }
+template <int DIST> __device__ __forceinline__ bool has_power(const RadParams &P) { return DIST == 7 ? P.power_frac != 0.0 : (DIST & 2) != 0; }
+template <int DIST> __device__ __forceinline__ bool has_kappa(const RadParams &P) { return DIST == 7 ? P.kappa_frac != 0.0 : (DIST & 4) != 0; }
+
+template <int DIST>
 __device__ __forceinline__ void synch_sample(const RadParams &P, const rad::Plasma &s, double om,
                                              double sin_theta_b, SynchSample &q) {
   q.om = om;
@@ -52,14 +60,14 @@ __device__ __forceinline__ void synch_sample(const RadParams &P, const rad::Plas
   q.n_e = s.n_e_cgs;
   q.n_nuc = s.n_e_cgs * q.nu_c * (phys::e * phys::e / phys::c);
   q.inv_nu_s = q.th_shape = q.h_kt = 0.0;
-  if (P.thermal_frac != 0.0) {
+  if (has_thermal<DIST>(P)) {
     // 1/nu_s = 9/2 / (nu_c theta_e^2 sin(theta_B)), with 1/theta_e already known
     q.inv_nu_s = 4.5 * s.inv_theta_e * s.inv_theta_e / (q.nu_c * sin_theta_b);
     q.th_shape = P.thermal_frac * (phys::sqrt2 * phys::pi / 27.0) * sin_theta_b * q.n_nuc;
     q.h_kt = phys::h * s.inv_theta_e * (1.0 / (phys::m_e * phys::c * phys::c));
   }
   q.log_om = q.log_ncs = q.log_ne = 0.0;
-  if (P.power_frac != 0.0 || P.kappa_frac != 0.0) {
+  if (has_power<DIST>(P) || has_kappa<DIST>(P)) {
     q.log_om = log(om);
     q.log_ncs = log(q.nu_c * sin_theta_b);
     q.log_ne = log(s.n_e_cgs);
@@ -67,13 +75,14 @@ __device__ __forceinline__ void synch_sample(const RadParams &P, const rad::Plas
 }
 
 // Coefficients at image frequency l.
+template <int DIST>
 __device__ __forceinline__ void synchrotron_unpolarized(const RadParams &P, const SynchSample &q, int l,
                                                         bool need_j, bool need_a, double &j_out, double &a_out) {
   double nu_cgs = q.om * P.freqs[l];
   double inv_nu = q.inv_om * P.inv_freqs[l];
   double inv_nu_2 = inv_nu * inv_nu;
   double j_val = 0.0, a_val = 0.0;
-  if (P.thermal_frac != 0.0) {
+  if (has_thermal<DIST>(P)) {
     double xx = nu_cgs * q.inv_nu_s;
     double xx_1_2 = sqrt(xx);
     double xx_1_3 = cbrt(xx);
@@ -90,17 +99,17 @@ __device__ __forceinline__ void synchrotron_unpolarized(const RadParams &P, cons
       if (a_val * a_val <= 0x1p-1024) a_val = 0.0;
     }
   }
-  if (P.power_frac != 0.0 || P.kappa_frac != 0.0) {
+  if (has_power<DIST>(P) || has_kappa<DIST>(P)) {
     double log_nu = q.log_om + P.log_freqs[l];
     double lr = log_nu - q.log_ncs;  // ln(nu / (nu_c sin(theta_B)))
-    if (P.power_frac != 0.0) {
+    if (has_power<DIST>(P)) {
       if (need_j)
         j_val += P.power_frac * q.n_nuc * inv_nu_2 * P.power_jj * q.sin_theta_b * bfm::exp_bf(-(P.plasma_p - 1.0) / 2.0 * lr);
       if (need_a)
         a_val += P.power_frac * q.n_e * (phys::e * phys::e / (phys::m_e * phys::c)) * P.power_aa *
                  bfm::exp_bf(-(P.plasma_p + 2.0) / 2.0 * lr);
     }
-    if (P.kappa_frac != 0.0) {
+    if (has_kappa<DIST>(P)) {
       double lx = lr - P.log_w2k2;  // ln(nu / nu_kappa)
       if (need_j) {
         // ln of kappa_frac n_e e^2 nu_c / (c nu^2) * sin(theta_B)
@@ -153,7 +162,7 @@ __device__ __forceinline__ void formula_fluid(const RadParams &P, double x, doub
 
 // LEAN: only the light image is requested (no auxiliary images, no rendering, no inter-block interpolation)
 // -- the common case gets a kernel without the dead register state of the rest.
-template <int FMAX, bool SIM, bool LEAN>
+template <int FMAX, bool SIM, bool LEAN, int DIST>
 __global__ void __launch_bounds__(kBlock, (FMAX <= 4 ? BL_RAD_MINB : 2))
 radiate_unpolarized_kernel(const __grid_constant__ RadArgs A, const __grid_constant__ RadParams P) {
   extern __shared__ double smem_bounds[];
@@ -284,7 +293,7 @@ radiate_unpolarized_kernel(const __grid_constant__ RadArgs A, const __grid_const
             // fluid-frame pitch angle: |k_spatial| = omega and |b| = sqrt(b^2) in the frame of u
             double c2 = kb * kb / (omega * omega * ps.b_sq);
             c2 = 1.0 < c2 ? 1.0 : c2;
-            synch_sample(P, ps, omega * mom, sqrt(1.0 - c2), sq);
+            synch_sample<DIST>(P, ps, omega * mom, sqrt(1.0 - c2), sq);
             coupled = true;
             nan_sample = st == rad::kSampleNan;
           }
@@ -333,7 +342,7 @@ BL_FREQ_LOOP
       double j = 0.0, alpha = 0.0;
       if (coupled) {
         if (SIM) {
-          synchrotron_unpolarized(P, sq, l, need_j, need_a, j, alpha);
+          synchrotron_unpolarized<DIST>(P, sq, l, need_j, need_a, j, alpha);
         } else if (P.fallback_nan && flagged) {
           if (l == 0) j = alpha = nan("");
         } else {
@@ -432,14 +441,17 @@ cudaError_t launch_fmax(const RadArgs &A, const RadParams &P, cudaStream_t strea
   unsigned grid = (unsigned)((A.rays + kBlock - 1) / kBlock);
   size_t smem = 0;
   if (sim && (size_t)A.grid.n_b * 6 * sizeof(double) <= 48 * 1024) smem = (size_t)A.grid.n_b * 6 * sizeof(double);
-  if (sim && lean)
-    radiate_unpolarized_kernel<FMAX, true, true><<<grid, kBlock, smem, stream>>>(A, P);
+  const bool thermal_only = P.thermal_frac != 0.0 && P.power_frac == 0.0 && P.kappa_frac == 0.0;
+  if (sim && lean && thermal_only)
+    radiate_unpolarized_kernel<FMAX, true, true, 1><<<grid, kBlock, smem, stream>>>(A, P);
+  else if (sim && lean)
+    radiate_unpolarized_kernel<FMAX, true, true, 7><<<grid, kBlock, smem, stream>>>(A, P);
   else if (sim)
-    radiate_unpolarized_kernel<FMAX, true, false><<<grid, kBlock, smem, stream>>>(A, P);
+    radiate_unpolarized_kernel<FMAX, true, false, 7><<<grid, kBlock, smem, stream>>>(A, P);
   else if (lean)
-    radiate_unpolarized_kernel<FMAX, false, true><<<grid, kBlock, 0, stream>>>(A, P);
+    radiate_unpolarized_kernel<FMAX, false, true, 7><<<grid, kBlock, 0, stream>>>(A, P);
   else
-    radiate_unpolarized_kernel<FMAX, false, false><<<grid, kBlock, 0, stream>>>(A, P);
+    radiate_unpolarized_kernel<FMAX, false, false, 7><<<grid, kBlock, 0, stream>>>(A, P);
   return cudaGetLastError();
 }
 
