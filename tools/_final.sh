@@ -1,0 +1,6 @@
+set -x
+timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -3
+timeout 400 python bench.py > gpurun_out/bench_final2.json 2> gpurun_out/bench_final2.err
+timeout 400 python bench.py --impl reference --steps 1 --warmup 1 > gpurun_out/bench_final2_ref.json 2> gpurun_out/bench_final2_ref.err
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r01m_launches_bench_1024.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
