@@ -207,6 +207,28 @@ void save_geodesic_checkpoint(bl_ctx *ctx, const RunConfig &cfg, const LevelData
   write_array(out, len.data(), n_len);
 }
 
+// Level-0 sampling checkpoint in the reference's byte format (sample_checkpoint.cpp:22-39): sample_inds (N,S,4) int32,
+// sample_fracs (N,S,3) when interpolating, sample_nan, sample_fallback (N,S) bytes -- what the fused kernel's parity
+// taps recorded during the first bl_radiate_level.  Entries the reference leaves unset (cut / off-grid samples,
+// n >= sample_num) hold -1 / 0 here and whatever its allocator returned there.
+void save_sample_checkpoint(bl_ctx *ctx, const RunConfig &cfg, const LevelData &root, int S) {
+  if (cfg.params.simulation_block_interp)
+    throw Error("checkpoint_sample_save with simulation_block_interp is outside the B200 hot-path scope.");
+  const bool interp = cfg.params.simulation_interp != 0;
+  size_t N = (size_t)root.rays, ns = N * (size_t)(S > 0 ? S : 1);
+  std::vector<int32_t> inds(ns * 4);
+  std::vector<double> fracs(interp ? ns * 3 : 0);
+  std::vector<uint8_t> nan_(ns), fallback(ns);
+  check(ctx, bl_download_sample_inds(ctx, 0, inds.data(), interp ? fracs.data() : nullptr, nan_.data(), nullptr, fallback.data()));
+  std::ofstream out(cfg.checkpoint_sample_file, std::ios::binary);
+  if (!out.is_open()) throw Error("Could not open sample checkpoint file.");
+  int n_inds[5] = {4, S, (int)N, 1, 1}, n_fracs[5] = {3, S, (int)N, 1, 1}, n_flag[5] = {S, (int)N, 1, 1, 1};
+  write_array(out, inds.data(), n_inds);
+  if (interp) write_array(out, fracs.data(), n_fracs);
+  write_array(out, nan_.data(), n_flag);
+  write_array(out, fallback.data(), n_flag);
+}
+
 // Inverse of save_geodesic_checkpoint: read a level-0 geodesic checkpoint written by the reference (or by us)
 // and hand its samples to the device instead of tracing (geodesic_checkpoint.cpp:77-108).
 template <typename T>
@@ -305,6 +327,7 @@ RunTimings run_input_file(const std::string &path, int device, bool quiet) {
   if (st.num_bad_geodesics > 0)
     warning(std::to_string(st.num_bad_geodesics) + " out of " + std::to_string(root.rays) + " geodesics terminate unexpectedly.");
   if (cfg.checkpoint_geodesic_save) save_geodesic_checkpoint(ctx, cfg, root, st.geodesic_num_steps);
+  const int level0_steps = st.geodesic_num_steps;
   T.geodesic += now_s() - t0;
 
   AthenaGrid grid;
@@ -384,8 +407,14 @@ RunTimings run_input_file(const std::string &path, int device, bool quiet) {
       t0 = now_s();
       L.image.resize((size_t)Q * L.rays);
       if (R > 0) L.render.resize((size_t)R * 3 * L.rays);
+      const bool save_sampling = sim && cfg.checkpoint_sample_save && n == 0 && level == 0;
+      if (save_sampling) check(ctx, bl_set_taps(ctx, 1));
       check(ctx, bl_radiate_level(ctx, level, n, L.image.data(), R > 0 ? L.render.data() : nullptr, &st));
       T.gpu_radiation_ms += st.ms_radiation;
+      if (save_sampling) {   // as the reference, after the first sampling pass of level 0 (radiation_integrator.cpp:697-704)
+        save_sample_checkpoint(ctx, cfg, L, level0_steps);
+        check(ctx, bl_set_taps(ctx, 0));
+      }
       if (sim && p.slow_light_on) {
         // same errors / warnings as the reference's sampling stage (simulation_sampling.cpp:577-617)
         bl_slow_stats ss{};

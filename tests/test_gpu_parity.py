@@ -820,6 +820,36 @@ def test_geodesic_checkpoint_exchange_with_reference(gpu, tmp_path):
         assert rel_err(loaded['I_nu'], ref['npz']['I_nu']) <= PIXEL_TOL, name
 
 
+@pytest.mark.parametrize('interp', ['true', 'false'])
+def test_sample_checkpoint_written_in_reference_format(interp, gpu, tmp_path):
+    """checkpoint_sample_save = true through the drop-in executable: the file has the reference's layout
+    (sample_checkpoint.cpp:22-39; arrays as file_io.cpp:64-75 dumps them) and, wherever the reference defines
+    them, its values: cell indices exactly, fractions to rounding, NaN / fallback flags exactly."""
+    if not os.path.exists(REF_BIN):
+        pytest.skip('oracle/_ref/blacklight not present')
+    import refio
+    case = Case(tmp_path, 'simulation.input', {'camera_resolution': 24, 'simulation_interp': interp},
+                mock=dict(blocks=(7, 2, 4)))
+    ref = case.run_reference()
+    path = os.path.join(case.dir, 'gpu_samp.ckpt')
+    npz, _ = case.run_gpu_file(extra={'checkpoint_sample_save': 'true', 'checkpoint_sample_load': 'false',
+                                      'checkpoint_sample_file': path})
+    mine = refio.read_sample_checkpoint(path, interp=interp == 'true')
+    rs, geo = ref['samp'], ref['geo']
+    assert mine['sample_inds'].shape == rs['sample_inds'].shape
+    S = rs['sample_nan'].shape[1]
+    mask = np.arange(S)[None, :] < geo['sample_num'][:, None]
+    assert np.array_equal(mine['sample_nan'][mask], rs['sample_nan'][mask])
+    assert np.array_equal(mine['sample_fallback'][mask], rs['sample_fallback'][mask])
+    valid = mask & (rs['sample_nan'] == 0) & (rs['sample_fallback'] == 0) & (mine['sample_inds'][..., 0] >= 0)
+    assert valid.sum() > 1000
+    assert np.array_equal(mine['sample_inds'][valid], rs['sample_inds'][valid])
+    if interp == 'true':
+        assert mine['sample_fracs'].shape == rs['sample_fracs'].shape
+        assert np.max(np.abs(mine['sample_fracs'][valid] - rs['sample_fracs'][valid])) < 1e-10
+    assert rel_err(npz['I_nu'], ref['npz']['I_nu']) <= PIXEL_TOL
+
+
 def test_division_sqrt_sequences(gpu, tmp_path):
     """The geodesic kernel divides and takes square roots through branch-free instruction sequences with one
     refined reciprocal per shared denominator (csrc/glibc_math.cuh: div_by, sqrt_rn).  Their results must be
