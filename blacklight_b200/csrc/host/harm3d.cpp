@@ -122,6 +122,7 @@ void read_harm3d(const std::string &path, bool want_kappa, bool gamma_set, doubl
   if (!in) throw Error("Unexpected end of harm3d file.");
   g.prim.assign((size_t)nv * cells, 0.0f);
   // file: variable fastest, then x3, x2, x1 slowest; ours: (var, k, j, i)
+#pragma omp parallel for schedule(static) collapse(2)
   for (int v = 0; v < nv; v++)
     for (int k = 0; k < n3; k++)
       for (int j = 0; j < n2; j++)
@@ -133,14 +134,17 @@ void read_harm3d(const std::string &path, bool want_kappa, bool gamma_set, doubl
   // (ConvertPrimitives4, simulation_geometry.cpp:242-327)
   const double a = simulation_a;
   auto at = [&](int v, int k, int j, int i) -> float & { return g.prim[(((size_t)v * n3 + k) * n2 + j) * n1 + i]; };
+  const std::vector<double> &x2_mod = x2v_mod;   // the parallel region's threads have their own thread_locals
+  const double h_slope = metric_h;
+#pragma omp parallel for schedule(static) collapse(2)
   for (int k = 0; k < n3; k++)
     for (int j = 0; j < n2; j++)
       for (int i = 0; i < n1; i++) {
-        double r = g.x1v[(size_t)i], th = g.x2v[(size_t)j], cth = std::cos(th), x2 = x2v_mod[(size_t)j];
+        double r = g.x1v[(size_t)i], th = g.x2v[(size_t)j], cth = std::cos(th), x2 = x2_mod[(size_t)j];
         double u0 = at(2, k, j, i), u1 = at(3, k, j, i), u2 = at(4, k, j, i), u3 = at(5, k, j, i);
         double b0 = at(6, k, j, i), b1 = at(7, k, j, i), b2 = at(8, k, j, i), b3 = at(9, k, j, i);
         double dr_dx1 = r;
-        double dth_dx2 = kPi + (1.0 - metric_h) * kPi * std::cos(2.0 * kPi * x2);
+        double dth_dx2 = kPi + (1.0 - h_slope) * kPi * std::cos(2.0 * kPi * x2);
         double sigma = r * r + a * a * cth * cth;
         double f = 2.0 * r / sigma;
         double gtt = -(1.0 + f), gtr = f, gtth = 0.0, gtph = 0.0;

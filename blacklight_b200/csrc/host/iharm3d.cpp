@@ -270,6 +270,7 @@ void read_iharm3d(const std::string &path, const std::string &kappa_name, bool r
   g.prim.assign((size_t)nv * cells, 0.0f);
   auto at = [&](int v, int k, int j, int i) -> float & { return g.prim[(((size_t)v * n3 + k) * n2 + j) * n1 + i]; };
   // file: (x1, x2, x3, variable) with the variable fastest; ours: (var, k, j, i)  (:797-802)
+#pragma omp parallel for schedule(static) collapse(2)
   for (int v = 0; v < nv; v++)
     for (int k = 0; k < n3; k++)
       for (int j = 0; j < n2; j++)

@@ -253,6 +253,15 @@ def test_athdf_and_harm3d_readers_return_the_generator_arrays(tmp_path):
     assert h['time'] == 3.0
     np.testing.assert_allclose(h['x1v'][0], np.sqrt(fields['rf'][:-1] * fields['rf'][1:]), rtol=1e-12)   # centres in ln r
     np.testing.assert_allclose(h['prim'][h['ind_rho'], 0], fields['prim'][0], rtol=1e-6)
+    # the conversions run over the host threads the input file names: same bits with one thread
+    h1 = bl.read_snapshot(_reader_case(tmp_path, 'harm3d', os.path.join(d, 'm.harm3d'), dict(kv, num_threads='1')))
+    assert np.array_equal(h1['prim'], h['prim']) and np.array_equal(h1['x2v'], h['x2v'])
+    # rho, pgas, u^phi and the field recover the generator's (its cell centres are arithmetic, the reader's
+    # logarithmic, so the radial velocity differs at first order in the cell size)
+    for q, name in ((1, 'ind_pgas'), (4, 'ind_uu3'), (5, 'ind_bb1'), (6, 'ind_bb2'), (7, 'ind_bb3')):
+        want = fields['prim'][q].astype(np.float64)
+        got = h['prim'][h[name], 0].astype(np.float64)
+        assert np.max(np.abs(got - want)) <= 2e-2 * np.max(np.abs(want)), name
 
 
 @pytest.mark.parametrize('fmks', [None, dict(poly_xt=0.82, poly_alpha=14.0, mks_smooth=0.5)])
@@ -293,6 +302,11 @@ def test_iharm3d_reader(tmp_path, fmks, capfd):
     else:
         np.testing.assert_allclose(g['x1v'][0], np.exp(lr), rtol=1e-14)
         np.testing.assert_allclose(g['x2v'][0], np.pi * x2 + (1.0 - hslope) / 2.0 * np.sin(2.0 * np.pi * x2), rtol=1e-14)
+    # host threads only split independent cells / table rows: one thread gives the same bits
+    g1 = bl.read_snapshot(_reader_case(tmp_path, 'iharm3d', snap, dict(kv, num_threads='1')))
+    assert np.array_equal(g1['prim'], g['prim'])
+    if fmks:
+        assert np.array_equal(g1['sks_map'], g['sks_map'])
     ph = 0.5 * (w['phf'][:-1] + w['phf'][1:])
     want = ms.mock_fields_at(w['r'][None], w['th'][None], ph[:, None, None])
     gm1 = np.float32(g['plasma_gamma'] - 1.0)
