@@ -57,6 +57,16 @@ def write_case(name, workdir):
     return path, kv['output_file']
 
 
+def dump_crc(input_path):
+    """CRC-32 of the mock dump an input file written by write_case points at (pins the generator to the fixture)."""
+    import zlib
+    for line in open(input_path):
+        if line.startswith('simulation_file'):
+            with open(line.split('=', 1)[1].strip(), 'rb') as f:
+                return zlib.crc32(f.read())
+    raise ValueError('no simulation_file in ' + input_path)
+
+
 def defined_pixels(name, workdir, path, shape):
     """FMKS only: the reference's scaled zone lookup forms indices one zone past the last row / plane
     (simulation_sampling.cpp:412-446); past the last cell of a variable's plane it reads the next variable's first
@@ -99,8 +109,9 @@ def main():
             npz = dict(np.load(out))
             keep = {k: v for k, v in npz.items() if k.endswith('_nu')}
             keep['defined'] = defined_pixels(name, d, path, npz['I_nu'].shape)
+            keep['dump_crc'] = np.uint32(dump_crc(path))
             np.savez_compressed(os.path.join(HERE, 'formats_%s.npz' % name), **keep)
-            print(name, {k: v.shape for k, v in keep.items()}, float(np.nanmax(keep['I_nu'])), 'undefined pixels', int((~keep['defined']).sum()))
+            print(name, {k: v.shape for k, v in keep.items() if k.endswith('_nu')}, float(np.nanmax(keep['I_nu'])), 'undefined pixels', int((~keep['defined']).sum()))
 
 
 if __name__ == '__main__':

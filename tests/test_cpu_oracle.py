@@ -74,3 +74,19 @@ def test_oracle_simulation(name, tmp_path):
     ok = ~np.isnan(ref)
     scale = np.maximum(np.abs(ref[ok]), 1e-12 * np.nanmax(np.abs(ref)))
     assert np.max(np.abs(got[ok] - ref[ok]) / scale) < 1e-10
+
+
+def test_format_fixtures_match_their_generator(tmp_path):
+    """tests/golden/formats_*.npz were produced by the unmodified reference from deterministic mock dumps
+    (AthenaK, iharm3d MKS / FMKS, harm3d); the dumps the GPU parity test rebuilds must be those same bytes."""
+    import sys
+    sys.path.insert(0, GOLDEN)
+    from make_golden_formats import FORMAT_CASES, dump_crc, write_case
+    for name in FORMAT_CASES:
+        gold = np.load(os.path.join(GOLDEN, 'formats_%s.npz' % name))
+        d = os.path.join(str(tmp_path), name)
+        os.makedirs(d)
+        path, _ = write_case(name, d)
+        assert dump_crc(path) == int(gold['dump_crc']), name
+        assert gold['defined'].shape == gold['I_nu'].shape and gold['defined'].mean() > 0.9
+        assert np.nanmax(gold['I_nu']) > 0.0
