@@ -90,3 +90,77 @@ def test_format_fixtures_match_their_generator(tmp_path):
         assert dump_crc(path) == int(gold['dump_crc']), name
         assert gold['defined'].shape == gold['I_nu'].shape and gold['defined'].mean() > 0.9
         assert np.nanmax(gold['I_nu']) > 0.0
+
+
+def test_fmks_table_and_zone_lookup_against_reference_checkpoint(tmp_path):
+    """FMKS host logic without a GPU: the (r, theta) -> (x1, x2) table our iharm3d reader builds, pushed through a numpy
+    restatement of the reference's scaled zone lookup (simulation_sampling.cpp:397-418), reproduces the cell indices
+    and fractions of the unmodified reference's sampling checkpoint exactly -- on the reference's own geodesics."""
+    import subprocess
+    import sys
+    from harness import REF_BIN
+    if not os.path.exists(REF_BIN):
+        pytest.skip('oracle/_ref/blacklight not present')
+    sys.path.insert(0, GOLDEN)
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import refio
+    from make_golden_formats import write_case
+    d = str(tmp_path)
+    path, _ = write_case('iharm3d_fmks_nearest_16', d)
+    lines = [ln for ln in open(path).read().splitlines() if not ln.startswith(('checkpoint_', 'simulation_interp'))]
+    lines += ['simulation_interp = true', 'checkpoint_sample_save = true', 'checkpoint_sample_load = false',
+              'checkpoint_sample_file = %s/samp.ckpt' % d, 'checkpoint_geodesic_save = true',
+              'checkpoint_geodesic_load = false', 'checkpoint_geodesic_file = %s/geo.ckpt' % d]
+    with open(path, 'w') as f:
+        f.write('\n'.join(lines) + '\n')
+    proc = subprocess.run([REF_BIN, path], cwd=d, capture_output=True, text=True, timeout=600)
+    assert proc.returncode == 0, proc.stdout + proc.stderr
+    s = refio.read_sample_checkpoint(os.path.join(d, 'samp.ckpt'), interp=True)
+    g = refio.read_geodesic_checkpoint(os.path.join(d, 'geo.ckpt'))
+    G = bl.read_snapshot(bl.Config(path))
+    x, y, z = (g['sample_pos'][..., c] for c in (1, 2, 3))
+    with np.errstate(all='ignore'):
+        r = np.sqrt(x * x + y * y + z * z)          # a = 0: the Kerr-Schild radius
+        th = np.arccos(z / r)
+    S = s['sample_nan'].shape[1]
+    valid = (np.arange(S)[None, :] < g['sample_num'][:, None]) & (s['sample_nan'] == 0) & (r <= 50.0)
+    x1, x2, m = r[valid], th[valid], G['sks_map']
+    f_i, i_ind = np.modf((x1 - G['sks_map_r_in']) / G['sks_map_dr'])
+    f_j, j_ind = np.modf(x2 / G['sks_map_dtheta'])
+    i, j = i_ind.astype(int), j_ind.astype(int)
+    nat_x1 = (1.0 - f_i) * m[0, j, i] + f_i * m[0, j, i + 1]
+    nat_x2 = (1.0 - f_j) * m[1, j + 1, i] + f_j * m[1, j + 1, i]
+    x1f, x2f = G['x1f'][0], G['x2f'][0]
+    frac_i, zone_i = np.modf((nat_x1 - x1f[0]) / (x1f[1] - x1f[0]))
+    frac_j, zone_j = np.modf(nat_x2 / (x2f[1] - x2f[0]))
+    inds, fracs = s['sample_inds'][valid], s['sample_fracs'][valid]
+    assert valid.sum() > 10000
+    assert np.array_equal(inds[:, 3], zone_i.astype(int)) and np.array_equal(inds[:, 2], zone_j.astype(int))
+    assert np.array_equal(fracs[:, 2], frac_i) and np.array_equal(fracs[:, 1], frac_j)
+
+
+@pytest.mark.parametrize('name', ['iharm3d_mks_16', 'harm3d_16'])
+def test_readers_through_the_restatement_against_reference_fixtures(name, tmp_path):
+    """Host readers without a GPU: the arrays our iharm3d / harm3d readers hand to bl_upload_grid (coordinates converted
+    to spherical Kerr-Schild, primitives to the standard frames), rendered by the plain-C restatement of the
+    reference's sampling + thermal transfer, against the unmodified reference's image of the same dump."""
+    import sys
+    sys.path.insert(0, GOLDEN)
+    from make_golden_formats import write_case
+    gold = np.load(os.path.join(GOLDEN, 'formats_%s.npz' % name))
+    path, _ = write_case(name, str(tmp_path))
+    with open(path) as f:
+        kv = bl.parse_input_text(f.read())
+    cfg = bl.Config(path)
+    g = bl.read_snapshot(cfg)
+    order = ('ind_rho', 'ind_pgas', 'ind_uu1', 'ind_uu2', 'ind_uu3', 'ind_bb1', 'ind_bb2', 'ind_bb3')   # the restatement's
+    grid = dict(g, prim=np.ascontiguousarray(np.stack([g['prim'][g[k]] for k in order]), np.float32))
+    pos, dirs, fac = cfg.camera_root()
+    s = oracle_lib.trace(kv, float(kv['simulation_a']), pos, dirs)
+    image, _ = oracle_lib.simulation_image(kv, s, fac, grid, want_inds=False)
+    res = cfg.resolution
+    ref, got = gold['I_nu'], image.reshape(res, res)
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    scale = np.maximum(np.abs(ref[ok]), 1e-12 * np.nanmax(np.abs(ref)))
+    assert np.max(np.abs(got[ok] - ref[ok]) / scale) < 1e-10
