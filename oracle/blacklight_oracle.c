@@ -354,6 +354,7 @@ typedef struct {
   int n_b, n_k, n_j, n_i, interp, fallback_nan;
   double d_unit, mu, ne_ni, rat_low, rat_high;
   double cut_sigma_max;   /* < 0 disables; the other value cuts of the examples are disabled */
+  int coord;              /* 0 spherical Kerr-Schild grid, 1 Cartesian Kerr-Schild grid (simulation_coord = cks) */
 } orc_sim;
 
 static double g4(const float *prim, const orc_sim *P, int v, int b, int k, int j, int i) {
@@ -434,6 +435,7 @@ void orc_simulation_image(const orc_sim *P, long n_rays, int cap, const int *num
           double x1 = r, x2 = acos(z / r), x3 = atan2(y, x) - atan(a / r);
           x3 += x3 < 0.0 ? 2.0 * PI : 0.0;
           x3 -= x3 >= 2.0 * PI ? 2.0 * PI : 0.0;
+          if (P->coord == 1) { x1 = x; x2 = y; x3 = z; }   /* radiation_geometry.cpp:37-57: cks keeps x, y, z */
           /* block: keep while inside (inclusive), else first match (simulation_sampling.cpp:352-394) */
           if (x1 < x1f[(size_t)b * (n_i + 1)] || x1 > x1f[(size_t)b * (n_i + 1) + n_i] || x2 < x2f[(size_t)b * (n_j + 1)] ||
               x2 > x2f[(size_t)b * (n_j + 1) + n_j] || x3 < x3f[(size_t)b * (n_k + 1)] || x3 > x3f[(size_t)b * (n_k + 1) + n_k]) {
@@ -494,6 +496,10 @@ void orc_simulation_image(const orc_sim *P, long n_rays, int cap, const int *num
         gs[3][3] = (r2 + a2 + 2.0 * a2 * r * sth2 / sigma_ks) * sth2;
         gc[0][0] = -(1.0 + 2.0 * r / sigma_ks); gc[0][1] = gc[1][0] = 2.0 * r / sigma_ks; gc[1][1] = delta / sigma_ks;
         gc[1][3] = gc[3][1] = a / sigma_ks; gc[2][2] = 1.0 / sigma_ks; gc[3][3] = 1.0 / (sigma_ks * sth2);
+        if (P->coord == 1) {   /* the grid's own coordinates are the Cartesian Kerr-Schild ones (radiation_geometry.cpp:425-457) */
+          metric_cov(&geo, x, y, z, gs);
+          metric_con(&geo, x, y, z, gc);
+        }
         double rho_cgs = rho * P->d_unit, pgas_cgs = pgas * e_unit;
         double n_e = rho_cgs / (P->mu * m_p) / (1.0 + 1.0 / P->ne_ni);
         double uu0 = sqrt(1.0 + gs[1][1] * uu[0] * uu[0] + 2.0 * gs[1][2] * uu[0] * uu[1] + 2.0 * gs[1][3] * uu[0] * uu[2] +
@@ -522,6 +528,10 @@ void orc_simulation_image(const orc_sim *P, long n_rays, int cap, const int *num
           jac[1][1] = sth * cph; jac[1][2] = cth * (r * cph - a * sph); jac[1][3] = sth * (-r * sph - a * cph);
           jac[2][1] = sth * sph; jac[2][2] = cth * (r * sph + a * cph); jac[2][3] = sth * (r * cph - a * sph);
           jac[3][1] = cth; jac[3][2] = -r * sth;
+          if (P->coord == 1) {   /* no change of coordinates */
+            memset(jac, 0, sizeof jac);
+            jac[0][0] = jac[1][1] = jac[2][2] = jac[3][3] = 1.0;
+          }
           double ucon[4] = {0, 0, 0, 0}, bcon[4] = {0, 0, 0, 0}, kcon[4] = {0, 0, 0, 0}, ucov[4] = {0, 0, 0, 0}, bcov[4] = {0, 0, 0, 0};
           double gcov[4][4], gcon[4][4], e[4][4];
           for (mu = 0; mu < 4; mu++) for (nu_ = 0; nu_ < 4; nu_++) { ucon[mu] += jac[mu][nu_] * us[nu_]; bcon[mu] += jac[mu][nu_] * bs[nu_]; }

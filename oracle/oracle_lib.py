@@ -22,7 +22,8 @@ class Formula(ctypes.Structure):
 class Sim(ctypes.Structure):
     _fields_ = [('a', ctypes.c_double), ('camera_r', ctypes.c_double), ('x_unit', ctypes.c_double)] + \
                [(n, ctypes.c_int) for n in ('n_b', 'n_k', 'n_j', 'n_i', 'interp', 'fallback_nan')] + \
-               [(n, ctypes.c_double) for n in ('d_unit', 'mu', 'ne_ni', 'rat_low', 'rat_high', 'cut_sigma_max')]
+               [(n, ctypes.c_double) for n in ('d_unit', 'mu', 'ne_ni', 'rat_low', 'rat_high', 'cut_sigma_max')] + \
+               [('coord', ctypes.c_int)]
 
 
 def _p(a):
@@ -84,7 +85,7 @@ def simulation_image(kv, s, mom, grid, want_inds=True):
             n_b=grid['n_b'], n_k=grid['n_k'], n_j=grid['n_j'], n_i=grid['n_i'], interp=int(kv['simulation_interp'] == 'true'),
             fallback_nan=int(kv['fallback_nan'] == 'true'), d_unit=float(kv['simulation_rho_cgs']), mu=float(kv['plasma_mu']),
             ne_ni=float(kv['plasma_ne_ni']), rat_low=float(kv['plasma_rat_low']), rat_high=float(kv['plasma_rat_high']),
-            cut_sigma_max=float(kv['cut_sigma_max']))
+            cut_sigma_max=float(kv['cut_sigma_max']), coord=int(kv.get('simulation_coord', 'sks') == 'cks'))
     n = len(mom)
     image = np.zeros(n)
     inds = np.full((n, s['cap'], 4), -1, np.int32) if want_inds else None

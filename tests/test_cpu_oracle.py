@@ -139,10 +139,11 @@ def test_fmks_table_and_zone_lookup_against_reference_checkpoint(tmp_path):
     assert np.array_equal(fracs[:, 2], frac_i) and np.array_equal(fracs[:, 1], frac_j)
 
 
-@pytest.mark.parametrize('name', ['iharm3d_mks_16', 'harm3d_16'])
+@pytest.mark.parametrize('name', ['iharm3d_mks_16', 'harm3d_16', 'athenak_16'])
 def test_readers_through_the_restatement_against_reference_fixtures(name, tmp_path):
-    """Host readers without a GPU: the arrays our iharm3d / harm3d readers hand to bl_upload_grid (coordinates converted
-    to spherical Kerr-Schild, primitives to the standard frames), rendered by the plain-C restatement of the
+    """Host readers without a GPU: the arrays our iharm3d / harm3d / AthenaK readers hand to bl_upload_grid (coordinates
+    converted to spherical Kerr-Schild and primitives to the standard frames for the Harm formats; Cartesian Kerr-Schild
+    blocks rebuilt from their edges for AthenaK), rendered by the plain-C restatement of the
     reference's sampling + thermal transfer, against the unmodified reference's image of the same dump."""
     import sys
     sys.path.insert(0, GOLDEN)
