@@ -14,6 +14,8 @@
  *   formula-model coefficients                             formula_coefficients.cpp:25-183
  *   grid sampling (block/cell search, nearest, trilinear)  simulation_sampling.cpp:122-575, 636-1044
  *   thermal synchrotron I coefficients                     simulation_coefficients.cpp:254-524
+ *   power-law synchrotron I coefficients and constants     simulation_coefficients.cpp:53-66, 559-585
+ *   Cartesian Kerr-Schild grids (simulation_coord = cks)   radiation_geometry.cpp:37-57, 425-457
  *   fluid-frame tetrad                                     radiation_geometry.cpp:597-658
  *   unpolarized transfer                                   unpolarized.cpp:31-221
  * Build: gcc -O2 -ffp-contract=off (no FMA contraction, like the reference's -O3 without -march).
@@ -355,6 +357,8 @@ typedef struct {
   double d_unit, mu, ne_ni, rat_low, rat_high;
   double cut_sigma_max;   /* < 0 disables; the other value cuts of the examples are disabled */
   int coord;              /* 0 spherical Kerr-Schild grid, 1 Cartesian Kerr-Schild grid (simulation_coord = cks) */
+  /* power-law electrons (simulation_coefficients.cpp:53-66,559-585); thermal fraction = 1 - power_frac */
+  double power_frac, power_p, power_gamma_min, power_gamma_max;
 } orc_sim;
 
 static double g4(const float *prim, const orc_sim *P, int v, int b, int k, int j, int i) {
@@ -552,12 +556,29 @@ void orc_simulation_image(const orc_sim *P, long n_rays, int cap, const int *num
           nu *= freq * mom_factor[m];
           double nu_c = qe * bb_cgs / (2.0 * PI * m_e * c), nu_s = 2.0 / 9.0 * nu_c * theta_e * theta_e * sin_t;
           double xx = nu / nu_s, x12 = sqrt(xx), x13 = cbrt(xx), x16 = sqrt(x13);
-          double coef = 1.0 * n_e * qe * qe * nu_c / (c * (nu * nu)) * exp(-x13);
-          double va = 1.4142135623730951 * PI / 27.0 * sin_t, vb = pow(2.0, 11.0 / 12.0), vc = x12 + vb * x16;
-          jv = coef * va * vc * vc;
-          double bnu = 2.0 * hpl / (c * c) / expm1(hpl * nu / kb_te);
-          av = jv / bnu;
-          if (1.0 / (av * av) == INFINITY) av = 0.0;
+          double thermal_frac = 1.0 - (P->power_frac + 0.0);
+          if (thermal_frac != 0.0) {
+            double coef = thermal_frac * n_e * qe * qe * nu_c / (c * (nu * nu)) * exp(-x13);
+            double va = 1.4142135623730951 * PI / 27.0 * sin_t, vb = pow(2.0, 11.0 / 12.0), vc = x12 + vb * x16;
+            jv = coef * va * vc * vc;
+            double bnu = 2.0 * hpl / (c * c) / expm1(hpl * nu / kb_te);
+            av = jv / bnu;
+            if (1.0 / (av * av) == INFINITY) av = 0.0;
+          }
+          if (P->power_frac != 0.0) {
+            /* constants (simulation_coefficients.cpp:56-66), emissivity and absorptivity (:559-585) */
+            double p = P->power_p;
+            double c_a = pow(3.0, p / 2.0) * (p - 1.0), c_b = 2.0 * (p + 1.0);
+            double c_c = pow(P->power_gamma_min, 1.0 - p) - pow(P->power_gamma_max, 1.0 - p);
+            double c_d = tgamma((3.0 * p - 1.0) / 12.0), c_e = tgamma((3.0 * p + 19.0) / 12.0);
+            double c_f = pow(3.0, (p + 1.0) / 2.0) * (p - 1.0) / 4.0;
+            double c_g = tgamma((3.0 * p + 2.0) / 12.0), c_h = tgamma((3.0 * p + 22.0) / 12.0);
+            double power_jj = c_a / c_b / c_c * c_d * c_e, power_aa = c_f / c_c * c_g * c_h;
+            double pj = pow(nu / (nu_c * sin_t), -(p - 1.0) / 2.0);
+            jv += P->power_frac * n_e * qe * qe * nu_c / (c * (nu * nu)) * power_jj * sin_t * pj;
+            double pa = pow(nu / (nu_c * sin_t), -(p + 2.0) / 2.0);
+            av += P->power_frac * n_e * qe * qe / (m_e * c) * power_aa * pa;
+          }
         }
       }
       I = transfer_step(I, jv, av, dl_cgs);

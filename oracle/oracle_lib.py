@@ -23,7 +23,8 @@ class Sim(ctypes.Structure):
     _fields_ = [('a', ctypes.c_double), ('camera_r', ctypes.c_double), ('x_unit', ctypes.c_double)] + \
                [(n, ctypes.c_int) for n in ('n_b', 'n_k', 'n_j', 'n_i', 'interp', 'fallback_nan')] + \
                [(n, ctypes.c_double) for n in ('d_unit', 'mu', 'ne_ni', 'rat_low', 'rat_high', 'cut_sigma_max')] + \
-               [('coord', ctypes.c_int)]
+               [('coord', ctypes.c_int)] + \
+               [(n, ctypes.c_double) for n in ('power_frac', 'power_p', 'power_gamma_min', 'power_gamma_max')]
 
 
 def _p(a):
@@ -85,7 +86,9 @@ def simulation_image(kv, s, mom, grid, want_inds=True):
             n_b=grid['n_b'], n_k=grid['n_k'], n_j=grid['n_j'], n_i=grid['n_i'], interp=int(kv['simulation_interp'] == 'true'),
             fallback_nan=int(kv['fallback_nan'] == 'true'), d_unit=float(kv['simulation_rho_cgs']), mu=float(kv['plasma_mu']),
             ne_ni=float(kv['plasma_ne_ni']), rat_low=float(kv['plasma_rat_low']), rat_high=float(kv['plasma_rat_high']),
-            cut_sigma_max=float(kv['cut_sigma_max']), coord=int(kv.get('simulation_coord', 'sks') == 'cks'))
+            cut_sigma_max=float(kv['cut_sigma_max']), coord=int(kv.get('simulation_coord', 'sks') == 'cks'),
+            power_frac=float(kv.get('plasma_power_frac', 0.0)), power_p=float(kv.get('plasma_p', 0.0)),
+            power_gamma_min=float(kv.get('plasma_gamma_min', 0.0)), power_gamma_max=float(kv.get('plasma_gamma_max', 0.0)))
     n = len(mom)
     image = np.zeros(n)
     inds = np.full((n, s['cap'], 4), -1, np.int32) if want_inds else None

@@ -165,3 +165,29 @@ def test_readers_through_the_restatement_against_reference_fixtures(name, tmp_pa
     ok = ~np.isnan(ref)
     scale = np.maximum(np.abs(ref[ok]), 1e-12 * np.nanmax(np.abs(ref)))
     assert np.max(np.abs(got[ok] - ref[ok]) / scale) < 1e-10
+
+
+def test_oracle_power_law_electrons(tmp_path):
+    """Thermal (0.6) + power-law (0.4, p = 3, gamma in [4, 1000]) electrons: the restatement's constants (tgamma forms,
+    simulation_coefficients.cpp:56-66) and per-sample emissivity / absorptivity (:559-585) against the unmodified
+    reference's image (tests/golden/cpu_simulation_power_law_16.npz, made with the harness's Case.run_reference)."""
+    over = {'camera_resolution': 16, 'plasma_power_frac': '0.4', 'plasma_p': '3.0', 'plasma_gamma_min': '4.0',
+            'plasma_gamma_max': '1000.0'}
+    kv = load_input('simulation.input')
+    kv.update({k: str(v) for k, v in over.items()})
+    path = os.path.join(tmp_path, 'o.input')
+    write_input(path, kv)
+    cfg = bl.Config(path)
+    grid = mock_snapshot.grid_view_arrays(mock_snapshot.make_mock(None))
+    pos, dirs, fac = cfg.camera_root()
+    s = oracle_lib.trace(kv, float(kv['simulation_a']), pos, dirs)
+    image, _ = oracle_lib.simulation_image(kv, s, fac, grid, want_inds=False)
+    ref = np.load(os.path.join(GOLDEN, 'cpu_simulation_power_law_16.npz'))['I_nu']
+    got = image.reshape(16, 16)
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    scale = np.maximum(np.abs(ref[ok]), 1e-12 * np.nanmax(np.abs(ref)))
+    assert np.max(np.abs(got[ok] - ref[ok]) / scale) < 1e-10
+    # and it differs from the purely thermal image, i.e. the power-law terms are exercised
+    thermal = np.load(os.path.join(GOLDEN, 'simulation_32.npz'))['I_nu']
+    assert abs(np.nanmax(ref) / np.nanmax(thermal) - 1.0) > 0.01
