@@ -15,6 +15,7 @@
  *   grid sampling (block/cell search, nearest, trilinear)  simulation_sampling.cpp:122-575, 636-1044
  *   thermal synchrotron I coefficients                     simulation_coefficients.cpp:254-524
  *   power-law synchrotron I coefficients and constants     simulation_coefficients.cpp:53-66, 559-585
+ *   kappa-distribution I coefficients and constants        simulation_coefficients.cpp:82-105, 608-653, 740-773
  *   Cartesian Kerr-Schild grids (simulation_coord = cks)   radiation_geometry.cpp:37-57, 425-457
  *   fluid-frame tetrad                                     radiation_geometry.cpp:597-658
  *   unpolarized transfer                                   unpolarized.cpp:31-221
@@ -359,7 +360,25 @@ typedef struct {
   int coord;              /* 0 spherical Kerr-Schild grid, 1 Cartesian Kerr-Schild grid (simulation_coord = cks) */
   /* power-law electrons (simulation_coefficients.cpp:53-66,559-585); thermal fraction = 1 - power_frac */
   double power_frac, power_p, power_gamma_min, power_gamma_max;
+  /* kappa-distribution electrons (simulation_coefficients.cpp:82-105,608-664) */
+  double kappa_frac, kappa, kappa_w;
 } orc_sim;
+
+/* Gauss hypergeometric function by the reference's transformed, 10-term series (simulation_coefficients.cpp:740-773) */
+static double hypergeometric(double alpha, double beta, double gamma, double z) {
+  double a = alpha, b = gamma - beta, c_ = gamma, x = z / (z - 1.0);
+  double result = 1.0, a_k = 1.0, b_k = 1.0, c_k = 1.0, xk = 1.0, k_factorial = 1.0;
+  int k;
+  for (k = 1; k <= 10; k++) {
+    a_k *= a + k - 1.0;
+    b_k *= b + k - 1.0;
+    c_k *= c_ + k - 1.0;
+    xk *= x;
+    k_factorial *= k;
+    result += a_k * b_k * xk / (c_k * k_factorial);
+  }
+  return result * pow(1.0 - z, -alpha);
+}
 
 static double g4(const float *prim, const orc_sim *P, int v, int b, int k, int j, int i) {
   return (double)prim[((((size_t)v * P->n_b + b) * P->n_k + k) * P->n_j + j) * P->n_i + i];
@@ -556,7 +575,7 @@ void orc_simulation_image(const orc_sim *P, long n_rays, int cap, const int *num
           nu *= freq * mom_factor[m];
           double nu_c = qe * bb_cgs / (2.0 * PI * m_e * c), nu_s = 2.0 / 9.0 * nu_c * theta_e * theta_e * sin_t;
           double xx = nu / nu_s, x12 = sqrt(xx), x13 = cbrt(xx), x16 = sqrt(x13);
-          double thermal_frac = 1.0 - (P->power_frac + 0.0);
+          double thermal_frac = 1.0 - (P->power_frac + P->kappa_frac);
           if (thermal_frac != 0.0) {
             double coef = thermal_frac * n_e * qe * qe * nu_c / (c * (nu * nu)) * exp(-x13);
             double va = 1.4142135623730951 * PI / 27.0 * sin_t, vb = pow(2.0, 11.0 / 12.0), vc = x12 + vb * x16;
@@ -578,6 +597,32 @@ void orc_simulation_image(const orc_sim *P, long n_rays, int cap, const int *num
             jv += P->power_frac * n_e * qe * qe * nu_c / (c * (nu * nu)) * power_jj * sin_t * pj;
             double pa = pow(nu / (nu_c * sin_t), -(p + 2.0) / 2.0);
             av += P->power_frac * n_e * qe * qe / (m_e * c) * power_aa * pa;
+          }
+          if (P->kappa_frac != 0.0) {
+            /* constants (simulation_coefficients.cpp:84-105) */
+            double kap = P->kappa, w = P->kappa_w;
+            double k_a = 4.0 * PI * tgamma(kap - 4.0 / 3.0), k_b = pow(3.0, 7.0 / 3.0) * tgamma(kap - 2.0);
+            double k_c = pow(3.0, (kap - 1.0) / 2.0), k_d = (kap - 2.0) * (kap - 1.0) / 4.0;
+            double k_e = tgamma(kap / 4.0 - 1.0 / 3.0), k_f = tgamma(kap / 4.0 + 4.0 / 3.0);
+            double k_g = pow(3.0, 1.0 / 6.0) * 10.0 / 41.0, k_h = w * kap;
+            double k_i = 2.0 * PI * pow(k_h, kap - 10.0 / 3.0), k_j = (kap - 2.0) * (kap - 1.0) * kap;
+            double k_k = 3.0 * kap - 1.0, k_l = tgamma(5.0 / 3.0);
+            double k_m = hypergeometric(kap - 1.0 / 3.0, kap + 1.0, kap + 2.0 / 3.0, -k_h);
+            double k_n = pow(PI, 1.5) / 3.0, k_o = k_j / (k_h * k_h * k_h);
+            double k_p = 2.0 * tgamma(2.0 + kap / 2.0) / (2.0 + kap) - 1.0;
+            double jj_low = k_a / k_b, jj_high = k_c * k_d * k_e * k_f, jj_x = 3.0 * pow(kap, -1.5);
+            double aa_low = k_g * k_i * k_j / k_k * k_l * k_m, aa_high = k_n * k_o * k_p, aa_x = pow(-1.75 + 1.6 * kap, -0.86);
+            /* kappa_aa_high_i is assigned only in polarized runs (:121); in an unpolarized run the member keeps its
+             * zero, the high branch is 0, 0^(-x) is infinite and the bridged absorptivity vanishes (:649-653) */
+            double aa_high_i = 0.0;
+            /* emissivity (:608-622) and absorptivity (:639-653) */
+            double nu_kappa = nu_c * w * w * kap * kap * sin_t, xk_ = nu / nu_kappa;
+            double e_a = P->kappa_frac * n_e * qe * qe * nu_c / (c * (nu * nu));
+            double e_lo = jj_low * e_a * (cbrt(xk_) * sin_t), e_hi = jj_high * e_a * (pow(xk_, -(kap - 2.0) / 2.0) * sin_t);
+            jv += pow(pow(e_lo, -jj_x) + pow(e_hi, -jj_x), -1.0 / jj_x);
+            double a_a = P->kappa_frac * n_e * qe * qe / (m_e * c);
+            double a_lo = aa_low * a_a * pow(xk_, -2.0 / 3.0), a_hi = aa_high * a_a * pow(xk_, -(1.0 + kap) / 2.0) * aa_high_i;
+            av += pow(pow(a_lo, -aa_x) + pow(a_hi, -aa_x), -1.0 / aa_x);
           }
         }
       }

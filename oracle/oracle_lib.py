@@ -24,7 +24,8 @@ class Sim(ctypes.Structure):
                [(n, ctypes.c_int) for n in ('n_b', 'n_k', 'n_j', 'n_i', 'interp', 'fallback_nan')] + \
                [(n, ctypes.c_double) for n in ('d_unit', 'mu', 'ne_ni', 'rat_low', 'rat_high', 'cut_sigma_max')] + \
                [('coord', ctypes.c_int)] + \
-               [(n, ctypes.c_double) for n in ('power_frac', 'power_p', 'power_gamma_min', 'power_gamma_max')]
+               [(n, ctypes.c_double) for n in ('power_frac', 'power_p', 'power_gamma_min', 'power_gamma_max',
+                                               'kappa_frac', 'kappa', 'kappa_w')]
 
 
 def _p(a):
@@ -88,7 +89,9 @@ def simulation_image(kv, s, mom, grid, want_inds=True):
             ne_ni=float(kv['plasma_ne_ni']), rat_low=float(kv['plasma_rat_low']), rat_high=float(kv['plasma_rat_high']),
             cut_sigma_max=float(kv['cut_sigma_max']), coord=int(kv.get('simulation_coord', 'sks') == 'cks'),
             power_frac=float(kv.get('plasma_power_frac', 0.0)), power_p=float(kv.get('plasma_p', 0.0)),
-            power_gamma_min=float(kv.get('plasma_gamma_min', 0.0)), power_gamma_max=float(kv.get('plasma_gamma_max', 0.0)))
+            power_gamma_min=float(kv.get('plasma_gamma_min', 0.0)), power_gamma_max=float(kv.get('plasma_gamma_max', 0.0)),
+            kappa_frac=float(kv.get('plasma_kappa_frac', 0.0)), kappa=float(kv.get('plasma_kappa', 0.0)),
+            kappa_w=float(kv.get('plasma_w', 0.0)))
     n = len(mom)
     image = np.zeros(n)
     inds = np.full((n, s['cap'], 4), -1, np.int32) if want_inds else None

@@ -167,14 +167,20 @@ def test_readers_through_the_restatement_against_reference_fixtures(name, tmp_pa
     assert np.max(np.abs(got[ok] - ref[ok]) / scale) < 1e-10
 
 
-def test_oracle_power_law_electrons(tmp_path):
-    """Thermal (0.6) + power-law (0.4, p = 3, gamma in [4, 1000]) electrons: the restatement's constants (tgamma forms,
-    simulation_coefficients.cpp:56-66) and per-sample emissivity / absorptivity (:559-585) against the unmodified
-    reference's image (tests/golden/cpu_simulation_power_law_16.npz, made with the harness's Case.run_reference)."""
-    over = {'camera_resolution': 16, 'plasma_power_frac': '0.4', 'plasma_p': '3.0', 'plasma_gamma_min': '4.0',
-            'plasma_gamma_max': '1000.0'}
+@pytest.mark.parametrize('fixture,over', [
+    ('cpu_simulation_power_law_16', {'plasma_power_frac': '0.4', 'plasma_p': '3.0', 'plasma_gamma_min': '4.0',
+                                     'plasma_gamma_max': '1000.0'}),
+    ('cpu_simulation_mixed_electrons_16', {'plasma_power_frac': '0.2', 'plasma_p': '3.0', 'plasma_gamma_min': '4.0',
+                                           'plasma_gamma_max': '1000.0', 'plasma_kappa_frac': '0.5', 'plasma_kappa': '4.0',
+                                           'plasma_w': '1.0'}),
+])
+def test_oracle_nonthermal_electrons(fixture, over, tmp_path):
+    """Thermal + power-law (+ kappa) electrons: the restatement's constants (tgamma forms and the truncated
+    hypergeometric series, simulation_coefficients.cpp:53-105,740-773) and per-sample emissivities / absorptivities
+    (:559-585, :608-653, including the kappa absorptivity that an unpolarized run of the reference zeroes) against the
+    unmodified reference's images (tests/golden/cpu_*.npz, made with the harness's Case.run_reference)."""
     kv = load_input('simulation.input')
-    kv.update({k: str(v) for k, v in over.items()})
+    kv.update(dict(over, camera_resolution='16'))
     path = os.path.join(tmp_path, 'o.input')
     write_input(path, kv)
     cfg = bl.Config(path)
@@ -182,12 +188,12 @@ def test_oracle_power_law_electrons(tmp_path):
     pos, dirs, fac = cfg.camera_root()
     s = oracle_lib.trace(kv, float(kv['simulation_a']), pos, dirs)
     image, _ = oracle_lib.simulation_image(kv, s, fac, grid, want_inds=False)
-    ref = np.load(os.path.join(GOLDEN, 'cpu_simulation_power_law_16.npz'))['I_nu']
+    ref = np.load(os.path.join(GOLDEN, fixture + '.npz'))['I_nu']
     got = image.reshape(16, 16)
     assert np.array_equal(np.isnan(got), np.isnan(ref))
     ok = ~np.isnan(ref)
     scale = np.maximum(np.abs(ref[ok]), 1e-12 * np.nanmax(np.abs(ref)))
     assert np.max(np.abs(got[ok] - ref[ok]) / scale) < 1e-10
-    # and it differs from the purely thermal image, i.e. the power-law terms are exercised
+    # and it differs from the purely thermal image, i.e. the non-thermal terms are exercised
     thermal = np.load(os.path.join(GOLDEN, 'simulation_32.npz'))['I_nu']
     assert abs(np.nanmax(ref) / np.nanmax(thermal) - 1.0) > 0.01
