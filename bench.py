@@ -99,7 +99,9 @@ def workload_case(args, workdir, resolution, write_mock):
         mock = {'n_r': 77 * k, 'n_th': 64 * k, 'n_ph': 128 * k}
     if args.workload == 'polarized_thermal':
         over.update({'image_polarization': 'true'})
-    case = Case(workdir, base, over, mock=mock)
+    # host threads (camera pixels, reader conversions) per rank: the box's cores shared among the ranks
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    case = Case(workdir, base, over, mock=mock, threads=max(1, (os.cpu_count() or 1) // world))
     return case
 
 
