@@ -83,7 +83,7 @@ def load_library():
         'blh_camera_blocks': (i64, [vp, i32, vp, i64, vp, vp, vp]),
         'blh_snapshot_read': (i32, [vp, ctypes.c_char_p, ctypes.POINTER(vp)]),
         'blh_snapshot_view': (i32, [vp, ctypes.POINTER(GridView), ctypes.POINTER(dbl), ctypes.POINTER(dbl)]),
-        'blh_snapshot_free': (None, [vp]),
+        'blh_snapshot_free': (None, [vp]), 'blh_snapshot_reread': (i32, [vp, ctypes.c_char_p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -323,15 +323,18 @@ class Context:
         return dict(inds=inds, fracs=fracs, nan=nan_, cut=cut, fallback=fb)
 
 
-def read_snapshot(config, path=None):
-    """Read one snapshot with the reader the input file selects (simulation_format = athena, athenak or harm3d):
-    blh_snapshot_read.  Returns the arrays of bl_grid_view as numpy copies (what Context.upload_grid takes) plus
-    'time' and 'plasma_gamma'."""
+def read_snapshot(config, path=None, then=None):
+    """Read one snapshot with the reader the input file selects (simulation_format = athena, athenak, iharm3d or
+    harm3d): blh_snapshot_read.  Returns the arrays of bl_grid_view as numpy copies (what Context.upload_grid takes)
+    plus 'time' and 'plasma_gamma'.  then: a later file of the same series, read on top of the first one the way the
+    driver does for time series (blh_snapshot_reread: layout kept, cell data and time refreshed)."""
     lib = load_library()
     h = ctypes.c_void_p()
     if lib.blh_snapshot_read(config._h, os.fsencode(path) if path else None, ctypes.byref(h)) != 0:
         raise BlacklightError(lib.blh_last_error().decode())
     try:
+        if then is not None and lib.blh_snapshot_reread(h, os.fsencode(then)) != 0:
+            raise BlacklightError(lib.blh_last_error().decode())
         v, t, g = GridView(), ctypes.c_double(), ctypes.c_double()
         lib.blh_snapshot_view(h, ctypes.byref(v), ctypes.byref(t), ctypes.byref(g))
         out = {n: getattr(v, n) for n, c in GridView._fields_ if c is ctypes.c_int32 and not n.startswith('sks_map')}

@@ -4,6 +4,7 @@
 #include "../../../include/blacklight_b200_host.h"
 
 #include <cstring>
+#include <memory>
 #include <string>
 
 #include "config.hpp"
@@ -15,6 +16,8 @@ struct blh_config {
 };
 
 struct blh_snapshot {
+  blh::RunConfig cfg;                            // the reader refers to it
+  std::unique_ptr<blh::SnapshotReader> reader;   // keeps the layout found in the first file (time series)
   blh::AthenaGrid grid;
   double plasma_gamma = 0.0;
 };
@@ -104,16 +107,22 @@ int blh_snapshot_read(const blh_config *c, const char *file, blh_snapshot **out)
   *out = nullptr;
   try {
     if (c->cfg.params.model_type != BL_MODEL_SIMULATION) throw blh::Error("model_type is not simulation.");
-    blh::SnapshotReader reader(c->cfg);
-    blh_snapshot *s = new blh_snapshot;
-    try {
-      reader.read(file ? std::string(file) : reader.first_file(), false, s->grid);
-    } catch (...) {
-      delete s;
-      throw;
-    }
-    s->plasma_gamma = reader.plasma_gamma();
-    *out = s;
+    std::unique_ptr<blh_snapshot> s(new blh_snapshot);
+    s->cfg = c->cfg;
+    s->reader.reset(new blh::SnapshotReader(s->cfg));
+    s->reader->read(file ? std::string(file) : s->reader->first_file(), false, s->grid);
+    s->plasma_gamma = s->reader->plasma_gamma();
+    *out = s.release();
+    return 0;
+  } catch (const std::exception &e) {
+    return fail(e);
+  }
+}
+
+int blh_snapshot_reread(blh_snapshot *s, const char *file) {
+  if (!s || !file) { g_error = "null argument"; return 1; }
+  try {
+    s->reader->read(file, true, s->grid);
     return 0;
   } catch (const std::exception &e) {
     return fail(e);

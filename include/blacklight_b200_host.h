@@ -46,6 +46,9 @@ int64_t blh_camera_blocks(const blh_config *cfg, int level, const int32_t *locs,
  * plasma_gamma is the adiabatic index the reader settled on (the file's where the input file gives none). */
 typedef struct blh_snapshot blh_snapshot;
 int blh_snapshot_read(const blh_config *cfg, const char *file, blh_snapshot **out);
+/* Next file of a time series: keeps the layout (coordinates, variable positions, adiabatic indices) found in the first
+ * file and refreshes the cell data and the time, as the reference's reader does after its first call. */
+int blh_snapshot_reread(blh_snapshot *snap, const char *file);
 int blh_snapshot_view(const blh_snapshot *snap, bl_grid_view *view, double *time, double *plasma_gamma);
 void blh_snapshot_free(blh_snapshot *snap);
 

@@ -319,6 +319,39 @@ def test_iharm3d_reader(tmp_path, fmks, capfd):
         assert np.max(np.abs(got - ref)) <= tol * scale, (name, np.max(np.abs(got - ref)) / scale)
 
 
+@pytest.mark.parametrize('fmt', ['athena', 'athenak', 'iharm3d', 'harm3d'])
+def test_time_series_reread_equals_fresh_read(fmt, tmp_path):
+    """Second file of a time series read on top of the first (blh_snapshot_reread: the layout, variable positions and
+    adiabatic index of the first file are kept, as simulation_reader.cpp does after its first call) gives exactly the
+    arrays of reading that file alone, with its own time."""
+    from blacklight_b200 import mock_snapshot as ms
+    d = str(tmp_path)
+    files, kv = [], {}
+    for n, amp in enumerate((0.1, 0.3)):
+        f = os.path.join(d, 'mock.%d' % n)
+        if fmt == 'athena':
+            ms.write_athdf(f, ms.to_blocks(ms.mock_fields(n_r=16, n_th=8, n_ph=8, pert_amp=amp, pert_n_ph=1), (2, 1, 2)), time=5.0 * n)
+        elif fmt == 'athenak':
+            grid = ms.to_blocks(ms.mock_fields_cks(n=8), (2, 1, 1))
+            grid['prim'] = grid['prim'] * np.float32(1.0 + amp)
+            ms.write_athenak(f, grid, gamma_adi=1.5, time=5.0 * n, spin=0.5)
+            kv = {'simulation_coord': 'cks', 'simulation_a': '0.5'}
+        elif fmt == 'iharm3d':
+            ms.write_iharm3d(f, n_r=16, n_th=8, n_ph=8, gamma_adi=1.5, time=5.0 * n, hslope=0.7, pert_amp=amp, pert_n_ph=1)
+            kv = {'simulation_coord': 'sks'}
+        else:
+            ms.write_harm3d(f, ms.mock_fields(n_r=16, n_th=8, n_ph=8, pert_amp=amp, pert_n_ph=1), gamma_adi=1.5, time=5.0 * n)
+            kv = {'simulation_coord': 'sks'}
+        files.append(f)
+    cfg = _reader_case(tmp_path, fmt, files[0], kv)
+    first, fresh = bl.read_snapshot(cfg, files[0]), bl.read_snapshot(cfg, files[1])
+    again = bl.read_snapshot(cfg, files[0], then=files[1])
+    assert again['time'] == fresh['time'] == 5.0 and first['time'] == 0.0
+    assert not np.array_equal(first['prim'], fresh['prim'])
+    for k in ('prim', 'x1f', 'x2f', 'x3f', 'x1v', 'x2v', 'x3v', 'levels', 'locations'):
+        assert np.array_equal(again[k], fresh[k]), k
+
+
 def test_npz_writer_and_athdf_reader_through_driver_without_gpu(tmp_path):
     """blh_run_input_file must fail loudly without a GPU, after parsing the file."""
     import torch
