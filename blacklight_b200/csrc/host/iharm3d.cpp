@@ -42,27 +42,34 @@ double fmks_theta(const Metric &metric, double x1, double x2) {
   return theta_g + std::exp(metric.mks_smooth * (std::log(metric.r_in) - x1)) * (theta_j - theta_g);
 }
 
-// SetJacobianFactors (simulation_geometry.cpp:440-471)
-void jacobian(const Metric &metric, double x1, double x2, double *dr_dx1, double *dth_dx1, double *dth_dx2) {
-  *dr_dx1 = std::exp(x1);
-  if (metric.fmks) {
-    double var_a = std::exp(metric.mks_smooth * (std::log(metric.r_in) - x1));
-    double var_b = kPi * (0.5 - x2);
-    double var_c = std::pow((2.0 * x2 - 1.0) / metric.poly_xt, metric.poly_alpha);
-    double var_d = 1.0 + metric.poly_alpha;
-    double var_e = metric.poly_norm * (1.0 + var_c / var_d);
-    double var_f = var_e * (2.0 * x2 - 1.0);
-    double var_g = -0.5 * (1.0 - metric.h) * std::sin(2.0 * kPi * x2);
-    *dth_dx1 = -metric.mks_smooth * var_a * (var_b + var_f + var_g);
-    double var_h = kPi + (1.0 - metric.h) * kPi * std::cos(2.0 * kPi * x2);
-    double var_i = -kPi + 2.0 * var_e;
-    double var_j = 2.0 * metric.poly_norm * metric.poly_alpha * var_c / var_d;
-    double var_k = -(1.0 - metric.h) * kPi * std::cos(2.0 * kPi * x2);
-    *dth_dx2 = var_h + var_a * (var_i + var_j + var_k);
-  } else {
-    *dth_dx1 = 0.0;
-    *dth_dx2 = kPi + (1.0 - metric.h) * kPi * std::cos(2.0 * kPi * x2);
+// Jacobian of (r, theta) with respect to the native (x1, x2): dr/dx1 = r, and the two theta derivatives -- for MKS the
+// h-slope map only, for FMKS the blend theta_g + s (theta_j - theta_g), s = exp(smooth (ln r_in - x1)), of the h-slope
+// map theta_g and the polynomial map theta_j (values as simulation_geometry.cpp:440-471 evaluates them).
+struct Jacobian {
+  double dr_dx1, dth_dx1, dth_dx2;
+};
+
+Jacobian jacobian(const Metric &metric, double x1, double x2) {
+  Jacobian J;
+  J.dr_dx1 = std::exp(x1);
+  const double slope_cos = (1.0 - metric.h) * kPi * std::cos(2.0 * kPi * x2);   // d theta_g / d x2 - pi
+  if (!metric.fmks) {
+    J.dth_dx1 = 0.0;
+    J.dth_dx2 = kPi + slope_cos;
+    return J;
   }
+  const double y = 2.0 * x2 - 1.0;
+  const double blend = std::exp(metric.mks_smooth * (std::log(metric.r_in) - x1));
+  const double y_pow = std::pow(y / metric.poly_xt, metric.poly_alpha);
+  const double order = 1.0 + metric.poly_alpha;
+  const double poly = metric.poly_norm * (1.0 + y_pow / order);          // (theta_j - pi/2) / y
+  // theta_j - theta_g = pi (1/2 - x2) + poly y - (1 - h)/2 sin(2 pi x2)
+  const double gap = kPi * (0.5 - x2) + poly * y + -0.5 * (1.0 - metric.h) * std::sin(2.0 * kPi * x2);
+  J.dth_dx1 = -metric.mks_smooth * blend * gap;
+  // d(theta_j - theta_g)/dx2 = -pi + 2 poly + 2 norm alpha y^alpha / (1 + alpha) - (1 - h) pi cos(2 pi x2)
+  const double gap_dx2 = (-kPi + 2.0 * poly) + 2.0 * metric.poly_norm * metric.poly_alpha * y_pow / order + -slope_cos;
+  J.dth_dx2 = (kPi + slope_cos) + blend * gap_dx2;
+  return J;
 }
 
 // GenerateSKSMap (simulation_geometry.cpp:330-413): x2(r, theta) by bisection on a uniform (r, theta) lattice.  The
@@ -282,75 +289,80 @@ void read_iharm3d(const std::string &path, const std::string &kappa_name, bool r
   const float gm1 = static_cast<float>(expect.plasma_gamma - 1.0);
   for (size_t c = 0; c < cells; c++) g.prim[(size_t)g.ind_pgas * cells + c] *= gm1;
 
-  // ConvertPrimitives3 (simulation_geometry.cpp:95-236): modified normal-frame velocity and lab-frame field ->
-  // standard spherical Kerr-Schild normal-frame velocity and coordinate-frame field
+  // Vector primitives (ConvertPrimitives3, simulation_geometry.cpp:95-236): the dump holds the normal-frame velocity
+  // u~^i and the lab-frame field B^i on the native coordinate basis.  Per cell: native metric from the spherical
+  // Kerr-Schild one through the Jacobian, u~ -> four-velocity, B -> magnetic four-vector, both pushed to the
+  // (t, r, theta, phi) basis, then back to normal-frame velocity and B^i = b^i u^t - b^t u^i there.
   const double a = expect.simulation_a;
   const Metric m = metric;                       // the parallel region's threads have their own thread_locals
   const std::vector<double> &x2_mod = x2v_mod;
+  const int vel[3] = {g.ind_uu1, g.ind_uu2, g.ind_uu3}, mag[3] = {g.ind_bb1, g.ind_bb2, g.ind_bb3};
 #pragma omp parallel for schedule(static) collapse(2)
   for (int k = 0; k < n3; k++)
     for (int j = 0; j < n2; j++)
       for (int i = 0; i < n1; i++) {
-        double r = g.x1v[(size_t)i], th = g.x2v[(size_t)j], x1, x2;
-        if (!m.fmks) {
-          x1 = std::log(r);
-          x2 = x2_mod[(size_t)j];
-        } else {
-          x1 = r;
-          x2 = th;
+        // the cell's native and spherical coordinates
+        double x1, x2, r, th;
+        if (m.fmks) {
+          x1 = g.x1v[(size_t)i];
+          x2 = g.x2v[(size_t)j];
           r = std::exp(x1);
           th = fmks_theta(m, x1, x2);
+        } else {
+          r = g.x1v[(size_t)i];
+          th = g.x2v[(size_t)j];
+          x1 = std::log(r);
+          x2 = x2_mod[(size_t)j];
         }
-        double sth = std::sin(th), cth = std::cos(th);
-        double uu1 = at(g.ind_uu1, k, j, i), uu2 = at(g.ind_uu2, k, j, i), uu3 = at(g.ind_uu3, k, j, i);
-        double bb1 = at(g.ind_bb1, k, j, i), bb2 = at(g.ind_bb2, k, j, i), bb3 = at(g.ind_bb3, k, j, i);
-        double dr_dx1, dth_dx1, dth_dx2;
-        jacobian(m, x1, x2, &dr_dx1, &dth_dx1, &dth_dx2);
-        double sigma = r * r + a * a * cth * cth;
-        double f = 2.0 * r / sigma;
-        double g_tr = f, g_tth = 0.0, g_tph = -a * f * sth * sth;
-        double g_rr = 1.0 + f, g_rth = 0.0, g_rph = -a * (1.0 + f) * sth * sth;
-        double g_thth = sigma, g_thph = 0.0;
-        double g_phph = (r * r + a * a + a * a * f * sth * sth) * sth * sth;
-        double gtt = -(1.0 + f), gtr = f, gtth = 0.0, gtph = 0.0;
-        double alpha = 1.0 / std::sqrt(-gtt);
-        double g_01 = dr_dx1 * g_tr + dth_dx1 * g_tth;
-        double g_02 = dth_dx2 * g_tth;
-        double g_03 = g_tph;
-        double g_11 = dr_dx1 * dr_dx1 * g_rr + 2.0 * dr_dx1 * dth_dx1 * g_rth + dth_dx1 * dth_dx1 * g_thth;
-        double g_12 = dr_dx1 * dth_dx2 * g_rth + dth_dx1 * dth_dx2 * g_thth;
-        double g_13 = dr_dx1 * g_rph + dth_dx1 * g_thph;
-        double g_22 = dth_dx2 * dth_dx2 * g_thth;
-        double g_23 = dth_dx2 * g_thph;
-        double g_33 = g_phph;
-        double g00 = gtt;
-        double g01 = gtr / dr_dx1;
-        double g02 = g_tth / dth_dx2 - dth_dx1 * g_tr / (dr_dx1 * dth_dx2);
-        double g03 = gtph;
-        double alpha_mod = 1.0 / std::sqrt(-g00);
-        double uu0 = std::sqrt(1.0 + g_11 * uu1 * uu1 + 2.0 * g_12 * uu1 * uu2 + 2.0 * g_13 * uu1 * uu3 + g_22 * uu2 * uu2 +
-                               2.0 * g_23 * uu2 * uu3 + g_33 * uu3 * uu3);
-        double u0 = uu0 / alpha_mod;
-        double u1 = uu1 - alpha_mod * g01 * uu0;
-        double u2 = uu2 - alpha_mod * g02 * uu0;
-        double u3 = uu3 - alpha_mod * g03 * uu0;
-        double u_1 = g_01 * u0 + g_11 * u1 + g_12 * u2 + g_13 * u3;
-        double u_2 = g_02 * u0 + g_12 * u1 + g_22 * u2 + g_23 * u3;
-        double u_3 = g_03 * u0 + g_13 * u1 + g_23 * u2 + g_33 * u3;
-        double ut = u0, ur = dr_dx1 * u1, uth = dth_dx1 * u1 + dth_dx2 * u2, uph = u3;
-        double uur = ur + alpha * alpha * gtr * ut;
-        double uuth = uth + alpha * alpha * gtth * ut;
-        double uuph = uph + alpha * alpha * gtph * ut;
-        double b0 = u_1 * bb1 + u_2 * bb2 + u_3 * bb3;
-        double b1 = (bb1 + b0 * u1) / u0, b2 = (bb2 + b0 * u2) / u0, b3 = (bb3 + b0 * u3) / u0;
-        double bt = b0, br = dr_dx1 * b1, bth = dth_dx1 * b1 + dth_dx2 * b2, bph = b3;
-        double bbr = br * ut - bt * ur, bbth = bth * ut - bt * uth, bbph = bph * ut - bt * uph;
-        at(g.ind_uu1, k, j, i) = static_cast<float>(uur);
-        at(g.ind_uu2, k, j, i) = static_cast<float>(uuth);
-        at(g.ind_uu3, k, j, i) = static_cast<float>(uuph);
-        at(g.ind_bb1, k, j, i) = static_cast<float>(bbr);
-        at(g.ind_bb2, k, j, i) = static_cast<float>(bbth);
-        at(g.ind_bb3, k, j, i) = static_cast<float>(bbph);
+        const Jacobian J = jacobian(m, x1, x2);
+        const double s2 = std::sin(th) * std::sin(th), c2 = std::cos(th) * std::cos(th);
+        // spherical Kerr-Schild metric, spatial part and time row (indices r, theta, phi), and g^{tt}, g^{tr}
+        const double sigma = r * r + a * a * c2, f = 2.0 * r / sigma;
+        const double time_row[3] = {f, 0.0, -a * f * s2};
+        const double space[3][3] = {{1.0 + f, 0.0, -a * (1.0 + f) * s2},
+                                    {0.0, sigma, 0.0},
+                                    {-a * (1.0 + f) * s2, 0.0, (r * r + a * a + a * a * f * s2) * s2}};
+        const double con_tt = -(1.0 + f), con_tr = f;
+        // native basis vectors in spherical components: e_1 = (dr/dx1, dth/dx1, 0), e_2 = (0, dth/dx2, 0), e_3 = phi
+        const double e[3][3] = {{J.dr_dx1, J.dth_dx1, 0.0}, {0.0, J.dth_dx2, 0.0}, {0.0, 0.0, 1.0}};
+        double nat_time[3], nat[3][3];
+        for (int p = 0; p < 3; p++) {
+          nat_time[p] = 0.0;
+          for (int q = 0; q < 3; q++) nat_time[p] += e[p][q] * time_row[q];
+          for (int q = 0; q < 3; q++) {
+            nat[p][q] = 0.0;
+            for (int u = 0; u < 3; u++)
+              for (int v = 0; v < 3; v++) nat[p][q] += e[p][u] * e[q][v] * space[u][v];
+          }
+        }
+        // native g^{0i} / (-g^{00}) is the shift; g^{00} is a scalar under the spatial change of coordinates
+        const double lapse = 1.0 / std::sqrt(-con_tt);
+        const double con_0[3] = {con_tr / J.dr_dx1, -J.dth_dx1 * f / (J.dr_dx1 * J.dth_dx2), 0.0};
+        double uu[3], bb[3];
+        for (int p = 0; p < 3; p++) {
+          uu[p] = at(vel[p], k, j, i);
+          bb[p] = at(mag[p], k, j, i);
+        }
+        double norm = 1.0;
+        for (int p = 0; p < 3; p++)
+          for (int q = 0; q < 3; q++) norm += nat[p][q] * uu[p] * uu[q];
+        const double gamma = std::sqrt(norm);
+        double u[4] = {gamma / lapse, 0.0, 0.0, 0.0}, u_low[3], b[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int p = 0; p < 3; p++) u[p + 1] = uu[p] - lapse * con_0[p] * gamma;
+        for (int p = 0; p < 3; p++) {
+          u_low[p] = nat_time[p] * u[0];
+          for (int q = 0; q < 3; q++) u_low[p] += nat[p][q] * u[q + 1];
+          b[0] += u_low[p] * bb[p];
+        }
+        for (int p = 0; p < 3; p++) b[p + 1] = (bb[p] + b[0] * u[p + 1]) / u[0];
+        // to the (r, theta, phi) basis: v^r = dr/dx1 v^1, v^theta = dth/dx1 v^1 + dth/dx2 v^2, v^phi = v^3
+        const double us[3] = {J.dr_dx1 * u[1], J.dth_dx1 * u[1] + J.dth_dx2 * u[2], u[3]};
+        const double bs[3] = {J.dr_dx1 * b[1], J.dth_dx1 * b[1] + J.dth_dx2 * b[2], b[3]};
+        const double shift[3] = {lapse * lapse * con_tr, 0.0, 0.0};   // alpha^2 g^{ti}; g^{t theta} = g^{t phi} = 0
+        for (int p = 0; p < 3; p++) {
+          at(vel[p], k, j, i) = static_cast<float>(us[p] + shift[p] * u[0]);
+          at(mag[p], k, j, i) = static_cast<float>(bs[p] * u[0] - b[0] * us[p]);
+        }
       }
 }
 
