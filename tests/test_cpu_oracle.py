@@ -197,3 +197,40 @@ def test_oracle_nonthermal_electrons(fixture, over, tmp_path):
     # and it differs from the purely thermal image, i.e. the non-thermal terms are exercised
     thermal = np.load(os.path.join(GOLDEN, 'simulation_32.npz'))['I_nu']
     assert abs(np.nanmax(ref) / np.nanmax(thermal) - 1.0) > 0.01
+
+
+def test_refinement_restatement_against_reference_fixture(tmp_path):
+    """Adaptive refinement decision (EvaluateBlock, radiation_adaptive.cpp:163-312; child order camera.cpp:445-459): the
+    numpy restatement applied to the unmodified reference's level-0 image reproduces the reference's list of level-1
+    blocks -- and the host layer's blh_camera_refined derives the same list from those flags."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import refine_oracle
+    base, over, _ = CASES['adaptive_32']
+    kv = load_input(base)
+    kv.update({k: str(v) for k, v in over.items()})
+    gold = np.load(os.path.join(GOLDEN, 'adaptive_32.npz'))
+    res, bs = int(kv['camera_resolution']), int(kv['adaptive_block_size'])
+    nb = res // bs
+    locs = np.array([[v, u] for v in range(nb) for u in range(nb)], np.int32)
+    blocks = gold['I_nu'].reshape(nb, bs, nb, bs).transpose(0, 2, 1, 3).reshape(nb * nb, bs, bs)
+    flags = refine_oracle.refinement_flags(blocks, locs, 0, kv)
+    assert int(flags.sum()) * 4 == int(gold['adaptive_num_blocks'][1]) == len(gold['adaptive_block_locs_1'])
+    assert np.array_equal(refine_oracle.child_locs(locs, flags), gold['adaptive_block_locs_1'])
+    path = os.path.join(tmp_path, 'a.input')
+    write_input(path, kv)
+    kids, _, _, _ = bl.Config(path).camera_refined(1, locs, flags)
+    assert np.array_equal(kids, gold['adaptive_block_locs_1'])
+    # every criterion of the restatement runs: make each the only active one on a block with a known answer
+    ramp = np.add.outer(np.arange(8.0), 2.0 * np.arange(8.0)) + 1.0
+    off = {k: '-1.0' for k in ('adaptive_val_frac', 'adaptive_abs_grad_frac', 'adaptive_rel_grad_frac',
+                               'adaptive_abs_lapl_frac', 'adaptive_rel_lapl_frac')}
+    for key, cut, image, want in (('val', 10.0, ramp, True), ('val', 100.0, ramp, False),
+                                  ('abs_grad', 2.0, ramp, True), ('abs_grad', 3.0, ramp, False),
+                                  ('rel_grad', 0.05, ramp, True), ('abs_lapl', 1e-9, ramp, False),
+                                  ('abs_lapl', 1.0, ramp ** 2, True), ('rel_lapl', 1e-3, ramp ** 2, True),
+                                  ('rel_lapl', 10.0, ramp ** 2, False)):
+        k2 = dict(kv, **off)
+        k2['adaptive_%s_frac' % key], k2['adaptive_%s_cut' % key] = '0.5', str(cut)
+        assert refine_oracle.evaluate_block(image, k2) is want, (key, cut)
+    assert refine_oracle.evaluate_block(np.full((8, 8), np.nan), dict(kv, adaptive_val_frac='0.0')) is False
