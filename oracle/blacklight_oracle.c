@@ -18,7 +18,7 @@
  *   kappa-distribution I coefficients and constants        simulation_coefficients.cpp:82-105, 608-653, 740-773
  *   Cartesian Kerr-Schild grids (simulation_coord = cks)   radiation_geometry.cpp:37-57, 425-457
  *   fluid-frame tetrad                                     radiation_geometry.cpp:597-658
- *   unpolarized transfer                                   unpolarized.cpp:31-221
+ *   unpolarized transfer, auxiliary images (formula model) unpolarized.cpp:31-221
  * Build: gcc -O2 -ffp-contract=off (no FMA contraction, like the reference's -O3 without -march).
  */
 #include <math.h>
@@ -297,24 +297,14 @@ typedef struct {
   int fallback_nan;
 } orc_formula;
 
-/* image: (F, n_rays).  Samples in the layout orc_trace_dp produces. */
-void orc_formula_image(const orc_formula *P, long n_rays, int cap, const int *num, const unsigned char *flags,
-                       const double *pos, const double *dir, const double *len, const double *mom_factor,
-                       int F, const double *freqs, double *image) {
-  long m;
-#pragma omp parallel for schedule(dynamic, 4)
-  for (m = 0; m < n_rays; m++) {
-    int l, n;
-    for (l = 0; l < F; l++) {
-      double I = 0.0;
-      for (n = 0; n < num[m]; n++) {
-        size_t o = (size_t)m * cap + n;
-        double x = pos[4 * o + 1], y = pos[4 * o + 2], z = pos[4 * o + 3];
-        const double *k = dir + 4 * o;
-        double j = 0.0, al = 0.0;
-        double dl_cgs = len[o] * P->x_unit / (freqs[l] * mom_factor[m]);
-        if (P->fallback_nan && flags[m]) {
-          if (l == 0) j = al = NAN;
+/* j / nu^2 and alpha nu of one sample (formula_coefficients.cpp:25-183); zero for samples beyond the camera radius */
+static void formula_j_alpha(const orc_formula *P, double x, double y, double z, const double *k, double freq, double mom,
+                            int flagged, int l, double *j_out, double *al_out) {
+  *j_out = 0.0;
+  *al_out = 0.0;
+  {
+        if (P->fallback_nan && flagged) {
+          if (l == 0) *j_out = *al_out = NAN;
         } else {
           double a = P->a, r = ks_radius(a, x, y, z);
           if (!(r > P->camera_r)) {
@@ -336,16 +326,92 @@ void orc_formula_image(const orc_formula *P, long n_rays, int cap, const int *nu
             double u2 = sth * sph * ur + cth * (r * sph + a * cph) * uth + sth * (r * cph - a * sph) * uph;
             double u3 = cth * ur - r * sth * uth;
             double nn0 = exp(-0.5 * (r * r / (P->r0 * P->r0) + P->h * P->h * cth * cth));
-            double nu = -(u0 * k[0] + u1 * k[1] + u2 * k[2] + u3 * k[3]) * freqs[l] * mom_factor[m];
+            double nu = -(u0 * k[0] + u1 * k[1] + u2 * k[2] + u3 * k[3]) * freq * mom;
             double jn = P->cn0 * nn0 * pow(nu / P->nup, -P->alpha);
-            j = jn / (nu * nu);
+            *j_out = jn / (nu * nu);
             double an = P->abs_a * P->cn0 * nn0 * pow(nu / P->nup, -P->beta - P->alpha);
-            al = an * nu;
+            *al_out = an * nu;
           }
         }
+  }
+}
+
+/* image: (F, n_rays).  Samples in the layout orc_trace_dp produces. */
+void orc_formula_image(const orc_formula *P, long n_rays, int cap, const int *num, const unsigned char *flags,
+                       const double *pos, const double *dir, const double *len, const double *mom_factor,
+                       int F, const double *freqs, double *image) {
+  long m;
+#pragma omp parallel for schedule(dynamic, 4)
+  for (m = 0; m < n_rays; m++) {
+    int l, n;
+    for (l = 0; l < F; l++) {
+      double I = 0.0;
+      for (n = 0; n < num[m]; n++) {
+        size_t o = (size_t)m * cap + n;
+        double j, al, dl_cgs = len[o] * P->x_unit / (freqs[l] * mom_factor[m]);
+        formula_j_alpha(P, pos[4 * o + 1], pos[4 * o + 2], pos[4 * o + 3], dir + 4 * o, freqs[l], mom_factor[m], flags[m], l, &j, &al);
         I = transfer_step(I, j, al, dl_cgs);
       }
       image[(size_t)l * n_rays + m] = I * (freqs[l] * freqs[l] * freqs[l]);
+    }
+  }
+}
+
+/* Auxiliary images of the formula model (unpolarized.cpp:60-185): earliest coordinate time [s], proper length [cm],
+ * affine length, integrated emissivity and optical depth per frequency, and the number of crossings of the plane through
+ * the origin normal to the camera position.  time, length, crossings: (n_rays); lambda, emission, tau: (F, n_rays). */
+void orc_formula_aux(const orc_formula *P, long n_rays, int cap, const int *num, const unsigned char *flags,
+                     const double *pos, const double *dir, const double *len, const double *mom_factor, int F,
+                     const double *freqs, const double *camera_x, double *time, double *length, double *lambda,
+                     double *emission, double *tau, double *crossings) {
+  const double t_unit = P->x_unit / 2.99792458e10;
+  orc_geo geo;
+  long m;
+  memset(&geo, 0, sizeof geo);
+  geo.a = P->a;
+#pragma omp parallel for schedule(dynamic, 4)
+  for (m = 0; m < n_rays; m++) {
+    int l, n, a, b, mu;
+    for (l = 0; l < F; l++) {
+      double sum_lambda = 0.0, sum_emission = 0.0, sum_tau = 0.0, earliest = 0.0, proper = 0.0;
+      int count = 0, sign = 0;
+      if (num[m] > 0) {
+        size_t o0 = (size_t)m * cap;
+        sign = camera_x[1] * pos[4 * o0 + 1] + camera_x[2] * pos[4 * o0 + 2] + camera_x[3] * pos[4 * o0 + 3] > 0.0;
+      }
+      for (n = 0; n < num[m]; n++) {
+        size_t o = (size_t)m * cap + n;
+        double x = pos[4 * o + 1], y = pos[4 * o + 2], z = pos[4 * o + 3];
+        const double *k = dir + 4 * o;
+        double j, al, dl_cgs = len[o] * P->x_unit / (freqs[l] * mom_factor[m]);
+        formula_j_alpha(P, x, y, z, k, freqs[l], mom_factor[m], flags[m], l, &j, &al);
+        sum_lambda += dl_cgs;
+        sum_emission += j * dl_cgs;
+        sum_tau += al * dl_cgs;
+        if (l == 0) {
+          double gcov[4][4], gcon[4][4], t[4] = {0, 0, 0, 0}, sq = 0.0, t_cgs = pos[4 * o] * t_unit;
+          int now;
+          earliest = t_cgs < earliest ? t_cgs : earliest;   /* std::min(image, t_cgs), image starting at 0 */
+          metric_cov(&geo, x, y, z, gcov);
+          metric_con(&geo, x, y, z, gcon);
+          for (a = 1; a < 4; a++)
+            for (mu = 0; mu < 4; mu++) t[a] += (gcon[a][mu] - gcon[0][a] * gcon[0][mu] / gcon[0][0]) * k[mu];
+          for (a = 1; a < 4; a++)
+            for (b = 1; b < 4; b++) sq += gcov[a][b] * t[a] * t[b];
+          proper += sqrt(sq) * len[o] * P->x_unit;
+          now = camera_x[1] * x + camera_x[2] * y + camera_x[3] * z > 0.0;
+          if (now != sign) count++;
+          sign = now;
+        }
+      }
+      lambda[(size_t)l * n_rays + m] = sum_lambda;
+      emission[(size_t)l * n_rays + m] = sum_emission;
+      tau[(size_t)l * n_rays + m] = sum_tau;
+      if (l == 0) {
+        time[m] = earliest;
+        length[m] = proper;
+        crossings[m] = (double)count;
+      }
     }
   }
 }

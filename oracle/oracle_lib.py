@@ -81,6 +81,26 @@ def formula_image(kv, s, mom, freqs):
     return image
 
 
+def formula_aux(kv, s, mom, freqs, camera_x):
+    """Auxiliary images of the formula model: dict(time, length, crossings: (n); lambda, emission, tau: (F, n))."""
+    a = float(kv['formula_spin'])
+    mass_msun = float(kv['formula_mass']) * C * C / GG_MSUN
+    P = Formula(a=a, camera_r=float(kv['camera_r']), x_unit=GG_MSUN * mass_msun / (C * C), r0=float(kv['formula_r0']),
+                h=float(kv['formula_h']), l0=float(kv['formula_l0']), q=float(kv['formula_q']), nup=float(kv['formula_nup']),
+                cn0=float(kv['formula_cn0']), alpha=float(kv['formula_alpha']), abs_a=float(kv['formula_a']),
+                beta=float(kv['formula_beta']), fallback_nan=int(kv['fallback_nan'] == 'true'))
+    n, F = len(mom), len(freqs)
+    out = {k: np.zeros(n) for k in ('time', 'length', 'crossings')}
+    out.update({k: np.zeros((F, n)) for k in ('lambda', 'emission', 'tau')})
+    freqs = np.ascontiguousarray(freqs, np.float64)
+    cam = np.ascontiguousarray(camera_x, np.float64)
+    lib().orc_formula_aux(ctypes.byref(P), ctypes.c_long(n), s['cap'], _p(s['num']), _p(s['flags']), _p(s['pos']),
+                          _p(s['dir']), _p(s['len']), _p(np.ascontiguousarray(mom)), F, _p(freqs), _p(cam),
+                          _p(out['time']), _p(out['length']), _p(out['lambda']), _p(out['emission']), _p(out['tau']),
+                          _p(out['crossings']))
+    return out
+
+
 def simulation_image(kv, s, mom, grid, want_inds=True):
     a = float(kv['simulation_a'])
     P = Sim(a=a, camera_r=float(kv['camera_r']), x_unit=GG_MSUN * float(kv['simulation_m_msun']) / (C * C),

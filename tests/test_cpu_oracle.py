@@ -139,6 +139,25 @@ def test_fmks_table_and_zone_lookup_against_reference_checkpoint(tmp_path):
     assert np.array_equal(fracs[:, 2], frac_i) and np.array_equal(fracs[:, 1], frac_j)
 
 
+def test_oracle_formula_auxiliary_images(tmp_path):
+    """Auxiliary images of the formula model (time, length, lambda, emission, tau, crossings; unpolarized.cpp:60-185)
+    restated in C against the unmodified reference's fixture."""
+    kv, cfg, gold, _ = setup('formula_aux_12', tmp_path)
+    pos, dirs, fac = cfg.camera_root()
+    s = oracle_lib.trace(kv, float(kv['formula_spin']), pos, dirs)
+    check_samples(s, gold)
+    aux = oracle_lib.formula_aux(kv, s, fac, gold['frequency'], cfg.camera_frame()['cam_x'])
+    res = cfg.resolution
+    for name in ('time', 'length', 'lambda', 'emission', 'tau', 'crossings'):
+        ref = gold[name]
+        got = (aux[name][0] if aux[name].ndim == 2 else aux[name]).reshape(res, res)
+        assert np.array_equal(np.isnan(got), np.isnan(ref)), name
+        ok = ~np.isnan(ref)
+        scale = np.maximum(np.maximum(np.abs(ref[ok]), 1e-12 * np.nanmax(np.abs(ref))), 1e-300)   # tau is 0 here: no absorption
+        assert np.max(np.abs(got[ok] - ref[ok]) / scale) < 1e-11, name
+    assert np.nanmax(gold['crossings']) >= 1 and np.nanmin(gold['time']) < 0.0
+
+
 @pytest.mark.parametrize('name', ['iharm3d_mks_16', 'harm3d_16', 'athenak_16'])
 def test_readers_through_the_restatement_against_reference_fixtures(name, tmp_path):
     """Host readers without a GPU: the arrays our iharm3d / harm3d / AthenaK readers hand to bl_upload_grid (coordinates
