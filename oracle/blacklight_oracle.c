@@ -18,7 +18,7 @@
  *   kappa-distribution I coefficients and constants        simulation_coefficients.cpp:82-105, 608-653, 740-773
  *   Cartesian Kerr-Schild grids (simulation_coord = cks)   radiation_geometry.cpp:37-57, 425-457
  *   fluid-frame tetrad                                     radiation_geometry.cpp:597-658
- *   unpolarized transfer, auxiliary images (formula model) unpolarized.cpp:31-221
+ *   unpolarized transfer, auxiliary images (both models)   unpolarized.cpp:31-221
  * Build: gcc -O2 -ffp-contract=off (no FMA contraction, like the reference's -O3 without -march).
  */
 #include <math.h>
@@ -490,11 +490,15 @@ static void tetrad(const double ucon[4], const double ucov[4], const double kcon
 }
 
 /* Per-sample thermal coefficients + transfer on an SKS grid.  image: (n_rays); inds out: (n_rays,cap,4) or NULL
- * (entries of cut / off-grid samples are left at -1).  One frequency, ti_te_beta model with plasma_use_p. */
+ * (entries of cut / off-grid samples are left at -1).  One frequency, ti_te_beta model with plasma_use_p.
+ * aux (with camera_x), optional: (27, n_rays) auxiliary images in the order time, length, lambda, emission, tau,
+ * crossings, lambda_ave[7], emission_ave[7], tau_int[7] over the cell values rho, n_e, p_gas, Theta_e, B, sigma,
+ * 1/beta (unpolarized.cpp:60-200; cell values simulation_coefficients.cpp:376-387). */
 void orc_simulation_image(const orc_sim *P, long n_rays, int cap, const int *num, const unsigned char *flags,
                           const double *pos, const double *dir, const double *len, const double *mom_factor,
                           double freq, const double *x1f, const double *x2f, const double *x3f, const double *x1v,
-                          const double *x2v, const double *x3v, const float *prim, double *image, int *inds) {
+                          const double *x2v, const double *x3v, const float *prim, double *image, int *inds,
+                          const double *camera_x, double *aux) {
   const double c = 2.99792458e10, hpl = 6.62607015e-27, m_p = 1.67262192369e-24, m_e = 9.1093837015e-28, qe = 4.80320425e-10;
   const double e_unit = P->d_unit * c * c, b_unit = sqrt(4.0 * PI * e_unit);
   orc_geo geo;
@@ -506,8 +510,16 @@ void orc_simulation_image(const orc_sim *P, long n_rays, int cap, const int *num
     int n, b = 0, i, j, k, mu, nu_;
     double I = 0.0;
     int n_i = P->n_i, n_j = P->n_j, n_k = P->n_k;
+    double a_time = 0.0, a_length = 0.0, a_lambda = 0.0, a_emission = 0.0, a_tau = 0.0, a_lave[7], a_eave[7], a_tint[7];
+    int a_cross = 0, a_sign = 0;
+    for (i = 0; i < 7; i++) a_lave[i] = a_eave[i] = a_tint[i] = 0.0;
+    if (aux && num[m] > 0) {
+      size_t o0 = (size_t)m * cap;
+      a_sign = camera_x[1] * pos[4 * o0 + 1] + camera_x[2] * pos[4 * o0 + 2] + camera_x[3] * pos[4 * o0 + 3] > 0.0;
+    }
     for (n = 0; n < num[m]; n++) {
       size_t o = (size_t)m * cap + n;
+      double cv[7] = {NAN, NAN, NAN, NAN, NAN, NAN, NAN};
       double x = pos[4 * o + 1], y = pos[4 * o + 2], z = pos[4 * o + 3];
       const double *kcov = dir + 4 * o;
       double dl_cgs = len[o] * P->x_unit / (freq * mom_factor[m]);
@@ -608,6 +620,7 @@ void orc_simulation_image(const orc_sim *P, long n_rays, int cap, const int *num
         double kb_te = (1.0 + P->ne_ni) / (tti_tte + P->ne_ni) * kb_tot;
         double theta_e = kb_te / (m_e * c * c);
         int cut = P->cut_sigma_max >= 0.0 && sig > P->cut_sigma_max;
+        if (!cut) { cv[0] = rho_cgs; cv[1] = n_e; cv[2] = pgas_cgs; cv[3] = theta_e; cv[4] = bb_cgs; cv[5] = sig; cv[6] = beta_inv; }
         if (!cut && !(bb[0] == 0.0 && bb[1] == 0.0 && bb[2] == 0.0)) {
           /* to CKS, tetrad, pitch angle (simulation_coefficients.cpp:397-455) */
           double sth = sqrt(1.0 - cth * cth), ph = atan2(y, x) - atan(a / r), sph = sin(ph), cph = cos(ph);
@@ -693,7 +706,42 @@ void orc_simulation_image(const orc_sim *P, long n_rays, int cap, const int *num
         }
       }
       I = transfer_step(I, jv, av, dl_cgs);
+      if (aux) {
+        double gcov[4][4], gcon[4][4], t[4] = {0, 0, 0, 0}, sq = 0.0, t_cgs = pos[4 * o] * (P->x_unit / c);
+        double dtau = av * dl_cgs, e_neg = exp(-dtau), e_m1 = expm1(dtau);
+        int aa, bb_, now;
+        a_time = t_cgs < a_time ? t_cgs : a_time;
+        metric_cov(&geo, x, y, z, gcov);
+        metric_con(&geo, x, y, z, gcon);
+        for (aa = 1; aa < 4; aa++)
+          for (mu = 0; mu < 4; mu++) t[aa] += (gcon[aa][mu] - gcon[0][aa] * gcon[0][mu] / gcon[0][0]) * kcov[mu];
+        for (aa = 1; aa < 4; aa++)
+          for (bb_ = 1; bb_ < 4; bb_++) sq += gcov[aa][bb_] * t[aa] * t[bb_];
+        a_length += sqrt(sq) * len[o] * P->x_unit;
+        a_lambda += dl_cgs;
+        a_emission += jv * dl_cgs;
+        a_tau += dtau;
+        if (!isnan(cv[0]))
+          for (aa = 0; aa < 7; aa++) {
+            a_lave[aa] += cv[aa] * dl_cgs;
+            a_eave[aa] += cv[aa] * jv * dl_cgs;
+            a_tint[aa] = dtau <= 100.0 ? e_neg * (a_tint[aa] + cv[aa] * e_m1) : cv[aa];
+          }
+        now = camera_x[1] * x + camera_x[2] * y + camera_x[3] * z > 0.0;
+        if (now != a_sign) a_cross++;
+        a_sign = now;
+      }
     }
     image[m] = I * (freq * freq * freq);
+    if (aux) {
+      size_t N = (size_t)n_rays;
+      aux[0 * N + m] = a_time; aux[1 * N + m] = a_length; aux[2 * N + m] = a_lambda; aux[3 * N + m] = a_emission;
+      aux[4 * N + m] = a_tau; aux[5 * N + m] = (double)a_cross;
+      for (i = 0; i < 7; i++) {
+        aux[(6 + i) * N + m] = a_lave[i] / a_lambda;
+        aux[(13 + i) * N + m] = a_eave[i] / a_emission;
+        aux[(20 + i) * N + m] = a_tint[i];
+      }
+    }
   }
 }

@@ -101,7 +101,13 @@ def formula_aux(kv, s, mom, freqs, camera_x):
     return out
 
 
-def simulation_image(kv, s, mom, grid, want_inds=True):
+AUX_NAMES = ['time', 'length', 'lambda', 'emission', 'tau', 'crossings'] + \
+            [p + c for p in ('lambda_ave_', 'emission_ave_', 'tau_int_')
+             for c in ('rho', 'n_e', 'p_gas', 'Theta_e', 'B', 'sigma', 'beta_inverse')]
+
+
+def simulation_image(kv, s, mom, grid, want_inds=True, camera_x=None):
+    """camera_x given: also the 27 auxiliary images, returned as a dict name -> (n) array in place of the indices."""
     a = float(kv['simulation_a'])
     P = Sim(a=a, camera_r=float(kv['camera_r']), x_unit=GG_MSUN * float(kv['simulation_m_msun']) / (C * C),
             n_b=grid['n_b'], n_k=grid['n_k'], n_j=grid['n_j'], n_i=grid['n_i'], interp=int(kv['simulation_interp'] == 'true'),
@@ -115,8 +121,12 @@ def simulation_image(kv, s, mom, grid, want_inds=True):
     n = len(mom)
     image = np.zeros(n)
     inds = np.full((n, s['cap'], 4), -1, np.int32) if want_inds else None
+    aux = np.zeros((27, n)) if camera_x is not None else None
     keep = [np.ascontiguousarray(grid[k]) for k in ('x1f', 'x2f', 'x3f', 'x1v', 'x2v', 'x3v', 'prim')]
     lib().orc_simulation_image(ctypes.byref(P), ctypes.c_long(n), s['cap'], _p(s['num']), _p(s['flags']), _p(s['pos']),
                                _p(s['dir']), _p(s['len']), _p(np.ascontiguousarray(mom)), ctypes.c_double(float(kv['image_frequency'])),
-                               *[_p(k) for k in keep], _p(image), _p(inds))
+                               *[_p(k) for k in keep], _p(image), _p(inds),
+                               _p(None if camera_x is None else np.ascontiguousarray(camera_x, np.float64)), _p(aux))
+    if aux is not None:
+        return image, dict(zip(AUX_NAMES, aux))
     return image, inds

@@ -158,6 +158,29 @@ def test_oracle_formula_auxiliary_images(tmp_path):
     assert np.nanmax(gold['crossings']) >= 1 and np.nanmin(gold['time']) < 0.0
 
 
+def test_oracle_simulation_auxiliary_images(tmp_path):
+    """All 27 auxiliary images of the simulation model -- time, length, lambda, emission, tau, crossings and the
+    lambda- / emission-averaged and tau-integrated cell values (rho, n_e, p_gas, Theta_e, B, sigma, 1/beta;
+    unpolarized.cpp:60-200, simulation_coefficients.cpp:376-387) -- restated in C against the reference's fixture."""
+    kv, cfg, gold, mock = setup('simulation_aux_16', tmp_path)
+    grid = mock_snapshot.grid_view_arrays(mock_snapshot.make_mock(None))
+    pos, dirs, fac = cfg.camera_root()
+    s = oracle_lib.trace(kv, float(kv['simulation_a']), pos, dirs)
+    check_samples(s, gold)
+    image, aux = oracle_lib.simulation_image(kv, s, fac, grid, want_inds=False, camera_x=cfg.camera_frame()['cam_x'])
+    res = cfg.resolution
+    worst = {}
+    for name in ['I_nu'] + oracle_lib.AUX_NAMES:
+        ref = gold[name]
+        got = (image if name == 'I_nu' else aux[name]).reshape(res, res)
+        assert np.array_equal(np.isnan(got), np.isnan(ref)), name
+        ok = ~np.isnan(ref)
+        scale = np.maximum(np.maximum(np.abs(ref[ok]), 1e-12 * np.nanmax(np.abs(ref))), 1e-300)
+        worst[name] = float(np.max(np.abs(got[ok] - ref[ok]) / scale))
+        assert worst[name] < 1e-9, (name, worst[name])
+    assert np.nanmax(gold['tau']) > 0.0 and np.nanmax(gold['tau_int_Theta_e']) > 0.0
+
+
 @pytest.mark.parametrize('name', ['iharm3d_mks_16', 'harm3d_16', 'athenak_16'])
 def test_readers_through_the_restatement_against_reference_fixtures(name, tmp_path):
     """Host readers without a GPU: the arrays our iharm3d / harm3d / AthenaK readers hand to bl_upload_grid (coordinates
