@@ -158,6 +158,26 @@ def test_oracle_formula_auxiliary_images(tmp_path):
     assert np.nanmax(gold['crossings']) >= 1 and np.nanmin(gold['time']) < 0.0
 
 
+def test_oracle_true_color_frequencies(tmp_path):
+    """BASELINE config 5 (true-colour): ten unpolarized frequencies on one set of geodesics; the restatement, run once
+    per frequency of the reference's own frequency list, against the reference's multi-frequency fixture."""
+    kv, cfg, gold, mock = setup('true_color_16', tmp_path)
+    grid = mock_snapshot.grid_view_arrays(mock_snapshot.make_mock(None))
+    pos, dirs, fac = cfg.camera_root()
+    s = oracle_lib.trace(kv, float(kv['simulation_a']), pos, dirs)
+    check_samples(s, gold)
+    res = cfg.resolution
+    freqs = np.atleast_1d(gold['frequency'])
+    assert len(freqs) == 10 and gold['I_nu'].shape == (10, res, res)
+    for l, nu in enumerate(freqs):
+        image, _ = oracle_lib.simulation_image(dict(kv, image_frequency=repr(float(nu))), s, fac, grid, want_inds=False)
+        ref, got = gold['I_nu'][l], image.reshape(res, res)
+        assert np.array_equal(np.isnan(got), np.isnan(ref)), l
+        ok = ~np.isnan(ref)
+        scale = np.maximum(np.abs(ref[ok]), 1e-12 * np.nanmax(np.abs(ref)))
+        assert np.max(np.abs(got[ok] - ref[ok]) / scale) < 1e-10, l
+
+
 def test_oracle_simulation_auxiliary_images(tmp_path):
     """All 27 auxiliary images of the simulation model -- time, length, lambda, emission, tau, crossings and the
     lambda- / emission-averaged and tau-integrated cell values (rho, n_e, p_gas, Theta_e, B, sigma, 1/beta;
