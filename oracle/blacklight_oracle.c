@@ -19,6 +19,7 @@
  *   Cartesian Kerr-Schild grids (simulation_coord = cks)   radiation_geometry.cpp:37-57, 425-457
  *   fluid-frame tetrad                                     radiation_geometry.cpp:597-658
  *   unpolarized transfer, auxiliary images (both models)   unpolarized.cpp:31-221
+ *   false-colour rendering (fills, threshold crossings)    rendering.cpp:25-179
  * Build: gcc -O2 -ffp-contract=off (no FMA contraction, like the reference's -O3 without -march).
  */
 #include <math.h>
@@ -428,7 +429,15 @@ typedef struct {
   double power_frac, power_p, power_gamma_min, power_gamma_max;
   /* kappa-distribution electrons (simulation_coefficients.cpp:82-105,608-664) */
   double kappa_frac, kappa, kappa_w;
+  int flat;               /* ray_flat: Minkowski geodesic metric in the radiation stage (radiation_geometry.cpp:142,210) */
+  double cut_omit_in, cut_omit_out;   /* sphere cuts, < 0 disables (simulation_sampling.cpp:256-261) */
 } orc_sim;
+
+/* one feature of a false-colour render image (rendering.cpp:100-165): type 0 fill, 1 thresh, 2 rise, 3 fall */
+typedef struct {
+  int image, quantity, type;
+  double min, max, tau_scale, thresh, opacity, xyz[3];
+} orc_feature;
 
 /* Gauss hypergeometric function by the reference's transformed, 10-term series (simulation_coefficients.cpp:740-773) */
 static double hypergeometric(double alpha, double beta, double gamma, double z) {
@@ -498,17 +507,21 @@ void orc_simulation_image(const orc_sim *P, long n_rays, int cap, const int *num
                           const double *pos, const double *dir, const double *len, const double *mom_factor,
                           double freq, const double *x1f, const double *x2f, const double *x3f, const double *x1v,
                           const double *x2v, const double *x3v, const float *prim, double *image, int *inds,
-                          const double *camera_x, double *aux) {
+                          const double *camera_x, double *aux, int n_feat, const orc_feature *feat, int n_render,
+                          double *render) {
   const double c = 2.99792458e10, hpl = 6.62607015e-27, m_p = 1.67262192369e-24, m_e = 9.1093837015e-28, qe = 4.80320425e-10;
   const double e_unit = P->d_unit * c * c, b_unit = sqrt(4.0 * PI * e_unit);
   orc_geo geo;
   memset(&geo, 0, sizeof geo);
   geo.a = P->a;
+  geo.flat = P->flat;
   long m;
 #pragma omp parallel for schedule(dynamic, 4)
   for (m = 0; m < n_rays; m++) {
     int n, b = 0, i, j, k, mu, nu_;
     double I = 0.0;
+    double prev_cv[7] = {NAN, NAN, NAN, NAN, NAN, NAN, NAN};   /* rendering.cpp:58-61 */
+    if (render) for (i = 0; i < n_render * 3; i++) render[(size_t)i * n_rays + m] = 0.0;
     int n_i = P->n_i, n_j = P->n_j, n_k = P->n_k;
     double a_time = 0.0, a_length = 0.0, a_lambda = 0.0, a_emission = 0.0, a_tau = 0.0, a_lave[7], a_eave[7], a_tint[7];
     int a_cross = 0, a_sign = 0;
@@ -532,7 +545,7 @@ void orc_simulation_image(const orc_sim *P, long n_rays, int cap, const int *num
         have = 1;
       } else {
         double a = P->a, r = ks_radius(a, x, y, z);
-        if (!(r > P->camera_r)) {
+        if (!(r > P->camera_r) && !((P->cut_omit_in >= 0.0 && r < P->cut_omit_in) || (P->cut_omit_out >= 0.0 && r > P->cut_omit_out))) {
           double x1 = r, x2 = acos(z / r), x3 = atan2(y, x) - atan(a / r);
           x3 += x3 < 0.0 ? 2.0 * PI : 0.0;
           x3 -= x3 >= 2.0 * PI ? 2.0 * PI : 0.0;
@@ -706,18 +719,42 @@ void orc_simulation_image(const orc_sim *P, long n_rays, int cap, const int *num
         }
       }
       I = transfer_step(I, jv, av, dl_cgs);
-      if (aux) {
-        double gcov[4][4], gcon[4][4], t[4] = {0, 0, 0, 0}, sq = 0.0, t_cgs = pos[4 * o] * (P->x_unit / c);
-        double dtau = av * dl_cgs, e_neg = exp(-dtau), e_m1 = expm1(dtau);
-        int aa, bb_, now;
-        a_time = t_cgs < a_time ? t_cgs : a_time;
+      double d_length = 0.0;   /* proper length of the step (unpolarized.cpp:117-130, rendering.cpp:86-99) */
+      if (aux || render) {
+        double gcov[4][4], gcon[4][4], t[4] = {0, 0, 0, 0}, sq = 0.0;
+        int aa, bb_;
         metric_cov(&geo, x, y, z, gcov);
         metric_con(&geo, x, y, z, gcon);
         for (aa = 1; aa < 4; aa++)
           for (mu = 0; mu < 4; mu++) t[aa] += (gcon[aa][mu] - gcon[0][aa] * gcon[0][mu] / gcon[0][0]) * kcov[mu];
         for (aa = 1; aa < 4; aa++)
           for (bb_ = 1; bb_ < 4; bb_++) sq += gcov[aa][bb_] * t[aa] * t[bb_];
-        a_length += sqrt(sq) * len[o] * P->x_unit;
+        d_length = sqrt(sq) * len[o] * P->x_unit;
+      }
+      if (render) {   /* rendering.cpp:100-170 */
+        int f, q;
+        for (f = 0; f < n_feat; f++) {
+          const orc_feature *ft = feat + f;
+          double *px = render + ((size_t)ft->image * 3) * n_rays + m, prev = prev_cv[ft->quantity], cur = cv[ft->quantity];
+          int crossed = 0;
+          if (ft->type == 0 && cur >= ft->min && cur <= ft->max) {
+            double dt = d_length / ft->tau_scale;
+            for (q = 0; q < 3; q++)
+              px[(size_t)q * n_rays] = dt <= 100.0 ? exp(-dt) * (px[(size_t)q * n_rays] + ft->xyz[q] * expm1(dt)) : ft->xyz[q];
+          }
+          if ((ft->type == 1 || ft->type == 2) && prev < ft->thresh && cur >= ft->thresh) crossed = 1;
+          if ((ft->type == 1 || ft->type == 3) && prev > ft->thresh && cur <= ft->thresh) crossed = 1;
+          if (crossed)
+            for (q = 0; q < 3; q++) px[(size_t)q * n_rays] = (1.0 - ft->opacity) * px[(size_t)q * n_rays] + ft->opacity * ft->xyz[q];
+        }
+        for (q = 0; q < 7; q++) prev_cv[q] = cv[q];
+      }
+      if (aux) {
+        double t_cgs = pos[4 * o] * (P->x_unit / c);
+        double dtau = av * dl_cgs, e_neg = exp(-dtau), e_m1 = expm1(dtau);
+        int aa, now;
+        a_time = t_cgs < a_time ? t_cgs : a_time;
+        a_length += d_length;
         a_lambda += dl_cgs;
         a_emission += jv * dl_cgs;
         a_tau += dtau;

@@ -25,7 +25,13 @@ class Sim(ctypes.Structure):
                [(n, ctypes.c_double) for n in ('d_unit', 'mu', 'ne_ni', 'rat_low', 'rat_high', 'cut_sigma_max')] + \
                [('coord', ctypes.c_int)] + \
                [(n, ctypes.c_double) for n in ('power_frac', 'power_p', 'power_gamma_min', 'power_gamma_max',
-                                               'kappa_frac', 'kappa', 'kappa_w')]
+                                               'kappa_frac', 'kappa', 'kappa_w')] + \
+               [('flat', ctypes.c_int), ('cut_omit_in', ctypes.c_double), ('cut_omit_out', ctypes.c_double)]
+
+
+class Feature(ctypes.Structure):
+    _fields_ = [('image', ctypes.c_int), ('quantity', ctypes.c_int), ('type', ctypes.c_int)] + \
+               [(n, ctypes.c_double) for n in ('min', 'max', 'tau_scale', 'thresh', 'opacity')] + [('xyz', ctypes.c_double * 3)]
 
 
 def _p(a):
@@ -106,8 +112,35 @@ AUX_NAMES = ['time', 'length', 'lambda', 'emission', 'tau', 'crossings'] + \
              for c in ('rho', 'n_e', 'p_gas', 'Theta_e', 'B', 'sigma', 'beta_inverse')]
 
 
-def simulation_image(kv, s, mom, grid, want_inds=True, camera_x=None):
-    """camera_x given: also the 27 auxiliary images, returned as a dict name -> (n) array in place of the indices."""
+def rgb_to_xyz(r, g, b):
+    """sRGB (0-255) to CIE XYZ as the input reader does for render_*_rgb keys (utils/colors.cpp:24-36)."""
+    lin = [c / 255.0 for c in (r, g, b)]
+    lin = [c / 12.92 if c <= 0.040449936 else ((c + 0.055) / 1.055) ** 2.4 for c in lin]
+    return (0.4123955889674142 * lin[0] + 0.3575834307637148 * lin[1] + 0.18049264738170154 * lin[2],
+            0.21258623078559552 * lin[0] + 0.715170303703411 * lin[1] + 0.0722004986433362 * lin[2],
+            0.019297215491746938 * lin[0] + 0.11918386458084851 * lin[1] + 0.9504971251315798 * lin[2])
+
+
+def render_features(kv):
+    """The render_<i>_<f>_* keys of an input file as a Feature array (render_reader.cpp)."""
+    quantities = ['rho', 'n_e', 'p_gas', 'Theta_e', 'B', 'sigma', 'beta_inverse']
+    types = {'fill': 0, 'thresh': 1, 'rise': 2, 'fall': 3}
+    feats = []
+    for i in range(1, int(kv.get('render_num_images', 0)) + 1):
+        for f in range(1, int(kv['render_%d_num_features' % i]) + 1):
+            key = lambda name: kv.get('render_%d_%d_%s' % (i, f, name))
+            ft = Feature(image=i - 1, quantity=quantities.index(key('quantity')), type=types[key('type')])
+            for name in ('min', 'max', 'tau_scale', 'thresh', 'opacity'):
+                setattr(ft, name, float(key(name)) if key(name) is not None else 0.0)
+            xyz = [float(v) for v in key('xyz').split(',')] if key('xyz') else rgb_to_xyz(*[float(v) for v in key('rgb').split(',')])
+            ft.xyz[:] = xyz
+            feats.append(ft)
+    return (Feature * len(feats))(*feats), len(feats)
+
+
+def simulation_image(kv, s, mom, grid, want_inds=True, camera_x=None, render=False):
+    """camera_x given: also the 27 auxiliary images, returned as a dict name -> (n) array in place of the indices.
+    render: also the false-colour images (render_num_images, 3, n) of the input file's render_* features, as a third value."""
     a = float(kv['simulation_a'])
     P = Sim(a=a, camera_r=float(kv['camera_r']), x_unit=GG_MSUN * float(kv['simulation_m_msun']) / (C * C),
             n_b=grid['n_b'], n_k=grid['n_k'], n_j=grid['n_j'], n_i=grid['n_i'], interp=int(kv['simulation_interp'] == 'true'),
@@ -117,16 +150,23 @@ def simulation_image(kv, s, mom, grid, want_inds=True, camera_x=None):
             power_frac=float(kv.get('plasma_power_frac', 0.0)), power_p=float(kv.get('plasma_p', 0.0)),
             power_gamma_min=float(kv.get('plasma_gamma_min', 0.0)), power_gamma_max=float(kv.get('plasma_gamma_max', 0.0)),
             kappa_frac=float(kv.get('plasma_kappa_frac', 0.0)), kappa=float(kv.get('plasma_kappa', 0.0)),
-            kappa_w=float(kv.get('plasma_w', 0.0)))
+            kappa_w=float(kv.get('plasma_w', 0.0)), flat=int(kv.get('ray_flat', 'false') == 'true'),
+            cut_omit_in=float(kv.get('cut_omit_in', -1.0)), cut_omit_out=float(kv.get('cut_omit_out', -1.0)))
     n = len(mom)
     image = np.zeros(n)
     inds = np.full((n, s['cap'], 4), -1, np.int32) if want_inds else None
     aux = np.zeros((27, n)) if camera_x is not None else None
+    feats, n_feat = render_features(kv) if render else (None, 0)
+    n_render = int(kv.get('render_num_images', 0)) if render else 0
+    rendering = np.zeros((n_render, 3, n)) if render else None
     keep = [np.ascontiguousarray(grid[k]) for k in ('x1f', 'x2f', 'x3f', 'x1v', 'x2v', 'x3v', 'prim')]
     lib().orc_simulation_image(ctypes.byref(P), ctypes.c_long(n), s['cap'], _p(s['num']), _p(s['flags']), _p(s['pos']),
                                _p(s['dir']), _p(s['len']), _p(np.ascontiguousarray(mom)), ctypes.c_double(float(kv['image_frequency'])),
                                *[_p(k) for k in keep], _p(image), _p(inds),
-                               _p(None if camera_x is None else np.ascontiguousarray(camera_x, np.float64)), _p(aux))
+                               _p(None if camera_x is None else np.ascontiguousarray(camera_x, np.float64)), _p(aux),
+                               n_feat, feats, n_render, _p(rendering))
+    if render:
+        return image, (dict(zip(AUX_NAMES, aux)) if aux is not None else inds), rendering
     if aux is not None:
         return image, dict(zip(AUX_NAMES, aux))
     return image, inds

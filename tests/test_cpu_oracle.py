@@ -178,6 +178,25 @@ def test_oracle_true_color_frequencies(tmp_path):
         assert np.max(np.abs(got[ok] - ref[ok]) / scale) < 1e-10, l
 
 
+def test_oracle_render(tmp_path):
+    """False-colour rendering (rendering.cpp:25-179; flat-space rays, no light image): fills with their optical-depth
+    law along the proper length, threshold crossings alpha-blended, colours through the sRGB -> XYZ conversion of
+    the input reader -- restated in C against the reference's fixture."""
+    kv, cfg, gold, mock = setup('render_32', tmp_path)
+    grid = mock_snapshot.grid_view_arrays(mock_snapshot.make_mock(None))
+    pos, dirs, fac = cfg.camera_root()
+    s = oracle_lib.trace(kv, float(kv['simulation_a']), pos, dirs)
+    check_samples(s, gold)
+    _, _, rendering = oracle_lib.simulation_image(kv, s, fac, grid, want_inds=False, render=True)
+    ref = gold['rendering']
+    got = rendering.reshape(ref.shape)
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    scale = np.maximum(np.abs(ref[ok]), 1e-12 * np.nanmax(np.abs(ref)))
+    assert np.max(np.abs(got[ok] - ref[ok]) / scale) < 1e-9
+    assert np.nanmax(ref) > 0.0
+
+
 def test_oracle_simulation_auxiliary_images(tmp_path):
     """All 27 auxiliary images of the simulation model -- time, length, lambda, emission, tau, crossings and the
     lambda- / emission-averaged and tau-integrated cell values (rho, n_e, p_gas, Theta_e, B, sigma, 1/beta;
