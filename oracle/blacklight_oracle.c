@@ -431,6 +431,9 @@ typedef struct {
   double kappa_frac, kappa, kappa_w;
   int flat;               /* ray_flat: Minkowski geodesic metric in the radiation stage (radiation_geometry.cpp:142,210) */
   double cut_omit_in, cut_omit_out;   /* sphere cuts, < 0 disables (simulation_sampling.cpp:256-261) */
+  /* plasma_use_p = false: electron temperature from the internal energies (simulation_coefficients.cpp:342-346) */
+  int use_energy;
+  double gamma, gamma_i, gamma_e;
 } orc_sim;
 
 /* one feature of a false-colour render image (rendering.cpp:100-165): type 0 fill, 1 thresh, 2 rise, 3 fall */
@@ -631,6 +634,10 @@ void orc_simulation_image(const orc_sim *P, long n_rays, int cap, const int *num
         double tti_tte = (P->rat_high + P->rat_low * beta_inv * beta_inv) / (1.0 + beta_inv * beta_inv);
         double kb_tot = P->mu * m_p * pgas_cgs / rho_cgs;
         double kb_te = (1.0 + P->ne_ni) / (tti_tte + P->ne_ni) * kb_tot;
+        if (P->use_energy) {
+          kb_te = (1.0 + P->ne_ni) * kb_tot / (P->gamma - 1.0);
+          kb_te /= tti_tte / (P->gamma_i - 1.0) + P->ne_ni / (P->gamma_e - 1.0);
+        }
         double theta_e = kb_te / (m_e * c * c);
         int cut = P->cut_sigma_max >= 0.0 && sig > P->cut_sigma_max;
         if (!cut) { cv[0] = rho_cgs; cv[1] = n_e; cv[2] = pgas_cgs; cv[3] = theta_e; cv[4] = bb_cgs; cv[5] = sig; cv[6] = beta_inv; }

@@ -42,6 +42,17 @@ CASES = {
                                                   'camera_r': '100.0', 'camera_urn': '-0.05', 'camera_rotation': '25.0'}, None),
 }
 
+# image-only fixtures for the CPU-only checks of the restatement (tests/test_cpu_oracle.py)
+PLAW = {'plasma_power_frac': '0.4', 'plasma_p': '3.0', 'plasma_gamma_min': '4.0', 'plasma_gamma_max': '1000.0'}
+CPU_CASES = {
+    'cpu_simulation_power_law_16': dict(PLAW, camera_resolution='16'),
+    'cpu_simulation_mixed_electrons_16': dict(PLAW, plasma_power_frac='0.2', plasma_kappa_frac='0.5', plasma_kappa='4.0',
+                                              plasma_w='1.0', camera_resolution='16'),
+    'cpu_simulation_energy_temperature_16': {'plasma_use_p': 'false', 'plasma_gamma': '1.5',
+                                             'plasma_gamma_i': '1.6666666666666667',
+                                             'plasma_gamma_e': '1.3333333333333333', 'camera_resolution': '16'},
+}
+
 
 def masked_inds_crc(geo, samp, sim_interp):
     num = geo['sample_num']
@@ -54,6 +65,13 @@ def masked_inds_crc(geo, samp, sim_interp):
 
 def main():
     only = sys.argv[1:]
+    for name, over in CPU_CASES.items():
+        if only and name not in only:
+            continue
+        with tempfile.TemporaryDirectory() as d:
+            ref = Case(d, 'simulation.input', over, threads=8).run_reference(checkpoints=False)
+            np.savez_compressed(os.path.join(os.environ.get('GOLDEN_OUT', HERE), name + '.npz'), I_nu=ref['npz']['I_nu'])
+            print(name, ref['npz']['I_nu'].shape)
     for name, (base, over, mock) in CASES.items():
         if only and name not in only:
             continue

@@ -254,11 +254,15 @@ def test_readers_through_the_restatement_against_reference_fixtures(name, tmp_pa
     ('cpu_simulation_mixed_electrons_16', {'plasma_power_frac': '0.2', 'plasma_p': '3.0', 'plasma_gamma_min': '4.0',
                                            'plasma_gamma_max': '1000.0', 'plasma_kappa_frac': '0.5', 'plasma_kappa': '4.0',
                                            'plasma_w': '1.0'}),
+    ('cpu_simulation_energy_temperature_16', {'plasma_use_p': 'false', 'plasma_gamma': '1.5',
+                                              'plasma_gamma_i': '1.6666666666666667',
+                                              'plasma_gamma_e': '1.3333333333333333'}),
 ])
 def test_oracle_nonthermal_electrons(fixture, over, tmp_path):
     """Thermal + power-law (+ kappa) electrons: the restatement's constants (tgamma forms and the truncated
     hypergeometric series, simulation_coefficients.cpp:53-105,740-773) and per-sample emissivities / absorptivities
-    (:559-585, :608-653, including the kappa absorptivity that an unpolarized run of the reference zeroes) against the
+    (:559-585, :608-653, including the kappa absorptivity that an unpolarized run of the reference zeroes), and the
+    electron temperature from the internal energies when plasma_use_p = false (:340-346), against the
     unmodified reference's images (tests/golden/cpu_*.npz, made with the harness's Case.run_reference)."""
     kv = load_input('simulation.input')
     kv.update(dict(over, camera_resolution='16'))
