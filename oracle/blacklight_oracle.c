@@ -434,6 +434,9 @@ typedef struct {
   /* plasma_use_p = false: electron temperature from the internal energies (simulation_coefficients.cpp:342-346) */
   int use_energy;
   double gamma, gamma_i, gamma_e;
+  /* plasma_model = code_kappa: electron entropy is variable 8 of prim (simulation_sampling.cpp:726,811-833;
+     simulation_coefficients.cpp:351-358) */
+  int code_kappa;
 } orc_sim;
 
 /* one feature of a false-colour render image (rendering.cpp:100-165): type 0 fill, 1 thresh, 2 rise, 3 fall */
@@ -540,7 +543,7 @@ void orc_simulation_image(const orc_sim *P, long n_rays, int cap, const int *num
       const double *kcov = dir + 4 * o;
       double dl_cgs = len[o] * P->x_unit / (freq * mom_factor[m]);
       double jv = 0.0, av = 0.0;
-      double rho, pgas, uu[3], bb[3];
+      double rho, pgas, uu[3], bb[3], entropy = 0.0;
       int have = 0;
       if (inds) for (i = 0; i < 4; i++) inds[4 * o + i] = -1;
       if (P->fallback_nan && flags[m]) {
@@ -574,6 +577,7 @@ void orc_simulation_image(const orc_sim *P, long n_rays, int cap, const int *num
             if (inds) { inds[4 * o] = b; inds[4 * o + 1] = k; inds[4 * o + 2] = j; inds[4 * o + 3] = i; }
             rho = g4(prim, P, 0, b, k, j, i); pgas = g4(prim, P, 1, b, k, j, i);
             for (mu = 0; mu < 3; mu++) { uu[mu] = g4(prim, P, 2 + mu, b, k, j, i); bb[mu] = g4(prim, P, 5 + mu, b, k, j, i); }
+            if (P->code_kappa) entropy = g4(prim, P, 8, b, k, j, i);
           } else {
             const double *v1 = x1v + (size_t)b * n_i, *v2 = x2v + (size_t)b * n_j, *v3 = x3v + (size_t)b * n_k;
             int im = (i == 0 || (i != n_i - 1 && x1 >= v1[i])) ? i : i - 1;
@@ -587,13 +591,17 @@ void orc_simulation_image(const orc_sim *P, long n_rays, int cap, const int *num
             pgas = trilinear(prim, P, 1, b, km, jm, im, fk, fj, fi);
             if (rho <= 0.0) rho = g4(prim, P, 0, b, km, jm, im);
             if (pgas <= 0.0) pgas = g4(prim, P, 1, b, km, jm, im);
+            if (P->code_kappa) {
+              entropy = trilinear(prim, P, 8, b, km, jm, im, fk, fj, fi);
+              if (entropy <= 0.0) entropy = g4(prim, P, 8, b, km, jm, im);
+            }
             for (mu = 0; mu < 3; mu++) {
               uu[mu] = trilinear(prim, P, 2 + mu, b, km, jm, im, fk, fj, fi);
               bb[mu] = trilinear(prim, P, 5 + mu, b, km, jm, im, fk, fj, fi);
             }
           }
           /* sampled values are stored as float (simulation_sampling.cpp:830-839) */
-          rho = (double)(float)rho; pgas = (double)(float)pgas;
+          rho = (double)(float)rho; pgas = (double)(float)pgas; entropy = (double)(float)entropy;
           for (mu = 0; mu < 3; mu++) { uu[mu] = (double)(float)uu[mu]; bb[mu] = (double)(float)bb[mu]; }
           have = 1;
         }
@@ -639,6 +647,13 @@ void orc_simulation_image(const orc_sim *P, long n_rays, int cap, const int *num
           kb_te /= tti_tte / (P->gamma_i - 1.0) + P->ne_ni / (P->gamma_e - 1.0);
         }
         double theta_e = kb_te / (m_e * c * c);
+        if (P->code_kappa) {
+          double mu_e = P->mu * (1.0 + 1.0 / P->ne_ni);
+          double rho_e = rho * m_e / (mu_e * m_p);
+          double q = cbrt(rho_e * entropy);
+          theta_e = 1.0 / 5.0 * (sqrt(1.0 + 25.0 * q * q) - 1.0);
+          kb_te = theta_e * m_e * c * c;
+        }
         int cut = P->cut_sigma_max >= 0.0 && sig > P->cut_sigma_max;
         if (!cut) { cv[0] = rho_cgs; cv[1] = n_e; cv[2] = pgas_cgs; cv[3] = theta_e; cv[4] = bb_cgs; cv[5] = sig; cv[6] = beta_inv; }
         if (!cut && !(bb[0] == 0.0 && bb[1] == 0.0 && bb[2] == 0.0)) {

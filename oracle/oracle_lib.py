@@ -27,7 +27,8 @@ class Sim(ctypes.Structure):
                [(n, ctypes.c_double) for n in ('power_frac', 'power_p', 'power_gamma_min', 'power_gamma_max',
                                                'kappa_frac', 'kappa', 'kappa_w')] + \
                [('flat', ctypes.c_int), ('cut_omit_in', ctypes.c_double), ('cut_omit_out', ctypes.c_double)] + \
-               [('use_energy', ctypes.c_int), ('gamma', ctypes.c_double), ('gamma_i', ctypes.c_double), ('gamma_e', ctypes.c_double)]
+               [('use_energy', ctypes.c_int), ('gamma', ctypes.c_double), ('gamma_i', ctypes.c_double), ('gamma_e', ctypes.c_double)] + \
+               [('code_kappa', ctypes.c_int)]
 
 
 class Feature(ctypes.Structure):
@@ -154,7 +155,8 @@ def simulation_image(kv, s, mom, grid, want_inds=True, camera_x=None, render=Fal
             kappa_w=float(kv.get('plasma_w', 0.0)), flat=int(kv.get('ray_flat', 'false') == 'true'),
             cut_omit_in=float(kv.get('cut_omit_in', -1.0)), cut_omit_out=float(kv.get('cut_omit_out', -1.0)),
             use_energy=int(kv.get('plasma_use_p', 'true') == 'false'), gamma=float(kv.get('plasma_gamma', 0.0)),
-            gamma_i=float(kv.get('plasma_gamma_i', 0.0)), gamma_e=float(kv.get('plasma_gamma_e', 0.0)))
+            gamma_i=float(kv.get('plasma_gamma_i', 0.0)), gamma_e=float(kv.get('plasma_gamma_e', 0.0)),
+            code_kappa=int(kv.get('plasma_model', 'ti_te_beta') == 'code_kappa'))
     n = len(mom)
     image = np.zeros(n)
     inds = np.full((n, s['cap'], 4), -1, np.int32) if want_inds else None

@@ -51,6 +51,9 @@ CPU_CASES = {
     'cpu_simulation_energy_temperature_16': {'plasma_use_p': 'false', 'plasma_gamma': '1.5',
                                              'plasma_gamma_i': '1.6666666666666667',
                                              'plasma_gamma_e': '1.3333333333333333', 'camera_resolution': '16'},
+    'cpu_simulation_code_kappa_16': {'plasma_model': 'code_kappa', 'simulation_kappa_name': 'r0', 'camera_resolution': '16'},
+    'cpu_simulation_code_kappa_nearest_16': {'plasma_model': 'code_kappa', 'simulation_kappa_name': 'r0',
+                                             'simulation_interp': 'false', 'camera_resolution': '16'},
 }
 
 
@@ -69,7 +72,8 @@ def main():
         if only and name not in only:
             continue
         with tempfile.TemporaryDirectory() as d:
-            ref = Case(d, 'simulation.input', over, threads=8).run_reference(checkpoints=False)
+            mock = dict(entropy=True) if over.get('plasma_model') == 'code_kappa' else None
+            ref = Case(d, 'simulation.input', over, mock=mock, threads=8).run_reference(checkpoints=False)
             np.savez_compressed(os.path.join(os.environ.get('GOLDEN_OUT', HERE), name + '.npz'), I_nu=ref['npz']['I_nu'])
             print(name, ref['npz']['I_nu'].shape)
     for name, (base, over, mock) in CASES.items():

@@ -284,6 +284,35 @@ def test_oracle_nonthermal_electrons(fixture, over, tmp_path):
     assert abs(np.nanmax(ref) / np.nanmax(thermal) - 1.0) > 0.01
 
 
+@pytest.mark.parametrize('fixture,over', [
+    ('cpu_simulation_code_kappa_16', {}),
+    ('cpu_simulation_code_kappa_nearest_16', {'simulation_interp': 'false'}),
+])
+def test_oracle_code_kappa(fixture, over, tmp_path):
+    """plasma_model = code_kappa: the electron-entropy variable sampled like the other primitives (nearest cell, or
+    trilinear with its own non-positive fallback and float storage, simulation_sampling.cpp:726,811-833) and the
+    electron temperature from it (simulation_coefficients.cpp:351-358), against the unmodified reference's images."""
+    kv = load_input('simulation.input')
+    kv.update(dict(over, plasma_model='code_kappa', simulation_kappa_name='r0', camera_resolution='16'))
+    path = os.path.join(tmp_path, 'o.input')
+    write_input(path, kv)
+    cfg = bl.Config(path)
+    g = mock_snapshot.grid_view_arrays(mock_snapshot.make_mock(None, entropy=True))
+    order = ('ind_rho', 'ind_pgas', 'ind_uu1', 'ind_uu2', 'ind_uu3', 'ind_bb1', 'ind_bb2', 'ind_bb3', 'ind_kappa')
+    grid = dict(g, prim=np.ascontiguousarray(np.stack([g['prim'][g[k]] for k in order]), np.float32))
+    pos, dirs, fac = cfg.camera_root()
+    s = oracle_lib.trace(kv, float(kv['simulation_a']), pos, dirs)
+    image, _ = oracle_lib.simulation_image(kv, s, fac, grid, want_inds=False)
+    ref = np.load(os.path.join(GOLDEN, fixture + '.npz'))['I_nu']
+    got = image.reshape(16, 16)
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    scale = np.maximum(np.abs(ref[ok]), 1e-12 * np.nanmax(np.abs(ref)))
+    assert np.max(np.abs(got[ok] - ref[ok]) / scale) < 1e-10
+    thermal = np.load(os.path.join(GOLDEN, 'simulation_32.npz'))['I_nu']
+    assert abs(np.nanmax(ref) / np.nanmax(thermal) - 1.0) > 0.01
+
+
 def test_refinement_restatement_against_reference_fixture(tmp_path):
     """Adaptive refinement decision (EvaluateBlock, radiation_adaptive.cpp:163-312; child order camera.cpp:445-459): the
     numpy restatement applied to the unmodified reference's level-0 image reproduces the reference's list of level-1
