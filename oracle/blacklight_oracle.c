@@ -437,6 +437,13 @@ typedef struct {
   /* plasma_model = code_kappa: electron entropy is variable 8 of prim (simulation_sampling.cpp:726,811-833;
      simulation_coefficients.cpp:351-358) */
   int code_kappa;
+  /* remaining cuts.  geometric (simulation_sampling.cpp:245-295): camera plane (near / far, with the camera position
+     cut_cam), midplane angle (radians, sign selects inside / outside) and height, arbitrary plane;
+     cell values (simulation_coefficients.cpp:361-375): min / max pairs of rho, n_e, p_gas, theta_e, B, sigma, 1/beta,
+     each < 0 disables (sigma max stays cut_sigma_max above) */
+  int cut_omit_near, cut_omit_far, cut_plane;
+  double cut_cam[3], cut_midplane_theta, cut_midplane_z, cut_plane_origin[3], cut_plane_normal[3];
+  double cut_val_min[7], cut_val_max[7];
 } orc_sim;
 
 /* one feature of a false-colour render image (rendering.cpp:100-165): type 0 fill, 1 thresh, 2 rise, 3 fall */
@@ -551,7 +558,23 @@ void orc_simulation_image(const orc_sim *P, long n_rays, int cap, const int *num
         have = 1;
       } else {
         double a = P->a, r = ks_radius(a, x, y, z);
-        if (!(r > P->camera_r) && !((P->cut_omit_in >= 0.0 && r < P->cut_omit_in) || (P->cut_omit_out >= 0.0 && r > P->cut_omit_out))) {
+        int geom_cut = r > P->camera_r;
+        if (!geom_cut && (P->cut_omit_near || P->cut_omit_far)) {
+          double dot = x * P->cut_cam[0] + y * P->cut_cam[1] + z * P->cut_cam[2];
+          geom_cut = (P->cut_omit_near && dot > 0.0) || (P->cut_omit_far && dot < 0.0);
+        }
+        if (!geom_cut) geom_cut = (P->cut_omit_in >= 0.0 && r < P->cut_omit_in) || (P->cut_omit_out >= 0.0 && r > P->cut_omit_out);
+        if (!geom_cut && P->cut_midplane_theta != 0.0) {
+          double dth = fabs(acos(z / r) - PI / 2.0);
+          geom_cut = (P->cut_midplane_theta > 0.0 && dth > P->cut_midplane_theta) ||
+                     (P->cut_midplane_theta < 0.0 && dth < -P->cut_midplane_theta);
+        }
+        if (!geom_cut)
+          geom_cut = (P->cut_midplane_z > 0.0 && fabs(z) > P->cut_midplane_z) || (P->cut_midplane_z < 0.0 && fabs(z) < -P->cut_midplane_z);
+        if (!geom_cut && P->cut_plane)
+          geom_cut = (x - P->cut_plane_origin[0]) * P->cut_plane_normal[0] + (y - P->cut_plane_origin[1]) * P->cut_plane_normal[1] +
+                     (z - P->cut_plane_origin[2]) * P->cut_plane_normal[2] < 0.0;
+        if (!geom_cut) {
           double x1 = r, x2 = acos(z / r), x3 = atan2(y, x) - atan(a / r);
           x3 += x3 < 0.0 ? 2.0 * PI : 0.0;
           x3 -= x3 >= 2.0 * PI ? 2.0 * PI : 0.0;
@@ -655,6 +678,11 @@ void orc_simulation_image(const orc_sim *P, long n_rays, int cap, const int *num
           kb_te = theta_e * m_e * c * c;
         }
         int cut = P->cut_sigma_max >= 0.0 && sig > P->cut_sigma_max;
+        {
+          double val[7] = {rho_cgs, n_e, pgas_cgs, theta_e, bb_cgs, sig, beta_inv};
+          for (i = 0; i < 7; i++)
+            if ((P->cut_val_min[i] >= 0.0 && val[i] < P->cut_val_min[i]) || (P->cut_val_max[i] >= 0.0 && val[i] > P->cut_val_max[i])) cut = 1;
+        }
         if (!cut) { cv[0] = rho_cgs; cv[1] = n_e; cv[2] = pgas_cgs; cv[3] = theta_e; cv[4] = bb_cgs; cv[5] = sig; cv[6] = beta_inv; }
         if (!cut && !(bb[0] == 0.0 && bb[1] == 0.0 && bb[2] == 0.0)) {
           /* to CKS, tetrad, pitch angle (simulation_coefficients.cpp:397-455) */

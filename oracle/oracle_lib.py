@@ -28,7 +28,13 @@ class Sim(ctypes.Structure):
                                                'kappa_frac', 'kappa', 'kappa_w')] + \
                [('flat', ctypes.c_int), ('cut_omit_in', ctypes.c_double), ('cut_omit_out', ctypes.c_double)] + \
                [('use_energy', ctypes.c_int), ('gamma', ctypes.c_double), ('gamma_i', ctypes.c_double), ('gamma_e', ctypes.c_double)] + \
-               [('code_kappa', ctypes.c_int)]
+               [('code_kappa', ctypes.c_int)] + \
+               [('cut_omit_near', ctypes.c_int), ('cut_omit_far', ctypes.c_int), ('cut_plane', ctypes.c_int),
+                ('cut_cam', ctypes.c_double * 3), ('cut_midplane_theta', ctypes.c_double), ('cut_midplane_z', ctypes.c_double),
+                ('cut_plane_origin', ctypes.c_double * 3), ('cut_plane_normal', ctypes.c_double * 3),
+                ('cut_val_min', ctypes.c_double * 7), ('cut_val_max', ctypes.c_double * 7)]
+
+CUT_VALUES = ('rho', 'n_e', 'p_gas', 'theta_e', 'b', 'sigma', 'beta_inverse')
 
 
 class Feature(ctypes.Structure):
@@ -140,7 +146,7 @@ def render_features(kv):
     return (Feature * len(feats))(*feats), len(feats)
 
 
-def simulation_image(kv, s, mom, grid, want_inds=True, camera_x=None, render=False):
+def simulation_image(kv, s, mom, grid, want_inds=True, camera_x=None, render=False, cut_camera_x=None):
     """camera_x given: also the 27 auxiliary images, returned as a dict name -> (n) array in place of the indices.
     render: also the false-colour images (render_num_images, 3, n) of the input file's render_* features, as a third value."""
     a = float(kv['simulation_a'])
@@ -156,7 +162,18 @@ def simulation_image(kv, s, mom, grid, want_inds=True, camera_x=None, render=Fal
             cut_omit_in=float(kv.get('cut_omit_in', -1.0)), cut_omit_out=float(kv.get('cut_omit_out', -1.0)),
             use_energy=int(kv.get('plasma_use_p', 'true') == 'false'), gamma=float(kv.get('plasma_gamma', 0.0)),
             gamma_i=float(kv.get('plasma_gamma_i', 0.0)), gamma_e=float(kv.get('plasma_gamma_e', 0.0)),
-            code_kappa=int(kv.get('plasma_model', 'ti_te_beta') == 'code_kappa'))
+            code_kappa=int(kv.get('plasma_model', 'ti_te_beta') == 'code_kappa'),
+            cut_omit_near=int(kv.get('cut_omit_near', 'false') == 'true'), cut_omit_far=int(kv.get('cut_omit_far', 'false') == 'true'),
+            cut_plane=int(kv.get('cut_plane', 'false') == 'true'),
+            cut_midplane_theta=float(kv.get('cut_midplane_theta', 0.0)) * np.pi / 180.0,
+            cut_midplane_z=float(kv.get('cut_midplane_z', 0.0)))
+    triple = lambda key: (ctypes.c_double * 3)(*[float(v) for v in kv.get(key, '0,0,0').split(',')])
+    P.cut_plane_origin, P.cut_plane_normal = triple('cut_plane_origin'), triple('cut_plane_normal')
+    # the sigma maximum is the struct's own cut_sigma_max
+    P.cut_val_min = (ctypes.c_double * 7)(*[float(kv.get('cut_%s_min' % v, -1.0)) for v in CUT_VALUES])
+    P.cut_val_max = (ctypes.c_double * 7)(*[-1.0 if v == 'sigma' else float(kv.get('cut_%s_max' % v, -1.0)) for v in CUT_VALUES])
+    if P.cut_omit_near or P.cut_omit_far:
+        P.cut_cam = (ctypes.c_double * 3)(*[float(v) for v in cut_camera_x[1:4]])
     n = len(mom)
     image = np.zeros(n)
     inds = np.full((n, s['cap'], 4), -1, np.int32) if want_inds else None

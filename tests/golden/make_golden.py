@@ -51,6 +51,18 @@ CPU_CASES = {
     'cpu_simulation_energy_temperature_16': {'plasma_use_p': 'false', 'plasma_gamma': '1.5',
                                              'plasma_gamma_i': '1.6666666666666667',
                                              'plasma_gamma_e': '1.3333333333333333', 'camera_resolution': '16'},
+    'cpu_simulation_cuts_a_16': {'cut_omit_near': 'true', 'cut_omit_in': '3.0', 'cut_midplane_theta': '30.0',
+                                 'cut_rho_min': '1.0e-18', 'camera_resolution': '16'},
+    'cpu_simulation_cuts_b_16': {'cut_omit_far': 'true', 'cut_omit_out': '30.0', 'cut_midplane_z': '6.0', 'cut_plane': 'true',
+                                 'cut_plane_origin': '1.0,0.0,0.5', 'cut_plane_normal': '0.2,1.0,0.1', 'cut_sigma_max': '-1.0',
+                                 'cut_beta_inverse_max': '5.0', 'cut_theta_e_max': '50.0', 'camera_resolution': '16'},
+    'cpu_simulation_cuts_c_16': {'cut_midplane_theta': '-5.0', 'cut_rho_min': '2.5e-17', 'cut_theta_e_max': '5.6',
+                                 'cut_b_max': '42.0', 'camera_resolution': '16'},
+    'cpu_simulation_cuts_d_16': {'cut_midplane_z': '-0.3', 'cut_n_e_max': '2.3e7', 'cut_p_gas_min': '450.0',
+                                 'cut_sigma_min': '3.2e-3', 'cut_beta_inverse_max': '7.5e-2', 'camera_resolution': '16'},
+    'cpu_simulation_cuts_e_16': {'cut_rho_max': '4.0e-17', 'cut_theta_e_min': '3.2', 'cut_b_min': '30.0', 'cut_n_e_min': '1.5e7',
+                                 'cut_p_gas_max': '1000.0', 'cut_beta_inverse_min': '6.0e-2', 'cut_sigma_max': '4.5e-3',
+                                 'camera_resolution': '16'},
     'cpu_simulation_code_kappa_16': {'plasma_model': 'code_kappa', 'simulation_kappa_name': 'r0', 'camera_resolution': '16'},
     'cpu_simulation_code_kappa_nearest_16': {'plasma_model': 'code_kappa', 'simulation_kappa_name': 'r0',
                                              'simulation_interp': 'false', 'camera_resolution': '16'},

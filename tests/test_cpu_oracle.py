@@ -313,6 +313,35 @@ def test_oracle_code_kappa(fixture, over, tmp_path):
     assert abs(np.nanmax(ref) / np.nanmax(thermal) - 1.0) > 0.01
 
 
+@pytest.mark.parametrize('name', ['cuts_a', 'cuts_b', 'cuts_c', 'cuts_d', 'cuts_e'])
+def test_oracle_cuts(name, tmp_path):
+    """Every cut of the input surface: camera plane near / far, spheres, midplane angle and height (both signs),
+    arbitrary plane (simulation_sampling.cpp:245-295) and the min / max cuts on the seven cell values
+    (simulation_coefficients.cpp:361-375), against the unmodified reference's images; the parameter sets are the
+    generator's (tests/golden/make_golden.py CPU_CASES)."""
+    import sys
+    sys.path.insert(0, GOLDEN)
+    from make_golden import CPU_CASES
+    kv = load_input('simulation.input')
+    kv.update(CPU_CASES['cpu_simulation_%s_16' % name])
+    path = os.path.join(tmp_path, 'o.input')
+    write_input(path, kv)
+    cfg = bl.Config(path)
+    grid = mock_snapshot.grid_view_arrays(mock_snapshot.make_mock(None))
+    pos, dirs, fac = cfg.camera_root()
+    s = oracle_lib.trace(kv, float(kv['simulation_a']), pos, dirs)
+    image, _ = oracle_lib.simulation_image(kv, s, fac, grid, want_inds=False, cut_camera_x=cfg.camera_frame()['cam_x'])
+    ref = np.load(os.path.join(GOLDEN, 'cpu_simulation_%s_16.npz' % name))['I_nu']
+    got = image.reshape(16, 16)
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    assert np.array_equal(got == 0.0, ref == 0.0)
+    scale = np.maximum(np.abs(ref), 1e-12 * np.nanmax(np.abs(ref)))
+    assert np.max(np.abs(got - ref) / scale) < 1e-10
+    # each case removes emission relative to the uncut image
+    full = np.load(os.path.join(GOLDEN, 'simulation_32.npz'))['I_nu']
+    assert np.nansum(ref) / ref.size < 0.9 * np.nansum(full) / full.size
+
+
 def test_refinement_restatement_against_reference_fixture(tmp_path):
     """Adaptive refinement decision (EvaluateBlock, radiation_adaptive.cpp:163-312; child order camera.cpp:445-459): the
     numpy restatement applied to the unmodified reference's level-0 image reproduces the reference's list of level-1
