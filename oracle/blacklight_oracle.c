@@ -444,6 +444,9 @@ typedef struct {
   int cut_omit_near, cut_omit_far, cut_plane;
   double cut_cam[3], cut_midplane_theta, cut_midplane_z, cut_plane_origin[3], cut_plane_normal[3];
   double cut_val_min[7], cut_val_max[7];
+  /* fallback_nan = false: samples outside the grid take these values, zero velocity and field, stored as float
+     (simulation_sampling.cpp:695-708; radiation_integrator.hpp:182-187) */
+  double fallback_rho, fallback_pgas, fallback_kappa;
 } orc_sim;
 
 /* one feature of a false-colour render image (rendering.cpp:100-165): type 0 fill, 1 thresh, 2 rise, 3 fall */
@@ -588,7 +591,12 @@ void orc_simulation_image(const orc_sim *P, long n_rays, int cap, const int *num
                   x2 <= x2f[(size_t)bn * (n_j + 1) + n_j] && x3 >= x3f[(size_t)bn * (n_k + 1)] && x3 <= x3f[(size_t)bn * (n_k + 1) + n_k])
                 break;
             if (bn == P->n_b) {
-              if (P->fallback_nan) { rho = pgas = uu[0] = uu[1] = uu[2] = bb[0] = bb[1] = bb[2] = NAN; have = 1; }
+              if (P->fallback_nan) rho = pgas = uu[0] = uu[1] = uu[2] = bb[0] = bb[1] = bb[2] = NAN;
+              else {
+                rho = (double)(float)P->fallback_rho; pgas = (double)(float)P->fallback_pgas; entropy = (double)(float)P->fallback_kappa;
+                uu[0] = uu[1] = uu[2] = bb[0] = bb[1] = bb[2] = 0.0;
+              }
+              have = 1;
               goto sampled;
             }
             b = bn;

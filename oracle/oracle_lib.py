@@ -32,7 +32,8 @@ class Sim(ctypes.Structure):
                [('cut_omit_near', ctypes.c_int), ('cut_omit_far', ctypes.c_int), ('cut_plane', ctypes.c_int),
                 ('cut_cam', ctypes.c_double * 3), ('cut_midplane_theta', ctypes.c_double), ('cut_midplane_z', ctypes.c_double),
                 ('cut_plane_origin', ctypes.c_double * 3), ('cut_plane_normal', ctypes.c_double * 3),
-                ('cut_val_min', ctypes.c_double * 7), ('cut_val_max', ctypes.c_double * 7)]
+                ('cut_val_min', ctypes.c_double * 7), ('cut_val_max', ctypes.c_double * 7)] + \
+               [(n, ctypes.c_double) for n in ('fallback_rho', 'fallback_pgas', 'fallback_kappa')]
 
 CUT_VALUES = ('rho', 'n_e', 'p_gas', 'theta_e', 'b', 'sigma', 'beta_inverse')
 
@@ -166,7 +167,8 @@ def simulation_image(kv, s, mom, grid, want_inds=True, camera_x=None, render=Fal
             cut_omit_near=int(kv.get('cut_omit_near', 'false') == 'true'), cut_omit_far=int(kv.get('cut_omit_far', 'false') == 'true'),
             cut_plane=int(kv.get('cut_plane', 'false') == 'true'),
             cut_midplane_theta=float(kv.get('cut_midplane_theta', 0.0)) * np.pi / 180.0,
-            cut_midplane_z=float(kv.get('cut_midplane_z', 0.0)))
+            cut_midplane_z=float(kv.get('cut_midplane_z', 0.0)), fallback_rho=float(kv.get('fallback_rho', 0.0)),
+            fallback_pgas=float(kv.get('fallback_pgas', 0.0)), fallback_kappa=float(kv.get('fallback_kappa', 0.0)))
     triple = lambda key: (ctypes.c_double * 3)(*[float(v) for v in kv.get(key, '0,0,0').split(',')])
     P.cut_plane_origin, P.cut_plane_normal = triple('cut_plane_origin'), triple('cut_plane_normal')
     # the sigma maximum is the struct's own cut_sigma_max

@@ -63,6 +63,9 @@ CPU_CASES = {
     'cpu_simulation_cuts_e_16': {'cut_rho_max': '4.0e-17', 'cut_theta_e_min': '3.2', 'cut_b_min': '30.0', 'cut_n_e_min': '1.5e7',
                                  'cut_p_gas_max': '1000.0', 'cut_beta_inverse_min': '6.0e-2', 'cut_sigma_max': '4.5e-3',
                                  'camera_resolution': '16'},
+    # all 27 auxiliary images kept: the fallback values only show in the cell-value averages
+    'cpu_simulation_fallback_values_16': dict(AUX_SIM, fallback_nan='false', fallback_rho='1.0e-6', fallback_pgas='1.0e-8',
+                                              camera_r='80.0', camera_width='60.0', camera_resolution='16'),
     'cpu_simulation_code_kappa_16': {'plasma_model': 'code_kappa', 'simulation_kappa_name': 'r0', 'camera_resolution': '16'},
     'cpu_simulation_code_kappa_nearest_16': {'plasma_model': 'code_kappa', 'simulation_kappa_name': 'r0',
                                              'simulation_interp': 'false', 'camera_resolution': '16'},
@@ -86,7 +89,8 @@ def main():
         with tempfile.TemporaryDirectory() as d:
             mock = dict(entropy=True) if over.get('plasma_model') == 'code_kappa' else None
             ref = Case(d, 'simulation.input', over, mock=mock, threads=8).run_reference(checkpoints=False)
-            np.savez_compressed(os.path.join(os.environ.get('GOLDEN_OUT', HERE), name + '.npz'), I_nu=ref['npz']['I_nu'])
+            keep = ref['npz'] if 'image_tau_int' in over else {'I_nu': ref['npz']['I_nu']}
+            np.savez_compressed(os.path.join(os.environ.get('GOLDEN_OUT', HERE), name + '.npz'), **keep)
             print(name, ref['npz']['I_nu'].shape)
     for name, (base, over, mock) in CASES.items():
         if only and name not in only:

@@ -342,6 +342,37 @@ def test_oracle_cuts(name, tmp_path):
     assert np.nansum(ref) / ref.size < 0.9 * np.nansum(full) / full.size
 
 
+def test_oracle_fallback_values(tmp_path):
+    """fallback_nan = false with a camera field of view wider than the grid: samples outside the grid carry
+    fallback_rho / fallback_pgas with zero velocity and field (simulation_sampling.cpp:695-708), poorly terminated
+    rays are integrated rather than blanked; visible in the cell-value averages.  All 27 auxiliary images against the
+    unmodified reference's."""
+    import sys
+    sys.path.insert(0, GOLDEN)
+    from make_golden import CPU_CASES
+    kv = load_input('simulation.input')
+    kv.update(CPU_CASES['cpu_simulation_fallback_values_16'])
+    path = os.path.join(tmp_path, 'o.input')
+    write_input(path, kv)
+    cfg = bl.Config(path)
+    grid = mock_snapshot.grid_view_arrays(mock_snapshot.make_mock(None))
+    pos, dirs, fac = cfg.camera_root()
+    s = oracle_lib.trace(kv, float(kv['simulation_a']), pos, dirs)
+    image, aux = oracle_lib.simulation_image(kv, s, fac, grid, want_inds=False, camera_x=cfg.camera_frame()['cam_x'])
+    gold = np.load(os.path.join(GOLDEN, 'cpu_simulation_fallback_values_16.npz'))
+    for name in ['I_nu'] + oracle_lib.AUX_NAMES:
+        ref = gold[name]
+        got = (image if name == 'I_nu' else aux[name]).reshape(16, 16)
+        assert np.array_equal(np.isnan(got), np.isnan(ref)), name
+        ok = ~np.isnan(ref)
+        scale = np.maximum(np.maximum(np.abs(ref[ok]), 1e-12 * np.nanmax(np.abs(ref))), 1e-300)
+        assert float(np.max(np.abs(got[ok] - ref[ok]) / scale)) < 1e-9, name
+    # the fallback samples (52 < r < 80, outside the grid) are in those averages: another fallback density moves them
+    _, other = oracle_lib.simulation_image(dict(kv, fallback_rho='1.0e-3'), s, fac, grid, want_inds=False,
+                                           camera_x=cfg.camera_frame()['cam_x'])
+    assert np.nanmin(np.abs(other['lambda_ave_rho'] / aux['lambda_ave_rho'] - 1.0)) > 1e-3
+
+
 def test_refinement_restatement_against_reference_fixture(tmp_path):
     """Adaptive refinement decision (EvaluateBlock, radiation_adaptive.cpp:163-312; child order camera.cpp:445-459): the
     numpy restatement applied to the unmodified reference's level-0 image reproduces the reference's list of level-1
