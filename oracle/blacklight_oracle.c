@@ -11,11 +11,14 @@
  *   Hamiltonian right-hand side with proper distance       geodesics.cpp:867-893
  *   Dormand-Prince RK5(4)7M integrator with dense output   geodesics.cpp:39-324
  *   truncation, momentum renormalisation, reversal         geodesics.cpp:327-371, 808-849
+ *   fixed-step RK4 / RK2 integrators                       geodesics.cpp:418-805
  *   formula-model coefficients                             formula_coefficients.cpp:25-183
  *   grid sampling (block/cell search, nearest, trilinear)  simulation_sampling.cpp:122-575, 636-1044
  *   thermal synchrotron I coefficients                     simulation_coefficients.cpp:254-524
  *   power-law synchrotron I coefficients and constants     simulation_coefficients.cpp:53-66, 559-585
  *   kappa-distribution I coefficients and constants        simulation_coefficients.cpp:82-105, 608-653, 740-773
+ *   electron temperature: ti_te_beta (p or energies), code_kappa   simulation_coefficients.cpp:333-358
+ *   geometric and cell-value cuts, value fallback          simulation_sampling.cpp:245-295, 695-708; simulation_coefficients.cpp:361-375
  *   Cartesian Kerr-Schild grids (simulation_coord = cks)   radiation_geometry.cpp:37-57, 425-457
  *   fluid-frame tetrad                                     radiation_geometry.cpp:597-658
  *   unpolarized transfer, auxiliary images (both models)   unpolarized.cpp:31-221
@@ -265,6 +268,76 @@ int orc_trace_dp(const orc_geo *g, long n_rays, const double *cam_pos, const dou
       }
     }
     /* renormalise stored momenta, reverse (geodesics.cpp:352-371, 808-849) */
+    for (n = 0; n < count; n++) {
+      renormalize(g, gp + (size_t)n * 9, gp + (size_t)n * 9 + 4);
+      size_t o = (size_t)m * cap + (size_t)(count - 1 - n);
+      for (p = 0; p < 4; p++) { pos[4 * o + p] = gp[(size_t)n * 9 + p]; dir[4 * o + p] = gp[(size_t)n * 9 + 4 + p]; }
+      len[o] = -gp[(size_t)n * 9 + 8];
+    }
+    num[m] = count;
+    flags[m] = (unsigned char)flag;
+    if (count > steps_max) steps_max = count;
+    free(gp);
+  }
+  return steps_max;
+}
+
+/* Fixed-step integrators, ray_integrator = rk4 (order 4, geodesics.cpp:418-623) and rk2 (order 2, :626-805).
+ * Step h = -ray_step (r - r_horizon) from the radius at the start of the step.  rk4 stores the mean of the step's two
+ * end states, rk2 the half-step state reached with the first slope; the carried momentum is renormalised after each
+ * step, the last allowed step flags the ray.  Truncation, renormalisation of the stored momenta and reversal are the
+ * adaptive integrator's. */
+int orc_trace_rk(const orc_geo *g, int order, long n_rays, const double *cam_pos, const double *cam_dir, int cap, int *num,
+                 unsigned char *flags, double *pos, double *dir, double *len) {
+  int steps_max = 0;
+  long m;
+  double r_horizon = 1.0 + sqrt(1.0 - g->a * g->a);
+#pragma omp parallel for schedule(dynamic, 4) reduction(max : steps_max)
+  for (m = 0; m < n_rays; m++) {
+    int ms = g->max_steps, p, n, count = 0, flag = 0;
+    double *gp = (double *)malloc((size_t)ms * 9 * sizeof(double));
+    double y[9], ys[9], acc[9], k[9];
+    for (p = 0; p < 4; p++) { y[p] = cam_pos[4 * m + p]; y[4 + p] = cam_dir[4 * m + p]; }
+    y[8] = ys[8] = 0.0;
+    double r_new = ks_radius(g->a, y[1], y[2], y[3]);
+    for (n = 0; n < ms; n++) {
+      double r = r_new, h = -g->ray_step * (r - r_horizon);
+      double *rec = gp + (size_t)n * 9;
+      if (order == 4) {
+        static const double node[4] = {0.0, 0.5, 0.5, 1.0}, weight[4] = {1.0 / 6.0, 1.0 / 3.0, 1.0 / 3.0, 1.0 / 6.0};
+        int st;
+        for (st = 0; st < 4; st++) {
+          if (st == 0) for (p = 0; p < 8; p++) ys[p] = y[p];
+          else for (p = 0; p < 8; p++) ys[p] = y[p] + node[st] * h * k[p];
+          rhs(g, ys, k);
+          if (st == 0) for (p = 0; p < 8; p++) acc[p] = y[p] + weight[st] * h * k[p];
+          else for (p = 0; p < 8; p++) acc[p] += weight[st] * h * k[p];
+        }
+        for (p = 0; p < 8; p++) rec[p] = 0.5 * (y[p] + acc[p]);
+        for (p = 0; p < 8; p++) y[p] = acc[p];
+      } else {
+        rhs(g, y, k);
+        for (p = 0; p < 8; p++) ys[p] = y[p] + h * k[p];
+        for (p = 0; p < 8; p++) y[p] += 1.0 / 2.0 * h * k[p];
+        for (p = 0; p < 8; p++) rec[p] = y[p];
+        rhs(g, ys, k);
+        for (p = 0; p < 8; p++) y[p] += 1.0 / 2.0 * h * k[p];
+      }
+      rec[8] = h;
+      renormalize(g, y, y + 4);
+      count++;
+      r_new = ks_radius(g->a, y[1], y[2], y[3]);
+      if ((r_new > g->camera_r && r_new > r) || r_new < g->r_terminate) break;
+      if (n + 1 >= ms) flag = 1;
+    }
+    if (count > 1) {
+      double rn = ks_radius(g->a, gp[1], gp[2], gp[3]);
+      for (n = 1; n < count; n++) {
+        double ro = rn;
+        rn = ks_radius(g->a, gp[(size_t)n * 9 + 1], gp[(size_t)n * 9 + 2], gp[(size_t)n * 9 + 3]);
+        if ((rn > g->camera_r && rn > ro) || rn < g->r_terminate) { count = n; break; }
+      }
+    }
     for (n = 0; n < count; n++) {
       renormalize(g, gp + (size_t)n * 9, gp + (size_t)n * 9 + 4);
       size_t o = (size_t)m * cap + (size_t)(count - 1 - n);

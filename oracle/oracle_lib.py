@@ -55,6 +55,7 @@ def lib():
     if _lib is None:
         _lib = ctypes.CDLL(LIB)
         _lib.orc_trace_dp.restype = ctypes.c_int
+        _lib.orc_trace_rk.restype = ctypes.c_int
     return _lib
 
 
@@ -73,8 +74,13 @@ def trace(kv, a, cam_pos, cam_dir):
     n, cap = len(cam_pos), g.max_steps
     num, flags = np.zeros(n, np.int32), np.zeros(n, np.uint8)
     pos, dirs, length = np.zeros((n, cap, 4)), np.zeros((n, cap, 4)), np.zeros((n, cap))
-    steps = lib().orc_trace_dp(ctypes.byref(g), ctypes.c_long(n), _p(np.ascontiguousarray(cam_pos)),
-                               _p(np.ascontiguousarray(cam_dir)), cap, _p(num), _p(flags), _p(pos), _p(dirs), _p(length))
+    args = (ctypes.c_long(n), _p(np.ascontiguousarray(cam_pos)), _p(np.ascontiguousarray(cam_dir)), cap, _p(num),
+            _p(flags), _p(pos), _p(dirs), _p(length))
+    kind = kv.get('ray_integrator', 'dp')
+    if kind == 'dp':
+        steps = lib().orc_trace_dp(ctypes.byref(g), *args)
+    else:
+        steps = lib().orc_trace_rk(ctypes.byref(g), {'rk4': 4, 'rk2': 2}[kind], *args)
     return dict(num=num, flags=flags, pos=pos, dir=dirs, len=length, steps=steps, cap=cap)
 
 

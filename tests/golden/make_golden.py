@@ -38,6 +38,11 @@ CASES = {
     'adaptive_32': ('adaptive.input', {}, None),
     'render_32': ('render.input', {'camera_resolution': 32}, None),
     'true_color_16': ('true_color.input', {'camera_resolution': 16}, None),
+    'simulation_rk4_16': ('simulation.input', {'camera_resolution': 16, 'ray_integrator': 'rk4', 'ray_step': '0.02'}, None),
+    'simulation_rk2_kerr_16': ('simulation.input', {'camera_resolution': 16, 'ray_integrator': 'rk2', 'ray_step': '0.02',
+                                                    'simulation_a': '0.9', 'camera_th': '80.0'}, None),
+    'formula_rk4_max_steps_12': ('formula.input', {'camera_resolution': 12, 'ray_integrator': 'rk4', 'ray_step': '0.02',
+                                                   'ray_max_steps': 600}, None),
     'formula_pinhole_pole_12': ('formula.input', {'camera_resolution': 12, 'camera_type': 'pinhole', 'camera_th': '180.0',
                                                   'camera_r': '100.0', 'camera_urn': '-0.05', 'camera_rotation': '25.0'}, None),
 }

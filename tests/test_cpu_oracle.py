@@ -41,7 +41,7 @@ def check_samples(s, gold):
     return mask
 
 
-@pytest.mark.parametrize('name', ['formula_16', 'formula_pinhole_pole_12'])
+@pytest.mark.parametrize('name', ['formula_16', 'formula_pinhole_pole_12', 'formula_rk4_max_steps_12'])
 def test_oracle_formula(name, tmp_path):
     kv, cfg, gold, _ = setup(name, tmp_path)
     pos, dirs, fac = cfg.camera_root()
@@ -56,7 +56,8 @@ def test_oracle_formula(name, tmp_path):
     assert np.max(np.abs(got[ok] - ref[ok]) / np.maximum(np.abs(ref[ok]), 1e-300)) < 1e-12
 
 
-@pytest.mark.parametrize('name', ['simulation_32', 'simulation_nearest_24', 'simulation_blocks_24', 'simulation_kerr_24'])
+@pytest.mark.parametrize('name', ['simulation_32', 'simulation_nearest_24', 'simulation_blocks_24', 'simulation_kerr_24',
+                                  'simulation_rk4_16', 'simulation_rk2_kerr_16'])
 def test_oracle_simulation(name, tmp_path):
     kv, cfg, gold, mock = setup(name, tmp_path)
     mock = dict(mock or {})
