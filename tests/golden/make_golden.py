@@ -43,6 +43,9 @@ CASES = {
                                                     'simulation_a': '0.9', 'camera_th': '80.0'}, None),
     'formula_rk4_max_steps_12': ('formula.input', {'camera_resolution': 12, 'ray_integrator': 'rk4', 'ray_step': '0.02',
                                                    'ray_max_steps': 600}, None),
+    'formula_photon_12': ('formula.input', {'camera_resolution': 12, 'ray_terminate': 'photon', 'formula_spin': '0.7'}, None),
+    'formula_additive_12': ('formula.input', {'camera_resolution': 12, 'ray_terminate': 'additive', 'ray_factor': '0.3',
+                                              'image_normalization': 'camera'}, None),
     'formula_pinhole_pole_12': ('formula.input', {'camera_resolution': 12, 'camera_type': 'pinhole', 'camera_th': '180.0',
                                                   'camera_r': '100.0', 'camera_urn': '-0.05', 'camera_rotation': '25.0'}, None),
 }

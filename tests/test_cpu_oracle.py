@@ -41,7 +41,8 @@ def check_samples(s, gold):
     return mask
 
 
-@pytest.mark.parametrize('name', ['formula_16', 'formula_pinhole_pole_12', 'formula_rk4_max_steps_12'])
+@pytest.mark.parametrize('name', ['formula_16', 'formula_pinhole_pole_12', 'formula_rk4_max_steps_12', 'formula_photon_12',
+                                  'formula_additive_12'])
 def test_oracle_formula(name, tmp_path):
     kv, cfg, gold, _ = setup(name, tmp_path)
     pos, dirs, fac = cfg.camera_root()
