@@ -19,6 +19,7 @@
  *   kappa-distribution I coefficients and constants        simulation_coefficients.cpp:82-105, 608-653, 740-773
  *   electron temperature: ti_te_beta (p or energies), code_kappa   simulation_coefficients.cpp:333-358
  *   geometric and cell-value cuts, value fallback          simulation_sampling.cpp:245-295, 695-708; simulation_coefficients.cpp:361-375
+ *   slow light: time slice per sample, nearest / blended   simulation_sampling.cpp:297-349, 736-775, 840-905
  *   Cartesian Kerr-Schild grids (simulation_coord = cks)   radiation_geometry.cpp:37-57, 425-457
  *   fluid-frame tetrad                                     radiation_geometry.cpp:597-658
  *   unpolarized transfer, auxiliary images (both models)   unpolarized.cpp:31-221
@@ -520,6 +521,10 @@ typedef struct {
   /* fallback_nan = false: samples outside the grid take these values, zero velocity and field, stored as float
      (simulation_sampling.cpp:695-708; radiation_integrator.hpp:182-187) */
   double fallback_rho, fallback_pgas, fallback_kappa;
+  /* slow light (simulation_sampling.cpp:297-349, 736-775, 840-905): n_t > 0 time slices in prim, newest first, at
+     times[]; a sample at coordinate time t is looked up at t + snapshot_time; nearest slice or linear blend */
+  int n_t, slow_interp;
+  double snapshot_time, times[64];
 } orc_sim;
 
 /* one feature of a false-colour render image (rendering.cpp:100-165): type 0 fill, 1 thresh, 2 rise, 3 fall */
@@ -558,6 +563,55 @@ static double trilinear(const float *prim, const orc_sim *P, int v, int b, int k
 }
 
 /* orthonormal tetrad (radiation_geometry.cpp:597-658) */
+/* rho, pgas, uu1-3, bb1-3, entropy of one time slice at a located sample: the cell's own values, or trilinear with
+   the non-positive fallback of rho, pgas and entropy (simulation_sampling.cpp:716-733, 796-835) */
+static void slice_values(const float *prim, const orc_sim *P, int b, int k, int j, int i, double fk, double fj, double fi,
+                         double out[9]) {
+  int q;
+  out[8] = 0.0;
+  if (!P->interp) {
+    for (q = 0; q < 8; q++) out[q] = g4(prim, P, q, b, k, j, i);
+    if (P->code_kappa) out[8] = g4(prim, P, 8, b, k, j, i);
+    return;
+  }
+  for (q = 0; q < 8; q++) out[q] = trilinear(prim, P, q, b, k, j, i, fk, fj, fi);
+  if (out[0] <= 0.0) out[0] = g4(prim, P, 0, b, k, j, i);
+  if (out[1] <= 0.0) out[1] = g4(prim, P, 1, b, k, j, i);
+  if (P->code_kappa) {
+    out[8] = trilinear(prim, P, 8, b, k, j, i, fk, fj, fi);
+    if (out[8] <= 0.0) out[8] = g4(prim, P, 8, b, k, j, i);
+  }
+}
+
+/* slow light: the values at time slice t_ind, or blended with slice t_ind + 1 (simulation_sampling.cpp:736-775, 840-905) */
+static void slow_values(const float *prim, const orc_sim *P, int t_ind, double t_frac, int b, int k, int j, int i, double fk,
+                        double fj, double fi, double out[9]) {
+  size_t stride = (size_t)(P->code_kappa ? 9 : 8) * P->n_b * P->n_k * P->n_j * P->n_i;
+  double next[9];
+  int q;
+  slice_values(prim + (size_t)t_ind * stride, P, b, k, j, i, fk, fj, fi, out);
+  if (!P->slow_interp) return;
+  slice_values(prim + (size_t)(t_ind + 1) * stride, P, b, k, j, i, fk, fj, fi, next);
+  for (q = 0; q < 9; q++) out[q] = (1.0 - t_frac) * out[q] + t_frac * next[q];
+}
+
+/* time slice of a sample at coordinate time x0 (simulation_sampling.cpp:297-349); times[] descend */
+static void slow_slice(const orc_sim *P, double x0, int *t_out, double *frac_out) {
+  int t = 0, n = P->n_t;
+  double frac = 0.0;
+  if (x0 >= P->times[0]) {
+  } else if (x0 <= P->times[n - 1]) {
+    if (P->slow_interp) { t = n - 2; frac = 1.0; }
+    else t = n - 1;
+  } else {
+    while (P->times[t] > x0) t++;
+    if (P->slow_interp) { t--; frac = (x0 - P->times[t]) / (P->times[t + 1] - P->times[t]); }
+    else if (P->times[t - 1] - x0 <= x0 - P->times[t]) t--;
+  }
+  *t_out = t;
+  *frac_out = frac;
+}
+
 static void tetrad(const double ucon[4], const double ucov[4], const double kcon[4], const double kcov[4],
                    const double up[4], double gcov[4][4], double gcon[4][4], double e[4][4]) {
   int m, n;
@@ -626,7 +680,8 @@ void orc_simulation_image(const orc_sim *P, long n_rays, int cap, const int *num
       const double *kcov = dir + 4 * o;
       double dl_cgs = len[o] * P->x_unit / (freq * mom_factor[m]);
       double jv = 0.0, av = 0.0;
-      double rho, pgas, uu[3], bb[3], entropy = 0.0;
+      double rho, pgas, uu[3], bb[3], entropy = 0.0, sv[9], t_frac = 0.0;
+      int t_ind = 0;
       int have = 0;
       if (inds) for (i = 0; i < 4; i++) inds[4 * o + i] = -1;
       if (P->fallback_nan && flags[m]) {
@@ -655,6 +710,7 @@ void orc_simulation_image(const orc_sim *P, long n_rays, int cap, const int *num
           x3 += x3 < 0.0 ? 2.0 * PI : 0.0;
           x3 -= x3 >= 2.0 * PI ? 2.0 * PI : 0.0;
           if (P->coord == 1) { x1 = x; x2 = y; x3 = z; }   /* radiation_geometry.cpp:37-57: cks keeps x, y, z */
+          if (P->n_t > 0) slow_slice(P, pos[4 * o] + P->snapshot_time, &t_ind, &t_frac);
           /* block: keep while inside (inclusive), else first match (simulation_sampling.cpp:352-394) */
           if (x1 < x1f[(size_t)b * (n_i + 1)] || x1 > x1f[(size_t)b * (n_i + 1) + n_i] || x2 < x2f[(size_t)b * (n_j + 1)] ||
               x2 > x2f[(size_t)b * (n_j + 1) + n_j] || x3 < x3f[(size_t)b * (n_k + 1)] || x3 > x3f[(size_t)b * (n_k + 1) + n_k]) {
@@ -682,6 +738,7 @@ void orc_simulation_image(const orc_sim *P, long n_rays, int cap, const int *num
             rho = g4(prim, P, 0, b, k, j, i); pgas = g4(prim, P, 1, b, k, j, i);
             for (mu = 0; mu < 3; mu++) { uu[mu] = g4(prim, P, 2 + mu, b, k, j, i); bb[mu] = g4(prim, P, 5 + mu, b, k, j, i); }
             if (P->code_kappa) entropy = g4(prim, P, 8, b, k, j, i);
+            if (P->n_t > 0) slow_values(prim, P, t_ind, t_frac, b, k, j, i, 0.0, 0.0, 0.0, sv);
           } else {
             const double *v1 = x1v + (size_t)b * n_i, *v2 = x2v + (size_t)b * n_j, *v3 = x3v + (size_t)b * n_k;
             int im = (i == 0 || (i != n_i - 1 && x1 >= v1[i])) ? i : i - 1;
@@ -703,6 +760,11 @@ void orc_simulation_image(const orc_sim *P, long n_rays, int cap, const int *num
               uu[mu] = trilinear(prim, P, 2 + mu, b, km, jm, im, fk, fj, fi);
               bb[mu] = trilinear(prim, P, 5 + mu, b, km, jm, im, fk, fj, fi);
             }
+            if (P->n_t > 0) slow_values(prim, P, t_ind, t_frac, b, km, jm, im, fk, fj, fi, sv);
+          }
+          if (P->n_t > 0) {
+            rho = sv[0]; pgas = sv[1]; entropy = sv[8];
+            for (mu = 0; mu < 3; mu++) { uu[mu] = sv[2 + mu]; bb[mu] = sv[5 + mu]; }
           }
           /* sampled values are stored as float (simulation_sampling.cpp:830-839) */
           rho = (double)(float)rho; pgas = (double)(float)pgas; entropy = (double)(float)entropy;

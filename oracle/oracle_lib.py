@@ -33,7 +33,9 @@ class Sim(ctypes.Structure):
                 ('cut_cam', ctypes.c_double * 3), ('cut_midplane_theta', ctypes.c_double), ('cut_midplane_z', ctypes.c_double),
                 ('cut_plane_origin', ctypes.c_double * 3), ('cut_plane_normal', ctypes.c_double * 3),
                 ('cut_val_min', ctypes.c_double * 7), ('cut_val_max', ctypes.c_double * 7)] + \
-               [(n, ctypes.c_double) for n in ('fallback_rho', 'fallback_pgas', 'fallback_kappa')]
+               [(n, ctypes.c_double) for n in ('fallback_rho', 'fallback_pgas', 'fallback_kappa')] + \
+               [('n_t', ctypes.c_int), ('slow_interp', ctypes.c_int), ('snapshot_time', ctypes.c_double),
+                ('times', ctypes.c_double * 64)]
 
 CUT_VALUES = ('rho', 'n_e', 'p_gas', 'theta_e', 'b', 'sigma', 'beta_inverse')
 
@@ -153,7 +155,7 @@ def render_features(kv):
     return (Feature * len(feats))(*feats), len(feats)
 
 
-def simulation_image(kv, s, mom, grid, want_inds=True, camera_x=None, render=False, cut_camera_x=None):
+def simulation_image(kv, s, mom, grid, want_inds=True, camera_x=None, render=False, cut_camera_x=None, slow=None):
     """camera_x given: also the 27 auxiliary images, returned as a dict name -> (n) array in place of the indices.
     render: also the false-colour images (render_num_images, 3, n) of the input file's render_* features, as a third value."""
     a = float(kv['simulation_a'])
@@ -182,6 +184,10 @@ def simulation_image(kv, s, mom, grid, want_inds=True, camera_x=None, render=Fal
     P.cut_val_max = (ctypes.c_double * 7)(*[-1.0 if v == 'sigma' else float(kv.get('cut_%s_max' % v, -1.0)) for v in CUT_VALUES])
     if P.cut_omit_near or P.cut_omit_far:
         P.cut_cam = (ctypes.c_double * 3)(*[float(v) for v in cut_camera_x[1:4]])
+    if slow is not None:   # dict(times=descending slice times, snapshot_time=...); grid['prim'] is (n_t, n_var, ...)
+        P.n_t, P.slow_interp, P.snapshot_time = len(slow['times']), int(kv['slow_interp'] == 'true'), float(slow['snapshot_time'])
+        for q, t in enumerate(slow['times']):
+            P.times[q] = float(t)
     n = len(mom)
     image = np.zeros(n)
     inds = np.full((n, s['cap'], 4), -1, np.int32) if want_inds else None
@@ -200,3 +206,15 @@ def simulation_image(kv, s, mom, grid, want_inds=True, camera_x=None, render=Fal
     if aux is not None:
         return image, dict(zip(AUX_NAMES, aux))
     return image, inds
+
+
+def slow_window(file_times, chunk, snapshot_time, first=0):
+    """Files resident for the first image of a slow-light run (simulation_reader.cpp:211-262): reading starts with
+    file first + chunk - 1 and advances until a file's time reaches snapshot_time (or the series ends); the window is
+    that file and the chunk - 1 before it, newest first.  Returns the file numbers."""
+    latest = first + chunk - 2
+    latest_time = -np.inf
+    while latest_time < snapshot_time and latest < first + len(file_times) - 1:
+        latest += 1
+        latest_time = file_times[latest - first]
+    return [latest - q for q in range(chunk)]

@@ -79,6 +79,51 @@ CPU_CASES = {
                                              'simulation_interp': 'false', 'camera_resolution': '16'},
 }
 
+# slow light: a 12-file time series of small mock snapshots; first image only (snapshot time = slow_t_start)
+SLOW_CASES = {
+    'cpu_slow_light_blend_12': {'slow_interp': 'true'},
+    'cpu_slow_light_nearest_slice_12': {'slow_interp': 'false'},
+    'cpu_slow_light_blend_nearest_cell_12': {'slow_interp': 'true', 'simulation_interp': 'false'},
+}
+SLOW_FILES, SLOW_DT_FILE = 12, 25.0
+
+
+def slow_light_setup(d, over):
+    """Writes the series under d/data and returns (input keys, list of per-file grids).  Shared with the CPU test."""
+    from harness import load_input
+    from blacklight_b200 import mock_snapshot as ms
+    os.makedirs(os.path.join(d, 'data'), exist_ok=True)
+    grids = []
+    for n in range(SLOW_FILES):
+        grid = ms.to_blocks(ms.mock_fields(n_r=32, n_th=16, n_ph=32, pert_amp=0.1 + 0.05 * n), (1, 1, 2))
+        ms.write_athdf(os.path.join(d, 'data', 'mock.%05d.athdf' % n), grid, time=SLOW_DT_FILE * n)
+        grids.append(grid)
+    kv = load_input('simulation.input')
+    kv.update({'camera_resolution': '12', 'simulation_file': os.path.join(d, 'data', 'mock.{05d}.athdf'),
+               'simulation_multiple': 'true', 'simulation_start': '0', 'simulation_end': str(SLOW_FILES - 1),
+               'slow_light_on': 'true', 'slow_chunk_size': '8', 'slow_t_start': '200.0', 'slow_dt': '20.0',
+               'slow_num_images': '1', 'slow_offset': '0', 'output_file': os.path.join(d, 'img.{03d}.npz'),
+               'num_threads': '8'})
+    kv.update(over)
+    return kv, grids
+
+
+def make_slow(only):
+    import subprocess
+    from harness import REF_BIN, write_input
+    for name, over in SLOW_CASES.items():
+        if only and name not in only:
+            continue
+        with tempfile.TemporaryDirectory() as d:
+            kv, _ = slow_light_setup(d, over)
+            path = os.path.join(d, 'ref.input')
+            write_input(path, kv)
+            proc = subprocess.run([REF_BIN, path], cwd=d, capture_output=True, text=True, timeout=3600)
+            assert proc.returncode == 0 and 'Calculation completed' in proc.stdout, proc.stdout + proc.stderr
+            image = np.load(os.path.join(d, 'img.000.npz'))['I_nu']
+            np.savez_compressed(os.path.join(os.environ.get('GOLDEN_OUT', HERE), name + '.npz'), I_nu=image)
+            print(name, image.shape, float(np.nanmax(image)))
+
 
 def masked_inds_crc(geo, samp, sim_interp):
     num = geo['sample_num']
@@ -91,6 +136,7 @@ def masked_inds_crc(geo, samp, sim_interp):
 
 def main():
     only = sys.argv[1:]
+    make_slow(only)
     for name, over in CPU_CASES.items():
         if only and name not in only:
             continue

@@ -375,6 +375,41 @@ def test_oracle_fallback_values(tmp_path):
     assert np.nanmin(np.abs(other['lambda_ave_rho'] / aux['lambda_ave_rho'] - 1.0)) > 1e-3
 
 
+@pytest.mark.parametrize('name', ['cpu_slow_light_blend_12', 'cpu_slow_light_nearest_slice_12',
+                                  'cpu_slow_light_blend_nearest_cell_12'])
+def test_oracle_slow_light(name, tmp_path):
+    """slow_light_on: which files of a time series are resident for the first image (simulation_reader.cpp:211-262),
+    the time slice of each sample at its coordinate time + snapshot time and the nearest-slice / blended values
+    (simulation_sampling.cpp:297-349, 736-775, 840-905), against the unmodified reference's image."""
+    import sys
+    sys.path.insert(0, GOLDEN)
+    from make_golden import SLOW_CASES, SLOW_DT_FILE, slow_light_setup
+    kv, grids = slow_light_setup(str(tmp_path), SLOW_CASES[name])
+    path = os.path.join(tmp_path, 'o.input')
+    write_input(path, kv)
+    cfg = bl.Config(path)
+    file_times = [SLOW_DT_FILE * n for n in range(len(grids))]
+    snapshot_time = float(kv['slow_t_start'])
+    window = oracle_lib.slow_window(file_times, int(kv['slow_chunk_size']), snapshot_time)
+    assert window == [8, 7, 6, 5, 4, 3, 2, 1]
+    views = [mock_snapshot.grid_view_arrays(grids[n]) for n in window]
+    grid = dict(views[0], prim=np.ascontiguousarray(np.stack([v['prim'] for v in views]), np.float32))
+    pos, dirs, fac = cfg.camera_root()
+    s = oracle_lib.trace(kv, float(kv['simulation_a']), pos, dirs)
+    slow = dict(times=[file_times[n] for n in window], snapshot_time=snapshot_time)
+    image, _ = oracle_lib.simulation_image(kv, s, fac, grid, want_inds=False, slow=slow)
+    ref = np.load(os.path.join(GOLDEN, name + '.npz'))['I_nu']
+    got = image.reshape(12, 12)
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    scale = np.maximum(np.abs(ref[ok]), 1e-12 * np.nanmax(np.abs(ref)))
+    assert np.max(np.abs(got[ok] - ref[ok]) / scale) < 1e-10
+    # the image is not that of any single file of the window
+    for v in views:
+        frozen, _ = oracle_lib.simulation_image(kv, s, fac, v, want_inds=False)
+        assert np.nanmax(np.abs(frozen.reshape(12, 12)[ok] - ref[ok]) / scale) > 1e-3
+
+
 def test_refinement_restatement_against_reference_fixture(tmp_path):
     """Adaptive refinement decision (EvaluateBlock, radiation_adaptive.cpp:163-312; child order camera.cpp:445-459): the
     numpy restatement applied to the unmodified reference's level-0 image reproduces the reference's list of level-1
