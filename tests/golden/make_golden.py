@@ -25,6 +25,11 @@ AUX = {'image_time': 'true', 'image_length': 'true', 'image_lambda': 'true', 'im
        'image_tau': 'true', 'image_crossings': 'true'}
 AUX_SIM = dict(AUX, image_lambda_ave='true', image_emission_ave='true', image_tau_int='true')
 
+def amr_refine(bi, bj, bk):
+    """Root blocks of the two-level mock mesh that are replaced by their eight children."""
+    return bi == 0 and bj == 1
+
+
 CASES = {
     'formula_16': ('formula.input', {'camera_resolution': 16}, None),
     'formula_aux_12': ('formula.input', dict(AUX, camera_resolution=12), None),
@@ -46,6 +51,8 @@ CASES = {
     'formula_photon_12': ('formula.input', {'camera_resolution': 12, 'ray_terminate': 'photon', 'formula_spin': '0.7'}, None),
     'formula_additive_12': ('formula.input', {'camera_resolution': 12, 'ray_terminate': 'additive', 'ray_factor': '0.3',
                                               'image_normalization': 'camera'}, None),
+    'simulation_amr_16': ('simulation.input', {'camera_resolution': 16},
+                          {'blocks': (2, 2, 4), 'n_r': 32, 'n_th': 16, 'n_ph': 32, 'refine': amr_refine}),
     'formula_pinhole_pole_12': ('formula.input', {'camera_resolution': 12, 'camera_type': 'pinhole', 'camera_th': '180.0',
                                                   'camera_r': '100.0', 'camera_urn': '-0.05', 'camera_rotation': '25.0'}, None),
 }

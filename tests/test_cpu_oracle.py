@@ -58,7 +58,7 @@ def test_oracle_formula(name, tmp_path):
 
 
 @pytest.mark.parametrize('name', ['simulation_32', 'simulation_nearest_24', 'simulation_blocks_24', 'simulation_kerr_24',
-                                  'simulation_rk4_16', 'simulation_rk2_kerr_16'])
+                                  'simulation_rk4_16', 'simulation_rk2_kerr_16', 'simulation_amr_16'])
 def test_oracle_simulation(name, tmp_path):
     kv, cfg, gold, mock = setup(name, tmp_path)
     mock = dict(mock or {})
