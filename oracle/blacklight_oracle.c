@@ -19,6 +19,7 @@
  *   kappa-distribution I coefficients and constants        simulation_coefficients.cpp:82-105, 608-653, 740-773
  *   electron temperature: ti_te_beta (p or energies), code_kappa   simulation_coefficients.cpp:333-358
  *   geometric and cell-value cuts, value fallback          simulation_sampling.cpp:245-295, 695-708; simulation_coefficients.cpp:361-375
+ *   inter-block trilinear anchors across refinement levels simulation_sampling.cpp:506-553, 1068-1331, 1365-1386
  *   slow light: time slice per sample, nearest / blended   simulation_sampling.cpp:297-349, 736-775, 840-905
  *   Cartesian Kerr-Schild grids (simulation_coord = cks)   radiation_geometry.cpp:37-57, 425-457
  *   fluid-frame tetrad                                     radiation_geometry.cpp:597-658
@@ -525,6 +526,11 @@ typedef struct {
      times[]; a sample at coordinate time t is looked up at t + snapshot_time; nearest slice or linear blend */
   int n_t, slow_interp;
   double snapshot_time, times[64];
+  /* simulation_block_interp = true (Athena++ / AthenaK meshes): trilinear anchors looked up across MeshBlocks
+     (simulation_sampling.cpp:506-553, 1068-1331, 1365-1386); levels (n_b), locations (n_b, 3) in i, j, k order,
+     n_3_root = root-grid cells in the third dimension.  Not combined with slow light here. */
+  int block_interp, n_3_root;
+  const int *levels, *locations;
 } orc_sim;
 
 /* one feature of a false-colour render image (rendering.cpp:100-165): type 0 fill, 1 thresh, 2 rise, 3 fall */
@@ -610,6 +616,94 @@ static void slow_slice(const orc_sim *P, double x0, int *t_out, double *frac_out
   }
   *t_out = t;
   *frac_out = frac;
+}
+
+static int mesh_find(const orc_sim *P, int level, const int want[3]) {
+  int b;
+  for (b = 0; b < P->n_b; b++)
+    if (P->levels[b] == level && P->locations[3 * b] == want[0] && P->locations[3 * b + 1] == want[1] &&
+        P->locations[3 * b + 2] == want[2])
+      return b;
+  return -1;
+}
+
+/* Anchor (block, k, j, i) for the cell index idx_in = (i, j, k) of block b, where components may be -1 or n (one cell
+ * beyond the block): the neighbouring block at the same level, else the coarser one, else the finer one (there shifted
+ * towards the sample), with phi periodic in spherical coordinates; directions without any neighbour are clamped
+ * (FindNearbyInds, simulation_sampling.cpp:1068-1331).  cell = (i, j, k) of the sample's own cell, x its coordinates,
+ * xv the three cell-centre arrays.  Integer divisions truncate as in the reference. */
+static void mesh_anchor(const orc_sim *P, const double *const xv[3], int b, const int idx_in[3], const int cell[3],
+                        const double x[3], int out[4]) {
+  int n[3] = {P->n_i, P->n_j, P->n_k}, idx[3], safe[3], upper[3], off[3], loc[3], want[3], sought[3];
+  int level = P->levels[b], d, e, ba, max_level = 0, inside = 1;
+  for (ba = 0; ba < P->n_b; ba++) if (P->levels[ba] > max_level) max_level = P->levels[ba];
+#define N3(l) ((P->n_3_root / P->n_k) << (l))
+  for (d = 0; d < 3; d++) {
+    idx[d] = idx_in[d];
+    loc[d] = P->locations[3 * b + d];
+    upper[d] = idx[d] > n[d] / 2;
+    safe[d] = idx[d] < 0 ? 0 : idx[d] > n[d] - 1 ? n[d] - 1 : idx[d];
+    off[d] = idx[d] != safe[d];
+    if (off[d]) inside = 0;
+  }
+  if (inside) { out[0] = b; out[1] = idx[2]; out[2] = idx[1]; out[3] = idx[0]; return; }
+  int wrap_low = P->coord == 0 && idx[2] == -1 && loc[2] == 0;
+  int wrap_high = P->coord == 0 && idx[2] == n[2] && loc[2] == N3(level) - 1;
+  for (ba = 0; ba < P->n_b; ba++) {
+    int la = P->levels[ba];
+    const int *q = P->locations + 3 * ba;
+    for (d = 0; d < 3; d++) {
+      if (!off[d]) continue;
+      int step = idx[d] == -1 ? -1 : 1, same = la == level, coarser = la == level - 1, finer = la == level + 1;
+      for (e = 0; e < 3; e++) {
+        same = same && q[e] == (e == d ? loc[e] + step : loc[e]);
+        coarser = coarser && q[e] == (e == d ? (loc[e] + step) / 2 : loc[e] / 2);
+        finer = finer && q[e] == (e == d ? (idx[d] == -1 ? loc[e] * 2 - 1 : loc[e] * 2 + 2) : loc[e] * 2 + upper[e]);
+      }
+      if (same || coarser || finer) off[d] = 0;
+      if (d == 2 && off[2] && (wrap_low || wrap_high)) {
+        int edge = wrap_low ? ((P->n_3_root / P->n_k) << la) - 1 : 0;
+        same = la == level && q[0] == loc[0] && q[1] == loc[1] && q[2] == edge;
+        coarser = la == level - 1 && q[0] == loc[0] / 2 && q[1] == loc[1] / 2 && q[2] == edge;
+        finer = la == level + 1 && q[0] == loc[0] * 2 + upper[0] && q[1] == loc[1] * 2 + upper[1] && q[2] == edge;
+        if (same || coarser || finer) off[2] = 0;
+      }
+    }
+  }
+  for (d = 0; d < 3; d++) if (off[d]) idx[d] = safe[d];
+  /* same level */
+  for (d = 0; d < 3; d++) {
+    want[d] = idx[d] == safe[d] ? loc[d] : idx[d] == -1 ? loc[d] - 1 : loc[d] + 1;
+    sought[d] = idx[d] == safe[d] ? idx[d] : idx[d] == -1 ? n[d] - 1 : 0;
+  }
+  wrap_low = P->coord == 0 && idx[2] == -1 && loc[2] == 0;
+  wrap_high = P->coord == 0 && idx[2] == n[2] && loc[2] == N3(level) - 1;
+  if (wrap_low) want[2] = N3(level) - 1;
+  if (wrap_high) want[2] = 0;
+  if ((ba = mesh_find(P, level, want)) >= 0) { out[0] = ba; out[1] = sought[2]; out[2] = sought[1]; out[3] = sought[0]; return; }
+  /* coarser level */
+  if (level - 1 >= 0) {
+    for (d = 0; d < 3; d++) {
+      want[d] = idx[d] == safe[d] ? loc[d] / 2 : idx[d] == -1 ? (loc[d] - 1) / 2 : (loc[d] + 1) / 2;
+      sought[d] = idx[d] == safe[d] ? (loc[d] % 2 * n[d] + idx[d]) / 2 : idx[d] == -1 ? n[d] - 1 : 0;
+    }
+    if (wrap_low) want[2] = N3(level - 1) - 1;
+    if (wrap_high) want[2] = 0;
+    if ((ba = mesh_find(P, level - 1, want)) >= 0) { out[0] = ba; out[1] = sought[2]; out[2] = sought[1]; out[3] = sought[0]; return; }
+  }
+  /* finer level */
+  for (d = 0; d < 3; d++) {
+    want[d] = loc[d] * 2 + (idx[d] == safe[d] ? 0 : idx[d] == -1 ? -1 : 1) + upper[d];
+    sought[d] = idx[d] == safe[d] ? (upper[d] ? (idx[d] - n[d] / 2) * 2 : idx[d] * 2) : idx[d] == -1 ? n[d] - 2 : 0;
+  }
+  if (wrap_low && level + 1 <= max_level) want[2] = N3(level + 1) - 1;
+  if (wrap_high) want[2] = 0;
+  ba = mesh_find(P, level + 1, want);
+  if (ba < 0) { out[0] = -1; out[1] = out[2] = out[3] = 0; return; }   /* the reference throws "Grid interpolation failed." */
+  for (d = 0; d < 3; d++)
+    sought[d] += (idx[d] < cell[d] || (idx[d] == cell[d] && x[d] > xv[d][(size_t)b * n[d] + cell[d]])) ? 1 : 0;
+  out[0] = ba; out[1] = sought[2]; out[2] = sought[1]; out[3] = sought[0];
+#undef N3
 }
 
 static void tetrad(const double ucon[4], const double ucov[4], const double kcon[4], const double kcov[4],
@@ -761,8 +855,35 @@ void orc_simulation_image(const orc_sim *P, long n_rays, int cap, const int *num
               bb[mu] = trilinear(prim, P, 5 + mu, b, km, jm, im, fk, fj, fi);
             }
             if (P->n_t > 0) slow_values(prim, P, t_ind, t_frac, b, km, jm, im, fk, fj, fi, sv);
+            if (P->block_interp) {
+              /* anchors one cell beyond the block are allowed; their coordinates mirror the block's own spacing
+                 (simulation_sampling.cpp:506-524; the upper mirror reads x?v one past the cell, as the reference does) */
+              const double *f1 = x1f + (size_t)b * (n_i + 1), *f2 = x2f + (size_t)b * (n_j + 1), *f3 = x3f + (size_t)b * (n_k + 1);
+              const double *const xv[3] = {x1v, x2v, x3v};
+              int lo[3] = {x1 >= v1[i] ? i : i - 1, x2 >= v2[j] ? j : j - 1, x3 >= v3[k] ? k : k - 1};
+              int cell[3] = {i, j, k}, p, q, anchor[8][4];
+              double xs[3] = {x1, x2, x3};
+              double x1m = lo[0] == -1 ? 2.0 * f1[i] - v1[i] : v1[lo[0]], x1p = lo[0] + 1 == n_i ? 2.0 * v1[i + 1] - v1[i] : v1[lo[0] + 1];
+              double x2m = lo[1] == -1 ? 2.0 * f2[j] - v2[j] : v2[lo[1]], x2p = lo[1] + 1 == n_j ? 2.0 * v2[j + 1] - v2[j] : v2[lo[1] + 1];
+              double x3m = lo[2] == -1 ? 2.0 * f3[k] - v3[k] : v3[lo[2]], x3p = lo[2] + 1 == n_k ? 2.0 * v3[k + 1] - v3[k] : v3[lo[2] + 1];
+              double gi = (x1 - x1m) / (x1p - x1m), gj = (x2 - x2m) / (x2p - x2m), gk = (x3 - x3m) / (x3p - x3m);
+              for (p = 0; p < 8; p++) {
+                int at[3] = {lo[0] + (p & 1), lo[1] + ((p >> 1) & 1), lo[2] + ((p >> 2) & 1)};
+                mesh_anchor(P, xv, b, at, cell, xs, anchor[p]);
+              }
+              if (inds) for (q = 0; q < 4; q++) inds[4 * o + q] = anchor[0][q];
+              for (q = 0; q < 9; q++) {
+                double c[8];
+                if (q == 8 && !P->code_kappa) { sv[8] = 0.0; break; }
+                for (p = 0; p < 8; p++) c[p] = g4(prim, P, q, anchor[p][0], anchor[p][1], anchor[p][2], anchor[p][3]);
+                sv[q] = (1.0 - gk) * (1.0 - gj) * (1.0 - gi) * c[0] + (1.0 - gk) * (1.0 - gj) * gi * c[1] +
+                        (1.0 - gk) * gj * (1.0 - gi) * c[2] + (1.0 - gk) * gj * gi * c[3] + gk * (1.0 - gj) * (1.0 - gi) * c[4] +
+                        gk * (1.0 - gj) * gi * c[5] + gk * gj * (1.0 - gi) * c[6] + gk * gj * gi * c[7];
+                if ((q < 2 || q == 8) && sv[q] <= 0.0) sv[q] = c[0];
+              }
+            }
           }
-          if (P->n_t > 0) {
+          if (P->n_t > 0 || (P->interp && P->block_interp)) {
             rho = sv[0]; pgas = sv[1]; entropy = sv[8];
             for (mu = 0; mu < 3; mu++) { uu[mu] = sv[2 + mu]; bb[mu] = sv[5 + mu]; }
           }

@@ -35,7 +35,9 @@ class Sim(ctypes.Structure):
                 ('cut_val_min', ctypes.c_double * 7), ('cut_val_max', ctypes.c_double * 7)] + \
                [(n, ctypes.c_double) for n in ('fallback_rho', 'fallback_pgas', 'fallback_kappa')] + \
                [('n_t', ctypes.c_int), ('slow_interp', ctypes.c_int), ('snapshot_time', ctypes.c_double),
-                ('times', ctypes.c_double * 64)]
+                ('times', ctypes.c_double * 64)] + \
+               [('block_interp', ctypes.c_int), ('n_3_root', ctypes.c_int), ('levels', ctypes.c_void_p),
+                ('locations', ctypes.c_void_p)]
 
 CUT_VALUES = ('rho', 'n_e', 'p_gas', 'theta_e', 'b', 'sigma', 'beta_inverse')
 
@@ -196,6 +198,13 @@ def simulation_image(kv, s, mom, grid, want_inds=True, camera_x=None, render=Fal
     n_render = int(kv.get('render_num_images', 0)) if render else 0
     rendering = np.zeros((n_render, 3, n)) if render else None
     keep = [np.ascontiguousarray(grid[k]) for k in ('x1f', 'x2f', 'x3f', 'x1v', 'x2v', 'x3v', 'prim')]
+    if kv.get('simulation_block_interp', 'false') == 'true' and kv['simulation_interp'] == 'true':
+        # the reference reads one element past a block's cell centres at its upper edge: pad the last block
+        for q in (3, 4, 5):
+            keep[q] = np.ascontiguousarray(np.concatenate([keep[q].ravel(), [0.0]]))
+        mesh = [np.ascontiguousarray(grid['levels'], np.int32), np.ascontiguousarray(grid['locations'], np.int32)]
+        P.block_interp, P.n_3_root = 1, int(grid['n_3_root'])
+        P.levels, P.locations = mesh[0].ctypes.data, mesh[1].ctypes.data
     lib().orc_simulation_image(ctypes.byref(P), ctypes.c_long(n), s['cap'], _p(s['num']), _p(s['flags']), _p(s['pos']),
                                _p(s['dir']), _p(s['len']), _p(np.ascontiguousarray(mom)), ctypes.c_double(float(kv['image_frequency'])),
                                *[_p(k) for k in keep], _p(image), _p(inds),

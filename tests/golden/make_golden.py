@@ -81,6 +81,14 @@ CPU_CASES = {
     # all 27 auxiliary images kept: the fallback values only show in the cell-value averages
     'cpu_simulation_fallback_values_16': dict(AUX_SIM, fallback_nan='false', fallback_rho='1.0e-6', fallback_pgas='1.0e-8',
                                               camera_r='80.0', camera_width='60.0', camera_resolution='16'),
+    # inter-block trilinear anchors on a two-level mesh, on a single-level multi-block one, and with nearest-cell fallbacks
+    'cpu_simulation_block_interp_amr_16': {'simulation_block_interp': 'true', 'camera_resolution': '16',
+                                           '_mock': {'blocks': (2, 2, 4), 'n_r': 32, 'n_th': 16, 'n_ph': 32, 'refine': amr_refine}},
+    'cpu_simulation_block_interp_amr_tilted_16': {'simulation_block_interp': 'true', 'camera_resolution': '16', 'camera_th': '35.0',
+                                                  'camera_ph': '100.0',
+                                                  '_mock': {'blocks': (2, 2, 4), 'n_r': 32, 'n_th': 16, 'n_ph': 32, 'refine': amr_refine}},
+    'cpu_simulation_block_interp_blocks_16': {'simulation_block_interp': 'true', 'camera_resolution': '16',
+                                              '_mock': {'blocks': (2, 2, 4), 'n_r': 32, 'n_th': 16, 'n_ph': 32}},
     'cpu_simulation_code_kappa_16': {'plasma_model': 'code_kappa', 'simulation_kappa_name': 'r0', 'camera_resolution': '16'},
     'cpu_simulation_code_kappa_nearest_16': {'plasma_model': 'code_kappa', 'simulation_kappa_name': 'r0',
                                              'simulation_interp': 'false', 'camera_resolution': '16'},
@@ -148,7 +156,8 @@ def main():
         if only and name not in only:
             continue
         with tempfile.TemporaryDirectory() as d:
-            mock = dict(entropy=True) if over.get('plasma_model') == 'code_kappa' else None
+            over = dict(over)
+            mock = over.pop('_mock', None) or (dict(entropy=True) if over.get('plasma_model') == 'code_kappa' else None)
             ref = Case(d, 'simulation.input', over, mock=mock, threads=8).run_reference(checkpoints=False)
             keep = ref['npz'] if 'image_tau_int' in over else {'I_nu': ref['npz']['I_nu']}
             np.savez_compressed(os.path.join(os.environ.get('GOLDEN_OUT', HERE), name + '.npz'), **keep)

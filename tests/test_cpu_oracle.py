@@ -410,6 +410,37 @@ def test_oracle_slow_light(name, tmp_path):
         assert np.nanmax(np.abs(frozen.reshape(12, 12)[ok] - ref[ok]) / scale) > 1e-3
 
 
+@pytest.mark.parametrize('name', ['block_interp_amr', 'block_interp_amr_tilted', 'block_interp_blocks'])
+def test_oracle_block_interpolation(name, tmp_path):
+    """simulation_block_interp = true: trilinear anchors one cell beyond a MeshBlock resolved on the neighbouring block of
+    the same, the coarser or the finer level, phi periodic (FindNearbyInds / InterpolateAdvanced,
+    simulation_sampling.cpp:506-553, 1068-1331, 1365-1386), on a two-level mesh and a single-level multi-block one,
+    against the unmodified reference's images."""
+    import sys
+    sys.path.insert(0, GOLDEN)
+    from make_golden import CPU_CASES
+    over = dict(CPU_CASES['cpu_simulation_%s_16' % name])
+    mock = dict(over.pop('_mock'))
+    kv = load_input('simulation.input')
+    kv.update(over)
+    path = os.path.join(tmp_path, 'o.input')
+    write_input(path, kv)
+    cfg = bl.Config(path)
+    grid = mock_snapshot.grid_view_arrays(mock_snapshot.make_mock(None, tuple(mock.pop('blocks')), **mock))
+    pos, dirs, fac = cfg.camera_root()
+    s = oracle_lib.trace(kv, float(kv['simulation_a']), pos, dirs)
+    image, _ = oracle_lib.simulation_image(kv, s, fac, grid, want_inds=False)
+    ref = np.load(os.path.join(GOLDEN, 'cpu_simulation_%s_16.npz' % name))['I_nu']
+    got = image.reshape(16, 16)
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    scale = np.maximum(np.abs(ref[ok]), 1e-12 * np.nanmax(np.abs(ref)))
+    assert np.max(np.abs(got[ok] - ref[ok]) / scale) < 1e-10
+    # and the anchors matter: in-block interpolation gives another image
+    plain, _ = oracle_lib.simulation_image(dict(kv, simulation_block_interp='false'), s, fac, grid, want_inds=False)
+    assert np.nanmax(np.abs(plain.reshape(16, 16)[ok] - ref[ok]) / scale) > 1e-4
+
+
 def test_refinement_restatement_against_reference_fixture(tmp_path):
     """Adaptive refinement decision (EvaluateBlock, radiation_adaptive.cpp:163-312; child order camera.cpp:445-459): the
     numpy restatement applied to the unmodified reference's level-0 image reproduces the reference's list of level-1
