@@ -89,6 +89,9 @@ CPU_CASES = {
                                                   '_mock': {'blocks': (2, 2, 4), 'n_r': 32, 'n_th': 16, 'n_ph': 32, 'refine': amr_refine}},
     'cpu_simulation_block_interp_blocks_16': {'simulation_block_interp': 'true', 'camera_resolution': '16',
                                               '_mock': {'blocks': (2, 2, 4), 'n_r': 32, 'n_th': 16, 'n_ph': 32}},
+    'cpu_simulation_fallback_entropy_16': dict(AUX_SIM, fallback_nan='false', fallback_rho='1.0e-6', fallback_pgas='1.0e-8',
+                                               fallback_kappa='1.0e8', plasma_model='code_kappa', simulation_kappa_name='r0',
+                                               camera_r='80.0', camera_width='60.0', camera_resolution='16'),
     'cpu_simulation_code_kappa_16': {'plasma_model': 'code_kappa', 'simulation_kappa_name': 'r0', 'camera_resolution': '16'},
     'cpu_simulation_code_kappa_nearest_16': {'plasma_model': 'code_kappa', 'simulation_kappa_name': 'r0',
                                              'simulation_interp': 'false', 'camera_resolution': '16'},

@@ -344,7 +344,8 @@ def test_oracle_cuts(name, tmp_path):
     assert np.nansum(ref) / ref.size < 0.9 * np.nansum(full) / full.size
 
 
-def test_oracle_fallback_values(tmp_path):
+@pytest.mark.parametrize('fixture', ['cpu_simulation_fallback_values_16', 'cpu_simulation_fallback_entropy_16'])
+def test_oracle_fallback_values(fixture, tmp_path):
     """fallback_nan = false with a camera field of view wider than the grid: samples outside the grid carry
     fallback_rho / fallback_pgas with zero velocity and field (simulation_sampling.cpp:695-708), poorly terminated
     rays are integrated rather than blanked; visible in the cell-value averages.  All 27 auxiliary images against the
@@ -353,15 +354,18 @@ def test_oracle_fallback_values(tmp_path):
     sys.path.insert(0, GOLDEN)
     from make_golden import CPU_CASES
     kv = load_input('simulation.input')
-    kv.update(CPU_CASES['cpu_simulation_fallback_values_16'])
+    kv.update(CPU_CASES[fixture])
     path = os.path.join(tmp_path, 'o.input')
     write_input(path, kv)
     cfg = bl.Config(path)
-    grid = mock_snapshot.grid_view_arrays(mock_snapshot.make_mock(None))
+    grid = mock_snapshot.grid_view_arrays(mock_snapshot.make_mock(None, entropy=kv['plasma_model'] == 'code_kappa'))
+    if kv['plasma_model'] == 'code_kappa':   # the restatement takes the entropy variable last
+        order = ('ind_rho', 'ind_pgas', 'ind_uu1', 'ind_uu2', 'ind_uu3', 'ind_bb1', 'ind_bb2', 'ind_bb3', 'ind_kappa')
+        grid = dict(grid, prim=np.ascontiguousarray(np.stack([grid['prim'][grid[k]] for k in order]), np.float32))
     pos, dirs, fac = cfg.camera_root()
     s = oracle_lib.trace(kv, float(kv['simulation_a']), pos, dirs)
     image, aux = oracle_lib.simulation_image(kv, s, fac, grid, want_inds=False, camera_x=cfg.camera_frame()['cam_x'])
-    gold = np.load(os.path.join(GOLDEN, 'cpu_simulation_fallback_values_16.npz'))
+    gold = np.load(os.path.join(GOLDEN, fixture + '.npz'))
     for name in ['I_nu'] + oracle_lib.AUX_NAMES:
         ref = gold[name]
         got = (image if name == 'I_nu' else aux[name]).reshape(16, 16)
@@ -373,6 +377,10 @@ def test_oracle_fallback_values(tmp_path):
     _, other = oracle_lib.simulation_image(dict(kv, fallback_rho='1.0e-3'), s, fac, grid, want_inds=False,
                                            camera_x=cfg.camera_frame()['cam_x'])
     assert np.nanmin(np.abs(other['lambda_ave_rho'] / aux['lambda_ave_rho'] - 1.0)) > 1e-3
+    if kv['plasma_model'] == 'code_kappa':   # and the fallback entropy sets the temperature there
+        _, other = oracle_lib.simulation_image(dict(kv, fallback_kappa='1.0e7'), s, fac, grid, want_inds=False,
+                                               camera_x=cfg.camera_frame()['cam_x'])
+        assert np.nanmin(np.abs(other['lambda_ave_Theta_e'] / aux['lambda_ave_Theta_e'] - 1.0)) > 1e-3
 
 
 @pytest.mark.parametrize('name', ['cpu_slow_light_blend_12', 'cpu_slow_light_nearest_slice_12',
