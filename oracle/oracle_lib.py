@@ -57,6 +57,10 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
+        src = os.path.join(HERE, 'blacklight_oracle.c')
+        if os.path.exists(LIB) and os.path.getmtime(src) > os.path.getmtime(LIB):   # struct layouts must match this file
+            import subprocess
+            subprocess.run(['make', '-C', HERE, 'restatement'], check=True, capture_output=True)
         _lib = ctypes.CDLL(LIB)
         _lib.orc_trace_dp.restype = ctypes.c_int
         _lib.orc_trace_rk.restype = ctypes.c_int
