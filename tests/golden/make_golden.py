@@ -142,6 +142,31 @@ def make_slow(only):
             np.savez_compressed(os.path.join(os.environ.get('GOLDEN_OUT', HERE), name + '.npz'), I_nu=image)
             print(name, image.shape, float(np.nanmax(image)))
 
+# adaptive refinement: one criterion per case, two levels, unpolarized; block lists and per-level images only
+ADAPT_OFF = {'adaptive_rel_lapl_frac': '-1.0', 'adaptive_max_level': '2', 'image_polarization': 'false'}
+ADAPT_CASES = {
+    'adaptive_value_32': dict(ADAPT_OFF, adaptive_val_cut='4.0e-5', adaptive_val_frac='0.3'),
+    'adaptive_abs_grad_32': dict(ADAPT_OFF, adaptive_abs_grad_cut='2.0e-5', adaptive_abs_grad_frac='0.2'),
+    'adaptive_rel_grad_32': dict(ADAPT_OFF, adaptive_rel_grad_cut='0.5', adaptive_rel_grad_frac='0.25'),
+    'adaptive_abs_lapl_32': dict(ADAPT_OFF, adaptive_abs_lapl_cut='1.0e-5', adaptive_abs_lapl_frac='0.2'),
+    'adaptive_rel_lapl_region_32': dict(ADAPT_OFF, adaptive_rel_lapl_frac='0.25', adaptive_num_regions='1',
+                                        adaptive_region_1_level='2', adaptive_region_1_x_min='-11.0',
+                                        adaptive_region_1_x_max='-7.0', adaptive_region_1_y_min='2.0',
+                                        adaptive_region_1_y_max='9.0'),
+}
+
+
+def make_adaptive(only):
+    for name, over in ADAPT_CASES.items():
+        if only and name not in only:
+            continue
+        with tempfile.TemporaryDirectory() as d:
+            ref = Case(d, 'adaptive.input', over, threads=8).run_reference(checkpoints=False)['npz']
+            keep = {k: v for k, v in ref.items() if k == 'I_nu' or k.startswith('adaptive_num') or
+                    k.startswith('adaptive_block_locs') or k.startswith('adaptive_I_nu')}
+            np.savez_compressed(os.path.join(os.environ.get('GOLDEN_OUT', HERE), name + '.npz'), **keep)
+            print(name, list(ref['adaptive_num_blocks']))
+
 
 def masked_inds_crc(geo, samp, sim_interp):
     num = geo['sample_num']
@@ -155,6 +180,7 @@ def masked_inds_crc(geo, samp, sim_interp):
 def main():
     only = sys.argv[1:]
     make_slow(only)
+    make_adaptive(only)
     for name, over in CPU_CASES.items():
         if only and name not in only:
             continue

@@ -484,3 +484,30 @@ def test_refinement_restatement_against_reference_fixture(tmp_path):
         k2['adaptive_%s_frac' % key], k2['adaptive_%s_cut' % key] = '0.5', str(cut)
         assert refine_oracle.evaluate_block(image, k2) is want, (key, cut)
     assert refine_oracle.evaluate_block(np.full((8, 8), np.nan), dict(kv, adaptive_val_frac='0.0')) is False
+
+
+@pytest.mark.parametrize('name', ['adaptive_value_32', 'adaptive_abs_grad_32', 'adaptive_rel_grad_32', 'adaptive_abs_lapl_32',
+                                  'adaptive_rel_lapl_region_32'])
+def test_refinement_restatement_each_criterion_two_levels(name, tmp_path):
+    """Each refinement criterion on its own (value, absolute / relative gradient, absolute / relative Laplacian; the last
+    with a forced region), two levels deep: the numpy restatement applied to the reference's level-0 and level-1 block
+    images reproduces the reference's level-1 and level-2 block lists (radiation_adaptive.cpp:163-312)."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    sys.path.insert(0, GOLDEN)
+    import refine_oracle
+    from make_golden import ADAPT_CASES
+    kv = load_input('adaptive.input')
+    kv.update(ADAPT_CASES[name])
+    gold = np.load(os.path.join(GOLDEN, name + '.npz'))
+    res, bs = int(kv['camera_resolution']), int(kv['adaptive_block_size'])
+    nb = res // bs
+    locs = np.array([[v, u] for v in range(nb) for u in range(nb)], np.int32)
+    blocks = gold['I_nu'].reshape(nb, bs, nb, bs).transpose(0, 2, 1, 3).reshape(nb * nb, bs, bs)
+    for level in (0, 1):
+        flags = refine_oracle.refinement_flags(blocks, locs, level, kv)
+        assert 0 < int(flags.sum()) < len(flags)
+        assert int(flags.sum()) * 4 == int(gold['adaptive_num_blocks'][level + 1])
+        locs = refine_oracle.child_locs(locs, flags)
+        assert np.array_equal(locs, gold['adaptive_block_locs_%d' % (level + 1)])
+        blocks = gold['adaptive_I_nu_%d' % (level + 1)]
