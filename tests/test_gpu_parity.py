@@ -938,3 +938,24 @@ def test_full_resolution_window_against_reference(root, levels, pol, window, gpu
         for k, v in stokes_err(mine, theirs).items():
             assert v <= PIXEL_TOL, '%s %.3e' % (k, v)
     ctx.close()
+
+
+@pytest.mark.parametrize('name', ['adaptive_value_32', 'adaptive_abs_grad_32', 'adaptive_rel_grad_32', 'adaptive_abs_lapl_32',
+                                  'adaptive_rel_lapl_region_32'])
+def test_golden_adaptive_each_criterion(name, gpu, tmp_path):
+    """Each refinement criterion of the device-side EvaluateBlock on its own (value, absolute / relative gradient,
+    absolute / relative Laplacian; the last with a forced region), two levels deep, through the drop-in executable path:
+    block counts, block lists and per-level images against the unmodified reference's (tests/golden/make_golden.py
+    ADAPT_CASES; radiation_adaptive.cpp:163-312)."""
+    from golden.make_golden import ADAPT_CASES
+    gold = dict(np.load(os.path.join(GOLDEN, name + '.npz')))
+    case = Case(tmp_path, 'adaptive.input', ADAPT_CASES[name])
+    npz, _ = case.run_gpu_file()
+    assert np.array_equal(npz['adaptive_num_blocks'], gold['adaptive_num_blocks'])
+    for k in gold:
+        if k.startswith('adaptive_block_locs'):
+            assert np.array_equal(npz[k], gold[k]), k
+    for k in gold:
+        if k == 'I_nu' or k.startswith('adaptive_I_nu'):
+            assert npz[k].shape == gold[k].shape, k
+            assert rel_err(npz[k], gold[k]) <= PIXEL_TOL, k
