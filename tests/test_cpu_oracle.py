@@ -504,10 +504,15 @@ def test_refinement_restatement_each_criterion_two_levels(name, tmp_path):
     nb = res // bs
     locs = np.array([[v, u] for v in range(nb) for u in range(nb)], np.int32)
     blocks = gold['I_nu'].reshape(nb, bs, nb, bs).transpose(0, 2, 1, 3).reshape(nb * nb, bs, bs)
+    path = os.path.join(tmp_path, 'o.input')
+    write_input(path, kv)
+    cfg = bl.Config(path)
     for level in (0, 1):
         flags = refine_oracle.refinement_flags(blocks, locs, level, kv)
         assert 0 < int(flags.sum()) < len(flags)
         assert int(flags.sum()) * 4 == int(gold['adaptive_num_blocks'][level + 1])
+        kids, _, _, _ = cfg.camera_refined(level + 1, locs, flags)     # the host layer's child list from the same flags
         locs = refine_oracle.child_locs(locs, flags)
+        assert np.array_equal(kids, locs)
         assert np.array_equal(locs, gold['adaptive_block_locs_%d' % (level + 1)])
         blocks = gold['adaptive_I_nu_%d' % (level + 1)]
