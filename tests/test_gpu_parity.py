@@ -959,3 +959,13 @@ def test_golden_adaptive_each_criterion(name, gpu, tmp_path):
         if k == 'I_nu' or k.startswith('adaptive_I_nu'):
             assert npz[k].shape == gold[k].shape, k
             assert rel_err(npz[k], gold[k]) <= PIXEL_TOL, k
+
+
+@pytest.mark.parametrize('name', ['formula_photon_12', 'formula_additive_12', 'formula_rk4_max_steps_12', 'simulation_rk4_16',
+                                  'simulation_rk2_kerr_16', 'simulation_amr_16'])
+def test_golden_unpolarized_more(name, gpu, tmp_path):
+    """Fixtures added with the restatement's later coverage: photon-orbit termination, camera-frame frequency
+    normalisation, the fixed-step integrators (one with rays flagged by the step limit) and the block search on a
+    two-level AMR mesh -- flags, counts, every stored sample and the sampled cell indices bit-identical, images to
+    tolerance (same checks as test_golden_unpolarized)."""
+    test_golden_unpolarized(name, gpu, tmp_path)
