@@ -969,3 +969,24 @@ def test_golden_unpolarized_more(name, gpu, tmp_path):
     two-level AMR mesh -- flags, counts, every stored sample and the sampled cell indices bit-identical, images to
     tolerance (same checks as test_golden_unpolarized)."""
     test_golden_unpolarized(name, gpu, tmp_path)
+
+
+def _cpu_case_names():
+    from golden.make_golden import CPU_CASES
+    return sorted(CPU_CASES)
+
+
+@pytest.mark.parametrize('name', _cpu_case_names())
+def test_golden_simulation_options(name, gpu, tmp_path):
+    """The image-only fixtures that pin the restatement's option coverage, through the CUDA path: non-thermal electron
+    mixes, electron temperature from energies, code_kappa, every geometric and cell-value cut (each checked to bite),
+    value fallbacks outside the grid (all auxiliary images) and inter-block interpolation on AMR / multi-block meshes.
+    Images within the per-pixel and flux tolerances of the unmodified reference's."""
+    from golden.make_golden import CPU_CASES
+    over = dict(CPU_CASES[name])
+    mock = over.pop('_mock', None) or (dict(entropy=True) if over.get('plasma_model') == 'code_kappa' else None)
+    gold = dict(np.load(os.path.join(GOLDEN, name + '.npz')))
+    case = Case(tmp_path, 'simulation.input', over, mock=mock)
+    cfg, ctx, image, _, _ = run_gpu_level0(case)
+    check_images(image_arrays(case, image, cfg.resolution), gold, name)
+    ctx.close()
