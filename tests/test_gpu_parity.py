@@ -990,3 +990,21 @@ def test_golden_simulation_options(name, gpu, tmp_path):
     cfg, ctx, image, _, _ = run_gpu_level0(case)
     check_images(image_arrays(case, image, cfg.resolution), gold, name)
     ctx.close()
+
+
+@pytest.mark.parametrize('name', ['cpu_slow_light_blend_12', 'cpu_slow_light_nearest_slice_12',
+                                  'cpu_slow_light_blend_nearest_cell_12'])
+def test_golden_slow_light(name, gpu, tmp_path):
+    """First image of a slow-light run over a 12-file series (nearest slice, blended slices, blended slices of the
+    nearest cell) through the drop-in executable path against the unmodified reference's image."""
+    from golden.make_golden import SLOW_CASES, slow_light_setup
+    from harness import write_input
+    d = str(tmp_path)
+    kv, _ = slow_light_setup(d, SLOW_CASES[name])
+    path = os.path.join(d, 'gpu.input')
+    write_input(path, kv)
+    bl.run_input_file(path)
+    mine = np.load(os.path.join(d, 'img.000.npz'))['I_nu']
+    ref = np.load(os.path.join(GOLDEN, name + '.npz'))['I_nu']
+    assert rel_err(mine, ref) <= PIXEL_TOL
+    assert flux_rel(mine, ref) <= FLUX_TOL
