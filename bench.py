@@ -424,7 +424,8 @@ def main():
                             'geodesic_tflops_as_written': geo_tflops, 'radiation_tflops_as_written': rad_tflops,
                             'fp64_peak_tflops_measured': fp64_peak,
                             'radiation_gather_gbs': gather_gbs, 'ray_freq_per_s': value * F,
-                            'host_wall_ms_per_step': 1e3 * wall_res / K, 'host_wall_ms_per_step_e2e': 1e3 * wall_e2e / K},
+                            'host_wall_ms_per_step': 1e3 * wall_res / K, 'host_wall_ms_per_step_e2e': 1e3 * wall_e2e / K,
+                            'polarized_stages_last_step': ctx.polarized_stage_ms(0)},
                 'roofline': roofline, 'roofline_other_kernel': other, 'clocks': clocks, 'device': info['name'],
                 'timing': 'CUDA events on the library stream, barrier + synchronize on both sides, max over ranks',
             }

@@ -69,6 +69,7 @@ def load_library():
         'bl_retrace_level': (i32, [vp, i32, ctypes.POINTER(LevelStats)]),
         'bl_upload_samples': (i32, [vp, i32, vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, ctypes.POINTER(LevelStats)]),
         'bl_launch_count': (ctypes.c_longlong, [vp]), 'bl_cuda_stream': (vp, [vp]),
+        'bl_polarized_stage_ms': (i32, [vp, i32, ctypes.POINTER(dbl * 3), ctypes.POINTER(ctypes.c_int32)]),
         'bl_download_samples': (i32, [vp, i32, vp, vp, vp, vp, vp]),
         'bl_download_sample_inds': (i32, [vp, i32, vp, vp, vp, vp, vp]),
         'bl_device_info': (i32, [vp, ctypes.c_char_p, i32, ctypes.POINTER(i32), ctypes.POINTER(dbl)]),
@@ -279,6 +280,13 @@ class Context:
 
     def launch_count(self):
         return int(_lib.bl_launch_count(self._h))
+
+    def polarized_stage_ms(self, level=0):
+        """Device ms of the three polarized stages (geometry, coefficients, transfer) in the last radiate_level and the
+        slab length; slab 0 means the fused kernel ran."""
+        ms, slab = (ctypes.c_double * 3)(), ctypes.c_int32()
+        self._check(_lib.bl_polarized_stage_ms(self._h, level, ctypes.byref(ms), ctypes.byref(slab)))
+        return {'geometry_ms': ms[0], 'coefficients_ms': ms[1], 'transfer_ms': ms[2], 'slab': slab.value}
 
     def cuda_stream(self):
         """cudaStream_t (as an integer) that this context's kernels and copies are issued on."""

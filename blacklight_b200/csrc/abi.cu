@@ -18,6 +18,11 @@ extern "C" cudaError_t bl_launch_geodesic_rk(const GeoArgs *args, int flat, int 
 BL_DECL_RAD(bl_launch_radiate_unpolarized_f1); BL_DECL_RAD(bl_launch_radiate_unpolarized_f4);
 BL_DECL_RAD(bl_launch_radiate_unpolarized_f32);
 BL_DECL_RAD(bl_launch_radiate_polarized);
+extern "C" int bl_polarized_split_fields(int num_freq);
+extern "C" int bl_polarized_split_slabs(int slab, int s_top);
+extern "C" cudaError_t bl_launch_radiate_polarized_split(const RadArgs *args, const RadParams *params, double *scratch,
+                                                         double *cam_map, int slab, int s_top, cudaStream_t stream,
+                                                         cudaEvent_t *events, long long *launches);
 extern "C" cudaError_t bl_launch_relayout_grid(const float *prim, int n_var, const int *var_index, size_t cells,
                                                float4 *out, float *kappa_out, cudaStream_t stream);
 extern "C" cudaError_t bl_launch_unpack_samples(const StepBuffer *sb, const int32_t *num, const double *cam_dir,
@@ -46,6 +51,11 @@ struct Level {
   bool traced = false;
   double *image = nullptr;    // device (Q, rays)
   double *render = nullptr;   // device (R,3,rays)
+  // three-stage polarized pipeline (radiate_pol_split.cu): slab scratch and the camera half-step map of one wave
+  double *scratch = nullptr;  // device (fields, slab, wave_rays)
+  double *cam_map = nullptr;  // device (10, wave_rays)
+  int32_t slab = 0;           // samples per slab; 0 = the level uses the fused kernel
+  double ms_stage[3] = {0.0, 0.0, 0.0};  // geometry, coefficients, transfer: device time of the last radiate call
   bl_level_stats stats{};
   bl_slow_stats slow{};
   // taps (allocated on demand)
@@ -73,6 +83,9 @@ struct bl_ctx {
   bool taps_enabled = false;
   long long launches = 0;   // kernels of ours launched so far
   int geo_min_blocks = 3;   // occupancy variant of the DP kernel (BL_GEO_BLOCKS overrides, tuning only)
+  std::vector<cudaEvent_t> stage_events;   // per-launch events of the three-stage polarized pipeline
+  int pol_slab = 0;         // BL_POL_SLAB: samples per slab of that pipeline (0 = chosen from the HBM budget)
+  bool pol_fused = false;   // BL_POL_FUSED=1: keep the single fused polarized kernel (A/B comparisons, parity cross-check)
 };
 
 namespace {
@@ -101,7 +114,7 @@ cudaError_t dev_alloc(T **p, size_t count) {
 
 void free_level(Level &L) {
   cudaFree(L.cam_pos); cudaFree(L.cam_dir); cudaFree(L.mom); cudaFree(L.num); cudaFree(L.flags);
-  cudaFree(L.step); cudaFree(L.image); cudaFree(L.render);
+  cudaFree(L.step); cudaFree(L.image); cudaFree(L.render); cudaFree(L.scratch); cudaFree(L.cam_map);
   cudaFree(L.tap_inds); cudaFree(L.tap_fracs); cudaFree(L.tap_nan); cudaFree(L.tap_cut); cudaFree(L.tap_fb);
   L = Level();
 }
@@ -380,6 +393,8 @@ int bl_create(const bl_params *params, bl_ctx **out) {
   fill_rad_params(*params, ctx->rad);
   ctx->levels.resize((size_t)params->adaptive_max_level + 1);
   if (const char *e = getenv("BL_GEO_BLOCKS")) ctx->geo_min_blocks = atoi(e);
+  if (const char *e = getenv("BL_POL_SLAB")) ctx->pol_slab = atoi(e);
+  if (const char *e = getenv("BL_POL_FUSED")) ctx->pol_fused = atoi(e) != 0;
 #define CREATE_CHECK(call)                                                                   \
   do {                                                                                       \
     cudaError_t e__ = (call);                                                                \
@@ -414,6 +429,7 @@ void bl_destroy(bl_ctx *ctx) {
   cudaFree(ctx->params_dev); cudaFree(ctx->counters); cudaFree(ctx->rad_counter); cudaFree(ctx->slow_counters);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  for (cudaEvent_t e : ctx->stage_events) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -531,6 +547,23 @@ static int upload_grid_slot(bl_ctx *ctx, const bl_grid_view *gv, int slot) {
   if (fmks && (gv->n_b != 1 || !gv->sks_map || gv->sks_map_n1 < 2 || gv->sks_map_n2 < 2 || !(gv->sks_map_dr > 0.0) ||
                !(gv->sks_map_dtheta > 0.0) || gv->n_i < 2 || gv->n_j < 2))
     return bl_fail(ctx, BL_ERR_ARG, "simulation_coord = fmks needs a single block and the reader's sks_map in the grid view");
+  // all argument validation happens before anything is freed or overwritten
+  {
+    const int vidx[8] = {gv->ind_rho, gv->ind_pgas, gv->ind_uu1, gv->ind_uu2, gv->ind_uu3, gv->ind_bb1, gv->ind_bb2, gv->ind_bb3};
+    for (int q = 0; q < 8; q++)
+      if (vidx[q] < 0 || vidx[q] >= gv->n_var) return bl_fail(ctx, BL_ERR_ARG, "bl_upload_grid: variable index %d out of range", q);
+    if (ctx->rad.block_interp) {
+      if (!gv->levels || !gv->locations)
+        return bl_fail(ctx, BL_ERR_ARG, "simulation_block_interp needs the blocks' levels and logical locations");
+      if (ctx->params.simulation_coord == BL_COORD_SKS && (gv->n_3_root <= 0 || gv->n_3_root % gv->n_k != 0))
+        return bl_fail(ctx, BL_ERR_ARG, "simulation_block_interp needs RootGridSize[2] (n_3_root) as a multiple of the block size");
+    }
+    if (fmks && same_shape && (ctx->grid.map_n1 != gv->sks_map_n1 || ctx->grid.map_n2 != gv->sks_map_n2))
+      return bl_fail(ctx, BL_ERR_ARG, "bl_upload_grid: sks_map changed shape between snapshots");
+  }
+  // from here on the grid counts as absent until the upload has completed: a CUDA failure below must not leave a
+  // half-built grid usable (slices of a slow-light window are added to a grid that stays valid meanwhile)
+  if (slot == 0) ctx->have_grid = false;
   size_t cells = (size_t)gv->n_b * gv->n_k * gv->n_j * gv->n_i;
   GridDev &g = ctx->grid;
   if (!same_shape) {
@@ -692,6 +725,29 @@ static int upload_grid_slot(bl_ctx *ctx, const bl_grid_view *gv, int slot) {
 
 namespace {
 
+// The three-stage polarized pipeline (radiate_pol_split.cu) covers the light image and the per-frequency sums
+// (tau, lambda, emission); everything that needs per-sample side outputs stays on the fused kernel.
+bool pol_split_eligible(const bl_ctx *ctx) {
+  const RadParams &r = ctx->rad;
+  return r.polarization && !ctx->pol_fused && !r.block_interp && !r.slow_light && r.coord != 2 &&
+         !(r.image_time || r.image_length || r.image_lambda_ave || r.image_emission_ave || r.image_tau_int ||
+           r.image_crossings) && r.render_num_images == 0;
+}
+
+// Slab length and scratch bytes per ray of that pipeline for a level of num_rays rays under `budget` bytes.
+int pol_split_slab(const bl_ctx *ctx, int64_t num_rays, size_t budget, size_t *bytes_per_ray) {
+  *bytes_per_ray = 0;
+  if (!pol_split_eligible(ctx)) return 0;
+  const size_t nf = (size_t)bl_polarized_split_fields(ctx->rad.num_freq);
+  int slab = ctx->pol_slab > 0 ? ctx->pol_slab : 64;
+  // small levels: fewer, longer slabs while the scratch stays under a tenth of the budget
+  if (ctx->pol_slab <= 0)
+    while (slab < 256 && (double)num_rays * (2.0 * slab) * (double)nf * 8.0 <= 0.1 * (double)budget) slab *= 2;
+  if (slab > ctx->params.ray_max_steps) slab = ctx->params.ray_max_steps;
+  *bytes_per_ray = (size_t)slab * nf * sizeof(double) + 10 * sizeof(double);
+  return slab;
+}
+
 // Trace rays [first, first+count) of a level into L.step (one wave).
 int trace_wave(bl_ctx *ctx, Level &L, int64_t first, int64_t count) {
   const bl_params &p = ctx->params;
@@ -728,7 +784,10 @@ int read_geo_counters(bl_ctx *ctx, Level &L) {
   return BL_OK;
 }
 
-int radiate_wave(bl_ctx *ctx, Level &L, int64_t first, int64_t count) {
+// s_top: upper bound of the sample counts of these rays (the slabs of the polarized pipeline start there).
+// *split_slabs: slabs launched by the three-stage pipeline (0: the fused kernels ran).
+int radiate_wave(bl_ctx *ctx, Level &L, int64_t first, int64_t count, int s_top, int *split_slabs) {
+  *split_slabs = 0;
   RadArgs A{};
   A.grid = ctx->grid;
   A.sb.buf = L.step; A.sb.rays = count; A.sb.cap = ctx->params.ray_max_steps;
@@ -754,6 +813,21 @@ int radiate_wave(bl_ctx *ctx, Level &L, int64_t first, int64_t count) {
   // the unpolarized kernel is instantiated for frequency-count buckets of 1, 4 and 32 (one object file each)
   const int F = ctx->rad.num_freq;
   cudaError_t le;
+  if (ctx->rad.polarization && L.slab > 0 && L.scratch && !L.tap_nan) {
+    // the Stokes state of the pipeline starts (and stays between slabs) in the image columns of these rays
+    BL_CUDA_CHECK(cudaMemset2DAsync(L.image + first, (size_t)L.rays * sizeof(double), 0, (size_t)count * sizeof(double),
+                                    (size_t)ctx->rad.num_quantities, ctx->stream));
+    const int slabs = bl_polarized_split_slabs(L.slab, s_top);
+    while ((int)ctx->stage_events.size() < 3 * slabs + 1) {
+      cudaEvent_t e;
+      BL_CUDA_CHECK(cudaEventCreate(&e));
+      ctx->stage_events.push_back(e);
+    }
+    BL_CUDA_CHECK(bl_launch_radiate_polarized_split(&A, &ctx->rad, L.scratch, L.cam_map, L.slab, s_top, ctx->stream,
+                                                    ctx->stage_events.data(), &ctx->launches));
+    *split_slabs = slabs;
+    return BL_OK;
+  }
   if (ctx->rad.polarization)
     le = bl_launch_radiate_polarized(&A, &ctx->rad, ctx->stream);
   else
@@ -762,6 +836,25 @@ int radiate_wave(bl_ctx *ctx, Level &L, int64_t first, int64_t count) {
                  : bl_launch_radiate_unpolarized_f32(&A, &ctx->rad, ctx->stream);
   BL_CUDA_CHECK(le);
   ctx->launches++;
+  return BL_OK;
+}
+
+// After the stream has been synchronised: add the device time of each stage of the last radiate_wave.
+int collect_stage_times(bl_ctx *ctx, Level &L, int slabs) {
+  for (int k = 0; k < 3 * slabs; k++) {
+    float ms = 0.f;
+    BL_CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->stage_events[k], ctx->stage_events[k + 1]));
+    L.ms_stage[k % 3] += ms;
+  }
+  return BL_OK;
+}
+
+int alloc_split_scratch(bl_ctx *ctx, Level &L, int slab) {
+  L.slab = slab;
+  if (slab <= 0) return BL_OK;
+  const size_t nf = (size_t)bl_polarized_split_fields(ctx->rad.num_freq);
+  BL_CUDA_CHECK(dev_alloc(&L.scratch, (size_t)L.wave_rays * (size_t)slab * nf));
+  BL_CUDA_CHECK(dev_alloc(&L.cam_map, (size_t)L.wave_rays * 10));
   return BL_OK;
 }
 
@@ -776,6 +869,8 @@ int bl_trace_level(bl_ctx *ctx, int level, const double *cam_pos, const double *
   if (!cam_pos || !cam_dir || !mom_factor || num_rays < 0) return bl_fail(ctx, BL_ERR_ARG, "bl_trace_level: null camera arrays");
   BL_CUDA_CHECK(cudaSetDevice(ctx->device));
   Level &L = ctx->levels[level];
+  // any failure below leaves the level empty rather than half built
+  struct Guard { Level &L; bool ok = false; ~Guard() { if (!ok) free_level(L); } } guard{L};
   // Device buffers are kept when the ray count is unchanged (time series, repeated renders): a
   // cudaFree/cudaMalloc pair of a ~100 GB step buffer costs far more than the kernels themselves.
   const bool reuse = L.rays == num_rays && num_rays > 0 && L.cam_pos && L.step;
@@ -787,7 +882,7 @@ int bl_trace_level(bl_ctx *ctx, int level, const double *cam_pos, const double *
     free_level(L);
   }
   L.rays = num_rays;
-  if (num_rays == 0) { L.traced = true; L.resident = true; if (stats) *stats = L.stats; return BL_OK; }
+  if (num_rays == 0) { L.traced = true; L.resident = true; guard.ok = true; if (stats) *stats = L.stats; return BL_OK; }
   const int Q = ctx->rad.num_quantities, R = ctx->rad.render_num_images;
   if (!reuse) {
     BL_CUDA_CHECK(dev_alloc(&L.cam_pos, (size_t)num_rays * 4));
@@ -808,20 +903,30 @@ int bl_trace_level(bl_ctx *ctx, int level, const double *cam_pos, const double *
     BL_CUDA_CHECK(cudaMemGetInfo(&fr, &tot));
     size_t per_ray = (size_t)ctx->params.ray_max_steps * StepBuffer::kRecord * sizeof(double);
     size_t budget = (size_t)((double)fr * 0.80);
-    int64_t fit = (int64_t)(budget / per_ray);
-    if (ctx->params.tile_rays > 0 && ctx->params.tile_rays < fit) fit = ctx->params.tile_rays;
-    if (fit < 128) return bl_fail(ctx, BL_ERR_NOMEM, "not enough free HBM for a 128-ray wave (%zu bytes per ray)", per_ray);
+    size_t per_ray_split = 0;
+    const int slab = pol_split_slab(ctx, num_rays, budget, &per_ray_split);
+    int64_t fit = (int64_t)(budget / (per_ray + per_ray_split));
+    if (fit < 128) {
+      free_level(L);
+      return bl_fail(ctx, BL_ERR_NOMEM, "not enough free HBM for a 128-ray wave (%zu bytes per ray)", per_ray + per_ray_split);
+    }
+    // a requested wave size is honoured in whole 128-ray groups (at least one)
+    if (ctx->params.tile_rays > 0 && ctx->params.tile_rays < fit) fit = ctx->params.tile_rays < 128 ? 128 : ctx->params.tile_rays;
     if (fit >= num_rays) {
       L.wave_rays = num_rays;
       L.resident = true;
     } else {
-      // split into equal waves (multiples of 128 rays) and keep headroom for other levels
+      // split into equal waves of whole 128-ray groups that never exceed the budget
+      fit = fit / 128 * 128;
       int64_t waves = (num_rays + fit - 1) / fit;
       int64_t w = (num_rays + waves - 1) / waves;
-      L.wave_rays = (w + 127) / 128 * 128;
+      w = (w + 127) / 128 * 128;
+      L.wave_rays = w < fit ? w : fit;
       L.resident = false;
     }
     BL_CUDA_CHECK(dev_alloc(&L.step, (size_t)L.wave_rays * per_ray / sizeof(double)));
+    int rc = alloc_split_scratch(ctx, L, slab);
+    if (rc) return rc;
   }
   BL_CUDA_CHECK(cudaMemsetAsync(ctx->counters, 0, sizeof(GeoCounters), ctx->stream));
   L.stats = bl_level_stats();
@@ -842,6 +947,7 @@ int bl_trace_level(bl_ctx *ctx, int level, const double *cam_pos, const double *
     L.traced = false;
     BL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   }
+  guard.ok = true;
   if (stats) *stats = L.stats;
   return BL_OK;
 }
@@ -854,6 +960,8 @@ int bl_upload_samples(bl_ctx *ctx, int level, const double *cam_pos, const doubl
   if (!cam_pos || !cam_dir || !mom_factor || !flags || !num || !pos || !dir || !len || num_rays <= 0 || S <= 0)
     return bl_fail(ctx, BL_ERR_ARG, "bl_upload_samples: null or empty argument");
   if (S > ctx->params.ray_max_steps) return bl_fail(ctx, BL_ERR_ARG, "bl_upload_samples: %d samples per ray exceed ray_max_steps = %d", S, ctx->params.ray_max_steps);
+  for (int64_t m = 0; m < num_rays; m++)
+    if (num[m] < 0 || num[m] > S) return bl_fail(ctx, BL_ERR_ARG, "bl_upload_samples: sample count %d of ray %lld outside [0, %d]", num[m], (long long)m, S);
   BL_CUDA_CHECK(cudaSetDevice(ctx->device));
   Level &L = ctx->levels[level];
   free_level(L);
@@ -869,11 +977,17 @@ int bl_upload_samples(bl_ctx *ctx, int level, const double *cam_pos, const doubl
   size_t per_ray = (size_t)ctx->params.ray_max_steps * StepBuffer::kRecord * sizeof(double);
   size_t fr = 0, tot = 0;
   BL_CUDA_CHECK(cudaMemGetInfo(&fr, &tot));
-  if ((double)per_ray * (double)num_rays > 0.80 * (double)fr)
+  size_t per_ray_split = 0;
+  const int slab = pol_split_slab(ctx, num_rays, (size_t)(0.80 * (double)fr), &per_ray_split);
+  if ((double)(per_ray + per_ray_split) * (double)num_rays > 0.80 * (double)fr)
     return bl_fail(ctx, BL_ERR_NOMEM, "bl_upload_samples: the level's step buffer (%zu bytes per ray) does not fit in HBM; uploaded geodesics must be resident", per_ray);
   L.wave_rays = num_rays;
   L.resident = true;
   BL_CUDA_CHECK(dev_alloc(&L.step, (size_t)num_rays * per_ray / sizeof(double)));
+  {
+    int rc = alloc_split_scratch(ctx, L, slab);
+    if (rc) return rc;
+  }
   BL_CUDA_CHECK(cudaMemcpyAsync(L.cam_pos, cam_pos, (size_t)num_rays * 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   BL_CUDA_CHECK(cudaMemcpyAsync(L.cam_dir, cam_dir, (size_t)num_rays * 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   BL_CUDA_CHECK(cudaMemcpyAsync(L.mom, mom_factor, (size_t)num_rays * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -915,6 +1029,15 @@ int bl_upload_samples(bl_ctx *ctx, int level, const double *cam_pos, const doubl
 
 long long bl_launch_count(const bl_ctx *ctx) { return ctx ? ctx->launches : -1; }
 
+int bl_polarized_stage_ms(bl_ctx *ctx, int level, double *ms3, int32_t *slab) {
+  if (!ctx || !ms3) return BL_ERR_ARG;
+  if (level < 0 || level >= (int)ctx->levels.size()) return bl_fail(ctx, BL_ERR_ARG, "bl_polarized_stage_ms: level %d out of range", level);
+  const Level &L = ctx->levels[level];
+  for (int k = 0; k < 3; k++) ms3[k] = L.ms_stage[k];
+  if (slab) *slab = (L.slab > 0 && L.scratch && !L.tap_nan) ? L.slab : 0;
+  return BL_OK;
+}
+
 void *bl_cuda_stream(const bl_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
 int bl_retrace_level(bl_ctx *ctx, int level, bl_level_stats *stats) {
@@ -945,7 +1068,8 @@ int bl_radiate_level(bl_ctx *ctx, int level, int snapshot, double *image, double
   if (!ctx) return BL_ERR_ARG;
   if (level < 0 || level >= (int)ctx->levels.size()) return bl_fail(ctx, BL_ERR_ARG, "bl_radiate_level: level %d out of range", level);
   Level &L = ctx->levels[level];
-  if (!L.cam_pos && L.rays > 0) return bl_fail(ctx, BL_ERR_STATE, "bl_radiate_level: level %d has not been traced", level);
+  if (L.rays > 0 && (!L.cam_pos || !L.step || L.wave_rays <= 0))
+    return bl_fail(ctx, BL_ERR_STATE, "bl_radiate_level: level %d has not been traced", level);
   bool sim = ctx->params.model_type == BL_MODEL_SIMULATION;
   if (sim && !ctx->have_grid) return bl_fail(ctx, BL_ERR_STATE, "bl_radiate_level: no grid uploaded");
   BL_CUDA_CHECK(cudaSetDevice(ctx->device));
@@ -974,14 +1098,18 @@ int bl_radiate_level(bl_ctx *ctx, int level, int snapshot, double *image, double
   }
   double ms_geo = 0.0, ms_rad = 0.0;
   float ms = 0.f;
+  int split_slabs = 0;
+  L.ms_stage[0] = L.ms_stage[1] = L.ms_stage[2] = 0.0;
   if (L.resident) {
     BL_CUDA_CHECK(cudaEventRecord(ctx->ev0, ctx->stream));
-    int rc = radiate_wave(ctx, L, 0, L.rays);
+    int rc = radiate_wave(ctx, L, 0, L.rays, L.stats.geodesic_num_steps, &split_slabs);
     if (rc) return rc;
     BL_CUDA_CHECK(cudaEventRecord(ctx->ev1, ctx->stream));
     BL_CUDA_CHECK(cudaEventSynchronize(ctx->ev1));
     BL_CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ms_rad = ms;
+    rc = collect_stage_times(ctx, L, split_slabs);
+    if (rc) return rc;
   } else {
     // waves: trace then radiate, reusing one step buffer; geodesic statistics accumulate over waves
     BL_CUDA_CHECK(cudaMemsetAsync(ctx->counters, 0, sizeof(GeoCounters), ctx->stream));
@@ -994,13 +1122,21 @@ int bl_radiate_level(bl_ctx *ctx, int level, int snapshot, double *image, double
       BL_CUDA_CHECK(cudaEventSynchronize(ctx->ev1));
       BL_CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
       ms_geo += ms;
+      // sample counts so far bound this wave's (the maximum only grows): where the polarized pipeline's slabs start
+      int s_top = ctx->params.ray_max_steps;
+      if (L.slab > 0) {
+        BL_CUDA_CHECK(cudaMemcpyAsync(&s_top, &ctx->counters->max_samples, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        BL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+      }
       BL_CUDA_CHECK(cudaEventRecord(ctx->ev0, ctx->stream));
-      rc = radiate_wave(ctx, L, first, count);
+      rc = radiate_wave(ctx, L, first, count, s_top, &split_slabs);
       if (rc) return rc;
       BL_CUDA_CHECK(cudaEventRecord(ctx->ev1, ctx->stream));
       BL_CUDA_CHECK(cudaEventSynchronize(ctx->ev1));
       BL_CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
       ms_rad += ms;
+      rc = collect_stage_times(ctx, L, split_slabs);
+      if (rc) return rc;
     }
     int rc = read_geo_counters(ctx, L);
     if (rc) return rc;

@@ -1,0 +1,396 @@
+// Polarized (Stokes IQUV) transfer as a three-stage pipeline over slabs of the step buffer.
+//
+// The fused kernel of radiate_pol.cu walks a ray with everything in one thread: geometry (Kerr-Schild jet,
+// tetrad, Stokes transport matrix), per-frequency synchrotron coefficients and the Stokes coupling.  Its
+// register state (255 + 2 KB of stack) allows two warps per scheduler, and ncu shows it waiting on
+// dependent FP64 latencies most of the time.  Only the last few dozen operations per sample and frequency
+// are really sequential along the ray (s <- M s; s <- O(coefficients) s + c), so the work is split by what
+// it depends on:
+//   pol_geometry_kernel      one thread per ray, a slab of `slab` consecutive samples: sampling of the grid,
+//                            plasma state, tetrad legs, and the frequency-independent transport matrix M
+//                            from the previous sample (polarized.cpp:136-292, :816-833); the only carried
+//                            state is the previous sample's frame, re-derived from one halo sample at the top
+//                            of the slab.  Writes 18 doubles per sample.
+//   pol_coefficient_kernel   one thread per (ray, sample): the eight polarized synchrotron coefficients of
+//                            every frequency (simulation_coefficients.cpp:458-698).  No carried state at all,
+//                            so it runs at whatever occupancy its registers allow.  Writes 8 F doubles.
+//   pol_transfer_kernel      one thread per (ray, frequency): s <- M s, Stokes coupling (polarized.cpp:379-790),
+//                            sequential over the slab; the Stokes state between slabs lives in the image
+//                            itself.  The last slab applies the half step to the camera and the projection on
+//                            the camera tetrad (:816-939).
+// Slabs run from the far end of the rays (large n) to the camera (n = 0), three launches each, on one stream.
+// The scratch between the stages is field-major, scratch[(field * slab + j) * rays + m]: every access of a warp
+// is a contiguous 256-byte row.
+#include "pol_common.cuh"
+
+namespace {
+
+enum : int {
+  kFieldM = 0,        // 9 entries of the 3x3 block of M, then vv
+  kFieldDlam = 10,
+  kFieldOm = 11,      // omega * momentum factor (nu = om * image frequency); 0 marks an uncoupled sample
+  kFieldSin = 12,
+  kFieldCos = 13,
+  kFieldBb = 14,      // |B| in gauss
+  kFieldNe = 15,      // electron number density
+  kFieldTheta = 16,
+  kFieldInvTheta = 17,
+  kFieldCoef = 18     // 8 per frequency: j_I, j_Q, j_V, alpha_I, alpha_Q, alpha_V, rho_Q, rho_V
+};
+
+struct SplitArgs {
+  double *scratch;     // (18 + 8 F, slab, rays)
+  double *cam_map;     // (10, rays): the half step to the camera, filled by the slab that holds n = 0
+  int32_t slab;        // samples per slab
+  int32_t n_lo, n_hi;  // this launch covers samples n_lo <= n < n_hi of every ray
+};
+
+__device__ __forceinline__ double *field_ptr(const SplitArgs &X, int64_t rays, int field, int j, int64_t m) {
+  return X.scratch + ((size_t)field * X.slab + j) * (size_t)rays + m;
+}
+
+// ---- stage 1: geometry --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock, 2)
+pol_geometry_kernel(const __grid_constant__ RadArgs A, const __grid_constant__ RadParams P, const SplitArgs X) {
+  extern __shared__ double smem_bounds[];
+  const GridDev &G = A.grid;
+  const double *bounds_s = nullptr;
+  {
+    int nb6 = G.n_b * 6;
+    if ((size_t)nb6 * sizeof(double) <= 48 * 1024) {
+      for (int t = threadIdx.x; t < nb6; t += blockDim.x) smem_bounds[t] = G.bounds[t];
+      __syncthreads();
+      bounds_s = smem_bounds;
+    }
+  }
+  const unsigned full = 0xffffffffu;
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = m < A.rays;
+  const int num = valid ? A.sample_num[m] : 0;
+  unsigned long long processed = 0;
+  if (num > X.n_lo) {
+    const bool flagged = A.sample_flags[m] != 0;
+    const double mom = A.mom_factor[m];
+    const double k_t = A.cam_dir[4 * m];
+    const int top = (X.n_hi < num ? X.n_hi : num) - 1;   // first sample of this slab in walking order
+    const bool halo = X.n_hi < num;                        // the sample before it belongs to the previous slab
+    rad::CellCache cache = {0, 0, 0, 0};
+    rad::SlowLight slow = {0, {0.0, 0.0, 0.0, 0.0}};
+    KsJet jet_p;
+    double k_p[4] = {0, 0, 0, 0}, e_p[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+    double dlam_p = 0.0;
+    bool have_prev = false;
+
+#pragma unroll 1
+    for (int n = halo ? top + 1 : top; n >= X.n_lo; n--) {
+      const bool store = n <= top;
+      const double2 *src = reinterpret_cast<const double2 *>(A.sb.buf + A.sb.at(n, m));
+      double2 r0 = __ldcs(src), r1 = __ldcs(src + 1), r2 = __ldcs(src + 2), r3 = __ldcs(src + 3);
+      double t = r0.x, x = r0.y, y = r1.x, z = r1.y;
+      double kc[4] = {k_t, r2.x, r2.y, r3.x};
+      double dlam = -r3.y;
+      double inv_r;
+      double r = rad::ks_radius(P.a, x, y, z, inv_r);
+
+      // ---- sample the plasma (as the fused kernel) ----
+      rad::SampleStatus st;
+      rad::Prims pr;
+      rad::SampleIndex si;
+      pr.rho = pr.pgas = pr.kappa = pr.uu1 = pr.uu2 = pr.uu3 = pr.bb1 = pr.bb2 = pr.bb3 = 0.0f;
+      if (P.fallback_nan && flagged)
+        st = rad::kSampleNan;
+      else if (rad::geometric_cut(P, x, y, z, r))
+        st = rad::kSampleCut;
+      else
+        st = rad::sample_grid<false>(P, G, bounds_s, x, y, z, r, inv_r, t + P.snapshot_time, cache, pr, si, slow);
+      if (st == rad::kSampleNan) {
+        float qn = nanf("");
+        pr.rho = pr.pgas = pr.kappa = pr.uu1 = pr.uu2 = pr.uu3 = pr.bb1 = pr.bb2 = pr.bb3 = qn;
+      } else if (st == rad::kSampleFallback) {
+        pr.rho = P.fallback_rho; pr.pgas = P.fallback_pgas; pr.kappa = P.fallback_kappa;
+        pr.uu1 = pr.uu2 = pr.uu3 = pr.bb1 = pr.bb2 = pr.bb3 = 0.0f;
+      }
+      rad::Plasma ps;
+      rad::plasma_state(P, x, y, z, r, inv_r, pr, 2, ps);
+      const bool coupled = st != rad::kSampleCut && !ps.value_cut && !ps.b_zero;
+
+      // ---- metric jet, momenta, fluid-frame tetrad ----
+      KsJet jet;
+      ks_jet(P, x, y, z, r, inv_r, jet);
+      double kcon[4], ucov[4];
+      raise(jet, kc, kcon);
+      lower(jet, ps.ucon, ucov);
+      double up[4] = {0.0, 0.0, 0.0, 1.0};
+      if (!ps.b_zero)
+        for (int mu = 0; mu < 4; mu++) up[mu] = ps.bcon[mu];
+      double e1[4], e2[4], f1[4], f2[4];
+      tetrad_legs(jet, ps.ucon, ucov, kcon, kc, up, e1, e2, f1, f2);
+
+      if (store) {
+        processed++;
+        const int j = n - X.n_lo;
+        // ---- Stokes transport matrix from the previous sample to this one ----
+        StokesMap M;
+        for (int a = 0; a < 3; a++)
+          for (int b = 0; b < 3; b++) M.m[a][b] = 0.0;
+        M.vv = 0.0;
+        if (have_prev) {
+          double ks[4] = {k_p[0] + kcon[0], k_p[1] + kcon[1], k_p[2] + kcon[2], k_p[3] + kcon[3]};
+          double A_avg[4][4], A_tmp[4][4], A_pp[4][4];
+          contracted_connection(jet_p, ks, A_avg);
+          contracted_connection(jet, ks, A_tmp);
+          for (int a = 0; a < 4; a++)
+            for (int b = 0; b < 4; b++) A_avg[a][b] = 0.25 * (A_avg[a][b] + A_tmp[a][b]);
+          contracted_connection(jet_p, k_p, A_pp);
+          double h = (dlam_p + dlam) / 2.0, h2 = (dlam_p + dlam) / 4.0;
+          LegProj L[2];
+          for (int c = 0; c < 2; c++) {
+            double vp[4], va[4], vap[4];
+            transport_rate(A_pp, e_p[c], vp);
+            transport_rate(A_avg, e_p[c], va);
+            transport_rate(A_avg, vp, vap);
+            L[c].u[0] = dot4(f1, e_p[c]);  L[c].u[1] = dot4(f2, e_p[c]);
+            L[c].up[0] = dot4(f1, vp);     L[c].up[1] = dot4(f2, vp);
+            L[c].ua[0] = dot4(f1, va);     L[c].ua[1] = dot4(f2, va);
+            L[c].uap[0] = dot4(f1, vap);   L[c].uap[1] = dot4(f2, vap);
+          }
+          stokes_map(L, h, h * h2, true, M);
+        }
+        for (int a = 0; a < 3; a++)
+          for (int b = 0; b < 3; b++) __stcs(field_ptr(X, A.rays, kFieldM + 3 * a + b, j, m), M.m[a][b]);
+        __stcs(field_ptr(X, A.rays, kFieldM + 9, j, m), M.vv);
+        __stcs(field_ptr(X, A.rays, kFieldDlam, j, m), dlam);
+
+        // ---- what the coefficient stage needs: frequency scale, pitch angle, field strength, n_e, theta_e ----
+        double om = 0.0, sin_theta_b = 0.0, cos_theta_b = 0.0;
+        if (coupled) {
+          double omega = -dot4(kc, ps.ucon);
+          double kb = dot4(kc, ps.bcon);
+          double c2 = kb * kb / (omega * omega * ps.b_sq);
+          c2 = 1.0 < c2 ? 1.0 : c2;
+          sin_theta_b = sqrt(1.0 - c2);
+          cos_theta_b = sqrt(c2) * (kb >= 0.0 ? 1.0 : -1.0);
+          om = omega * mom;
+        }
+        __stcs(field_ptr(X, A.rays, kFieldOm, j, m), om);
+        if (coupled) {
+          __stcs(field_ptr(X, A.rays, kFieldSin, j, m), sin_theta_b);
+          __stcs(field_ptr(X, A.rays, kFieldCos, j, m), cos_theta_b);
+          __stcs(field_ptr(X, A.rays, kFieldBb, j, m), ps.bb_cgs);
+          __stcs(field_ptr(X, A.rays, kFieldNe, j, m), ps.n_e_cgs);
+          __stcs(field_ptr(X, A.rays, kFieldTheta, j, m), ps.theta_e);
+          __stcs(field_ptr(X, A.rays, kFieldInvTheta, j, m), ps.inv_theta_e);
+        }
+      }
+
+      // ---- carry the frame to the next sample ----
+      jet_p = jet;
+      for (int mu = 0; mu < 4; mu++) {
+        k_p[mu] = kcon[mu];
+        e_p[0][mu] = e1[mu];
+        e_p[1][mu] = e2[mu];
+      }
+      dlam_p = dlam;
+      have_prev = true;
+    }
+
+    if (X.n_lo == 0) {
+      // last half step of transport, then projection on the camera tetrad (polarized.cpp:816-833, :875-939)
+      const double *cp = A.cam_pos + 4 * m, *cd = A.cam_dir + 4 * m;
+      KsJet jc;
+      double inv_rc;
+      double rc = rad::ks_radius(P.a, cp[1], cp[2], cp[3], inv_rc);
+      ks_jet(P, cp[1], cp[2], cp[3], rc, inv_rc, jc);
+      double kcov[4] = {cd[0], cd[1], cd[2], cd[3]}, kcon[4];
+      raise(jc, kcov, kcon);
+      const double *uc = P.camera_u_con, *ul = P.camera_u_cov, *vc = P.camera_vert_con_c;
+      double up[4];
+      up[0] = uc[0] * vc[0] - (ul[1] * vc[1] + ul[2] * vc[2] + ul[3] * vc[3]) / ul[0];
+      up[1] = vc[1] + uc[1] * vc[0];
+      up[2] = vc[2] + uc[2] * vc[0];
+      up[3] = vc[3] + uc[3] * vc[0];
+      double e1[4], e2[4], f1[4], f2[4];
+      tetrad_legs(jc, uc, ul, kcon, kcov, up, e1, e2, f1, f2);
+      double A_pp[4][4];
+      contracted_connection(jet_p, k_p, A_pp);
+      LegProj L[2];
+      for (int c = 0; c < 2; c++) {
+        double vp[4];
+        transport_rate(A_pp, e_p[c], vp);
+        L[c].u[0] = dot4(f1, e_p[c]);  L[c].u[1] = dot4(f2, e_p[c]);
+        L[c].up[0] = dot4(f1, vp);     L[c].up[1] = dot4(f2, vp);
+        L[c].ua[0] = L[c].ua[1] = L[c].uap[0] = L[c].uap[1] = 0.0;
+      }
+      StokesMap M;
+      stokes_map(L, 0.0, dlam_p / 2.0, false, M);
+      for (int a = 0; a < 3; a++)
+        for (int b = 0; b < 3; b++) X.cam_map[(size_t)(3 * a + b) * A.rays + m] = M.m[a][b];
+      X.cam_map[(size_t)9 * A.rays + m] = M.vv;
+    }
+  }
+  if (A.sample_counter) {
+    for (int off = 16; off > 0; off >>= 1) processed += __shfl_down_sync(full, processed, off);
+    if ((threadIdx.x & 31) == 0 && processed) atomicAdd(A.sample_counter, processed);
+  }
+}
+
+// ---- stage 2: coefficients ----------------------------------------------------------------------------------
+#ifndef BL_POLC_MINB
+#define BL_POLC_MINB 4
+#endif
+template <int DIST>
+__global__ void __launch_bounds__(kBlock, BL_POLC_MINB)
+pol_coefficient_kernel(const __grid_constant__ RadArgs A, const __grid_constant__ RadParams P, const SplitArgs X) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y;
+  if (m >= A.rays) return;
+  const int n = X.n_lo + j;
+  if (n >= X.n_hi || n >= A.sample_num[m]) return;
+  const int F = P.num_freq;
+  const double om = __ldcs(field_ptr(X, A.rays, kFieldOm, j, m));
+  if (om == 0.0) {
+    for (int q = 0; q < 8 * F; q++) __stcs(field_ptr(X, A.rays, kFieldCoef + q, j, m), 0.0);
+    return;
+  }
+  rad::Plasma s;
+  const double sin_b = __ldcs(field_ptr(X, A.rays, kFieldSin, j, m));
+  const double cos_b = __ldcs(field_ptr(X, A.rays, kFieldCos, j, m));
+  s.bb_cgs = __ldcs(field_ptr(X, A.rays, kFieldBb, j, m));
+  s.n_e_cgs = __ldcs(field_ptr(X, A.rays, kFieldNe, j, m));
+  s.theta_e = __ldcs(field_ptr(X, A.rays, kFieldTheta, j, m));
+  s.inv_theta_e = __ldcs(field_ptr(X, A.rays, kFieldInvTheta, j, m));
+  double kk[3] = {0.0, 0.0, 0.0};
+  if (has_thermal<DIST>(P) && s.theta_e >= 0.01) {
+    bfm::bessel_k01(s.inv_theta_e, kk[0], kk[1]);
+    kk[2] = kk[0] + 2.0 * s.theta_e * kk[1];
+  }
+  PolSample sq;
+  pol_sample<DIST>(P, s, om, sin_b, cos_b, kk, sq);
+BL_FREQ_LOOP
+  for (int l = 0; l < F; l++) {
+    Coefficients C;
+    synchrotron_polarized<DIST>(P, sq, l, C);
+    double *dst = field_ptr(X, A.rays, kFieldCoef + 8 * l, j, m);
+    const size_t fs = (size_t)X.slab * (size_t)A.rays;   // distance between consecutive fields
+    __stcs(dst, C.j[0]); __stcs(dst + fs, C.j[1]); __stcs(dst + 2 * fs, C.j[2]);
+    __stcs(dst + 3 * fs, C.a[0]); __stcs(dst + 4 * fs, C.a[1]); __stcs(dst + 5 * fs, C.a[2]);
+    __stcs(dst + 6 * fs, C.rho[0]); __stcs(dst + 7 * fs, C.rho[1]);
+  }
+}
+
+// ---- stage 3: transfer --------------------------------------------------------------------------------------
+#ifndef BL_POLT_MINB
+#define BL_POLT_MINB 4
+#endif
+// FW: frequencies per CTA (1, 2 or 4); the CTA's 128 threads are 128/FW adjacent rays x FW frequencies, so that a
+// warp is 32 adjacent rays at one frequency and the FW warps of a ray group share M through L1.
+template <int FW>
+__global__ void __launch_bounds__(kBlock, BL_POLT_MINB)
+pol_transfer_kernel(const __grid_constant__ RadArgs A, const __grid_constant__ RadParams P, const SplitArgs X) {
+  constexpr int kRays = kBlock / FW;
+  const int64_t m = (int64_t)blockIdx.x * kRays + (threadIdx.x % kRays);
+  const int l = blockIdx.y * FW + threadIdx.x / kRays;
+  if (m >= A.rays || l >= P.num_freq) return;
+  const int num = A.sample_num[m];
+  if (num <= X.n_lo) return;
+  const int top = (X.n_hi < num ? X.n_hi : num) - 1;
+  const int64_t stride = A.image_stride;
+  double *img = A.image + m;
+  // the Stokes state between slabs lives in the image's own slots (zeroed before the first slab)
+  double s[4];
+  for (int a = 0; a < 4; a++) s[a] = img[(size_t)(4 * l + a) * stride];
+  const double dl_factor = P.x_unit / A.mom_factor[m] * P.inv_freqs[l];
+  const size_t fs = (size_t)X.slab * (size_t)A.rays;
+  double tau = 0.0, lam = 0.0, emi = 0.0;
+  if (P.image_tau) tau = img[(size_t)(P.off_tau + l) * stride];
+  if (P.image_lambda) lam = img[(size_t)(P.off_lambda + l) * stride];
+  if (P.image_emission) emi = img[(size_t)(P.off_emission + l) * stride];
+
+#pragma unroll 1
+  for (int n = top; n >= X.n_lo; n--) {
+    const int j = n - X.n_lo;
+    const double *lk = field_ptr(X, A.rays, kFieldM, j, m);
+    const double *cf = field_ptr(X, A.rays, kFieldCoef + 8 * l, j, m);
+    double mm[10];
+#pragma unroll
+    for (int q = 0; q < 10; q++) mm[q] = __ldg(lk + q * fs);
+    const double dlam = __ldg(lk + 10 * fs);
+    Coefficients C;
+    C.j[0] = __ldcs(cf); C.j[1] = __ldcs(cf + fs); C.j[2] = __ldcs(cf + 2 * fs);
+    C.a[0] = __ldcs(cf + 3 * fs); C.a[1] = __ldcs(cf + 4 * fs); C.a[2] = __ldcs(cf + 5 * fs);
+    C.rho[0] = __ldcs(cf + 6 * fs); C.rho[1] = __ldcs(cf + 7 * fs);
+    const double dl_cgs = dlam * dl_factor;
+    double t0 = mm[0] * s[0] + mm[1] * s[1] + mm[2] * s[2];
+    double t1 = mm[3] * s[0] + mm[4] * s[1] + mm[5] * s[2];
+    double t2 = mm[6] * s[0] + mm[7] * s[1] + mm[8] * s[2];
+    double t3 = mm[9] * s[3];
+    s[0] = t0; s[1] = t1; s[2] = t2; s[3] = t3;
+    if (P.image_tau) tau += C.a[0] * dl_cgs;
+    if (P.image_lambda) lam += dl_cgs;
+    if (P.image_emission) emi += C.j[0] * dl_cgs;
+    couple(P, C, dl_cgs, s);
+  }
+
+  if (X.n_lo == 0) {
+    double mm[10];
+    for (int q = 0; q < 10; q++) mm[q] = X.cam_map[(size_t)q * A.rays + m];
+    double f = P.freqs[l], nu_cu = f * f * f;
+    img[(size_t)(4 * l + 0) * stride] = (mm[0] * s[0] + mm[1] * s[1] + mm[2] * s[2]) * nu_cu;
+    img[(size_t)(4 * l + 1) * stride] = (mm[3] * s[0] + mm[4] * s[1] + mm[5] * s[2]) * nu_cu;
+    img[(size_t)(4 * l + 2) * stride] = (mm[6] * s[0] + mm[7] * s[1] + mm[8] * s[2]) * nu_cu;
+    img[(size_t)(4 * l + 3) * stride] = mm[9] * s[3] * nu_cu;
+  } else {
+    for (int a = 0; a < 4; a++) img[(size_t)(4 * l + a) * stride] = s[a];
+  }
+  if (P.image_tau) img[(size_t)(P.off_tau + l) * stride] = tau;
+  if (P.image_lambda) img[(size_t)(P.off_lambda + l) * stride] = lam;
+  if (P.image_emission) img[(size_t)(P.off_emission + l) * stride] = emi;
+}
+
+}  // namespace
+
+extern "C" int bl_polarized_split_fields(int num_freq) { return kFieldCoef + 8 * num_freq; }
+
+// One pass of the three stages over all slabs of a wave: samples [0, s_top) of args->rays rays.  scratch holds
+// bl_polarized_split_fields(F) * slab * rays doubles, cam_map 10 * rays; the wave's image columns must be zero.
+// events (or nullptr): 3 * slabs + 1 events recorded on `stream` around every launch, so that the caller can
+// attribute device time to the three stages after synchronising; *launches is advanced by the kernels launched.
+extern "C" int bl_polarized_split_slabs(int slab, int s_top) { return s_top <= 0 ? 0 : (s_top + slab - 1) / slab; }
+
+extern "C" cudaError_t bl_launch_radiate_polarized_split(const RadArgs *args, const RadParams *params, double *scratch,
+                                                         double *cam_map, int slab, int s_top, cudaStream_t stream,
+                                                         cudaEvent_t *events, long long *launches) {
+  const RadArgs &A = *args;
+  const RadParams &P = *params;
+  if (A.rays <= 0 || s_top <= 0) return cudaSuccess;
+  size_t smem = 0;
+  if ((size_t)A.grid.n_b * 6 * sizeof(double) <= 48 * 1024) smem = (size_t)A.grid.n_b * 6 * sizeof(double);
+  const bool thermal_only = P.thermal_frac != 0.0 && P.power_frac == 0.0 && P.kappa_frac == 0.0;
+  const bool kappa_only = P.kappa_frac != 0.0 && P.power_frac == 0.0 && P.thermal_frac == 0.0;
+  const int F = P.num_freq;
+  const int fw = F >= 4 ? 4 : (F >= 2 ? 2 : 1);
+  const unsigned ray_blocks = (unsigned)((A.rays + kBlock - 1) / kBlock);
+  int ev = 0;
+  if (events) cudaEventRecord(events[ev++], stream);
+  for (int n_hi = (s_top + slab - 1) / slab * slab; n_hi > 0; n_hi -= slab) {
+    SplitArgs X;
+    X.scratch = scratch; X.cam_map = cam_map; X.slab = slab;
+    X.n_lo = n_hi - slab; X.n_hi = n_hi < s_top ? n_hi : s_top;
+    pol_geometry_kernel<<<ray_blocks, kBlock, smem, stream>>>(A, P, X);
+    if (events) cudaEventRecord(events[ev++], stream);
+    dim3 cgrid(ray_blocks, (unsigned)(X.n_hi - X.n_lo));
+    if (thermal_only) pol_coefficient_kernel<1><<<cgrid, kBlock, 0, stream>>>(A, P, X);
+    else if (kappa_only) pol_coefficient_kernel<4><<<cgrid, kBlock, 0, stream>>>(A, P, X);
+    else pol_coefficient_kernel<7><<<cgrid, kBlock, 0, stream>>>(A, P, X);
+    if (events) cudaEventRecord(events[ev++], stream);
+    dim3 tgrid((unsigned)((A.rays + kBlock / fw - 1) / (kBlock / fw)), (unsigned)((F + fw - 1) / fw));
+    if (fw == 4) pol_transfer_kernel<4><<<tgrid, kBlock, 0, stream>>>(A, P, X);
+    else if (fw == 2) pol_transfer_kernel<2><<<tgrid, kBlock, 0, stream>>>(A, P, X);
+    else pol_transfer_kernel<1><<<tgrid, kBlock, 0, stream>>>(A, P, X);
+    if (events) cudaEventRecord(events[ev++], stream);
+    if (launches) *launches += 3;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}

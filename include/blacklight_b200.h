@@ -222,6 +222,13 @@ int bl_retrace_level(bl_ctx *ctx, int level, bl_level_stats *stats);
 /* Number of CUDA kernels of this library launched by the context so far (bench accounting). */
 long long bl_launch_count(const bl_ctx *ctx);
 
+/* Polarized levels without per-sample side outputs are rendered by a three-stage pipeline over slabs of the step
+ * buffer (geometry + Stokes transport matrix | synchrotron coefficients | Stokes coupling; csrc/radiate_pol_split.cu)
+ * in place of the single fused kernel.  ms3: device time of the three stages during the last bl_radiate_level of the
+ * level (CUDA events around every launch); *slab: samples per slab, 0 if the fused kernel ran.  Environment, tuning
+ * only: BL_POL_FUSED=1 keeps the fused kernel, BL_POL_SLAB=n fixes the slab length. */
+int bl_polarized_stage_ms(bl_ctx *ctx, int level, double *ms3, int32_t *slab);
+
 /* The CUDA stream (cudaStream_t) every kernel and copy of this context is issued on, so that a host
  * can bracket calls with its own events or order other work against them. */
 void *bl_cuda_stream(const bl_ctx *ctx);

@@ -1008,3 +1008,60 @@ def test_golden_slow_light(name, gpu, tmp_path):
     ref = np.load(os.path.join(GOLDEN, name + '.npz'))['I_nu']
     assert rel_err(mine, ref) <= PIXEL_TOL
     assert flux_rel(mine, ref) <= FLUX_TOL
+
+
+C4_PHYSICS = {'image_polarization': 'true', 'image_num_frequencies': 4, 'image_frequency_start': '8.6e10',
+              'image_frequency_end': '3.45e11', 'image_frequency_spacing': 'log', 'plasma_kappa_frac': '1.0',
+              'plasma_kappa': '4.0', 'plasma_w': '1.0'}
+
+
+def _render_polarized(case, env, tile_rays=0):
+    """One level-0 polarized image with the given BL_POL_* environment (read by bl_create)."""
+    saved = {k: os.environ.get(k) for k in ('BL_POL_FUSED', 'BL_POL_SLAB')}
+    try:
+        for k in saved:
+            os.environ.pop(k, None)
+        os.environ.update(env)
+        cfg = case.config(tile_rays=tile_rays)
+        ctx = bl.Context(cfg)
+    finally:
+        for k, v in saved.items():
+            os.environ.pop(k, None)
+            if v is not None:
+                os.environ[k] = v
+    ctx.upload_grid(case.grid_arrays())
+    pos, dirs, fac = cfg.camera_root()
+    ctx.trace_level(0, pos, dirs, fac)
+    image, _, stats = ctx.radiate_level(0)
+    stages = ctx.polarized_stage_ms(0)
+    ctx.close()
+    return image, stats, stages
+
+
+@pytest.mark.parametrize('over', [
+    dict(C4_PHYSICS, camera_resolution=40),
+    {'camera_resolution': 40, 'image_polarization': 'true', 'image_tau': 'true', 'image_lambda': 'true', 'image_emission': 'true'},
+    {'camera_resolution': 32, 'image_polarization': 'true', 'image_rotation_split': 'true', 'image_num_frequencies': 2,
+     'image_frequency_start': '2.3e11', 'image_frequency_end': '4.6e11', 'image_frequency_spacing': 'log',
+     'plasma_power_frac': '0.5', 'plasma_p': '3.0', 'plasma_gamma_min': '4.0', 'plasma_gamma_max': '1000.0',
+     'plasma_kappa_frac': '0.25', 'plasma_kappa': '3.7', 'plasma_w': '1.5', 'simulation_a': '0.9'},
+])
+def test_polarized_pipeline_matches_fused_kernel(over, gpu, tmp_path):
+    """The three-stage polarized pipeline (geometry | coefficients | transfer over slabs, radiate_pol_split.cu) and the
+    single fused kernel evaluate the same formulas: the images must agree to rounding, for every slab length (a slab
+    boundary re-derives the previous sample's frame from a halo sample) and when the level is traced in waves."""
+    case = Case(tmp_path, 'simulation.input', over)
+    fused, st_f, stages_f = _render_polarized(case, {'BL_POL_FUSED': '1'})
+    assert stages_f['slab'] == 0
+    for env, tile in (({}, 0), ({'BL_POL_SLAB': '16'}, 0), ({'BL_POL_SLAB': '7'}, 0), ({'BL_POL_SLAB': '2000'}, 0),
+                      ({'BL_POL_SLAB': '32'}, 512)):
+        image, st, stages = _render_polarized(case, env, tile_rays=tile)
+        assert stages['slab'] > 0, 'the pipeline did not run'
+        assert st['num_samples'] == st_f['num_samples']
+        assert np.array_equal(np.isnan(image), np.isnan(fused))
+        light = 4 * int(over.get('image_num_frequencies', 1))
+        scale = np.nanmax(np.abs(fused[0:light:4]))   # brightest Stokes I
+        err = np.nanmax(np.abs(image[:light] - fused[:light])) / scale
+        assert err <= 1e-12, 'slab %s tile %d: Stokes images differ by %.3e of the peak' % (env, tile, err)
+        if image.shape[0] > light:
+            assert rel_err(image[light:], fused[light:]) <= 1e-12
