@@ -69,6 +69,7 @@ def load_library():
         'bl_retrace_level': (i32, [vp, i32, ctypes.POINTER(LevelStats)]),
         'bl_upload_samples': (i32, [vp, i32, vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, ctypes.POINTER(LevelStats)]),
         'bl_launch_count': (ctypes.c_longlong, [vp]), 'bl_cuda_stream': (vp, [vp]),
+        'bl_device_image': (i32, [vp, i32, ctypes.POINTER(vp), ctypes.POINTER(i64)]),
         'bl_polarized_stage_ms': (i32, [vp, i32, ctypes.POINTER(dbl * 3), ctypes.POINTER(ctypes.c_int32)]),
         'bl_download_samples': (i32, [vp, i32, vp, vp, vp, vp, vp]),
         'bl_download_sample_inds': (i32, [vp, i32, vp, vp, vp, vp, vp]),
@@ -280,6 +281,12 @@ class Context:
 
     def launch_count(self):
         return int(_lib.bl_launch_count(self._h))
+
+    def device_image(self, level=0):
+        """(device pointer, (Q, rays)) of the level's image in HBM: bl_device_image."""
+        ptr, n = ctypes.c_void_p(), ctypes.c_int64()
+        self._check(_lib.bl_device_image(self._h, level, ctypes.byref(ptr), ctypes.byref(n)))
+        return ptr.value, (self.num_quantities, n.value)
 
     def polarized_stage_ms(self, level=0):
         """Device ms of the three polarized stages (geometry, coefficients, transfer) in the last radiate_level and the

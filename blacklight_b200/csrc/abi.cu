@@ -1029,6 +1029,16 @@ int bl_upload_samples(bl_ctx *ctx, int level, const double *cam_pos, const doubl
 
 long long bl_launch_count(const bl_ctx *ctx) { return ctx ? ctx->launches : -1; }
 
+int bl_device_image(bl_ctx *ctx, int level, void **image, int64_t *num_rays) {
+  if (!ctx || !image) return BL_ERR_ARG;
+  if (level < 0 || level >= (int)ctx->levels.size()) return bl_fail(ctx, BL_ERR_ARG, "bl_device_image: level %d out of range", level);
+  const Level &L = ctx->levels[level];
+  if (!L.image) return bl_fail(ctx, BL_ERR_STATE, "bl_device_image: level %d has no image", level);
+  *image = L.image;
+  if (num_rays) *num_rays = L.rays;
+  return BL_OK;
+}
+
 int bl_polarized_stage_ms(bl_ctx *ctx, int level, double *ms3, int32_t *slab) {
   if (!ctx || !ms3) return BL_ERR_ARG;
   if (level < 0 || level >= (int)ctx->levels.size()) return bl_fail(ctx, BL_ERR_ARG, "bl_polarized_stage_ms: level %d out of range", level);

@@ -11,7 +11,22 @@
 
 namespace blh {
 
+// What the first file of a series fixes and later files of the series (reuse_layout) rely on.  It belongs to the grid
+// that was read, so two open snapshots -- or two threads -- never see each other's.
+struct ReaderLayout {
+  // athenak: position in the file of each internal variable, bytes per block record, and what the layout was taken from
+  int file_ind[9] = {0, 0, 0, 0, 0, 0, 0, 0, -1};
+  long block_bytes = 0;
+  int num_file_variables = 0, location_size = 0, variable_size = 0;
+  // harm3d / iharm3d: x2 cell centres in the modified coordinates (for the Jacobian) and the coordinate parameters
+  // (simulation_reader.cpp:362-428)
+  std::vector<double> x2v_mod;
+  bool fmks = false;
+  double a = 0.0, h = 1.0, r_in = 0.0, poly_xt = 0.0, poly_alpha = 0.0, mks_smooth = 0.0, poly_norm = 0.0;
+};
+
 struct AthenaGrid {
+  ReaderLayout layout;
   int n_b = 0, n_k = 0, n_j = 0, n_i = 0, n_var = 0;
   std::vector<int32_t> levels, locations;
   std::vector<double> x1f, x2f, x3f, x1v, x2v, x3v;  // float32 file values widened to double

@@ -111,13 +111,6 @@ void block_axis(double lo, double hi, int n, double *f, double *v) {
   for (int i = 0; i < n; i++) v[i] = 0.5 * (f[i] + f[i + 1]);
 }
 
-// Layout of the open snapshot as found in the first file (file variable position of each internal variable)
-struct Layout {
-  int file_ind[9] = {0, 0, 0, 0, 0, 0, 0, 0, -1};
-  long block_bytes = 0;
-};
-thread_local Layout layout;
-
 }  // namespace
 
 void read_athenak_header(const std::string &path, double *time, double *gamma_adi) {
@@ -135,7 +128,22 @@ void read_athenak(const std::string &path, const std::string &kappa_name, bool r
   Header hd = read_header(in);
   g.time = hd.time;
   const bool want_kappa = !kappa_name.empty();
+  ReaderLayout &layout = g.layout;   // found in the first file of the series, kept with the grid
+  if (reuse_layout) {
+    // a later file must have the records the stored layout describes
+    if (g.n_b <= 0 || layout.block_bytes <= 0) throw Error("AthenaK series: no first snapshot to take the layout from.");
+    if ((int)hd.names.size() != layout.num_file_variables || hd.location_size != layout.location_size ||
+        hd.variable_size != layout.variable_size)
+      throw Error("AthenaK file does not match the layout of the first snapshot of the series.");
+    in.seekg(0, std::ios::end);
+    if (((long)in.tellg() - (long)hd.data_begin) / layout.block_bytes != g.n_b)
+      throw Error("AthenaK file does not match the layout of the first snapshot of the series.");
+  }
   if (!reuse_layout) {
+    layout = ReaderLayout();
+    layout.num_file_variables = (int)hd.names.size();
+    layout.location_size = hd.location_size;
+    layout.variable_size = hd.variable_size;
     // internal order rho, uu1, uu2, uu3, pgas, bb1, bb2, bb3, [kappa] (simulation_reader.cpp:1279-1288)
     layout.file_ind[0] = locate(hd, "dens", "Unable to locate \"dens\" values in data file.");
     layout.file_ind[4] = locate(hd, "eint", "Unable to locate \"eint\" values in data file.");

@@ -62,8 +62,10 @@ void read_harm3d(const std::string &path, bool want_kappa, bool gamma_set, doubl
   if (!in.is_open()) throw Error("Could not open file for reading.");
   Header hd = read_header(in);
   g.time = hd.time;
-  static thread_local std::vector<double> x2v_mod;   // x2 centres in modified coordinates (for the Jacobian)
-  static thread_local double metric_h = 1.0;
+  std::vector<double> &x2v_mod = g.layout.x2v_mod;   // x2 centres in modified coordinates (for the Jacobian)
+  double &metric_h = g.layout.h;
+  if (reuse_layout && (g.n_b != 1 || g.n_i != hd.n[0] || g.n_j != hd.n[1] || g.n_k != hd.n[2] || (int)x2v_mod.size() != g.n_j))
+    throw Error("harm3d file does not match the layout of the first snapshot of the series.");
   if (!reuse_layout) {
     g.n_b = 1;
     g.n_i = hd.n[0]; g.n_j = hd.n[1]; g.n_k = hd.n[2];
@@ -134,7 +136,7 @@ void read_harm3d(const std::string &path, bool want_kappa, bool gamma_set, doubl
   // (ConvertPrimitives4, simulation_geometry.cpp:242-327)
   const double a = simulation_a;
   auto at = [&](int v, int k, int j, int i) -> float & { return g.prim[(((size_t)v * n3 + k) * n2 + j) * n1 + i]; };
-  const std::vector<double> &x2_mod = x2v_mod;   // the parallel region's threads have their own thread_locals
+  const std::vector<double> &x2_mod = x2v_mod;
   const double h_slope = metric_h;
 #pragma omp parallel for schedule(static) collapse(2)
   for (int k = 0; k < n3; k++)

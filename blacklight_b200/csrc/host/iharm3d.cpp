@@ -20,13 +20,8 @@ constexpr double kAngularDomainTolerance = 0.1;   // simulation_reader.hpp:100
 constexpr int kMapN1 = 2048, kMapN2 = 2048, kMapMaxIter = 1000;   // :109-112
 constexpr double kMapTol = 1.0e-8;
 
-// parameters of the modified coordinates (simulation_reader.cpp:362-428)
-struct Metric {
-  bool fmks = false;
-  double a = 0.0, h = 1.0, r_in = 0.0, poly_xt = 0.0, poly_alpha = 0.0, mks_smooth = 0.0, poly_norm = 0.0;
-};
-thread_local Metric metric;
-thread_local std::vector<double> x2v_mod;   // x2 centres in modified coordinates (for the Jacobian)
+// parameters of the modified coordinates (simulation_reader.cpp:362-428): kept with the grid they were read for
+using Metric = ReaderLayout;
 
 double scalar(const H5File &f, const std::string &path) {
   std::vector<double> v = double_dataset(f, path);
@@ -188,6 +183,10 @@ void read_iharm3d(const std::string &path, const std::string &kappa_name, bool r
                   AthenaGrid &g) {
   H5File f(path);
   g.time = scalar(f, "t");
+  Metric &metric = g.layout;
+  std::vector<double> &x2v_mod = g.layout.x2v_mod;   // x2 centres in modified coordinates (for the Jacobian)
+  if (reuse_layout && (g.n_b != 1 || g.n_var <= 0 || (!metric.fmks && (int)x2v_mod.size() != g.n_j)))
+    throw Error("iharm3d series: no first snapshot to take the layout from.");
   if (!reuse_layout) {
     // metric (simulation_reader.cpp:362-432)
     std::vector<std::string> name = string_dataset(f, "header/metric");
@@ -294,7 +293,7 @@ void read_iharm3d(const std::string &path, const std::string &kappa_name, bool r
   // Kerr-Schild one through the Jacobian, u~ -> four-velocity, B -> magnetic four-vector, both pushed to the
   // (t, r, theta, phi) basis, then back to normal-frame velocity and B^i = b^i u^t - b^t u^i there.
   const double a = expect.simulation_a;
-  const Metric m = metric;                       // the parallel region's threads have their own thread_locals
+  const Metric &m = metric;
   const std::vector<double> &x2_mod = x2v_mod;
   const int vel[3] = {g.ind_uu1, g.ind_uu2, g.ind_uu3}, mag[3] = {g.ind_bb1, g.ind_bb2, g.ind_bb3};
 #pragma omp parallel for schedule(static) collapse(2)

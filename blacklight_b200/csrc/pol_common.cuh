@@ -115,6 +115,53 @@ __device__ __forceinline__ void contracted_connection(const KsJet &J, const doub
   }
 }
 
+// The same contraction applied to a vector without forming the matrix: out^mu = -Gamma^mu_{alpha beta} k^alpha v^beta,
+// the rate of change of a parallel-transported vector's components along k.  With g = eta + f l l (stationary),
+//   2 Gamma_{mu alpha beta} k^alpha v^beta = k.d g_{mu beta} v^beta + v.d g_{mu alpha} k^alpha - d_mu g_{alpha beta} k^alpha v^beta
+// and every term is a handful of dot products of k, v with l, grad f and grad l.  The parts that depend on k alone are
+// gathered once per (jet, k) in KContraction; a vector then costs ~110 operations instead of a 16-entry matrix row
+// sweep, and no 4x4 arrays stay live in registers.
+struct KContraction {
+  double k[4];
+  double kf;      // k.grad f
+  double lk;      // l_alpha k^alpha
+  double kl[3];   // k.grad l_i
+  double mk[3];   // k^i d_a l_i
+};
+
+__device__ __forceinline__ void k_contraction(const KsJet &J, const double k[4], KContraction &K) {
+  for (int mu = 0; mu < 4; mu++) K.k[mu] = k[mu];
+  K.kf = k[1] * J.df[0] + k[2] * J.df[1] + k[3] * J.df[2];
+  K.lk = k[0] + J.l[0] * k[1] + J.l[1] * k[2] + J.l[2] * k[3];
+  for (int i = 0; i < 3; i++) {
+    K.kl[i] = k[1] * J.dl[i][0] + k[2] * J.dl[i][1] + k[3] * J.dl[i][2];
+    K.mk[i] = k[1] * J.dl[0][i] + k[2] * J.dl[1][i] + k[3] * J.dl[2][i];
+  }
+}
+
+__device__ __forceinline__ void transport_rate_direct(const KsJet &J, const KContraction &K, const double v[4], double out[4]) {
+  const double lv = v[0] + J.l[0] * v[1] + J.l[1] * v[2] + J.l[2] * v[3];
+  const double vf = v[1] * J.df[0] + v[2] * J.df[1] + v[3] * J.df[2];
+  double vl[3], mv[3];
+  for (int i = 0; i < 3; i++) {
+    vl[i] = v[1] * J.dl[i][0] + v[2] * J.dl[i][1] + v[3] * J.dl[i][2];
+    mv[i] = v[1] * J.dl[0][i] + v[2] * J.dl[1][i] + v[3] * J.dl[2][i];
+  }
+  const double klv = K.kl[0] * v[1] + K.kl[1] * v[2] + K.kl[2] * v[3];
+  const double vlk = vl[0] * K.k[1] + vl[1] * K.k[2] + vl[2] * K.k[3];
+  const double a12 = (K.kf * lv + J.f * klv) + (vf * K.lk + J.f * vlk);   // coefficient of l_mu in the first two terms
+  const double b1 = J.f * lv, b2 = J.f * K.lk, c3 = K.lk * lv;
+  const double g0 = 0.5 * a12;
+  double g[3];
+  for (int i = 0; i < 3; i++)
+    g[i] = 0.5 * (a12 * J.l[i] + b1 * K.kl[i] + b2 * vl[i] - (J.df[i] * c3 + b1 * K.mk[i] + b2 * mv[i]));
+  const double s = J.f * (-g0 + J.l[0] * g[0] + J.l[1] * g[1] + J.l[2] * g[2]);
+  out[0] = g0 - s;
+  out[1] = s * J.l[0] - g[0];
+  out[2] = s * J.l[1] - g[1];
+  out[3] = s * J.l[2] - g[2];
+}
+
 // (D v)^mu = -A^mu_beta v^beta : rate of change of a parallel-transported vector's components
 __device__ __forceinline__ void transport_rate(const double A[4][4], const double v[4], double out[4]) {
   for (int mu = 0; mu < 4; mu++) out[mu] = -(A[mu][0] * v[0] + A[mu][1] * v[1] + A[mu][2] * v[2] + A[mu][3] * v[3]);
@@ -198,6 +245,55 @@ __device__ __forceinline__ void stokes_map(const LegProj L[2], double h, double 
     M.m[row][2] = c12;         // U
   }
   M.vv = 0.5 * (Pm[1][0][1][0] - Pm[0][1][1][0] - Pm[1][0][0][1] + Pm[0][1][0][1]);
+}
+
+// Stokes transport matrix from the previous sample (jet_p, contravariant momentum k_p, legs e_p, affine step dlam_p) to the
+// current one (jet, kcon, covariant legs f1, f2, affine step dlam): predictor with the previous sample's own connection,
+// corrector with the average of both samples' connections contracted with the averaged momentum (polarized.cpp:136-192).
+__device__ __forceinline__ void transport_map(const KsJet &jet_p, const double k_p[4], const double e_p[2][4], double dlam_p,
+                                              const KsJet &jet, const double kcon[4], const double f1[4], const double f2[4],
+                                              double dlam, StokesMap &M) {
+  const double ks[4] = {k_p[0] + kcon[0], k_p[1] + kcon[1], k_p[2] + kcon[2], k_p[3] + kcon[3]};
+  KContraction Kpp, Kps, Kns;
+  k_contraction(jet_p, k_p, Kpp);
+  k_contraction(jet_p, ks, Kps);
+  k_contraction(jet, ks, Kns);
+  const double h = (dlam_p + dlam) / 2.0, h2 = (dlam_p + dlam) / 4.0;
+  LegProj L[2];
+  for (int c = 0; c < 2; c++) {
+    double vp[4], va[4], vap[4], t0[4], t1[4];
+    transport_rate_direct(jet_p, Kpp, e_p[c], vp);
+    // the corrector's connection is the mean of the two samples' (each contracted with (k_p + k) / 2): a factor 1/4
+    transport_rate_direct(jet_p, Kps, e_p[c], t0);
+    transport_rate_direct(jet, Kns, e_p[c], t1);
+    for (int mu = 0; mu < 4; mu++) va[mu] = 0.25 * (t0[mu] + t1[mu]);
+    // the corrector derivative acts on the predicted tensor: Da(e + h2 Dp e) = Da e + h2 Da Dp e
+    transport_rate_direct(jet_p, Kps, vp, t0);
+    transport_rate_direct(jet, Kns, vp, t1);
+    for (int mu = 0; mu < 4; mu++) vap[mu] = 0.25 * (t0[mu] + t1[mu]);
+    L[c].u[0] = dot4(f1, e_p[c]);  L[c].u[1] = dot4(f2, e_p[c]);
+    L[c].up[0] = dot4(f1, vp);     L[c].up[1] = dot4(f2, vp);
+    L[c].ua[0] = dot4(f1, va);     L[c].ua[1] = dot4(f2, va);
+    L[c].uap[0] = dot4(f1, vap);   L[c].uap[1] = dot4(f2, vap);
+  }
+  stokes_map(L, h, h * h2, true, M);
+}
+
+// The last half step, from the sample nearest the camera onto the camera tetrad's covariant legs (polarized.cpp:816-833):
+// predictor only.
+__device__ __forceinline__ void transport_map_final(const KsJet &jet_p, const double k_p[4], const double e_p[2][4], double dlam_p,
+                                                    const double f1[4], const double f2[4], StokesMap &M) {
+  KContraction Kpp;
+  k_contraction(jet_p, k_p, Kpp);
+  LegProj L[2];
+  for (int c = 0; c < 2; c++) {
+    double vp[4];
+    transport_rate_direct(jet_p, Kpp, e_p[c], vp);
+    L[c].u[0] = dot4(f1, e_p[c]);  L[c].u[1] = dot4(f2, e_p[c]);
+    L[c].up[0] = dot4(f1, vp);     L[c].up[1] = dot4(f2, vp);
+    L[c].ua[0] = L[c].ua[1] = L[c].uap[0] = L[c].uap[1] = 0.0;
+  }
+  stokes_map(L, 0.0, dlam_p / 2.0, false, M);
 }
 
 struct Coefficients {
@@ -499,59 +595,57 @@ __device__ __forceinline__ void couple(const RadParams &P, const Coefficients &C
     double lambda_2 = sqrt(lambda_a - lambda_b);
     double theta = lambda_1 * lambda_1 + lambda_2 * lambda_2;
     double sg = alpha_rho >= 0.0 ? 1.0 : -1.0;
-    double m2[4][4] = {}, m3[4][4] = {}, m4[4][4] = {};
-    m2[0][1] = lambda_2 * al[1] - sg * lambda_1 * rho[1];
-    m2[0][3] = lambda_2 * al[3] - sg * lambda_1 * rho[3];
-    m2[1][2] = sg * lambda_1 * al[1] + lambda_2 * rho[1];
-    m2[1][0] = m2[0][1];
-    m2[3][0] = m2[0][3];
-    m2[2][1] = -m2[1][2];
-    m3[0][1] = lambda_1 * al[1] + sg * lambda_2 * rho[1];
-    m3[0][3] = lambda_1 * al[3] + sg * lambda_2 * rho[3];
-    m3[1][2] = -(sg * lambda_2 * al[1] - lambda_1 * rho[1]);
-    m3[1][0] = m3[0][1];
-    m3[3][0] = m3[0][3];
-    m3[2][1] = -m3[1][2];
-    double half = (alpha_sq + rho_sq) / 2.0;
-    m4[0][0] = half;
-    m4[1][1] = al[1] * al[1] + rho[1] * rho[1] - half;
-    m4[2][2] = -half;
-    m4[3][3] = al[3] * al[3] + rho[3] * rho[3] - half;
-    m4[0][2] = al[1] * rho[3] - al[3] * rho[1];
-    m4[1][3] = al[3] * al[1] + rho[3] * rho[1];
-    m4[2][0] = -m4[0][2];
-    m4[3][1] = m4[1][3];
-    double it = 1.0 / theta, it2 = 2.0 / theta;
-    for (int a = 0; a < 4; a++)
-      for (int b = 0; b < 4; b++) {
-        m2[a][b] *= it;
-        m3[a][b] *= it;
-        m4[a][b] *= it2;
-      }
+    // Of the sixteen entries of each matrix the reference fills six of mm_2 and mm_3 -- (0,1), (1,0), (0,3), (3,0),
+    // (1,2), (2,1) -- and eight of mm_4 -- the diagonal, (0,2), (2,0), (1,3), (3,1); the identity mm_1 has the
+    // diagonal.  Only those entries are evaluated: three kinds (diagonal, mm_2/mm_3 entry, off-diagonal mm_4
+    // entry), each with the terms of polarized.cpp:735-779 that do not vanish identically.
+    const double it = 1.0 / theta, it2 = 2.0 / theta;
+    const double x01_2 = (lambda_2 * al[1] - sg * lambda_1 * rho[1]) * it;
+    const double x03_2 = (lambda_2 * al[3] - sg * lambda_1 * rho[3]) * it;
+    const double x12_2 = (sg * lambda_1 * al[1] + lambda_2 * rho[1]) * it;
+    const double x01_3 = (lambda_1 * al[1] + sg * lambda_2 * rho[1]) * it;
+    const double x03_3 = (lambda_1 * al[3] + sg * lambda_2 * rho[3]) * it;
+    const double x12_3 = -(sg * lambda_2 * al[1] - lambda_1 * rho[1]) * it;
+    const double half = (alpha_sq + rho_sq) / 2.0;
+    const double d0 = half * it2, d1 = (al[1] * al[1] + rho[1] * rho[1] - half) * it2, d2 = -half * it2;
+    const double d3 = (al[3] * al[3] + rho[3] * rho[3] - half) * it2;
+    const double y02 = (al[1] * rho[3] - al[3] * rho[1]) * it2, y13 = (al[3] * al[1] + rho[3] * rho[1]) * it2;
     double ex = 0.0, sn = 0.0, cs = 0.0, snh = 0.0, csh = 0.0;
     if (thin) {
       ex = bfm::exp_bf(-delta_tau);
       sincos(lambda_2 * dl, &sn, &cs);
       bfm::sinhcosh_bf(lambda_1 * dl, snh, csh);
     }
-    double f_1 = 1.0 / (al[0] * al[0] - lambda_1 * lambda_1);
-    double f_2 = 1.0 / (al[0] * al[0] + lambda_2 * lambda_2);
-    for (int a = 0; a < 4; a++)
-      for (int b = 0; b < 4; b++) {
-        double m1 = a == b ? 1.0 : 0.0;
-        double cosh_term = -lambda_1 * f_1 * m3[a][b] + 0.5 * al[0] * f_1 * (m1 + m4[a][b]);
-        double cos_term = -lambda_2 * f_2 * m2[a][b] + 0.5 * al[0] * f_2 * (m1 - m4[a][b]);
-        double pp = cosh_term + cos_term;
-        if (thin) {
-          double sin_term = -al[0] * f_2 * m2[a][b] - 0.5 * lambda_2 * f_2 * (m1 - m4[a][b]);
-          double sinh_term = -al[0] * f_1 * m3[a][b] + 0.5 * lambda_1 * f_1 * (m1 + m4[a][b]);
-          pp -= ex * (cosh_term * csh + cos_term * cs + sin_term * sn + sinh_term * snh);
-          double oo = ex * (0.5 * (m1 + m4[a][b]) * csh + 0.5 * (m1 - m4[a][b]) * cs - m2[a][b] * sn - m3[a][b] * snh);
-          out[a] += pp * j[b] + oo * s[b];
-        } else {
-          out[a] += pp * j[b];
-        }
-      }
+    const double f_1 = 1.0 / (al[0] * al[0] - lambda_1 * lambda_1);
+    const double f_2 = 1.0 / (al[0] * al[0] + lambda_2 * lambda_2);
+    const double a1f = al[0] * f_1, a2f = al[0] * f_2, l1f = lambda_1 * f_1, l2f = lambda_2 * f_2;
+    // entry with (mm_1 + mm_4) / 2 = p and (mm_1 - mm_4) / 2 = q, mm_2 = mm_3 = 0
+    auto even_entry = [&](double p, double q, double jb, double sb) {
+      double cosh_term = a1f * p, cos_term = a2f * q;
+      double pp = cosh_term + cos_term;
+      if (!thin) return pp * jb;
+      pp -= ex * (cosh_term * csh + cos_term * cs + (-l2f * q) * sn + (l1f * p) * snh);
+      return pp * jb + ex * (p * csh + q * cs) * sb;
+    };
+    // entry with mm_2 = x2, mm_3 = x3, mm_1 = mm_4 = 0
+    auto odd_entry = [&](double x2, double x3, double jb, double sb) {
+      double cosh_term = -l1f * x3, cos_term = -l2f * x2;
+      double pp = cosh_term + cos_term;
+      if (!thin) return pp * jb;
+      pp -= ex * (cosh_term * csh + cos_term * cs + (-a2f * x2) * sn + (-a1f * x3) * snh);
+      return pp * jb + ex * (-x2 * sn - x3 * snh) * sb;
+    };
+    // column 2 multiplies j_U = 0: only the propagator part survives there
+    auto even_prop = [&](double p, double q, double sb) { return thin ? ex * (p * csh + q * cs) * sb : 0.0; };
+    auto odd_prop = [&](double x2, double x3, double sb) { return thin ? ex * (-x2 * sn - x3 * snh) * sb : 0.0; };
+    out[0] = even_entry(0.5 * (1.0 + d0), 0.5 * (1.0 - d0), j[0], s[0]) + odd_entry(x01_2, x01_3, j[1], s[1]) +
+             even_prop(0.5 * y02, -0.5 * y02, s[2]) + odd_entry(x03_2, x03_3, j[3], s[3]);
+    out[1] = odd_entry(x01_2, x01_3, j[0], s[0]) + even_entry(0.5 * (1.0 + d1), 0.5 * (1.0 - d1), j[1], s[1]) +
+             odd_prop(x12_2, x12_3, s[2]) + even_entry(0.5 * y13, -0.5 * y13, j[3], s[3]);
+    out[2] = even_entry(-0.5 * y02, 0.5 * y02, j[0], s[0]) + odd_entry(-x12_2, -x12_3, j[1], s[1]) +
+             even_prop(0.5 * (1.0 + d2), 0.5 * (1.0 - d2), s[2]);
+    out[3] = odd_entry(x03_2, x03_3, j[0], s[0]) + even_entry(0.5 * y13, -0.5 * y13, j[1], s[1]) +
+             even_entry(0.5 * (1.0 + d3), 0.5 * (1.0 - d3), j[3], s[3]);
   }
   admissible(out, true);
   for (int a = 0; a < 4; a++) s[a] = out[a];

@@ -135,29 +135,7 @@ radiate_polarized_kernel(const __grid_constant__ RadArgs A, const __grid_constan
 
     // ---- Stokes transport matrix from the previous sample to this one ----
     StokesMap M;
-    if (have_prev) {
-      double ks[4] = {k_p[0] + kcon[0], k_p[1] + kcon[1], k_p[2] + kcon[2], k_p[3] + kcon[3]};
-      double A_avg[4][4], A_tmp[4][4], A_pp[4][4];
-      contracted_connection(jet_p, ks, A_avg);
-      contracted_connection(jet, ks, A_tmp);
-      for (int a = 0; a < 4; a++)
-        for (int b = 0; b < 4; b++) A_avg[a][b] = 0.25 * (A_avg[a][b] + A_tmp[a][b]);
-      contracted_connection(jet_p, k_p, A_pp);
-      double h = (dlam_p + dlam) / 2.0, h2 = (dlam_p + dlam) / 4.0;
-      LegProj L[2];
-      for (int c = 0; c < 2; c++) {
-        double vp[4], va[4], vap[4];
-        transport_rate(A_pp, e_p[c], vp);
-        // corrector derivative acts on the predicted tensor: Da(e + h2 Dp e) = Da e + h2 Da Dp e
-        transport_rate(A_avg, e_p[c], va);
-        transport_rate(A_avg, vp, vap);
-        L[c].u[0] = dot4(f1, e_p[c]);  L[c].u[1] = dot4(f2, e_p[c]);
-        L[c].up[0] = dot4(f1, vp);     L[c].up[1] = dot4(f2, vp);
-        L[c].ua[0] = dot4(f1, va);     L[c].ua[1] = dot4(f2, va);
-        L[c].uap[0] = dot4(f1, vap);   L[c].uap[1] = dot4(f2, vap);
-      }
-      stokes_map(L, h, h * h2, true, M);
-    }
+    if (have_prev) transport_map(jet_p, k_p, e_p, dlam_p, jet, kcon, f1, f2, dlam, M);
 
     // pitch angle from invariants (see radiate_unpol.cu)
     double omega = -dot4(kc, ps.ucon);
@@ -267,18 +245,8 @@ BL_FREQ_LOOP
       up[3] = vc[3] + uc[3] * vc[0];
       double e1[4], e2[4], f1[4], f2[4];
       tetrad_legs(jc, uc, ul, kcon, kcov, up, e1, e2, f1, f2);
-      double A_pp[4][4];
-      contracted_connection(jet_p, k_p, A_pp);
-      LegProj L[2];
-      for (int c = 0; c < 2; c++) {
-        double vp[4];
-        transport_rate(A_pp, e_p[c], vp);
-        L[c].u[0] = dot4(f1, e_p[c]);  L[c].u[1] = dot4(f2, e_p[c]);
-        L[c].up[0] = dot4(f1, vp);     L[c].up[1] = dot4(f2, vp);
-        L[c].ua[0] = L[c].ua[1] = L[c].uap[0] = L[c].uap[1] = 0.0;
-      }
       StokesMap M;
-      stokes_map(L, 0.0, dlam_p / 2.0, false, M);
+      transport_map_final(jet_p, k_p, e_p, dlam_p, f1, f2, M);
       if (P.image_light)
 BL_FREQ_LOOP
         for (int l = 0; l < F; l++) {

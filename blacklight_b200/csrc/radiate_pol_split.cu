@@ -21,6 +21,9 @@
 // Slabs run from the far end of the rays (large n) to the camera (n = 0), three launches each, on one stream.
 // The scratch between the stages is field-major, scratch[(field * slab + j) * rays + m]: every access of a warp
 // is a contiguous 256-byte row.
+#include <cstdio>
+#include <cstdlib>
+
 #include "pol_common.cuh"
 
 namespace {
@@ -50,7 +53,8 @@ __device__ __forceinline__ double *field_ptr(const SplitArgs &X, int64_t rays, i
 }
 
 // ---- stage 1: geometry --------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock, 2)
+template <int MINB>
+__global__ void __launch_bounds__(kBlock, MINB)
 pol_geometry_kernel(const __grid_constant__ RadArgs A, const __grid_constant__ RadParams P, const SplitArgs X) {
   extern __shared__ double smem_bounds[];
   const GridDev &G = A.grid;
@@ -134,28 +138,7 @@ pol_geometry_kernel(const __grid_constant__ RadArgs A, const __grid_constant__ R
         for (int a = 0; a < 3; a++)
           for (int b = 0; b < 3; b++) M.m[a][b] = 0.0;
         M.vv = 0.0;
-        if (have_prev) {
-          double ks[4] = {k_p[0] + kcon[0], k_p[1] + kcon[1], k_p[2] + kcon[2], k_p[3] + kcon[3]};
-          double A_avg[4][4], A_tmp[4][4], A_pp[4][4];
-          contracted_connection(jet_p, ks, A_avg);
-          contracted_connection(jet, ks, A_tmp);
-          for (int a = 0; a < 4; a++)
-            for (int b = 0; b < 4; b++) A_avg[a][b] = 0.25 * (A_avg[a][b] + A_tmp[a][b]);
-          contracted_connection(jet_p, k_p, A_pp);
-          double h = (dlam_p + dlam) / 2.0, h2 = (dlam_p + dlam) / 4.0;
-          LegProj L[2];
-          for (int c = 0; c < 2; c++) {
-            double vp[4], va[4], vap[4];
-            transport_rate(A_pp, e_p[c], vp);
-            transport_rate(A_avg, e_p[c], va);
-            transport_rate(A_avg, vp, vap);
-            L[c].u[0] = dot4(f1, e_p[c]);  L[c].u[1] = dot4(f2, e_p[c]);
-            L[c].up[0] = dot4(f1, vp);     L[c].up[1] = dot4(f2, vp);
-            L[c].ua[0] = dot4(f1, va);     L[c].ua[1] = dot4(f2, va);
-            L[c].uap[0] = dot4(f1, vap);   L[c].uap[1] = dot4(f2, vap);
-          }
-          stokes_map(L, h, h * h2, true, M);
-        }
+        if (have_prev) transport_map(jet_p, k_p, e_p, dlam_p, jet, kcon, f1, f2, dlam, M);
         for (int a = 0; a < 3; a++)
           for (int b = 0; b < 3; b++) __stcs(field_ptr(X, A.rays, kFieldM + 3 * a + b, j, m), M.m[a][b]);
         __stcs(field_ptr(X, A.rays, kFieldM + 9, j, m), M.vv);
@@ -211,18 +194,8 @@ pol_geometry_kernel(const __grid_constant__ RadArgs A, const __grid_constant__ R
       up[3] = vc[3] + uc[3] * vc[0];
       double e1[4], e2[4], f1[4], f2[4];
       tetrad_legs(jc, uc, ul, kcon, kcov, up, e1, e2, f1, f2);
-      double A_pp[4][4];
-      contracted_connection(jet_p, k_p, A_pp);
-      LegProj L[2];
-      for (int c = 0; c < 2; c++) {
-        double vp[4];
-        transport_rate(A_pp, e_p[c], vp);
-        L[c].u[0] = dot4(f1, e_p[c]);  L[c].u[1] = dot4(f2, e_p[c]);
-        L[c].up[0] = dot4(f1, vp);     L[c].up[1] = dot4(f2, vp);
-        L[c].ua[0] = L[c].ua[1] = L[c].uap[0] = L[c].uap[1] = 0.0;
-      }
       StokesMap M;
-      stokes_map(L, 0.0, dlam_p / 2.0, false, M);
+      transport_map_final(jet_p, k_p, e_p, dlam_p, f1, f2, M);
       for (int a = 0; a < 3; a++)
         for (int b = 0; b < 3; b++) X.cam_map[(size_t)(3 * a + b) * A.rays + m] = M.m[a][b];
       X.cam_map[(size_t)9 * A.rays + m] = M.vv;
@@ -235,11 +208,8 @@ pol_geometry_kernel(const __grid_constant__ RadArgs A, const __grid_constant__ R
 }
 
 // ---- stage 2: coefficients ----------------------------------------------------------------------------------
-#ifndef BL_POLC_MINB
-#define BL_POLC_MINB 4
-#endif
-template <int DIST>
-__global__ void __launch_bounds__(kBlock, BL_POLC_MINB)
+template <int DIST, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB)
 pol_coefficient_kernel(const __grid_constant__ RadArgs A, const __grid_constant__ RadParams P, const SplitArgs X) {
   const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int j = blockIdx.y;
@@ -279,13 +249,10 @@ BL_FREQ_LOOP
 }
 
 // ---- stage 3: transfer --------------------------------------------------------------------------------------
-#ifndef BL_POLT_MINB
-#define BL_POLT_MINB 4
-#endif
 // FW: frequencies per CTA (1, 2 or 4); the CTA's 128 threads are 128/FW adjacent rays x FW frequencies, so that a
 // warp is 32 adjacent rays at one frequency and the FW warps of a ray group share M through L1.
-template <int FW>
-__global__ void __launch_bounds__(kBlock, BL_POLT_MINB)
+template <int FW, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB)
 pol_transfer_kernel(const __grid_constant__ RadArgs A, const __grid_constant__ RadParams P, const SplitArgs X) {
   constexpr int kRays = kBlock / FW;
   const int64_t m = (int64_t)blockIdx.x * kRays + (threadIdx.x % kRays);
@@ -347,6 +314,32 @@ pol_transfer_kernel(const __grid_constant__ RadArgs A, const __grid_constant__ R
   if (P.image_emission) img[(size_t)(P.off_emission + l) * stride] = emi;
 }
 
+template <int MINB>
+void launch_coefficients(int dist, dim3 grid, cudaStream_t stream, const RadArgs &A, const RadParams &P, const SplitArgs &X) {
+  if (dist == 1) pol_coefficient_kernel<1, MINB><<<grid, kBlock, 0, stream>>>(A, P, X);
+  else if (dist == 4) pol_coefficient_kernel<4, MINB><<<grid, kBlock, 0, stream>>>(A, P, X);
+  else pol_coefficient_kernel<7, MINB><<<grid, kBlock, 0, stream>>>(A, P, X);
+}
+
+template <int MINB>
+void launch_transfer(int fw, dim3 grid, cudaStream_t stream, const RadArgs &A, const RadParams &P, const SplitArgs &X) {
+  if (fw == 4) pol_transfer_kernel<4, MINB><<<grid, kBlock, 0, stream>>>(A, P, X);
+  else if (fw == 2) pol_transfer_kernel<2, MINB><<<grid, kBlock, 0, stream>>>(A, P, X);
+  else pol_transfer_kernel<1, MINB><<<grid, kBlock, 0, stream>>>(A, P, X);
+}
+
+// Resident CTAs per SM each stage is register-capped for.  The defaults are the measured best on B200; the
+// environment variables exist for re-tuning (BL_POL_OCC="g,c,t").
+struct Occupancy { int g, c, t; };
+Occupancy stage_occupancy() {
+  static Occupancy occ = [] {
+    Occupancy o = {3, 4, 5};
+    if (const char *e = getenv("BL_POL_OCC")) sscanf(e, "%d,%d,%d", &o.g, &o.c, &o.t);
+    return o;
+  }();
+  return occ;
+}
+
 }  // namespace
 
 extern "C" int bl_polarized_split_fields(int num_freq) { return kFieldCoef + 8 * num_freq; }
@@ -367,6 +360,8 @@ extern "C" cudaError_t bl_launch_radiate_polarized_split(const RadArgs *args, co
   if ((size_t)A.grid.n_b * 6 * sizeof(double) <= 48 * 1024) smem = (size_t)A.grid.n_b * 6 * sizeof(double);
   const bool thermal_only = P.thermal_frac != 0.0 && P.power_frac == 0.0 && P.kappa_frac == 0.0;
   const bool kappa_only = P.kappa_frac != 0.0 && P.power_frac == 0.0 && P.thermal_frac == 0.0;
+  const int dist = thermal_only ? 1 : (kappa_only ? 4 : 7);
+  const Occupancy occ = stage_occupancy();
   const int F = P.num_freq;
   const int fw = F >= 4 ? 4 : (F >= 2 ? 2 : 1);
   const unsigned ray_blocks = (unsigned)((A.rays + kBlock - 1) / kBlock);
@@ -376,17 +371,21 @@ extern "C" cudaError_t bl_launch_radiate_polarized_split(const RadArgs *args, co
     SplitArgs X;
     X.scratch = scratch; X.cam_map = cam_map; X.slab = slab;
     X.n_lo = n_hi - slab; X.n_hi = n_hi < s_top ? n_hi : s_top;
-    pol_geometry_kernel<<<ray_blocks, kBlock, smem, stream>>>(A, P, X);
+    if (occ.g == 3) pol_geometry_kernel<3><<<ray_blocks, kBlock, smem, stream>>>(A, P, X);
+    else if (occ.g == 4) pol_geometry_kernel<4><<<ray_blocks, kBlock, smem, stream>>>(A, P, X);
+    else pol_geometry_kernel<2><<<ray_blocks, kBlock, smem, stream>>>(A, P, X);
     if (events) cudaEventRecord(events[ev++], stream);
     dim3 cgrid(ray_blocks, (unsigned)(X.n_hi - X.n_lo));
-    if (thermal_only) pol_coefficient_kernel<1><<<cgrid, kBlock, 0, stream>>>(A, P, X);
-    else if (kappa_only) pol_coefficient_kernel<4><<<cgrid, kBlock, 0, stream>>>(A, P, X);
-    else pol_coefficient_kernel<7><<<cgrid, kBlock, 0, stream>>>(A, P, X);
+    if (occ.c == 3) launch_coefficients<3>(dist, cgrid, stream, A, P, X);
+    else if (occ.c == 5) launch_coefficients<5>(dist, cgrid, stream, A, P, X);
+    else if (occ.c == 6) launch_coefficients<6>(dist, cgrid, stream, A, P, X);
+    else launch_coefficients<4>(dist, cgrid, stream, A, P, X);
     if (events) cudaEventRecord(events[ev++], stream);
     dim3 tgrid((unsigned)((A.rays + kBlock / fw - 1) / (kBlock / fw)), (unsigned)((F + fw - 1) / fw));
-    if (fw == 4) pol_transfer_kernel<4><<<tgrid, kBlock, 0, stream>>>(A, P, X);
-    else if (fw == 2) pol_transfer_kernel<2><<<tgrid, kBlock, 0, stream>>>(A, P, X);
-    else pol_transfer_kernel<1><<<tgrid, kBlock, 0, stream>>>(A, P, X);
+    if (occ.t == 3) launch_transfer<3>(fw, tgrid, stream, A, P, X);
+    else if (occ.t == 5) launch_transfer<5>(fw, tgrid, stream, A, P, X);
+    else if (occ.t == 6) launch_transfer<6>(fw, tgrid, stream, A, P, X);
+    else launch_transfer<4>(fw, tgrid, stream, A, P, X);
     if (events) cudaEventRecord(events[ev++], stream);
     if (launches) *launches += 3;
     cudaError_t e = cudaGetLastError();

@@ -222,6 +222,12 @@ int bl_retrace_level(bl_ctx *ctx, int level, bl_level_stats *stats);
 /* Number of CUDA kernels of this library launched by the context so far (bench accounting). */
 long long bl_launch_count(const bl_ctx *ctx);
 
+/* The level's image where bl_radiate_level leaves it in HBM, (image_num_quantities, num_rays) f64 -- for a host that
+ * gathers the images of several GPUs device to device (peer copies, NCCL) instead of bouncing them through host memory.
+ * Valid until the level is traced again with a different ray count or the context is destroyed; complete when
+ * bl_radiate_level has returned. */
+int bl_device_image(bl_ctx *ctx, int level, void **image, int64_t *num_rays);
+
 /* Polarized levels without per-sample side outputs are rendered by a three-stage pipeline over slabs of the step
  * buffer (geometry + Stokes transport matrix | synchrotron coefficients | Stokes coupling; csrc/radiate_pol_split.cu)
  * in place of the single fused kernel.  ms3: device time of the three stages during the last bl_radiate_level of the

@@ -13,47 +13,14 @@ sys.path.insert(0, os.path.join(ROOT, 'oracle'))
 import blacklight_b200 as bl  # noqa: E402
 from blacklight_b200 import mock_snapshot  # noqa: E402
 
-INPUTS = os.path.join(ROOT, 'tests', 'inputs')
+from blacklight_b200 import cases  # noqa: E402
+from blacklight_b200.cases import load_input, parse_timers, write_input  # noqa: E402,F401
+
 REF_BIN = os.path.join(ROOT, 'oracle', '_ref', 'blacklight')
 
 
-def load_input(name):
-    with open(os.path.join(INPUTS, name)) as f:
-        return bl.parse_input_text(f.read())
-
-
-def write_input(path, kv):
-    with open(path, 'w') as f:
-        for k, v in kv.items():
-            f.write('%s = %s\n' % (k, v))
-
-
-class Case:
-    """One configuration in its own directory: <dir>/case.input, <dir>/data/mock.athdf, <dir>/out_*/"""
-
-    def __init__(self, workdir, base, overrides=None, mock=None, threads=None):
-        self.dir = str(workdir)
-        os.makedirs(os.path.join(self.dir, 'data'), exist_ok=True)
-        self.kv = load_input(base)
-        self.kv.update({k: str(v) for k, v in (overrides or {}).items()})
-        self.kv['num_threads'] = str(threads or os.cpu_count() or 1)
-        self.grid = None
-        self.sim = self.kv['model_type'] == 'simulation'
-        if self.sim:
-            mock = dict(mock or {})
-            blocks = tuple(mock.pop('blocks', (1, 1, 1)))
-            self.kv['simulation_file'] = os.path.join(self.dir, 'data', 'mock.athdf')
-            self.grid = mock_snapshot.make_mock(self.kv['simulation_file'], blocks, **mock)
-
-    def _input(self, tag, extra):
-        kv = dict(self.kv)
-        out = os.path.join(self.dir, 'out_' + tag)
-        os.makedirs(out, exist_ok=True)
-        kv['output_file'] = os.path.join(out, 'image.npz')
-        kv.update(extra)
-        path = os.path.join(self.dir, tag + '.input')
-        write_input(path, kv)
-        return path, out
+class Case(cases.Case):
+    """The benchmark's workload case plus the checker: a run of the unmodified reference on the same inputs."""
 
     def run_reference(self, checkpoints=True):
         """Run the unmodified reference; returns dict(npz=..., geo=..., samp=..., timers=...)."""
@@ -77,31 +44,6 @@ class Case:
                 res['samp'] = refio.read_sample_checkpoint(extra['checkpoint_sample_file'],
                                                            interp=self.kv['simulation_interp'] == 'true')
         return res
-
-    def config(self, device=0, tile_rays=0, extra=None):
-        path, _ = self._input('gpu', extra or {})
-        return bl.Config(path, device=device, tile_rays=tile_rays)
-
-    def run_gpu_file(self, device=0, extra=None, tag='gpufile'):
-        """Full drop-in run through blh_run_input_file; returns (npz dict, timings)."""
-        path, out = self._input(tag, extra or {})
-        t = bl.run_input_file(path, device=device)
-        return dict(np.load(os.path.join(out, 'image.npz'))), t
-
-    def grid_arrays(self):
-        return mock_snapshot.grid_view_arrays(self.grid)
-
-
-def parse_timers(stdout):
-    t = {}
-    for line in stdout.splitlines():
-        if ':' in line and line.strip().endswith(' s'):
-            k, v = line.rsplit(':', 1)
-            try:
-                t[k.strip()] = float(v.strip()[:-2])
-            except ValueError:
-                pass
-    return t
 
 
 def rel_err(a, b, floor_frac=1e-12):

@@ -352,6 +352,66 @@ def test_time_series_reread_equals_fresh_read(fmt, tmp_path):
         assert np.array_equal(again[k], fresh[k]), k
 
 
+def test_open_snapshots_do_not_share_reader_state(tmp_path):
+    """Two snapshot handles open at the same time, and a reread issued from another thread: what the first file of a
+    series fixed (AthenaK variable positions and record size, harm3d / iharm3d coordinate parameters and modified x2
+    centres) belongs to the handle, so interleaved reads of other files cannot change what a reread returns."""
+    import ctypes
+    import threading
+    from blacklight_b200 import mock_snapshot as ms
+    lib = bl.load_library()
+    d = str(tmp_path)
+    series = {}
+    for fmt in ('athenak', 'iharm3d', 'harm3d'):
+        files = []
+        for n, amp in enumerate((0.1, 0.3)):
+            f = os.path.join(d, '%s.%d' % (fmt, n))
+            if fmt == 'athenak':
+                grid = ms.to_blocks(ms.mock_fields_cks(n=8), (2, 1, 1))
+                grid['prim'] = grid['prim'] * np.float32(1.0 + amp)
+                ms.write_athenak(f, grid, gamma_adi=1.5, time=5.0 * n, spin=0.5)
+                kv = {'simulation_coord': 'cks', 'simulation_a': '0.5'}
+            elif fmt == 'iharm3d':
+                ms.write_iharm3d(f, n_r=16, n_th=8, n_ph=8, gamma_adi=1.5, time=5.0 * n, hslope=0.7, pert_amp=amp, pert_n_ph=1)
+                kv = {'simulation_coord': 'sks'}
+            else:
+                ms.write_harm3d(f, ms.mock_fields(n_r=12, n_th=6, n_ph=4, pert_amp=amp, pert_n_ph=1), gamma_adi=1.5, time=5.0 * n)
+                kv = {'simulation_coord': 'sks'}
+            files.append(f)
+        sub = tmp_path / fmt
+        sub.mkdir()
+        series[fmt] = (_reader_case(sub, fmt, files[0], kv), files)
+
+    def prim_of(handle):
+        v, t, g = bl.GridView(), ctypes.c_double(), ctypes.c_double()
+        lib.blh_snapshot_view(handle, ctypes.byref(v), ctypes.byref(t), ctypes.byref(g))
+        n = v.n_var * v.n_b * v.n_k * v.n_j * v.n_i
+        return np.frombuffer((ctypes.c_char * (4 * n)).from_address(v.prim), dtype=np.float32).copy(), t.value
+
+    handles = {}
+    for fmt, (cfg, files) in series.items():      # all three first files open at once
+        h = ctypes.c_void_p()
+        assert lib.blh_snapshot_read(cfg._h, os.fsencode(files[0]), ctypes.byref(h)) == 0, lib.blh_last_error()
+        handles[fmt] = h
+    results = {}
+
+    def reread(fmt):                               # on a fresh thread, after the other formats were read on the main one
+        rc = lib.blh_snapshot_reread(handles[fmt], os.fsencode(series[fmt][1][1]))
+        results[fmt] = (rc,) + (prim_of(handles[fmt]) if rc == 0 else (None, None))
+
+    for fmt in ('athenak', 'harm3d', 'iharm3d'):
+        t = threading.Thread(target=reread, args=(fmt,))
+        t.start()
+        t.join()
+    for fmt, (cfg, files) in series.items():
+        rc, prim, time = results[fmt]
+        assert rc == 0, fmt
+        fresh = bl.read_snapshot(cfg, files[1])
+        assert time == fresh['time'] == 5.0
+        assert np.array_equal(prim, fresh['prim'].ravel()), fmt
+        lib.blh_snapshot_free(handles[fmt])
+
+
 def test_npz_writer_and_athdf_reader_through_driver_without_gpu(tmp_path):
     """blh_run_input_file must fail loudly without a GPU, after parsing the file."""
     import torch
