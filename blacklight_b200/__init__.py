@@ -82,6 +82,9 @@ def load_library():
         'blh_camera_root': (i64, [vp, vp, vp, vp]),
         'blh_camera_refined': (i64, [vp, i32, vp, vp, i64, vp, vp, vp, vp]),
         'blh_run_input_file': (i32, [ctypes.c_char_p, i32, i32, vp]),
+        'blh_camera_rows': (i64, [vp, vp, i64, vp, vp, vp]),
+        'blh_run_input_file_devices': (i32, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_int), i32, i32, vp]),
+        'bl_device_count': (i32, []),
         'blh_camera_blocks': (i64, [vp, i32, vp, i64, vp, vp, vp]),
         'blh_snapshot_read': (i32, [vp, ctypes.c_char_p, ctypes.POINTER(vp)]),
         'blh_snapshot_view': (i32, [vp, ctypes.POINTER(GridView), ctypes.POINTER(dbl), ctypes.POINTER(dbl)]),
@@ -167,6 +170,15 @@ class Config:
             raise BlacklightError(_lib.blh_last_error().decode())
         return locs, pos, dirs, fac
 
+
+    def camera_rows(self, rows, pinned=False):
+        """Camera arrays of the given level-0 image rows only: blh_camera_rows."""
+        rows = np.ascontiguousarray(rows, np.int64)
+        n = len(rows) * self.resolution
+        pos, dirs, fac = _host_array((n, 4), pinned), _host_array((n, 4), pinned), _host_array((n,), pinned)
+        if _lib.blh_camera_rows(self._h, _ptr(rows), len(rows), _ptr(pos), _ptr(dirs), _ptr(fac)) != n:
+            raise BlacklightError(_lib.blh_last_error().decode())
+        return pos, dirs, fac
 
     def camera_blocks(self, level, locs):
         """Camera arrays of the given blocks of a level only ((n,2) block locations): blh_camera_blocks."""
@@ -376,12 +388,18 @@ def read_snapshot(config, path=None, then=None):
         lib.blh_snapshot_free(h)
 
 
-def run_input_file(path, device=-1, quiet=True):
-    """Full drop-in run (read input, trace, radiate, write output): blh_run_input_file."""
+def run_input_file(path, device=-1, quiet=True, devices=None):
+    """Full drop-in run (read input, trace, radiate, write output): blh_run_input_file, or on a list of CUDA devices
+    blh_run_input_file_devices (one context per device inside this process)."""
     lib = load_library()
     t = np.zeros(12)
-    if lib.blh_run_input_file(os.fsencode(path), device, 1 if quiet else 0, _ptr(t)) != 0:
+    if devices is not None:
+        arr = (ctypes.c_int * len(devices))(*devices)
+        rc = lib.blh_run_input_file_devices(os.fsencode(path), arr, len(devices), 1 if quiet else 0, _ptr(t))
+    else:
+        rc = lib.blh_run_input_file(os.fsencode(path), device, 1 if quiet else 0, _ptr(t))
+    if rc != 0:
         raise BlacklightError(lib.blh_last_error().decode())
     names = ('total_s', 'geodesic_s', 'read_s', 'sample_s', 'image_s', 'render_s', 'gpu_geodesic_ms',
-             'gpu_radiation_ms', 'gpu_refine_ms', 'rays', 'samples')
+             'gpu_radiation_ms', 'gpu_refine_ms', 'rays', 'samples', 'devices')
     return dict(zip(names, t))

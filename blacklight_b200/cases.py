@@ -59,10 +59,11 @@ class Case:
         path, _ = self._input('gpu', extra or {})
         return Config(path, device=device, tile_rays=tile_rays)
 
-    def run_gpu_file(self, device=0, extra=None, tag='gpufile'):
-        """Full drop-in run through blh_run_input_file; returns (npz dict, timings)."""
+    def run_gpu_file(self, device=0, extra=None, tag='gpufile', devices=None):
+        """Full drop-in run through blh_run_input_file (devices: a list of CUDA ordinals -> blh_run_input_file_devices);
+        returns (npz dict, timings)."""
         path, out = self._input(tag, extra or {})
-        t = run_input_file(path, device=device)
+        t = run_input_file(path, device=device, devices=devices)
         return dict(np.load(os.path.join(out, 'image.npz'))), t
 
     def grid_arrays(self):

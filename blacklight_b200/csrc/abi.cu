@@ -434,6 +434,11 @@ void bl_destroy(bl_ctx *ctx) {
   delete ctx;
 }
 
+int bl_device_count(void) {
+  int count = 0;
+  return cudaGetDeviceCount(&count) == cudaSuccess ? count : 0;
+}
+
 int bl_image_num_quantities(const bl_ctx *ctx) { return ctx ? ctx->rad.num_quantities : -1; }
 
 int bl_set_taps(bl_ctx *ctx, int enabled) {

@@ -321,6 +321,36 @@ void camera_root(const CameraSetup &s, const CameraFrame &f, std::vector<double>
   }
 }
 
+void camera_rows(const CameraSetup &s, const CameraFrame &f, const long long *rows, long long num_rows, double *pos, double *dir,
+                 double *factor) {
+  const int res = s.resolution;
+#pragma omp parallel for schedule(static)
+  for (long long r = 0; r < num_rows; r++) {
+    const double v_ind = ((int)rows[r] - res / 2.0 + 0.5) / res;
+    for (int col = 0; col < res; col++) {
+      const double u_ind = (col - res / 2.0 + 0.5) / res;
+      const size_t o = (size_t)r * res + col;
+      camera_pixel(s, f, u_ind, v_ind, &pos[4 * o], &dir[4 * o], &factor[o]);
+    }
+  }
+}
+
+void child_blocks(const std::vector<int32_t> &parent_locs, const std::vector<uint8_t> &flags, std::vector<int32_t> &child_locs) {
+  size_t refined = 0;
+  for (uint8_t fl : flags) refined += fl ? 1 : 0;
+  child_locs.resize(refined * 4 * 2);
+  size_t block = 0;
+  for (size_t parent = 0; parent < flags.size(); parent++) {
+    if (!flags[parent]) continue;
+    int pv = parent_locs[2 * parent], pu = parent_locs[2 * parent + 1];
+    for (int bv = 2 * pv; bv <= 2 * pv + 1; bv++)
+      for (int bu = 2 * pu; bu <= 2 * pu + 1; bu++, block++) {
+        child_locs[2 * block] = bv;
+        child_locs[2 * block + 1] = bu;
+      }
+  }
+}
+
 void camera_blocks(const CameraSetup &s, const CameraFrame &f, int level, int block_size, const int32_t *locs, long long blocks,
                    double *pos, double *dir, double *factor) {
   int eff_res = s.resolution;
@@ -345,24 +375,13 @@ void camera_refined(const CameraSetup &s, const CameraFrame &f, int level, int b
                     std::vector<double> &factor) {
   int eff_res = s.resolution;
   for (int n = 1; n <= level; n++) eff_res *= 2;
-  size_t refined = 0;
-  for (uint8_t fl : flags) refined += fl ? 1 : 0;
-  const size_t bpix = (size_t)block_size * block_size;
-  child_locs.resize(refined * 4 * 2);
-  pos.resize(refined * 4 * bpix * 4);
-  dir.resize(refined * 4 * bpix * 4);
-  factor.resize(refined * 4 * bpix);
   // child list: parents in index order x 4 children (camera.cpp:445-459); then every pixel is independent
-  size_t block = 0;
-  for (size_t parent = 0; parent < flags.size(); parent++) {
-    if (!flags[parent]) continue;
-    int pv = parent_locs[2 * parent], pu = parent_locs[2 * parent + 1];
-    for (int bv = 2 * pv; bv <= 2 * pv + 1; bv++)
-      for (int bu = 2 * pu; bu <= 2 * pu + 1; bu++, block++) {
-        child_locs[2 * block] = bv;
-        child_locs[2 * block + 1] = bu;
-      }
-  }
+  child_blocks(parent_locs, flags, child_locs);
+  const size_t block = child_locs.size() / 2;
+  const size_t bpix = (size_t)block_size * block_size;
+  pos.resize(block * bpix * 4);
+  dir.resize(block * bpix * 4);
+  factor.resize(block * bpix);
   camera_blocks(s, f, level, block_size, child_locs.data(), (long long)block, pos.data(), dir.data(), factor.data());
 }
 

@@ -51,6 +51,14 @@ void camera_refined(const CameraSetup &s, const CameraFrame &f, int level, int b
 void camera_blocks(const CameraSetup &s, const CameraFrame &f, int level, int block_size, const int32_t *locs, long long blocks,
                    double *pos, double *dir, double *factor);
 
+// Level-0 pixels of the listed image rows only (pixel order within a row as camera_root): what a device that owns a share
+// of the frame's rows builds.  pos, dir: (num_rows * res, 4); factor: (num_rows * res).
+void camera_rows(const CameraSetup &s, const CameraFrame &f, const long long *rows, long long num_rows, double *pos, double *dir,
+                 double *factor);
+
+// Child blocks of the flagged parents: parents in index order x 4 children (2v..2v+1) x (2u..2u+1) (camera.cpp:445-459).
+void child_blocks(const std::vector<int32_t> &parent_locs, const std::vector<uint8_t> &flags, std::vector<int32_t> &child_locs);
+
 // Image frequencies (camera.cpp:30-50). spacing: 0 lin_freq, 1 lin_wave, 2 log
 std::vector<double> image_frequencies(int num, double single, double start, double end, int spacing);
 

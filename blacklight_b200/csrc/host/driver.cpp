@@ -1,5 +1,8 @@
 #include "driver.hpp"
 
+#include <omp.h>
+
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -7,6 +10,7 @@
 #include <fstream>
 #include <memory>
 #include <sstream>
+#include <thread>
 #include <vector>
 
 #include "athdf.hpp"
@@ -270,9 +274,99 @@ void load_geodesic_checkpoint(bl_ctx *ctx, const RunConfig &cfg, LevelData &root
                                pos.data(), dir.data(), len.data(), st));
 }
 
+// ---- one bl_ctx per GPU --------------------------------------------------------------------------------------------
+// The reference parallelises inside main with OpenMP threads over pixels (blacklight.cpp:77,94,204,221); here the same
+// main drives one context per device from one host thread each.  Rays never interact, so a level is split into units
+// -- image rows of a plain frame, refinement blocks of an adaptive one (the root level included: level0_block_major)
+// -- dealt round-robin over the devices (ray cost varies strongly across the image); the grid is replicated.  What is
+// exchanged: per level the refinement flags (every device flags its own blocks, the host merges them into the one
+// vector the child list is derived from, camera.cpp:445-459) and, per level and snapshot, each device's image part,
+// which its bl_radiate_level copies device-to-host straight into its slice of a host buffer and the device's thread
+// then scatters into the frame in the reference's pixel order.  Results are bitwise independent of the device count.
+struct Worker {
+  int device = 0;
+  bl_ctx *ctx = nullptr;
+  std::vector<double> pos, dir, factor;   // camera arrays of the level being traced
+  std::vector<double> image, render;      // this device's part of the level being radiated
+  std::vector<int32_t> locs;              // this device's blocks of that level
+  std::vector<uint8_t> flags;
+  std::vector<std::vector<long long>> units;   // per level: ids of the rows / blocks this device owns
+  bl_level_stats st{};
+  double ms_geodesic = 0.0, ms_radiation = 0.0, ms_refine = 0.0;
+  long long samples = 0;
+};
+
+struct Workers {
+  std::vector<Worker> w;
+  ~Workers() {
+    for (Worker &x : w) bl_destroy(x.ctx);
+  }
+  // fn(worker) on one host thread per device; the first exception is rethrown on the caller
+  template <typename F>
+  void each(int host_threads, F fn) {
+    if (w.size() == 1) {
+      fn(w[0]);
+      return;
+    }
+    std::vector<std::exception_ptr> err(w.size());
+    std::vector<std::thread> threads;
+    const int per = std::max(1, host_threads / (int)w.size());
+    for (size_t i = 0; i < w.size(); i++)
+      threads.emplace_back([&, i] {
+        try {
+          omp_set_num_threads(per);   // the camera loops inside run on this thread's own OpenMP team
+          fn(w[i]);
+        } catch (...) {
+          err[i] = std::current_exception();
+        }
+      });
+    for (std::thread &t : threads) t.join();
+    for (std::exception_ptr &e : err)
+      if (e) std::rethrow_exception(e);
+  }
+};
+
+// BLACKLIGHT_DEVICES = "all" | "0-7" | "0,2,3" (a list of CUDA ordinals); unset: the single device BLACKLIGHT_DEVICE or 0
+std::vector<int> devices_from_environment(int device) {
+  std::vector<int> out;
+  if (device >= 0) return {device};
+  const char *list = std::getenv("BLACKLIGHT_DEVICES");
+  if (list && *list) {
+    std::string s(list);
+    if (s == "all") {
+      int n = bl_device_count();
+      for (int d = 0; d < n; d++) out.push_back(d);
+    } else {
+      std::stringstream ss(s);
+      std::string item;
+      while (std::getline(ss, item, ',')) {
+        size_t dash = item.find('-');
+        try {
+          if (dash == std::string::npos) {
+            out.push_back(std::stoi(item));
+          } else {
+            int lo = std::stoi(item.substr(0, dash)), hi = std::stoi(item.substr(dash + 1));
+            for (int d = lo; d <= hi; d++) out.push_back(d);
+          }
+        } catch (const std::exception &) {
+          throw Error("Could not parse BLACKLIGHT_DEVICES.");
+        }
+      }
+    }
+    if (out.empty()) throw Error("BLACKLIGHT_DEVICES names no device.");
+    return out;
+  }
+  const char *env = std::getenv("BLACKLIGHT_DEVICE");
+  return {env ? std::atoi(env) : 0};
+}
+
 }  // namespace
 
 RunTimings run_input_file(const std::string &path, int device, bool quiet) {
+  return run_input_file(path, devices_from_environment(device), quiet);
+}
+
+RunTimings run_input_file(const std::string &path, const std::vector<int> &devices_in, bool quiet) {
   RunTimings T;
   double t_begin = now_s();
   InputFile in(path);
@@ -289,27 +383,78 @@ RunTimings run_input_file(const std::string &path, int device, bool quiet) {
   }
   auto read_snapshot = [&](const std::string &file, bool reuse, AthenaGrid &into) { reader->read(file, reuse, into); };
   auto snapshot_time_of = [&](const std::string &file) { return reader->time_of(file); };
-  if (device < 0) {
-    const char *env = std::getenv("BLACKLIGHT_DEVICE");
-    device = env ? std::atoi(env) : 0;
+  std::vector<int> devices = devices_in;
+  if (devices.empty()) throw Error("No device given.");
+  // checkpoints hold whole levels in the reference's layouts: they go through a single device
+  if (devices.size() > 1 && (cfg.checkpoint_geodesic_save || cfg.checkpoint_geodesic_load || cfg.checkpoint_sample_save)) {
+    warning("Checkpoints are exchanged through a single device; ignoring all but the first of BLACKLIGHT_DEVICES.");
+    devices.resize(1);
   }
-  p.device = device;
+  const int N = (int)devices.size();
+  const int host_threads = cfg.num_threads > 0 ? cfg.num_threads : omp_get_max_threads();
+  const bool adaptive = p.adaptive_max_level > 0;
+  const int bs = p.adaptive_block_size, res = p.camera_resolution;
+  if (N > 1 && adaptive) p.level0_block_major = 1;   // root blocks are handed over block by block, like refined ones
 
-  CtxGuard guard;
-  if (bl_create(&p, &guard.ctx) != BL_OK) throw Error(bl_last_error(nullptr));
-  bl_ctx *ctx = guard.ctx;
-  const int Q = bl_image_num_quantities(ctx);
+  Workers W;
+  W.w.resize((size_t)N);
+  for (int i = 0; i < N; i++) {
+    W.w[(size_t)i].device = devices[(size_t)i];
+    W.w[(size_t)i].units.resize((size_t)p.adaptive_max_level + 1);
+  }
+  W.each(host_threads, [&](Worker &w) {
+    bl_params q = p;
+    q.device = w.device;
+    if (bl_create(&q, &w.ctx) != BL_OK) throw Error(bl_last_error(nullptr));
+  });
+  bl_ctx *ctx0 = W.w[0].ctx;
+  const int Q = bl_image_num_quantities(ctx0);
   const int R = sim ? p.render_num_images : 0;
-  const int bs = p.adaptive_block_size;
   std::vector<LevelData> levels((size_t)p.adaptive_max_level + 1);
+  const bool block_units = N > 1 && adaptive;                  // units of level 0: blocks, else rows
+  const long long bs2 = (long long)bs * bs;
+  auto unit_rays = [&](int level) { return level == 0 && !block_units ? (long long)res : bs2; };
+
+  // units of a level with `count` of them, dealt round-robin
+  auto deal = [&](int level, long long count) {
+    for (int i = 0; i < N; i++) {
+      std::vector<long long> &u = W.w[(size_t)i].units[(size_t)level];
+      u.clear();
+      for (long long k = i; k < count; k += N) u.push_back(k);
+    }
+  };
+  // trace this device's share of a level whose camera arrays it builds itself
+  auto trace_share = [&](Worker &w, int level, const LevelData &L) {
+    const std::vector<long long> &u = w.units[(size_t)level];
+    const long long rays = (long long)u.size() * unit_rays(level);
+    w.pos.resize((size_t)rays * 4);
+    w.dir.resize((size_t)rays * 4);
+    w.factor.resize((size_t)rays);
+    if (level == 0 && !block_units) {
+      camera_rows(cfg.camera, cfg.frame, u.data(), (long long)u.size(), w.pos.data(), w.dir.data(), w.factor.data());
+    } else {
+      w.locs.resize(u.size() * 2);
+      for (size_t k = 0; k < u.size(); k++) {
+        w.locs[2 * k] = L.locs[2 * (size_t)u[k]];
+        w.locs[2 * k + 1] = L.locs[2 * (size_t)u[k] + 1];
+      }
+      camera_blocks(cfg.camera, cfg.frame, level, bs, w.locs.data(), (long long)u.size(), w.pos.data(), w.dir.data(), w.factor.data());
+    }
+    check(w.ctx, bl_trace_level(w.ctx, level, w.pos.data(), w.dir.data(), w.factor.data(), rays, &w.st));
+    w.ms_geodesic += w.st.ms_geodesic;
+  };
+  auto bad_geodesics_warning = [&](long long rays) {
+    long long bad = 0;
+    for (Worker &w : W.w) bad += w.st.num_bad_geodesics;
+    if (bad > 0) warning(std::to_string(bad) + " out of " + std::to_string(rays) + " geodesics terminate unexpectedly.");
+  };
 
   // level 0 camera + geodesics (GeodesicIntegrator::Integrate)
   double t0 = now_s();
   LevelData &root = levels[0];
-  if (!cfg.checkpoint_geodesic_load) camera_root(cfg.camera, cfg.frame, root.pos, root.dir, root.factor);
-  root.rays = (long long)p.camera_resolution * p.camera_resolution;
-  if (p.adaptive_max_level > 0) {
-    int nb = p.camera_resolution / bs;
+  root.rays = (long long)res * res;
+  if (adaptive) {
+    int nb = res / bs;
     root.blocks = nb * nb;
     root.locs.resize((size_t)root.blocks * 2);
     for (int v = 0, b = 0; v < nb; v++)
@@ -319,15 +464,25 @@ RunTimings run_input_file(const std::string &path, int device, bool quiet) {
       }
   }
   bl_level_stats st{};
-  if (cfg.checkpoint_geodesic_load)
-    load_geodesic_checkpoint(ctx, cfg, root, &st);
-  else
-    check(ctx, bl_trace_level(ctx, 0, root.pos.data(), root.dir.data(), root.factor.data(), root.rays, &st));
-  T.gpu_geodesic_ms += st.ms_geodesic;
-  if (st.num_bad_geodesics > 0)
-    warning(std::to_string(st.num_bad_geodesics) + " out of " + std::to_string(root.rays) + " geodesics terminate unexpectedly.");
-  if (cfg.checkpoint_geodesic_save) save_geodesic_checkpoint(ctx, cfg, root, st.geodesic_num_steps);
-  const int level0_steps = st.geodesic_num_steps;
+  int level0_steps = 0;
+  if (N == 1) {
+    // single device: the whole raster, exactly as the reference's main
+    if (!cfg.checkpoint_geodesic_load) camera_root(cfg.camera, cfg.frame, root.pos, root.dir, root.factor);
+    if (cfg.checkpoint_geodesic_load)
+      load_geodesic_checkpoint(ctx0, cfg, root, &st);
+    else
+      check(ctx0, bl_trace_level(ctx0, 0, root.pos.data(), root.dir.data(), root.factor.data(), root.rays, &st));
+    W.w[0].st = st;
+    W.w[0].ms_geodesic += st.ms_geodesic;
+    bad_geodesics_warning(root.rays);
+    if (cfg.checkpoint_geodesic_save) save_geodesic_checkpoint(ctx0, cfg, root, st.geodesic_num_steps);
+    level0_steps = st.geodesic_num_steps;
+  } else {
+    deal(0, block_units ? root.blocks : res);
+    W.each(host_threads, [&](Worker &w) { trace_share(w, 0, root); });
+    bad_geodesics_warning(root.rays);
+    if (cfg.output_camera) camera_root(cfg.camera, cfg.frame, root.pos, root.dir, root.factor);
+  }
   T.geodesic += now_s() - t0;
 
   AthenaGrid grid;
@@ -388,9 +543,11 @@ RunTimings run_input_file(const std::string &path, int device, bool quiet) {
         first_read = false;
         window_time[(size_t)t] = grid.time;
         bl_grid_view view = grid.view();
-        check(ctx, bl_upload_grid_slice(ctx, &view, window_slot[(size_t)t]));
+        W.each(host_threads, [&](Worker &w) { check(w.ctx, bl_upload_grid_slice(w.ctx, &view, window_slot[(size_t)t])); });
       }
-      check(ctx, bl_set_time_window(ctx, chunk, window_slot.data(), window_time.data(), snapshot_time));
+      W.each(host_threads, [&](Worker &w) {
+        check(w.ctx, bl_set_time_window(w.ctx, chunk, window_slot.data(), window_time.data(), snapshot_time));
+      });
       T.read += now_s() - t0;
     } else if (sim) {
       t0 = now_s();
@@ -398,7 +555,7 @@ RunTimings run_input_file(const std::string &path, int device, bool quiet) {
       if (cfg.simulation_multiple) file = format_numbered(cfg.simulation_file, cfg.simulation_start + n, "simulation_file");
       read_snapshot(file, n > 0, grid);
       bl_grid_view view = grid.view();
-      check(ctx, bl_upload_grid(ctx, &view));
+      W.each(host_threads, [&](Worker &w) { check(w.ctx, bl_upload_grid(w.ctx, &view)); });   // replicated on every device
       T.read += now_s() - t0;
     }
     int level = 0, num_levels = 0;
@@ -408,17 +565,79 @@ RunTimings run_input_file(const std::string &path, int device, bool quiet) {
       L.image.resize((size_t)Q * L.rays);
       if (R > 0) L.render.resize((size_t)R * 3 * L.rays);
       const bool save_sampling = sim && cfg.checkpoint_sample_save && n == 0 && level == 0;
-      if (save_sampling) check(ctx, bl_set_taps(ctx, 1));
-      check(ctx, bl_radiate_level(ctx, level, n, L.image.data(), R > 0 ? L.render.data() : nullptr, &st));
-      T.gpu_radiation_ms += st.ms_radiation;
-      if (save_sampling) {   // as the reference, after the first sampling pass of level 0 (radiation_integrator.cpp:697-704)
-        save_sample_checkpoint(ctx, cfg, L, level0_steps);
-        check(ctx, bl_set_taps(ctx, 0));
+      if (N == 1) {
+        if (save_sampling) check(ctx0, bl_set_taps(ctx0, 1));
+        check(ctx0, bl_radiate_level(ctx0, level, n, L.image.data(), R > 0 ? L.render.data() : nullptr, &st));
+        W.w[0].st = st;
+        W.w[0].ms_radiation += st.ms_radiation;
+        if (level == 0 && n == 0 && st.ms_geodesic > 0 && W.w[0].ms_geodesic == 0) W.w[0].ms_geodesic += st.ms_geodesic;
+        W.w[0].samples += st.num_samples;
+        if (save_sampling) {   // as the reference, after the first sampling pass of level 0 (radiation_integrator.cpp:697-704)
+          save_sample_checkpoint(ctx0, cfg, L, level0_steps);
+          check(ctx0, bl_set_taps(ctx0, 0));
+        }
+      } else {
+        // every device radiates its units; its thread then scatters them into the frame (disjoint destinations)
+        const long long ur = unit_rays(level);
+        const long long units_total = L.rays / ur;
+        W.each(host_threads, [&](Worker &w) {
+          const std::vector<long long> &u = w.units[(size_t)level];
+          const long long rays = (long long)u.size() * ur;
+          w.image.resize((size_t)Q * rays);
+          if (R > 0) w.render.resize((size_t)R * 3 * rays);
+          const bool first_wave_trace = w.ms_geodesic == 0;
+          check(w.ctx, bl_radiate_level(w.ctx, level, n, w.image.data(), R > 0 ? w.render.data() : nullptr, &w.st));
+          w.ms_radiation += w.st.ms_radiation;
+          if (level == 0 && n == 0 && first_wave_trace && w.st.ms_geodesic > 0) w.ms_geodesic += w.st.ms_geodesic;
+          w.samples += w.st.num_samples;
+          for (int q = 0; q < Q; q++)
+            for (size_t k = 0; k < u.size(); k++)
+              std::memcpy(L.image.data() + ((size_t)q * units_total + (size_t)u[k]) * ur, w.image.data() + ((size_t)q * u.size() + k) * ur,
+                          (size_t)ur * sizeof(double));
+          for (int q = 0; q < 3 * R; q++)
+            for (size_t k = 0; k < u.size(); k++)
+              std::memcpy(L.render.data() + ((size_t)q * units_total + (size_t)u[k]) * ur, w.render.data() + ((size_t)q * u.size() + k) * ur,
+                          (size_t)ur * sizeof(double));
+        });
+        if (level == 0 && block_units) {
+          // the root level was radiated block by block: back to the reference's raster order (m = row * res + col)
+          std::vector<double> raster(L.image.size());
+          const int nb = res / bs;
+#pragma omp parallel for schedule(static) collapse(2)
+          for (int q = 0; q < Q; q++)
+            for (int b = 0; b < nb * nb; b++) {
+              const int v = b / nb, u = b % nb;
+              for (int i = 0; i < bs; i++)
+                std::memcpy(raster.data() + (size_t)q * L.rays + ((size_t)v * bs + i) * res + (size_t)u * bs,
+                            L.image.data() + ((size_t)q * nb * nb + b) * bs2 + (size_t)i * bs, (size_t)bs * sizeof(double));
+            }
+          L.image.swap(raster);
+          if (R > 0) {
+            std::vector<double> rr(L.render.size());
+            for (int q = 0; q < 3 * R; q++)
+              for (int b = 0; b < nb * nb; b++) {
+                const int v = b / nb, u = b % nb;
+                for (int i = 0; i < bs; i++)
+                  std::memcpy(rr.data() + (size_t)q * L.rays + ((size_t)v * bs + i) * res + (size_t)u * bs,
+                              L.render.data() + ((size_t)q * nb * nb + b) * bs2 + (size_t)i * bs, (size_t)bs * sizeof(double));
+              }
+            L.render.swap(rr);
+          }
+        }
       }
       if (sim && p.slow_light_on) {
         // same errors / warnings as the reference's sampling stage (simulation_sampling.cpp:577-617)
         bl_slow_stats ss{};
-        check(ctx, bl_slow_light_stats(ctx, level, &ss));
+        for (Worker &w : W.w) {
+          bl_slow_stats part{};
+          check(w.ctx, bl_slow_light_stats(w.ctx, level, &part));
+          for (int side = 0; side < 2; side++) {
+            ss.num_small[side] += part.num_small[side];
+            ss.num_large[side] += part.num_large[side];
+            ss.val_small[side] = std::max(ss.val_small[side], part.val_small[side]);
+            ss.val_large[side] = std::max(ss.val_large[side], part.val_large[side]);
+          }
+        }
         const double snapshot_time = cfg.slow_t_start + cfg.slow_dt * n;
         const char *direction[2] = {"forward", "backward"};
         for (int side = 0; side < 2; side++)
@@ -438,14 +657,30 @@ RunTimings run_input_file(const std::string &path, int device, bool quiet) {
             warning(msg.str());
           }
       }
-      if (level == 0 && n == 0 && st.ms_geodesic > 0 && T.gpu_geodesic_ms == 0) T.gpu_geodesic_ms += st.ms_geodesic;
       T.rays += L.rays;
-      T.samples += st.num_samples;
       bool complete = true;
-      if (p.adaptive_max_level > 0 && level < p.adaptive_max_level) {
+      if (adaptive && level < p.adaptive_max_level) {
         L.flags.assign((size_t)L.blocks, 0);
         int64_t refined = 0;
-        check(ctx, bl_refine_level(ctx, level, L.locs.data(), L.blocks, L.flags.data(), &refined));
+        if (N == 1) {
+          check(ctx0, bl_refine_level(ctx0, level, L.locs.data(), L.blocks, L.flags.data(), &refined));
+          W.w[0].ms_refine += 0.0;
+        } else {
+          // each device flags its own blocks; the merged vector is what every child list is derived from
+          W.each(host_threads, [&](Worker &w) {
+            const std::vector<long long> &u = w.units[(size_t)level];
+            w.locs.resize(u.size() * 2);
+            for (size_t k = 0; k < u.size(); k++) {
+              w.locs[2 * k] = L.locs[2 * (size_t)u[k]];
+              w.locs[2 * k + 1] = L.locs[2 * (size_t)u[k] + 1];
+            }
+            w.flags.assign(u.size(), 0);
+            int64_t mine = 0;
+            check(w.ctx, bl_refine_level(w.ctx, level, w.locs.data(), (int64_t)u.size(), w.flags.data(), &mine));
+            for (size_t k = 0; k < u.size(); k++) L.flags[(size_t)u[k]] = w.flags[k];
+          });
+          for (uint8_t f : L.flags) refined += f ? 1 : 0;
+        }
         complete = refined == 0;
       }
       T.image += now_s() - t0;
@@ -456,17 +691,38 @@ RunTimings run_input_file(const std::string &path, int device, bool quiet) {
       // next level: augment camera, trace (GeodesicIntegrator::AddGeodesics)
       t0 = now_s();
       LevelData &C = levels[(size_t)level + 1];
-      camera_refined(cfg.camera, cfg.frame, level + 1, bs, L.locs, L.flags, C.locs, C.pos, C.dir, C.factor);
-      C.blocks = (int)(C.locs.size() / 2);
-      C.rays = (long long)C.blocks * bs * bs;
-      check(ctx, bl_trace_level(ctx, level + 1, C.pos.data(), C.dir.data(), C.factor.data(), C.rays, &st));
-      T.gpu_geodesic_ms += st.ms_geodesic;
-      if (st.num_bad_geodesics > 0)
-        warning(std::to_string(st.num_bad_geodesics) + " out of " + std::to_string(C.rays) + " geodesics terminate unexpectedly.");
+      if (N == 1) {
+        camera_refined(cfg.camera, cfg.frame, level + 1, bs, L.locs, L.flags, C.locs, C.pos, C.dir, C.factor);
+        C.blocks = (int)(C.locs.size() / 2);
+        C.rays = (long long)C.blocks * bs * bs;
+        check(ctx0, bl_trace_level(ctx0, level + 1, C.pos.data(), C.dir.data(), C.factor.data(), C.rays, &st));
+        W.w[0].st = st;
+        W.w[0].ms_geodesic += st.ms_geodesic;
+      } else {
+        // child list: parents in index order x 4 children (camera.cpp:445-459); pixels are built per device
+        child_blocks(L.locs, L.flags, C.locs);
+        C.blocks = (int)(C.locs.size() / 2);
+        C.rays = (long long)C.blocks * bs * bs;
+        deal(level + 1, C.blocks);
+        W.each(host_threads, [&](Worker &w) { trace_share(w, level + 1, C); });
+        if (cfg.output_camera) {
+          C.pos.resize((size_t)C.rays * 4);
+          C.dir.resize((size_t)C.rays * 4);
+          C.factor.resize((size_t)C.rays);
+          camera_blocks(cfg.camera, cfg.frame, level + 1, bs, C.locs.data(), C.blocks, C.pos.data(), C.dir.data(), C.factor.data());
+        }
+      }
+      bad_geodesics_warning(C.rays);
       T.geodesic += now_s() - t0;
       level++;
     }
     write_output(cfg, levels, num_levels, n);
+  }
+  for (Worker &w : W.w) {
+    // device times: the slowest device bounds the run
+    T.gpu_geodesic_ms = std::max(T.gpu_geodesic_ms, w.ms_geodesic);
+    T.gpu_radiation_ms = std::max(T.gpu_radiation_ms, w.ms_radiation);
+    T.samples += w.samples;
   }
   T.total = now_s() - t_begin;
   if (!quiet) {
@@ -479,8 +735,8 @@ RunTimings run_input_file(const std::string &path, int device, bool quiet) {
     std::printf("\n  Integrating image:     %.7g s", T.image);
     std::printf("\n  Rendering:             %.7g s", T.render);
     std::printf("\n\n");
-    std::printf("[B200] geodesic kernels %.3f ms, radiation kernels %.3f ms, %lld rays, %lld samples\n",
-                T.gpu_geodesic_ms, T.gpu_radiation_ms, T.rays, T.samples);
+    std::printf("[B200] %d device(s): geodesic kernels %.3f ms, radiation kernels %.3f ms (slowest device), %lld rays, %lld samples\n",
+                N, T.gpu_geodesic_ms, T.gpu_radiation_ms, T.rays, T.samples);
   }
   return T;
 }

@@ -3,6 +3,7 @@
 // the same five-line timing summary.  All heavy work goes through the C ABI.
 #pragma once
 #include <string>
+#include <vector>
 
 namespace blh {
 
@@ -12,7 +13,10 @@ struct RunTimings {
   long long rays = 0, samples = 0;
 };
 
-// Throws blh::Error.  device < 0: use BLACKLIGHT_DEVICE or 0.
+// Throws blh::Error.  device < 0: the devices BLACKLIGHT_DEVICES names ("all", "0-7", "0,2,3"), else BLACKLIGHT_DEVICE, else 0.
 RunTimings run_input_file(const std::string &path, int device, bool quiet);
+// The same on an explicit list of CUDA devices: one context and one host thread per device, image rows (adaptive runs:
+// refinement blocks) dealt round-robin, the grid replicated; outputs are bitwise independent of the list.
+RunTimings run_input_file(const std::string &path, const std::vector<int> &devices, bool quiet);
 
 }  // namespace blh

@@ -102,6 +102,15 @@ int64_t blh_camera_blocks(const blh_config *c, int level, const int32_t *locs, i
   return num_blocks;
 }
 
+int64_t blh_camera_rows(const blh_config *c, const int64_t *rows, int64_t num_rows, double *pos, double *dir, double *factor) {
+  if (!c || !rows || !pos || !dir || !factor || num_rows < 0) { g_error = "bad argument"; return -1; }
+  for (int64_t r = 0; r < num_rows; r++)
+    if (rows[r] < 0 || rows[r] >= c->cfg.camera.resolution) { g_error = "row outside the image"; return -1; }
+  std::vector<long long> list(rows, rows + num_rows);
+  blh::camera_rows(c->cfg.camera, c->cfg.frame, list.data(), (long long)num_rows, pos, dir, factor);
+  return num_rows * c->cfg.camera.resolution;
+}
+
 int blh_snapshot_read(const blh_config *c, const char *file, blh_snapshot **out) {
   if (!c || !out) { g_error = "null argument"; return 1; }
   *out = nullptr;
@@ -146,6 +155,21 @@ int blh_run_input_file(const char *path, int device, int quiet, double timings[1
     if (timings) {
       double v[12] = {t.total, t.geodesic, t.read, t.sample, t.image, t.render, t.gpu_geodesic_ms,
                       t.gpu_radiation_ms, t.gpu_refine_ms, (double)t.rays, (double)t.samples, 0.0};
+      std::memcpy(timings, v, sizeof v);
+    }
+    return 0;
+  } catch (const std::exception &e) {
+    return fail(e);
+  }
+}
+
+int blh_run_input_file_devices(const char *path, const int *devices, int num_devices, int quiet, double timings[12]) {
+  if (!path || !devices || num_devices <= 0) { g_error = "bad argument"; return 1; }
+  try {
+    blh::RunTimings t = blh::run_input_file(path, std::vector<int>(devices, devices + num_devices), quiet != 0);
+    if (timings) {
+      double v[12] = {t.total, t.geodesic, t.read, t.sample, t.image, t.render, t.gpu_geodesic_ms,
+                      t.gpu_radiation_ms, t.gpu_refine_ms, (double)t.rays, (double)t.samples, (double)num_devices};
       std::memcpy(timings, v, sizeof v);
     }
     return 0;

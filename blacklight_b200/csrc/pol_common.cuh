@@ -115,53 +115,6 @@ __device__ __forceinline__ void contracted_connection(const KsJet &J, const doub
   }
 }
 
-// The same contraction applied to a vector without forming the matrix: out^mu = -Gamma^mu_{alpha beta} k^alpha v^beta,
-// the rate of change of a parallel-transported vector's components along k.  With g = eta + f l l (stationary),
-//   2 Gamma_{mu alpha beta} k^alpha v^beta = k.d g_{mu beta} v^beta + v.d g_{mu alpha} k^alpha - d_mu g_{alpha beta} k^alpha v^beta
-// and every term is a handful of dot products of k, v with l, grad f and grad l.  The parts that depend on k alone are
-// gathered once per (jet, k) in KContraction; a vector then costs ~110 operations instead of a 16-entry matrix row
-// sweep, and no 4x4 arrays stay live in registers.
-struct KContraction {
-  double k[4];
-  double kf;      // k.grad f
-  double lk;      // l_alpha k^alpha
-  double kl[3];   // k.grad l_i
-  double mk[3];   // k^i d_a l_i
-};
-
-__device__ __forceinline__ void k_contraction(const KsJet &J, const double k[4], KContraction &K) {
-  for (int mu = 0; mu < 4; mu++) K.k[mu] = k[mu];
-  K.kf = k[1] * J.df[0] + k[2] * J.df[1] + k[3] * J.df[2];
-  K.lk = k[0] + J.l[0] * k[1] + J.l[1] * k[2] + J.l[2] * k[3];
-  for (int i = 0; i < 3; i++) {
-    K.kl[i] = k[1] * J.dl[i][0] + k[2] * J.dl[i][1] + k[3] * J.dl[i][2];
-    K.mk[i] = k[1] * J.dl[0][i] + k[2] * J.dl[1][i] + k[3] * J.dl[2][i];
-  }
-}
-
-__device__ __forceinline__ void transport_rate_direct(const KsJet &J, const KContraction &K, const double v[4], double out[4]) {
-  const double lv = v[0] + J.l[0] * v[1] + J.l[1] * v[2] + J.l[2] * v[3];
-  const double vf = v[1] * J.df[0] + v[2] * J.df[1] + v[3] * J.df[2];
-  double vl[3], mv[3];
-  for (int i = 0; i < 3; i++) {
-    vl[i] = v[1] * J.dl[i][0] + v[2] * J.dl[i][1] + v[3] * J.dl[i][2];
-    mv[i] = v[1] * J.dl[0][i] + v[2] * J.dl[1][i] + v[3] * J.dl[2][i];
-  }
-  const double klv = K.kl[0] * v[1] + K.kl[1] * v[2] + K.kl[2] * v[3];
-  const double vlk = vl[0] * K.k[1] + vl[1] * K.k[2] + vl[2] * K.k[3];
-  const double a12 = (K.kf * lv + J.f * klv) + (vf * K.lk + J.f * vlk);   // coefficient of l_mu in the first two terms
-  const double b1 = J.f * lv, b2 = J.f * K.lk, c3 = K.lk * lv;
-  const double g0 = 0.5 * a12;
-  double g[3];
-  for (int i = 0; i < 3; i++)
-    g[i] = 0.5 * (a12 * J.l[i] + b1 * K.kl[i] + b2 * vl[i] - (J.df[i] * c3 + b1 * K.mk[i] + b2 * mv[i]));
-  const double s = J.f * (-g0 + J.l[0] * g[0] + J.l[1] * g[1] + J.l[2] * g[2]);
-  out[0] = g0 - s;
-  out[1] = s * J.l[0] - g[0];
-  out[2] = s * J.l[1] - g[1];
-  out[3] = s * J.l[2] - g[2];
-}
-
 // (D v)^mu = -A^mu_beta v^beta : rate of change of a parallel-transported vector's components
 __device__ __forceinline__ void transport_rate(const double A[4][4], const double v[4], double out[4]) {
   for (int mu = 0; mu < 4; mu++) out[mu] = -(A[mu][0] * v[0] + A[mu][1] * v[1] + A[mu][2] * v[2] + A[mu][3] * v[3]);
@@ -254,23 +207,20 @@ __device__ __forceinline__ void transport_map(const KsJet &jet_p, const double k
                                               const KsJet &jet, const double kcon[4], const double f1[4], const double f2[4],
                                               double dlam, StokesMap &M) {
   const double ks[4] = {k_p[0] + kcon[0], k_p[1] + kcon[1], k_p[2] + kcon[2], k_p[3] + kcon[3]};
-  KContraction Kpp, Kps, Kns;
-  k_contraction(jet_p, k_p, Kpp);
-  k_contraction(jet_p, ks, Kps);
-  k_contraction(jet, ks, Kns);
+  double A_avg[4][4], A_tmp[4][4], A_pp[4][4];
+  contracted_connection(jet_p, ks, A_avg);
+  contracted_connection(jet, ks, A_tmp);
+  for (int a = 0; a < 4; a++)
+    for (int b = 0; b < 4; b++) A_avg[a][b] = 0.25 * (A_avg[a][b] + A_tmp[a][b]);
+  contracted_connection(jet_p, k_p, A_pp);
   const double h = (dlam_p + dlam) / 2.0, h2 = (dlam_p + dlam) / 4.0;
   LegProj L[2];
   for (int c = 0; c < 2; c++) {
-    double vp[4], va[4], vap[4], t0[4], t1[4];
-    transport_rate_direct(jet_p, Kpp, e_p[c], vp);
-    // the corrector's connection is the mean of the two samples' (each contracted with (k_p + k) / 2): a factor 1/4
-    transport_rate_direct(jet_p, Kps, e_p[c], t0);
-    transport_rate_direct(jet, Kns, e_p[c], t1);
-    for (int mu = 0; mu < 4; mu++) va[mu] = 0.25 * (t0[mu] + t1[mu]);
-    // the corrector derivative acts on the predicted tensor: Da(e + h2 Dp e) = Da e + h2 Da Dp e
-    transport_rate_direct(jet_p, Kps, vp, t0);
-    transport_rate_direct(jet, Kns, vp, t1);
-    for (int mu = 0; mu < 4; mu++) vap[mu] = 0.25 * (t0[mu] + t1[mu]);
+    double vp[4], va[4], vap[4];
+    transport_rate(A_pp, e_p[c], vp);
+    // corrector derivative acts on the predicted tensor: Da(e + h2 Dp e) = Da e + h2 Da Dp e
+    transport_rate(A_avg, e_p[c], va);
+    transport_rate(A_avg, vp, vap);
     L[c].u[0] = dot4(f1, e_p[c]);  L[c].u[1] = dot4(f2, e_p[c]);
     L[c].up[0] = dot4(f1, vp);     L[c].up[1] = dot4(f2, vp);
     L[c].ua[0] = dot4(f1, va);     L[c].ua[1] = dot4(f2, va);
@@ -283,12 +233,12 @@ __device__ __forceinline__ void transport_map(const KsJet &jet_p, const double k
 // predictor only.
 __device__ __forceinline__ void transport_map_final(const KsJet &jet_p, const double k_p[4], const double e_p[2][4], double dlam_p,
                                                     const double f1[4], const double f2[4], StokesMap &M) {
-  KContraction Kpp;
-  k_contraction(jet_p, k_p, Kpp);
+  double A_pp[4][4];
+  contracted_connection(jet_p, k_p, A_pp);
   LegProj L[2];
   for (int c = 0; c < 2; c++) {
     double vp[4];
-    transport_rate_direct(jet_p, Kpp, e_p[c], vp);
+    transport_rate(A_pp, e_p[c], vp);
     L[c].u[0] = dot4(f1, e_p[c]);  L[c].u[1] = dot4(f2, e_p[c]);
     L[c].up[0] = dot4(f1, vp);     L[c].up[1] = dot4(f2, vp);
     L[c].ua[0] = L[c].ua[1] = L[c].uap[0] = L[c].uap[1] = 0.0;
@@ -474,12 +424,20 @@ __device__ __forceinline__ void synchrotron_polarized(const RadParams &P, const 
         double vb = P.kappa_frac * 2.0 * q.n_e * e2 * q.nu_c * q.cos_b * inv_nu * (1.0 / (phys::m_e * phys::c));
         double x084 = bfm::exp_bf(0.84 * lx);
         double xx_m12 = bfm::exp_bf(lm12);
-        double q_lo = va * P.kappa_rho_q_low_a * (1.0 - bfm::exp_bf(P.kappa_rho_q_low_b * x084) -
-                      sin(P.kappa_rho_q_low_c * xx) * bfm::exp_bf(P.kappa_rho_q_low_d * bfm::exp_bf(P.kappa_rho_q_low_e * lx)));
-        double q_hi = va * P.kappa_rho_q_high_a * (1.0 - bfm::exp_bf(P.kappa_rho_q_high_b * x084) -
-                      sin(P.kappa_rho_q_high_c * xx) * bfm::exp_bf(P.kappa_rho_q_high_d * bfm::exp_bf(P.kappa_rho_q_high_e * lx)));
-        double v_lo = P.kappa_rho_v * vb * P.kappa_rho_v_low_a * (1.0 - 0.17 * bfm::log_bf(1.0 + P.kappa_rho_v_low_b * xx_m12));
-        double v_hi = P.kappa_rho_v * vb * P.kappa_rho_v_high_a * (1.0 - 0.17 * bfm::log_bf(1.0 + P.kappa_rho_v_high_b * xx_m12));
+        // The fits are tabulated at kappa = 3.5, 4, 4.5, 5 and blended linearly in between.  On a tabulated value one
+        // weight is exactly zero and that entry (4 exponentials, a sine and a logarithm) is not evaluated; its term
+        // is 0 x (a finite number) in the reference.
+        double q_lo = 0.0, q_hi = 0.0, v_lo = 0.0, v_hi = 0.0;
+        if (P.kappa_rho_frac != 1.0) {
+          q_lo = va * P.kappa_rho_q_low_a * (1.0 - bfm::exp_bf(P.kappa_rho_q_low_b * x084) -
+                 sin(P.kappa_rho_q_low_c * xx) * bfm::exp_bf(P.kappa_rho_q_low_d * bfm::exp_bf(P.kappa_rho_q_low_e * lx)));
+          v_lo = P.kappa_rho_v * vb * P.kappa_rho_v_low_a * (1.0 - 0.17 * bfm::log_bf(1.0 + P.kappa_rho_v_low_b * xx_m12));
+        }
+        if (P.kappa_rho_frac != 0.0) {
+          q_hi = va * P.kappa_rho_q_high_a * (1.0 - bfm::exp_bf(P.kappa_rho_q_high_b * x084) -
+                 sin(P.kappa_rho_q_high_c * xx) * bfm::exp_bf(P.kappa_rho_q_high_d * bfm::exp_bf(P.kappa_rho_q_high_e * lx)));
+          v_hi = P.kappa_rho_v * vb * P.kappa_rho_v_high_a * (1.0 - 0.17 * bfm::log_bf(1.0 + P.kappa_rho_v_high_b * xx_m12));
+        }
         C.rho[0] += (1.0 - P.kappa_rho_frac) * q_lo + P.kappa_rho_frac * q_hi;
         C.rho[1] += (1.0 - P.kappa_rho_frac) * v_lo + P.kappa_rho_frac * v_hi;
       }

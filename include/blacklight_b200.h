@@ -175,6 +175,7 @@ int bl_create(const bl_params *params, bl_ctx **out);
 void bl_destroy(bl_ctx *ctx);
 const char *bl_last_error(const bl_ctx *ctx);   /* ctx may be NULL: error of a failed bl_create */
 int bl_image_num_quantities(const bl_ctx *ctx);
+int bl_device_count(void);                       /* usable CUDA devices (0 if none): one bl_ctx drives one of them */
 
 /* Replaces RadiationIntegrator::ObtainGridData: one H2D copy of the whole grid (per snapshot). */
 int bl_upload_grid(bl_ctx *ctx, const bl_grid_view *grid);

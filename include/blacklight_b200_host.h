@@ -38,6 +38,9 @@ int64_t blh_camera_refined(const blh_config *cfg, int level, const int32_t *pare
  * that owns a share of a level's blocks (AugmentCamera's per-pixel expressions, camera.cpp:461-503). */
 int64_t blh_camera_blocks(const blh_config *cfg, int level, const int32_t *locs, int64_t num_blocks, double *pos, double *dir,
                           double *factor);
+/* Level-0 pixels of the listed image rows only (what a GPU that owns a share of the frame's rows traces): pos, dir
+ * (num_rows * res, 4), factor (num_rows * res), bit-identical to the same rows of blh_camera_root.  Returns the ray count. */
+int64_t blh_camera_rows(const blh_config *cfg, const int64_t *rows, int64_t num_rows, double *pos, double *dir, double *factor);
 /* timings: total, geodesic, read, sample, image, render [s]; gpu geodesic, radiation, refine [ms];
  * rays, samples, reserved */
 /* Snapshot readers -- the upload side of SimulationReader::Read (simulation_reader.cpp:200-861): simulation_format
@@ -53,6 +56,12 @@ int blh_snapshot_view(const blh_snapshot *snap, bl_grid_view *view, double *time
 void blh_snapshot_free(blh_snapshot *snap);
 
 int blh_run_input_file(const char *path, int device, int quiet, double timings[12]);
+/* The same run spread over several GPUs of the node from this one process (the reference parallelises inside main too,
+ * blacklight.cpp:77): one context and one host thread per listed CUDA device, the image rows -- refinement blocks for
+ * adaptive runs -- dealt round-robin over them, the grid replicated on each; the written output is bitwise the single
+ * device's.  blh_run_input_file(path, -1, ...) and the executable take the list from BLACKLIGHT_DEVICES ("all", "0-7",
+ * "0,2,3").  timings[11] = number of devices used. */
+int blh_run_input_file_devices(const char *path, const int *devices, int num_devices, int quiet, double timings[12]);
 
 #ifdef __cplusplus
 }

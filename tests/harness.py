@@ -25,9 +25,11 @@ class Case(cases.Case):
     def run_reference(self, checkpoints=True):
         """Run the unmodified reference; returns dict(npz=..., geo=..., samp=..., timers=...)."""
         extra = {}
+        sample_only = checkpoints == 'sample'   # large cases: the geodesic checkpoint would be several GB
         if checkpoints:
-            extra.update({'checkpoint_geodesic_save': 'true', 'checkpoint_geodesic_load': 'false',
-                          'checkpoint_geodesic_file': os.path.join(self.dir, 'out_ref', 'geo.ckpt')})
+            if not sample_only:
+                extra.update({'checkpoint_geodesic_save': 'true', 'checkpoint_geodesic_load': 'false',
+                              'checkpoint_geodesic_file': os.path.join(self.dir, 'out_ref', 'geo.ckpt')})
             if self.sim:
                 extra.update({'checkpoint_sample_save': 'true', 'checkpoint_sample_load': 'false',
                               'checkpoint_sample_file': os.path.join(self.dir, 'out_ref', 'samp.ckpt')})
@@ -39,7 +41,8 @@ class Case(cases.Case):
         res['timers'] = parse_timers(proc.stdout)
         if checkpoints:
             import refio  # oracle/: checkpoint readers, reference runs only
-            res['geo'] = refio.read_geodesic_checkpoint(extra['checkpoint_geodesic_file'])
+            if not sample_only:
+                res['geo'] = refio.read_geodesic_checkpoint(extra['checkpoint_geodesic_file'])
             if self.sim:
                 res['samp'] = refio.read_sample_checkpoint(extra['checkpoint_sample_file'],
                                                            interp=self.kv['simulation_interp'] == 'true')

@@ -352,6 +352,22 @@ def test_time_series_reread_equals_fresh_read(fmt, tmp_path):
         assert np.array_equal(again[k], fresh[k]), k
 
 
+def test_camera_rows_equal_the_rows_of_the_full_camera(tmp_path):
+    """blh_camera_rows (a device's share of the frame in the multi-GPU driver) is bit for bit the same rows of
+    blh_camera_root, plane and pinhole cameras."""
+    for over in ({'camera_resolution': 12}, {'camera_resolution': 10, 'camera_type': 'pinhole', 'camera_th': '30.0'}):
+        case = Case(tmp_path / ('c%d' % len(over)), 'formula.input', over)
+        cfg = case.config()
+        res = cfg.resolution
+        pos, dirs, fac = cfg.camera_root()
+        rows = np.arange(1, res, 3)
+        p2, d2, f2 = cfg.camera_rows(rows)
+        idx = (rows[:, None] * res + np.arange(res)[None, :]).ravel()
+        assert np.array_equal(p2, pos[idx]) and np.array_equal(d2, dirs[idx]) and np.array_equal(f2, fac[idx])
+        with pytest.raises(bl.BlacklightError):
+            cfg.camera_rows([res])
+
+
 def test_open_snapshots_do_not_share_reader_state(tmp_path):
     """Two snapshot handles open at the same time, and a reread issued from another thread: what the first file of a
     series fixed (AthenaK variable positions and record size, harm3d / iharm3d coordinate parameters and modified x2

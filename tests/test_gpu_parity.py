@@ -13,6 +13,7 @@ import numpy as np
 import pytest
 
 import blacklight_b200 as bl
+from blacklight_b200.cases import C4_PHYSICS
 from harness import REF_BIN, Case, flux_rel, rel_err
 from golden.make_golden import CASES
 
@@ -898,6 +899,7 @@ def test_division_sqrt_sequences(gpu, tmp_path):
     (32, 2, False, ('-4.0', '7.0', '-5.0', '2.0')),
     (256, 2, False, ('-1.0', '4.5', '-3.5', '0.5')),      # the benchmark's 1024^2 frame
     (256, 4, True, ('1.0', '3.2', '-2.5', '-1.0')),       # the 4096^2 polarized target frame (traced in waves)
+    (128, 5, 'c4', ('1.0', '1.8', '-2.0', '-1.2')),       # the same frame with the benchmark's physics: kappa = 4, 4 frequencies
 ])
 def test_full_resolution_window_against_reference(root, levels, pol, window, gpu, tmp_path):
     """Parity at a resolution the reference cannot hold in memory as a full frame: a coarse
@@ -911,16 +913,36 @@ def test_full_resolution_window_against_reference(root, levels, pol, window, gpu
     bs = 8
     fine = root * 2 ** levels
     over = {'camera_resolution': root, 'image_polarization': 'true' if pol else 'false', 'image_tau': 'false',
-            'adaptive_max_level': levels, 'adaptive_block_size': bs, 'adaptive_num_regions': 1,
+            'adaptive_frequency_num': 1, 'adaptive_max_level': levels, 'adaptive_block_size': bs, 'adaptive_num_regions': 1,
             'adaptive_region_1_level': levels, 'adaptive_region_1_x_min': window[0], 'adaptive_region_1_x_max': window[1],
             'adaptive_region_1_y_min': window[2], 'adaptive_region_1_y_max': window[3],
             'adaptive_val_frac': '-1.0', 'adaptive_abs_grad_frac': '-1.0', 'adaptive_rel_grad_frac': '-1.0',
             'adaptive_abs_lapl_frac': '-1.0', 'adaptive_rel_lapl_frac': '-1.0'}
+    F = 1
+    if pol == 'c4':
+        over.update(C4_PHYSICS)
+        F = 4
     case = Case(tmp_path / 'ref', 'adaptive.input', over)
     ref = case.run_reference(checkpoints=False)['npz']
     assert int(ref['adaptive_num_levels'][0]) == levels
     locs, blocks = ref['adaptive_block_locs_%d' % levels], ref['adaptive_I_nu_%d' % levels]
-    assert len(locs) > 0 and blocks.shape[1:] == (bs, bs)
+    assert len(locs) > 0 and blocks.shape[-2:] == (bs, bs)
+    if F > 1:
+        # every frequency: image slots 4 l + s of the fine frame against the reference's (F, blocks, bs, bs) arrays
+        full_over = {k: v for k, v in over.items() if not k.startswith('adaptive_')}
+        full_over.update({'camera_resolution': fine, 'adaptive_max_level': 0})
+        cfg, ctx, image, _, _ = run_gpu_level0(Case(tmp_path / 'gpu', 'adaptive.input', full_over))
+        assert ctx.polarized_stage_ms(0)['slab'] > 0   # the three-stage pipeline rendered it
+        cut = lambda plane: np.stack([plane.reshape(fine, fine)[v * bs:(v + 1) * bs, u * bs:(u + 1) * bs] for v, u in locs])
+        for l in range(F):
+            mine = {name: cut(image[4 * l + s_ind]) for s_ind, name in enumerate(('I_nu', 'Q_nu', 'U_nu', 'V_nu'))}
+            theirs = {name: ref['adaptive_%s_%d' % (name, levels)][l] for name in mine}
+            assert rel_err(mine['I_nu'], theirs['I_nu']) <= PIXEL_TOL, 'frequency %d' % l
+            assert flux_rel(mine['I_nu'], theirs['I_nu']) <= FLUX_TOL
+            for k, v in stokes_err(mine, theirs).items():
+                assert v <= PIXEL_TOL, 'frequency %d %s %.3e' % (l, k, v)
+        ctx.close()
+        return
     full_over = {k: v for k, v in over.items() if not k.startswith('adaptive_')}
     full_over.update({'camera_resolution': fine, 'adaptive_max_level': 0})
     full_case = Case(tmp_path / 'gpu', 'adaptive.input', full_over)
@@ -1010,11 +1032,6 @@ def test_golden_slow_light(name, gpu, tmp_path):
     assert flux_rel(mine, ref) <= FLUX_TOL
 
 
-C4_PHYSICS = {'image_polarization': 'true', 'image_num_frequencies': 4, 'image_frequency_start': '8.6e10',
-              'image_frequency_end': '3.45e11', 'image_frequency_spacing': 'log', 'plasma_kappa_frac': '1.0',
-              'plasma_kappa': '4.0', 'plasma_w': '1.0'}
-
-
 def _render_polarized(case, env, tile_rays=0):
     """One level-0 polarized image with the given BL_POL_* environment (read by bl_create)."""
     saved = {k: os.environ.get(k) for k in ('BL_POL_FUSED', 'BL_POL_SLAB')}
@@ -1065,3 +1082,69 @@ def test_polarized_pipeline_matches_fused_kernel(over, gpu, tmp_path):
         assert err <= 1e-12, 'slab %s tile %d: Stokes images differ by %.3e of the peak' % (env, tile, err)
         if image.shape[0] > light:
             assert rel_err(image[light:], fused[light:]) <= 1e-12
+
+
+@pytest.mark.parametrize('base,over,mock', [
+    ('simulation.input', dict(C4_PHYSICS, camera_resolution=30), None),
+    ('simulation.input', {'camera_resolution': 24, 'image_time': 'true', 'image_tau': 'true', 'image_crossings': 'true'}, {'blocks': (2, 2, 2)}),
+    ('adaptive.input', {'camera_resolution': 32, 'adaptive_max_level': 2, 'adaptive_num_regions': 1, 'adaptive_region_1_level': 2,
+                        'adaptive_region_1_x_min': '-4', 'adaptive_region_1_x_max': '4', 'adaptive_region_1_y_min': '-4',
+                        'adaptive_region_1_y_max': '4'}, None),
+    ('render.input', {'camera_resolution': 24}, None),
+    ('formula.input', {'camera_resolution': 20}, None),
+])
+def test_multi_device_driver_is_bitwise_the_single_device(base, over, mock, gpu, tmp_path):
+    """blh_run_input_file_devices: one context and one host thread per listed device, rows (adaptive: refinement blocks,
+    the root level included) dealt round-robin, parts scattered into the frame.  Every array of the written npz must be
+    bit for bit the single-device run's -- here with three contexts sharing the one GPU of the test box (the driver does
+    not care whether the ordinals differ)."""
+    case = Case(tmp_path, base, over, mock=mock)
+    one, t1 = case.run_gpu_file(tag='one', devices=[0])
+    three, t3 = case.run_gpu_file(tag='three', devices=[0, 0, 0])
+    assert t3['devices'] == 3 and t1['rays'] == t3['rays'] and t1['samples'] == t3['samples']
+    assert sorted(one) == sorted(three)
+    for k in one:
+        assert one[k].shape == three[k].shape, k
+        assert np.array_equal(one[k], three[k], equal_nan=True), k
+
+
+def test_sampled_cell_indices_exact_at_scale(gpu, tmp_path):
+    """north_star asks for bit-exact sampled cell indices; the radiation kernels locate a sample with fused arithmetic
+    (r from one rsqrt, CUDA acos / atan2), so exactness is an empirical property: an index can only differ where a
+    coordinate rounds to the other side of a cell face.  Measured here on > 10^8 samples: three 256^2 frames (single
+    block trilinear; 16 blocks, Kerr a = 0.9, inclined, nearest; two-level AMR mesh, tilted camera, trilinear) against
+    the reference's sampling checkpoint.  Any mismatch fails the test and is printed with its count."""
+    if not os.path.exists(REF_BIN):
+        pytest.skip('oracle/_ref/blacklight not present')
+    configs = [
+        ({'camera_resolution': 256}, None),
+        ({'camera_resolution': 256, 'simulation_interp': 'false', 'simulation_a': '0.9', 'camera_th': '70.0', 'camera_ph': '25.0'},
+         {'blocks': (2, 2, 4)}),
+        ({'camera_resolution': 256, 'camera_th': '60.0', 'camera_rotation': '20.0'}, dict(AMR_MOCK, refine=_amr_refine)),
+    ]
+    total = bad_inds = bad_flags = 0
+    worst_frac = 0.0
+    for n, (over, mock) in enumerate(configs):
+        case = Case(tmp_path / str(n), 'simulation.input', over, mock=mock)
+        rs = case.run_reference(checkpoints='sample')['samp']
+        cfg, ctx, image, _, stats = run_gpu_level0(case, taps=True)
+        interp = case.kv['simulation_interp'] == 'true'
+        t = ctx.download_sample_inds(0, interp=interp)
+        num = ctx.download_samples(0, arrays=False)['num']
+        ctx.close()
+        S = t['nan'].shape[1]
+        assert rs['sample_nan'].shape == t['nan'].shape
+        mask = np.arange(S)[None, :] < num[:, None]
+        bad_flags += int(np.count_nonzero((t['nan'] != rs['sample_nan'])[mask])) + int(np.count_nonzero((t['fallback'] != rs['sample_fallback'])[mask]))
+        valid = mask & (t['cut'] == 0) & (t['nan'] == 0) & (t['fallback'] == 0)
+        differ = np.any(t['inds'] != rs['sample_inds'], axis=2) & valid
+        total += int(np.count_nonzero(valid))
+        bad_inds += int(np.count_nonzero(differ))
+        if interp:
+            worst_frac = max(worst_frac, float(np.max(np.abs(t['fracs'] - rs['sample_fracs'])[valid & ~differ])))
+        del t, rs
+    print('sampled cell indices: %d samples compared, %d index mismatches, %d flag mismatches, worst fraction difference %.2e'
+          % (total, bad_inds, bad_flags, worst_frac))
+    assert total > 100_000_000
+    assert bad_inds == 0 and bad_flags == 0
+    assert worst_frac < 1e-9
