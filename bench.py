@@ -20,6 +20,7 @@ of the kernel sources it was taken from); here that count is multiplied by the l
 the kernel's live CUDA-event time and by the DFMA peak measured in the same run.
 """
 import argparse
+import datetime
 import hashlib
 import json
 import math
@@ -326,7 +327,7 @@ def measure(args, name, resolution, steps, warmup, rank, world, local_rank, main
     import torch
     import torch.distributed as dist
     import blacklight_b200 as bl
-    from blacklight_b200.sharding import shard_rows
+    from blacklight_b200.sharding import gather_rows, shard_rows
     dev = torch.device('cuda', local_rank)
     workdir = tempfile.mkdtemp(prefix='bl_bench_%d_' % rank)
     try:
@@ -388,13 +389,12 @@ def measure(args, name, resolution, steps, warmup, rank, world, local_rank, main
                 _, _, st_ = ctx.radiate_level(0, image=image_host.numpy(), render=render_host, num_render=R)   # kernels + D2H
                 return st_
             _, _, st_ = ctx.radiate_level(0, download=False, render=render_host, num_render=R)
-            ptr, shape = ctx.device_image(0)
-            mine = torch.as_tensor(_DeviceArray(ptr, shape), device=dev)
-            dist.gather(mine, parts, dst=0)                                # rows of every rank to rank 0 over NVLink
-            if rank == 0:
-                for r in range(world):                                     # interleave the rows, then one D2H of the frame
-                    full_dev[:, r::world, :] = parts[r].view(Q, -1, resolution)
-                image_host.copy_(full_dev.view(Q, -1), non_blocking=True)
+            if Q > 0:
+                ptr, shape = ctx.device_image(0)
+                mine = torch.as_tensor(_DeviceArray(ptr, shape), device=dev)
+                gather_rows(mine, parts, full_dev, resolution, rank, world, dist)   # rows of every rank to rank 0 over NVLink
+                if rank == 0:
+                    image_host.copy_(full_dev.view(Q, -1), non_blocking=True)    # one D2H of the assembled frame
             torch.cuda.current_stream().synchronize()
             return st_
 
@@ -555,7 +555,8 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        # a rank that cannot follow (an exception on one side of a collective) must cost minutes, not the default 10
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank), timeout=datetime.timedelta(seconds=240))
     name = args.workload
     scaling = args.scaling
     peaks = {}

@@ -70,6 +70,7 @@ def load_library():
         'bl_upload_samples': (i32, [vp, i32, vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, ctypes.POINTER(LevelStats)]),
         'bl_launch_count': (ctypes.c_longlong, [vp]), 'bl_cuda_stream': (vp, [vp]),
         'bl_device_image': (i32, [vp, i32, ctypes.POINTER(vp), ctypes.POINTER(i64)]),
+        'bl_download_polarized_scratch': (i32, [vp, i32, vp, vp, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i64)]),
         'bl_polarized_stage_ms': (i32, [vp, i32, ctypes.POINTER(dbl * 3), ctypes.POINTER(ctypes.c_int32)]),
         'bl_download_samples': (i32, [vp, i32, vp, vp, vp, vp, vp]),
         'bl_download_sample_inds': (i32, [vp, i32, vp, vp, vp, vp, vp]),
@@ -299,6 +300,15 @@ class Context:
         ptr, n = ctypes.c_void_p(), ctypes.c_int64()
         self._check(_lib.bl_device_image(self._h, level, ctypes.byref(ptr), ctypes.byref(n)))
         return ptr.value, (self.num_quantities, n.value)
+
+    def polarized_scratch(self, level=0):
+        """(fields, slab, rays) scratch of the last slab of the three-stage polarized pipeline and the (10, rays) camera
+        half-step map: bl_download_polarized_scratch."""
+        nf, slab, rays = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        self._check(_lib.bl_download_polarized_scratch(self._h, level, None, None, ctypes.byref(nf), ctypes.byref(slab), ctypes.byref(rays)))
+        out, cam = np.empty((nf.value, slab.value, rays.value)), np.empty((10, rays.value))
+        self._check(_lib.bl_download_polarized_scratch(self._h, level, _ptr(out), _ptr(cam), None, None, None))
+        return out, cam
 
     def polarized_stage_ms(self, level=0):
         """Device ms of the three polarized stages (geometry, coefficients, transfer) in the last radiate_level and the

@@ -1044,6 +1044,28 @@ int bl_device_image(bl_ctx *ctx, int level, void **image, int64_t *num_rays) {
   return BL_OK;
 }
 
+int bl_download_polarized_scratch(bl_ctx *ctx, int level, double *out, double *cam_map, int64_t *num_fields, int64_t *slab,
+                                  int64_t *num_rays) {
+  if (!ctx) return BL_ERR_ARG;
+  if (level < 0 || level >= (int)ctx->levels.size()) return bl_fail(ctx, BL_ERR_ARG, "bl_download_polarized_scratch: level %d out of range", level);
+  Level &L = ctx->levels[level];
+  if (!L.scratch || L.slab <= 0 || !L.resident)
+    return bl_fail(ctx, BL_ERR_STATE, "bl_download_polarized_scratch: level %d was not rendered by the three-stage pipeline as one wave", level);
+  const int64_t nf = bl_polarized_split_fields(ctx->rad.num_freq);
+  if (num_fields) *num_fields = nf;
+  if (slab) *slab = L.slab;
+  if (num_rays) *num_rays = L.wave_rays;
+  if (out) {
+    BL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    BL_CUDA_CHECK(cudaMemcpy(out, L.scratch, (size_t)nf * (size_t)L.slab * (size_t)L.wave_rays * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  if (cam_map) {
+    BL_CUDA_CHECK(cudaSetDevice(ctx->device));
+    BL_CUDA_CHECK(cudaMemcpy(cam_map, L.cam_map, (size_t)10 * (size_t)L.wave_rays * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  return BL_OK;
+}
+
 int bl_polarized_stage_ms(bl_ctx *ctx, int level, double *ms3, int32_t *slab) {
   if (!ctx || !ms3) return BL_ERR_ARG;
   if (level < 0 || level >= (int)ctx->levels.size()) return bl_fail(ctx, BL_ERR_ARG, "bl_polarized_stage_ms: level %d out of range", level);

@@ -25,3 +25,22 @@ def assemble(parts, resolution, world):
 def shard_blocks(num_blocks, rank, world):
     """Adaptive refinement blocks owned by `rank` (contiguous block ids, round-robin)."""
     return np.arange(rank, num_blocks, world)
+
+
+def gather_rows(mine, parts, full, resolution, rank, world, dist):
+    """Final exchange of a row-sharded frame: every rank's (Q, rows_r * res) image part to rank 0 (one collective), where
+    the rows are interleaved into `full` (Q, res, res).  Torch tensors on the device of the process group's backend
+    (CUDA with nccl, CPU with gloo); parts / full are rank 0's receive buffers (None elsewhere).  A frame without image
+    quantities (rendering only: Q = 0) has nothing to exchange.  Written so that no rank can leave it early: the only
+    rank-dependent work is plain strided copies on rank 0."""
+    if resolution % world != 0:   # the same on every rank: a gather needs equal parts
+        raise ValueError('gather_rows: %d rows do not divide over %d ranks' % (resolution, world))
+    if mine.shape[0] == 0:
+        return full
+    dist.gather(mine, parts if rank == 0 else None, dst=0)
+    if rank == 0:
+        q = mine.shape[0]
+        for r in range(world):
+            rows_r = len(range(r, resolution, world))
+            full[:, r::world, :] = parts[r].reshape(q, rows_r, resolution)
+    return full

@@ -235,6 +235,13 @@ int bl_device_image(bl_ctx *ctx, int level, void **image, int64_t *num_rays);
  * level (CUDA events around every launch); *slab: samples per slab, 0 if the fused kernel ran.  Environment, tuning
  * only: BL_POL_FUSED=1 keeps the fused kernel, BL_POL_SLAB=n fixes the slab length. */
 int bl_polarized_stage_ms(bl_ctx *ctx, int level, double *ms3, int32_t *slab);
+/* Parity tap of that pipeline: the scratch of the LAST slab it processed (samples 0 <= n < slab of every ray; with
+ * BL_POL_SLAB >= ray_max_steps the whole level), (num_fields, slab, num_rays) f64 -- per sample the 3x3 + 1 entries of
+ * the Stokes transport matrix, the affine step, seven plasma scalars and 8 synchrotron coefficients per frequency
+ * (field order: csrc/radiate_pol_split.cu); cam_map: (10, num_rays), the half step from the last sample onto the camera
+ * tetrad.  out / cam_map may be NULL (e.g. to query the extents first).  Resident levels only. */
+int bl_download_polarized_scratch(bl_ctx *ctx, int level, double *out, double *cam_map, int64_t *num_fields, int64_t *slab,
+                                  int64_t *num_rays);
 
 /* The CUDA stream (cudaStream_t) every kernel and copy of this context is issued on, so that a host
  * can bracket calls with its own events or order other work against them. */

@@ -469,6 +469,44 @@ def test_row_sharding_and_gather_world_size_2():
     assert q.get(timeout=10) is True
 
 
+def _gather_rows_worker(rank, world, port, res, q):
+    import torch
+    import torch.distributed as dist
+    from blacklight_b200.sharding import gather_rows, shard_rows
+    dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%d' % port, rank=rank, world_size=world)
+    ok = True
+    for quantities in (3, 0):       # Q = 0: a rendering-only frame has no image quantities to exchange
+        _, idx = shard_rows(res, rank, world)
+        mine = torch.from_numpy((idx[None, :] * (np.arange(quantities)[:, None] + 1.0)).reshape(quantities, len(idx)))
+        parts = [torch.empty((quantities, len(shard_rows(res, r, world)[1])), dtype=torch.float64) for r in range(world)] if rank == 0 else None
+        full = torch.zeros((quantities, res, res), dtype=torch.float64) if rank == 0 else None
+        gather_rows(mine, parts, full, res, rank, world, dist)
+        if rank == 0:
+            m = np.arange(res * res, dtype=np.float64)
+            ok = ok and all(np.array_equal(full[k].numpy().ravel(), m * (k + 1.0)) for k in range(quantities))
+    dist.barrier()                  # both ranks are still in step after the empty frame
+    if rank == 0:
+        q.put(bool(ok))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('res', [12, 16])
+def test_gather_rows_world_size_2(res):
+    """bench.py's final exchange (blacklight_b200.sharding.gather_rows): rank 0 ends up with the frame in the reference's
+    pixel order, a frame without image quantities exchanges nothing, and neither rank is left behind."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 31000 + os.getpid() % 2000 + res
+    procs = [ctx.Process(target=_gather_rows_worker, args=(r, 2, port, res, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) is True
+
+
 class _FakeConfig:
     """Stands in for blacklight_b200.Config in the sharded-adaptive host logic test: an 8x8 image of 2x2 blocks."""
     resolution, block_size = 8, 2
