@@ -13,6 +13,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include "bf_tables.h"
+
 #if defined(__CUDACC__)
 #define BF_HD __host__ __device__ __forceinline__
 #else
@@ -60,65 +62,80 @@ BF_HD double rcp_seed(double d) {
 #endif
 }
 
+// Tables (tools/bf_tables.py): on the device they sit in global memory behind the read-only path -- the indices of a
+// warp diverge, which the constant cache would serialise.
+#if defined(__CUDACC__)
+static __device__ const double bf_exp_table_dev[64] = BF_EXP_TABLE;
+static __device__ const double bf_log_table_dev[256] = BF_LOG_TABLE;
+#endif
+static const double bf_exp_table_host[64] = BF_EXP_TABLE;
+static const double bf_log_table_host[256] = BF_LOG_TABLE;
+
+BF_HD double exp_table(int j) {
+#if defined(__CUDA_ARCH__)
+  return __ldg(bf_exp_table_dev + j);
+#else
+  return bf_exp_table_host[j];
+#endif
+}
+BF_HD double log_table(int j) {
+#if defined(__CUDA_ARCH__)
+  return __ldg(bf_log_table_dev + j);
+#else
+  return bf_log_table_host[j];
+#endif
+}
+
+// e^x = 2^k 2^(j/64) e^r with x = (64 k + j) ln2 / 64 + r, |r| <= ln2 / 128: a 64-entry table and a degree-6 polynomial
+// (truncation r^7 / 5040 = 3e-20) instead of a degree-13 one -- 15 FP64 instructions.
 BF_HD double exp_bf(double x) {
   // NaN-preserving clamp (both comparisons are false for NaN)
   double xc = x < -745.2 ? -745.2 : (x > 709.7 ? 709.7 : x);
   const double magic = 6755399441055744.0;  // 1.5 * 2^52: rounds to nearest integer in the low word
-  double t = fma(xc, 1.4426950408889634, magic);
-  int k = lo_word(t);
+  double t = fma(xc, 92.332482616893657 /* 64 / ln 2 */, magic);
+  int ki = lo_word(t);
   double kd = t - magic;
-  double r = fma(kd, -6.93147180369123816490e-01, xc);
-  r = fma(kd, -1.90821492927058770002e-10, r);
-  // e^r, |r| <= ln2/2, Taylor to r^13 (truncation 4e-18), Estrin
-  double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
-  double a0 = 1.0 + r;
-  double a1 = fma(r, 1.0 / 6.0, 0.5);
-  double a2 = fma(r, 1.0 / 120.0, 1.0 / 24.0);
-  double a3 = fma(r, 1.0 / 5040.0, 1.0 / 720.0);
-  double a4 = fma(r, 1.0 / 362880.0, 1.0 / 40320.0);
-  double a5 = fma(r, 1.0 / 39916800.0, 1.0 / 3628800.0);
-  double a6 = fma(r, 1.0 / 6227020800.0, 1.0 / 479001600.0);
-  double b0 = fma(a1, r2, a0);
-  double b1 = fma(a3, r2, a2);
-  double b2 = fma(a5, r2, a4);
-  double c0 = fma(b1, r4, b0);
-  double c1 = fma(a6, r4, b2);
-  double p = fma(c1, r8, c0);
+  // ln2 / 64 in two pieces; the high one has 32 significant bits, so kd * hi is exact
+  double r = fma(kd, -6.93147180369123816490e-01 / 64.0, xc);
+  r = fma(kd, -1.90821492927058770002e-10 / 64.0, r);
+  double r2 = r * r;
+  double q = fma(r, 1.0 / 720.0, 1.0 / 120.0);
+  double u = fma(r, 1.0 / 6.0, 0.5);
+  q = fma(q, r, 1.0 / 24.0);
+  double p = fma(fma(q, r2, u), r2, r);   // e^r - 1
+  double tj = exp_table(ki & 63);
+  double v = fma(tj, p, tj);
   // 2^k in two normal factors so that results in the subnormal range round once
+  int k = ki >> 6;
   int k1 = k >> 1, k2 = k - k1;
   double s1 = make_double((k1 + 1023) << 20, 0), s2 = make_double((k2 + 1023) << 20, 0);
-  return (p * s1) * s2;
+  return (v * s1) * s2;
 }
 
+// log x = k ln 2 + log c + log1p(r), x = 2^k z, z in [0.6875, 1.375), r = z / c - 1 for the centre c of z's interval (128
+// intervals uniform in the bit pattern of z; table of 1 / c and log c), |r| <= 2^-7, degree-8 polynomial for log1p: 14
+// FP64 instructions.  Arguments in [1, 1 + 2^-7) have c = 1, r = z - 1 exactly: log_bf(1 + y) keeps full relative accuracy
+// for small y (the bridging forms need it); elsewhere the absolute error is ~1e-16 max(1, |log x|).
 BF_HD double log_bf(double x) {
   int hi = hi_word(x);
-  int k = (hi >> 20) - 1023;
-  double m = make_double((hi & 0x000fffff) | 0x3ff00000, lo_word(x));  // [1, 2)
-  bool big = m > 1.4142135623730951;
-  m = big ? 0.5 * m : m;                                             // [sqrt(1/2), sqrt(2)]
-  double kd = (double)(k + (big ? 1 : 0));
-  // f = (m - 1) / (m + 1) by a Newton-refined reciprocal and one residual correction
-  double d = m + 1.0, n = m - 1.0;
-  double y = rcp_seed(d);
-  double e = fma(-d, y, 1.0);
-  y = fma(y, e, y);
-  e = fma(-d, y, 1.0);
-  y = fma(y, e, y);
-  double f = n * y;
-  f = fma(fma(-d, f, n), y, f);
-  // log m = 2 atanh f = 2 f (1 + s/3 + s^2/5 + ... + s^10/21), s = f^2 <= 0.0295
-  double s = f * f, s2 = s * s, s4 = s2 * s2, s8 = s4 * s4;
-  double a0 = fma(s, 1.0 / 3.0, 1.0);
-  double a1 = fma(s, 1.0 / 7.0, 1.0 / 5.0);
-  double a2 = fma(s, 1.0 / 11.0, 1.0 / 9.0);
-  double a3 = fma(s, 1.0 / 15.0, 1.0 / 13.0);
-  double a4 = fma(s, 1.0 / 19.0, 1.0 / 17.0);
-  double b0 = fma(a1, s2, a0);
-  double b1 = fma(a3, s2, a2);
-  double c0 = fma(b1, s4, b0);
-  double c1 = fma(s2, 1.0 / 21.0, a4);
-  double p = fma(c1, s8, c0);
-  double res = fma(kd, 6.93147180369123816490e-01, fma(kd, 1.90821492927058770002e-10, 2.0 * f * p));
+  int tmp = hi - 0x3fe60000;
+  int i = (tmp >> 13) & 127;
+  int k = tmp >> 20;
+  double z = make_double(hi - (tmp & (int)0xfff00000), lo_word(x));
+  double invc = log_table(2 * i), logc = log_table(2 * i + 1);
+  double r = fma(z, invc, -1.0);
+  double kd = (double)k;
+  double r2 = r * r, r4 = r2 * r2;
+  // log1p(r) - r = r^2 (-1/2 + r/3 - r^2/4 + r^3/5 - r^4/6 + r^5/7 - r^6/8)
+  double a0 = fma(r, 1.0 / 3.0, -0.5);
+  double a1 = fma(r, 1.0 / 5.0, -0.25);
+  double a2 = fma(r, 1.0 / 7.0, -1.0 / 6.0);
+  double b0 = fma(a1, r2, a0);
+  double b1 = fma(r2, -0.125, a2);
+  double q = fma(b1, r4, b0);
+  double head = fma(kd, 6.93147180369123816490e-01, logc);
+  double tail = fma(kd, 1.90821492927058770002e-10, fma(q, r2, r));
+  double res = head + tail;
   return x != x ? x : res;
 }
 

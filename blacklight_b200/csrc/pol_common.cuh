@@ -522,20 +522,21 @@ __device__ __forceinline__ void couple(const RadParams &P, const Coefficients &C
   double delta_tau = al[0] * dl;
   bool thin = delta_tau <= 100.0;
   double alpha_sq = al[1] * al[1] + al[3] * al[3];
-  double alpha_p = sqrt(alpha_sq);
   double rho_sq = rho[1] * rho[1] + rho[3] * rho[3];
-  double rho_p = sqrt(rho_sq);
+  // the reference tests rho_p = sqrt(rho_sq) against zero: the same as testing rho_sq (the square root of a positive
+  // double is positive)
+  const bool no_rotation = rho_sq == 0.0;
   double out[4] = {0.0, 0.0, 0.0, 0.0};
   if (P.rotation_split) {
     // Strang splitting: half absorb/emit, full rotate, half absorb/emit
     couple_absorb(s, j, al, dl / 2.0, delta_tau / 2.0, thin, out);
     admissible(out, true);
     for (int a = 0; a < 4; a++) s[a] = out[a];
-    if (rho_p != 0.0) couple_rotate(s, rho, dl, out);
+    if (!no_rotation) couple_rotate(s, rho, dl, out);
     admissible(out, false);
     for (int a = 0; a < 4; a++) s[a] = out[a];
     couple_absorb(s, j, al, dl / 2.0, delta_tau / 2.0, thin, out);
-  } else if (rho_p == 0.0) {
+  } else if (no_rotation) {
     couple_absorb(s, j, al, dl, delta_tau, thin, out);
   } else if (al[0] == 0.0) {
     couple_rotate(s, rho, dl, out);

@@ -53,9 +53,7 @@ __device__ __forceinline__ double *field_ptr(const SplitArgs &X, int64_t rays, i
 }
 
 // ---- stage 1: geometry --------------------------------------------------------------------------------------
-// SYNC: the CTA's warps walk the slab in lock step (a barrier per sample), which keeps all four in the same stretch
-// of the ~5 k-instruction loop body and so in the instruction cache.
-template <int MINB, bool SYNC>
+template <int MINB>
 __global__ void __launch_bounds__(kBlock, MINB)
 pol_geometry_kernel(const __grid_constant__ RadArgs A, const __grid_constant__ RadParams P, const SplitArgs X) {
   extern __shared__ double smem_bounds[];
@@ -74,14 +72,12 @@ pol_geometry_kernel(const __grid_constant__ RadArgs A, const __grid_constant__ R
   const bool valid = m < A.rays;
   const int num = valid ? A.sample_num[m] : 0;
   unsigned long long processed = 0;
-  const bool active = num > X.n_lo;
-  if (active || SYNC) {
-    const bool flagged = active ? A.sample_flags[m] != 0 : false;
-    const double mom = active ? A.mom_factor[m] : 1.0;
-    const double k_t = active ? A.cam_dir[4 * m] : 0.0;
+  if (num > X.n_lo) {
+    const bool flagged = A.sample_flags[m] != 0;
+    const double mom = A.mom_factor[m];
+    const double k_t = A.cam_dir[4 * m];
     const int top = (X.n_hi < num ? X.n_hi : num) - 1;   // first sample of this slab in walking order
     const bool halo = X.n_hi < num;                        // the sample before it belongs to the previous slab
-    const int start = active ? (halo ? top + 1 : top) : -1;
     rad::CellCache cache = {0, 0, 0, 0};
     rad::SlowLight slow = {0, {0.0, 0.0, 0.0, 0.0}};
     KsJet jet_p;
@@ -90,11 +86,7 @@ pol_geometry_kernel(const __grid_constant__ RadArgs A, const __grid_constant__ R
     bool have_prev = false;
 
 #pragma unroll 1
-    for (int n = SYNC ? X.n_hi : start; n >= X.n_lo; n--) {
-      if (SYNC) {
-        __syncthreads();
-        if (n > start) continue;
-      }
+    for (int n = halo ? top + 1 : top; n >= X.n_lo; n--) {
       const bool store = n <= top;
       const double2 *src = reinterpret_cast<const double2 *>(A.sb.buf + A.sb.at(n, m));
       double2 r0 = __ldcs(src), r1 = __ldcs(src + 1), r2 = __ldcs(src + 2), r3 = __ldcs(src + 3);
@@ -185,7 +177,7 @@ pol_geometry_kernel(const __grid_constant__ RadArgs A, const __grid_constant__ R
       have_prev = true;
     }
 
-    if (X.n_lo == 0 && active) {
+    if (X.n_lo == 0) {
       // last half step of transport, then projection on the camera tetrad (polarized.cpp:816-833, :875-939)
       const double *cp = A.cam_pos + 4 * m, *cd = A.cam_dir + 4 * m;
       KsJet jc;
@@ -259,9 +251,7 @@ BL_FREQ_LOOP
 // ---- stage 3: transfer --------------------------------------------------------------------------------------
 // FW: frequencies per CTA (1, 2 or 4); the CTA's 128 threads are 128/FW adjacent rays x FW frequencies, so that a
 // warp is 32 adjacent rays at one frequency and the FW warps of a ray group share M through L1.
-// PF: the next sample's 19 inputs are loaded while the current one is coupled (the loads otherwise sit at the head of
-// a sequential dependency chain).
-template <int FW, int MINB, bool PF>
+template <int FW, int MINB>
 __global__ void __launch_bounds__(kBlock, MINB)
 pol_transfer_kernel(const __grid_constant__ RadArgs A, const __grid_constant__ RadParams P, const SplitArgs X) {
   constexpr int kRays = kBlock / FW;
@@ -283,33 +273,19 @@ pol_transfer_kernel(const __grid_constant__ RadArgs A, const __grid_constant__ R
   if (P.image_lambda) lam = img[(size_t)(P.off_lambda + l) * stride];
   if (P.image_emission) emi = img[(size_t)(P.off_emission + l) * stride];
 
-  double in[19];
-  auto load_inputs = [&](int n, double v[19]) {
+#pragma unroll 1
+  for (int n = top; n >= X.n_lo; n--) {
     const int j = n - X.n_lo;
     const double *lk = field_ptr(X, A.rays, kFieldM, j, m);
     const double *cf = field_ptr(X, A.rays, kFieldCoef + 8 * l, j, m);
+    double mm[10];
 #pragma unroll
-    for (int q = 0; q < 11; q++) v[q] = __ldg(lk + q * fs);
-#pragma unroll
-    for (int q = 0; q < 8; q++) v[11 + q] = __ldcs(cf + q * fs);
-  };
-  if (PF) load_inputs(top, in);
-#pragma unroll 1
-  for (int n = top; n >= X.n_lo; n--) {
-    double cur[19];
-    if (PF) {
-#pragma unroll
-      for (int q = 0; q < 19; q++) cur[q] = in[q];
-      if (n > X.n_lo) load_inputs(n - 1, in);
-    } else {
-      load_inputs(n, cur);
-    }
-    const double *mm = cur;
-    const double dlam = cur[10];
+    for (int q = 0; q < 10; q++) mm[q] = __ldg(lk + q * fs);
+    const double dlam = __ldg(lk + 10 * fs);
     Coefficients C;
-    C.j[0] = cur[11]; C.j[1] = cur[12]; C.j[2] = cur[13];
-    C.a[0] = cur[14]; C.a[1] = cur[15]; C.a[2] = cur[16];
-    C.rho[0] = cur[17]; C.rho[1] = cur[18];
+    C.j[0] = __ldcs(cf); C.j[1] = __ldcs(cf + fs); C.j[2] = __ldcs(cf + 2 * fs);
+    C.a[0] = __ldcs(cf + 3 * fs); C.a[1] = __ldcs(cf + 4 * fs); C.a[2] = __ldcs(cf + 5 * fs);
+    C.rho[0] = __ldcs(cf + 6 * fs); C.rho[1] = __ldcs(cf + 7 * fs);
     const double dl_cgs = dlam * dl_factor;
     double t0 = mm[0] * s[0] + mm[1] * s[1] + mm[2] * s[2];
     double t1 = mm[3] * s[0] + mm[4] * s[1] + mm[5] * s[2];
@@ -345,20 +321,20 @@ void launch_coefficients(int dist, dim3 grid, cudaStream_t stream, const RadArgs
   else pol_coefficient_kernel<7, MINB><<<grid, kBlock, 0, stream>>>(A, P, X);
 }
 
-template <int MINB, bool PF>
+template <int MINB>
 void launch_transfer(int fw, dim3 grid, cudaStream_t stream, const RadArgs &A, const RadParams &P, const SplitArgs &X) {
-  if (fw == 4) pol_transfer_kernel<4, MINB, PF><<<grid, kBlock, 0, stream>>>(A, P, X);
-  else if (fw == 2) pol_transfer_kernel<2, MINB, PF><<<grid, kBlock, 0, stream>>>(A, P, X);
-  else pol_transfer_kernel<1, MINB, PF><<<grid, kBlock, 0, stream>>>(A, P, X);
+  if (fw == 4) pol_transfer_kernel<4, MINB><<<grid, kBlock, 0, stream>>>(A, P, X);
+  else if (fw == 2) pol_transfer_kernel<2, MINB><<<grid, kBlock, 0, stream>>>(A, P, X);
+  else pol_transfer_kernel<1, MINB><<<grid, kBlock, 0, stream>>>(A, P, X);
 }
 
 // Resident CTAs per SM each stage is register-capped for.  The defaults are the measured best on B200; the
 // environment variables exist for re-tuning (BL_POL_OCC="g,c,t").
-struct Occupancy { int g, c, t, gsync, tpf; };
+struct Occupancy { int g, c, t; };
 Occupancy stage_occupancy() {
   static Occupancy occ = [] {
-    Occupancy o = {3, 4, 5, 0, 0};
-    if (const char *e = getenv("BL_POL_OCC")) sscanf(e, "%d,%d,%d,%d,%d", &o.g, &o.c, &o.t, &o.gsync, &o.tpf);
+    Occupancy o = {3, 4, 5};
+    if (const char *e = getenv("BL_POL_OCC")) sscanf(e, "%d,%d,%d", &o.g, &o.c, &o.t);
     return o;
   }();
   return occ;
@@ -395,25 +371,20 @@ extern "C" cudaError_t bl_launch_radiate_polarized_split(const RadArgs *args, co
     SplitArgs X;
     X.scratch = scratch; X.cam_map = cam_map; X.slab = slab;
     X.n_lo = n_hi - slab; X.n_hi = n_hi < s_top ? n_hi : s_top;
-    if (occ.g == 3 && occ.gsync) pol_geometry_kernel<3, true><<<ray_blocks, kBlock, smem, stream>>>(A, P, X);
-    else if (occ.g == 3) pol_geometry_kernel<3, false><<<ray_blocks, kBlock, smem, stream>>>(A, P, X);
-    else if (occ.g == 4) pol_geometry_kernel<4, false><<<ray_blocks, kBlock, smem, stream>>>(A, P, X);
-    else if (occ.gsync) pol_geometry_kernel<2, true><<<ray_blocks, kBlock, smem, stream>>>(A, P, X);
-    else pol_geometry_kernel<2, false><<<ray_blocks, kBlock, smem, stream>>>(A, P, X);
+    if (occ.g == 2) pol_geometry_kernel<2><<<ray_blocks, kBlock, smem, stream>>>(A, P, X);
+    else if (occ.g == 4) pol_geometry_kernel<4><<<ray_blocks, kBlock, smem, stream>>>(A, P, X);
+    else pol_geometry_kernel<3><<<ray_blocks, kBlock, smem, stream>>>(A, P, X);
     if (events) cudaEventRecord(events[ev++], stream);
     dim3 cgrid(ray_blocks, (unsigned)(X.n_hi - X.n_lo));
     if (occ.c == 3) launch_coefficients<3>(dist, cgrid, stream, A, P, X);
     else if (occ.c == 5) launch_coefficients<5>(dist, cgrid, stream, A, P, X);
-    else if (occ.c == 6) launch_coefficients<6>(dist, cgrid, stream, A, P, X);
     else launch_coefficients<4>(dist, cgrid, stream, A, P, X);
     if (events) cudaEventRecord(events[ev++], stream);
     dim3 tgrid((unsigned)((A.rays + kBlock / fw - 1) / (kBlock / fw)), (unsigned)((F + fw - 1) / fw));
-    if (occ.t == 3) launch_transfer<3, false>(fw, tgrid, stream, A, P, X);
-    else if (occ.t == 5 && occ.tpf) launch_transfer<5, true>(fw, tgrid, stream, A, P, X);
-    else if (occ.t == 5) launch_transfer<5, false>(fw, tgrid, stream, A, P, X);
-    else if (occ.t == 6) launch_transfer<6, false>(fw, tgrid, stream, A, P, X);
-    else if (occ.tpf) launch_transfer<4, true>(fw, tgrid, stream, A, P, X);
-    else launch_transfer<4, false>(fw, tgrid, stream, A, P, X);
+    if (occ.t == 3) launch_transfer<3>(fw, tgrid, stream, A, P, X);
+    else if (occ.t == 4) launch_transfer<4>(fw, tgrid, stream, A, P, X);
+    else if (occ.t == 6) launch_transfer<6>(fw, tgrid, stream, A, P, X);
+    else launch_transfer<5>(fw, tgrid, stream, A, P, X);
     if (events) cudaEventRecord(events[ev++], stream);
     if (launches) *launches += 3;
     cudaError_t e = cudaGetLastError();
