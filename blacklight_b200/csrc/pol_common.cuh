@@ -84,34 +84,38 @@ __device__ __forceinline__ void raise(const KsJet &J, const double v[4], double 
 // A^mu_beta = k^alpha Gamma^mu_{alpha beta} for the Kerr-Schild connection (radiation_geometry.cpp:274-410),
 // without forming Gamma:  A = 1/2 g^{mu nu} (k.d g_{beta nu} + k^alpha d_beta g_{alpha nu} - k^alpha d_nu g_{alpha beta}).
 __device__ __forceinline__ void contracted_connection(const KsJet &J, const double k[4], double A[4][4]) {
-  const double lc[4] = {1.0, J.l[0], J.l[1], J.l[2]};   // l_mu
-  double kf = k[1] * J.df[0] + k[2] * J.df[1] + k[3] * J.df[2];          // k.grad f
-  double kl[4] = {0.0, 0.0, 0.0, 0.0};                                    // k.grad l_beta
-  double m[4] = {0.0, 0.0, 0.0, 0.0};                                     // k^alpha d_beta l_alpha
-  for (int i = 0; i < 3; i++) {
-    kl[1 + i] = k[1] * J.dl[i][0] + k[2] * J.dl[i][1] + k[3] * J.dl[i][2];
-    m[1 + i] = k[1] * J.dl[0][i] + k[2] * J.dl[1][i] + k[3] * J.dl[2][i];
-  }
-  double lk = k[0] + J.l[0] * k[1] + J.l[1] * k[2] + J.l[2] * k[3];      // l_alpha k^alpha
-  double dfc[4] = {0.0, J.df[0], J.df[1], J.df[2]};
+  // W_{beta nu} = k.d g_{beta nu} + k^alpha d_beta g_{alpha nu} - k^alpha d_nu g_{alpha beta} written out for
+  // g = eta + f l l with l_0 = 1 and nothing depending on time: with
+  //   u_i = (k.grad f) l_i + f k.grad l_i,   v_i = d_i f (l.k) + f k^j d_i l_j,
+  // W_00 = k.grad f,  W_0j = u_j - v_j,  W_i0 = u_i + v_i,
+  // W_ij = W_i0 l_j + l_i (f k.grad l_j - v_j) + f (l.k) (d_i l_j - d_j l_i)
+  // (the products with the vanishing time components are dropped instead of being multiplied out).
+  const double kf = k[1] * J.df[0] + k[2] * J.df[1] + k[3] * J.df[2];
+  const double lk = k[0] + J.l[0] * k[1] + J.l[1] * k[2] + J.l[2] * k[3];
+  const double g = J.f * lk;
   double W[4][4];
-  for (int b = 0; b < 4; b++)
-    for (int n = 0; n < 4; n++) {
-      double dl_nb = (n > 0 && b > 0) ? J.dl[n - 1][b - 1] : 0.0;   // d_b l_n
-      double dl_bn = (n > 0 && b > 0) ? J.dl[b - 1][n - 1] : 0.0;   // d_n l_b
-      double s1 = kf * lc[b] * lc[n] + J.f * (kl[b] * lc[n] + lc[b] * kl[n]);
-      double t_bn = dfc[b] * lk * lc[n] + J.f * (m[b] * lc[n] + lk * dl_nb);
-      double t_nb = dfc[n] * lk * lc[b] + J.f * (m[n] * lc[b] + lk * dl_bn);
-      W[b][n] = s1 + t_bn - t_nb;
-    }
-  const double lu[4] = {-1.0, J.l[0], J.l[1], J.l[2]};  // l^mu
+  double q[3];
+  W[0][0] = kf;
+  for (int i = 0; i < 3; i++) {
+    const double kl = k[1] * J.dl[i][0] + k[2] * J.dl[i][1] + k[3] * J.dl[i][2];   // k.grad l_i
+    const double m = k[1] * J.dl[0][i] + k[2] * J.dl[1][i] + k[3] * J.dl[2][i];    // k^j d_i l_j
+    const double fkl = J.f * kl;
+    const double u = kf * J.l[i] + fkl, v = J.df[i] * lk + J.f * m;
+    W[0][1 + i] = u - v;
+    W[1 + i][0] = u + v;
+    q[i] = fkl - v;
+  }
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++)
+      W[1 + i][1 + j] = W[1 + i][0] * J.l[j] + J.l[i] * q[j] + g * (J.dl[j][i] - J.dl[i][j]);
+  // A^mu_beta = 1/2 g^{mu nu} W_{beta nu},  g^{mu nu} = eta - f l^mu l^nu,  l^mu = (-1, l_i)
   for (int b = 0; b < 4; b++) {
-    double lw = lu[0] * W[b][0] + lu[1] * W[b][1] + lu[2] * W[b][2] + lu[3] * W[b][3];
-    double s = J.f * lw;
-    A[0][b] = 0.5 * (-W[b][0] - s * lu[0]);
-    A[1][b] = 0.5 * (W[b][1] - s * lu[1]);
-    A[2][b] = 0.5 * (W[b][2] - s * lu[2]);
-    A[3][b] = 0.5 * (W[b][3] - s * lu[3]);
+    const double lw = J.l[0] * W[b][1] + J.l[1] * W[b][2] + J.l[2] * W[b][3] - W[b][0];
+    const double s = J.f * lw;
+    A[0][b] = 0.5 * (s - W[b][0]);
+    A[1][b] = 0.5 * (W[b][1] - s * J.l[0]);
+    A[2][b] = 0.5 * (W[b][2] - s * J.l[1]);
+    A[3][b] = 0.5 * (W[b][3] - s * J.l[2]);
   }
 }
 
