@@ -257,10 +257,11 @@ def test_live_reference_cartesian_kerr_schild(over, gpu, tmp_path):
         assert np.array_equal(t['inds'][valid], ri[valid])
         check_images(mine, ref['npz'], str(over))
     else:
-        # In this synthetic box the left-edge pixels are 1e-7 ... 1e-11 of the peak brightness; there the two
-        # polarized solvers agree only to 1e-7 ... 1e-2 of the (negligible) pixel value, while the unpolarized
-        # images agree to 1e-14 everywhere and the polarized ones to 1e-11 (median).  Open item (DESIGN.md
-        # section 3.2); the comparison is restricted to pixels above 1e-6 of the peak.
+        # In this synthetic box a few left-edge pixels are 1e-8 ... 1e-10 of the peak brightness: their rays cross the
+        # dense midplane in 3-unit cells with optical depths of tens per step, where the reference's closed-form step
+        # amplifies round-off to 1e-6 ... 1e-4 of the pixel value (measured against an 80-bit evaluation of the same
+        # recurrence in test_cks_polarized_faint_pixels_are_roundoff_limited, which checks EVERY pixel against that
+        # per-pixel bound).  Here the plain 1e-6 bound is applied to the pixels above 1e-6 of the peak.
         I_ref = ref['npz']['I_nu']
         bright = I_ref >= 1e-6 * np.nanmax(I_ref)
         assert bright.sum() > 0.5 * bright.size
