@@ -83,6 +83,7 @@ def load_library():
         'blh_camera_root': (i64, [vp, vp, vp, vp]),
         'blh_camera_refined': (i64, [vp, i32, vp, vp, i64, vp, vp, vp, vp]),
         'blh_run_input_file': (i32, [ctypes.c_char_p, i32, i32, vp]),
+        'blh_crc32': (ctypes.c_uint32, [vp, ctypes.c_uint64]),
         'blh_camera_rows': (i64, [vp, vp, i64, vp, vp, vp]),
         'blh_run_input_file_devices': (i32, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_int), i32, i32, vp]),
         'bl_device_count': (i32, []),

@@ -52,6 +52,11 @@ struct Level {
   double *image = nullptr;    // device (Q, rays)
   double *render = nullptr;   // device (R,3,rays)
   // three-stage polarized pipeline (radiate_pol_split.cu): slab scratch and the camera half-step map of one wave
+  // deferred emission of the DP integrator (geodesic_dp.cu): step records of one wave
+  double *defer_rec = nullptr;     // device (defer_cap, kDeferFields, wave_rays)
+  int32_t *defer_count = nullptr;  // device (wave_rays)
+  int32_t *defer_trunc = nullptr;  // device (wave_rays)
+  int32_t defer_cap = 0;
   double *scratch = nullptr;  // device (fields, slab, wave_rays)
   double *cam_map = nullptr;  // device (10, wave_rays)
   int32_t slab = 0;           // samples per slab; 0 = the level uses the fused kernel
@@ -84,6 +89,10 @@ struct bl_ctx {
   long long launches = 0;   // kernels of ours launched so far
   int geo_min_blocks = 3;   // occupancy variant of the DP kernel (BL_GEO_BLOCKS overrides, tuning only)
   std::vector<cudaEvent_t> stage_events;   // per-launch events of the three-stage polarized pipeline
+  int geo_defer = -1;       // BL_GEO_DEFER: step records per ray for deferred emission (-1 = ray_max_steps / 20 in [64, 384], 0 = off)
+  int geo_defer_min = 3;    // BL_GEO_DEFER_MIN: accepted steps cut into at least this many pieces are deferred
+  int geo_cta_sync = 1;     // BL_GEO_SYNC: barrier per DP step attempt (instruction-cache locality against warp independence)
+  int rad_prefetch = 2;     // BL_RAD_PREFETCH: samples ahead the radiation kernels prefetch step-buffer records into L2 (0 = off)
   int pol_slab = 0;         // BL_POL_SLAB: samples per slab of that pipeline (0 = chosen from the HBM budget)
   bool pol_fused = false;   // BL_POL_FUSED=1: keep the single fused polarized kernel (A/B comparisons, parity cross-check)
 };
@@ -115,6 +124,7 @@ cudaError_t dev_alloc(T **p, size_t count) {
 void free_level(Level &L) {
   cudaFree(L.cam_pos); cudaFree(L.cam_dir); cudaFree(L.mom); cudaFree(L.num); cudaFree(L.flags);
   cudaFree(L.step); cudaFree(L.image); cudaFree(L.render); cudaFree(L.scratch); cudaFree(L.cam_map);
+  cudaFree(L.defer_rec); cudaFree(L.defer_count); cudaFree(L.defer_trunc);
   cudaFree(L.tap_inds); cudaFree(L.tap_fracs); cudaFree(L.tap_nan); cudaFree(L.tap_cut); cudaFree(L.tap_fb);
   L = Level();
 }
@@ -394,6 +404,10 @@ int bl_create(const bl_params *params, bl_ctx **out) {
   ctx->levels.resize((size_t)params->adaptive_max_level + 1);
   if (const char *e = getenv("BL_GEO_BLOCKS")) ctx->geo_min_blocks = atoi(e);
   if (const char *e = getenv("BL_POL_SLAB")) ctx->pol_slab = atoi(e);
+  if (const char *e = getenv("BL_RAD_PREFETCH")) ctx->rad_prefetch = atoi(e);
+  if (const char *e = getenv("BL_GEO_SYNC")) ctx->geo_cta_sync = atoi(e);
+  if (const char *e = getenv("BL_GEO_DEFER")) ctx->geo_defer = atoi(e);
+  if (const char *e = getenv("BL_GEO_DEFER_MIN")) ctx->geo_defer_min = atoi(e) < 2 ? 2 : atoi(e);
   if (const char *e = getenv("BL_POL_FUSED")) ctx->pol_fused = atoi(e) != 0;
 #define CREATE_CHECK(call)                                                                   \
   do {                                                                                       \
@@ -753,6 +767,18 @@ int pol_split_slab(const bl_ctx *ctx, int64_t num_rays, size_t budget, size_t *b
   return slab;
 }
 
+// Step records per ray for the DP integrator's deferred emission, and their bytes per ray.
+int geo_defer_cap(const bl_ctx *ctx, size_t *bytes_per_ray) {
+  *bytes_per_ray = 0;
+  if (ctx->params.ray_integrator != BL_INTEGRATOR_DP || ctx->geo_defer == 0) return 0;
+  int cap = ctx->geo_defer > 0 ? ctx->geo_defer : ctx->params.ray_max_steps / 20;
+  if (ctx->geo_defer < 0) cap = cap < 64 ? 64 : (cap > 384 ? 384 : cap);
+  *bytes_per_ray = (size_t)cap * GeoArgs::kDeferFields * sizeof(double) + 2 * sizeof(int32_t);
+  return cap;
+}
+
+int alloc_defer(bl_ctx *ctx, Level &L, int cap);
+
 // Trace rays [first, first+count) of a level into L.step (one wave).
 int trace_wave(bl_ctx *ctx, Level &L, int64_t first, int64_t count) {
   const bl_params &p = ctx->params;
@@ -767,10 +793,18 @@ int trace_wave(bl_ctx *ctx, Level &L, int64_t first, int64_t count) {
   g.sample_num = L.num + first;
   g.sample_flags = L.flags + first;
   g.counters = ctx->counters;
+  g.cta_sync = ctx->geo_cta_sync;
+  g.defer_rec = L.defer_rec;
+  g.defer_count = L.defer_count;
+  g.trunc = L.defer_trunc;
+  g.defer_cap = L.defer_cap;
+  g.defer_min = ctx->geo_defer_min;
   BL_CUDA_CHECK(cudaMemsetAsync(&ctx->counters->next_ray, 0, sizeof(unsigned long long), ctx->stream));
   if (p.ray_integrator == BL_INTEGRATOR_DP)
+  {
     BL_CUDA_CHECK(bl_launch_geodesic_dp(&g, p.ray_flat, ctx->sm_count, ctx->geo_min_blocks, ctx->stream));
-  else
+    if (g.defer_rec) ctx->launches++;
+  } else
     BL_CUDA_CHECK(bl_launch_geodesic_rk(&g, p.ray_flat, p.ray_integrator == BL_INTEGRATOR_RK4 ? 4 : 2, ctx->sm_count, ctx->stream));
   ctx->launches++;
   return BL_OK;
@@ -806,6 +840,7 @@ int radiate_wave(bl_ctx *ctx, Level &L, int64_t first, int64_t count, int s_top,
   A.image_stride = L.rays;
   A.render = L.render ? L.render + first : nullptr;
   A.sample_counter = ctx->rad_counter;
+  A.prefetch = ctx->rad_prefetch;
   A.slow_counters = ctx->rad.slow_light ? ctx->slow_counters : nullptr;
   if (L.tap_nan) {
     size_t o = (size_t)first * L.tap_S;
@@ -851,6 +886,15 @@ int collect_stage_times(bl_ctx *ctx, Level &L, int slabs) {
     BL_CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->stage_events[k], ctx->stage_events[k + 1]));
     L.ms_stage[k % 3] += ms;
   }
+  return BL_OK;
+}
+
+int alloc_defer(bl_ctx *ctx, Level &L, int cap) {
+  L.defer_cap = cap;
+  if (cap <= 0) return BL_OK;
+  BL_CUDA_CHECK(dev_alloc(&L.defer_rec, (size_t)L.wave_rays * (size_t)cap * GeoArgs::kDeferFields));
+  BL_CUDA_CHECK(dev_alloc(&L.defer_count, (size_t)L.wave_rays));
+  BL_CUDA_CHECK(dev_alloc(&L.defer_trunc, (size_t)L.wave_rays));
   return BL_OK;
 }
 
@@ -910,6 +954,9 @@ int bl_trace_level(bl_ctx *ctx, int level, const double *cam_pos, const double *
     size_t budget = (size_t)((double)fr * 0.80);
     size_t per_ray_split = 0;
     const int slab = pol_split_slab(ctx, num_rays, budget, &per_ray_split);
+    size_t per_ray_defer = 0;
+    const int defer_cap = geo_defer_cap(ctx, &per_ray_defer);
+    per_ray_split += per_ray_defer;
     int64_t fit = (int64_t)(budget / (per_ray + per_ray_split));
     if (fit < 128) {
       free_level(L);
@@ -931,6 +978,8 @@ int bl_trace_level(bl_ctx *ctx, int level, const double *cam_pos, const double *
     }
     BL_CUDA_CHECK(dev_alloc(&L.step, (size_t)L.wave_rays * per_ray / sizeof(double)));
     int rc = alloc_split_scratch(ctx, L, slab);
+    if (rc) return rc;
+    rc = alloc_defer(ctx, L, defer_cap);
     if (rc) return rc;
   }
   BL_CUDA_CHECK(cudaMemsetAsync(ctx->counters, 0, sizeof(GeoCounters), ctx->stream));

@@ -40,6 +40,16 @@ struct GeoArgs {
   int32_t *sample_num;   // (rays)
   uint8_t *sample_flags; // (rays)
   GeoCounters *counters;
+  int32_t cta_sync;      // DP kernel: barrier per step attempt (see geodesic_dp.cu)
+  // Deferred emission (DP kernel): an accepted step that is cut into defer_min or more stored pieces leaves a record
+  // (kDeferFields doubles: start state, quartic coefficients, piece length and counts) instead of storing the pieces
+  // itself; geodesic_emit_kernel evaluates them afterwards.  rec[(k * kDeferFields + f) * rays + m], k < defer_count[m].
+  double *defer_rec;     // nullptr: every piece is stored by the integrator
+  int32_t *defer_count;  // (rays)
+  int32_t *trunc;        // (rays) first truncated sample index found so far, INT_MAX if none
+  int32_t defer_cap;     // records per ray
+  int32_t defer_min;
+  static constexpr int kDeferFields = 41;
 };
 
 #define BL_CUDA_CHECK(call)                                                        \

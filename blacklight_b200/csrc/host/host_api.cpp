@@ -9,6 +9,7 @@
 
 #include "config.hpp"
 #include "driver.hpp"
+#include "npz_writer.hpp"
 #include "snapshot.hpp"
 
 struct blh_config {
@@ -162,6 +163,8 @@ int blh_run_input_file(const char *path, int device, int quiet, double timings[1
     return fail(e);
   }
 }
+
+uint32_t blh_crc32(const void *data, uint64_t bytes) { return blh::crc32(static_cast<const uint8_t *>(data), (size_t)bytes); }
 
 int blh_run_input_file_devices(const char *path, const int *devices, int num_devices, int quiet, double timings[12]) {
   if (!path || !devices || num_devices <= 0) { g_error = "bad argument"; return 1; }

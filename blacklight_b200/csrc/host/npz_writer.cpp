@@ -61,9 +61,10 @@ void put(std::vector<uint8_t> &v, T x) {
 
 }  // namespace
 
-uint32_t crc32(const uint8_t *p, size_t n) {
+namespace {
+
+uint32_t crc32_update(uint32_t c, const uint8_t *p, size_t n) {
   static const CrcTables T;
-  uint32_t c = 0xffffffffu;
   while (n >= 8) {
     uint32_t lo, hi;
     std::memcpy(&lo, p, 4);
@@ -75,7 +76,63 @@ uint32_t crc32(const uint8_t *p, size_t n) {
     n -= 8;
   }
   while (n--) c = T.t[0][(c ^ *p++) & 0xff] ^ (c >> 8);
-  return c ^ 0xffffffffu;
+  return c;
+}
+
+// CRC of a concatenation from the CRCs of its parts: crc(A || B) = shift(crc(A), 8 |B| zero bits) ^ crc(B), the shift
+// being multiplication by x^(8 |B|) modulo the CRC polynomial, done as a 32 x 32 bit matrix over GF(2) raised to that
+// power by repeated squaring (the construction zlib's crc32_combine uses).
+uint32_t gf2_times(const uint32_t *mat, uint32_t vec) {
+  uint32_t sum = 0;
+  for (int i = 0; vec; vec >>= 1, i++)
+    if (vec & 1) sum ^= mat[i];
+  return sum;
+}
+void gf2_square(uint32_t *square, const uint32_t *mat) {
+  for (int n = 0; n < 32; n++) square[n] = gf2_times(mat, mat[n]);
+}
+uint32_t crc32_concat(uint32_t crc_a, uint32_t crc_b, size_t len_b) {
+  if (len_b == 0) return crc_a;
+  uint32_t even[32], odd[32];
+  odd[0] = 0xedb88320u;   // one zero bit
+  uint32_t row = 1;
+  for (int n = 1; n < 32; n++) {
+    odd[n] = row;
+    row <<= 1;
+  }
+  gf2_square(even, odd);   // two zero bits
+  gf2_square(odd, even);   // four
+  do {                      // first pass: one zero byte (eight zero bits), then squares of it
+    gf2_square(even, odd);
+    if (len_b & 1) crc_a = gf2_times(even, crc_a);
+    len_b >>= 1;
+    if (len_b == 0) break;
+    gf2_square(odd, even);
+    if (len_b & 1) crc_a = gf2_times(odd, crc_a);
+    len_b >>= 1;
+  } while (len_b != 0);
+  return crc_a ^ crc_b;
+}
+
+}  // namespace
+
+// A 4096^2 multi-frequency frame is gigabytes of payload: the chunks are summed on all host threads and combined.
+uint32_t crc32(const uint8_t *p, size_t n) {
+  const size_t chunk = (size_t)4 << 20;
+  if (n < 2 * chunk) return crc32_update(0xffffffffu, p, n) ^ 0xffffffffu;
+  const size_t parts = (n + chunk - 1) / chunk;
+  std::vector<uint32_t> crc(parts);
+#pragma omp parallel for schedule(static)
+  for (long long i = 0; i < (long long)parts; i++) {
+    const size_t at = (size_t)i * chunk, len = at + chunk <= n ? chunk : n - at;
+    crc[(size_t)i] = crc32_update(0xffffffffu, p + at, len) ^ 0xffffffffu;
+  }
+  uint32_t total = crc[0];
+  for (size_t i = 1; i < parts; i++) {
+    const size_t at = i * chunk, len = at + chunk <= n ? chunk : n - at;
+    total = crc32_concat(total, crc[i], len);
+  }
+  return total;
 }
 
 std::vector<uint8_t> npy_bytes(const double *data, const std::vector<int> &shape) {

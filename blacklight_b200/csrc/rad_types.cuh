@@ -166,6 +166,7 @@ struct RadArgs {
   double *render;               // (R, 3, level_rays) or nullptr, offset likewise
   SampleTaps taps;              // pointers already offset to this wave's first ray
   unsigned long long *sample_counter;  // processed (ray, sample) pairs, for roofline accounting
+  int32_t prefetch;             // step-buffer records are prefetched this many samples ahead into L2 (0 = off)
   unsigned long long *slow_counters;   // [0..3] pixels extrapolating (camera small, camera large, source small,
                                        // source large), [4..7] the largest extrapolations as double bits; or nullptr
 };

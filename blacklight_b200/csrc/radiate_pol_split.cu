@@ -89,7 +89,8 @@ pol_geometry_kernel(const __grid_constant__ RadArgs A, const __grid_constant__ R
     for (int n = halo ? top + 1 : top; n >= X.n_lo; n--) {
       const bool store = n <= top;
       const double2 *src = reinterpret_cast<const double2 *>(A.sb.buf + A.sb.at(n, m));
-      double2 r0 = __ldcs(src), r1 = __ldcs(src + 1), r2 = __ldcs(src + 2), r3 = __ldcs(src + 3);
+      rad::prefetch_record(A.sb, n, m, A.prefetch);
+    double2 r0 = __ldcs(src), r1 = __ldcs(src + 1), r2 = __ldcs(src + 2), r3 = __ldcs(src + 3);
       double t = r0.x, x = r0.y, y = r1.x, z = r1.y;
       double kc[4] = {k_t, r2.x, r2.y, r3.x};
       double dlam = -r3.y;
@@ -236,12 +237,12 @@ pol_coefficient_kernel(const __grid_constant__ RadArgs A, const __grid_constant_
   }
   PolSample sq;
   pol_sample<DIST>(P, s, om, sin_b, cos_b, kk, sq);
+  const size_t fs = (size_t)X.slab * (size_t)A.rays;   // distance between consecutive fields
 BL_FREQ_LOOP
   for (int l = 0; l < F; l++) {
     Coefficients C;
     synchrotron_polarized<DIST>(P, sq, l, C);
     double *dst = field_ptr(X, A.rays, kFieldCoef + 8 * l, j, m);
-    const size_t fs = (size_t)X.slab * (size_t)A.rays;   // distance between consecutive fields
     __stcs(dst, C.j[0]); __stcs(dst + fs, C.j[1]); __stcs(dst + 2 * fs, C.j[2]);
     __stcs(dst + 3 * fs, C.a[0]); __stcs(dst + 4 * fs, C.a[1]); __stcs(dst + 5 * fs, C.a[2]);
     __stcs(dst + 6 * fs, C.rho[0]); __stcs(dst + 7 * fs, C.rho[1]);
@@ -333,7 +334,7 @@ void launch_transfer(int fw, dim3 grid, cudaStream_t stream, const RadArgs &A, c
 struct Occupancy { int g, c, t; };
 Occupancy stage_occupancy() {
   static Occupancy occ = [] {
-    Occupancy o = {3, 4, 5};
+    Occupancy o = {3, 0, 5};   // coefficient stage: 0 = by electron distribution
     if (const char *e = getenv("BL_POL_OCC")) sscanf(e, "%d,%d,%d", &o.g, &o.c, &o.t);
     return o;
   }();
@@ -376,8 +377,11 @@ extern "C" cudaError_t bl_launch_radiate_polarized_split(const RadArgs *args, co
     else pol_geometry_kernel<3><<<ray_blocks, kBlock, smem, stream>>>(A, P, X);
     if (events) cudaEventRecord(events[ev++], stream);
     dim3 cgrid(ray_blocks, (unsigned)(X.n_hi - X.n_lo));
-    if (occ.c == 3) launch_coefficients<3>(dist, cgrid, stream, A, P, X);
-    else if (occ.c == 5) launch_coefficients<5>(dist, cgrid, stream, A, P, X);
+    // the thermal-only coefficient code is light enough for five CTAs per SM (58 -> 51 ms per 1024^2 frame)
+    const int occ_c = occ.c > 0 ? occ.c : (dist == 1 ? 5 : 4);
+    if (occ_c == 3) launch_coefficients<3>(dist, cgrid, stream, A, P, X);
+    else if (occ_c == 5) launch_coefficients<5>(dist, cgrid, stream, A, P, X);
+    else if (occ_c == 6) launch_coefficients<6>(dist, cgrid, stream, A, P, X);
     else launch_coefficients<4>(dist, cgrid, stream, A, P, X);
     if (events) cudaEventRecord(events[ev++], stream);
     dim3 tgrid((unsigned)((A.rays + kBlock / fw - 1) / (kBlock / fw)), (unsigned)((F + fw - 1) / fw));

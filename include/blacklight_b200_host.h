@@ -55,6 +55,10 @@ int blh_snapshot_reread(blh_snapshot *snap, const char *file);
 int blh_snapshot_view(const blh_snapshot *snap, bl_grid_view *view, double *time, double *plasma_gamma);
 void blh_snapshot_free(blh_snapshot *snap);
 
+/* CRC-32 (IEEE 802.3, as zip / zlib) of a host buffer, the npz writer's checksum (the reference's is a byte-at-a-time loop,
+ * zip_format.cpp:289-362): slice-by-8 per chunk on all host threads, chunk sums combined in GF(2). */
+uint32_t blh_crc32(const void *data, uint64_t bytes);
+
 int blh_run_input_file(const char *path, int device, int quiet, double timings[12]);
 /* The same run spread over several GPUs of the node from this one process (the reference parallelises inside main too,
  * blacklight.cpp:77): one context and one host thread per listed CUDA device, the image rows -- refinement blocks for

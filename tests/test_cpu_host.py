@@ -352,6 +352,17 @@ def test_time_series_reread_equals_fresh_read(fmt, tmp_path):
         assert np.array_equal(again[k], fresh[k]), k
 
 
+def test_parallel_crc32_equals_zlib():
+    """The npz writer's CRC-32 (chunks on all host threads, combined in GF(2)) against zlib, across the serial / parallel
+    threshold and with ragged tails."""
+    import zlib
+    lib = bl.load_library()
+    rng = np.random.default_rng(11)
+    for n in (0, 1, 7, 4096, (8 << 20) - 1, (8 << 20) + 5, 37 * (1 << 20) + 123):
+        buf = rng.integers(0, 256, n, dtype=np.uint8)
+        assert lib.blh_crc32(buf.ctypes.data, n) == (zlib.crc32(buf.tobytes()) & 0xffffffff), n
+
+
 def test_camera_rows_equal_the_rows_of_the_full_camera(tmp_path):
     """blh_camera_rows (a device's share of the frame in the multi-GPU driver) is bit for bit the same rows of
     blh_camera_root, plane and pinhole cameras."""
