@@ -85,6 +85,8 @@ def parse_args():
                     help='refine the mock snapshot by this factor per dimension (4: 308x256x512 cells, 1.3 GB of primitives -- '
                          'the gather leaves L2 and becomes HBM traffic; SURVEY.md section 8d)')
     ap.add_argument('--cpu-resolution', type=int, default=0, help='side of the bounded CPU sample (0 = auto)')
+    ap.add_argument('--e2e-budget-s', type=float, default=60.0,
+                    help='the end-to-end leg runs over min(steps, budget / seconds per pass) passes, at least 3')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-extras', action='store_true', help='only the main workload (no `extra` lines)')
     ap.add_argument('--dump-units', default='', help='write the unit counts of the main workload (for tools/ncu_flops_json.py)')
@@ -412,11 +414,24 @@ def measure(args, name, resolution, steps, warmup, rank, world, local_rank, main
             ms_acc['slab'] = sg['slab']
             return st_
 
+        t_w = time.perf_counter()
         for _ in range(warmup):
             step_e2e()
+        torch.cuda.synchronize()
+        step_s = (time.perf_counter() - t_w) / max(1, warmup)
+        # `value` is always timed over exactly `steps` passes.  The end-to-end leg repeats the same passes with the host
+        # copies inside; when one pass takes seconds (the 4096^2 frame on one GPU) it runs over fewer passes (at least 3,
+        # stated in e2e.steps) so that the whole default run still ends within minutes.
+        e2e_steps = steps
+        if step_s * steps > args.e2e_budget_s:
+            e2e_steps = max(min(3, steps), min(steps, int(args.e2e_budget_s / step_s)))
+        if world > 1:   # every rank must run the same number of passes (the gather is a collective)
+            es = torch.tensor([e2e_steps], dtype=torch.int64, device=dev)
+            dist.all_reduce(es, op=dist.ReduceOp.MIN)
+            e2e_steps = int(es.item())
         fp64_peak = ctx.measure_fp64_peak() if main else None
         sampler = ClockSampler(local_rank) if main else None
-        t_e2e, wall_e2e, _ = timed(step_e2e, steps)
+        t_e2e, wall_e2e, _ = timed(step_e2e, e2e_steps)
         launches0 = ctx.launch_count()
         t_res, wall_res, st = timed(step_resident, steps)
         launches = ctx.launch_count() - launches0
@@ -436,14 +451,14 @@ def measure(args, name, resolution, steps, warmup, rank, world, local_rank, main
             finite = np.isfinite(img)
             out = {
                 'workload': name, 'value': total_rays * K / t_res, 'unit': 'rays/s', 'ms_per_step': 1e3 * t_res / K,
-                'e2e': {'value': total_rays * K / t_e2e, 'unit': 'rays/s', 'ms_per_step': 1e3 * t_e2e / K,
-                        'h2d_bytes_per_step': int(total_rays * 72), 'd2h_bytes_per_step': int(total_rays * 8 * Q)},
+                'e2e': {'value': total_rays * e2e_steps / t_e2e, 'unit': 'rays/s', 'ms_per_step': 1e3 * t_e2e / e2e_steps,
+                        'steps': e2e_steps, 'h2d_bytes_per_step': int(total_rays * 72), 'd2h_bytes_per_step': int(total_rays * 8 * Q)},
                 'gpu_launches': int(total_launches), 'rays': int(total_rays), 'rays_rank0': n_rays, 'frequencies': F,
                 'samples_per_step': int(total_samples), 'ray_freq_per_s': total_rays * K / t_res * F,
                 # the assembled frame of the last end-to-end step: equal across N means the sharded image is bitwise the same
                 'image_crc32': '%08x' % (zlib.crc32(img.tobytes()) & 0xffffffff),
                 'image_sum': float(img[finite].sum()) if img.size else 0.0,
-                'host_wall_ms_per_step': 1e3 * wall_res / K, 'host_wall_ms_per_step_e2e': 1e3 * wall_e2e / K,
+                'host_wall_ms_per_step': 1e3 * wall_res / K, 'host_wall_ms_per_step_e2e': 1e3 * wall_e2e / e2e_steps,
                 'l2': 'inputs larger than L2: %.1f GB step buffer written and re-read per step on rank 0' % (st['num_samples'] * 64 / 1e9),
                 '_st': st, '_ms': {'geo': ms_acc['geo'] / K, 'rad': ms_acc['rad'] / K}, '_polarized': polarized,
                 '_stages': {'geometry_ms': ms_acc['stage'][0] / K, 'coefficients_ms': ms_acc['stage'][1] / K,

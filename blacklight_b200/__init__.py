@@ -135,6 +135,7 @@ class Config:
     def set_level0_block_major(self, on=True):
         """Level-0 rays will be handed over block by block (sharded adaptive runs); set before Context()."""
         _lib.blh_config_set_level0_block_major(self._h, 1 if on else 0)
+        self.level0_block_major = bool(on)
 
     @property
     def params_ptr(self):
@@ -213,6 +214,7 @@ class Context:
     def __init__(self, config):
         lib = load_library()
         self.config = config
+        self.level0_block_major = bool(getattr(config, 'level0_block_major', False))   # as bl_create saw it
         self._h = ctypes.c_void_p()
         if lib.bl_create(config.params_ptr, ctypes.byref(self._h)) != 0:
             raise BlacklightError(lib.bl_last_error(None).decode())

@@ -34,6 +34,9 @@ extern "C" cudaError_t bl_launch_pack_samples(const StepBuffer *sb, const int32_
 extern "C" cudaError_t bl_launch_refine(const double *image, int64_t stride, int level, const int32_t *block_locs,
                                         int64_t num_blocks, const bl_params *params_dev, uint8_t *flags,
                                         cudaStream_t stream);
+extern "C" cudaError_t bl_launch_camera_pixels(const CameraDev *cam, int kind, const int32_t *units, int eff_res, int block_size,
+                                               int64_t num_pixels, double *cam_pos, double *cam_dir, double *mom_factor,
+                                               cudaStream_t stream);
 extern "C" cudaError_t bl_launch_fp64_peak(double *out, int blocks, int iters, cudaStream_t stream);
 extern "C" cudaError_t bl_launch_division_selftest(unsigned long long seed, int blocks, int iters,
                                                    unsigned long long *mismatches, cudaStream_t stream);
@@ -52,11 +55,6 @@ struct Level {
   double *image = nullptr;    // device (Q, rays)
   double *render = nullptr;   // device (R,3,rays)
   // three-stage polarized pipeline (radiate_pol_split.cu): slab scratch and the camera half-step map of one wave
-  // deferred emission of the DP integrator (geodesic_dp.cu): step records of one wave
-  double *defer_rec = nullptr;     // device (defer_cap, kDeferFields, wave_rays)
-  int32_t *defer_count = nullptr;  // device (wave_rays)
-  int32_t *defer_trunc = nullptr;  // device (wave_rays)
-  int32_t defer_cap = 0;
   double *scratch = nullptr;  // device (fields, slab, wave_rays)
   double *cam_map = nullptr;  // device (10, wave_rays)
   int32_t slab = 0;           // samples per slab; 0 = the level uses the fused kernel
@@ -89,9 +87,10 @@ struct bl_ctx {
   long long launches = 0;   // kernels of ours launched so far
   int geo_min_blocks = 3;   // occupancy variant of the DP kernel (BL_GEO_BLOCKS overrides, tuning only)
   std::vector<cudaEvent_t> stage_events;   // per-launch events of the three-stage polarized pipeline
-  int geo_defer = -1;       // BL_GEO_DEFER: step records per ray for deferred emission (-1 = ray_max_steps / 20 in [64, 384], 0 = off)
-  int geo_defer_min = 3;    // BL_GEO_DEFER_MIN: accepted steps cut into at least this many pieces are deferred
-  int geo_cta_sync = 1;     // BL_GEO_SYNC: barrier per DP step attempt (instruction-cache locality against warp independence)
+  bool have_camera = false; // bl_set_camera was called
+  CameraDev camera;         // device-side camera description (camera_kernel.cu)
+  int32_t *units_dev = nullptr;   // unit list (rows / block locations) of the last bl_trace_level_pixels
+  size_t units_cap = 0;           // its capacity in int32
   int rad_prefetch = 2;     // BL_RAD_PREFETCH: samples ahead the radiation kernels prefetch step-buffer records into L2 (0 = off)
   int pol_slab = 0;         // BL_POL_SLAB: samples per slab of that pipeline (0 = chosen from the HBM budget)
   bool pol_fused = false;   // BL_POL_FUSED=1: keep the single fused polarized kernel (A/B comparisons, parity cross-check)
@@ -124,7 +123,6 @@ cudaError_t dev_alloc(T **p, size_t count) {
 void free_level(Level &L) {
   cudaFree(L.cam_pos); cudaFree(L.cam_dir); cudaFree(L.mom); cudaFree(L.num); cudaFree(L.flags);
   cudaFree(L.step); cudaFree(L.image); cudaFree(L.render); cudaFree(L.scratch); cudaFree(L.cam_map);
-  cudaFree(L.defer_rec); cudaFree(L.defer_count); cudaFree(L.defer_trunc);
   cudaFree(L.tap_inds); cudaFree(L.tap_fracs); cudaFree(L.tap_nan); cudaFree(L.tap_cut); cudaFree(L.tap_fb);
   L = Level();
 }
@@ -405,9 +403,6 @@ int bl_create(const bl_params *params, bl_ctx **out) {
   if (const char *e = getenv("BL_GEO_BLOCKS")) ctx->geo_min_blocks = atoi(e);
   if (const char *e = getenv("BL_POL_SLAB")) ctx->pol_slab = atoi(e);
   if (const char *e = getenv("BL_RAD_PREFETCH")) ctx->rad_prefetch = atoi(e);
-  if (const char *e = getenv("BL_GEO_SYNC")) ctx->geo_cta_sync = atoi(e);
-  if (const char *e = getenv("BL_GEO_DEFER")) ctx->geo_defer = atoi(e);
-  if (const char *e = getenv("BL_GEO_DEFER_MIN")) ctx->geo_defer_min = atoi(e) < 2 ? 2 : atoi(e);
   if (const char *e = getenv("BL_POL_FUSED")) ctx->pol_fused = atoi(e) != 0;
 #define CREATE_CHECK(call)                                                                   \
   do {                                                                                       \
@@ -440,7 +435,7 @@ void bl_destroy(bl_ctx *ctx) {
   cudaSetDevice(ctx->device);
   for (auto &L : ctx->levels) free_level(L);
   for (void *p : ctx->grid_allocs) cudaFree(p);
-  cudaFree(ctx->params_dev); cudaFree(ctx->counters); cudaFree(ctx->rad_counter); cudaFree(ctx->slow_counters);
+  cudaFree(ctx->units_dev); cudaFree(ctx->params_dev); cudaFree(ctx->counters); cudaFree(ctx->rad_counter); cudaFree(ctx->slow_counters);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   for (cudaEvent_t e : ctx->stage_events) cudaEventDestroy(e);
@@ -767,18 +762,6 @@ int pol_split_slab(const bl_ctx *ctx, int64_t num_rays, size_t budget, size_t *b
   return slab;
 }
 
-// Step records per ray for the DP integrator's deferred emission, and their bytes per ray.
-int geo_defer_cap(const bl_ctx *ctx, size_t *bytes_per_ray) {
-  *bytes_per_ray = 0;
-  if (ctx->params.ray_integrator != BL_INTEGRATOR_DP || ctx->geo_defer == 0) return 0;
-  int cap = ctx->geo_defer > 0 ? ctx->geo_defer : ctx->params.ray_max_steps / 20;
-  if (ctx->geo_defer < 0) cap = cap < 64 ? 64 : (cap > 384 ? 384 : cap);
-  *bytes_per_ray = (size_t)cap * GeoArgs::kDeferFields * sizeof(double) + 2 * sizeof(int32_t);
-  return cap;
-}
-
-int alloc_defer(bl_ctx *ctx, Level &L, int cap);
-
 // Trace rays [first, first+count) of a level into L.step (one wave).
 int trace_wave(bl_ctx *ctx, Level &L, int64_t first, int64_t count) {
   const bl_params &p = ctx->params;
@@ -793,18 +776,10 @@ int trace_wave(bl_ctx *ctx, Level &L, int64_t first, int64_t count) {
   g.sample_num = L.num + first;
   g.sample_flags = L.flags + first;
   g.counters = ctx->counters;
-  g.cta_sync = ctx->geo_cta_sync;
-  g.defer_rec = L.defer_rec;
-  g.defer_count = L.defer_count;
-  g.trunc = L.defer_trunc;
-  g.defer_cap = L.defer_cap;
-  g.defer_min = ctx->geo_defer_min;
   BL_CUDA_CHECK(cudaMemsetAsync(&ctx->counters->next_ray, 0, sizeof(unsigned long long), ctx->stream));
   if (p.ray_integrator == BL_INTEGRATOR_DP)
-  {
     BL_CUDA_CHECK(bl_launch_geodesic_dp(&g, p.ray_flat, ctx->sm_count, ctx->geo_min_blocks, ctx->stream));
-    if (g.defer_rec) ctx->launches++;
-  } else
+  else
     BL_CUDA_CHECK(bl_launch_geodesic_rk(&g, p.ray_flat, p.ray_integrator == BL_INTEGRATOR_RK4 ? 4 : 2, ctx->sm_count, ctx->stream));
   ctx->launches++;
   return BL_OK;
@@ -889,15 +864,6 @@ int collect_stage_times(bl_ctx *ctx, Level &L, int slabs) {
   return BL_OK;
 }
 
-int alloc_defer(bl_ctx *ctx, Level &L, int cap) {
-  L.defer_cap = cap;
-  if (cap <= 0) return BL_OK;
-  BL_CUDA_CHECK(dev_alloc(&L.defer_rec, (size_t)L.wave_rays * (size_t)cap * GeoArgs::kDeferFields));
-  BL_CUDA_CHECK(dev_alloc(&L.defer_count, (size_t)L.wave_rays));
-  BL_CUDA_CHECK(dev_alloc(&L.defer_trunc, (size_t)L.wave_rays));
-  return BL_OK;
-}
-
 int alloc_split_scratch(bl_ctx *ctx, Level &L, int slab) {
   L.slab = slab;
   if (slab <= 0) return BL_OK;
@@ -911,11 +877,14 @@ int alloc_split_scratch(bl_ctx *ctx, Level &L, int slab) {
 
 extern "C" {
 
-int bl_trace_level(bl_ctx *ctx, int level, const double *cam_pos, const double *cam_dir, const double *mom_factor,
-                   int64_t num_rays, bl_level_stats *stats) {
-  if (!ctx) return BL_ERR_ARG;
-  if (level < 0 || level >= (int)ctx->levels.size()) return bl_fail(ctx, BL_ERR_ARG, "bl_trace_level: level %d out of range", level);
-  if (!cam_pos || !cam_dir || !mom_factor || num_rays < 0) return bl_fail(ctx, BL_ERR_ARG, "bl_trace_level: null camera arrays");
+}  // extern "C"
+
+namespace {
+
+// Common part of bl_trace_level and bl_trace_level_pixels: (re)allocate the level for num_rays rays, let `fill` put the
+// camera arrays into L.cam_pos / L.cam_dir / L.mom (enqueued on the context's stream), size the waves, trace if resident.
+template <class Fill>
+int trace_level_impl(bl_ctx *ctx, int level, int64_t num_rays, bl_level_stats *stats, Fill fill) {
   BL_CUDA_CHECK(cudaSetDevice(ctx->device));
   Level &L = ctx->levels[level];
   // any failure below leaves the level empty rather than half built
@@ -942,9 +911,10 @@ int bl_trace_level(bl_ctx *ctx, int level, const double *cam_pos, const double *
     BL_CUDA_CHECK(dev_alloc(&L.image, (size_t)num_rays * (size_t)(Q > 0 ? Q : 1)));
     if (R > 0) BL_CUDA_CHECK(dev_alloc(&L.render, (size_t)num_rays * 3 * R));
   }
-  BL_CUDA_CHECK(cudaMemcpyAsync(L.cam_pos, cam_pos, (size_t)num_rays * 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  BL_CUDA_CHECK(cudaMemcpyAsync(L.cam_dir, cam_dir, (size_t)num_rays * 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  BL_CUDA_CHECK(cudaMemcpyAsync(L.mom, mom_factor, (size_t)num_rays * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  {
+    int rc = fill(L);
+    if (rc) return rc;
+  }
 
   if (!reuse) {
     // wave size from the HBM budget: 64 bytes per sample slot, ray_max_steps slots per ray
@@ -954,9 +924,6 @@ int bl_trace_level(bl_ctx *ctx, int level, const double *cam_pos, const double *
     size_t budget = (size_t)((double)fr * 0.80);
     size_t per_ray_split = 0;
     const int slab = pol_split_slab(ctx, num_rays, budget, &per_ray_split);
-    size_t per_ray_defer = 0;
-    const int defer_cap = geo_defer_cap(ctx, &per_ray_defer);
-    per_ray_split += per_ray_defer;
     int64_t fit = (int64_t)(budget / (per_ray + per_ray_split));
     if (fit < 128) {
       free_level(L);
@@ -978,8 +945,6 @@ int bl_trace_level(bl_ctx *ctx, int level, const double *cam_pos, const double *
     }
     BL_CUDA_CHECK(dev_alloc(&L.step, (size_t)L.wave_rays * per_ray / sizeof(double)));
     int rc = alloc_split_scratch(ctx, L, slab);
-    if (rc) return rc;
-    rc = alloc_defer(ctx, L, defer_cap);
     if (rc) return rc;
   }
   BL_CUDA_CHECK(cudaMemsetAsync(ctx->counters, 0, sizeof(GeoCounters), ctx->stream));
@@ -1003,6 +968,103 @@ int bl_trace_level(bl_ctx *ctx, int level, const double *cam_pos, const double *
   }
   guard.ok = true;
   if (stats) *stats = L.stats;
+  return BL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bl_trace_level(bl_ctx *ctx, int level, const double *cam_pos, const double *cam_dir, const double *mom_factor,
+                   int64_t num_rays, bl_level_stats *stats) {
+  if (!ctx) return BL_ERR_ARG;
+  if (level < 0 || level >= (int)ctx->levels.size()) return bl_fail(ctx, BL_ERR_ARG, "bl_trace_level: level %d out of range", level);
+  if (!cam_pos || !cam_dir || !mom_factor || num_rays < 0) return bl_fail(ctx, BL_ERR_ARG, "bl_trace_level: null camera arrays");
+  return trace_level_impl(ctx, level, num_rays, stats, [&](Level &L) -> int {
+    BL_CUDA_CHECK(cudaMemcpyAsync(L.cam_pos, cam_pos, (size_t)num_rays * 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    BL_CUDA_CHECK(cudaMemcpyAsync(L.cam_dir, cam_dir, (size_t)num_rays * 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    BL_CUDA_CHECK(cudaMemcpyAsync(L.mom, mom_factor, (size_t)num_rays * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    return BL_OK;
+  });
+}
+
+int bl_set_camera(bl_ctx *ctx, const bl_camera *camera) {
+  if (!ctx || !camera) return BL_ERR_ARG;
+  if (camera->type != BL_CAMERA_PLANE && camera->type != BL_CAMERA_PINHOLE) return bl_fail(ctx, BL_ERR_ARG, "bl_set_camera: unknown camera type %d", camera->type);
+  if (camera->normalization != BL_NORM_CAMERA && camera->normalization != BL_NORM_INFINITY)
+    return bl_fail(ctx, BL_ERR_ARG, "bl_set_camera: unknown image normalization %d", camera->normalization);
+  CameraDev &c = ctx->camera;
+  c.type = camera->type;
+  c.normalization = camera->normalization;
+  c.flat = ctx->params.ray_flat ? 1 : 0;
+  c.pad = 0;
+  c.a = ctx->params.bh_a;
+  c.width = camera->width;
+  c.r = camera->r;
+  for (int m = 0; m < 4; m++) {
+    c.x[m] = camera->x[m];
+    c.u_con[m] = camera->u_con[m];
+    c.u_cov[m] = camera->u_cov[m];
+    c.norm_con[m] = camera->norm_con[m];
+    c.norm_con_c[m] = camera->norm_con_c[m];
+    c.hor_con_c[m] = camera->hor_con_c[m];
+    c.vert_con_c[m] = camera->vert_con_c[m];
+  }
+  ctx->have_camera = true;
+  return BL_OK;
+}
+
+int bl_trace_level_pixels(bl_ctx *ctx, int level, int kind, const int32_t *units, int64_t num_units, bl_level_stats *stats) {
+  if (!ctx) return BL_ERR_ARG;
+  if (level < 0 || level >= (int)ctx->levels.size()) return bl_fail(ctx, BL_ERR_ARG, "bl_trace_level_pixels: level %d out of range", level);
+  if (!ctx->have_camera) return bl_fail(ctx, BL_ERR_STATE, "bl_trace_level_pixels: no camera (bl_set_camera)");
+  if (kind != BL_PIXELS_ROWS && kind != BL_PIXELS_BLOCKS) return bl_fail(ctx, BL_ERR_ARG, "bl_trace_level_pixels: unknown unit kind %d", kind);
+  if (num_units < 0 || (kind == BL_PIXELS_BLOCKS && !units && num_units > 0)) return bl_fail(ctx, BL_ERR_ARG, "bl_trace_level_pixels: null unit list");
+  const int64_t eff_res64 = (int64_t)ctx->params.camera_resolution << level;
+  if (ctx->params.camera_resolution <= 0 || eff_res64 > 0x7fffffff) return bl_fail(ctx, BL_ERR_ARG, "bl_trace_level_pixels: effective resolution out of range");
+  const int eff_res = (int)eff_res64;
+  const int bs = ctx->params.adaptive_block_size;
+  if (kind == BL_PIXELS_BLOCKS && (bs <= 0 || eff_res % bs != 0)) return bl_fail(ctx, BL_ERR_ARG, "bl_trace_level_pixels: adaptive_block_size must divide the effective resolution");
+  // the unit list is validated here, on the host: a bad entry would only move a pixel, never fault, but it is a caller bug
+  const int64_t per_unit = kind == BL_PIXELS_ROWS ? eff_res : (int64_t)bs * bs;
+  const int64_t limit = kind == BL_PIXELS_ROWS ? eff_res : eff_res / bs;
+  const int64_t entries = kind == BL_PIXELS_ROWS ? num_units : 2 * num_units;
+  if (!units && num_units > eff_res) return bl_fail(ctx, BL_ERR_ARG, "bl_trace_level_pixels: %lld rows of a %d-row raster", (long long)num_units, eff_res);
+  if (units)
+    for (int64_t q = 0; q < entries; q++)
+      if (units[q] < 0 || units[q] >= limit) return bl_fail(ctx, BL_ERR_ARG, "bl_trace_level_pixels: unit entry %d outside [0, %lld)", units[q], (long long)limit);
+  const int64_t num_rays = num_units * per_unit;
+  return trace_level_impl(ctx, level, num_rays, stats, [&](Level &L) -> int {
+    const int32_t *units_dev = nullptr;
+    if (units && entries > 0) {
+      if ((size_t)entries > ctx->units_cap) {
+        cudaFree(ctx->units_dev);
+        ctx->units_dev = nullptr;
+        ctx->units_cap = 0;
+        BL_CUDA_CHECK(dev_alloc(&ctx->units_dev, (size_t)entries));
+        ctx->units_cap = (size_t)entries;
+      }
+      BL_CUDA_CHECK(cudaMemcpyAsync(ctx->units_dev, units, (size_t)entries * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+      units_dev = ctx->units_dev;
+    }
+    BL_CUDA_CHECK(bl_launch_camera_pixels(&ctx->camera, kind, units_dev, eff_res, bs, num_rays, L.cam_pos, L.cam_dir, L.mom, ctx->stream));
+    ctx->launches++;
+    return BL_OK;
+  });
+}
+
+int bl_download_camera(bl_ctx *ctx, int level, double *cam_pos, double *cam_dir, double *mom_factor) {
+  if (!ctx) return BL_ERR_ARG;
+  if (level < 0 || level >= (int)ctx->levels.size()) return bl_fail(ctx, BL_ERR_ARG, "bl_download_camera: level %d out of range", level);
+  Level &L = ctx->levels[level];
+  if (L.rays > 0 && !L.cam_pos) return bl_fail(ctx, BL_ERR_STATE, "bl_download_camera: level %d has no camera arrays", level);
+  BL_CUDA_CHECK(cudaSetDevice(ctx->device));
+  if (L.rays > 0) {
+    if (cam_pos) BL_CUDA_CHECK(cudaMemcpyAsync(cam_pos, L.cam_pos, (size_t)L.rays * 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (cam_dir) BL_CUDA_CHECK(cudaMemcpyAsync(cam_dir, L.cam_dir, (size_t)L.rays * 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (mom_factor) BL_CUDA_CHECK(cudaMemcpyAsync(mom_factor, L.mom, (size_t)L.rays * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    BL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  }
   return BL_OK;
 }
 

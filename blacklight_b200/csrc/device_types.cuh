@@ -40,16 +40,13 @@ struct GeoArgs {
   int32_t *sample_num;   // (rays)
   uint8_t *sample_flags; // (rays)
   GeoCounters *counters;
-  int32_t cta_sync;      // DP kernel: barrier per step attempt (see geodesic_dp.cu)
-  // Deferred emission (DP kernel): an accepted step that is cut into defer_min or more stored pieces leaves a record
-  // (kDeferFields doubles: start state, quartic coefficients, piece length and counts) instead of storing the pieces
-  // itself; geodesic_emit_kernel evaluates them afterwards.  rec[(k * kDeferFields + f) * rays + m], k < defer_count[m].
-  double *defer_rec;     // nullptr: every piece is stored by the integrator
-  int32_t *defer_count;  // (rays)
-  int32_t *trunc;        // (rays) first truncated sample index found so far, INT_MAX if none
-  int32_t defer_cap;     // records per ray
-  int32_t defer_min;
-  static constexpr int kDeferFields = 41;
+};
+
+// What InitializeCamera leaves (reference camera.cpp:53-380; host build_camera_frame), by value to camera_pixels_kernel.
+struct CameraDev {
+  int32_t type, normalization, flat, pad;   // BL_CAMERA_*, BL_NORM_*, ray_flat
+  double a, width, r;
+  double x[4], u_con[4], u_cov[4], norm_con[4], norm_con_c[4], hor_con_c[4], vert_con_c[4];
 };
 
 #define BL_CUDA_CHECK(call)                                                        \

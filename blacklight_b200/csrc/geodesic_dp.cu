@@ -49,7 +49,6 @@ struct Ray {
   int n;          // samples stored so far
   int num_retry;
   int trunc;      // first truncated sample index, -1 if none
-  int defer_n;    // step records written (deferred emission)
   double ds0;     // ds/dlambda of stage 0 (first-same-as-last)
   bool prev_fail, flag, need_k0;
 };
@@ -133,7 +132,6 @@ __global__ void __launch_bounds__(kBlock, MINB) geodesic_dp_kernel(GeoArgs g) {
           ray.n = 0;
           ray.num_retry = 0;
           ray.trunc = -1;
-          ray.defer_n = 0;
           ray.r_prev_sample = 0.0;
           ray.prev_fail = false;
           ray.flag = false;
@@ -143,14 +141,12 @@ __global__ void __launch_bounds__(kBlock, MINB) geodesic_dp_kernel(GeoArgs g) {
       }
       if (base + __popc(idle) >= (unsigned long long)g.rays) exhausted = true;
     }
-    // cta_sync: keep the CTA's warps in the same region of the (instruction-cache-sized) loop body -- worth 7 % when the
-    // warps' attempts cost about the same; when the sub-sample store loops differ a lot between warps (far cameras:
-    // 1 ... 60 pieces per accepted step) the barrier makes every warp wait for the slowest one instead
-    if (g.cta_sync) {
-      if (!__syncthreads_or(active ? 1 : 0)) break;
-    } else {
-      if (!__any_sync(full, active)) break;
-    }
+#if !defined(BL_GEO_NOSYNC)
+    // keep the CTA's warps in the same region of the (instruction-cache-sized) loop body
+    if (!__syncthreads_or(active ? 1 : 0)) break;
+#else
+    if (!__any_sync(full, active)) break;
+#endif
     if (!active) continue;
 
     // ---- one step attempt ----
@@ -292,47 +288,17 @@ __global__ void __launch_bounds__(kBlock, MINB) geodesic_dp_kernel(GeoArgs g) {
           }
           const blmath::Recip inv_n = blmath::recip_of((double)n_ideal);
           double len = blmath::div_by(h, inv_n);
-          if (g.defer_rec && n_ideal >= g.defer_min && n_sub > 0 && ray.defer_n < g.defer_cap) {
-            // Many pieces: lanes of a warp cut their steps into 1 ... 60 pieces, and a loop over them here would run as
-            // long as the warp's largest count.  Leave the step's record; geodesic_emit_kernel stores the pieces (same
-            // expressions, same translation unit and flags: the same bits).
-            double *rec = g.defer_rec + ((size_t)ray.defer_n * GeoArgs::kDeferFields) * (size_t)g.rays + ray.m;
-            const size_t fs = (size_t)g.rays;
+          for (int nn = 0; nn < n_sub; nn++) {
+            double frac = blmath::div_by(nn + 0.5, inv_n);
+            double v[8];
+            v[4] = ray.y[4];
 #pragma unroll
             for (int j = 0; j < 7; j++) {
-              __stcs(rec + (size_t)j * fs, ray.y[yc[j]]);
-              __stcs(rec + (size_t)(7 + j) * fs, q0[j]);
-              __stcs(rec + (size_t)(14 + j) * fs, q1[j]);
-              __stcs(rec + (size_t)(21 + j) * fs, q2[j]);
-              __stcs(rec + (size_t)(28 + j) * fs, q3[j]);
+              int c = yc[j];
+              v[c] = ray.y[c] +
+                     frac * (q0[j] + (1.0 - frac) * (q1[j] + frac * (q2[j] + (1.0 - frac) * q3[j])));
             }
-            __stcs(rec + 35 * fs, len);
-            __stcs(rec + 36 * fs, (double)n_ideal);
-            __stcs(rec + 37 * fs, (double)n_sub);
-            __stcs(rec + 38 * fs, (double)ray.n);
-            __stcs(rec + 39 * fs, ray.r_prev_sample);
-            __stcs(rec + 40 * fs, ray.y[4]);
-            ray.defer_n++;
-            // the truncation test of the next stored sample looks at the radius of this step's last piece
-            double frac = blmath::div_by((n_sub - 1) + 0.5, inv_n);
-            double vx[3];
-#pragma unroll
-            for (int j = 1; j < 4; j++)
-              vx[j - 1] = ray.y[j] + frac * (q0[j] + (1.0 - frac) * (q1[j] + frac * (q2[j] + (1.0 - frac) * q3[j])));
-            ray.r_prev_sample = ksx::radius(g.a, vx[0], vx[1], vx[2]);
-          } else {
-            for (int nn = 0; nn < n_sub; nn++) {
-              double frac = blmath::div_by(nn + 0.5, inv_n);
-              double v[8];
-              v[4] = ray.y[4];
-#pragma unroll
-              for (int j = 0; j < 7; j++) {
-                int c = yc[j];
-                v[c] = ray.y[c] +
-                       frac * (q0[j] + (1.0 - frac) * (q1[j] + frac * (q2[j] + (1.0 - frac) * q3[j])));
-              }
-              store_sample<flat>(g, ray, ray.n + nn, v, len);
-            }
+            store_sample<flat>(g, ray, ray.n + nn, v, len);
           }
         }
 
@@ -354,20 +320,13 @@ __global__ void __launch_bounds__(kBlock, MINB) geodesic_dp_kernel(GeoArgs g) {
     }
 
     if (finished) {
+      int count = ray.n;
+      if (ray.trunc >= 0 && count > 1) count = ray.trunc;
+      g.sample_num[ray.m] = count;
       g.sample_flags[ray.m] = ray.flag ? 1 : 0;
+      atomicAdd(&g.counters->samples, (unsigned long long)count);
       if (ray.flag) atomicAdd(&g.counters->bad, 1ull);
-      if (g.defer_rec) {
-        // pieces are still to be stored (and tested for truncation): geodesic_emit_kernel settles the count
-        g.sample_num[ray.m] = ray.n;
-        g.defer_count[ray.m] = ray.defer_n;
-        g.trunc[ray.m] = ray.trunc >= 0 ? ray.trunc : 0x7fffffff;
-      } else {
-        int count = ray.n;
-        if (ray.trunc >= 0 && count > 1) count = ray.trunc;
-        g.sample_num[ray.m] = count;
-        atomicAdd(&g.counters->samples, (unsigned long long)count);
-        atomicMax(&g.counters->max_samples, count);
-      }
+      atomicMax(&g.counters->max_samples, count);
       active = false;
     }
   }
@@ -383,74 +342,6 @@ __global__ void __launch_bounds__(kBlock, MINB) geodesic_dp_kernel(GeoArgs g) {
   }
 }
 
-
-// Deferred emission: one thread per ray walks the step records the integrator left (GeoArgs::defer_rec) and stores
-// their pieces -- the quartic through both endpoints, both end slopes and the 4th-order midpoint evaluated at the
-// piece midpoints (geodesics.cpp:262-293), truncation test and momentum renormalisation per piece -- with exactly the
-// expressions of the inline path.  Adjacent rays cut their steps alike, so the lanes of a warp run nearly the same trip
-// counts here, which is what the integrator's warps (lanes at unrelated steps) cannot offer.  Truncation is the first
-// flagged index over inline and deferred pieces alike; a piece's flag depends only on its own radius and its
-// predecessor's, so the order of evaluation does not matter.
-template <bool flat>
-__global__ void __launch_bounds__(kBlock) geodesic_emit_kernel(GeoArgs g) {
-  const unsigned full = 0xffffffffu;
-  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int count = 0;
-  if (m < g.rays) {
-    const int records = g.defer_count[m];
-    int trunc = g.trunc[m];
-    const size_t fs = (size_t)g.rays;
-    Ray ray;
-    ray.m = m;
-    for (int k = 0; k < records; k++) {
-      const double *rec = g.defer_rec + ((size_t)k * GeoArgs::kDeferFields) * fs + m;
-      double y0[7], q0[7], q1[7], q2[7], q3[7];
-#pragma unroll
-      for (int j = 0; j < 7; j++) {
-        y0[j] = __ldcs(rec + (size_t)j * fs);
-        q0[j] = __ldcs(rec + (size_t)(7 + j) * fs);
-        q1[j] = __ldcs(rec + (size_t)(14 + j) * fs);
-        q2[j] = __ldcs(rec + (size_t)(21 + j) * fs);
-        q3[j] = __ldcs(rec + (size_t)(28 + j) * fs);
-      }
-      const double len = __ldcs(rec + 35 * fs);
-      const int n_ideal = (int)__ldcs(rec + 36 * fs), n_sub = (int)__ldcs(rec + 37 * fs), first = (int)__ldcs(rec + 38 * fs);
-      const double p_t = __ldcs(rec + 40 * fs);
-      // store_sample's state for this step: nothing truncated yet as far as this step knows (a flag of an earlier piece
-      // wins through the minimum below; pieces stored past it are never read)
-      ray.trunc = -1;
-      ray.r_prev_sample = __ldcs(rec + 39 * fs);
-      const blmath::Recip inv_n = blmath::recip_of((double)n_ideal);
-      const int yc[7] = {0, 1, 2, 3, 5, 6, 7};
-      for (int nn = 0; nn < n_sub; nn++) {
-        double frac = blmath::div_by(nn + 0.5, inv_n);
-        double v[8];
-        v[4] = p_t;
-#pragma unroll
-        for (int j = 0; j < 7; j++)
-          v[yc[j]] = y0[j] + frac * (q0[j] + (1.0 - frac) * (q1[j] + frac * (q2[j] + (1.0 - frac) * q3[j])));
-        store_sample<flat>(g, ray, first + nn, v, len);
-        if (ray.trunc >= 0) break;
-      }
-      if (ray.trunc >= 0 && ray.trunc < trunc) trunc = ray.trunc;
-    }
-    count = g.sample_num[m];
-    if (trunc != 0x7fffffff && count > 1) count = trunc;
-    g.sample_num[m] = count;
-  }
-  // totals of the wave (roofline accounting, geodesic_num_steps)
-  unsigned long long total = (unsigned long long)count;
-  int most = count;
-  for (int off = 16; off > 0; off >>= 1) {
-    total += __shfl_down_sync(full, total, off);
-    int o = __shfl_down_sync(full, most, off);
-    most = o > most ? o : most;
-  }
-  if ((threadIdx.x & 31) == 0 && total) {
-    atomicAdd(&g.counters->samples, total);
-    atomicMax(&g.counters->max_samples, most);
-  }
-}
 
 // Fixed-fraction-step integrators (reference geodesics.cpp:418-606 RK4, :626-795 RK2): one sample per
 // step, h = -ray_step (r - r_horizon).  Same store path (truncation + renormalisation) as DP.
@@ -537,7 +428,6 @@ cudaError_t launch_dp(const GeoArgs *args, int sm_count, cudaStream_t stream) {
   if (grid > want) grid = want;
   if (grid < 1) grid = 1;
   geodesic_dp_kernel<flat, MINB><<<(unsigned)grid, kBlock, smem, stream>>>(*args);
-  if (args->defer_rec) geodesic_emit_kernel<flat><<<(unsigned)want, kBlock, 0, stream>>>(*args);
   return cudaGetLastError();
 }
 }  // namespace

@@ -267,8 +267,11 @@ void load_geodesic_checkpoint(bl_ctx *ctx, const RunConfig &cfg, LevelData &root
   read_array(in, dir, n);
   read_array(in, len, n);
   if (N != (long long)cfg.params.camera_resolution * cfg.params.camera_resolution || (long long)root.factor.size() != N ||
-      (long long)len.size() != N * S)
+      (long long)root.pos.size() != 4 * N || (long long)root.dir.size() != 4 * N)
     throw Error("Geodesic checkpoint does not match camera_resolution.");
+  if (S <= 0 || (long long)flags.size() != N || (long long)num.size() != N || (long long)len.size() != N * S ||
+      (long long)pos.size() != 4 * N * S || (long long)dir.size() != 4 * N * S)
+    throw Error("Geodesic checkpoint does not match its own sample count.");
   root.rays = N;
   check(ctx, bl_upload_samples(ctx, 0, root.pos.data(), root.dir.data(), root.factor.data(), N, S, flags.data(), num.data(),
                                pos.data(), dir.data(), len.data(), st));

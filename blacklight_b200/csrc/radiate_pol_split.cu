@@ -90,7 +90,7 @@ pol_geometry_kernel(const __grid_constant__ RadArgs A, const __grid_constant__ R
       const bool store = n <= top;
       const double2 *src = reinterpret_cast<const double2 *>(A.sb.buf + A.sb.at(n, m));
       rad::prefetch_record(A.sb, n, m, A.prefetch);
-    double2 r0 = __ldcs(src), r1 = __ldcs(src + 1), r2 = __ldcs(src + 2), r3 = __ldcs(src + 3);
+      double2 r0 = __ldcs(src), r1 = __ldcs(src + 1), r2 = __ldcs(src + 2), r3 = __ldcs(src + 3);
       double t = r0.x, x = r0.y, y = r1.x, z = r1.y;
       double kc[4] = {k_t, r2.x, r2.y, r3.x};
       double dlam = -r3.y;

@@ -39,6 +39,11 @@ def adaptive_worker(cfg, ctx, rank, world, max_level, num_render=0):
     ('gather_arrays', arrays, shapes of every rank's arrays) -> per-rank lists of arrays on rank 0 / None elsewhere; returns (via StopIteration.value) on rank 0 a list
     over levels of dict(locs=(B,2) int32, flags=(B,) uint8 or None, image=(Q, B*bs*bs) f64 in the reference's
     pixel order for that level [level 0: raster], stats=...), None on other ranks."""
+    if not getattr(ctx, 'level0_block_major', False):
+        raise ValueError('adaptive_worker: the context must be created from a config with set_level0_block_major(True) '
+                         '(the root level is handed over block by block)')
+    if num_render > 0:
+        raise ValueError('adaptive_worker: rendering is not gathered in sharded adaptive runs (use the C++ multi-device driver)')
     bs2 = cfg.block_size ** 2
     T = {k: 0.0 for k in ('camera', 'select', 'trace', 'radiate', 'refine', 'exchange', 'assemble')}
     last_stage_seconds.clear()

@@ -187,6 +187,29 @@ int bl_upload_grid(bl_ctx *ctx, const bl_grid_view *grid);
 int bl_trace_level(bl_ctx *ctx, int level, const double *cam_pos, const double *cam_dir,
                    const double *mom_factor, int64_t num_rays, bl_level_stats *stats);
 
+/* Camera pixels generated on the device (reference camera.cpp:390-413 root raster, :471-499 refined blocks, :528-671
+ * SetPixelPlane / SetPixelPinhole): bl_set_camera hands over what InitializeCamera leaves (camera.cpp:53-380; the host
+ * layer's blh_camera_frame), bl_trace_level_pixels then replaces "build the camera arrays on the host + bl_trace_level":
+ * the level's rays are the pixels of the listed units at effective resolution camera_resolution * 2^level, computed in
+ * HBM bit for bit as the host code computes them (csrc/camera_kernel.cu), so only the unit list crosses PCIe.
+ *   BL_PIXELS_ROWS:   units = image rows (num_units int32), ray m = unit_index * eff_res + column; units == NULL
+ *                     means rows 0 .. num_units-1 (num_units = eff_res: the whole raster)
+ *   BL_PIXELS_BLOCKS: units = (num_units, 2) int32 (v, u) block locations, adaptive_block_size^2 rays per block,
+ *                     block-major like the reference's refined levels
+ * bl_download_camera returns the level's camera arrays (any pointer may be NULL), e.g. for output_camera. */
+typedef struct bl_camera {
+  int32_t type;                   /* BL_CAMERA_* */
+  int32_t normalization;          /* BL_NORM_* (image_normalization) */
+  double width, r;                /* camera_width, camera_r */
+  double x[4], u_con[4], u_cov[4];
+  double norm_con[4], norm_con_c[4], hor_con_c[4], vert_con_c[4];
+} bl_camera;
+enum { BL_PIXELS_ROWS = 0, BL_PIXELS_BLOCKS = 1 };
+int bl_set_camera(bl_ctx *ctx, const bl_camera *camera);
+int bl_trace_level_pixels(bl_ctx *ctx, int level, int kind, const int32_t *units, int64_t num_units,
+                          bl_level_stats *stats);
+int bl_download_camera(bl_ctx *ctx, int level, double *cam_pos, double *cam_dir, double *mom_factor);
+
 /* Slow light (reference simulation_reader.cpp:211-303, simulation_sampling.cpp:298-349): the context keeps
  * slow_chunk_size snapshots resident in HBM.  bl_upload_grid_slice puts one snapshot into slot `slot`
  * (0 <= slot < slow_chunk_size; slot 0 is what bl_upload_grid fills); bl_set_time_window then declares, for the

@@ -535,6 +535,7 @@ class _FakeConfig:
 class _FakeContext:
     """"Image" of a ray = its momentum factor (so assembly order is checkable); refine blocks whose first
     pixel's tag is a multiple of 3."""
+    level0_block_major = True
 
     def trace_level(self, level, pos, dirs, fac):
         self.fac = fac
