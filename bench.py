@@ -8,7 +8,8 @@ Default workload = BASELINE.json configs[3], the configuration the metric is quo
 rendered as a 4096^2 polarized (Stokes IQUV) image, kappa-distribution electrons (kappa = 4), 4 frequencies, with the
 image rows dealt round-robin over the N ranks (STRONG scaling: the frame is fixed, per-GPU work shrinks as N grows).
 A step is one pass of the hot path over the whole frame.  `value` is rays/s with the camera arrays and the grid already
-resident in HBM; `e2e` is the same metric through the C ABI from pinned HOST buffers: H2D of the camera arrays, the
+resident in HBM; `e2e` is the same metric through the C ABI from pinned HOST buffers: H2D of the step's input (the list of image rows
+this rank renders -- the camera pixels are generated on the device; --host-camera uploads host-built arrays), the
 kernels, the gather of every rank's rows into rank 0's image over NCCL, and the D2H of the assembled frame, all inside
 the timed region.  The other configurations of BASELINE.json (formula plasma, 1024^2 unpolarized, adaptive refinement
 sharded over the ranks, true colour, false-colour rendering) are measured the same way with fewer steps and appended
@@ -87,6 +88,9 @@ def parse_args():
     ap.add_argument('--cpu-resolution', type=int, default=0, help='side of the bounded CPU sample (0 = auto)')
     ap.add_argument('--e2e-budget-s', type=float, default=60.0,
                     help='the end-to-end leg runs over min(steps, budget / seconds per pass) passes, at least 3')
+    ap.add_argument('--host-camera', action='store_true',
+                    help='end-to-end leg: build the camera arrays on the host and upload them (round 1) instead of generating '
+                         'the pixels on the device')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-extras', action='store_true', help='only the main workload (no `extra` lines)')
     ap.add_argument('--dump-units', default='', help='write the unit counts of the main workload (for tools/ncu_flops_json.py)')
@@ -338,15 +342,22 @@ def measure(args, name, resolution, steps, warmup, rank, world, local_rank, main
         F = int(cfg.keys.get('image_num_frequencies', '1'))
         R = int(cfg.keys.get('render_num_images', '0')) if case.sim else 0
         polarized = case.sim and cfg.keys.get('image_polarization', 'false') == 'true'
-        # this rank's rays: image rows rank, rank + world, ... (cost varies strongly across the image)
-        pos_all, dir_all, fac_all = cfg.camera_root()
-        _, idx = shard_rows(resolution, rank, world)
+        # this rank's rays: image rows rank, rank + world, ... (cost varies strongly across the image).  Their camera
+        # pixels are generated on the device from the row list (bl_trace_level_pixels); --host-camera builds the camera
+        # arrays on the host instead and uploads them from pinned memory every step, as round 1 did (72 bytes per ray)
+        rows, idx = shard_rows(resolution, rank, world)
         n_rays = len(idx)
-        pos = torch.from_numpy(pos_all[idx]).pin_memory()
-        dirs = torch.from_numpy(dir_all[idx]).pin_memory()
-        fac = torch.from_numpy(fac_all[idx]).pin_memory()
-        del pos_all, dir_all, fac_all
-        pos_np, dir_np, fac_np = pos.numpy(), dirs.numpy(), fac.numpy()
+        rows_np = torch.from_numpy(rows.astype(np.int32)).pin_memory().numpy()
+        pos_np = dir_np = fac_np = None
+        if args.host_camera:
+            pos_all, dir_all, fac_all = cfg.camera_root()
+            pos = torch.from_numpy(pos_all[idx]).pin_memory()
+            dirs = torch.from_numpy(dir_all[idx]).pin_memory()
+            fac = torch.from_numpy(fac_all[idx]).pin_memory()
+            del pos_all, dir_all, fac_all
+            pos_np, dir_np, fac_np = pos.numpy(), dirs.numpy(), fac.numpy()
+        h2d_bytes = n_rays * 72 if args.host_camera else rows_np.nbytes
+        del idx
 
         ctx = bl.Context(cfg)
         info = ctx.device_info()
@@ -386,7 +397,10 @@ def measure(args, name, resolution, steps, warmup, rank, world, local_rank, main
             return ev0.elapsed_time(ev1) * 1e-3, time.perf_counter() - t0, out
 
         def step_e2e():
-            ctx.trace_level(0, pos_np, dir_np, fac_np)                     # H2D of the camera arrays (+ trace if resident)
+            if args.host_camera:
+                ctx.trace_level(0, pos_np, dir_np, fac_np)                 # H2D of the camera arrays (+ trace if resident)
+            else:
+                ctx.trace_level_pixels(0, rows=rows_np)                    # H2D of the row list, pixels on the device (+ trace)
             if world == 1:
                 _, _, st_ = ctx.radiate_level(0, image=image_host.numpy(), render=render_host, num_render=R)   # kernels + D2H
                 return st_
@@ -438,12 +452,12 @@ def measure(args, name, resolution, steps, warmup, rank, world, local_rank, main
         clocks = sampler.stop() if sampler else None
 
         times = torch.tensor([t_e2e, t_res], dtype=torch.float64, device=dev)
-        counts = torch.tensor([float(n_rays), float(launches), float(st['num_samples'])], dtype=torch.float64, device=dev)
+        counts = torch.tensor([float(n_rays), float(launches), float(st['num_samples']), float(h2d_bytes)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(times, op=dist.ReduceOp.MAX)
             dist.all_reduce(counts, op=dist.ReduceOp.SUM)
         t_e2e, t_res = times.tolist()
-        total_rays, total_launches, total_samples = counts.tolist()
+        total_rays, total_launches, total_samples, total_h2d = counts.tolist()
         out = None
         if rank == 0:
             K = steps
@@ -452,7 +466,9 @@ def measure(args, name, resolution, steps, warmup, rank, world, local_rank, main
             out = {
                 'workload': name, 'value': total_rays * K / t_res, 'unit': 'rays/s', 'ms_per_step': 1e3 * t_res / K,
                 'e2e': {'value': total_rays * e2e_steps / t_e2e, 'unit': 'rays/s', 'ms_per_step': 1e3 * t_e2e / e2e_steps,
-                        'steps': e2e_steps, 'h2d_bytes_per_step': int(total_rays * 72), 'd2h_bytes_per_step': int(total_rays * 8 * Q)},
+                        'steps': e2e_steps, 'h2d_bytes_per_step': int(total_h2d), 'd2h_bytes_per_step': int(total_rays * 8 * Q),
+                        'camera': 'host arrays uploaded (72 B per ray)' if args.host_camera else
+                                  'pixels generated on the device from the row list (bl_trace_level_pixels)'},
                 'gpu_launches': int(total_launches), 'rays': int(total_rays), 'rays_rank0': n_rays, 'frequencies': F,
                 'samples_per_step': int(total_samples), 'ray_freq_per_s': total_rays * K / t_res * F,
                 # the assembled frame of the last end-to-end step: equal across N means the sharded image is bitwise the same

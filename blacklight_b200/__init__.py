@@ -45,6 +45,14 @@ class LevelStats(ctypes.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class Camera(ctypes.Structure):
+    """bl_camera"""
+    _fields_ = [('type', ctypes.c_int32), ('normalization', ctypes.c_int32), ('width', ctypes.c_double), ('r', ctypes.c_double)] + \
+               [(n, ctypes.c_double * 4) for n in ('x', 'u_con', 'u_cov', 'norm_con', 'norm_con_c', 'hor_con_c', 'vert_con_c')]
+
+
+PIXELS_ROWS, PIXELS_BLOCKS = 0, 1   # bl_trace_level_pixels unit kinds
+
 _lib = None
 
 
@@ -87,6 +95,10 @@ def load_library():
         'blh_camera_rows': (i64, [vp, vp, i64, vp, vp, vp]),
         'blh_run_input_file_devices': (i32, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_int), i32, i32, vp]),
         'bl_device_count': (i32, []),
+        'bl_set_camera': (i32, [vp, ctypes.POINTER(Camera)]),
+        'bl_trace_level_pixels': (i32, [vp, i32, i32, vp, i64, ctypes.POINTER(LevelStats)]),
+        'bl_download_camera': (i32, [vp, i32, vp, vp, vp]),
+        'blh_camera_struct': (i32, [vp, ctypes.POINTER(Camera)]),
         'blh_camera_blocks': (i64, [vp, i32, vp, i64, vp, vp, vp]),
         'blh_snapshot_read': (i32, [vp, ctypes.c_char_p, ctypes.POINTER(vp)]),
         'blh_snapshot_view': (i32, [vp, ctypes.POINTER(GridView), ctypes.POINTER(dbl), ctypes.POINTER(dbl)]),
@@ -268,6 +280,42 @@ class Context:
             for d in range(6):
                 v.simulation_bounds[d] = float(g['simulation_bounds'][d])
         self._check(_lib.bl_upload_grid(self._h, ctypes.byref(v)))
+
+    def set_camera(self, config=None):
+        """Hand the camera frame of `config` (default: the context's own) to the device: bl_set_camera."""
+        cam = Camera()
+        cfg = config or self.config
+        if _lib.blh_camera_struct(cfg._h, ctypes.byref(cam)) != 0:
+            raise BlacklightError(_lib.blh_last_error().decode())
+        self._check(_lib.bl_set_camera(self._h, ctypes.byref(cam)))
+        self._have_camera = True
+
+    def trace_level_pixels(self, level, rows=None, blocks=None):
+        """Trace a level whose camera pixels are generated on the device (bl_trace_level_pixels): `rows` = image rows of
+        the level's raster (None with blocks None: the whole raster), or `blocks` = (B, 2) int32 (v, u) block locations."""
+        if not getattr(self, '_have_camera', False):
+            self.set_camera()
+        res = self.config.resolution << level
+        st = LevelStats()
+        if blocks is not None:
+            units = np.ascontiguousarray(blocks, np.int32).reshape(-1, 2)
+            n_units, per, kind = len(units), self.config.block_size ** 2, PIXELS_BLOCKS
+        elif rows is not None:
+            units = np.ascontiguousarray(rows, np.int32).ravel()
+            n_units, per, kind = len(units), res, PIXELS_ROWS
+        else:
+            units, n_units, per, kind = None, res, res, PIXELS_ROWS
+        self._check(_lib.bl_trace_level_pixels(self._h, level, kind, _ptr(units), n_units, ctypes.byref(st)))
+        self._rays[level] = n_units * per
+        self._steps[level] = st.geodesic_num_steps
+        return st.as_dict()
+
+    def download_camera(self, level=0):
+        """(pos (N,4), dir (N,4), factor (N)) of the level's rays as they sit in HBM: bl_download_camera."""
+        n = self._rays[level]
+        pos, dirs, fac = np.empty((n, 4)), np.empty((n, 4)), np.empty(n)
+        self._check(_lib.bl_download_camera(self._h, level, _ptr(pos), _ptr(dirs), _ptr(fac)))
+        return pos, dirs, fac
 
     def trace_level(self, level, pos, dirs, fac):
         pos, dirs, fac = (np.ascontiguousarray(a, np.float64) for a in (pos, dirs, fac))

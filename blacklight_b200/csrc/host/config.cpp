@@ -393,4 +393,22 @@ RunConfig make_config(const InputFile &in) {
   return c;
 }
 
+bl_camera make_bl_camera(const RunConfig &cfg) {
+  bl_camera c{};
+  c.type = cfg.camera.type == 0 ? BL_CAMERA_PLANE : BL_CAMERA_PINHOLE;
+  c.normalization = cfg.camera.normalization == 0 ? BL_NORM_CAMERA : BL_NORM_INFINITY;
+  c.width = cfg.camera.width;
+  c.r = cfg.camera.r;
+  for (int m = 0; m < 4; m++) {
+    c.x[m] = cfg.frame.x[m];
+    c.u_con[m] = cfg.frame.u_con[m];
+    c.u_cov[m] = cfg.frame.u_cov[m];
+    c.norm_con[m] = cfg.frame.norm_con[m];
+    c.norm_con_c[m] = cfg.frame.norm_con_c[m];
+    c.hor_con_c[m] = cfg.frame.hor_con_c[m];
+    c.vert_con_c[m] = cfg.frame.vert_con_c[m];
+  }
+  return c;
+}
+
 }  // namespace blh

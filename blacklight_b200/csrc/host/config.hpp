@@ -36,4 +36,7 @@ struct RunConfig {
 
 RunConfig make_config(const InputFile &in);
 
+// What bl_set_camera takes: the frame InitializeCamera leaves plus the per-pixel parameters (camera.cpp:53-380)
+bl_camera make_bl_camera(const RunConfig &cfg);
+
 }  // namespace blh

@@ -399,6 +399,11 @@ RunTimings run_input_file(const std::string &path, const std::vector<int> &devic
   const int bs = p.adaptive_block_size, res = p.camera_resolution;
   if (N > 1 && adaptive) p.level0_block_major = 1;   // root blocks are handed over block by block, like refined ones
 
+  // camera pixels are generated on the device unless BLACKLIGHT_HOST_CAMERA=1 (A/B and parity checks)
+  const char *host_camera_env = std::getenv("BLACKLIGHT_HOST_CAMERA");
+  const bool host_camera = host_camera_env && std::atoi(host_camera_env) != 0;
+  const bl_camera cam = make_bl_camera(cfg);
+
   Workers W;
   W.w.resize((size_t)N);
   for (int i = 0; i < N; i++) {
@@ -409,6 +414,7 @@ RunTimings run_input_file(const std::string &path, const std::vector<int> &devic
     bl_params q = p;
     q.device = w.device;
     if (bl_create(&q, &w.ctx) != BL_OK) throw Error(bl_last_error(nullptr));
+    check(w.ctx, bl_set_camera(w.ctx, &cam));
   });
   bl_ctx *ctx0 = W.w[0].ctx;
   const int Q = bl_image_num_quantities(ctx0);
@@ -426,24 +432,33 @@ RunTimings run_input_file(const std::string &path, const std::vector<int> &devic
       for (long long k = i; k < count; k += N) u.push_back(k);
     }
   };
-  // trace this device's share of a level whose camera arrays it builds itself
+  // trace this device's share of a level: the pixels of its rows / blocks are generated on the device
+  // (bl_trace_level_pixels; BLACKLIGHT_HOST_CAMERA=1 builds them here and uploads them, as round 1 did)
   auto trace_share = [&](Worker &w, int level, const LevelData &L) {
     const std::vector<long long> &u = w.units[(size_t)level];
     const long long rays = (long long)u.size() * unit_rays(level);
-    w.pos.resize((size_t)rays * 4);
-    w.dir.resize((size_t)rays * 4);
-    w.factor.resize((size_t)rays);
-    if (level == 0 && !block_units) {
-      camera_rows(cfg.camera, cfg.frame, u.data(), (long long)u.size(), w.pos.data(), w.dir.data(), w.factor.data());
-    } else {
-      w.locs.resize(u.size() * 2);
-      for (size_t k = 0; k < u.size(); k++) {
+    const bool rows = level == 0 && !block_units;
+    w.locs.resize(rows ? u.size() : u.size() * 2);
+    for (size_t k = 0; k < u.size(); k++) {
+      if (rows) {
+        w.locs[k] = (int32_t)u[k];
+      } else {
         w.locs[2 * k] = L.locs[2 * (size_t)u[k]];
         w.locs[2 * k + 1] = L.locs[2 * (size_t)u[k] + 1];
       }
-      camera_blocks(cfg.camera, cfg.frame, level, bs, w.locs.data(), (long long)u.size(), w.pos.data(), w.dir.data(), w.factor.data());
     }
-    check(w.ctx, bl_trace_level(w.ctx, level, w.pos.data(), w.dir.data(), w.factor.data(), rays, &w.st));
+    if (!host_camera) {
+      check(w.ctx, bl_trace_level_pixels(w.ctx, level, rows ? BL_PIXELS_ROWS : BL_PIXELS_BLOCKS, w.locs.data(), (int64_t)u.size(), &w.st));
+    } else {
+      w.pos.resize((size_t)rays * 4);
+      w.dir.resize((size_t)rays * 4);
+      w.factor.resize((size_t)rays);
+      if (rows)
+        camera_rows(cfg.camera, cfg.frame, u.data(), (long long)u.size(), w.pos.data(), w.dir.data(), w.factor.data());
+      else
+        camera_blocks(cfg.camera, cfg.frame, level, bs, w.locs.data(), (long long)u.size(), w.pos.data(), w.dir.data(), w.factor.data());
+      check(w.ctx, bl_trace_level(w.ctx, level, w.pos.data(), w.dir.data(), w.factor.data(), rays, &w.st));
+    }
     w.ms_geodesic += w.st.ms_geodesic;
   };
   auto bad_geodesics_warning = [&](long long rays) {
@@ -470,11 +485,15 @@ RunTimings run_input_file(const std::string &path, const std::vector<int> &devic
   int level0_steps = 0;
   if (N == 1) {
     // single device: the whole raster, exactly as the reference's main
-    if (!cfg.checkpoint_geodesic_load) camera_root(cfg.camera, cfg.frame, root.pos, root.dir, root.factor);
+    // (the host copy of the camera arrays is only needed where it is written out)
+    if (!cfg.checkpoint_geodesic_load && (host_camera || cfg.output_camera || cfg.checkpoint_geodesic_save))
+      camera_root(cfg.camera, cfg.frame, root.pos, root.dir, root.factor);
     if (cfg.checkpoint_geodesic_load)
       load_geodesic_checkpoint(ctx0, cfg, root, &st);
-    else
+    else if (host_camera)
       check(ctx0, bl_trace_level(ctx0, 0, root.pos.data(), root.dir.data(), root.factor.data(), root.rays, &st));
+    else
+      check(ctx0, bl_trace_level_pixels(ctx0, 0, BL_PIXELS_ROWS, nullptr, res, &st));
     W.w[0].st = st;
     W.w[0].ms_geodesic += st.ms_geodesic;
     bad_geodesics_warning(root.rays);
@@ -695,10 +714,17 @@ RunTimings run_input_file(const std::string &path, const std::vector<int> &devic
       t0 = now_s();
       LevelData &C = levels[(size_t)level + 1];
       if (N == 1) {
-        camera_refined(cfg.camera, cfg.frame, level + 1, bs, L.locs, L.flags, C.locs, C.pos, C.dir, C.factor);
+        if (host_camera || cfg.output_camera) {
+          camera_refined(cfg.camera, cfg.frame, level + 1, bs, L.locs, L.flags, C.locs, C.pos, C.dir, C.factor);
+        } else {
+          child_blocks(L.locs, L.flags, C.locs);
+        }
         C.blocks = (int)(C.locs.size() / 2);
         C.rays = (long long)C.blocks * bs * bs;
-        check(ctx0, bl_trace_level(ctx0, level + 1, C.pos.data(), C.dir.data(), C.factor.data(), C.rays, &st));
+        if (host_camera)
+          check(ctx0, bl_trace_level(ctx0, level + 1, C.pos.data(), C.dir.data(), C.factor.data(), C.rays, &st));
+        else
+          check(ctx0, bl_trace_level_pixels(ctx0, level + 1, BL_PIXELS_BLOCKS, C.locs.data(), C.blocks, &st));
         W.w[0].st = st;
         W.w[0].ms_geodesic += st.ms_geodesic;
       } else {

@@ -72,6 +72,12 @@ int blh_camera_frame(const blh_config *c, double out[28]) {
   return 0;
 }
 
+int blh_camera_struct(const blh_config *c, bl_camera *out) {
+  if (!c || !out) { g_error = "null argument"; return 1; }
+  *out = blh::make_bl_camera(c->cfg);
+  return 0;
+}
+
 int64_t blh_camera_root(const blh_config *c, double *pos, double *dir, double *factor) {
   if (!c || !pos || !dir || !factor) { g_error = "null argument"; return -1; }
   std::vector<double> p, d, f;

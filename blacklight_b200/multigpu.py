@@ -51,22 +51,17 @@ def adaptive_worker(cfg, ctx, rank, world, max_level, num_render=0):
     clock = time.perf_counter
     t0 = clock()
     locs_all, pix = _root_blocks(cfg)
-    pos_r, dir_r, fac_r = cfg.camera_root()
     T['camera'] += clock() - t0
     mine_levels = []
     level = 0
-    pos = dirs = fac = None
     while True:
         t0 = clock()
         blocks = shard_blocks(len(locs_all), rank, world)
-        if level == 0:
-            sel = pix[blocks].ravel()
-            pos, dirs, fac = pos_r[sel], dir_r[sel], fac_r[sel]
-        else:             # refined level: camera pixels of this rank's blocks only
-            pos, dirs, fac = cfg.camera_blocks(level, locs_all[blocks])
         t1 = clock()
-        T['camera' if level else 'select'] += t1 - t0
-        stats = ctx.trace_level(level, pos, dirs, fac)
+        T['select'] += t1 - t0
+        # the pixels of this rank's blocks are generated on the device (bl_trace_level_pixels): only the block list
+        # crosses PCIe, and the host camera stage of round 1 is gone
+        stats = ctx.trace_level_pixels(level, blocks=locs_all[blocks])
         t2 = clock()
         image, render, rstats = ctx.radiate_level(level, num_render=num_render)
         t3 = clock()

@@ -28,6 +28,10 @@ void blh_config_set_device(blh_config *cfg, int device, int64_t tile_rays);
 void blh_config_set_level0_block_major(blh_config *cfg, int block_major);
 /* cam_x, u_con, u_cov, norm_con, norm_con_c, hor_con_c, vert_con_c: 7 x 4 doubles */
 int blh_camera_frame(const blh_config *cfg, double out[28]);
+/* The same frame with the per-pixel parameters, as bl_set_camera takes it (pixels are then generated on the device by
+ * bl_trace_level_pixels; the blh_camera_* functions below are the host versions, kept for output_camera, checkpoints
+ * and as the parity reference of the device kernel). */
+int blh_camera_struct(const blh_config *cfg, bl_camera *out);
 /* pos, dir: (res*res,4); factor: (res*res).  Returns the number of rays. */
 int64_t blh_camera_root(const blh_config *cfg, double *pos, double *dir, double *factor);
 /* Children of the flagged parents.  Output buffers sized for 4 * (#flags set) blocks of

@@ -522,23 +522,19 @@ class _FakeConfig:
     """Stands in for blacklight_b200.Config in the sharded-adaptive host logic test: an 8x8 image of 2x2 blocks."""
     resolution, block_size = 8, 2
 
-    def camera_root(self):
-        m = np.arange(64, dtype=np.float64)
-        return np.stack([m, m, m, m], 1), np.stack([-m, m, m, m], 1), m.copy()
-
-    def camera_blocks(self, level, locs):
-        locs = np.asarray(locs, np.int32).reshape(-1, 2)
-        tag = 1000.0 * level + (locs[:, 0].repeat(4) * 64 + locs[:, 1].repeat(4)) * 4.0 + np.tile(np.arange(4.0), len(locs))
-        return np.stack([tag] * 4, 1), np.stack([-tag] * 4, 1), tag.copy()
-
 
 class _FakeContext:
-    """"Image" of a ray = its momentum factor (so assembly order is checkable); refine blocks whose first
-    pixel's tag is a multiple of 3."""
+    """"Image" of a ray = a tag of its pixel (level 0: the raster index, so assembly order is checkable); refine blocks
+    whose first pixel's tag is a multiple of 3."""
     level0_block_major = True
 
-    def trace_level(self, level, pos, dirs, fac):
-        self.fac = fac
+    def trace_level_pixels(self, level, rows=None, blocks=None):
+        locs = np.asarray(blocks, np.int32).reshape(-1, 2)
+        if level == 0:
+            i, j = np.divmod(np.arange(4), 2)
+            self.fac = ((locs[:, 0, None] * 2 + i[None, :]) * 8 + locs[:, 1, None] * 2 + j[None, :]).astype(np.float64).ravel()
+        else:
+            self.fac = 1000.0 * level + (locs[:, 0].repeat(4) * 64 + locs[:, 1].repeat(4)) * 4.0 + np.tile(np.arange(4.0), len(locs))
         return {'num_bad_geodesics': 0}
 
     def radiate_level(self, level, num_render=0):

@@ -1212,3 +1212,102 @@ def test_cks_polarized_faint_pixels_are_roundoff_limited(gpu, tmp_path):
     assert np.all(err_ref[lit] <= np.maximum(PIXEL_TOL, 100.0 * kappa[lit]))
     assert np.all(kappa[off] > 1e-8)
     assert np.all(I_ref[off] < 1e-5 * peak)
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float64).view(np.uint64)
+
+
+DEVICE_CAMERAS = [
+    ('formula.input', {'camera_resolution': 48}),                                                  # plane, a = 0.9, the bench's C1 camera
+    ('formula.input', {'camera_resolution': 40, 'camera_type': 'pinhole', 'camera_th': '30.0', 'camera_ph': '50.0',
+                       'camera_rotation': '25.0', 'camera_urn': '0.1', 'camera_uthn': '0.05', 'camera_uphn': '-0.02',
+                       'camera_k_th': '0.1', 'camera_k_ph': '-0.05', 'image_normalization': 'infinity'}),
+    ('formula.input', {'camera_resolution': 32, 'camera_th': '0.0'}),                              # pole camera, plane
+    ('formula.input', {'camera_resolution': 32, 'camera_th': '180.0', 'camera_type': 'pinhole'}),  # south pole, pinhole
+    ('formula.input', {'camera_resolution': 32, 'ray_flat': 'true', 'camera_rotation': '10.0'}),
+    ('formula.input', {'camera_resolution': 32, 'formula_spin': '0.0', 'camera_th': '90.0'}),      # a = 0: hypot(x, 0); equatorial
+    ('simulation.input', {'camera_resolution': 64}),                                               # the bench's C2 / C4 camera
+]
+
+
+@pytest.mark.parametrize('base,over', DEVICE_CAMERAS)
+def test_device_camera_is_bitwise_the_host_camera(base, over, gpu, tmp_path):
+    """bl_trace_level_pixels (csrc/camera_kernel.cu): positions, covariant momenta and frequency factors of the rays as the
+    device generates them, against the host camera (csrc/host/camera.cpp, itself bit-identical to the reference's
+    checkpoint: test_cpu_host.py::test_camera_bit_exact) -- every array element bit for bit, whole raster and a row
+    subset, plane / pinhole / pole / flat-space / moving / rotated cameras, both frequency normalisations."""
+    case = Case(tmp_path, base, over)
+    cfg = case.config()
+    ctx = bl.Context(cfg)
+    res = cfg.resolution
+    pos, dirs, fac = cfg.camera_root()
+    st = ctx.trace_level_pixels(0)
+    dpos, ddir, dfac = ctx.download_camera(0)
+    assert np.array_equal(_bits(dpos), _bits(pos)) and np.array_equal(_bits(ddir), _bits(dirs)) and np.array_equal(_bits(dfac), _bits(fac))
+    num_d = ctx.download_samples(0, arrays=False)
+    # the geodesics integrated from them are the host path's
+    st_h = ctx.trace_level(0, pos, dirs, fac)
+    num_h = ctx.download_samples(0, arrays=False)
+    assert st['num_samples'] == st_h['num_samples'] and np.array_equal(num_d['num'], num_h['num']) and np.array_equal(num_d['flags'], num_h['flags'])
+    rows = np.array([res - 1, 3, 0, res // 2, 17 % res], np.int64)
+    rpos, rdir, rfac = cfg.camera_rows(rows)
+    ctx.trace_level_pixels(0, rows=rows)
+    dpos, ddir, dfac = ctx.download_camera(0)
+    assert np.array_equal(_bits(dpos), _bits(rpos)) and np.array_equal(_bits(ddir), _bits(rdir)) and np.array_equal(_bits(dfac), _bits(rfac))
+    ctx.close()
+
+
+def test_device_camera_blocks_and_large_raster(gpu, tmp_path):
+    """Refined-level blocks (effective resolution res * 2^level, block-major) and a 1024^2 raster (10^6 pixels) bit for bit
+    the host camera's; bad unit lists are refused."""
+    over = {'camera_resolution': 32, 'adaptive_max_level': 3, 'adaptive_block_size': 8, 'camera_th': '70.0', 'camera_rotation': '5.0'}
+    case = Case(tmp_path / 'blocks', 'adaptive.input', over)
+    cfg = case.config()
+    ctx = bl.Context(cfg)
+    rng = np.random.default_rng(7)
+    for level in (0, 1, 2, 3):
+        nb = (32 << level) // 8
+        locs = np.stack([rng.integers(0, nb, 23), rng.integers(0, nb, 23)], 1).astype(np.int32)
+        locs[0], locs[1] = (0, 0), (nb - 1, nb - 1)
+        pos, dirs, fac = cfg.camera_blocks(level, locs)
+        ctx.trace_level_pixels(level, blocks=locs)
+        dpos, ddir, dfac = ctx.download_camera(level)
+        assert np.array_equal(_bits(dpos), _bits(pos)) and np.array_equal(_bits(ddir), _bits(dirs)) and np.array_equal(_bits(dfac), _bits(fac)), level
+    with pytest.raises(bl.BlacklightError):
+        ctx.trace_level_pixels(1, blocks=np.array([[0, 8]], np.int32))     # 8 blocks per side at level 1
+    with pytest.raises(bl.BlacklightError):
+        ctx.trace_level_pixels(0, rows=np.array([32], np.int32))
+    ctx.close()
+    big = Case(tmp_path / 'big', 'simulation.input', {'camera_resolution': 1024, 'camera_type': 'pinhole', 'ray_max_steps': 40})
+    cfg = big.config()
+    ctx = bl.Context(cfg)
+    pos, dirs, fac = cfg.camera_root()
+    ctx.trace_level_pixels(0)
+    dpos, ddir, dfac = ctx.download_camera(0)
+    assert np.array_equal(_bits(dpos), _bits(pos)) and np.array_equal(_bits(ddir), _bits(dirs)) and np.array_equal(_bits(dfac), _bits(fac))
+    ctx.close()
+
+
+@pytest.mark.parametrize('base,over', [
+    ('simulation.input', {'camera_resolution': 24, 'image_polarization': 'true', 'output_camera': 'true'}),
+    ('adaptive.input', {'camera_resolution': 32, 'adaptive_max_level': 2, 'output_camera': 'true', 'adaptive_num_regions': 1,
+                        'adaptive_region_1_level': 2, 'adaptive_region_1_x_min': '-4', 'adaptive_region_1_x_max': '4',
+                        'adaptive_region_1_y_min': '-4', 'adaptive_region_1_y_max': '4'}),
+    ('formula.input', {'camera_resolution': 20, 'camera_type': 'pinhole', 'output_camera': 'true'}),
+])
+def test_drop_in_with_device_camera_matches_host_camera(base, over, gpu, tmp_path):
+    """The drop-in driver generates the camera pixels on the device by default; BLACKLIGHT_HOST_CAMERA=1 keeps round 1's
+    host arrays + upload.  Both runs (one device and three contexts) must write identical files, camera arrays included."""
+    case = Case(tmp_path, base, over)
+    dev, _ = case.run_gpu_file(tag='dev', devices=[0])
+    dev3, _ = case.run_gpu_file(tag='dev3', devices=[0, 0, 0])
+    os.environ['BLACKLIGHT_HOST_CAMERA'] = '1'
+    try:
+        host, _ = case.run_gpu_file(tag='host', devices=[0])
+    finally:
+        del os.environ['BLACKLIGHT_HOST_CAMERA']
+    assert sorted(dev) == sorted(host) == sorted(dev3)
+    for k in host:
+        assert np.array_equal(dev[k], host[k], equal_nan=True), k
+        assert np.array_equal(dev3[k], host[k], equal_nan=True), k
