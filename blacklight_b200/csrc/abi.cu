@@ -22,7 +22,8 @@ extern "C" int bl_polarized_split_fields(int num_freq);
 extern "C" int bl_polarized_split_slabs(int slab, int s_top);
 extern "C" cudaError_t bl_launch_radiate_polarized_split(const RadArgs *args, const RadParams *params, double *scratch,
                                                          double *cam_map, int slab, int s_top, cudaStream_t stream,
-                                                         cudaEvent_t *events, long long *launches);
+                                                         cudaEvent_t *events, long long *launches,
+                                                         const int64_t *alive, int num_alive);
 extern "C" cudaError_t bl_launch_relayout_grid(const float *prim, int n_var, const int *var_index, size_t cells,
                                                float4 *out, float *kappa_out, cudaStream_t stream);
 extern "C" cudaError_t bl_launch_unpack_samples(const StepBuffer *sb, const int32_t *num, const double *cam_dir,
@@ -37,6 +38,10 @@ extern "C" cudaError_t bl_launch_refine(const double *image, int64_t stride, int
 extern "C" cudaError_t bl_launch_camera_pixels(const CameraDev *cam, int kind, const int32_t *units, int eff_res, int block_size,
                                                int64_t num_pixels, double *cam_pos, double *cam_dir, double *mom_factor,
                                                cudaStream_t stream);
+extern "C" int bl_ray_order_max_buckets(void);
+extern "C" size_t bl_ray_order_workspace(int64_t rays, int buckets);
+extern "C" cudaError_t bl_launch_ray_order(const int32_t *num, int64_t rays, int unit, int buckets, int32_t *workspace,
+                                           int32_t *order, cudaStream_t stream);
 extern "C" cudaError_t bl_launch_fp64_peak(double *out, int blocks, int iters, cudaStream_t stream);
 extern "C" cudaError_t bl_launch_division_selftest(unsigned long long seed, int blocks, int iters,
                                                    unsigned long long *mismatches, cudaStream_t stream);
@@ -55,6 +60,10 @@ struct Level {
   double *image = nullptr;    // device (Q, rays)
   double *render = nullptr;   // device (R,3,rays)
   // three-stage polarized pipeline (radiate_pol_split.cu): slab scratch and the camera half-step map of one wave
+  // rays of one wave sorted by length, longest first (ray_order.cu): the radiation kernels take their rays from it
+  int32_t *order = nullptr;        // device (wave_rays)
+  int32_t *order_ws = nullptr;     // device workspace of the sort; its tail holds the bucket totals
+  int32_t order_unit = 0, order_buckets = 0;   // bucket = ceil(num / unit); 0 buckets: rays are taken in index order
   double *scratch = nullptr;  // device (fields, slab, wave_rays)
   double *cam_map = nullptr;  // device (10, wave_rays)
   int32_t slab = 0;           // samples per slab; 0 = the level uses the fused kernel
@@ -93,6 +102,7 @@ struct bl_ctx {
   size_t units_cap = 0;           // its capacity in int32
   int rad_prefetch = 2;     // BL_RAD_PREFETCH: samples ahead the radiation kernels prefetch step-buffer records into L2 (0 = off)
   int pol_slab = 0;         // BL_POL_SLAB: samples per slab of that pipeline (0 = chosen from the HBM budget)
+  int ray_order = 1;        // BL_RAY_ORDER=0: radiation kernels take the rays in index order (A/B comparisons)
   bool pol_fused = false;   // BL_POL_FUSED=1: keep the single fused polarized kernel (A/B comparisons, parity cross-check)
 };
 
@@ -123,6 +133,7 @@ cudaError_t dev_alloc(T **p, size_t count) {
 void free_level(Level &L) {
   cudaFree(L.cam_pos); cudaFree(L.cam_dir); cudaFree(L.mom); cudaFree(L.num); cudaFree(L.flags);
   cudaFree(L.step); cudaFree(L.image); cudaFree(L.render); cudaFree(L.scratch); cudaFree(L.cam_map);
+  cudaFree(L.order); cudaFree(L.order_ws);
   cudaFree(L.tap_inds); cudaFree(L.tap_fracs); cudaFree(L.tap_nan); cudaFree(L.tap_cut); cudaFree(L.tap_fb);
   L = Level();
 }
@@ -332,6 +343,31 @@ void fill_rad_params(const bl_params &p, RadParams &r) {
       r.log_ka_high_q = std::log(r.kappa_aa_high_q); r.log_ka_high_v = std::log(r.kappa_aa_high_v);
     }
   }
+  if (sim && p.plasma_kappa_frac != 0.0 && r.polarization) {
+    const double kk = p.plasma_kappa;
+    const double x[6] = {r.kappa_jj_x_i, r.kappa_jj_x_q, r.kappa_jj_x_v, r.kappa_aa_x_i, r.kappa_aa_x_q, r.kappa_aa_x_v};
+    // d ln(lo) / d ln nu and d ln(hi) / d ln nu of the six bridged coefficients (pol_common.cuh: synchrotron_polarized)
+    const double j_lo = -2.0 + 1.0 / 3.0, j_hi = -2.0 - (kk - 2.0) / 2.0, a_lo = -2.0 / 3.0, a_hi = -(1.0 + kk) / 2.0;
+    const double s_lo[6] = {j_lo, j_lo, j_lo - 0.35, a_lo, a_lo, a_lo - 0.35};
+    const double s_hi[6] = {j_hi, j_hi, j_hi - 0.5, a_hi, a_hi, a_hi - 0.5};
+    for (int l = 0; l < p.image_num_frequencies; l++) {
+      const double d = std::log(p.image_frequencies[l]) - std::log(p.image_frequencies[0]);
+      r.dlog_freqs[l] = d;
+      for (int t = 0; t < 6; t++) {
+        r.kappa_k[t][l] = std::exp(-x[t] * (s_lo[t] - s_hi[t]) * d);
+        r.kappa_kinv[t][l] = std::exp(x[t] * (s_lo[t] - s_hi[t]) * d);
+      }
+      r.rho_c84[l] = std::exp(0.84 * d);
+      r.rho_cm12[l] = std::exp(-0.5 * d);
+      r.rho_cqe_low[l] = std::exp(r.kappa_rho_q_low_e * d);
+      r.rho_cqe_high[l] = std::exp(r.kappa_rho_q_high_e * d);
+    }
+    for (int t = 0; t < 6; t++) {
+      r.kappa_inv_x[t] = 1.0 / x[t];
+      r.kappa_slope_lo[t] = s_lo[t];
+      r.kappa_slope_hi[t] = s_hi[t];
+    }
+  }
   if (sim && p.plasma_power_frac != 0.0) r.log_power_gmin = std::log(2.0 * p.plasma_gamma_min * p.plasma_gamma_min / 3.0);
   r.fallback_nan = p.fallback_nan; r.fallback_rho = p.fallback_rho; r.fallback_pgas = p.fallback_pgas;
   r.fallback_kappa = p.fallback_kappa;
@@ -403,6 +439,7 @@ int bl_create(const bl_params *params, bl_ctx **out) {
   if (const char *e = getenv("BL_GEO_BLOCKS")) ctx->geo_min_blocks = atoi(e);
   if (const char *e = getenv("BL_POL_SLAB")) ctx->pol_slab = atoi(e);
   if (const char *e = getenv("BL_RAD_PREFETCH")) ctx->rad_prefetch = atoi(e);
+  if (const char *e = getenv("BL_RAY_ORDER")) ctx->ray_order = atoi(e);
   if (const char *e = getenv("BL_POL_FUSED")) ctx->pol_fused = atoi(e) != 0;
 #define CREATE_CHECK(call)                                                                   \
   do {                                                                                       \
@@ -828,6 +865,29 @@ int radiate_wave(bl_ctx *ctx, Level &L, int64_t first, int64_t count, int s_top,
   // the unpolarized kernel is instantiated for frequency-count buckets of 1, 4 and 32 (one object file each)
   const int F = ctx->rad.num_freq;
   cudaError_t le;
+  // rays sorted by length, longest first; alive[s] = rays with more than s * unit samples (a prefix of the list)
+  std::vector<int64_t> alive;
+  A.order = nullptr;
+  A.active = count;
+  if (L.order_buckets > 0 && L.order) {
+    const int nb = L.order_buckets;
+    BL_CUDA_CHECK(bl_launch_ray_order(L.num + first, count, L.order_unit, nb, L.order_ws, L.order, ctx->stream));
+    ctx->launches += 3;
+    std::vector<int32_t> totals((size_t)nb);
+    const int64_t chunks = (count + 1023) / 1024;
+    BL_CUDA_CHECK(cudaMemcpyAsync(totals.data(), L.order_ws + (size_t)nb * (size_t)chunks, (size_t)nb * sizeof(int32_t),
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+    BL_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    // bucket b holds the rays with ceil(num / unit) == nb - 1 - b
+    alive.assign((size_t)nb, 0);
+    int64_t run = 0;
+    for (int key = nb - 1; key >= 1; key--) {
+      run += totals[(size_t)(nb - 1 - key)];
+      alive[(size_t)(key - 1)] = run;     // rays with ceil(num / unit) > key - 1
+    }
+    A.order = L.order;
+    A.active = alive[0];                  // rays with at least one sample
+  }
   if (ctx->rad.polarization && L.slab > 0 && L.scratch && !L.tap_nan) {
     // the Stokes state of the pipeline starts (and stays between slabs) in the image columns of these rays
     BL_CUDA_CHECK(cudaMemset2DAsync(L.image + first, (size_t)L.rays * sizeof(double), 0, (size_t)count * sizeof(double),
@@ -839,7 +899,8 @@ int radiate_wave(bl_ctx *ctx, Level &L, int64_t first, int64_t count, int s_top,
       ctx->stage_events.push_back(e);
     }
     BL_CUDA_CHECK(bl_launch_radiate_polarized_split(&A, &ctx->rad, L.scratch, L.cam_map, L.slab, s_top, ctx->stream,
-                                                    ctx->stage_events.data(), &ctx->launches));
+                                                    ctx->stage_events.data(), &ctx->launches,
+                                                    alive.empty() ? nullptr : alive.data(), (int)alive.size()));
     *split_slabs = slabs;
     return BL_OK;
   }
@@ -946,6 +1007,14 @@ int trace_level_impl(bl_ctx *ctx, int level, int64_t num_rays, bl_level_stats *s
     BL_CUDA_CHECK(dev_alloc(&L.step, (size_t)L.wave_rays * per_ray / sizeof(double)));
     int rc = alloc_split_scratch(ctx, L, slab);
     if (rc) return rc;
+    // length buckets of the ray ordering: the pipeline's slabs, else 64 groups over the step capacity
+    L.order_unit = slab > 0 ? slab : (ctx->params.ray_max_steps + 63) / 64;
+    L.order_buckets = ctx->params.ray_max_steps / L.order_unit + 2;
+    if (!ctx->ray_order || L.order_buckets > bl_ray_order_max_buckets()) L.order_buckets = 0;
+    if (L.order_buckets > 0) {
+      BL_CUDA_CHECK(dev_alloc(&L.order, (size_t)L.wave_rays));
+      BL_CUDA_CHECK(dev_alloc(&L.order_ws, bl_ray_order_workspace(L.wave_rays, L.order_buckets)));
+    }
   }
   BL_CUDA_CHECK(cudaMemsetAsync(ctx->counters, 0, sizeof(GeoCounters), ctx->stream));
   L.stats = bl_level_stats();

@@ -139,6 +139,12 @@ BF_HD double log_bf(double x) {
   return x != x ? x : res;
 }
 
+// log_bf with log 0 = -inf (log_bf itself returns about -744 there: its callers in the frequency loops never pass zero)
+BF_HD double log_bf_z(double x) {
+  double res = log_bf(x);
+  return x == 0.0 ? -1.0 / 0.0 : res;
+}
+
 // sinh and cosh of the same argument from two exponentials; below |x| = 0.25 the odd series keeps sinh's
 // relative accuracy (selected, not branched).  < 3 ulp.
 BF_HD void sinhcosh_bf(double x, double &sh, double &ch) {

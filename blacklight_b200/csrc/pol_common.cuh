@@ -311,19 +311,21 @@ __device__ __forceinline__ void pol_sample(const RadParams &P, const rad::Plasma
   q.log_ncs = q.log_ne = q.cot = q.power_vb = q.inv_nu_k = 0.0;
   q.lvd_j = q.lvf_j = q.lvd_a = q.lvf_a = 0.0;
   if (has_power<DIST>(P) || has_kappa<DIST>(P)) {
-    q.log_ncs = log(q.nu_c * sin_b);
+    // table-driven logarithms / exponentials (bf_math.cuh) here too: ten libm calls per sample were an eighth of the
+    // coefficient stage.  sin(theta_B) = 0 or 1 gives logarithms of zero, hence the _z variant (-inf, as libm).
+    q.log_ncs = bfm::log_bf_z(q.nu_c * sin_b);
     q.log_ne = bfm::log_bf(s.n_e_cgs);
-    double log_sin = log(sin_b);
+    double log_sin = bfm::log_bf_z(sin_b);
     if (has_power<DIST>(P)) {
       q.cot = cos_b / sin_b;
       q.power_vb = pow(3.1 * exp(-1.92 * log_sin) - 3.1, 0.512);
     }
     if (has_kappa<DIST>(P)) {
       q.inv_nu_k = 1.0 / (q.nu_c * P.plasma_w * P.plasma_w * P.plasma_kappa * P.plasma_kappa * sin_b);
-      q.lvd_j = 0.48 * log(exp(-2.4 * log_sin) - 1.0);
-      q.lvf_j = 0.44 * log(exp(-2.5 * log_sin) - 1.0);
-      q.lvd_a = 0.446 * log(exp(-2.28 * log_sin) - 1.0);
-      q.lvf_a = 0.5 * log(exp(-2.05 * log_sin) - 1.0);
+      q.lvd_j = 0.48 * bfm::log_bf_z(bfm::exp_bf(-2.4 * log_sin) - 1.0);
+      q.lvf_j = 0.44 * bfm::log_bf_z(bfm::exp_bf(-2.5 * log_sin) - 1.0);
+      q.lvd_a = 0.446 * bfm::log_bf_z(bfm::exp_bf(-2.28 * log_sin) - 1.0);
+      q.lvf_a = 0.5 * bfm::log_bf_z(bfm::exp_bf(-2.05 * log_sin) - 1.0);
     }
   }
 }
@@ -404,7 +406,7 @@ __device__ __forceinline__ void synchrotron_polarized(const RadParams &P, const 
       double xx = nu_cgs * q.inv_nu_k;
       double lm035 = -0.35 * lx, lm12 = -0.5 * lx;
       {
-        const double ix_i = 1.0 / P.kappa_jj_x_i, ix_q = 1.0 / P.kappa_jj_x_q, ix_v = 1.0 / P.kappa_jj_x_v;
+        const double ix_i = P.kappa_inv_x[0], ix_q = P.kappa_inv_x[1], ix_v = P.kappa_inv_x[2];
         double lva = P.log_k_j_pref + q.log_ne + q.log_ncs - 2.0 * log_nu;  // includes the sin(theta_B) factor
         double l_lo = P.log_kjl + lva + lx * (1.0 / 3.0);
         double l_hi = P.log_kjh + lva - (P.plasma_kappa - 2.0) / 2.0 * lx;
@@ -414,7 +416,7 @@ __device__ __forceinline__ void synchrotron_polarized(const RadParams &P, const 
                          P.kappa_jj_x_v, ix_v) * q.sgn;
       }
       {
-        const double ix_i = 1.0 / P.kappa_aa_x_i, ix_q = 1.0 / P.kappa_aa_x_q, ix_v = 1.0 / P.kappa_aa_x_v;
+        const double ix_i = P.kappa_inv_x[3], ix_q = P.kappa_inv_x[4], ix_v = P.kappa_inv_x[5];
         double lva = P.log_k_a_pref + q.log_ne;
         double l_lo = P.log_kal + lva - 2.0 / 3.0 * lx;
         double l_hi = P.log_kah_base + lva - (1.0 + P.plasma_kappa) / 2.0 * lx;
@@ -446,6 +448,75 @@ __device__ __forceinline__ void synchrotron_polarized(const RadParams &P, const 
         C.rho[1] += (1.0 - P.kappa_rho_frac) * v_lo + P.kappa_rho_frac * v_hi;
       }
     }
+  }
+}
+
+// The polarized kappa coefficients of ALL image frequencies of one sample, term by term (kappa-only plasmas; same
+// formulas as synchrotron_polarized<4>, simulation_coefficients.cpp:608-698).  For a bridged coefficient
+// (lo^-x + hi^-x)^(-1/x) = exp(m - ln(1 + e^(-x |d|)) / x), d = ln lo - ln hi, m = min(ln lo, ln hi), both logarithms are
+// affine in ln nu, so e^(-x d) at frequency l is e^(-x d) at frequency 0 times a host constant: two exponentials per
+// sample (e^(-x d_0), e^(+x d_0): the one not selected may overflow, harmlessly) replace one per frequency.  The pure
+// powers of nu / nu_kappa inside the Faraday fits are shared the same way.  store(k, l, value): coefficient k = 0..7
+// (j_I, j_Q, j_V, alpha_I, alpha_Q, alpha_V, rho_Q, rho_V) at frequency l.
+template <class Store>
+__device__ __forceinline__ void kappa_polarized_all(const RadParams &P, const PolSample &q, int F, Store store) {
+  const double e2 = phys::e * phys::e;
+  const double log_nu0 = q.log_om + P.log_freqs[0];
+  const double lr0 = log_nu0 - q.log_ncs;
+  const double lx0 = lr0 - P.log_w2k2;   // ln(nu_0 / nu_kappa)
+  const double lva_j = P.log_k_j_pref + q.log_ne + q.log_ncs - 2.0 * log_nu0;
+  const double jlo = P.log_kjl + lva_j + lx0 * (1.0 / 3.0);
+  const double jhi = P.log_kjh + lva_j - (P.plasma_kappa - 2.0) / 2.0 * lx0;
+  const double lva_a = P.log_k_a_pref + q.log_ne;
+  const double alo = P.log_kal + lva_a - 2.0 / 3.0 * lx0;
+  const double ahi = P.log_kah_base + lva_a - (1.0 + P.plasma_kappa) / 2.0 * lx0;
+  auto bridged = [&](int t, double a0, double b0, double x, double sign) {
+    const double inv_x = P.kappa_inv_x[t], s_lo = P.kappa_slope_lo[t], s_hi = P.kappa_slope_hi[t];
+    const double d0 = a0 == b0 ? 0.0 : a0 - b0;
+    const double e_neg = bfm::exp_bf(-x * d0), e_pos = bfm::exp_bf(x * d0);
+BL_FREQ_LOOP
+    for (int l = 0; l < F; l++) {
+      const double dl = P.dlog_freqs[l];
+      const double a = fma(s_lo, dl, a0), b = fma(s_hi, dl, b0);
+      const double d = a == b ? 0.0 : a - b;
+      const double u = d < 0.0 ? e_pos * P.kappa_kinv[t][l] : e_neg * P.kappa_k[t][l];   // e^(-x |d|)
+      const double m = d < 0.0 ? a : b;
+      store(t, l, sign * bfm::exp_bf(m - bfm::log_bf(1.0 + u) * inv_x));
+    }
+  };
+  bridged(0, jlo, jhi, P.kappa_jj_x_i, 1.0);
+  bridged(1, jlo + P.log_kj_low_q, jhi + P.log_kj_high_q, P.kappa_jj_x_q, -1.0);
+  bridged(2, jlo + P.log_kj_low_v + q.lvd_j - 0.35 * lx0, jhi + P.log_kj_high_v + q.lvf_j - 0.5 * lx0, P.kappa_jj_x_v, q.sgn);
+  bridged(3, alo, ahi + (P.log_kah - P.log_kah_base), P.kappa_aa_x_i, 1.0);
+  bridged(4, alo + P.log_ka_low_q, ahi + P.log_ka_high_q, P.kappa_aa_x_q, -1.0);
+  bridged(5, alo + P.log_ka_low_v + q.lvd_a - 0.35 * lx0, ahi + P.log_ka_high_v + q.lvf_a - 0.5 * lx0, P.kappa_aa_x_v, q.sgn);
+  // Faraday conversion and rotation: fits tabulated at kappa = 3.5, 4, 4.5, 5, blended (a zero weight skips its entry)
+  const double x084_0 = bfm::exp_bf(0.84 * lx0), xm12_0 = bfm::exp_bf(-0.5 * lx0);
+  const bool use_lo = P.kappa_rho_frac != 1.0, use_hi = P.kappa_rho_frac != 0.0;
+  const double ein_lo0 = use_lo ? bfm::exp_bf(P.kappa_rho_q_low_e * lx0) : 0.0;
+  const double ein_hi0 = use_hi ? bfm::exp_bf(P.kappa_rho_q_high_e * lx0) : 0.0;
+  const double pref = P.kappa_frac * q.n_e * e2 * q.nu_c * (1.0 / (phys::m_e * phys::c));
+BL_FREQ_LOOP
+  for (int l = 0; l < F; l++) {
+    const double nu_cgs = q.om * P.freqs[l];
+    const double inv_nu = q.inv_om * P.inv_freqs[l];
+    const double xx = nu_cgs * q.inv_nu_k;
+    const double va = -pref * q.nu_c * q.sin2 * inv_nu * inv_nu;
+    const double vb = pref * 2.0 * q.cos_b * inv_nu;
+    const double x084 = x084_0 * P.rho_c84[l], xx_m12 = xm12_0 * P.rho_cm12[l];
+    double q_lo = 0.0, q_hi = 0.0, v_lo = 0.0, v_hi = 0.0;
+    if (use_lo) {
+      q_lo = va * P.kappa_rho_q_low_a * (1.0 - bfm::exp_bf(P.kappa_rho_q_low_b * x084) -
+             sin(P.kappa_rho_q_low_c * xx) * bfm::exp_bf(P.kappa_rho_q_low_d * (ein_lo0 * P.rho_cqe_low[l])));
+      v_lo = P.kappa_rho_v * vb * P.kappa_rho_v_low_a * (1.0 - 0.17 * bfm::log_bf(1.0 + P.kappa_rho_v_low_b * xx_m12));
+    }
+    if (use_hi) {
+      q_hi = va * P.kappa_rho_q_high_a * (1.0 - bfm::exp_bf(P.kappa_rho_q_high_b * x084) -
+             sin(P.kappa_rho_q_high_c * xx) * bfm::exp_bf(P.kappa_rho_q_high_d * (ein_hi0 * P.rho_cqe_high[l])));
+      v_hi = P.kappa_rho_v * vb * P.kappa_rho_v_high_a * (1.0 - 0.17 * bfm::log_bf(1.0 + P.kappa_rho_v_high_b * xx_m12));
+    }
+    store(6, l, (1.0 - P.kappa_rho_frac) * q_lo + P.kappa_rho_frac * q_hi);
+    store(7, l, (1.0 - P.kappa_rho_frac) * v_lo + P.kappa_rho_frac * v_hi);
   }
 }
 

@@ -133,6 +133,16 @@ struct RadParams {
   double log_kj_low_q, log_kj_low_v, log_kj_high_q, log_kj_high_v;   // ln kappa_jj_{low,high}_{q,v}
   double log_ka_low_q, log_ka_low_v, log_ka_high_q, log_ka_high_v;   // ln kappa_aa_{low,high}_{q,v}
   double log_power_gmin;                       // ln(2 gamma_min^2 / 3)
+  // Term-major evaluation of the polarized kappa coefficients over the image frequencies (pol_common.cuh:
+  // kappa_polarized_all).  Every bridged coefficient t = j_I, j_Q, j_V, alpha_I, alpha_Q, alpha_V is
+  // (lo^-x + hi^-x)^(-1/x) with ln lo, ln hi affine in ln nu: slopes kappa_slope_lo/hi[t], so that between image
+  // frequencies only the host constants kappa_k[t][l] = exp(-x_t (slope_lo - slope_hi) ln(nu_l / nu_0)) and their
+  // reciprocals change; likewise the pure powers of nu / nu_kappa inside the Faraday fits.
+  double dlog_freqs[RAD_MAX_FREQ];             // ln(image_frequencies[l] / image_frequencies[0])
+  double kappa_inv_x[6], kappa_slope_lo[6], kappa_slope_hi[6];
+  double kappa_k[6][RAD_MAX_FREQ], kappa_kinv[6][RAD_MAX_FREQ];
+  double rho_c84[RAD_MAX_FREQ], rho_cm12[RAD_MAX_FREQ];          // (nu_l / nu_0)^0.84, (nu_l / nu_0)^-0.5
+  double rho_cqe_low[RAD_MAX_FREQ], rho_cqe_high[RAD_MAX_FREQ];  // (nu_l / nu_0)^kappa_rho_q_{low,high}_e
   int32_t need_sigma_beta;          // sigma / beta_inverse needed as values (cell values or cuts)
   // rendering
   int32_t render_num_images;
@@ -161,6 +171,8 @@ struct RadArgs {
   const double *cam_pos;        // (wave rays,4) camera position / covariant momentum of each ray:
   const double *cam_dir;        //   the polarized kernel projects onto the camera tetrad at the end
   int64_t rays;                 // rays in this wave
+  const int32_t *order;         // rays of the wave sorted by length, longest first (ray_order.cu), or nullptr: thread i
+  int64_t active;               //   takes ray order[i] (i itself without a list), i < active
   double *image;                // (Q, level_rays) device, already offset to this wave's first ray
   int64_t image_stride;         // level_rays
   double *render;               // (R, 3, level_rays) or nullptr, offset likewise

@@ -238,14 +238,20 @@ pol_coefficient_kernel(const __grid_constant__ RadArgs A, const __grid_constant_
   PolSample sq;
   pol_sample<DIST>(P, s, om, sin_b, cos_b, kk, sq);
   const size_t fs = (size_t)X.slab * (size_t)A.rays;   // distance between consecutive fields
+  if constexpr (DIST == 4) {
+    // kappa only: term-major over the frequencies, values go straight to the scratch
+    double *dst = field_ptr(X, A.rays, kFieldCoef, j, m);
+    kappa_polarized_all(P, sq, F, [&](int k, int l, double v) { __stcs(dst + (size_t)(8 * l + k) * fs, v); });
+  } else {
 BL_FREQ_LOOP
-  for (int l = 0; l < F; l++) {
-    Coefficients C;
-    synchrotron_polarized<DIST>(P, sq, l, C);
-    double *dst = field_ptr(X, A.rays, kFieldCoef + 8 * l, j, m);
-    __stcs(dst, C.j[0]); __stcs(dst + fs, C.j[1]); __stcs(dst + 2 * fs, C.j[2]);
-    __stcs(dst + 3 * fs, C.a[0]); __stcs(dst + 4 * fs, C.a[1]); __stcs(dst + 5 * fs, C.a[2]);
-    __stcs(dst + 6 * fs, C.rho[0]); __stcs(dst + 7 * fs, C.rho[1]);
+    for (int l = 0; l < F; l++) {
+      Coefficients C;
+      synchrotron_polarized<DIST>(P, sq, l, C);
+      double *dst = field_ptr(X, A.rays, kFieldCoef + 8 * l, j, m);
+      __stcs(dst, C.j[0]); __stcs(dst + fs, C.j[1]); __stcs(dst + 2 * fs, C.j[2]);
+      __stcs(dst + 3 * fs, C.a[0]); __stcs(dst + 4 * fs, C.a[1]); __stcs(dst + 5 * fs, C.a[2]);
+      __stcs(dst + 6 * fs, C.rho[0]); __stcs(dst + 7 * fs, C.rho[1]);
+    }
   }
 }
 
@@ -377,11 +383,14 @@ extern "C" cudaError_t bl_launch_radiate_polarized_split(const RadArgs *args, co
     else pol_geometry_kernel<3><<<ray_blocks, kBlock, smem, stream>>>(A, P, X);
     if (events) cudaEventRecord(events[ev++], stream);
     dim3 cgrid(ray_blocks, (unsigned)(X.n_hi - X.n_lo));
-    // the thermal-only coefficient code is light enough for five CTAs per SM (58 -> 51 ms per 1024^2 frame)
-    const int occ_c = occ.c > 0 ? occ.c : (dist == 1 ? 5 : 4);
+    // the thermal-only coefficient code is light enough for five CTAs per SM (58 -> 51 ms per 1024^2 frame), the
+    // term-major kappa code for six (155 -> 141 -> 134 ms at four, five, six)
+    const int occ_c = occ.c > 0 ? occ.c : (dist == 1 ? 5 : (dist == 4 ? 6 : 4));
     if (occ_c == 3) launch_coefficients<3>(dist, cgrid, stream, A, P, X);
     else if (occ_c == 5) launch_coefficients<5>(dist, cgrid, stream, A, P, X);
     else if (occ_c == 6) launch_coefficients<6>(dist, cgrid, stream, A, P, X);
+    else if (occ_c == 7) launch_coefficients<7>(dist, cgrid, stream, A, P, X);
+    else if (occ_c == 8) launch_coefficients<8>(dist, cgrid, stream, A, P, X);
     else launch_coefficients<4>(dist, cgrid, stream, A, P, X);
     if (events) cudaEventRecord(events[ev++], stream);
     dim3 tgrid((unsigned)((A.rays + kBlock / fw - 1) / (kBlock / fw)), (unsigned)((F + fw - 1) / fw));
