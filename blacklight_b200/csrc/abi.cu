@@ -64,6 +64,7 @@ struct Level {
   int32_t *order = nullptr;        // device (wave_rays)
   int32_t *order_ws = nullptr;     // device workspace of the sort; its tail holds the bucket totals
   int32_t order_unit = 0, order_buckets = 0;   // bucket = ceil(num / unit); 0 buckets: rays are taken in index order
+  int64_t order_alive0 = -1;       // rays with at least one sample in the last radiated wave (-1: no list was used)
   double *scratch = nullptr;  // device (fields, slab, wave_rays)
   double *cam_map = nullptr;  // device (10, wave_rays)
   int32_t slab = 0;           // samples per slab; 0 = the level uses the fused kernel
@@ -885,9 +886,10 @@ int radiate_wave(bl_ctx *ctx, Level &L, int64_t first, int64_t count, int s_top,
       run += totals[(size_t)(nb - 1 - key)];
       alive[(size_t)(key - 1)] = run;     // rays with ceil(num / unit) > key - 1
     }
-    A.order = L.order;
-    A.active = alive[0];                  // rays with at least one sample
+    A.order = L.order;                    // the fused kernels walk the whole list (rays without samples still write
+                                          // their pixels); the pipeline's slabs take the prefixes alive[s]
   }
+  L.order_alive0 = A.order ? alive[0] : -1;
   if (ctx->rad.polarization && L.slab > 0 && L.scratch && !L.tap_nan) {
     // the Stokes state of the pipeline starts (and stays between slabs) in the image columns of these rays
     BL_CUDA_CHECK(cudaMemset2DAsync(L.image + first, (size_t)L.rays * sizeof(double), 0, (size_t)count * sizeof(double),
@@ -1237,7 +1239,19 @@ int bl_download_polarized_scratch(bl_ctx *ctx, int level, double *out, double *c
   if (num_rays) *num_rays = L.wave_rays;
   if (out) {
     BL_CUDA_CHECK(cudaSetDevice(ctx->device));
-    BL_CUDA_CHECK(cudaMemcpy(out, L.scratch, (size_t)nf * (size_t)L.slab * (size_t)L.wave_rays * sizeof(double), cudaMemcpyDeviceToHost));
+    const size_t rows = (size_t)nf * (size_t)L.slab, rays = (size_t)L.wave_rays;
+    if (L.order_alive0 < 0) {
+      BL_CUDA_CHECK(cudaMemcpy(out, L.scratch, rows * rays * sizeof(double), cudaMemcpyDeviceToHost));
+    } else {
+      // the pipeline addressed the scratch by position in the sorted ray list: hand it out by ray
+      std::vector<double> tmp(rows * rays);
+      std::vector<int32_t> order(rays);
+      BL_CUDA_CHECK(cudaMemcpy(tmp.data(), L.scratch, rows * rays * sizeof(double), cudaMemcpyDeviceToHost));
+      BL_CUDA_CHECK(cudaMemcpy(order.data(), L.order, rays * sizeof(int32_t), cudaMemcpyDeviceToHost));
+      std::memset(out, 0, rows * rays * sizeof(double));
+      for (size_t r = 0; r < rows; r++)
+        for (size_t i = 0; i < (size_t)L.order_alive0; i++) out[r * rays + (size_t)order[i]] = tmp[r * rays + i];
+    }
   }
   if (cam_map) {
     BL_CUDA_CHECK(cudaSetDevice(ctx->device));

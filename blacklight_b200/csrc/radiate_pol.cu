@@ -34,8 +34,10 @@ radiate_polarized_kernel(const __grid_constant__ RadArgs A, const __grid_constan
     }
   }
   const unsigned full = 0xffffffffu;
-  int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  bool valid = m < A.rays;
+  // thread i takes ray order[i] of the wave's list sorted by length (ray_order.cu): a warp's rays end together
+  const int64_t i_list = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool valid = i_list < A.active;
+  int64_t m = valid ? (A.order ? (int64_t)A.order[i_list] : i_list) : 0;
   int num = valid ? A.sample_num[m] : 0;
   bool flagged = valid ? A.sample_flags[m] != 0 : false;
   double mom = valid ? A.mom_factor[m] : 1.0;

@@ -19,8 +19,9 @@
 //                            itself.  The last slab applies the half step to the camera and the projection on
 //                            the camera tetrad (:816-939).
 // Slabs run from the far end of the rays (large n) to the camera (n = 0), three launches each, on one stream.
-// The scratch between the stages is field-major, scratch[(field * slab + j) * rays + m]: every access of a warp
-// is a contiguous 256-byte row.
+// The scratch between the stages is field-major, scratch[(field * slab + j) * rays + i]: every access of a warp
+// is a contiguous 256-byte row.  i is the ray's position in the wave's list of rays sorted by length (ray_order.cu;
+// the ray itself without a list): a slab is launched over the rays still alive in it, a prefix of that list.
 #include <cstdio>
 #include <cstdlib>
 
@@ -48,8 +49,8 @@ struct SplitArgs {
   int32_t n_lo, n_hi;  // this launch covers samples n_lo <= n < n_hi of every ray
 };
 
-__device__ __forceinline__ double *field_ptr(const SplitArgs &X, int64_t rays, int field, int j, int64_t m) {
-  return X.scratch + ((size_t)field * X.slab + j) * (size_t)rays + m;
+__device__ __forceinline__ double *field_ptr(const SplitArgs &X, int64_t rays, int field, int j, int64_t i) {
+  return X.scratch + ((size_t)field * X.slab + j) * (size_t)rays + i;
 }
 
 // ---- stage 1: geometry --------------------------------------------------------------------------------------
@@ -68,8 +69,9 @@ pol_geometry_kernel(const __grid_constant__ RadArgs A, const __grid_constant__ R
     }
   }
   const unsigned full = 0xffffffffu;
-  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool valid = m < A.rays;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // position in the list: addresses the scratch
+  const bool valid = i < A.active;
+  const int64_t m = valid ? (A.order ? (int64_t)A.order[i] : i) : 0;   // the ray
   const int num = valid ? A.sample_num[m] : 0;
   unsigned long long processed = 0;
   if (num > X.n_lo) {
@@ -141,9 +143,9 @@ pol_geometry_kernel(const __grid_constant__ RadArgs A, const __grid_constant__ R
         M.vv = 0.0;
         if (have_prev) transport_map(jet_p, k_p, e_p, dlam_p, jet, kcon, f1, f2, dlam, M);
         for (int a = 0; a < 3; a++)
-          for (int b = 0; b < 3; b++) __stcs(field_ptr(X, A.rays, kFieldM + 3 * a + b, j, m), M.m[a][b]);
-        __stcs(field_ptr(X, A.rays, kFieldM + 9, j, m), M.vv);
-        __stcs(field_ptr(X, A.rays, kFieldDlam, j, m), dlam);
+          for (int b = 0; b < 3; b++) __stcs(field_ptr(X, A.rays, kFieldM + 3 * a + b, j, i), M.m[a][b]);
+        __stcs(field_ptr(X, A.rays, kFieldM + 9, j, i), M.vv);
+        __stcs(field_ptr(X, A.rays, kFieldDlam, j, i), dlam);
 
         // ---- what the coefficient stage needs: frequency scale, pitch angle, field strength, n_e, theta_e ----
         double om = 0.0, sin_theta_b = 0.0, cos_theta_b = 0.0;
@@ -156,14 +158,14 @@ pol_geometry_kernel(const __grid_constant__ RadArgs A, const __grid_constant__ R
           cos_theta_b = sqrt(c2) * (kb >= 0.0 ? 1.0 : -1.0);
           om = omega * mom;
         }
-        __stcs(field_ptr(X, A.rays, kFieldOm, j, m), om);
+        __stcs(field_ptr(X, A.rays, kFieldOm, j, i), om);
         if (coupled) {
-          __stcs(field_ptr(X, A.rays, kFieldSin, j, m), sin_theta_b);
-          __stcs(field_ptr(X, A.rays, kFieldCos, j, m), cos_theta_b);
-          __stcs(field_ptr(X, A.rays, kFieldBb, j, m), ps.bb_cgs);
-          __stcs(field_ptr(X, A.rays, kFieldNe, j, m), ps.n_e_cgs);
-          __stcs(field_ptr(X, A.rays, kFieldTheta, j, m), ps.theta_e);
-          __stcs(field_ptr(X, A.rays, kFieldInvTheta, j, m), ps.inv_theta_e);
+          __stcs(field_ptr(X, A.rays, kFieldSin, j, i), sin_theta_b);
+          __stcs(field_ptr(X, A.rays, kFieldCos, j, i), cos_theta_b);
+          __stcs(field_ptr(X, A.rays, kFieldBb, j, i), ps.bb_cgs);
+          __stcs(field_ptr(X, A.rays, kFieldNe, j, i), ps.n_e_cgs);
+          __stcs(field_ptr(X, A.rays, kFieldTheta, j, i), ps.theta_e);
+          __stcs(field_ptr(X, A.rays, kFieldInvTheta, j, i), ps.inv_theta_e);
         }
       }
 
@@ -212,24 +214,25 @@ pol_geometry_kernel(const __grid_constant__ RadArgs A, const __grid_constant__ R
 template <int DIST, int MINB>
 __global__ void __launch_bounds__(kBlock, MINB)
 pol_coefficient_kernel(const __grid_constant__ RadArgs A, const __grid_constant__ RadParams P, const SplitArgs X) {
-  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int j = blockIdx.y;
-  if (m >= A.rays) return;
+  if (i >= A.active) return;
+  const int64_t m = A.order ? (int64_t)A.order[i] : i;
   const int n = X.n_lo + j;
   if (n >= X.n_hi || n >= A.sample_num[m]) return;
   const int F = P.num_freq;
-  const double om = __ldcs(field_ptr(X, A.rays, kFieldOm, j, m));
+  const double om = __ldcs(field_ptr(X, A.rays, kFieldOm, j, i));
   if (om == 0.0) {
-    for (int q = 0; q < 8 * F; q++) __stcs(field_ptr(X, A.rays, kFieldCoef + q, j, m), 0.0);
+    for (int q = 0; q < 8 * F; q++) __stcs(field_ptr(X, A.rays, kFieldCoef + q, j, i), 0.0);
     return;
   }
   rad::Plasma s;
-  const double sin_b = __ldcs(field_ptr(X, A.rays, kFieldSin, j, m));
-  const double cos_b = __ldcs(field_ptr(X, A.rays, kFieldCos, j, m));
-  s.bb_cgs = __ldcs(field_ptr(X, A.rays, kFieldBb, j, m));
-  s.n_e_cgs = __ldcs(field_ptr(X, A.rays, kFieldNe, j, m));
-  s.theta_e = __ldcs(field_ptr(X, A.rays, kFieldTheta, j, m));
-  s.inv_theta_e = __ldcs(field_ptr(X, A.rays, kFieldInvTheta, j, m));
+  const double sin_b = __ldcs(field_ptr(X, A.rays, kFieldSin, j, i));
+  const double cos_b = __ldcs(field_ptr(X, A.rays, kFieldCos, j, i));
+  s.bb_cgs = __ldcs(field_ptr(X, A.rays, kFieldBb, j, i));
+  s.n_e_cgs = __ldcs(field_ptr(X, A.rays, kFieldNe, j, i));
+  s.theta_e = __ldcs(field_ptr(X, A.rays, kFieldTheta, j, i));
+  s.inv_theta_e = __ldcs(field_ptr(X, A.rays, kFieldInvTheta, j, i));
   double kk[3] = {0.0, 0.0, 0.0};
   if (has_thermal<DIST>(P) && s.theta_e >= 0.01) {
     bfm::bessel_k01(s.inv_theta_e, kk[0], kk[1]);
@@ -240,14 +243,14 @@ pol_coefficient_kernel(const __grid_constant__ RadArgs A, const __grid_constant_
   const size_t fs = (size_t)X.slab * (size_t)A.rays;   // distance between consecutive fields
   if constexpr (DIST == 4) {
     // kappa only: term-major over the frequencies, values go straight to the scratch
-    double *dst = field_ptr(X, A.rays, kFieldCoef, j, m);
+    double *dst = field_ptr(X, A.rays, kFieldCoef, j, i);
     kappa_polarized_all(P, sq, F, [&](int k, int l, double v) { __stcs(dst + (size_t)(8 * l + k) * fs, v); });
   } else {
 BL_FREQ_LOOP
     for (int l = 0; l < F; l++) {
       Coefficients C;
       synchrotron_polarized<DIST>(P, sq, l, C);
-      double *dst = field_ptr(X, A.rays, kFieldCoef + 8 * l, j, m);
+      double *dst = field_ptr(X, A.rays, kFieldCoef + 8 * l, j, i);
       __stcs(dst, C.j[0]); __stcs(dst + fs, C.j[1]); __stcs(dst + 2 * fs, C.j[2]);
       __stcs(dst + 3 * fs, C.a[0]); __stcs(dst + 4 * fs, C.a[1]); __stcs(dst + 5 * fs, C.a[2]);
       __stcs(dst + 6 * fs, C.rho[0]); __stcs(dst + 7 * fs, C.rho[1]);
@@ -262,9 +265,10 @@ template <int FW, int MINB>
 __global__ void __launch_bounds__(kBlock, MINB)
 pol_transfer_kernel(const __grid_constant__ RadArgs A, const __grid_constant__ RadParams P, const SplitArgs X) {
   constexpr int kRays = kBlock / FW;
-  const int64_t m = (int64_t)blockIdx.x * kRays + (threadIdx.x % kRays);
+  const int64_t i = (int64_t)blockIdx.x * kRays + (threadIdx.x % kRays);
   const int l = blockIdx.y * FW + threadIdx.x / kRays;
-  if (m >= A.rays || l >= P.num_freq) return;
+  if (i >= A.active || l >= P.num_freq) return;
+  const int64_t m = A.order ? (int64_t)A.order[i] : i;
   const int num = A.sample_num[m];
   if (num <= X.n_lo) return;
   const int top = (X.n_hi < num ? X.n_hi : num) - 1;
@@ -283,8 +287,8 @@ pol_transfer_kernel(const __grid_constant__ RadArgs A, const __grid_constant__ R
 #pragma unroll 1
   for (int n = top; n >= X.n_lo; n--) {
     const int j = n - X.n_lo;
-    const double *lk = field_ptr(X, A.rays, kFieldM, j, m);
-    const double *cf = field_ptr(X, A.rays, kFieldCoef + 8 * l, j, m);
+    const double *lk = field_ptr(X, A.rays, kFieldM, j, i);
+    const double *cf = field_ptr(X, A.rays, kFieldCoef + 8 * l, j, i);
     double mm[10];
 #pragma unroll
     for (int q = 0; q < 10; q++) mm[q] = __ldg(lk + q * fs);
@@ -359,8 +363,9 @@ extern "C" int bl_polarized_split_slabs(int slab, int s_top) { return s_top <= 0
 
 extern "C" cudaError_t bl_launch_radiate_polarized_split(const RadArgs *args, const RadParams *params, double *scratch,
                                                          double *cam_map, int slab, int s_top, cudaStream_t stream,
-                                                         cudaEvent_t *events, long long *launches) {
-  const RadArgs &A = *args;
+                                                         cudaEvent_t *events, long long *launches,
+                                                         const int64_t *alive, int num_alive) {
+  RadArgs A = *args;
   const RadParams &P = *params;
   if (A.rays <= 0 || s_top <= 0) return cudaSuccess;
   size_t smem = 0;
@@ -371,13 +376,20 @@ extern "C" cudaError_t bl_launch_radiate_polarized_split(const RadArgs *args, co
   const Occupancy occ = stage_occupancy();
   const int F = P.num_freq;
   const int fw = F >= 4 ? 4 : (F >= 2 ? 2 : 1);
-  const unsigned ray_blocks = (unsigned)((A.rays + kBlock - 1) / kBlock);
   int ev = 0;
   if (events) cudaEventRecord(events[ev++], stream);
   for (int n_hi = (s_top + slab - 1) / slab * slab; n_hi > 0; n_hi -= slab) {
     SplitArgs X;
     X.scratch = scratch; X.cam_map = cam_map; X.slab = slab;
     X.n_lo = n_hi - slab; X.n_hi = n_hi < s_top ? n_hi : s_top;
+    // the rays alive in this slab: with the sorted list a prefix of it (alive[s]: rays longer than s slabs)
+    const int slab_index = X.n_lo / slab;
+    if (alive && A.order) A.active = slab_index < num_alive ? alive[slab_index] : 0;
+    const unsigned ray_blocks = (unsigned)((A.active + kBlock - 1) / kBlock);
+    if (ray_blocks == 0) {
+      if (events) { cudaEventRecord(events[ev++], stream); cudaEventRecord(events[ev++], stream); cudaEventRecord(events[ev++], stream); }
+      continue;
+    }
     if (occ.g == 2) pol_geometry_kernel<2><<<ray_blocks, kBlock, smem, stream>>>(A, P, X);
     else if (occ.g == 4) pol_geometry_kernel<4><<<ray_blocks, kBlock, smem, stream>>>(A, P, X);
     else pol_geometry_kernel<3><<<ray_blocks, kBlock, smem, stream>>>(A, P, X);
@@ -393,7 +405,7 @@ extern "C" cudaError_t bl_launch_radiate_polarized_split(const RadArgs *args, co
     else if (occ_c == 8) launch_coefficients<8>(dist, cgrid, stream, A, P, X);
     else launch_coefficients<4>(dist, cgrid, stream, A, P, X);
     if (events) cudaEventRecord(events[ev++], stream);
-    dim3 tgrid((unsigned)((A.rays + kBlock / fw - 1) / (kBlock / fw)), (unsigned)((F + fw - 1) / fw));
+    dim3 tgrid((unsigned)((A.active + kBlock / fw - 1) / (kBlock / fw)), (unsigned)((F + fw - 1) / fw));
     if (occ.t == 3) launch_transfer<3>(fw, tgrid, stream, A, P, X);
     else if (occ.t == 4) launch_transfer<4>(fw, tgrid, stream, A, P, X);
     else if (occ.t == 6) launch_transfer<6>(fw, tgrid, stream, A, P, X);

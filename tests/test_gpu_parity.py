@@ -1311,3 +1311,44 @@ def test_drop_in_with_device_camera_matches_host_camera(base, over, gpu, tmp_pat
     for k in host:
         assert np.array_equal(dev[k], host[k], equal_nan=True), k
         assert np.array_equal(dev3[k], host[k], equal_nan=True), k
+
+
+@pytest.mark.parametrize('base,over,tile', [
+    ('simulation.input', {'camera_resolution': 48}, 0),
+    ('simulation.input', dict(C4_PHYSICS, camera_resolution=40), 0),
+    ('simulation.input', dict(C4_PHYSICS, camera_resolution=40), 512),                               # waves
+    ('simulation.input', {'camera_resolution': 32, 'image_polarization': 'true', 'image_time': 'true', 'image_tau': 'true',
+                          'image_crossings': 'true'}, 0),                                            # fused polarized kernel
+    ('formula.input', {'camera_resolution': 40}, 0),
+    ('true_color.input', {'camera_resolution': 24}, 384),
+])
+def test_ray_ordering_does_not_change_a_bit(base, over, tile, gpu, tmp_path):
+    """The radiation kernels take their rays from the wave's list sorted by length (csrc/ray_order.cu) and the polarized
+    pipeline launches each slab over the rays still alive in it, addressing its scratch by list position.  A ray's own
+    arithmetic is untouched: every image array must equal, bit for bit, the one rendered in index order (BL_RAY_ORDER=0),
+    for resident levels and waves, the three-stage pipeline (two slab lengths) and the fused kernels."""
+    case = Case(tmp_path, base, over)
+
+    def render(env):
+        saved = {k: os.environ.get(k) for k in env}
+        os.environ.update(env)
+        try:
+            cfg = case.config(tile_rays=tile)
+            ctx = bl.Context(cfg)
+        finally:
+            for k, v in saved.items():
+                os.environ.pop(k, None)
+                if v is not None:
+                    os.environ[k] = v
+        if case.sim:
+            ctx.upload_grid(case.grid_arrays())
+        ctx.trace_level_pixels(0)
+        image, _, st = ctx.radiate_level(0)
+        ctx.close()
+        return image, st
+
+    plain, st0 = render({'BL_RAY_ORDER': '0'})
+    for env in ({}, {'BL_POL_SLAB': '7'}, {'BL_POL_SLAB': '200'}):
+        image, st = render(env)
+        assert st['num_samples'] == st0['num_samples']
+        assert np.array_equal(_bits(image), _bits(plain)), env
