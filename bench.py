@@ -317,9 +317,11 @@ def kernel_rooflines(name, st, stages, ms_geo, ms_rad, fp64_peak, hbm_peak, exec
     ns = st['num_samples']
     add('geodesic_dp_kernel', ms_geo, ns * RECORD_BYTES_PER_SAMPLE)
     if stages and stages['slab'] > 0:
-        # scratch between the stages: 18 doubles per sample out of the geometry stage, 7 read + 8 F written by the
-        # coefficient stage, 11 + 8 F read by the transfer stage (radiate_pol_split.cu)
-        add('pol_geometry_kernel', stages['geometry_ms'], ns * (RECORD_BYTES_PER_SAMPLE + 18 * 8.0))
+        # scratch between the stages: 8 + 7 doubles per sample out of the sampling stage, 8 read + 11 written by the
+        # geometry stage, 7 read + 8 F written by the coefficient stage, 11 + 8 F read by the transfer stage
+        # (radiate_pol_split.cu); the first two read the 64-byte step-buffer record
+        add('pol_sampling_kernel', stages['sampling_ms'], ns * (RECORD_BYTES_PER_SAMPLE + 15 * 8.0))
+        add('pol_geometry_kernel', stages['geometry_ms'], ns * (RECORD_BYTES_PER_SAMPLE + 19 * 8.0))
         add('pol_coefficient_kernel', stages['coefficients_ms'], ns * (7 + 8 * F) * 8.0)
         add('pol_transfer_kernel', stages['transfer_ms'], ns * (11 + 8 * F) * 8.0)
     else:
@@ -414,7 +416,7 @@ def measure(args, name, resolution, steps, warmup, rank, world, local_rank, main
             torch.cuda.current_stream().synchronize()
             return st_
 
-        ms_acc = {'geo': 0.0, 'rad': 0.0, 'stage': [0.0, 0.0, 0.0], 'slab': 0}
+        ms_acc = {'geo': 0.0, 'rad': 0.0, 'stage': [0.0, 0.0, 0.0, 0.0], 'slab': 0}
 
         def step_resident():
             st0 = ctx.retrace_level(0)
@@ -423,7 +425,7 @@ def measure(args, name, resolution, steps, warmup, rank, world, local_rank, main
             ms_acc['geo'] += st0['ms_geodesic'] if st0['ms_geodesic'] > 0 and st_['ms_geodesic'] == st0['ms_geodesic'] else st_['ms_geodesic']
             ms_acc['rad'] += st_['ms_radiation']
             sg = ctx.polarized_stage_ms(0)
-            for k, key in enumerate(('geometry_ms', 'coefficients_ms', 'transfer_ms')):
+            for k, key in enumerate(('geometry_ms', 'coefficients_ms', 'transfer_ms', 'sampling_ms')):
                 ms_acc['stage'][k] += sg[key]
             ms_acc['slab'] = sg['slab']
             return st_
@@ -478,7 +480,7 @@ def measure(args, name, resolution, steps, warmup, rank, world, local_rank, main
                 'l2': 'inputs larger than L2: %.1f GB step buffer written and re-read per step on rank 0' % (st['num_samples'] * 64 / 1e9),
                 '_st': st, '_ms': {'geo': ms_acc['geo'] / K, 'rad': ms_acc['rad'] / K}, '_polarized': polarized,
                 '_stages': {'geometry_ms': ms_acc['stage'][0] / K, 'coefficients_ms': ms_acc['stage'][1] / K,
-                            'transfer_ms': ms_acc['stage'][2] / K, 'slab': ms_acc['slab']},
+                            'transfer_ms': ms_acc['stage'][2] / K, 'sampling_ms': ms_acc['stage'][3] / K, 'slab': ms_acc['slab']},
                 '_fp64_peak': fp64_peak, '_clocks': clocks, '_device': info['name'], '_resolution': resolution,
             }
         ctx.close()

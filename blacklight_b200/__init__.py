@@ -80,6 +80,7 @@ def load_library():
         'bl_device_image': (i32, [vp, i32, ctypes.POINTER(vp), ctypes.POINTER(i64)]),
         'bl_download_polarized_scratch': (i32, [vp, i32, vp, vp, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i64)]),
         'bl_polarized_stage_ms': (i32, [vp, i32, ctypes.POINTER(dbl * 3), ctypes.POINTER(ctypes.c_int32)]),
+        'bl_polarized_sampling_ms': (i32, [vp, i32, ctypes.POINTER(dbl)]),
         'bl_download_samples': (i32, [vp, i32, vp, vp, vp, vp, vp]),
         'bl_download_sample_inds': (i32, [vp, i32, vp, vp, vp, vp, vp]),
         'bl_device_info': (i32, [vp, ctypes.c_char_p, i32, ctypes.POINTER(i32), ctypes.POINTER(dbl)]),
@@ -362,11 +363,13 @@ class Context:
         return out, cam
 
     def polarized_stage_ms(self, level=0):
-        """Device ms of the three polarized stages (geometry, coefficients, transfer) in the last radiate_level and the
-        slab length; slab 0 means the fused kernel ran."""
+        """Device ms of the four polarized stages (sampling, geometry, coefficients, transfer) in the last radiate_level
+        and the slab length; slab 0 means the fused kernel ran."""
         ms, slab = (ctypes.c_double * 3)(), ctypes.c_int32()
         self._check(_lib.bl_polarized_stage_ms(self._h, level, ctypes.byref(ms), ctypes.byref(slab)))
-        return {'geometry_ms': ms[0], 'coefficients_ms': ms[1], 'transfer_ms': ms[2], 'slab': slab.value}
+        smp = ctypes.c_double()
+        self._check(_lib.bl_polarized_sampling_ms(self._h, level, ctypes.byref(smp)))
+        return {'sampling_ms': smp.value, 'geometry_ms': ms[0], 'coefficients_ms': ms[1], 'transfer_ms': ms[2], 'slab': slab.value}
 
     def cuda_stream(self):
         """cudaStream_t (as an integer) that this context's kernels and copies are issued on."""

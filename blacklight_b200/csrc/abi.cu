@@ -21,7 +21,7 @@ BL_DECL_RAD(bl_launch_radiate_polarized);
 extern "C" int bl_polarized_split_fields(int num_freq);
 extern "C" int bl_polarized_split_slabs(int slab, int s_top);
 extern "C" cudaError_t bl_launch_radiate_polarized_split(const RadArgs *args, const RadParams *params, double *scratch,
-                                                         double *cam_map, int slab, int s_top, cudaStream_t stream,
+                                                         double *frame, double *cam_map, int slab, int s_top, cudaStream_t stream,
                                                          cudaEvent_t *events, long long *launches,
                                                          const int64_t *alive, int num_alive);
 extern "C" cudaError_t bl_launch_relayout_grid(const float *prim, int n_var, const int *var_index, size_t cells,
@@ -42,11 +42,16 @@ extern "C" int bl_ray_order_max_buckets(void);
 extern "C" size_t bl_ray_order_workspace(int64_t rays, int buckets);
 extern "C" cudaError_t bl_launch_ray_order(const int32_t *num, int64_t rays, int unit, int buckets, int32_t *workspace,
                                            int32_t *order, cudaStream_t stream);
+extern "C" cudaError_t bl_launch_impact_order(const double *cam_pos, const double *cam_dir, int64_t rays, int32_t *keys,
+                                              unsigned int *b_max_bits, int buckets, int32_t *workspace, int32_t *order,
+                                              cudaStream_t stream);
 extern "C" cudaError_t bl_launch_fp64_peak(double *out, int blocks, int iters, cudaStream_t stream);
 extern "C" cudaError_t bl_launch_division_selftest(unsigned long long seed, int blocks, int iters,
                                                    unsigned long long *mismatches, cudaStream_t stream);
 
 namespace {
+
+constexpr int kImpactBuckets = 130;   // impact-parameter buckets of the integrator's queue order
 
 struct Level {
   int64_t rays = 0;
@@ -66,9 +71,10 @@ struct Level {
   int32_t order_unit = 0, order_buckets = 0;   // bucket = ceil(num / unit); 0 buckets: rays are taken in index order
   int64_t order_alive0 = -1;       // rays with at least one sample in the last radiated wave (-1: no list was used)
   double *scratch = nullptr;  // device (fields, slab, wave_rays)
+  double *frame = nullptr;    // device (8, slab + 1, wave_rays): fluid frame between the sampling and the geometry stage
   double *cam_map = nullptr;  // device (10, wave_rays)
   int32_t slab = 0;           // samples per slab; 0 = the level uses the fused kernel
-  double ms_stage[3] = {0.0, 0.0, 0.0};  // geometry, coefficients, transfer: device time of the last radiate call
+  double ms_stage[4] = {0.0, 0.0, 0.0, 0.0};  // sampling, geometry, coefficients, transfer: device time of the last radiate call
   bl_level_stats stats{};
   bl_slow_stats slow{};
   // taps (allocated on demand)
@@ -103,6 +109,7 @@ struct bl_ctx {
   size_t units_cap = 0;           // its capacity in int32
   int rad_prefetch = 2;     // BL_RAD_PREFETCH: samples ahead the radiation kernels prefetch step-buffer records into L2 (0 = off)
   int pol_slab = 0;         // BL_POL_SLAB: samples per slab of that pipeline (0 = chosen from the HBM budget)
+  int geo_order = 1;        // BL_GEO_ORDER=0: the integrator's queue hands out the rays in index order
   int ray_order = 1;        // BL_RAY_ORDER=0: radiation kernels take the rays in index order (A/B comparisons)
   bool pol_fused = false;   // BL_POL_FUSED=1: keep the single fused polarized kernel (A/B comparisons, parity cross-check)
 };
@@ -133,7 +140,7 @@ cudaError_t dev_alloc(T **p, size_t count) {
 
 void free_level(Level &L) {
   cudaFree(L.cam_pos); cudaFree(L.cam_dir); cudaFree(L.mom); cudaFree(L.num); cudaFree(L.flags);
-  cudaFree(L.step); cudaFree(L.image); cudaFree(L.render); cudaFree(L.scratch); cudaFree(L.cam_map);
+  cudaFree(L.step); cudaFree(L.image); cudaFree(L.render); cudaFree(L.scratch); cudaFree(L.frame); cudaFree(L.cam_map);
   cudaFree(L.order); cudaFree(L.order_ws);
   cudaFree(L.tap_inds); cudaFree(L.tap_fracs); cudaFree(L.tap_nan); cudaFree(L.tap_cut); cudaFree(L.tap_fb);
   L = Level();
@@ -441,6 +448,7 @@ int bl_create(const bl_params *params, bl_ctx **out) {
   if (const char *e = getenv("BL_POL_SLAB")) ctx->pol_slab = atoi(e);
   if (const char *e = getenv("BL_RAD_PREFETCH")) ctx->rad_prefetch = atoi(e);
   if (const char *e = getenv("BL_RAY_ORDER")) ctx->ray_order = atoi(e);
+  if (const char *e = getenv("BL_GEO_ORDER")) ctx->geo_order = atoi(e);
   if (const char *e = getenv("BL_POL_FUSED")) ctx->pol_fused = atoi(e) != 0;
 #define CREATE_CHECK(call)                                                                   \
   do {                                                                                       \
@@ -796,12 +804,20 @@ int pol_split_slab(const bl_ctx *ctx, int64_t num_rays, size_t budget, size_t *b
   if (ctx->pol_slab <= 0)
     while (slab < 256 && (double)num_rays * (2.0 * slab) * (double)nf * 8.0 <= 0.1 * (double)budget) slab *= 2;
   if (slab > ctx->params.ray_max_steps) slab = ctx->params.ray_max_steps;
-  *bytes_per_ray = (size_t)slab * nf * sizeof(double) + 10 * sizeof(double);
+  *bytes_per_ray = ((size_t)slab * nf + (size_t)(slab + 1) * 8 + 10) * sizeof(double) + sizeof(int32_t);   // scratch, frame, camera map, list
   return slab;
 }
 
 // Trace rays [first, first+count) of a level into L.step (one wave).
 int trace_wave(bl_ctx *ctx, Level &L, int64_t first, int64_t count) {
+  // the integrator's queue hands out the rays by increasing impact parameter: longest first (ray_order.cu)
+  const bool queue_order = ctx->params.ray_integrator == BL_INTEGRATOR_DP && L.order && L.order_buckets > 0 && ctx->geo_order;
+  if (queue_order) {
+    BL_CUDA_CHECK(cudaMemsetAsync(&ctx->counters->b_max_bits, 0, sizeof(unsigned int), ctx->stream));
+    BL_CUDA_CHECK(bl_launch_impact_order(L.cam_pos + 4 * first, L.cam_dir + 4 * first, count, L.num + first,
+                                         &ctx->counters->b_max_bits, kImpactBuckets, L.order_ws, L.order, ctx->stream));
+    ctx->launches += 5;
+  }
   const bl_params &p = ctx->params;
   GeoArgs g{};
   g.cam_pos = L.cam_pos + 4 * first;
@@ -814,6 +830,7 @@ int trace_wave(bl_ctx *ctx, Level &L, int64_t first, int64_t count) {
   g.sample_num = L.num + first;
   g.sample_flags = L.flags + first;
   g.counters = ctx->counters;
+  g.order = queue_order ? L.order : nullptr;
   BL_CUDA_CHECK(cudaMemsetAsync(&ctx->counters->next_ray, 0, sizeof(unsigned long long), ctx->stream));
   if (p.ray_integrator == BL_INTEGRATOR_DP)
     BL_CUDA_CHECK(bl_launch_geodesic_dp(&g, p.ray_flat, ctx->sm_count, ctx->geo_min_blocks, ctx->stream));
@@ -895,12 +912,12 @@ int radiate_wave(bl_ctx *ctx, Level &L, int64_t first, int64_t count, int s_top,
     BL_CUDA_CHECK(cudaMemset2DAsync(L.image + first, (size_t)L.rays * sizeof(double), 0, (size_t)count * sizeof(double),
                                     (size_t)ctx->rad.num_quantities, ctx->stream));
     const int slabs = bl_polarized_split_slabs(L.slab, s_top);
-    while ((int)ctx->stage_events.size() < 3 * slabs + 1) {
+    while ((int)ctx->stage_events.size() < 4 * slabs + 1) {
       cudaEvent_t e;
       BL_CUDA_CHECK(cudaEventCreate(&e));
       ctx->stage_events.push_back(e);
     }
-    BL_CUDA_CHECK(bl_launch_radiate_polarized_split(&A, &ctx->rad, L.scratch, L.cam_map, L.slab, s_top, ctx->stream,
+    BL_CUDA_CHECK(bl_launch_radiate_polarized_split(&A, &ctx->rad, L.scratch, L.frame, L.cam_map, L.slab, s_top, ctx->stream,
                                                     ctx->stage_events.data(), &ctx->launches,
                                                     alive.empty() ? nullptr : alive.data(), (int)alive.size()));
     *split_slabs = slabs;
@@ -919,10 +936,10 @@ int radiate_wave(bl_ctx *ctx, Level &L, int64_t first, int64_t count, int s_top,
 
 // After the stream has been synchronised: add the device time of each stage of the last radiate_wave.
 int collect_stage_times(bl_ctx *ctx, Level &L, int slabs) {
-  for (int k = 0; k < 3 * slabs; k++) {
+  for (int k = 0; k < 4 * slabs; k++) {
     float ms = 0.f;
     BL_CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->stage_events[k], ctx->stage_events[k + 1]));
-    L.ms_stage[k % 3] += ms;
+    L.ms_stage[k % 4] += ms;
   }
   return BL_OK;
 }
@@ -932,6 +949,7 @@ int alloc_split_scratch(bl_ctx *ctx, Level &L, int slab) {
   if (slab <= 0) return BL_OK;
   const size_t nf = (size_t)bl_polarized_split_fields(ctx->rad.num_freq);
   BL_CUDA_CHECK(dev_alloc(&L.scratch, (size_t)L.wave_rays * (size_t)slab * nf));
+  BL_CUDA_CHECK(dev_alloc(&L.frame, (size_t)L.wave_rays * (size_t)(slab + 1) * 8));
   BL_CUDA_CHECK(dev_alloc(&L.cam_map, (size_t)L.wave_rays * 10));
   return BL_OK;
 }
@@ -1015,7 +1033,8 @@ int trace_level_impl(bl_ctx *ctx, int level, int64_t num_rays, bl_level_stats *s
     if (!ctx->ray_order || L.order_buckets > bl_ray_order_max_buckets()) L.order_buckets = 0;
     if (L.order_buckets > 0) {
       BL_CUDA_CHECK(dev_alloc(&L.order, (size_t)L.wave_rays));
-      BL_CUDA_CHECK(dev_alloc(&L.order_ws, bl_ray_order_workspace(L.wave_rays, L.order_buckets)));
+      const int ws_buckets = L.order_buckets > kImpactBuckets ? L.order_buckets : kImpactBuckets;
+      BL_CUDA_CHECK(dev_alloc(&L.order_ws, bl_ray_order_workspace(L.wave_rays, ws_buckets)));
     }
   }
   BL_CUDA_CHECK(cudaMemsetAsync(ctx->counters, 0, sizeof(GeoCounters), ctx->stream));
@@ -1264,8 +1283,15 @@ int bl_polarized_stage_ms(bl_ctx *ctx, int level, double *ms3, int32_t *slab) {
   if (!ctx || !ms3) return BL_ERR_ARG;
   if (level < 0 || level >= (int)ctx->levels.size()) return bl_fail(ctx, BL_ERR_ARG, "bl_polarized_stage_ms: level %d out of range", level);
   const Level &L = ctx->levels[level];
-  for (int k = 0; k < 3; k++) ms3[k] = L.ms_stage[k];
+  for (int k = 0; k < 3; k++) ms3[k] = L.ms_stage[k + 1];
   if (slab) *slab = (L.slab > 0 && L.scratch && !L.tap_nan) ? L.slab : 0;
+  return BL_OK;
+}
+
+int bl_polarized_sampling_ms(bl_ctx *ctx, int level, double *ms) {
+  if (!ctx || !ms) return BL_ERR_ARG;
+  if (level < 0 || level >= (int)ctx->levels.size()) return bl_fail(ctx, BL_ERR_ARG, "bl_polarized_sampling_ms: level %d out of range", level);
+  *ms = ctx->levels[level].ms_stage[0];
   return BL_OK;
 }
 
@@ -1330,7 +1356,7 @@ int bl_radiate_level(bl_ctx *ctx, int level, int snapshot, double *image, double
   double ms_geo = 0.0, ms_rad = 0.0;
   float ms = 0.f;
   int split_slabs = 0;
-  L.ms_stage[0] = L.ms_stage[1] = L.ms_stage[2] = 0.0;
+  L.ms_stage[0] = L.ms_stage[1] = L.ms_stage[2] = L.ms_stage[3] = 0.0;
   if (L.resident) {
     BL_CUDA_CHECK(cudaEventRecord(ctx->ev0, ctx->stream));
     int rc = radiate_wave(ctx, L, 0, L.rays, L.stats.geodesic_num_steps, &split_slabs);

@@ -27,7 +27,7 @@ struct GeoCounters {
   unsigned long long bad;
   unsigned long long samples;
   int max_samples;
-  int pad;
+  unsigned int b_max_bits;   // largest impact parameter of the wave's rays (float bits), for the integrator's queue order
 };
 
 struct GeoArgs {
@@ -40,6 +40,7 @@ struct GeoArgs {
   int32_t *sample_num;   // (rays)
   uint8_t *sample_flags; // (rays)
   GeoCounters *counters;
+  const int32_t *order;  // DP: the ray queue hands out order[0], order[1], ... (longest rays first, ray_order.cu); nullptr: 0, 1, ...
 };
 
 // What InitializeCamera leaves (reference camera.cpp:53-380; host build_camera_frame), by value to camera_pixels_kernel.

@@ -118,9 +118,9 @@ __global__ void __launch_bounds__(kBlock, MINB) geodesic_dp_kernel(GeoArgs g) {
       if (!active) {
         unsigned long long idx = base + __popc(idle & ((1u << lane) - 1u));
         if (idx < (unsigned long long)g.rays) {
-          ray.m = (int64_t)idx;
-          const double *cp = g.cam_pos + 4 * idx;
-          const double *cd = g.cam_dir + 4 * idx;
+          ray.m = g.order ? (int64_t)g.order[idx] : (int64_t)idx;
+          const double *cp = g.cam_pos + 4 * ray.m;
+          const double *cd = g.cam_dir + 4 * ray.m;
           for (int c = 0; c < 4; c++) {
             ray.y[c] = cp[c];
             ray.y[4 + c] = cd[c];

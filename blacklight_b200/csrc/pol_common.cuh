@@ -633,7 +633,7 @@ __device__ __forceinline__ void couple(const RadParams &P, const Coefficients &C
     // (1,2), (2,1) -- and eight of mm_4 -- the diagonal, (0,2), (2,0), (1,3), (3,1); the identity mm_1 has the
     // diagonal.  Only those entries are evaluated: three kinds (diagonal, mm_2/mm_3 entry, off-diagonal mm_4
     // entry), each with the terms of polarized.cpp:735-779 that do not vanish identically.
-    const double it = 1.0 / theta, it2 = 2.0 / theta;
+    const double it = 1.0 / theta, it2 = 2.0 * it;   // 2 / theta, bit for bit: doubling is exact
     const double x01_2 = (lambda_2 * al[1] - sg * lambda_1 * rho[1]) * it;
     const double x03_2 = (lambda_2 * al[3] - sg * lambda_1 * rho[3]) * it;
     const double x12_2 = (sg * lambda_1 * al[1] + lambda_2 * rho[1]) * it;

@@ -1,4 +1,4 @@
-// Polarized (Stokes IQUV) transfer as a three-stage pipeline over slabs of the step buffer.
+// Polarized (Stokes IQUV) transfer as a pipeline of four kernels over slabs of the step buffer.
 //
 // The fused kernel of radiate_pol.cu walks a ray with everything in one thread: geometry (Kerr-Schild jet,
 // tetrad, Stokes transport matrix), per-frequency synchrotron coefficients and the Stokes coupling.  Its
@@ -6,11 +6,15 @@
 // dependent FP64 latencies most of the time.  Only the last few dozen operations per sample and frequency
 // are really sequential along the ray (s <- M s; s <- O(coefficients) s + c), so the work is split by what
 // it depends on:
-//   pol_geometry_kernel      one thread per ray, a slab of `slab` consecutive samples: sampling of the grid,
-//                            plasma state, tetrad legs, and the frequency-independent transport matrix M
-//                            from the previous sample (polarized.cpp:136-292, :816-833); the only carried
-//                            state is the previous sample's frame, re-derived from one halo sample at the top
-//                            of the slab.  Writes 18 doubles per sample.
+//   pol_sampling_kernel      one thread per ray, a slab of `slab` consecutive samples: sampling of the grid and
+//                            plasma state; writes the fluid frame (u^mu, the tetrad's "up" vector: 8 doubles)
+//                            and the 7 scalars the coefficient stage needs.  Carried state: the cell hint.
+//   pol_geometry_kernel      one thread per ray over the same slab: metric jet, tetrad legs, and the
+//                            frequency-independent transport matrix M from the previous sample
+//                            (polarized.cpp:136-292, :816-833); the only carried state is the previous sample's
+//                            frame, re-derived from one halo sample at the top of the slab.  Writes 11 doubles.
+//                            (Round 2 started with these two as one kernel: 168 registers, 12 warps per SM, and
+//                            more than half of its time in the sampling code's gathers.)
 //   pol_coefficient_kernel   one thread per (ray, sample): the eight polarized synchrotron coefficients of
 //                            every frequency (simulation_coefficients.cpp:458-698).  No carried state at all,
 //                            so it runs at whatever occupancy its registers allow.  Writes 8 F doubles.
@@ -18,7 +22,7 @@
 //                            sequential over the slab; the Stokes state between slabs lives in the image
 //                            itself.  The last slab applies the half step to the camera and the projection on
 //                            the camera tetrad (:816-939).
-// Slabs run from the far end of the rays (large n) to the camera (n = 0), three launches each, on one stream.
+// Slabs run from the far end of the rays (large n) to the camera (n = 0), four launches each, on one stream.
 // The scratch between the stages is field-major, scratch[(field * slab + j) * rays + i]: every access of a warp
 // is a contiguous 256-byte row.  i is the ray's position in the wave's list of rays sorted by length (ray_order.cu;
 // the ray itself without a list): a slab is launched over the rays still alive in it, a prefix of that list.
@@ -43,20 +47,32 @@ enum : int {
 };
 
 struct SplitArgs {
+  double *frame;       // (8, slab + 1, rays): u^mu and the tetrad's "up" vector of every sample of the slab + its halo
   double *scratch;     // (18 + 8 F, slab, rays)
   double *cam_map;     // (10, rays): the half step to the camera, filled by the slab that holds n = 0
   int32_t slab;        // samples per slab
   int32_t n_lo, n_hi;  // this launch covers samples n_lo <= n < n_hi of every ray
+  int32_t prefetch;    // transfer stage: 1 prefetches the next sample's rows into L2, 2 into L1, 0 not at all (BL_POL_PREFETCH)
 };
 
 __device__ __forceinline__ double *field_ptr(const SplitArgs &X, int64_t rays, int field, int j, int64_t i) {
   return X.scratch + ((size_t)field * X.slab + j) * (size_t)rays + i;
 }
 
-// ---- stage 1: geometry --------------------------------------------------------------------------------------
+__device__ __forceinline__ double *frame_ptr(const SplitArgs &X, int64_t rays, int field, int j, int64_t i) {
+  return X.frame + ((size_t)field * (X.slab + 1) + j) * (size_t)rays + i;
+}
+
+// ---- stage 1a: sampling -------------------------------------------------------------------------------------
+// The plasma at every sample of the slab: grid sampling (cell search from the previous sample's cell, trilinear
+// gather), plasma state, and from it what the later stages need -- the fluid four-velocity and the "up" vector of the
+// tetrad (the magnetic field) for the frame stage, the seven scalars of the coefficient stage.  Half of the old
+// single geometry kernel's time was spent here, waiting on gathers with the 12 warps per SM its transport-matrix
+// arithmetic left; on its own the sampling code needs 88 registers and runs with 20.  When the slab does not start at
+// the ray's far end, the sample before it (the frame stage's halo) is sampled again into the extra slot j = n_hi - n_lo.
 template <int MINB>
 __global__ void __launch_bounds__(kBlock, MINB)
-pol_geometry_kernel(const __grid_constant__ RadArgs A, const __grid_constant__ RadParams P, const SplitArgs X) {
+pol_sampling_kernel(const __grid_constant__ RadArgs A, const __grid_constant__ RadParams P, const SplitArgs X) {
   extern __shared__ double smem_bounds[];
   const GridDev &G = A.grid;
   const double *bounds_s = nullptr;
@@ -82,24 +98,18 @@ pol_geometry_kernel(const __grid_constant__ RadArgs A, const __grid_constant__ R
     const bool halo = X.n_hi < num;                        // the sample before it belongs to the previous slab
     rad::CellCache cache = {0, 0, 0, 0};
     rad::SlowLight slow = {0, {0.0, 0.0, 0.0, 0.0}};
-    KsJet jet_p;
-    double k_p[4] = {0, 0, 0, 0}, e_p[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
-    double dlam_p = 0.0;
-    bool have_prev = false;
-
 #pragma unroll 1
     for (int n = halo ? top + 1 : top; n >= X.n_lo; n--) {
       const bool store = n <= top;
+      const int j = n - X.n_lo;
       const double2 *src = reinterpret_cast<const double2 *>(A.sb.buf + A.sb.at(n, m));
       rad::prefetch_record(A.sb, n, m, A.prefetch);
       double2 r0 = __ldcs(src), r1 = __ldcs(src + 1), r2 = __ldcs(src + 2), r3 = __ldcs(src + 3);
       double t = r0.x, x = r0.y, y = r1.x, z = r1.y;
       double kc[4] = {k_t, r2.x, r2.y, r3.x};
-      double dlam = -r3.y;
       double inv_r;
       double r = rad::ks_radius(P.a, x, y, z, inv_r);
 
-      // ---- sample the plasma (as the fused kernel) ----
       rad::SampleStatus st;
       rad::Prims pr;
       rad::SampleIndex si;
@@ -121,32 +131,13 @@ pol_geometry_kernel(const __grid_constant__ RadArgs A, const __grid_constant__ R
       rad::plasma_state(P, x, y, z, r, inv_r, pr, 2, ps);
       const bool coupled = st != rad::kSampleCut && !ps.value_cut && !ps.b_zero;
 
-      // ---- metric jet, momenta, fluid-frame tetrad ----
-      KsJet jet;
-      ks_jet(P, x, y, z, r, inv_r, jet);
-      double kcon[4], ucov[4];
-      raise(jet, kc, kcon);
-      lower(jet, ps.ucon, ucov);
-      double up[4] = {0.0, 0.0, 0.0, 1.0};
-      if (!ps.b_zero)
-        for (int mu = 0; mu < 4; mu++) up[mu] = ps.bcon[mu];
-      double e1[4], e2[4], f1[4], f2[4];
-      tetrad_legs(jet, ps.ucon, ucov, kcon, kc, up, e1, e2, f1, f2);
-
+      // ---- the fluid frame for the frame stage ----
+      for (int mu = 0; mu < 4; mu++) {
+        __stcs(frame_ptr(X, A.rays, mu, j, i), ps.ucon[mu]);
+        __stcs(frame_ptr(X, A.rays, 4 + mu, j, i), ps.b_zero ? (mu == 3 ? 1.0 : 0.0) : ps.bcon[mu]);
+      }
       if (store) {
         processed++;
-        const int j = n - X.n_lo;
-        // ---- Stokes transport matrix from the previous sample to this one ----
-        StokesMap M;
-        for (int a = 0; a < 3; a++)
-          for (int b = 0; b < 3; b++) M.m[a][b] = 0.0;
-        M.vv = 0.0;
-        if (have_prev) transport_map(jet_p, k_p, e_p, dlam_p, jet, kcon, f1, f2, dlam, M);
-        for (int a = 0; a < 3; a++)
-          for (int b = 0; b < 3; b++) __stcs(field_ptr(X, A.rays, kFieldM + 3 * a + b, j, i), M.m[a][b]);
-        __stcs(field_ptr(X, A.rays, kFieldM + 9, j, i), M.vv);
-        __stcs(field_ptr(X, A.rays, kFieldDlam, j, i), dlam);
-
         // ---- what the coefficient stage needs: frequency scale, pitch angle, field strength, n_e, theta_e ----
         double om = 0.0, sin_theta_b = 0.0, cos_theta_b = 0.0;
         if (coupled) {
@@ -168,45 +159,107 @@ pol_geometry_kernel(const __grid_constant__ RadArgs A, const __grid_constant__ R
           __stcs(field_ptr(X, A.rays, kFieldInvTheta, j, i), ps.inv_theta_e);
         }
       }
-
-      // ---- carry the frame to the next sample ----
-      jet_p = jet;
-      for (int mu = 0; mu < 4; mu++) {
-        k_p[mu] = kcon[mu];
-        e_p[0][mu] = e1[mu];
-        e_p[1][mu] = e2[mu];
-      }
-      dlam_p = dlam;
-      have_prev = true;
-    }
-
-    if (X.n_lo == 0) {
-      // last half step of transport, then projection on the camera tetrad (polarized.cpp:816-833, :875-939)
-      const double *cp = A.cam_pos + 4 * m, *cd = A.cam_dir + 4 * m;
-      KsJet jc;
-      double inv_rc;
-      double rc = rad::ks_radius(P.a, cp[1], cp[2], cp[3], inv_rc);
-      ks_jet(P, cp[1], cp[2], cp[3], rc, inv_rc, jc);
-      double kcov[4] = {cd[0], cd[1], cd[2], cd[3]}, kcon[4];
-      raise(jc, kcov, kcon);
-      const double *uc = P.camera_u_con, *ul = P.camera_u_cov, *vc = P.camera_vert_con_c;
-      double up[4];
-      up[0] = uc[0] * vc[0] - (ul[1] * vc[1] + ul[2] * vc[2] + ul[3] * vc[3]) / ul[0];
-      up[1] = vc[1] + uc[1] * vc[0];
-      up[2] = vc[2] + uc[2] * vc[0];
-      up[3] = vc[3] + uc[3] * vc[0];
-      double e1[4], e2[4], f1[4], f2[4];
-      tetrad_legs(jc, uc, ul, kcon, kcov, up, e1, e2, f1, f2);
-      StokesMap M;
-      transport_map_final(jet_p, k_p, e_p, dlam_p, f1, f2, M);
-      for (int a = 0; a < 3; a++)
-        for (int b = 0; b < 3; b++) X.cam_map[(size_t)(3 * a + b) * A.rays + m] = M.m[a][b];
-      X.cam_map[(size_t)9 * A.rays + m] = M.vv;
     }
   }
   if (A.sample_counter) {
     for (int off = 16; off > 0; off >>= 1) processed += __shfl_down_sync(full, processed, off);
     if ((threadIdx.x & 31) == 0 && processed) atomicAdd(A.sample_counter, processed);
+  }
+}
+
+// ---- stage 1b: frames and the Stokes transport matrix ------------------------------------------------------------
+// Metric jet, photon momentum, fluid-frame tetrad at every sample (from the sampling stage's u^mu and "up"), and the
+// frequency-independent transport matrix M from the previous sample (polarized.cpp:136-292, :816-833).  The carried
+// state is the previous sample's frame, re-derived at a slab's top from the halo sample.
+template <int MINB>
+__global__ void __launch_bounds__(kBlock, MINB)
+pol_geometry_kernel(const __grid_constant__ RadArgs A, const __grid_constant__ RadParams P, const SplitArgs X) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.active) return;
+  const int64_t m = A.order ? (int64_t)A.order[i] : i;
+  const int num = A.sample_num[m];
+  if (num <= X.n_lo) return;
+  const double k_t = A.cam_dir[4 * m];
+  const int top = (X.n_hi < num ? X.n_hi : num) - 1;
+  const bool halo = X.n_hi < num;
+  KsJet jet_p;
+  double k_p[4] = {0, 0, 0, 0}, e_p[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+  double dlam_p = 0.0;
+  bool have_prev = false;
+
+#pragma unroll 1
+  for (int n = halo ? top + 1 : top; n >= X.n_lo; n--) {
+    const bool store = n <= top;
+    const int j = n - X.n_lo;
+    const double2 *src = reinterpret_cast<const double2 *>(A.sb.buf + A.sb.at(n, m));
+    rad::prefetch_record(A.sb, n, m, A.prefetch);
+    double2 r0 = __ldcs(src), r1 = __ldcs(src + 1), r2 = __ldcs(src + 2), r3 = __ldcs(src + 3);
+    double ucon[4], up[4];
+    for (int mu = 0; mu < 4; mu++) {
+      ucon[mu] = __ldcs(frame_ptr(X, A.rays, mu, j, i));
+      up[mu] = __ldcs(frame_ptr(X, A.rays, 4 + mu, j, i));
+    }
+    double x = r0.y, y = r1.x, z = r1.y;
+    double kc[4] = {k_t, r2.x, r2.y, r3.x};
+    double dlam = -r3.y;
+    double inv_r;
+    double r = rad::ks_radius(P.a, x, y, z, inv_r);
+
+    // ---- metric jet, momenta, fluid-frame tetrad ----
+    KsJet jet;
+    ks_jet(P, x, y, z, r, inv_r, jet);
+    double kcon[4], ucov[4];
+    raise(jet, kc, kcon);
+    lower(jet, ucon, ucov);
+    double e1[4], e2[4], f1[4], f2[4];
+    tetrad_legs(jet, ucon, ucov, kcon, kc, up, e1, e2, f1, f2);
+
+    if (store) {
+      // ---- Stokes transport matrix from the previous sample to this one ----
+      StokesMap M;
+      for (int a = 0; a < 3; a++)
+        for (int b = 0; b < 3; b++) M.m[a][b] = 0.0;
+      M.vv = 0.0;
+      if (have_prev) transport_map(jet_p, k_p, e_p, dlam_p, jet, kcon, f1, f2, dlam, M);
+      for (int a = 0; a < 3; a++)
+        for (int b = 0; b < 3; b++) __stcs(field_ptr(X, A.rays, kFieldM + 3 * a + b, j, i), M.m[a][b]);
+      __stcs(field_ptr(X, A.rays, kFieldM + 9, j, i), M.vv);
+      __stcs(field_ptr(X, A.rays, kFieldDlam, j, i), dlam);
+    }
+
+    // ---- carry the frame to the next sample ----
+    jet_p = jet;
+    for (int mu = 0; mu < 4; mu++) {
+      k_p[mu] = kcon[mu];
+      e_p[0][mu] = e1[mu];
+      e_p[1][mu] = e2[mu];
+    }
+    dlam_p = dlam;
+    have_prev = true;
+  }
+
+  if (X.n_lo == 0) {
+    // last half step of transport, then projection on the camera tetrad (polarized.cpp:816-833, :875-939)
+    const double *cp = A.cam_pos + 4 * m, *cd = A.cam_dir + 4 * m;
+    KsJet jc;
+    double inv_rc;
+    double rc = rad::ks_radius(P.a, cp[1], cp[2], cp[3], inv_rc);
+    ks_jet(P, cp[1], cp[2], cp[3], rc, inv_rc, jc);
+    double kcov[4] = {cd[0], cd[1], cd[2], cd[3]}, kcon[4];
+    raise(jc, kcov, kcon);
+    const double *uc = P.camera_u_con, *ul = P.camera_u_cov, *vc = P.camera_vert_con_c;
+    double up[4];
+    up[0] = uc[0] * vc[0] - (ul[1] * vc[1] + ul[2] * vc[2] + ul[3] * vc[3]) / ul[0];
+    up[1] = vc[1] + uc[1] * vc[0];
+    up[2] = vc[2] + uc[2] * vc[0];
+    up[3] = vc[3] + uc[3] * vc[0];
+    double e1[4], e2[4], f1[4], f2[4];
+    tetrad_legs(jc, uc, ul, kcon, kcov, up, e1, e2, f1, f2);
+    StokesMap M;
+    transport_map_final(jet_p, k_p, e_p, dlam_p, f1, f2, M);
+    for (int a = 0; a < 3; a++)
+      for (int b = 0; b < 3; b++) X.cam_map[(size_t)(3 * a + b) * A.rays + m] = M.m[a][b];
+    X.cam_map[(size_t)9 * A.rays + m] = M.vv;
   }
 }
 
@@ -289,6 +342,21 @@ pol_transfer_kernel(const __grid_constant__ RadArgs A, const __grid_constant__ R
     const int j = n - X.n_lo;
     const double *lk = field_ptr(X, A.rays, kFieldM, j, i);
     const double *cf = field_ptr(X, A.rays, kFieldCoef + 8 * l, j, i);
+    if (X.prefetch > 0 && n > X.n_lo) {
+      // the next sample's 11 + 8 rows, on their way from HBM while this sample is coupled (its first use of M and of the
+      // affine step were 18 % of the stage's stall samples, all waiting on these loads)
+      if (X.prefetch == 1) {
+#pragma unroll
+        for (int q = 0; q < 11; q++) asm volatile("prefetch.global.L2 [%0];" ::"l"(lk - A.rays + q * fs));
+#pragma unroll
+        for (int q = 0; q < 8; q++) asm volatile("prefetch.global.L2 [%0];" ::"l"(cf - A.rays + q * fs));
+      } else {
+#pragma unroll
+        for (int q = 0; q < 11; q++) asm volatile("prefetch.global.L1 [%0];" ::"l"(lk - A.rays + q * fs));
+#pragma unroll
+        for (int q = 0; q < 8; q++) asm volatile("prefetch.global.L1 [%0];" ::"l"(cf - A.rays + q * fs));
+      }
+    }
     double mm[10];
 #pragma unroll
     for (int q = 0; q < 10; q++) mm[q] = __ldg(lk + q * fs);
@@ -341,11 +409,11 @@ void launch_transfer(int fw, dim3 grid, cudaStream_t stream, const RadArgs &A, c
 
 // Resident CTAs per SM each stage is register-capped for.  The defaults are the measured best on B200; the
 // environment variables exist for re-tuning (BL_POL_OCC="g,c,t").
-struct Occupancy { int g, c, t; };
+struct Occupancy { int g, c, t, s; };
 Occupancy stage_occupancy() {
   static Occupancy occ = [] {
-    Occupancy o = {3, 0, 5};   // coefficient stage: 0 = by electron distribution
-    if (const char *e = getenv("BL_POL_OCC")) sscanf(e, "%d,%d,%d", &o.g, &o.c, &o.t);
+    Occupancy o = {3, 0, 5, 5};   // coefficient stage: 0 = by electron distribution
+    if (const char *e = getenv("BL_POL_OCC")) sscanf(e, "%d,%d,%d,%d", &o.g, &o.c, &o.t, &o.s);
     return o;
   }();
   return occ;
@@ -357,12 +425,13 @@ extern "C" int bl_polarized_split_fields(int num_freq) { return kFieldCoef + 8 *
 
 // One pass of the three stages over all slabs of a wave: samples [0, s_top) of args->rays rays.  scratch holds
 // bl_polarized_split_fields(F) * slab * rays doubles, cam_map 10 * rays; the wave's image columns must be zero.
-// events (or nullptr): 3 * slabs + 1 events recorded on `stream` around every launch, so that the caller can
-// attribute device time to the three stages after synchronising; *launches is advanced by the kernels launched.
+// frame holds 8 * (slab + 1) * rays doubles.  events (or nullptr): 4 * slabs + 1 events recorded on `stream` around
+// every launch (sampling, geometry, coefficients, transfer), so that the caller can attribute device time to the stages
+// after synchronising; *launches is advanced by the kernels launched.
 extern "C" int bl_polarized_split_slabs(int slab, int s_top) { return s_top <= 0 ? 0 : (s_top + slab - 1) / slab; }
 
 extern "C" cudaError_t bl_launch_radiate_polarized_split(const RadArgs *args, const RadParams *params, double *scratch,
-                                                         double *cam_map, int slab, int s_top, cudaStream_t stream,
+                                                         double *frame, double *cam_map, int slab, int s_top, cudaStream_t stream,
                                                          cudaEvent_t *events, long long *launches,
                                                          const int64_t *alive, int num_alive) {
   RadArgs A = *args;
@@ -380,19 +449,26 @@ extern "C" cudaError_t bl_launch_radiate_polarized_split(const RadArgs *args, co
   if (events) cudaEventRecord(events[ev++], stream);
   for (int n_hi = (s_top + slab - 1) / slab * slab; n_hi > 0; n_hi -= slab) {
     SplitArgs X;
-    X.scratch = scratch; X.cam_map = cam_map; X.slab = slab;
+    X.scratch = scratch; X.frame = frame; X.cam_map = cam_map; X.slab = slab;
+    static const int pol_prefetch = [] { const char *e = getenv("BL_POL_PREFETCH"); return e ? atoi(e) : 1; }();
+    X.prefetch = pol_prefetch;
     X.n_lo = n_hi - slab; X.n_hi = n_hi < s_top ? n_hi : s_top;
     // the rays alive in this slab: with the sorted list a prefix of it (alive[s]: rays longer than s slabs)
     const int slab_index = X.n_lo / slab;
     if (alive && A.order) A.active = slab_index < num_alive ? alive[slab_index] : 0;
     const unsigned ray_blocks = (unsigned)((A.active + kBlock - 1) / kBlock);
     if (ray_blocks == 0) {
-      if (events) { cudaEventRecord(events[ev++], stream); cudaEventRecord(events[ev++], stream); cudaEventRecord(events[ev++], stream); }
+      if (events) for (int q = 0; q < 4; q++) cudaEventRecord(events[ev++], stream);
       continue;
     }
-    if (occ.g == 2) pol_geometry_kernel<2><<<ray_blocks, kBlock, smem, stream>>>(A, P, X);
-    else if (occ.g == 4) pol_geometry_kernel<4><<<ray_blocks, kBlock, smem, stream>>>(A, P, X);
-    else pol_geometry_kernel<3><<<ray_blocks, kBlock, smem, stream>>>(A, P, X);
+    if (occ.s == 4) pol_sampling_kernel<4><<<ray_blocks, kBlock, smem, stream>>>(A, P, X);
+    else if (occ.s == 6) pol_sampling_kernel<6><<<ray_blocks, kBlock, smem, stream>>>(A, P, X);
+    else pol_sampling_kernel<5><<<ray_blocks, kBlock, smem, stream>>>(A, P, X);
+    if (events) cudaEventRecord(events[ev++], stream);
+    if (occ.g == 2) pol_geometry_kernel<2><<<ray_blocks, kBlock, 0, stream>>>(A, P, X);
+    else if (occ.g == 4) pol_geometry_kernel<4><<<ray_blocks, kBlock, 0, stream>>>(A, P, X);
+    else if (occ.g == 5) pol_geometry_kernel<5><<<ray_blocks, kBlock, 0, stream>>>(A, P, X);
+    else pol_geometry_kernel<3><<<ray_blocks, kBlock, 0, stream>>>(A, P, X);
     if (events) cudaEventRecord(events[ev++], stream);
     dim3 cgrid(ray_blocks, (unsigned)(X.n_hi - X.n_lo));
     // the thermal-only coefficient code is light enough for five CTAs per SM (58 -> 51 ms per 1024^2 frame), the
@@ -411,7 +487,7 @@ extern "C" cudaError_t bl_launch_radiate_polarized_split(const RadArgs *args, co
     else if (occ.t == 6) launch_transfer<6>(fw, tgrid, stream, A, P, X);
     else launch_transfer<5>(fw, tgrid, stream, A, P, X);
     if (events) cudaEventRecord(events[ev++], stream);
-    if (launches) *launches += 3;
+    if (launches) *launches += 4;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }

@@ -124,3 +124,59 @@ extern "C" cudaError_t bl_launch_ray_order(const int32_t *num, int64_t rays, int
   order_scatter_kernel<<<chunks, 32, 0, stream>>>(num, rays, unit, buckets, chunks, workspace, order);
   return cudaGetLastError();
 }
+
+// ---- longest rays first for the geodesic integrator -------------------------------------------------------------------
+// The integrator's persistent warps take rays from a queue; what limits a far camera is the serial chain of its
+// longest rays (example_formula: median 115 Dormand-Prince attempts per ray, but the 4 % that plunge towards the horizon
+// take 3000 - 4400), so those should start first and the short ones fill the gaps (longest-processing-time-first).
+// The cost of a ray is not known before it is traced, but it falls monotonically with the impact parameter
+// b = |x cross p| / |p| of its initial condition: measured on both benchmark cameras, attempts per ray drop from
+// > 1000 (formula) / 130 (simulation) inside b = 5 to ~100 / ~45 at the image corners.  Rays are therefore queued in
+// order of increasing b (1024 buckets, stable): a scheduling hint only, results do not depend on it.
+namespace {
+
+__global__ void impact_parameter_kernel(const double *__restrict__ cam_pos, const double *__restrict__ cam_dir, int64_t rays,
+                                        float *__restrict__ b_out, unsigned int *__restrict__ b_max_bits) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float b = 0.0f;
+  if (m < rays) {
+    const double x = cam_pos[4 * m + 1], y = cam_pos[4 * m + 2], z = cam_pos[4 * m + 3];
+    const double px = cam_dir[4 * m + 1], py = cam_dir[4 * m + 2], pz = cam_dir[4 * m + 3];
+    const double cx = y * pz - z * py, cy = z * px - x * pz, cz = x * py - y * px;
+    const double p2 = px * px + py * py + pz * pz;
+    b = p2 > 0.0 ? (float)sqrt((cx * cx + cy * cy + cz * cz) / p2) : 0.0f;
+    if (!(b >= 0.0f) || isinf(b)) b = 0.0f;
+    b_out[m] = b;
+  }
+  // non-negative floats order like their bit patterns
+  unsigned int bits = __float_as_uint(b);
+  for (int off = 16; off > 0; off >>= 1) {
+    unsigned int o = __shfl_xor_sync(0xffffffffu, bits, off);
+    bits = o > bits ? o : bits;
+  }
+  if ((threadIdx.x & 31) == 0 && bits) atomicMax(b_max_bits, bits);
+}
+
+__global__ void impact_key_kernel(int32_t *__restrict__ keys_inout, int64_t rays, const unsigned int *__restrict__ b_max_bits,
+                                  int buckets) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= rays) return;
+  const float b = __int_as_float(keys_inout[m]), b_max = __uint_as_float(*b_max_bits);
+  int q = b_max > 0.0f ? (int)(b / b_max * (float)(buckets - 2)) : 0;
+  q = q < 0 ? 0 : (q > buckets - 2 ? buckets - 2 : q);
+  keys_inout[m] = buckets - 2 - q;   // smallest impact parameter = largest key = first in the list
+}
+
+}  // namespace
+
+// order[i]: rays by increasing impact parameter.  keys: int32 scratch of `rays` entries (the level's sample_num array,
+// which the integrator overwrites afterwards); b_max_bits: one zeroed unsigned int on the device.
+extern "C" cudaError_t bl_launch_impact_order(const double *cam_pos, const double *cam_dir, int64_t rays, int32_t *keys,
+                                              unsigned int *b_max_bits, int buckets, int32_t *workspace, int32_t *order,
+                                              cudaStream_t stream) {
+  if (rays <= 0) return cudaSuccess;
+  const unsigned grid = (unsigned)((rays + 255) / 256);
+  impact_parameter_kernel<<<grid, 256, 0, stream>>>(cam_pos, cam_dir, rays, reinterpret_cast<float *>(keys), b_max_bits);
+  impact_key_kernel<<<grid, 256, 0, stream>>>(keys, rays, b_max_bits, buckets);
+  return bl_launch_ray_order(keys, rays, 1, buckets, workspace, order, stream);
+}

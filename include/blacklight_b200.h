@@ -252,12 +252,14 @@ long long bl_launch_count(const bl_ctx *ctx);
  * bl_radiate_level has returned. */
 int bl_device_image(bl_ctx *ctx, int level, void **image, int64_t *num_rays);
 
-/* Polarized levels without per-sample side outputs are rendered by a three-stage pipeline over slabs of the step
- * buffer (geometry + Stokes transport matrix | synchrotron coefficients | Stokes coupling; csrc/radiate_pol_split.cu)
- * in place of the single fused kernel.  ms3: device time of the three stages during the last bl_radiate_level of the
- * level (CUDA events around every launch); *slab: samples per slab, 0 if the fused kernel ran.  Environment, tuning
- * only: BL_POL_FUSED=1 keeps the fused kernel, BL_POL_SLAB=n fixes the slab length. */
+/* Polarized levels without per-sample side outputs are rendered by a pipeline of four kernels over slabs of the step
+ * buffer (grid sampling + plasma state | metric jet, tetrad, Stokes transport matrix | synchrotron coefficients | Stokes
+ * coupling; csrc/radiate_pol_split.cu) in place of the single fused kernel.  ms3: device time of the last three stages
+ * during the last bl_radiate_level of the level (CUDA events around every launch), bl_polarized_sampling_ms: of the
+ * first; *slab: samples per slab, 0 if the fused kernel ran.  Environment, tuning only: BL_POL_FUSED=1 keeps the fused
+ * kernel, BL_POL_SLAB=n fixes the slab length, BL_RAY_ORDER=0 takes the rays in index order instead of by length. */
 int bl_polarized_stage_ms(bl_ctx *ctx, int level, double *ms3, int32_t *slab);
+int bl_polarized_sampling_ms(bl_ctx *ctx, int level, double *ms);
 /* Parity tap of that pipeline: the scratch of the LAST slab it processed (samples 0 <= n < slab of every ray; with
  * BL_POL_SLAB >= ray_max_steps the whole level), (num_fields, slab, num_rays) f64 -- per sample the 3x3 + 1 entries of
  * the Stokes transport matrix, the affine step, seven plasma scalars and 8 synchrotron coefficients per frequency
