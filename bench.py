@@ -482,6 +482,7 @@ def measure(args, name, resolution, steps, warmup, rank, world, local_rank, main
                 '_stages': {'geometry_ms': ms_acc['stage'][0] / K, 'coefficients_ms': ms_acc['stage'][1] / K,
                             'transfer_ms': ms_acc['stage'][2] / K, 'sampling_ms': ms_acc['stage'][3] / K, 'slab': ms_acc['slab']},
                 '_fp64_peak': fp64_peak, '_clocks': clocks, '_device': info['name'], '_resolution': resolution,
+                '_passes': warmup + e2e_steps + steps,
             }
         ctx.close()
         del full_dev, parts
@@ -553,7 +554,7 @@ def finish(res, world, scaling, executed, hbm_peak, fp64_peak):
     """Turn the raw numbers of measure() into the public dict (kernel list with executed rooflines)."""
     st, ms, stages = res.pop('_st'), res.pop('_ms'), res.pop('_stages')
     name, resolution, polarized = res['workload'], res.pop('_resolution'), res.pop('_polarized')
-    for k in ('_fp64_peak', '_clocks', '_device'):
+    for k in ('_fp64_peak', '_clocks', '_device', '_passes'):
         res.pop(k, None)
     kernels = kernel_rooflines(name, st, stages, ms['geo'], ms['rad'], fp64_peak, hbm_peak, executed, res['frequencies'], polarized)
     res['config'] = {'workload': workload_label(name, resolution, world, scaling), 'frequencies': res['frequencies'],
@@ -630,7 +631,7 @@ def main():
         if rank == 0:
             fp64_peak, clocks, device = res['_fp64_peak'], res['_clocks'], res['_device']
             units = {'workload': name, 'resolution': resolution, 'n_gpus': world, 'stats_rank0': res['_st'],
-                     'passes': args.warmup + 2 * args.steps, 'frequencies': res['frequencies']}
+                     'passes': res['_passes'], 'frequencies': res['frequencies']}
             res = finish(res, world, scaling, executed, hbm_peak, fp64_peak)
             line = dict(common)
             line.update({'value': res.pop('value'), 'unit': res.pop('unit'), 'steps': args.steps, 'ms_per_step': res.pop('ms_per_step'),

@@ -101,7 +101,7 @@ struct bl_ctx {
   std::string error;
   bool taps_enabled = false;
   long long launches = 0;   // kernels of ours launched so far
-  int geo_min_blocks = 3;   // occupancy variant of the DP kernel (BL_GEO_BLOCKS overrides, tuning only)
+  int geo_min_blocks = 0;   // occupancy variant of the DP kernel: 0 = by rays per thread (trace_wave); BL_GEO_BLOCKS overrides
   std::vector<cudaEvent_t> stage_events;   // per-launch events of the three-stage polarized pipeline
   bool have_camera = false; // bl_set_camera was called
   CameraDev camera;         // device-side camera description (camera_kernel.cu)
@@ -832,8 +832,13 @@ int trace_wave(bl_ctx *ctx, Level &L, int64_t first, int64_t count) {
   g.counters = ctx->counters;
   g.order = queue_order ? L.order : nullptr;
   BL_CUDA_CHECK(cudaMemsetAsync(&ctx->counters->next_ray, 0, sizeof(unsigned long long), ctx->stream));
+  // Three CTAs per SM give the best throughput (56 ms against 62 at two, 1024^2 rays of the simulation camera); with
+  // fewer than eight rays per thread the kernel is bound by the serial chain of its longest rays instead, and those run
+  // faster with two (example_formula at 512^2: 113 -> 103 ms)
+  int min_blocks = ctx->geo_min_blocks;
+  if (min_blocks <= 0) min_blocks = count < (int64_t)8 * ctx->sm_count * 3 * 128 ? 2 : 3;
   if (p.ray_integrator == BL_INTEGRATOR_DP)
-    BL_CUDA_CHECK(bl_launch_geodesic_dp(&g, p.ray_flat, ctx->sm_count, ctx->geo_min_blocks, ctx->stream));
+    BL_CUDA_CHECK(bl_launch_geodesic_dp(&g, p.ray_flat, ctx->sm_count, min_blocks, ctx->stream));
   else
     BL_CUDA_CHECK(bl_launch_geodesic_rk(&g, p.ray_flat, p.ray_integrator == BL_INTEGRATOR_RK4 ? 4 : 2, ctx->sm_count, ctx->stream));
   ctx->launches++;

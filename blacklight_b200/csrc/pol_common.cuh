@@ -653,33 +653,25 @@ __device__ __forceinline__ void couple(const RadParams &P, const Coefficients &C
     const double f_1 = 1.0 / (al[0] * al[0] - lambda_1 * lambda_1);
     const double f_2 = 1.0 / (al[0] * al[0] + lambda_2 * lambda_2);
     const double a1f = al[0] * f_1, a2f = al[0] * f_2, l1f = lambda_1 * f_1, l2f = lambda_2 * f_2;
-    // entry with (mm_1 + mm_4) / 2 = p and (mm_1 - mm_4) / 2 = q, mm_2 = mm_3 = 0
-    auto even_entry = [&](double p, double q, double jb, double sb) {
-      double cosh_term = a1f * p, cos_term = a2f * q;
-      double pp = cosh_term + cos_term;
-      if (!thin) return pp * jb;
-      pp -= ex * (cosh_term * csh + cos_term * cs + (-l2f * q) * sn + (l1f * p) * snh);
-      return pp * jb + ex * (p * csh + q * cs) * sb;
-    };
-    // entry with mm_2 = x2, mm_3 = x3, mm_1 = mm_4 = 0
-    auto odd_entry = [&](double x2, double x3, double jb, double sb) {
-      double cosh_term = -l1f * x3, cos_term = -l2f * x2;
-      double pp = cosh_term + cos_term;
-      if (!thin) return pp * jb;
-      pp -= ex * (cosh_term * csh + cos_term * cs + (-a2f * x2) * sn + (-a1f * x3) * snh);
-      return pp * jb + ex * (-x2 * sn - x3 * snh) * sb;
-    };
+    // Every entry of polarized.cpp:735-779 is linear in the entry's matrix elements with coefficients that depend only
+    // on (alpha_I, lambda_1, lambda_2, dl): with mm_1 +- mm_4 = 2p, 2q and mm_2, mm_3 = x2, x3 the source part of an
+    // entry is p Kp + q Kq + x3 L3 + x2 L2 and its propagator part p Gp + q Gq + x2 H2 + x3 H3.  The eight
+    // coefficients are formed once per sample instead of inside each of the fourteen entries (thick steps: ex = 0
+    // leaves the asymptotic values, exactly the reference's branch).
+    const double Kp = a1f - ex * (a1f * csh + l1f * snh), Kq = a2f - ex * (a2f * cs - l2f * sn);
+    const double L3 = ex * (l1f * csh + a1f * snh) - l1f, L2 = ex * (l2f * cs + a2f * sn) - l2f;
+    const double Gp = ex * csh, Gq = ex * cs, H2 = -(ex * sn), H3 = -(ex * snh);
+    const double Ks = 0.5 * (Kp + Kq), Kd = 0.5 * (Kp - Kq), Gs = 0.5 * (Gp + Gq), Gd = 0.5 * (Gp - Gq);
+    // diagonal entries: mm_1 = 1, mm_4 = d_k, i.e. p, q = (1 +- d_k) / 2; off-diagonal mm_4 entries y: p, q = +-y / 2
+    const double o01_j = x01_3 * L3 + x01_2 * L2, o01_s = x01_2 * H2 + x01_3 * H3;
+    const double o03_j = x03_3 * L3 + x03_2 * L2, o03_s = x03_2 * H2 + x03_3 * H3;
+    const double o12_j = x12_3 * L3 + x12_2 * L2, o12_s = x12_2 * H2 + x12_3 * H3;
+    const double y02_j = y02 * Kd, y02_s = y02 * Gd, y13_j = y13 * Kd, y13_s = y13 * Gd;
     // column 2 multiplies j_U = 0: only the propagator part survives there
-    auto even_prop = [&](double p, double q, double sb) { return thin ? ex * (p * csh + q * cs) * sb : 0.0; };
-    auto odd_prop = [&](double x2, double x3, double sb) { return thin ? ex * (-x2 * sn - x3 * snh) * sb : 0.0; };
-    out[0] = even_entry(0.5 * (1.0 + d0), 0.5 * (1.0 - d0), j[0], s[0]) + odd_entry(x01_2, x01_3, j[1], s[1]) +
-             even_prop(0.5 * y02, -0.5 * y02, s[2]) + odd_entry(x03_2, x03_3, j[3], s[3]);
-    out[1] = odd_entry(x01_2, x01_3, j[0], s[0]) + even_entry(0.5 * (1.0 + d1), 0.5 * (1.0 - d1), j[1], s[1]) +
-             odd_prop(x12_2, x12_3, s[2]) + even_entry(0.5 * y13, -0.5 * y13, j[3], s[3]);
-    out[2] = even_entry(-0.5 * y02, 0.5 * y02, j[0], s[0]) + odd_entry(-x12_2, -x12_3, j[1], s[1]) +
-             even_prop(0.5 * (1.0 + d2), 0.5 * (1.0 - d2), s[2]);
-    out[3] = odd_entry(x03_2, x03_3, j[0], s[0]) + even_entry(0.5 * y13, -0.5 * y13, j[1], s[1]) +
-             even_entry(0.5 * (1.0 + d3), 0.5 * (1.0 - d3), j[3], s[3]);
+    out[0] = (Ks + d0 * Kd) * j[0] + (Gs + d0 * Gd) * s[0] + o01_j * j[1] + o01_s * s[1] + y02_s * s[2] + o03_j * j[3] + o03_s * s[3];
+    out[1] = o01_j * j[0] + o01_s * s[0] + (Ks + d1 * Kd) * j[1] + (Gs + d1 * Gd) * s[1] + o12_s * s[2] + y13_j * j[3] + y13_s * s[3];
+    out[2] = -(y02_j * j[0] + y02_s * s[0]) - (o12_j * j[1] + o12_s * s[1]) + (Gs + d2 * Gd) * s[2];
+    out[3] = o03_j * j[0] + o03_s * s[0] + y13_j * j[1] + y13_s * s[1] + (Ks + d3 * Kd) * j[3] + (Gs + d3 * Gd) * s[3];
   }
   admissible(out, true);
   for (int a = 0; a < 4; a++) s[a] = out[a];

@@ -112,8 +112,13 @@ __device__ __forceinline__ void load_cell_past_end(const GridDev &g, size_t slot
 // The radiation kernels walk a ray's records one after the other and the first use of a record sits at the head of the
 // sample's dependency chain (ncu: ~10 % of the unpolarized kernel's stall samples wait on that load).  One instruction, no
 // register: ask L2 for the record `ahead` samples further down the walk.
+// ahead = 1 ... 9: into L2; 10 + k: k samples ahead into L1 (BL_RAD_PREFETCH, tuning).
 __device__ __forceinline__ void prefetch_record(const StepBuffer &sb, int n, int64_t m, int ahead) {
-  if (ahead > 0 && n - ahead >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(sb.buf + sb.at(n - ahead, m)));
+  if (ahead >= 10) {
+    if (n - (ahead - 10) >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(sb.buf + sb.at(n - (ahead - 10), m)));
+  } else if (ahead > 0 && n - ahead >= 0) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(sb.buf + sb.at(n - ahead, m)));
+  }
 }
 
 // Geometric cuts of one sample (simulation_sampling.cpp:237-292, formula_coefficients.cpp:75-119).

@@ -52,7 +52,6 @@ struct SplitArgs {
   double *cam_map;     // (10, rays): the half step to the camera, filled by the slab that holds n = 0
   int32_t slab;        // samples per slab
   int32_t n_lo, n_hi;  // this launch covers samples n_lo <= n < n_hi of every ray
-  int32_t prefetch;    // transfer stage: 1 prefetches the next sample's rows into L2, 2 into L1, 0 not at all (BL_POL_PREFETCH)
 };
 
 __device__ __forceinline__ double *field_ptr(const SplitArgs &X, int64_t rays, int field, int j, int64_t i) {
@@ -342,21 +341,6 @@ pol_transfer_kernel(const __grid_constant__ RadArgs A, const __grid_constant__ R
     const int j = n - X.n_lo;
     const double *lk = field_ptr(X, A.rays, kFieldM, j, i);
     const double *cf = field_ptr(X, A.rays, kFieldCoef + 8 * l, j, i);
-    if (X.prefetch > 0 && n > X.n_lo) {
-      // the next sample's 11 + 8 rows, on their way from HBM while this sample is coupled (its first use of M and of the
-      // affine step were 18 % of the stage's stall samples, all waiting on these loads)
-      if (X.prefetch == 1) {
-#pragma unroll
-        for (int q = 0; q < 11; q++) asm volatile("prefetch.global.L2 [%0];" ::"l"(lk - A.rays + q * fs));
-#pragma unroll
-        for (int q = 0; q < 8; q++) asm volatile("prefetch.global.L2 [%0];" ::"l"(cf - A.rays + q * fs));
-      } else {
-#pragma unroll
-        for (int q = 0; q < 11; q++) asm volatile("prefetch.global.L1 [%0];" ::"l"(lk - A.rays + q * fs));
-#pragma unroll
-        for (int q = 0; q < 8; q++) asm volatile("prefetch.global.L1 [%0];" ::"l"(cf - A.rays + q * fs));
-      }
-    }
     double mm[10];
 #pragma unroll
     for (int q = 0; q < 10; q++) mm[q] = __ldg(lk + q * fs);
@@ -450,8 +434,6 @@ extern "C" cudaError_t bl_launch_radiate_polarized_split(const RadArgs *args, co
   for (int n_hi = (s_top + slab - 1) / slab * slab; n_hi > 0; n_hi -= slab) {
     SplitArgs X;
     X.scratch = scratch; X.frame = frame; X.cam_map = cam_map; X.slab = slab;
-    static const int pol_prefetch = [] { const char *e = getenv("BL_POL_PREFETCH"); return e ? atoi(e) : 1; }();
-    X.prefetch = pol_prefetch;
     X.n_lo = n_hi - slab; X.n_hi = n_hi < s_top ? n_hi : s_top;
     // the rays alive in this slab: with the sorted list a prefix of it (alive[s]: rays longer than s slabs)
     const int slab_index = X.n_lo / slab;
