@@ -29,7 +29,7 @@ else
       -o gpurun_out/${tag}_${name} python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-extras "$@" > gpurun_out/${tag}_${name}.log 2>&1
     tail -1 gpurun_out/${tag}_${name}.log | cut -c1-200
   }
-  full split pol_ 51 3 --workload c4 --resolution 512
+  full split pol_ 96 4 --workload c4 --resolution 512
   full unpol 'geodesic_dp|radiate_unpolarized' 0 2 --workload simulation --resolution 512
   full formula 'geodesic_dp|radiate_unpolarized' 0 2 --workload formula --resolution 384
 fi
