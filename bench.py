@@ -512,8 +512,17 @@ def measure_adaptive(root, levels, steps, warmup, rank, world, local_rank):
         ctx = bl.Context(cfg)
         ctx.upload_grid(case.grid_arrays())
 
+        dev = torch.device('cuda', local_rank)
+        Q = ctx.num_quantities
+
+        def device_image(c, level):   # the level's image where bl_radiate_level left it in HBM
+            if c._rays.get(level, 0) == 0:   # this rank owns no block of the level
+                return torch.empty((Q, 0), dtype=torch.float64, device=dev)
+            ptr, shape = c.device_image(level)
+            return torch.as_tensor(_DeviceArray(ptr, shape), device=dev)
+
         def step():
-            worker = multigpu.adaptive_worker(cfg, ctx, rank, world, levels)
+            worker = multigpu.adaptive_worker(cfg, ctx, rank, world, levels, device_images=device_image)
             if world > 1:
                 return multigpu.run_distributed(worker, rank, world)
             return multigpu.run_local([worker])[0]

@@ -22,6 +22,20 @@ from .sharding import shard_blocks
 last_stage_seconds = {}
 
 
+_pinned_cache = {}
+
+
+def _pinned(key, shape):
+    """Pinned float64 host tensor of the given shape, kept between runs (pinning 200 MB costs more than copying it).
+    The arrays a run returns are views of these buffers: valid until the next run on this process."""
+    import torch
+    t = _pinned_cache.get(key)
+    if t is None or tuple(t.shape) != tuple(shape):
+        t = torch.empty(shape, dtype=torch.float64).pin_memory()
+        _pinned_cache[key] = t
+    return t
+
+
 def _root_blocks(cfg):
     """Level-0 blocks in the reference's index order (block = v * nb + u) and, for each, the raster pixel indices
     of its bs x bs rays in block-major order."""
@@ -34,11 +48,14 @@ def _root_blocks(cfg):
     return locs, pix
 
 
-def adaptive_worker(cfg, ctx, rank, world, max_level, num_render=0):
+def adaptive_worker(cfg, ctx, rank, world, max_level, num_render=0, device_images=None):
     """Generator.  Yields ('allgather', uint8 array) -> list of per-rank arrays, and finally
     ('gather_arrays', arrays, shapes of every rank's arrays) -> per-rank lists of arrays on rank 0 / None elsewhere; returns (via StopIteration.value) on rank 0 a list
     over levels of dict(locs=(B,2) int32, flags=(B,) uint8 or None, image=(Q, B*bs*bs) f64 in the reference's
-    pixel order for that level [level 0: raster], stats=...), None on other ranks."""
+    pixel order for that level [level 0: raster], stats=...), None on other ranks.
+    device_images: callable (ctx, level) -> torch CUDA tensor (Q, rays) viewing the level's image in HBM (bl_device_image).
+    With it nothing but the refinement flags touches the host before the end: every rank's blocks go to rank 0 device to
+    device, are interleaved into the levels' images there, and each level is downloaded once."""
     if not getattr(ctx, 'level0_block_major', False):
         raise ValueError('adaptive_worker: the context must be created from a config with set_level0_block_major(True) '
                          '(the root level is handed over block by block)')
@@ -63,7 +80,11 @@ def adaptive_worker(cfg, ctx, rank, world, max_level, num_render=0):
         # crosses PCIe, and the host camera stage of round 1 is gone
         stats = ctx.trace_level_pixels(level, blocks=locs_all[blocks])
         t2 = clock()
-        image, render, rstats = ctx.radiate_level(level, num_render=num_render)
+        if device_images is None:
+            image, render, rstats = ctx.radiate_level(level, num_render=num_render)
+        else:
+            _, render, rstats = ctx.radiate_level(level, num_render=num_render, download=False)
+            image = device_images(ctx, level)
         t3 = clock()
         T['trace'] += t2 - t1
         T['radiate'] += t3 - t2
@@ -96,7 +117,9 @@ def adaptive_worker(cfg, ctx, rank, world, max_level, num_render=0):
     # ranks can derive (levels x Q x this rank's blocks x bs2) -- no pickling, NCCL point-to-point when distributed
     Q = mine_levels[0]['image'].shape[0]
     shapes = [[(Q, len(shard_blocks(len(L['locs']), r, world)) * bs2) for L in mine_levels] for r in range(world)]
-    gathered = yield ('gather_arrays', [np.ascontiguousarray(L['image'], np.float64) for L in mine_levels], shapes)
+    on_device = device_images is not None
+    gathered = yield ('gather_arrays', [L['image'] if on_device else np.ascontiguousarray(L['image'], np.float64) for L in mine_levels],
+                      shapes)
     T['exchange'] += clock() - t0
     last_stage_seconds.update(T)
     if gathered is None:
@@ -104,17 +127,25 @@ def adaptive_worker(cfg, ctx, rank, world, max_level, num_render=0):
     t0 = clock()
     out = []
     res = cfg.resolution
+    if on_device:
+        import torch
+        dev = mine_levels[0]['image'].device
+        pix_index = torch.from_numpy(np.ascontiguousarray(pix.ravel(), np.int64)).to(dev)
     for lv, L in enumerate(mine_levels):
         n_blocks = len(L['locs'])
-        full = np.empty((Q, n_blocks, bs2))
+        full = torch.empty((Q, n_blocks, bs2), dtype=torch.float64, device=dev) if on_device else np.empty((Q, n_blocks, bs2))
         for r, part in enumerate(gathered):   # shard_blocks deals blocks round-robin: rank r owns blocks r, r + world, ...
             full[:, r::world] = part[lv].reshape(Q, -1, bs2)
         if lv == 0:   # back to the reference's raster order for the root level
-            raster = np.empty((Q, res * res))
-            raster[:, pix.ravel()] = full.reshape(Q, -1)
+            raster = torch.empty((Q, res * res), dtype=torch.float64, device=dev) if on_device else np.empty((Q, res * res))
+            raster[:, pix_index if on_device else pix.ravel()] = full.reshape(Q, -1)
             image = raster
         else:
             image = full.reshape(Q, -1)
+        if on_device:
+            host = _pinned(('level', lv), tuple(image.shape))   # one device-to-host copy per level, into pinned memory
+            host.copy_(image)
+            image = host.numpy()
         out.append(dict(locs=L['locs'], flags=L['flags'], image=image))
     T['assemble'] += clock() - t0
     last_stage_seconds.update(T)
@@ -159,13 +190,15 @@ def run_distributed(worker, rank, world):
             shapes = request[2]
             dev = torch.device('cuda', torch.cuda.current_device()) if dist.get_backend() == 'nccl' else torch.device('cpu')
             count = lambda r: sum(int(np.prod(sh)) for sh in shapes[r])
+            tensors = len(payload) > 0 and torch.is_tensor(payload[0])   # device-resident images: nothing goes through the host
             if rank == 0:
                 starts = np.concatenate([[0], np.cumsum([count(r) for r in range(1, world)])]).astype(np.int64)
                 buf = torch.empty(int(starts[-1]), dtype=torch.float64, device=dev)
-                reqs = [dist.irecv(buf[int(starts[r - 1]):int(starts[r])], src=r) for r in range(1, world) if count(r)]
-                for q in reqs:
-                    q.wait()
-                flat_all = buf.cpu().numpy()          # one device-to-host copy for all ranks
+                ops = [dist.P2POp(dist.irecv, buf[int(starts[r - 1]):int(starts[r])], r) for r in range(1, world) if count(r)]
+                if ops:
+                    for q in dist.batch_isend_irecv(ops):
+                        q.wait()
+                flat_all = buf if tensors else buf.cpu().numpy()          # one device-to-host copy for all ranks
                 reply = [payload]
                 for r in range(1, world):
                     arrays, at = [], int(starts[r - 1])
@@ -176,8 +209,12 @@ def run_distributed(worker, rank, world):
                     reply.append(arrays)
             else:
                 if count(rank):
-                    flat = np.concatenate([np.asarray(a, np.float64).ravel() for a in payload])
-                    dist.send(torch.from_numpy(flat).to(dev), dst=0)
+                    if tensors:
+                        flat = torch.cat([a.reshape(-1) for a in payload])
+                    else:
+                        flat = torch.from_numpy(np.concatenate([np.asarray(a, np.float64).ravel() for a in payload])).to(dev)
+                    for q in dist.batch_isend_irecv([dist.P2POp(dist.isend, flat, 0)]):
+                        q.wait()
                 reply = None
         else:
             parts = [None] * world if rank == 0 else None

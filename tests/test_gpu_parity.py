@@ -513,13 +513,29 @@ def test_adaptive_drop_in(gpu, tmp_path):
         assert v <= PIXEL_TOL, k
 
 
-@pytest.mark.parametrize('world', [1, 3])
+def _device_image_tensor(ctx, level):
+    """torch view of a level's image in HBM (bl_device_image), as bench.py hands it to the sharded adaptive worker."""
+    import torch
+    if ctx._rays.get(level, 0) == 0:
+        return torch.empty((ctx.num_quantities, 0), dtype=torch.float64, device='cuda:0')
+
+    class View:
+        pass
+    ptr, shape = ctx.device_image(level)
+    v = View()
+    v.__cuda_array_interface__ = {'shape': tuple(shape), 'typestr': '<f8', 'data': (int(ptr), False), 'version': 2}
+    return torch.as_tensor(v, device='cuda:0')
+
+
+@pytest.mark.parametrize('world', [1, 3, -3])
 def test_adaptive_sharded_over_ranks(world, gpu, tmp_path):
     """example_adaptive with the blocks of every level (root level included) dealt round-robin over `world` ranks
     (blacklight_b200/multigpu.py; the ranks are stepped in lock step inside this process, each with its own
     context): refinement flags, child block order and per-level images must not depend on the number of ranks
     and must match the reference."""
     from blacklight_b200 import multigpu
+    on_device = world < 0   # -3: three ranks whose images stay in HBM until the assembled levels are downloaded
+    world = abs(world)
     base, over, mock = CASES['adaptive_32']
     gold = dict(np.load(os.path.join(GOLDEN, 'adaptive_32.npz')))
     case = Case(tmp_path, base, over, mock=mock)
@@ -531,7 +547,8 @@ def test_adaptive_sharded_over_ranks(world, gpu, tmp_path):
         ctx = bl.Context(cfg)
         ctx.upload_grid(case.grid_arrays())
         ctxs.append(ctx)
-        workers.append(multigpu.adaptive_worker(cfg, ctx, rank, world, max_level))
+        workers.append(multigpu.adaptive_worker(cfg, ctx, rank, world, max_level,
+                                                device_images=_device_image_tensor if on_device else None))
     levels = multigpu.run_local(workers)[0]
     for ctx in ctxs:
         ctx.close()
