@@ -14,7 +14,7 @@ scale = {'ns': 1.0, 'us': 1e3, 'ms': 1e6, 'nsecond': 1.0, 'usecond': 1e3, 'mseco
 for r in rows:
     if r['Metric Name'] != 'gpu__time_duration.sum':
         continue
-    k = re.sub(r'<.*', '', re.sub(r'void <unnamed>::', '', r['Kernel Name']).split('(')[0])
+    k = re.sub(r'<.*', '', r['Kernel Name'].replace('void ', '').replace('<unnamed>::', '').split('(')[0])
     ns[k] += float(r['Metric Value'].replace(',', '')) * scale.get(r['Metric Unit'], 1.0)
     count[k] += 1
 total = sum(ns.values())
