@@ -354,7 +354,7 @@ class Context:
         return ptr.value, (self.num_quantities, n.value)
 
     def polarized_scratch(self, level=0):
-        """(fields, slab, rays) scratch of the last slab of the three-stage polarized pipeline and the (10, rays) camera
+        """(fields, slab, rays) scratch of the last slab of the polarized pipeline and the (10, rays) camera
         half-step map: bl_download_polarized_scratch."""
         nf, slab, rays = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
         self._check(_lib.bl_download_polarized_scratch(self._h, level, None, None, ctypes.byref(nf), ctypes.byref(slab), ctypes.byref(rays)))

@@ -951,7 +951,7 @@ def test_full_resolution_window_against_reference(root, levels, pol, window, gpu
         full_over = {k: v for k, v in over.items() if not k.startswith('adaptive_')}
         full_over.update({'camera_resolution': fine, 'adaptive_max_level': 0})
         cfg, ctx, image, _, _ = run_gpu_level0(Case(tmp_path / 'gpu', 'adaptive.input', full_over))
-        assert ctx.polarized_stage_ms(0)['slab'] > 0   # the three-stage pipeline rendered it
+        assert ctx.polarized_stage_ms(0)['slab'] > 0   # the slab pipeline rendered it
         cut = lambda plane: np.stack([plane.reshape(fine, fine)[v * bs:(v + 1) * bs, u * bs:(u + 1) * bs] for v, u in locs])
         for l in range(F):
             mine = {name: cut(image[4 * l + s_ind]) for s_ind, name in enumerate(('I_nu', 'Q_nu', 'U_nu', 'V_nu'))}
@@ -1083,7 +1083,7 @@ def _render_polarized(case, env, tile_rays=0):
      'plasma_kappa_frac': '0.25', 'plasma_kappa': '3.7', 'plasma_w': '1.5', 'simulation_a': '0.9'},
 ])
 def test_polarized_pipeline_matches_fused_kernel(over, gpu, tmp_path):
-    """The three-stage polarized pipeline (geometry | coefficients | transfer over slabs, radiate_pol_split.cu) and the
+    """The polarized pipeline (sampling | geometry | coefficients | transfer over slabs, radiate_pol_split.cu) and the
     single fused kernel evaluate the same formulas: the images must agree to rounding, for every slab length (a slab
     boundary re-derives the previous sample's frame from a halo sample) and when the level is traced in waves."""
     case = Case(tmp_path, 'simulation.input', over)
@@ -1343,7 +1343,7 @@ def test_ray_ordering_does_not_change_a_bit(base, over, tile, gpu, tmp_path):
     """The radiation kernels take their rays from the wave's list sorted by length (csrc/ray_order.cu) and the polarized
     pipeline launches each slab over the rays still alive in it, addressing its scratch by list position.  A ray's own
     arithmetic is untouched: every image array must equal, bit for bit, the one rendered in index order (BL_RAY_ORDER=0),
-    for resident levels and waves, the three-stage pipeline (two slab lengths) and the fused kernels."""
+    for resident levels and waves, the slab pipeline (three slab lengths) and the fused kernels."""
     case = Case(tmp_path, base, over)
 
     def render(env):
