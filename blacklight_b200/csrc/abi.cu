@@ -107,6 +107,9 @@ struct bl_ctx {
   CameraDev camera;         // device-side camera description (camera_kernel.cu)
   int32_t *units_dev = nullptr;   // unit list (rows / block locations) of the last bl_trace_level_pixels
   size_t units_cap = 0;           // its capacity in int32
+  int32_t *refine_locs = nullptr; // bl_refine_level: block locations and flags on the device, kept between calls
+  uint8_t *refine_flags = nullptr;
+  size_t refine_cap = 0;          // blocks they hold
   int rad_prefetch = 2;     // BL_RAD_PREFETCH: samples ahead the radiation kernels prefetch step-buffer records into L2 (0 = off)
   int pol_slab = 0;         // BL_POL_SLAB: samples per slab of that pipeline (0 = chosen from the HBM budget)
   int geo_order = 1;        // BL_GEO_ORDER=0: the integrator's queue hands out the rays in index order
@@ -481,7 +484,7 @@ void bl_destroy(bl_ctx *ctx) {
   cudaSetDevice(ctx->device);
   for (auto &L : ctx->levels) free_level(L);
   for (void *p : ctx->grid_allocs) cudaFree(p);
-  cudaFree(ctx->units_dev); cudaFree(ctx->params_dev); cudaFree(ctx->counters); cudaFree(ctx->rad_counter); cudaFree(ctx->slow_counters);
+  cudaFree(ctx->units_dev); cudaFree(ctx->refine_locs); cudaFree(ctx->refine_flags); cudaFree(ctx->params_dev); cudaFree(ctx->counters); cudaFree(ctx->rad_counter); cudaFree(ctx->slow_counters);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   for (cudaEvent_t e : ctx->stage_events) cudaEventDestroy(e);
@@ -1438,10 +1441,15 @@ int bl_refine_level(bl_ctx *ctx, int level, const int32_t *block_locs, int64_t n
   BL_CUDA_CHECK(cudaSetDevice(ctx->device));
   if (n_refined) *n_refined = 0;
   if (num_blocks == 0) return BL_OK;
-  int32_t *locs_dev = nullptr;
-  uint8_t *flags_dev = nullptr;
-  BL_CUDA_CHECK(dev_alloc(&locs_dev, (size_t)num_blocks * 2));
-  BL_CUDA_CHECK(dev_alloc(&flags_dev, (size_t)num_blocks));
+  if ((size_t)num_blocks > ctx->refine_cap) {   // grow-only buffers: no allocation per call
+    cudaFree(ctx->refine_locs); cudaFree(ctx->refine_flags);
+    ctx->refine_locs = nullptr; ctx->refine_flags = nullptr; ctx->refine_cap = 0;
+    BL_CUDA_CHECK(dev_alloc(&ctx->refine_locs, (size_t)num_blocks * 2));
+    BL_CUDA_CHECK(dev_alloc(&ctx->refine_flags, (size_t)num_blocks));
+    ctx->refine_cap = (size_t)num_blocks;
+  }
+  int32_t *locs_dev = ctx->refine_locs;
+  uint8_t *flags_dev = ctx->refine_flags;
   cudaError_t e = cudaMemcpyAsync(locs_dev, block_locs, (size_t)num_blocks * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaEventRecord(ctx->ev0, ctx->stream);
   if (e == cudaSuccess) e = bl_launch_refine(L.image, L.rays, level, locs_dev, num_blocks, ctx->params_dev, flags_dev, ctx->stream);
@@ -1450,7 +1458,6 @@ int bl_refine_level(bl_ctx *ctx, int level, const int32_t *block_locs, int64_t n
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   float ms = 0.f;
   if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
-  cudaFree(locs_dev); cudaFree(flags_dev);
   if (e != cudaSuccess) return bl_fail_cuda(ctx, e, "refine", __FILE__, __LINE__);
   L.stats.ms_refine = ms;
   int64_t cnt = 0;
