@@ -862,7 +862,7 @@ int read_geo_counters(bl_ctx *ctx, Level &L) {
 }
 
 // s_top: upper bound of the sample counts of these rays (the slabs of the polarized pipeline start there).
-// *split_slabs: slabs launched by the three-stage pipeline (0: the fused kernels ran).
+// *split_slabs: slabs launched by the polarized pipeline (0: the fused kernels ran).
 int radiate_wave(bl_ctx *ctx, Level &L, int64_t first, int64_t count, int s_top, int *split_slabs) {
   *split_slabs = 0;
   RadArgs A{};
