@@ -64,7 +64,7 @@ struct Level {
   bool traced = false;
   double *image = nullptr;    // device (Q, rays)
   double *render = nullptr;   // device (R,3,rays)
-  // three-stage polarized pipeline (radiate_pol_split.cu): slab scratch and the camera half-step map of one wave
+  // polarized pipeline (radiate_pol_split.cu): slab scratch and the camera half-step map of one wave
   // rays of one wave sorted by length, longest first (ray_order.cu): the radiation kernels take their rays from it
   int32_t *order = nullptr;        // device (wave_rays)
   int32_t *order_ws = nullptr;     // device workspace of the sort; its tail holds the bucket totals
@@ -102,7 +102,7 @@ struct bl_ctx {
   bool taps_enabled = false;
   long long launches = 0;   // kernels of ours launched so far
   int geo_min_blocks = 0;   // occupancy variant of the DP kernel: 0 = by rays per thread (trace_wave); BL_GEO_BLOCKS overrides
-  std::vector<cudaEvent_t> stage_events;   // per-launch events of the three-stage polarized pipeline
+  std::vector<cudaEvent_t> stage_events;   // per-launch events of the polarized pipeline
   bool have_camera = false; // bl_set_camera was called
   CameraDev camera;         // device-side camera description (camera_kernel.cu)
   int32_t *units_dev = nullptr;   // unit list (rows / block locations) of the last bl_trace_level_pixels
@@ -788,7 +788,7 @@ static int upload_grid_slot(bl_ctx *ctx, const bl_grid_view *gv, int slot) {
 
 namespace {
 
-// The three-stage polarized pipeline (radiate_pol_split.cu) covers the light image and the per-frequency sums
+// The polarized pipeline (radiate_pol_split.cu) covers the light image and the per-frequency sums
 // (tau, lambda, emission); everything that needs per-sample side outputs stays on the fused kernel.
 bool pol_split_eligible(const bl_ctx *ctx) {
   const RadParams &r = ctx->rad;
@@ -1259,7 +1259,7 @@ int bl_download_polarized_scratch(bl_ctx *ctx, int level, double *out, double *c
   if (level < 0 || level >= (int)ctx->levels.size()) return bl_fail(ctx, BL_ERR_ARG, "bl_download_polarized_scratch: level %d out of range", level);
   Level &L = ctx->levels[level];
   if (!L.scratch || L.slab <= 0 || !L.resident)
-    return bl_fail(ctx, BL_ERR_STATE, "bl_download_polarized_scratch: level %d was not rendered by the three-stage pipeline as one wave", level);
+    return bl_fail(ctx, BL_ERR_STATE, "bl_download_polarized_scratch: level %d was not rendered by the slab pipeline as one wave", level);
   const int64_t nf = bl_polarized_split_fields(ctx->rad.num_freq);
   if (num_fields) *num_fields = nf;
   if (slab) *slab = L.slab;

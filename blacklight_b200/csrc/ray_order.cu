@@ -1,6 +1,6 @@
 // Rays of a wave ordered by length for the radiation kernels.
 //
-// The radiation kernels give a thread a ray; a warp runs as long as its longest ray, and the three-stage polarized
+// The radiation kernels give a thread a ray; a warp runs as long as its longest ray, and the polarized
 // pipeline (radiate_pol_split.cu) launches every slab of 64 samples over all rays although beyond the median length
 // most rays have already ended (mock snapshot, 1024^2: 32 % of all samples sit in slabs in which fewer than half of the
 // rays are alive, and such a slab ran at about half the efficiency of a full one).  A stable counting sort of the rays
